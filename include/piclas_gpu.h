@@ -1,0 +1,199 @@
+/* piclas_gpu.h — C ABI of the B200 particle step for PICLas' PIC-Poisson (HDG) solver.
+ *
+ * The reference has no plugin/FFI boundary around its particle path: the "interface" is a set of
+ * argument-less Fortran subroutines working on module-global arrays, called from one time-step routine
+ * (reference src/timedisc/timedisc_TimeStepPoissonByBorisLeapfrog.f90:93-279 and the Leapfrog sibling
+ * src/timedisc/timedisc_TimeStepPoisson.f90:90-284).  This header DEFINES the boundary a Fortran host binds
+ * with ISO_C_BINDING (the in-tree precedent for the style is src/output/output.f90:33-48); the Fortran side
+ * is in piclas_b200/fortran/mod_particle_gpu.f90 and INTEGRATION.md.
+ *
+ * Conventions (so that Fortran arrays can be passed as they are):
+ *   - every pointer is to host memory in Fortran column-major order; the C index order given in the
+ *     comments is the Fortran order reversed, e.g. PartState(1:6,1:n) == double[n][6];
+ *   - element/side/node ids are 1-based exactly as in the Fortran tables, except ElemSideNodeID, which
+ *     the reference itself stores 0-based ("+1 at use", particle_mesh_tools.f90:1885-1895);
+ *   - INTEGER == int32_t, REAL == double, LOGICAL == int32_t (0 = .FALSE.);
+ *   - every function returns 0 on success, nonzero on error (the host then calls Abort(__STAMP__,
+ *     piclas_gpu_last_error()) as the replaced code does, globals/globals.f90:322-397); nothing here
+ *     ever calls exit();
+ *   - the host keeps ownership of everything it passes; the library copies at the call;
+ *   - one MPI rank == one GPU; calls arrive from the rank's main thread; every call is synchronous
+ *     at return.
+ */
+#ifndef PICLAS_GPU_H
+#define PICLAS_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* TrackingMethod, src/piclas.h:357-359 */
+#define PGPU_REFMAPPING    1
+#define PGPU_TRACING       2   /* not supported */
+#define PGPU_TRIATRACKING  3
+
+/* DepositionType as the string->integer map of pic_depo_method.f90:39-44 */
+#define PGPU_DEPO_CVW          0   /* cell_volweight               (not supported) */
+#define PGPU_DEPO_SF           1   /* shape_function                */
+#define PGPU_DEPO_SF_CC        2   /* shape_function_cc             */
+#define PGPU_DEPO_SF_ADAPTIVE  3   /* shape_function_adaptive       */
+#define PGPU_DEPO_CVWM         6   /* cell_volweight_mean           */
+
+/* PP_TimeDiscMethod values of the two time-step routines that own this path */
+#define PGPU_TIMEDISC_LEAPFROG        509  /* timedisc_TimeStepPoisson.f90            */
+#define PGPU_TIMEDISC_BORIS_LEAPFROG  508  /* timedisc_TimeStepPoissonByBorisLeapfrog */
+
+/* PartBound%TargetBoundCond, particle_boundary_condition.f90:167-214 */
+#define PGPU_BC_OPEN        1
+#define PGPU_BC_REFLECTIVE  2   /* not supported yet: the five configs are periodic */
+#define PGPU_BC_PERIODIC    3
+
+/* ---- mesh + basis tables (built once by InitParticleMesh / InitializeDeposition) ----------------------
+ * Arrays are GLOBAL (all nGlobalElems elements, as the reference's MPI-3 shared windows *_Shared,
+ * particle_mesh_vars.f90:109-205) unless marked LOCAL (offsetElem+1 .. offsetElem+nElems). */
+typedef struct pgpu_mesh {
+  int32_t nGlobalElems, nSides, nNonUniqueNodes, nUniqueGlobalNodes;
+  int32_t NGeo;              /* geometry degree; this build requires NGeo == 1                          */
+  int32_t N;                 /* solution degree, uniform: N_DG_Mapping(2,:) all equal (dg_vars.f90:38)   */
+  int32_t offsetElem;        /* first global element of this rank minus 1 (mesh_vars offsetElem)         */
+  int32_t nElems;            /* local element count                                                      */
+  int32_t elemInfoSize;      /* leading dimension of ElemInfo (ELEMINFOSIZE = 8 with MPI, piclas.h:143)  */
+  int32_t sideInfoSize;      /* leading dimension of SideInfo (SIDEINFOSIZE = 8, piclas.h:166)           */
+  const int32_t *ElemInfo;        /* [nGlobalElems][elemInfoSize]; cols piclas.h:149-158, 7 = ELEM_RANK  */
+  const int32_t *SideInfo;        /* [nSides][sideInfoSize]; cols piclas.h:167-175                       */
+  const double  *NodeCoords;      /* [nNonUniqueNodes][3]                                                */
+  const int32_t *NodeInfo;        /* [nNonUniqueNodes] unique node id                                    */
+  const int32_t *ElemNodeID;      /* [nGlobalElems][8]  non-unique node ids in CGNS corner order         */
+  const int32_t *ElemSideNodeID;  /* [nGlobalElems][6][4]  0-based non-unique node ids                   */
+  const int32_t *ConcaveElemSide; /* [nGlobalElems][6]  LOGICAL                                          */
+  const double  *XCL_NGeo;        /* [nGlobalElems][NGeo+1][NGeo+1][NGeo+1][3]                           */
+  const double  *dXCL_NGeo;       /* [nGlobalElems][NGeo+1][NGeo+1][NGeo+1][3][3]  (Fortran (dd,nn,i,j,k)) */
+  const double  *XiCL_NGeo;       /* [NGeo+1]                                                            */
+  const double  *wBaryCL_NGeo;    /* [NGeo+1]                                                            */
+  const double  *ElemBaryNGeo;    /* [nGlobalElems][3]                                                   */
+  const double  *ElemRadius2NGeo; /* [nGlobalElems]                                                      */
+  const double  *XiEtaZetaBasis;  /* [nGlobalElems][6][3]                                                */
+  const double  *slenXiEtaZetaBasis; /* [nGlobalElems][6]                                                */
+  const double  *xGP, *wGP, *wBary;  /* [N+1] N_Inter(N)%xGP / wGP / wBary (interpolation_vars.f90:25-51)*/
+  const double  *Elem_xGP;        /* [nGlobalElems][N+1][N+1][N+1][3]  (k,j,i order)                     */
+  const double  *ElemsJ;          /* [nGlobalElems][N+1][N+1][N+1]                                       */
+  int32_t nBCs;
+  const int32_t *bc_kind;         /* [nBCs] PartBound%TargetBoundCond(PartBound%MapToPartBC(BCID))       */
+  const int32_t *bc_alpha;        /* [nBCs] BoundaryType(BCID,BC_ALPHA): signed periodic-vector id       */
+  int32_t nPeriodicVectors;
+  const double  *PeriodicVectors; /* [nPeriodicVectors][3]  GEO%PeriodicVectors                          */
+  /* cell_volweight_mean (pic_depo_vars.f90:118-154) */
+  const int32_t *Periodic_nNodes;     /* [nUniqueGlobalNodes]                                            */
+  const int32_t *Periodic_offsetNode; /* [nUniqueGlobalNodes]                                            */
+  const int32_t *Periodic_Nodes;      /* [nPeriodicNodesTotal] unique node ids                           */
+  int32_t nPeriodicNodesTotal;
+  const double  *NodeVolume;      /* [nUniqueGlobalNodes]                                                */
+  /* fast-init background mesh FIBGM (particle_mesh_vars.f90:70-73, GEO%FIBGM*) — RefMapping / shape function */
+  double  FIBGMdeltas[3];
+  double  xyzminglob[3], xyzmaxglob[3];   /* GEO%xminglob .. GEO%zmaxglob */
+  int32_t FIBGMmin[3], FIBGMmax[3];       /* GEO%FIBGMimin..kmax */
+  const int32_t *FIBGM_nElems;    /* [kmax-kmin+1][jmax-jmin+1][imax-imin+1]                             */
+  const int32_t *FIBGM_offsetElem;/* same shape                                                          */
+  const int32_t *FIBGM_Element;   /* [nFIBGMElemsTotal] global element ids                               */
+  int32_t nFIBGMElemsTotal;
+  /* RefMapping only */
+  const double  *ElemEpsOneCell;  /* [nGlobalElems]                                                      */
+  const int32_t *ElemToBCSides;   /* [nGlobalElems][2]  (ELEM_NBR_BCSIDES, ELEM_FIRST_BCSIDE)            */
+  const double  *SideBCMetrics;   /* [nBCSidesTotal][7]  REAL-typed (particle_mesh_vars.f90:83-84)       */
+  int32_t nBCSidesTotal;
+  const int32_t *SideType;        /* [nSides] PLANAR_RECT=0 ...                                          */
+  const double  *SideNormVec;     /* [nSides][3]                                                         */
+  const double  *SideDistance;    /* [nSides]                                                            */
+  const double  *BaseVectors0, *BaseVectors1, *BaseVectors2; /* [nSides][3]                              */
+  const double  *BaseVectorsScale;/* [nSides]                                                            */
+  /* shape function */
+  const double  *SFElemr2;        /* [nGlobalElems][2] adaptive radius (r, r^2) or NULL                  */
+} pgpu_mesh_t;
+
+/* ---- already-parsed run-time parameters (parameter.ini keys in the comments) -------------------------- */
+typedef struct pgpu_params {
+  int32_t TrackingMethod;       /* TrackingMethod                                  particle_mesh.f90:62   */
+  int32_t RefMappingGuess;      /* RefMappingGuess (1..4)                          particle_mesh.f90:352  */
+  double  RefMappingEps;        /* RefMappingEps  (default 1e-4)                   particle_mesh.f90:366  */
+  int32_t CartesianPeriodic;    /* CartesianPeriodic (must be 0)                   particle_mesh.f90:97   */
+  int32_t TimeDiscMethod;       /* PGPU_TIMEDISC_*  (compile-time PP_TimeDiscMethod in the reference)    */
+  int32_t DoInterpolation;      /* PIC-DoInterpolation                             pic_interpolation.f90  */
+  int32_t DoDeposition;         /* PIC-DoDeposition                                                      */
+  int32_t DepositionType;       /* PIC-Deposition-Type as PGPU_DEPO_*                                    */
+  double  externalField[6];     /* PIC-externalField                               pic_interpolation.f90:67 */
+  double  c2_inv;               /* 1/c^2 (globals_vars.f90:87-90; variable with READIN_CONSTANTS)        */
+  int32_t nSpecies;
+  const double *ChargeIC;       /* [nSpecies] Part-Species$-ChargeIC                                     */
+  const double *MassIC;         /* [nSpecies] Part-Species$-MassIC                                       */
+  const double *MacroParticleFactor; /* [nSpecies] Part-Species$-MacroParticleFactor                     */
+  /* shape function (pic_depo.f90:55-75, pic_depo_shapefunction_tools.f90:1131-1294) */
+  double  r_sf;                 /* PIC-shapefunction-radius                                              */
+  int32_t alpha_sf;             /* PIC-shapefunction-alpha                                               */
+  int32_t dim_sf;               /* PIC-shapefunction-dimension                                           */
+  int32_t dim_sf_dir;           /* PIC-shapefunction-direction                                           */
+  int32_t sfDepo3D;             /* PIC-shapefunction-3D-deposition                                       */
+  double  w_sf;                 /* normalisation weight computed by InitShapeFunctionDimensionalty       */
+  double  dimFactorSF;
+  /* device layer */
+  int32_t device;               /* CUDA device ordinal                                                   */
+  int32_t myRank, nRanks;       /* rank in MPI_COMM_PICLAS; partition given by ElemInfo(ELEM_RANK,:)     */
+  int64_t maxParticleNumber;    /* PDM%maxParticleNumber (capacity of the device SoA)                    */
+  int32_t carryParticleIDs;     /* 1: carry a 64-bit id per particle through sort/migration (tests)      */
+  int32_t arithmetic;           /* 0: reference operation order everywhere; 1: restructured (<=1e-12)    */
+} pgpu_params_t;
+
+/* after InitParticleMesh + InitializeDeposition (piclaslib.f90:177) */
+int piclas_gpu_init(const pgpu_mesh_t *mesh, const pgpu_params_t *params);
+int piclas_gpu_finalize(void);
+const char *piclas_gpu_last_error(void);
+
+/* host AoS -> device SoA; after ParticleRestart / initial ParticleInserting and after any host-side
+ * insertion.  append=0 replaces the device population, append=1 adds to it.
+ * PartState[n][6], PartSpecies[n] (1-based), GlobalElemID[n] (PEM%GlobalElemID), ParticleInside[n] and
+ * IsNewPart[n] LOGICALs (particle_vars.f90:50-167); PartPosRef[n][3] or NULL; ids[n] or NULL. */
+int piclas_gpu_upload_particles(int64_t n, const double *PartState, const int32_t *PartSpecies,
+                                const int32_t *GlobalElemID, const int32_t *ParticleInside,
+                                const int32_t *IsNewPart, const double *PartPosRef, const int64_t *ids,
+                                int32_t append);
+
+/* replaces CALL Deposition() (pic_depo.f90:944-1018).
+ * PartSource: LOCAL [nElems][N+1][N+1][N+1][4] == PS_N(iElem)%PartSource(1:4,i,j,k) packed by element;
+ * NodeSource: [nUniqueGlobalNodes][4] (cell_volweight_mean only) or NULL.  Either may be NULL. */
+int piclas_gpu_deposit(double *PartSource, double *NodeSource);
+
+/* after CALL HDG(time,iter): E == U_N(iElem)%E(1:3,i,j,k) packed, LOCAL [nElems][N+1][N+1][N+1][3] */
+int piclas_gpu_set_field(const double *E);
+
+/* replaces timedisc_TimeStepPoissonByBorisLeapfrog.f90:109-215: LastPartPos/LastGlobalElemID copy,
+ * InterpolateFieldToParticle, push, PerformTracking, (MPI exchange, see below), UpdateNextFreePosition.
+ * nLost: particles removed by tracking (NbrOfLostParticles). */
+int piclas_gpu_push_track(double dt, int64_t iter, int32_t *nLost);
+
+/* device SoA -> host AoS, compacted 1..n (PDM%ParticleVecLength == n, all ParticleInside);
+ * call before PerformAnalyze / WriteStateToHDF5 / load balance.  Any output pointer may be NULL. */
+int64_t piclas_gpu_num_particles(void);
+int piclas_gpu_download_particles(int64_t nmax, double *PartState, int32_t *PartSpecies,
+                                  int32_t *GlobalElemID, double *PartPosRef, int64_t *ids, int64_t *n_out);
+
+/* ---- particle exchange between ranks (replaces particle_mpi.f90:202-1024, message layout :158-183) ------
+ * After push_track the emigrants of this rank are grouped by destination rank in a device buffer of
+ * PartCommSize doubles per particle.  The transport (NCCL/MPI/P2P) is the caller's; see INTEGRATION.md. */
+int piclas_gpu_exchange_info(int32_t *partCommSize, int64_t *nSendPerRank /*[nRanks]*/, void **devSendBuf);
+int piclas_gpu_exchange_recv_buffer(int64_t nRecvTotal, void **devRecvBuf);
+int piclas_gpu_exchange_finish(int64_t nRecvTotal);
+
+/* ---- cell_volweight_mean node halo (replaces pic_depo_method.f90:565-673) ------------------------------
+ * deposit() leaves the rank-local NodeSource on the device; the caller sums it over ranks in rank
+ * order and hands the result back before PartSource is formed.  Single-rank runs never call these. */
+int piclas_gpu_nodesource_device(void **devNodeSource /* double[nUniqueGlobalNodes][4] */);
+int piclas_gpu_deposit_finish(double *PartSource, double *NodeSource);
+
+/* timing of the last call's kernels (ms, CUDA events on the launch stream) and launch count */
+int piclas_gpu_last_timing(double *ms_kernels, int32_t *nLaunches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,68 @@
+// common.cuh — device-side data layout of the B200 particle step (see DESIGN.md "Data layout in HBM").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/piclas_gpu.h"
+
+#define PGPU_MAX_N 7          // highest supported solution degree (N+1 <= 8)
+#define PGPU_NCORNER 8        // NGeo == 1
+
+// ---- per-element records, built once at init from the host tables ---------------------------------------------
+// Tria record: everything ParticleInsideQuad3D / ThroughSideCheck3DFast / IntersectionWithWall need for one
+// element (reference tables ElemInfo/SideInfo/ElemSideNodeID/NodeCoords/ConcaveElemSide),
+// flattened so that a CTA can stage it with one coalesced copy.  40 doubles = 320 B.
+struct __align__(16) TriaElem {
+  double corner[8][3];     // the element's 8 non-unique nodes in storage (tensor) order: NodeCoords(:,first+1..first+8)
+  int32_t nbElem[6];       // SIDE_NBELEMID of local side 1..6 (global id, 0 = none)
+  int32_t sideID[6];       // global SideInfo index (1-based) of local side 1..6
+  uint8_t sideNode[6][4];  // ElemSideNodeID(1:4,side) - ELEM_FIRSTNODEIND  (0..7)
+  uint8_t bcid[6];         // SIDE_BCID (0 = inner side); nBCs <= 255
+  uint8_t concave;         // bit s-1 = ConcaveElemSide(s)
+  uint8_t pad[1];
+};
+
+// Geometry record for the Newton reference mapping at NGeo == 1: 123 doubles.
+struct __align__(16) GeoElem {
+  double XCL[8][3];        // XCL_NGeo(1:3,i,j,k), node index i+2j+4k
+  double dXCL[8][3][3];    // [node][nn][dd] == dXCL_NGeo(dd,nn,i,j,k)
+  double bary[3];          // ElemBaryNGeo
+  double xez[6][3];        // XiEtaZetaBasis(1:3,1:6)
+  double slen[6];          // slenXiEtaZetaBasis(1:6)
+  double pad;              // keep sizeof a multiple of 16
+};
+
+// small read-only tables in constant memory
+struct ConstTables {
+  double xGP[PGPU_MAX_N + 1], wGP[PGPU_MAX_N + 1], wBary[PGPU_MAX_N + 1];
+  double cvwFac[PGPU_MAX_N + 1];   // CellVolWeight%Fac = (xGP+1)/2
+  double XiCL[2], wBaryCL[2];
+  double externalField[6];
+  double c2_inv;
+  double RefMappingEps;
+  int32_t RefMappingGuess;
+  int32_t TrackingMethod, TimeDiscMethod, DoInterpolation, DepositionType;
+  int32_t nSpecies;
+  double ChargeIC[32], MassIC[32], MPF[32];
+  int32_t nBCs;
+  int32_t bc_kind[256], bc_alpha[256];
+  int32_t nPeriodicVectors;
+  double PeriodicVectors[8][3];
+  int32_t nGlobalElems, nElems, offsetElem, N, nRanks, myRank;
+};
+
+// particle SoA (one of two buffers)
+struct PartBuf {
+  double *x[3];
+  double *v[3];
+  double *xi[3];      // cached reference position of the current (x, elem); valid iff Ctx::xiValid
+  int32_t *elem;      // PEM%GlobalElemID (1-based global), 0 = removed
+  uint8_t *meta;      // bits 0-5 species-1, bit 6 = xi mapping failed (SucRefPos = F), bit 7 = PDM%IsNewPart
+  int64_t *id;        // optional
+};
+
+#define META_SPEC_MASK 0x3F
+#define META_XIFAIL 0x40
+#define META_ISNEW 0x80
+
+#define KEY_DEAD 0xFFFFFFFFu

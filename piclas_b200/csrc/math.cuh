@@ -1,0 +1,563 @@
+// math.cuh — per-particle device functions of the particle step, sm_100a.
+//
+// Arithmetic contract (DESIGN.md "Arithmetic"): the translation unit is compiled with --fmad=false, so the
+// compiler never fuses; every expression below is written in the reference's evaluation order, and the only
+// fused operations are the explicit fma() calls in the three tensor-product accumulations (field evaluation,
+// Newton residual, Newton Jacobian) — the places where gfortran -O3 -march=native contracts in the reference
+// build (cmake/SetCompiler.cmake:138,149).  Element ownership is decided exclusively by unfused arithmetic.
+#pragma once
+#include "common.cuh"
+
+__constant__ ConstTables cst;
+
+#define EPSMACH 2.220446049250313e-16   /* EPSILON(0.) with REAL == 64 bit, globals_vars.f90:50 */
+#define HUGE_D 1.7976931348623157e308
+
+// ---- basis.f90:1011-1035 ALMOSTEQUAL_UNITY, :1223-1264 LagrangeInterpolationPolys ----------------------------------
+__device__ __forceinline__ bool almost_equal_unity(double x, double y) {
+  const double d = fabs(x - y);
+  if (x == 0. || y == 0.) return d <= 2. * EPSMACH;
+  return (d <= EPSMACH * fabs(x)) && (d <= EPSMACH * fabs(y));
+}
+
+template <int NP>  // NP = N_in + 1 nodes
+__device__ __forceinline__ void lagrange_polys(double x, const double* __restrict__ xGP, const double* __restrict__ wBary,
+                                               double* L) {
+  bool hit = false;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const bool e = almost_equal_unity(x, xGP[i]);
+    L[i] = e ? 1. : 0.;
+    hit |= e;
+  }
+  if (hit) return;
+  double s = 0.;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    L[i] = wBary[i] / (x - xGP[i]);
+    s = s + L[i];
+  }
+#pragma unroll
+  for (int i = 0; i < NP; ++i) L[i] = L[i] / s;
+}
+
+// ---- eval_xyz.f90:448-495 getDet / getInv ----------------------------------------------------------------------------
+__device__ __forceinline__ double get_det(const double M[3][3]) {
+  return (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * M[2][2] + (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * M[2][0] +
+         (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * M[2][1];
+}
+__device__ __forceinline__ void get_inv(const double M[3][3], double sdet, double R[3][3]) {
+  R[0][0] = (M[1][1] * M[2][2] - M[1][2] * M[2][1]) * sdet;
+  R[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) * sdet;
+  R[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * sdet;
+  R[1][0] = (M[1][2] * M[2][0] - M[1][0] * M[2][2]) * sdet;
+  R[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) * sdet;
+  R[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * sdet;
+  R[2][0] = (M[1][0] * M[2][1] - M[1][1] * M[2][0]) * sdet;
+  R[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) * sdet;
+  R[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * sdet;
+}
+
+// ---- eval_xyz.f90:498-612 GetRefNewtonStartValue (guesses 1, 3, 4; guess 2 needs Elem_xGP and is mapped by the host
+// layer to an error at init) -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void newton_start_value(const GeoElem* __restrict__ g, const double x[3], double xi[3]) {
+  const int guess = cst.RefMappingGuess;
+  if (guess == 1) {
+    const double epsOne = 1.0 + cst.RefMappingEps;
+    const double P0 = x[0] - g->bary[0], P1 = x[1] - g->bary[1], P2 = x[2] - g->bary[2];
+    double lin[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) lin[d] = ((P0 * g->xez[d][0] + P1 * g->xez[d][1]) + P2 * g->xez[d][2]) * g->slen[d];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xi[d] = 0.5 * (lin[d] - lin[d + 3]);
+    const double mx = fmax(fabs(xi[0]), fmax(fabs(xi[1]), fabs(xi[2])));
+    if (mx > epsOne) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xi[d] = fmax(fmin(1.0, xi[d]), -1.0);
+    }
+  } else if (guess == 3) {
+    double d0 = x[0] - g->XCL[0][0], d1 = x[1] - g->XCL[0][1], d2 = x[2] - g->XCL[0][2];
+    double win = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+    xi[0] = xi[1] = xi[2] = cst.XiCL[0];
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j)
+        for (int k = 0; k < 2; ++k) {
+          const double* p = g->XCL[i + 2 * j + 4 * k];
+          const double dX = fabs(x[0] - p[0]);
+          if (dX > win) continue;
+          const double dY = fabs(x[1] - p[1]);
+          if (dY > win) continue;
+          const double dZ = fabs(x[2] - p[2]);
+          if (dZ > win) continue;
+          const double dist = sqrt((dX * dX + dY * dY) + dZ * dZ);
+          if (dist < win) {
+            win = dist;
+            xi[0] = cst.XiCL[i];
+            xi[1] = cst.XiCL[j];
+            xi[2] = cst.XiCL[k];
+          }
+        }
+  } else {
+    xi[0] = xi[1] = xi[2] = 0.;
+  }
+}
+
+// ---- eval_xyz.f90:298-445 RefElemNewton at NGeo == 1 ----------------------------------------------------------------------
+// returns: bit0 = isSuccessful (always 1 when !hasSuccess), bit1 = abort requested (Mode 1 without isSuccessful)
+__device__ __forceinline__ int ref_elem_newton(const GeoElem* __restrict__ g, const double x_in[3], double xi[3], int mode,
+                                               bool hasSuccess) {
+  double Lag[3][2];
+  double F[3];
+  int result = 1;
+  lagrange_polys<2>(xi[0], cst.XiCL, cst.wBaryCL, Lag[0]);
+  lagrange_polys<2>(xi[1], cst.XiCL, cst.wBaryCL, Lag[1]);
+  lagrange_polys<2>(xi[2], cst.XiCL, cst.wBaryCL, Lag[2]);
+  F[0] = -x_in[0];
+  F[1] = -x_in[1];
+  F[2] = -x_in[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const double buff = Lag[1][j] * Lag[2][k];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const double* p = g->XCL[i + 2 * j + 4 * k];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) F[d] = fma(p[d] * Lag[0][i], buff, F[d]);  // F+XCL*Lag(1,i)*buff, :343-349
+      }
+    }
+  double deltaXi2 = (fabs(F[0]) < EPSMACH && fabs(F[1]) < EPSMACH && fabs(F[2]) < EPSMACH) ? 0. : 1.;
+  double Norm_F = (F[0] * F[0] + F[1] * F[1]) + F[2] * F[2];
+  double Norm_F_old;
+  int it = 0;
+  const double eps = cst.RefMappingEps;
+  while (deltaXi2 > eps && it < 100) {
+    ++it;
+    double Jac[3][3], sJac[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Jac[r][c] = 0.;
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double buff = Lag[1][j] * Lag[2][k];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const double buff2 = Lag[0][i] * buff;
+          const double(*dx)[3] = g->dXCL[i + 2 * j + 4 * k];  // [nn][dd]
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Jac[r][c] = fma(dx[r][c], buff2, Jac[r][c]);  // Jac(r,c)+=dXCL(c,r,..)*buff2
+        }
+      }
+    double sdet = get_det(Jac);
+    if (sdet > 0.) sdet = 1. / sdet;
+    get_inv(Jac, sdet, sJac);
+    double dXi[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) dXi[r] = (sJac[r][0] * F[0] + sJac[r][1] * F[1]) + sJac[r][2] * F[2];
+    deltaXi2 = (dXi[0] * dXi[0] + dXi[1] * dXi[1]) + dXi[2] * dXi[2];
+    const double xo0 = xi[0], xo1 = xi[1], xo2 = xi[2];
+    Norm_F_old = Norm_F;
+    Norm_F = Norm_F * 2.;
+    double lambda = 1.0;
+    int iArmijo = 1;
+    while (Norm_F > Norm_F_old * (1. - 0.0001 * lambda) && iArmijo <= 8) {
+      xi[0] = xo0 - lambda * dXi[0];
+      xi[1] = xo1 - lambda * dXi[1];
+      xi[2] = xo2 - lambda * dXi[2];
+      lagrange_polys<2>(xi[0], cst.XiCL, cst.wBaryCL, Lag[0]);
+      lagrange_polys<2>(xi[1], cst.XiCL, cst.wBaryCL, Lag[1]);
+      lagrange_polys<2>(xi[2], cst.XiCL, cst.wBaryCL, Lag[2]);
+      F[0] = -x_in[0];
+      F[1] = -x_in[1];
+      F[2] = -x_in[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double buff = Lag[1][j] * Lag[2][k];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const double buff2 = Lag[0][i] * buff;
+            const double* p = g->XCL[i + 2 * j + 4 * k];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) F[d] = fma(p[d], buff2, F[d]);  // F+XCL*buff2, :404-413
+          }
+        }
+      lambda = 0.2 * lambda;
+      ++iArmijo;
+      Norm_F = (F[0] * F[0] + F[1] * F[1]) + F[2] * F[2];
+    }
+    if (fabs(xi[0]) > 1.5 || fabs(xi[1]) > 1.5 || fabs(xi[2]) > 1.5) {
+      if (hasSuccess) {
+        result = 0;
+        break;
+      } else if (mode == 1) {
+        result = 1 | 2;
+        break;
+      } else
+        break;
+    }
+  }
+  return result;
+}
+
+// eval_xyz.f90:35-123 GetPositionInRefElem without DoReUseMap
+__device__ __forceinline__ int position_in_ref_elem(const GeoElem* __restrict__ g, const double x[3], double xi[3], bool forceMode,
+                                                    bool hasSuccess) {
+  newton_start_value(g, x, xi);
+  return ref_elem_newton(g, x, xi, forceMode ? 1 : 2, hasSuccess);
+}
+
+// ---- eval_xyz.f90:167-295 EvaluateFieldAtRefPos (E only; PP_nVar == 1) -----------------------------------------------------
+// U: the element's field tile [(k*NP+j)*NP+i][3]
+template <int NP>
+__device__ __forceinline__ void evaluate_field(const double xi[3], const double* __restrict__ U, double out[3]) {
+  double L0[NP], L1[NP], L2[NP];
+  lagrange_polys<NP>(xi[0], cst.xGP, cst.wBary, L0);
+  lagrange_polys<NP>(xi[1], cst.xGP, cst.wBary, L1);
+  lagrange_polys<NP>(xi[2], cst.xGP, cst.wBary, L2);
+  double o0 = 0., o1 = 0., o2 = 0.;
+#pragma unroll
+  for (int k = 0; k < NP; ++k)
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const double lez = L1[j] * L2[k];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        const double* u = U + ((k * NP + j) * NP + i) * 3;
+        o0 = fma(u[0] * L0[i], lez, o0);  // U_OUT + U_IN*L_xi(1,i)*L_Eta_Zeta, :207-215
+        o1 = fma(u[1] * L0[i], lez, o1);
+        o2 = fma(u[2] * L0[i], lez, o2);
+      }
+    }
+  out[0] = o0;
+  out[1] = o1;
+  out[2] = o2;
+}
+
+// pic_interpolation_tools.f90:458-572 GetEMFieldDW: inverse-distance weighting over the element's Gauss points
+// (only reached when the Newton mapping failed and the deposition is cell_volweight_mean)
+template <int NP>
+__device__ __noinline__ void field_inverse_distance(const double pos[3], const double* __restrict__ U,
+                                                    const double* __restrict__ xgp /* Elem_xGP tile [(k*NP+j)*NP+i][3] */,
+                                                    double out[3]) {
+  // two passes instead of a temporary array; weights are recomputed bit-identically
+  int hk = -1, hl = -1, hm = -1;  // last exact hit (norm == 0)
+  double DistSum = 0.0;
+  for (int k = 0; k < NP; ++k)
+    for (int l = 0; l < NP; ++l)
+      for (int m = 0; m < NP; ++m) {
+        const double* gp = xgp + ((m * NP + l) * NP + k) * 3;
+        const double d0 = gp[0] - pos[0], d1 = gp[1] - pos[1], d2 = gp[2] - pos[2];
+        const double norm = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+        if (norm > 0.) {
+          DistSum = DistSum + 1. / norm;
+        } else {
+          hk = k; hl = l; hm = m;
+          DistSum = 1.;
+          break;  // EXIT leaves the m loop only (:548)
+        }
+      }
+  double o0 = 0., o1 = 0., o2 = 0.;
+  for (int k = 0; k < NP; ++k)
+    for (int l = 0; l < NP; ++l)
+      for (int m = 0; m < NP; ++m) {
+        // weight of (k,l,m) as left in PartDistDepo by the first loop
+        double w;
+        const int lin = (k * NP + l) * NP + m, hlin = (hk * NP + hl) * NP + hm;
+        if (hk >= 0 && lin < hlin) w = 0.;                       // zeroed by PartDistDepo(:,:,:) = 0
+        else if (hk >= 0 && lin == hlin) w = 1.;
+        else if (hk >= 0 && k == hk && l == hl && m > hm) w = 0.;  // skipped by the EXIT, still zero
+        else {
+          const double* gp = xgp + ((m * NP + l) * NP + k) * 3;
+          const double d0 = gp[0] - pos[0], d1 = gp[1] - pos[1], d2 = gp[2] - pos[2];
+          const double norm = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+          w = (norm > 0.) ? 1. / norm : 1.;
+        }
+        const double* u = U + ((m * NP + l) * NP + k) * 3;
+        const double ww = w / DistSum;
+        o0 = o0 + ww * u[0];
+        o1 = o1 + ww * u[1];
+        o2 = o2 + ww * u[2];
+      }
+  out[0] = o0; out[1] = o1; out[2] = o2;
+}
+
+// ---- particle push: timedisc_TimeStepPoissonByBorisLeapfrog.f90:128-198 (508), timedisc_TimeStepPoisson.f90:111-181 (509)
+__device__ __forceinline__ void push_particle(double x[3], double v[3], const double F[6], int spec0, bool& isNew, double dt) {
+  const double q = cst.ChargeIC[spec0], mass = cst.MassIC[spec0];
+  const bool isPush = fabs(q) > 0.0;
+  const double c2_inv = cst.c2_inv;
+  if (cst.TimeDiscMethod == PGPU_TIMEDISC_BORIS_LEAPFROG) {
+    if (isNew) {
+      if (isPush && cst.DoInterpolation) {
+        const double qmt = q / mass;  // PartRHS_NR, particle_rhs.f90:206-228
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[d] = v[d] - ((F[d] * qmt) * dt) * 0.5;
+      }
+      isNew = false;
+    }
+    if (isPush && cst.DoInterpolation) {
+      const double c_1 = (q * dt) / (mass * 2.);
+      const double gamma = 1. / sqrt(1 - (((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]) * c2_inv));
+      double vm[3], t[3], vp[3], vn[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) vm[d] = v[d] * gamma + c_1 * F[d];
+      const double gamma_minus = sqrt(1 + ((vm[0] * vm[0] + vm[1] * vm[1]) + vm[2] * vm[2]) * c2_inv);
+      const double Bn = sqrt((F[3] * F[3] + F[4] * F[4]) + F[5] * F[5]);  // VECNORM3D
+      double u[3] = {0., 0., 0.};
+      if (fabs(Bn) > 0.0) {  // UNITVECTOR
+        const double invL = 1. / Bn;
+        u[0] = F[3] * invL; u[1] = F[4] * invL; u[2] = F[5] * invL;
+      }
+      const double tn = tan(c_1 / gamma_minus * Bn);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) t[d] = tn * u[d];
+      vp[0] = vm[0] + (vm[1] * t[2] - vm[2] * t[1]);
+      vp[1] = vm[1] + (vm[2] * t[0] - vm[0] * t[2]);
+      vp[2] = vm[2] + (vm[0] * t[1] - vm[1] * t[0]);
+      const double fac = 2.0 / (1. + ((t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]));
+      vn[0] = (vm[0] + fac * (vp[1] * t[2] - vp[2] * t[1])) + c_1 * F[0];
+      vn[1] = (vm[1] + fac * (vp[2] * t[0] - vp[0] * t[2])) + c_1 * F[1];
+      vn[2] = (vm[2] + fac * (vp[0] * t[1] - vp[1] * t[0])) + c_1 * F[2];
+      const double s = sqrt(1 + ((vn[0] * vn[0] + vn[1] * vn[1]) + vn[2] * vn[2]) * c2_inv);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[d] = vn[d] / s;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = x[d] + v[d] * dt;
+  } else {
+    double Pt[3] = {0., 0., 0.};
+    if (cst.DoInterpolation && isPush) {
+      const double qmt = q / mass;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Pt[d] = F[d] * qmt;
+    }
+    if (isNew) {
+      if (isPush) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[d] = v[d] - (Pt[d] * dt) * 0.5;
+      }
+      isNew = false;
+    }
+    if (isPush) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[d] = v[d] + Pt[d] * dt;
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x[d] = x[d] + v[d] * dt;
+  }
+}
+
+// ---- particle_mesh_tools.f90:78-222 ParticleInsideQuad3D (regular sides) --------------------------------------------------------
+// det[s][t]: determinant of triangle t of local side s+1.  Returns InElementCheck.
+__device__ __forceinline__ bool inside_quad3d(const TriaElem* __restrict__ te, const double x[3], double det[6][2]) {
+  bool inElem = true;
+  const unsigned conc = te->concave;
+#pragma unroll
+  for (int s = 0; s < 6; ++s) {
+    double A[4][3];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const double* c = te->corner[te->sideNode[s][n]];
+      A[n][0] = c[0] - x[0];
+      A[n][1] = c[1] - x[1];
+      A[n][2] = c[2] - x[2];
+    }
+    const double c0 = A[0][1] * A[2][2] - A[0][2] * A[2][1];
+    const double c1 = A[0][2] * A[2][0] - A[0][0] * A[2][2];
+    const double c2 = A[0][0] * A[2][1] - A[0][1] * A[2][0];
+    double d1 = (c0 * A[1][0] + c1 * A[1][1]) + c2 * A[1][2];
+    d1 = -d1;
+    const double d2 = (c0 * A[3][0] + c1 * A[3][1]) + c2 * A[3][2];
+    det[s][0] = d1;
+    det[s][1] = d2;
+    const bool neg = (d1 < 0) || (d2 < 0);
+    const bool pos = !(d1 < 0) || !(d2 < 0);
+    if ((conc >> s) & 1u) {
+      if (!pos) inElem = false;
+    } else {
+      if (neg) inElem = false;
+    }
+  }
+  return inElem;
+}
+
+// ---- particle_intersection.f90:167-280 ParticleThroughSideCheck3DFast (regular side) -------------------------------------------
+__device__ __forceinline__ bool through_side_check_fast(const TriaElem* __restrict__ te, const double lp[3], const double V[3],
+                                                        int s /*0-based local side*/, int tri /*1|2*/) {
+  double Ax[3], Ay[3], Az[3];
+  {
+    const double* c = te->corner[te->sideNode[s][0]];
+    Ax[0] = c[0] - lp[0]; Ay[0] = c[1] - lp[1]; Az[0] = c[2] - lp[2];
+  }
+#pragma unroll
+  for (int n = 1; n < 3; ++n) {
+    const double* c = te->corner[te->sideNode[s][n + tri - 1]];
+    Ax[n] = c[0] - lp[0]; Ay[n] = c[1] - lp[1]; Az[n] = c[2] - lp[2];
+  }
+  const double Vx = V[0], Vy = V[1], Vz = V[2];
+  bool through = true;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int o = (r + 2) % 3;  // rows use A(3), A(1), A(2) as third factor
+    const double a = (Ay[r] * Vz - Az[r] * Vy) * Ax[o];
+    const double b = (Az[r] * Vx - Ax[r] * Vz) * Ay[o];
+    const double c = (Ax[r] * Vy - Ay[r] * Vx) * Az[o];
+    const double det = (a + b) + c;
+    double mn = HUGE_D;
+    const double fa = fabs(a), fb = fabs(b), fc = fabs(c);
+    if (fa > 0.0 && fa < mn) mn = fa;
+    if (fb > 0.0 && fb < mn) mn = fb;
+    if (fc > 0.0 && fc < mn) mn = fc;
+    const double minComp = -EPSMACH * mn;
+    if (!(det >= minComp)) through = false;
+  }
+  return through;
+}
+
+// ---- particle_intersection.f90:430-512 ParticleThroughSideLastPosCheck (regular side) -------------------------------------------
+__device__ __forceinline__ bool through_side_lastpos_check(const TriaElem* __restrict__ te, const double lp[3], int s, int tri,
+                                                           double& det) {
+  double Ax[3], Ay[3], Az[3];
+#pragma unroll
+  for (int n = 0; n < 3; ++n) {
+    const int node = (n == 0) ? 0 : n + tri - 1;
+    const double* c = te->corner[te->sideNode[s][node]];
+    Ax[n] = c[0] - lp[0]; Ay[n] = c[1] - lp[1]; Az[n] = c[2] - lp[2];
+  }
+  det = ((Ay[0] * Az[1] - Az[0] * Ay[1]) * Ax[2] + (Az[0] * Ax[1] - Ax[0] * Az[1]) * Ay[2]) +
+        (Ax[0] * Ay[1] - Ay[0] * Ax[1]) * Az[2];
+  return !((det < 0) || (det != det));
+}
+
+// ---- particle_intersection.f90:79-164 IntersectionWithWall: returns TrackInfo%alpha ------------------------------------------------
+__device__ __forceinline__ double intersection_with_wall(const TriaElem* __restrict__ te, const double lp[3], const double V[3],
+                                                         int s, int tri) {
+  const double* n0 = te->corner[te->sideNode[s][0]];
+  const double* n1 = te->corner[te->sideNode[s][tri]];
+  const double* n2 = te->corner[te->sideNode[s][tri + 1]];
+  const double xN = n0[0], yN = n0[1], zN = n0[2];
+  const double v1x = n1[0] - xN, v1y = n1[1] - yN, v1z = n1[2] - zN;
+  const double v2x = n2[0] - xN, v2y = n2[1] - yN, v2z = n2[2] - zN;
+  double nx = v1y * v2z - v1z * v2y;
+  double ny = v1z * v2x - v1x * v2z;
+  double nz = v1x * v2y - v1y * v2x;
+  const double nVal = sqrt((nx * nx + ny * ny) + nz * nz);
+  nx = nx / nVal; ny = ny / nVal; nz = nz / nVal;
+  const double bx = lp[0] - xN, by = lp[1] - yN, bz = lp[2] - zN;
+  const double bn = (bx * nx + by * ny) + bz * nz;
+  const double ax = bx - nx * bn, ay = by - ny * bn, az = bz - nz * bn;
+  const double t0 = ay * bz - az * by, t1 = az * bx - ax * bz, t2 = ax * by - ay * bx;
+  double dist = sqrt(((t0 * t0 + t1 * t1) + t2 * t2) / ((ax * ax + ay * ay) + az * az));
+  if (dist != dist) dist = sqrt((bx * bx + by * by) + bz * bz);
+  double alpha = (V[0] * nx + V[1] * ny) + V[2] * nz;
+  if (fabs(alpha) > 0.) alpha = dist / alpha;
+  return alpha;
+}
+
+enum { TRK_OK = 0, TRK_LOST = 1, TRK_REMOVED = 2, TRK_ERR_BC = 3, TRK_ERR_ELEM = 4, TRK_ERR_LOOP = 5 };
+
+// ---- particle_triatracking.f90:137-484 SingleParticleTriaTracking3D, continued after the first (failed) inside test ----------
+// x: pushed position (may be shifted by periodic BCs), lp: LastPartPos.  elem: in = element whose inside test failed with
+// determinants det, out = new element.  tria: global TriaElem array (index = global element id - 1).
+__device__ __noinline__ int tria_track_walk(const TriaElem* __restrict__ tria, double x[3], double lp[3], int& elem,
+                                            double det[6][2]) {
+  int done[6][4];  // DoneLastElem(1:4,1:6) -> [slot][entry]
+#pragma unroll
+  for (int a = 0; a < 6; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) done[a][b] = 0;
+  int ElemID = elem;
+  const TriaElem* te = tria + (ElemID - 1);
+  for (int guard = 0; guard < 100000; ++guard) {
+    // 2b) find the crossed side
+    double V[3] = {x[0] - lp[0], x[1] - lp[1], x[2] - lp[2]};
+    double len = sqrt((V[0] * V[0] + V[1] * V[1]) + V[2] * V[2]);
+    if (fabs(len) > 0.) {
+      V[0] = V[0] / len; V[1] = V[1] / len; V[2] = V[2] / len;
+    }
+    int nThrough = 0;
+    int locS[6], triN[6];
+    int side = -1, tri = 0;
+    for (int s = 0; s < 6; ++s)
+      for (int t = 1; t <= 2; ++t)
+        if (det[s][t - 1] <= -0.0) {
+          if (through_side_check_fast(te, lp, V, s, t)) {
+            if (nThrough < 6) { locS[nThrough] = s; triN[nThrough] = t; }
+            ++nThrough;
+            side = s;
+          }
+        }
+    if (nThrough > 6) nThrough = 6;  // cannot happen for a hexahedron with consistent orientation (LocSidesTemp(1:6))
+    tri = (nThrough > 0) ? triN[0] : 0;
+    if (nThrough != 1) {
+      if (nThrough == 0) return TRK_LOST;
+      int second = 0;
+      double minRatio = 0;
+      for (int i2 = 0; i2 < nThrough; ++i2) {
+        bool doCheck = true;
+        const int gside = te->sideID[locS[i2]];
+        for (int is = 1; is < 6; ++is)
+          if (done[is][0] == ElemID && done[is][3] == gside && done[is][2] == triN[i2]) doCheck = false;
+        if (!doCheck) continue;
+        double detM;
+        if (!through_side_lastpos_check(te, lp, locS[i2], triN[i2], detM)) continue;
+        const double dS = det[locS[i2]][triN[i2] - 1];
+        if (detM == 0 && dS == 0) continue;
+        if (detM == 0 && minRatio == 0) {
+          ++second; side = locS[i2]; tri = triN[i2];
+        } else {
+          if (detM == 0) continue;
+          const double ratio = dS / detM;
+          if (ratio < minRatio) {
+            minRatio = ratio;
+            ++second; side = locS[i2]; tri = triN[i2];
+          }
+        }
+      }
+      if (second == 0) return TRK_LOST;
+    }
+    // 3) boundary interaction or step into the neighbour
+    const int gside = te->sideID[side];
+    const int bc = te->bcid[side];
+    const int oldElem = ElemID;
+    bool clearDone = false;
+    if (bc > 0) {
+      const int kind = cst.bc_kind[bc - 1];
+      if (kind == PGPU_BC_OPEN) return TRK_REMOVED;
+      if (kind != PGPU_BC_PERIODIC) return TRK_ERR_BC;
+      const double alpha = intersection_with_wall(te, lp, V, side, tri);
+      // PeriodicBoundary, particle_boundary_condition.f90:224-284
+      const int pvid = cst.bc_alpha[bc - 1];
+      const int pv = (pvid < 0 ? -pvid : pvid) - 1;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        lp[d] = lp[d] + V[d] * alpha;
+        lp[d] = lp[d] + copysign(cst.PeriodicVectors[pv][d], (double)pvid);
+        x[d] = lp[d] + (len - alpha) * V[d];
+      }
+      ElemID = te->nbElem[side];
+      (void)clearDone;
+    } else {
+      ElemID = te->nbElem[side];
+    }
+    for (int a = 5; a >= 1; --a)
+      for (int b = 0; b < 4; ++b) done[a][b] = done[a - 1][b];
+    done[0][0] = oldElem; done[0][1] = side + 1; done[0][2] = tri; done[0][3] = gside;
+    if (ElemID < 1) return TRK_ERR_ELEM;
+    te = tria + (ElemID - 1);
+    // 2a) inside test in the new element
+    if (inside_quad3d(te, x, det)) {
+      elem = ElemID;
+      return TRK_OK;
+    }
+  }
+  return TRK_ERR_LOOP;
+}

@@ -1,0 +1,616 @@
+// piclas_gpu.cu — C ABI (include/piclas_gpu.h) of the B200 particle step: context, host<->device transfers, step driver.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "sort.cuh"
+
+namespace {
+
+enum { ELEM_FIRSTSIDEIND = 2, ELEM_LASTSIDEIND = 3, ELEM_FIRSTNODEIND = 4, ELEM_LASTNODEIND = 5, ELEM_RANK = 6 };
+enum { SIDE_NBELEMID = 2, SIDE_BCID = 4, SIDE_LOCALID = 6 };
+
+struct Ctx {
+  bool ready = false;
+  int device = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  pgpu_params_t prm;
+  int nGlobalElems = 0, nElems = 0, offsetElem = 0, N = 0, NP = 0, ND = 0, nNodes = 0, nRanks = 1, myRank = 0;
+  int nSMs = 148;
+  // mesh records
+  TriaElem* dTria = nullptr;
+  GeoElem* dGeo = nullptr;
+  int32_t* dElemRank = nullptr;
+  double* dElemXGP = nullptr;   // Elem_xGP (global) — inverse-distance fallback only
+  // CVWM
+  int32_t *dAdjOff = nullptr, *dAdj = nullptr, *dElemNodeU = nullptr;
+  int32_t *dPerN = nullptr, *dPerOff = nullptr, *dPerNodes = nullptr;
+  double *dNodeVolume = nullptr, *dElemAcc = nullptr, *dS = nullptr, *dNodeSource = nullptr, *dPartSource = nullptr;
+  // field
+  double* dE = nullptr;
+  bool haveField = false;
+  // particles
+  PartBuf buf[2];
+  double* dXi[3] = {nullptr, nullptr, nullptr};  // cached reference positions (never permuted: recomputed after a sort)
+  int cur = 0;
+  int64_t cap = 0, nPart = 0, nTotalSorted = 0;
+  bool carryIDs = false;
+  bool xiValid = false;
+  int64_t* dElemOff = nullptr;        // [nElems + nRanks + 2]
+  std::vector<int64_t> hTailOff;      // host copy of elemOff[nElems .. nElems+nRanks+1]
+  uint32_t* dKeys = nullptr;          // [cap]
+  int* dCounters = nullptr;           // [4]
+  SortWorkspace sortws;
+  int keyBits = 1;
+  // staging for AoS transfers
+  double* dStage = nullptr;
+  int32_t* dStageI = nullptr;
+  int64_t* dStageL = nullptr;
+  int64_t stageCap = 0;
+  // timing
+  double lastMs = 0.;
+  int lastLaunches = 0;
+};
+
+Ctx g;
+std::string g_err;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                                       cudaGetErrorString(e_));                                        \
+  } while (0)
+
+template <typename T>
+int upload(T** d, const T* h, size_t n) {
+  CK(cudaMalloc((void**)d, (n ? n : 1) * sizeof(T)));
+  if (n) CK(cudaMemcpy(*d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int alloc_partbuf(PartBuf& b, int64_t cap, bool ids) {
+  for (int d = 0; d < 3; ++d) {
+    CK(cudaMalloc((void**)&b.x[d], cap * 8));
+    CK(cudaMalloc((void**)&b.v[d], cap * 8));
+    b.xi[d] = nullptr;
+  }
+  CK(cudaMalloc((void**)&b.elem, cap * 4));
+  CK(cudaMalloc((void**)&b.meta, cap));
+  b.id = nullptr;
+  if (ids) CK(cudaMalloc((void**)&b.id, cap * 8));
+  return 0;
+}
+void free_partbuf(PartBuf& b) {
+  for (int d = 0; d < 3; ++d) { cudaFree(b.x[d]); cudaFree(b.v[d]); b.x[d] = b.v[d] = b.xi[d] = nullptr; }
+  cudaFree(b.elem); cudaFree(b.meta); cudaFree(b.id);
+  b.elem = nullptr; b.meta = nullptr; b.id = nullptr;
+}
+
+int reserve_particles(int64_t need) {
+  if (need <= g.cap) return 0;
+  int64_t ncap = need + need / 8 + 1024;
+  if (g.prm.maxParticleNumber > ncap) ncap = g.prm.maxParticleNumber;
+  PartBuf nb[2];
+  if (alloc_partbuf(nb[0], ncap, g.carryIDs)) return 1;
+  if (alloc_partbuf(nb[1], ncap, g.carryIDs)) return 1;
+  if (g.cap > 0 && g.nPart > 0) {
+    const PartBuf& o = g.buf[g.cur];
+    for (int d = 0; d < 3; ++d) {
+      CK(cudaMemcpy(nb[0].x[d], o.x[d], g.nPart * 8, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(nb[0].v[d], o.v[d], g.nPart * 8, cudaMemcpyDeviceToDevice));
+    }
+    CK(cudaMemcpy(nb[0].elem, o.elem, g.nPart * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(nb[0].meta, o.meta, g.nPart, cudaMemcpyDeviceToDevice));
+    if (g.carryIDs) CK(cudaMemcpy(nb[0].id, o.id, g.nPart * 8, cudaMemcpyDeviceToDevice));
+  }
+  if (g.cap > 0) {
+    free_partbuf(g.buf[0]);
+    free_partbuf(g.buf[1]);
+  }
+  for (int d = 0; d < 3; ++d) {
+    cudaFree(g.dXi[d]);
+    CK(cudaMalloc((void**)&g.dXi[d], ncap * 8));
+    nb[0].xi[d] = nb[1].xi[d] = g.dXi[d];
+  }
+  g.buf[0] = nb[0];
+  g.buf[1] = nb[1];
+  g.cur = 0;
+  g.cap = ncap;
+  cudaFree(g.dKeys);
+  CK(cudaMalloc((void**)&g.dKeys, ncap * 4));
+  CK(sort_workspace_reserve(g.sortws, (size_t)ncap));
+  g.xiValid = false;
+  return 0;
+}
+
+int reserve_stage(int64_t n) {
+  if (n <= g.stageCap) return 0;
+  cudaFree(g.dStage); cudaFree(g.dStageI); cudaFree(g.dStageL);
+  CK(cudaMalloc((void**)&g.dStage, n * 9 * 8));
+  CK(cudaMalloc((void**)&g.dStageI, n * 4 * 4));
+  CK(cudaMalloc((void**)&g.dStageL, n * 8));
+  g.stageCap = n;
+  return 0;
+}
+
+__global__ void k_aos_to_soa(PartBuf pb, int64_t dst0, int64_t n, const double* __restrict__ ps, const int32_t* __restrict__ spec,
+                             const int32_t* __restrict__ elem, const int32_t* __restrict__ inside, const int32_t* __restrict__ isnew,
+                             const int64_t* __restrict__ ids, int64_t idBase) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = dst0 + i;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    pb.x[d][p] = ps[i * 6 + d];
+    pb.v[d][p] = ps[i * 6 + 3 + d];
+  }
+  const bool in = inside ? (inside[i] != 0) : true;
+  pb.elem[p] = in ? elem[i] : 0;
+  pb.meta[p] = (uint8_t)(((spec[i] - 1) & META_SPEC_MASK) | ((isnew && isnew[i]) ? META_ISNEW : 0));
+  if (pb.id) pb.id[p] = ids ? ids[i] : (idBase + i);
+}
+
+__global__ void k_soa_to_aos(PartBuf pb, int64_t src0, int64_t n, double* __restrict__ ps, int32_t* __restrict__ spec,
+                             int32_t* __restrict__ elem, double* __restrict__ xi, int64_t* __restrict__ ids) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = src0 + i;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    ps[i * 6 + d] = pb.x[d][p];
+    ps[i * 6 + 3 + d] = pb.v[d][p];
+    if (xi) xi[i * 3 + d] = pb.xi[d][p];
+  }
+  spec[i] = (pb.meta[p] & META_SPEC_MASK) + 1;
+  elem[i] = pb.elem[p];
+  if (ids) ids[i] = pb.id ? pb.id[p] : -1;
+}
+
+// sort the first nIn particles of the current buffer by key (keys already in g.dKeys), gather into the other buffer
+int sort_and_permute(int64_t nIn) {
+  uint32_t *sk = nullptr, *perm = nullptr;
+  CK(radix_sort_by_key(g.sortws, g.dKeys, (size_t)nIn, g.keyBits, g.st, &sk, &perm, &g.lastLaunches));
+  const PartBuf& a = g.buf[g.cur];
+  PartBuf& b = g.buf[g.cur ^ 1];
+  for (int d = 0; d < 3; ++d) {
+    CK(gather_f64(a.x[d], b.x[d], perm, (size_t)nIn, g.st));
+    CK(gather_f64(a.v[d], b.v[d], perm, (size_t)nIn, g.st));
+  }
+  CK(gather_i32(a.elem, b.elem, perm, (size_t)nIn, g.st));
+  CK(gather_u8(a.meta, b.meta, perm, (size_t)nIn, g.st));
+  g.lastLaunches += 8;
+  if (g.carryIDs) { CK(gather_i64(a.id, b.id, perm, (size_t)nIn, g.st)); ++g.lastLaunches; }
+  const uint32_t nKeys = (uint32_t)(g.nElems + g.nRanks + 1);
+  CK(segment_offsets(sk, (size_t)nIn, nKeys, g.dElemOff, g.st));
+  ++g.lastLaunches;
+  g.hTailOff.assign(g.nRanks + 2, 0);
+  CK(cudaMemcpyAsync(g.hTailOff.data(), g.dElemOff + g.nElems, (g.nRanks + 2) * sizeof(int64_t), cudaMemcpyDeviceToHost, g.st));
+  CK(cudaStreamSynchronize(g.st));
+  g.cur ^= 1;
+  g.nPart = g.hTailOff[0];                  // particles owned by this rank
+  g.nTotalSorted = g.hTailOff[g.nRanks];    // + emigrants grouped by destination rank behind them
+  g.xiValid = false;
+  return 0;
+}
+
+template <int NP>
+void launch_push_track(double dt) {
+  const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
+  k_push_track_tria<NP><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dE, g.dElemXGP,
+                                                   g.dElemRank, g.dKeys, dt, g.xiValid ? 1 : 0, g.dCounters);
+}
+template <int NP>
+void launch_dofs() {
+  const size_t total = (size_t)g.nElems * NP * NP * NP * 4;
+  k_nodes_to_dofs<NP><<<(unsigned)((total + 255) / 256), 256, 0, g.st>>>(g.dNodeSource, g.dElemNodeU, g.dPartSource, g.nElems);
+}
+
+void begin_timing() {
+  g.lastLaunches = 0;
+  cudaEventRecord(g.ev0, g.st);
+}
+void end_timing() {
+  cudaEventRecord(g.ev1, g.st);
+  cudaEventSynchronize(g.ev1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, g.ev0, g.ev1);
+  g.lastMs = ms;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* piclas_gpu_last_error(void) { return g_err.c_str(); }
+
+int piclas_gpu_finalize(void) {
+  if (!g.ready && !g.st) return 0;
+  cudaSetDevice(g.device);
+  cudaDeviceSynchronize();
+  cudaFree(g.dTria); cudaFree(g.dGeo); cudaFree(g.dElemRank); cudaFree(g.dElemXGP);
+  cudaFree(g.dAdjOff); cudaFree(g.dAdj); cudaFree(g.dElemNodeU); cudaFree(g.dPerN); cudaFree(g.dPerOff); cudaFree(g.dPerNodes);
+  cudaFree(g.dNodeVolume); cudaFree(g.dElemAcc); cudaFree(g.dS); cudaFree(g.dNodeSource); cudaFree(g.dPartSource);
+  cudaFree(g.dE); cudaFree(g.dElemOff); cudaFree(g.dKeys); cudaFree(g.dCounters);
+  cudaFree(g.dStage); cudaFree(g.dStageI); cudaFree(g.dStageL);
+  if (g.cap > 0) {
+    free_partbuf(g.buf[0]);
+    free_partbuf(g.buf[1]);
+  }
+  for (int d = 0; d < 3; ++d) cudaFree(g.dXi[d]);
+  sort_workspace_free(g.sortws);
+  if (g.ev0) cudaEventDestroy(g.ev0);
+  if (g.ev1) cudaEventDestroy(g.ev1);
+  if (g.st) cudaStreamDestroy(g.st);
+  g = Ctx();
+  return 0;
+}
+
+int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
+  if (g.ready) piclas_gpu_finalize();
+  g_err.clear();
+  if (!m || !p) return fail("piclas_gpu_init: null argument");
+  // ---- what this build supports; everything else aborts loudly ----------------------
+  if (m->NGeo != 1) return fail("piclas_gpu_init: NGeo=%d not supported (straight-sided NGeo=1 meshes only)", m->NGeo);
+  if (m->N < 1 || m->N > PGPU_MAX_N) return fail("piclas_gpu_init: N=%d outside 1..%d", m->N, PGPU_MAX_N);
+  if (p->TrackingMethod != PGPU_TRIATRACKING) return fail("piclas_gpu_init: TrackingMethod=%d not supported yet (triatracking only)", p->TrackingMethod);
+  if (p->DoDeposition && p->DepositionType != PGPU_DEPO_CVWM) return fail("piclas_gpu_init: PIC-Deposition-Type %d not supported yet (cell_volweight_mean only)", p->DepositionType);
+  if (p->TimeDiscMethod != PGPU_TIMEDISC_BORIS_LEAPFROG && p->TimeDiscMethod != PGPU_TIMEDISC_LEAPFROG)
+    return fail("piclas_gpu_init: TimeDiscMethod=%d not supported (508 Boris-Leapfrog, 509 Leapfrog)", p->TimeDiscMethod);
+  if (p->CartesianPeriodic) return fail("piclas_gpu_init: CartesianPeriodic=T not supported");
+  if (p->RefMappingGuess == 2) return fail("piclas_gpu_init: RefMappingGuess=2 not supported (use 1, 3 or 4)");
+  if (p->RefMappingGuess < 1 || p->RefMappingGuess > 4) return fail("piclas_gpu_init: RefMappingGuess=%d invalid", p->RefMappingGuess);
+  if (p->nSpecies < 1 || p->nSpecies > 32) return fail("piclas_gpu_init: nSpecies=%d outside 1..32", p->nSpecies);
+  if (m->nBCs > 255) return fail("piclas_gpu_init: more than 255 boundary conditions");
+  if (m->nPeriodicVectors > 8) return fail("piclas_gpu_init: more than 8 periodic vectors");
+  if (m->elemInfoSize < 7 || m->sideInfoSize < 8) return fail("piclas_gpu_init: ElemInfo/SideInfo leading dimension too small");
+  if (p->nRanks < 1 || p->myRank < 0 || p->myRank >= p->nRanks) return fail("piclas_gpu_init: bad rank layout");
+  for (int b = 0; b < m->nBCs; ++b)
+    if (m->bc_kind[b] != PGPU_BC_OPEN && m->bc_kind[b] != PGPU_BC_PERIODIC)
+      return fail("piclas_gpu_init: boundary %d has TargetBoundCond=%d; only open (1) and periodic (3) are supported", b + 1, m->bc_kind[b]);
+
+  g.device = p->device;
+  CK(cudaSetDevice(g.device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, g.device));
+  g.nSMs = prop.multiProcessorCount;
+  CK(cudaStreamCreate(&g.st));
+  CK(cudaEventCreate(&g.ev0));
+  CK(cudaEventCreate(&g.ev1));
+  g.prm = *p;
+  g.prm.ChargeIC = g.prm.MassIC = g.prm.MacroParticleFactor = nullptr;
+  g.nGlobalElems = m->nGlobalElems;
+  g.nElems = m->nElems;
+  g.offsetElem = m->offsetElem;
+  g.N = m->N;
+  g.NP = m->N + 1;
+  g.ND = g.NP * g.NP * g.NP;
+  g.nNodes = m->nUniqueGlobalNodes;
+  g.nRanks = p->nRanks;
+  g.myRank = p->myRank;
+  g.carryIDs = p->carryParticleIDs != 0;
+  const int nG = m->nGlobalElems;
+
+  // ---- per-element records ------------------------------------------------------------------------------------
+  std::vector<TriaElem> tria(nG);
+  std::vector<GeoElem> geo(nG);
+  std::vector<int32_t> rank(nG);
+  for (int e = 0; e < nG; ++e) {
+    const int32_t* ei = m->ElemInfo + (size_t)e * m->elemInfoSize;
+    const int firstSide = ei[ELEM_FIRSTSIDEIND], lastSide = ei[ELEM_LASTSIDEIND];
+    const int firstNode = ei[ELEM_FIRSTNODEIND], lastNode = ei[ELEM_LASTNODEIND];
+    if (lastSide - firstSide != 6) return fail("piclas_gpu_init: element %d has %d sides (mortar meshes are not supported)", e + 1, lastSide - firstSide);
+    if (lastNode - firstNode != 8) return fail("piclas_gpu_init: element %d has %d nodes (NGeo=1 hexahedra only)", e + 1, lastNode - firstNode);
+    rank[e] = ei[ELEM_RANK];
+    if (rank[e] < 0 || rank[e] >= g.nRanks) return fail("piclas_gpu_init: ELEM_RANK of element %d outside 0..nRanks-1", e + 1);
+    TriaElem& t = tria[e];
+    memset(&t, 0, sizeof(t));
+    for (int n = 0; n < 8; ++n)
+      for (int d = 0; d < 3; ++d) t.corner[n][d] = m->NodeCoords[(size_t)(firstNode + n) * 3 + d];
+    for (int s = 0; s < 6; ++s) {
+      const int sid = firstSide + s + 1;  // 1-based SideInfo index
+      const int32_t* si = m->SideInfo + (size_t)(sid - 1) * m->sideInfoSize;
+      if (si[SIDE_LOCALID] != s + 1) return fail("piclas_gpu_init: element %d: SIDE_LOCALID out of order (mortar meshes are not supported)", e + 1);
+      if (si[SIDE_NBELEMID] < 0) return fail("piclas_gpu_init: element %d has a mortar side", e + 1);
+      if (si[SIDE_BCID] < 0 || si[SIDE_BCID] > m->nBCs) return fail("piclas_gpu_init: element %d: SIDE_BCID out of range", e + 1);
+      t.nbElem[s] = si[SIDE_NBELEMID];
+      t.sideID[s] = sid;
+      t.bcid[s] = (uint8_t)si[SIDE_BCID];
+      if (m->ConcaveElemSide[(size_t)e * 6 + s]) t.concave |= (uint8_t)(1u << s);
+      for (int n = 0; n < 4; ++n) {
+        const int loc = m->ElemSideNodeID[((size_t)e * 6 + s) * 4 + n] - firstNode;
+        if (loc < 0 || loc > 7) return fail("piclas_gpu_init: ElemSideNodeID of element %d points outside the element", e + 1);
+        t.sideNode[s][n] = (uint8_t)loc;
+      }
+    }
+    GeoElem& ge = geo[e];
+    memset(&ge, 0, sizeof(ge));
+    memcpy(ge.XCL, m->XCL_NGeo + (size_t)e * 24, 24 * 8);
+    memcpy(ge.dXCL, m->dXCL_NGeo + (size_t)e * 72, 72 * 8);
+    memcpy(ge.bary, m->ElemBaryNGeo + (size_t)e * 3, 3 * 8);
+    memcpy(ge.xez, m->XiEtaZetaBasis + (size_t)e * 18, 18 * 8);
+    memcpy(ge.slen, m->slenXiEtaZetaBasis + (size_t)e * 6, 6 * 8);
+  }
+  if (upload(&g.dTria, tria.data(), (size_t)nG)) return 1;
+  if (upload(&g.dGeo, geo.data(), (size_t)nG)) return 1;
+  if (upload(&g.dElemRank, rank.data(), (size_t)nG)) return 1;
+  if (upload(&g.dElemXGP, m->Elem_xGP, (size_t)nG * g.ND * 3)) return 1;
+
+  // ---- cell_volweight_mean tables ---------------------------------------------------------------------------------
+  {
+    std::vector<int32_t> elemNodeU((size_t)g.nElems * 8), cnt(g.nNodes + 1, 0);
+    for (int e = 0; e < g.nElems; ++e)
+      for (int c = 0; c < 8; ++c) {
+        const int nu = m->NodeInfo[m->ElemNodeID[(size_t)(g.offsetElem + e) * 8 + c] - 1] - 1;
+        if (nu < 0 || nu >= g.nNodes) return fail("piclas_gpu_init: NodeInfo out of range");
+        elemNodeU[(size_t)e * 8 + c] = nu;
+        cnt[nu + 1]++;
+      }
+    for (int n = 0; n < g.nNodes; ++n) cnt[n + 1] += cnt[n];
+    std::vector<int32_t> adj((size_t)g.nElems * 8), fill(cnt.begin(), cnt.end() - 1);
+    for (int e = 0; e < g.nElems; ++e)
+      for (int c = 0; c < 8; ++c) adj[fill[elemNodeU[(size_t)e * 8 + c]]++] = e * 8 + c;
+    if (upload(&g.dAdjOff, cnt.data(), cnt.size())) return 1;
+    if (upload(&g.dAdj, adj.data(), adj.size())) return 1;
+    if (upload(&g.dElemNodeU, elemNodeU.data(), elemNodeU.size())) return 1;
+    if (upload(&g.dPerN, m->Periodic_nNodes, (size_t)g.nNodes)) return 1;
+    if (upload(&g.dPerOff, m->Periodic_offsetNode, (size_t)g.nNodes)) return 1;
+    if (upload(&g.dPerNodes, m->Periodic_Nodes, (size_t)m->nPeriodicNodesTotal)) return 1;
+    if (upload(&g.dNodeVolume, m->NodeVolume, (size_t)g.nNodes)) return 1;
+    CK(cudaMalloc((void**)&g.dElemAcc, (size_t)(g.nElems ? g.nElems : 1) * 32 * 8));
+    CK(cudaMalloc((void**)&g.dS, (size_t)g.nNodes * 4 * 8));
+    CK(cudaMalloc((void**)&g.dNodeSource, (size_t)g.nNodes * 4 * 8));
+    CK(cudaMalloc((void**)&g.dPartSource, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 4 * 8));
+  }
+  CK(cudaMalloc((void**)&g.dE, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
+  CK(cudaMemset(g.dE, 0, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
+  CK(cudaMalloc((void**)&g.dElemOff, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
+  CK(cudaMemset(g.dElemOff, 0, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
+  CK(cudaMalloc((void**)&g.dCounters, 4 * sizeof(int)));
+  g.keyBits = 1;
+  while ((1u << g.keyBits) < (uint32_t)(g.nElems + g.nRanks + 1)) ++g.keyBits;
+
+  // ---- constant tables ------------------------------------------------------------------------------------------------
+  static ConstTables h;
+  memset(&h, 0, sizeof(h));
+  for (int i = 0; i <= m->N; ++i) {
+    h.xGP[i] = m->xGP[i]; h.wGP[i] = m->wGP[i]; h.wBary[i] = m->wBary[i];
+    h.cvwFac[i] = (m->xGP[i] + 1.0) / 2.0;  // pic_depo.f90:271-275
+  }
+  for (int i = 0; i < 2; ++i) { h.XiCL[i] = m->XiCL_NGeo[i]; h.wBaryCL[i] = m->wBaryCL_NGeo[i]; }
+  for (int i = 0; i < 6; ++i) h.externalField[i] = p->externalField[i];
+  h.c2_inv = p->c2_inv;
+  h.RefMappingEps = p->RefMappingEps;
+  h.RefMappingGuess = p->RefMappingGuess;
+  h.TrackingMethod = p->TrackingMethod;
+  h.TimeDiscMethod = p->TimeDiscMethod;
+  h.DoInterpolation = p->DoInterpolation;
+  h.DepositionType = p->DepositionType;
+  h.nSpecies = p->nSpecies;
+  for (int s = 0; s < p->nSpecies; ++s) { h.ChargeIC[s] = p->ChargeIC[s]; h.MassIC[s] = p->MassIC[s]; h.MPF[s] = p->MacroParticleFactor[s]; }
+  h.nBCs = m->nBCs;
+  for (int b = 0; b < m->nBCs; ++b) { h.bc_kind[b] = m->bc_kind[b]; h.bc_alpha[b] = m->bc_alpha[b]; }
+  h.nPeriodicVectors = m->nPeriodicVectors;
+  for (int v = 0; v < m->nPeriodicVectors; ++v)
+    for (int d = 0; d < 3; ++d) h.PeriodicVectors[v][d] = m->PeriodicVectors[v * 3 + d];
+  h.nGlobalElems = nG; h.nElems = g.nElems; h.offsetElem = g.offsetElem; h.N = g.N; h.nRanks = g.nRanks; h.myRank = g.myRank;
+  CK(cudaMemcpyToSymbol(cst, &h, sizeof(h)));
+  CK(cudaDeviceSynchronize());
+  g.nPart = 0;
+  g.hTailOff.assign(g.nRanks + 2, 0);
+  g.ready = true;
+  if (p->maxParticleNumber > 0 && reserve_particles(p->maxParticleNumber)) return 1;
+  return 0;
+}
+
+int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_t* PartSpecies, const int32_t* GlobalElemID,
+                                const int32_t* ParticleInside, const int32_t* IsNewPart, const double* PartPosRef,
+                                const int64_t* ids, int32_t append) {
+  if (!g.ready) return fail("piclas_gpu_upload_particles: not initialised");
+  (void)PartPosRef;
+  CK(cudaSetDevice(g.device));
+  if (n < 0) return fail("piclas_gpu_upload_particles: n < 0");
+  if (n > 0 && (!PartState || !PartSpecies || !GlobalElemID)) return fail("piclas_gpu_upload_particles: null array");
+  const int64_t base = append ? g.nPart : 0;
+  if (base + n >= (int64_t)0x7fffffff) return fail("piclas_gpu_upload_particles: more than 2^31-1 particles on one GPU");
+  if (reserve_particles(base + n)) return 1;
+  begin_timing();
+  const int64_t chunk = 1 << 22;
+  if (reserve_stage(n < chunk ? (n ? n : 1) : chunk)) return 1;
+  for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+    const int64_t m = (n - c0 < chunk) ? n - c0 : chunk;
+    int32_t* dI = g.dStageI;
+    CK(cudaMemcpyAsync(g.dStage, PartState + c0 * 6, m * 6 * 8, cudaMemcpyHostToDevice, g.st));
+    CK(cudaMemcpyAsync(dI, PartSpecies + c0, m * 4, cudaMemcpyHostToDevice, g.st));
+    CK(cudaMemcpyAsync(dI + g.stageCap, GlobalElemID + c0, m * 4, cudaMemcpyHostToDevice, g.st));
+    if (ParticleInside) CK(cudaMemcpyAsync(dI + 2 * g.stageCap, ParticleInside + c0, m * 4, cudaMemcpyHostToDevice, g.st));
+    if (IsNewPart) CK(cudaMemcpyAsync(dI + 3 * g.stageCap, IsNewPart + c0, m * 4, cudaMemcpyHostToDevice, g.st));
+    if (ids && g.carryIDs) CK(cudaMemcpyAsync(g.dStageL, ids + c0, m * 8, cudaMemcpyHostToDevice, g.st));
+    k_aos_to_soa<<<(unsigned)((m + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], base + c0, m, g.dStage, dI, dI + g.stageCap,
+                                                               ParticleInside ? dI + 2 * g.stageCap : nullptr,
+                                                               IsNewPart ? dI + 3 * g.stageCap : nullptr,
+                                                               (ids && g.carryIDs) ? g.dStageL : nullptr, base + c0);
+    ++g.lastLaunches;
+    CK(cudaStreamSynchronize(g.st));
+  }
+  const int64_t nIn = base + n;
+  if (nIn > 0) {
+    k_keys_from_elem<<<(unsigned)((nIn + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur].elem, g.dElemRank, g.dKeys, nIn, g.nElems,
+                                                                      g.offsetElem, g.myRank, g.nRanks);
+    ++g.lastLaunches;
+  }
+  if (sort_and_permute(nIn)) return 1;
+  end_timing();
+  if (g.nTotalSorted != g.nPart) return fail("piclas_gpu_upload_particles: %lld particles lie in elements of other ranks",
+                                             (long long)(g.nTotalSorted - g.nPart));
+  return 0;
+}
+
+int64_t piclas_gpu_num_particles(void) { return g.ready ? g.nPart : -1; }
+
+int piclas_gpu_download_particles(int64_t nmax, double* PartState, int32_t* PartSpecies, int32_t* GlobalElemID, double* PartPosRef,
+                                  int64_t* ids, int64_t* n_out) {
+  if (!g.ready) return fail("piclas_gpu_download_particles: not initialised");
+  CK(cudaSetDevice(g.device));
+  const int64_t n = g.nPart;
+  if (n_out) *n_out = n;
+  if (n > nmax) return fail("piclas_gpu_download_particles: %lld particles do not fit into nmax=%lld", (long long)n, (long long)nmax);
+  if (PartPosRef && !g.xiValid) return fail("piclas_gpu_download_particles: reference positions are not current (call deposit first)");
+  const int64_t chunk = 1 << 22;
+  if (reserve_stage(n < chunk ? (n ? n : 1) : chunk)) return 1;
+  for (int64_t c0 = 0; c0 < n; c0 += chunk) {
+    const int64_t m = (n - c0 < chunk) ? n - c0 : chunk;
+    double* dXi = g.dStage + 6 * g.stageCap;
+    k_soa_to_aos<<<(unsigned)((m + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], c0, m, g.dStage, g.dStageI, g.dStageI + g.stageCap,
+                                                               PartPosRef ? dXi : nullptr, ids ? g.dStageL : nullptr);
+    if (PartState) CK(cudaMemcpyAsync(PartState + c0 * 6, g.dStage, m * 6 * 8, cudaMemcpyDeviceToHost, g.st));
+    if (PartSpecies) CK(cudaMemcpyAsync(PartSpecies + c0, g.dStageI, m * 4, cudaMemcpyDeviceToHost, g.st));
+    if (GlobalElemID) CK(cudaMemcpyAsync(GlobalElemID + c0, g.dStageI + g.stageCap, m * 4, cudaMemcpyDeviceToHost, g.st));
+    if (PartPosRef) CK(cudaMemcpyAsync(PartPosRef + c0 * 3, dXi, m * 3 * 8, cudaMemcpyDeviceToHost, g.st));
+    if (ids) CK(cudaMemcpyAsync(ids + c0, g.dStageL, m * 8, cudaMemcpyDeviceToHost, g.st));
+    CK(cudaStreamSynchronize(g.st));
+  }
+  return 0;
+}
+
+int piclas_gpu_set_field(const double* E) {
+  if (!g.ready) return fail("piclas_gpu_set_field: not initialised");
+  if (!E) return fail("piclas_gpu_set_field: null field");
+  CK(cudaSetDevice(g.device));
+  CK(cudaMemcpyAsync(g.dE, E, (size_t)g.nElems * g.ND * 3 * 8, cudaMemcpyHostToDevice, g.st));
+  CK(cudaStreamSynchronize(g.st));
+  g.haveField = true;
+  return 0;
+}
+
+static int deposit_local() {
+  const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
+  if (grid > 0) {
+    k_deposit_cvwm<<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dElemAcc, g.dCounters);
+    ++g.lastLaunches;
+  }
+  k_node_sum<<<(g.nNodes * 4 + 255) / 256, 256, 0, g.st>>>(g.dAdjOff, g.dAdj, g.dElemAcc, g.dS, g.nNodes);
+  ++g.lastLaunches;
+  CK(cudaGetLastError());
+  g.xiValid = true;
+  return 0;
+}
+
+static int deposit_finish(double* PartSource, double* NodeSource) {
+  k_node_final<<<(g.nNodes * 4 + 255) / 256, 256, 0, g.st>>>(g.dS, g.dPerN, g.dPerOff, g.dPerNodes, g.dNodeVolume, g.dNodeSource, g.nNodes,
+                                                            g.prm.CartesianPeriodic ? 1 : 1);
+  ++g.lastLaunches;
+  if (g.nElems > 0) {
+    switch (g.NP) {
+      case 2: launch_dofs<2>(); break;
+      case 3: launch_dofs<3>(); break;
+      case 4: launch_dofs<4>(); break;
+      case 5: launch_dofs<5>(); break;
+      case 6: launch_dofs<6>(); break;
+      case 7: launch_dofs<7>(); break;
+      case 8: launch_dofs<8>(); break;
+    }
+    ++g.lastLaunches;
+  }
+  CK(cudaGetLastError());
+  end_timing();
+  if (PartSource) CK(cudaMemcpyAsync(PartSource, g.dPartSource, (size_t)g.nElems * g.ND * 4 * 8, cudaMemcpyDeviceToHost, g.st));
+  if (NodeSource) CK(cudaMemcpyAsync(NodeSource, g.dNodeSource, (size_t)g.nNodes * 4 * 8, cudaMemcpyDeviceToHost, g.st));
+  CK(cudaStreamSynchronize(g.st));
+  return 0;
+}
+
+int piclas_gpu_deposit(double* PartSource, double* NodeSource) {
+  if (!g.ready) return fail("piclas_gpu_deposit: not initialised");
+  if (!g.prm.DoDeposition) return fail("piclas_gpu_deposit: PIC-DoDeposition=F");
+  CK(cudaSetDevice(g.device));
+  begin_timing();
+  if (deposit_local()) return 1;
+  if (g.nRanks > 1) {  // caller sums the node array over ranks, then piclas_gpu_deposit_finish
+    end_timing();
+    CK(cudaStreamSynchronize(g.st));
+    return 0;
+  }
+  return deposit_finish(PartSource, NodeSource);
+}
+
+int piclas_gpu_nodesource_device(void** devNodeSource) {
+  if (!g.ready) return fail("piclas_gpu_nodesource_device: not initialised");
+  *devNodeSource = g.dS;
+  return 0;
+}
+
+int piclas_gpu_deposit_finish(double* PartSource, double* NodeSource) {
+  if (!g.ready) return fail("piclas_gpu_deposit_finish: not initialised");
+  CK(cudaSetDevice(g.device));
+  const int keep = g.lastLaunches;
+  const double ms = g.lastMs;
+  begin_timing();
+  g.lastLaunches = keep;
+  const int rc = deposit_finish(PartSource, NodeSource);
+  g.lastMs += ms;
+  return rc;
+}
+
+int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
+  (void)iter;
+  if (!g.ready) return fail("piclas_gpu_push_track: not initialised");
+  CK(cudaSetDevice(g.device));
+  if (g.prm.DoInterpolation && !g.haveField) return fail("piclas_gpu_push_track: no field set (piclas_gpu_set_field)");
+  begin_timing();
+  CK(cudaMemsetAsync(g.dCounters, 0, 4 * sizeof(int), g.st));
+  if (g.nPart > 0) {
+    switch (g.NP) {
+      case 2: launch_push_track<2>(dt); break;
+      case 3: launch_push_track<3>(dt); break;
+      case 4: launch_push_track<4>(dt); break;
+      case 5: launch_push_track<5>(dt); break;
+      case 6: launch_push_track<6>(dt); break;
+      case 7: launch_push_track<7>(dt); break;
+      case 8: launch_push_track<8>(dt); break;
+    }
+    ++g.lastLaunches;
+    CK(cudaGetLastError());
+  }
+  int hc[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
+  if (sort_and_permute(g.nPart)) return 1;   // also synchronises
+  end_timing();
+  if (nLost) *nLost = hc[0];
+  if (hc[1] == TRK_ERR_BC) return fail("piclas_gpu_push_track: particle hit a boundary condition that is not supported");
+  if (hc[1] == TRK_ERR_ELEM) return fail("piclas_gpu_push_track: ERROR: Element not defined! Please increase the size of the halo region (HaloEpsVelo)!");
+  if (hc[1] == TRK_ERR_LOOP) return fail("piclas_gpu_push_track: tracking loop did not terminate");
+  return 0;
+}
+
+int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void** devSendBuf) {
+  if (!g.ready) return fail("piclas_gpu_exchange_info: not initialised");
+  if (partCommSize) *partCommSize = 8;  // PartState(1:6), Species, GlobalElemID as REAL (particle_mpi.f90:158-183)
+  for (int r = 0; r < g.nRanks; ++r) nSendPerRank[r] = g.hTailOff[r + 1] - g.hTailOff[r];
+  if (devSendBuf) *devSendBuf = nullptr;
+  return fail("piclas_gpu_exchange_info: multi-rank exchange not implemented yet");
+}
+int piclas_gpu_exchange_recv_buffer(int64_t, void**) { return fail("piclas_gpu_exchange_recv_buffer: not implemented yet"); }
+int piclas_gpu_exchange_finish(int64_t) { return fail("piclas_gpu_exchange_finish: not implemented yet"); }
+
+int piclas_gpu_last_timing(double* ms_kernels, int32_t* nLaunches) {
+  if (ms_kernels) *ms_kernels = g.lastMs;
+  if (nLaunches) *nLaunches = g.lastLaunches;
+  return 0;
+}
+
+}  // extern "C"

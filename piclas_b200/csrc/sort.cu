@@ -1,0 +1,274 @@
+// sort.cu — stable LSD radix sort (8-bit digits), exclusive scan, permutation gathers, segment offsets.
+#include "sort.cuh"
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_NT = 256;              // threads per CTA
+constexpr int SORT_IPT = 16;              // keys per thread
+constexpr int SORT_TILE = SORT_NT * SORT_IPT;
+constexpr int SORT_WARPS = SORT_NT / 32;
+
+__global__ void k_iota(uint32_t* p, size_t n) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+
+// per-tile digit histogram -> blockHist[digit * nBlocks + block]
+__global__ void __launch_bounds__(SORT_NT) k_hist(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t mask,
+                                                  uint32_t* __restrict__ blockHist, uint32_t nBlocks) {
+  __shared__ uint32_t h[RADIX];
+  for (int i = threadIdx.x; i < RADIX; i += SORT_NT) h[i] = 0;
+  __syncthreads();
+  const size_t base = (size_t)blockIdx.x * SORT_TILE;
+#pragma unroll 4
+  for (int r = 0; r < SORT_IPT; ++r) {
+    const size_t i = base + (size_t)r * SORT_NT + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & mask], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < RADIX; i += SORT_NT) blockHist[(size_t)i * nBlocks + blockIdx.x] = h[i];
+}
+
+// stable scatter: rank of a key among equal digits = (#equal digits earlier in memory order)
+__global__ void __launch_bounds__(SORT_NT) k_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ permIn,
+                                                     uint32_t* __restrict__ keysOut, uint32_t* __restrict__ permOut, size_t n,
+                                                     int shift, uint32_t mask, const uint32_t* __restrict__ blockOff,
+                                                     uint32_t nBlocks) {
+  __shared__ uint32_t base[RADIX];                 // running output offset per digit
+  __shared__ uint32_t warpCnt[SORT_WARPS][RADIX];  // per round: count per warp and digit, then exclusive over warps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < RADIX; i += SORT_NT) base[i] = blockOff[(size_t)i * nBlocks + blockIdx.x];
+  const size_t tile = (size_t)blockIdx.x * SORT_TILE;
+  for (int r = 0; r < SORT_IPT; ++r) {
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_NT) (&warpCnt[0][0])[i] = 0;
+    __syncthreads();
+    const size_t i = tile + (size_t)r * SORT_NT + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t key = 0, src = 0, digit = RADIX;  // invalid lanes get a digit outside the table
+    if (valid) {
+      key = keysIn[i];
+      src = permIn[i];
+      digit = (key >> shift) & mask;
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t rankInWarp = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rankInWarp == 0) warpCnt[warp][digit] = __popc(peers);
+    __syncthreads();
+    // exclusive prefix over warps for each digit, advancing the running base (one thread per digit)
+    for (int d = threadIdx.x; d < RADIX; d += SORT_NT) {
+      uint32_t run = base[d];
+#pragma unroll
+      for (int w = 0; w < SORT_WARPS; ++w) {
+        const uint32_t c = warpCnt[w][d];
+        warpCnt[w][d] = run;
+        run += c;
+      }
+      base[d] = run;
+    }
+    __syncthreads();
+    if (valid) {
+      const uint32_t dst = warpCnt[warp][digit] + rankInWarp;
+      keysOut[dst] = key;
+      permOut[dst] = src;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- exclusive scan (3 phases, recursive on the block sums) --------------------------------------------------------
+constexpr int SCAN_NT = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = SCAN_NT * SCAN_IPT;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t ws[SCAN_NT / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) ws[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t s = (lane < SCAN_NT / 32) ? ws[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += t;
+    }
+    if (lane < SCAN_NT / 32) ws[lane] = s;
+  }
+  __syncthreads();
+  const uint32_t warpOff = warp ? ws[warp - 1] : 0;
+  *total = ws[SCAN_NT / 32 - 1];
+  __syncthreads();
+  return warpOff + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_NT) k_scan_reduce(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ sums) {
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_IPT;
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; ++k)
+    if (base + k < n) s += in[base + k];
+  uint32_t tot;
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_NT) k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n,
+                                                        const uint32_t* __restrict__ blockOff) {
+  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_IPT;
+  uint32_t v[SCAN_IPT];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    s += v[k];
+  }
+  uint32_t tot;
+  uint32_t off = block_exclusive_scan(s, &tot) + (blockOff ? blockOff[blockIdx.x] : 0);
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; ++k) {
+    if (base + k < n) out[base + k] = off;
+    off += v[k];
+  }
+}
+
+cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp1, uint32_t* tmp2, cudaStream_t st,
+                           int* nLaunches) {
+  const size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb <= 1) {
+    k_scan_apply<<<1, SCAN_NT, 0, st>>>(in, out, n, nullptr);
+    ++*nLaunches;
+    return cudaGetLastError();
+  }
+  k_scan_reduce<<<(unsigned)nb, SCAN_NT, 0, st>>>(in, n, tmp1);
+  ++*nLaunches;
+  // scan the block sums (in place in tmp1) using tmp2 for the next level
+  const size_t nb2 = (nb + SCAN_TILE - 1) / SCAN_TILE;
+  if (nb2 <= 1) {
+    k_scan_apply<<<1, SCAN_NT, 0, st>>>(tmp1, tmp1, nb, nullptr);
+    ++*nLaunches;
+  } else {
+    k_scan_reduce<<<(unsigned)nb2, SCAN_NT, 0, st>>>(tmp1, nb, tmp2);
+    k_scan_apply<<<1, SCAN_NT, 0, st>>>(tmp2, tmp2, nb2, nullptr);  // nb2 <= SCAN_TILE guaranteed by reserve()
+    k_scan_apply<<<(unsigned)nb2, SCAN_NT, 0, st>>>(tmp1, tmp1, nb, tmp2);
+    *nLaunches += 3;
+  }
+  k_scan_apply<<<(unsigned)nb, SCAN_NT, 0, st>>>(in, out, n, tmp1);
+  ++*nLaunches;
+  return cudaGetLastError();
+}
+
+template <typename T>
+__global__ void k_gather(const T* __restrict__ in, T* __restrict__ out, const uint32_t* __restrict__ perm, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[perm[i]];
+}
+
+__global__ void k_segment_offsets(const uint32_t* __restrict__ keys, size_t n, uint32_t nKeys, int64_t* __restrict__ off) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nKeys) return;
+  size_t lo = 0, hi = n;  // first i with keys[i] >= k
+  while (lo < hi) {
+    const size_t mid = (lo + hi) >> 1;
+    if (keys[mid] < k) lo = mid + 1;
+    else hi = mid;
+  }
+  off[k] = (int64_t)lo;
+}
+
+}  // namespace
+
+cudaError_t sort_workspace_reserve(SortWorkspace& ws, size_t n) {
+  if (n <= ws.capacity && ws.keysA) return cudaSuccess;
+  sort_workspace_free(ws);
+  if (n == 0) n = 1;
+  cudaError_t e;
+  const size_t nBlocks = (n + SORT_TILE - 1) / SORT_TILE;
+  const size_t nh = nBlocks * RADIX;
+  const size_t t1 = (nh + SCAN_TILE - 1) / SCAN_TILE + 1;
+  const size_t t2 = (t1 + SCAN_TILE - 1) / SCAN_TILE + 1;
+  if (t2 > (size_t)SCAN_TILE) return cudaErrorInvalidValue;  // > 2^33 histogram entries: not reachable
+  if ((e = cudaMalloc(&ws.keysA, n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&ws.keysB, n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&ws.permA, n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&ws.permB, n * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&ws.blockHist, nh * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&ws.scanTmp1, t1 * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&ws.scanTmp2, t2 * 4)) != cudaSuccess) return e;
+  ws.capacity = n;
+  ws.histCapacity = nh;
+  ws.tmp1Capacity = t1;
+  ws.tmp2Capacity = t2;
+  return cudaSuccess;
+}
+
+void sort_workspace_free(SortWorkspace& ws) {
+  cudaFree(ws.keysA); cudaFree(ws.keysB); cudaFree(ws.permA); cudaFree(ws.permB);
+  cudaFree(ws.blockHist); cudaFree(ws.scanTmp1); cudaFree(ws.scanTmp2);
+  ws = SortWorkspace();
+}
+
+cudaError_t radix_sort_by_key(SortWorkspace& ws, const uint32_t* keys, size_t n, int bits, cudaStream_t st,
+                              uint32_t** sortedKeys, uint32_t** perm, int* nLaunches) {
+  cudaError_t e;
+  if (n > ws.capacity) return cudaErrorInvalidValue;
+  const uint32_t nBlocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+  if (n == 0) {
+    *sortedKeys = ws.keysA;
+    *perm = ws.permA;
+    return cudaSuccess;
+  }
+  k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.permA, n);
+  ++*nLaunches;
+  const uint32_t* kin = keys;
+  uint32_t* pin = ws.permA;
+  uint32_t* kout = ws.keysB;
+  uint32_t* pout = ws.permB;
+  const int passes = (bits + RADIX_BITS - 1) / RADIX_BITS;
+  for (int p = 0; p < (passes < 1 ? 1 : passes); ++p) {
+    const int shift = p * RADIX_BITS;
+    k_hist<<<nBlocks, SORT_NT, 0, st>>>(kin, n, shift, RADIX - 1, ws.blockHist, nBlocks);
+    ++*nLaunches;
+    if ((e = exclusive_scan(ws.blockHist, ws.blockHist, (size_t)nBlocks * RADIX, ws.scanTmp1, ws.scanTmp2, st, nLaunches)) !=
+        cudaSuccess)
+      return e;
+    k_scatter<<<nBlocks, SORT_NT, 0, st>>>(kin, pin, kout, pout, n, shift, RADIX - 1, ws.blockHist, nBlocks);
+    ++*nLaunches;
+    // ping-pong (first pass read the caller's keys)
+    kin = kout;
+    uint32_t* tp = pin; pin = pout; pout = tp;
+    kout = (kout == ws.keysB) ? ws.keysA : ws.keysB;
+  }
+  *sortedKeys = const_cast<uint32_t*>(kin);
+  *perm = pin;
+  return cudaGetLastError();
+}
+
+cudaError_t gather_f64(const double* in, double* out, const uint32_t* perm, size_t n, cudaStream_t st) {
+  if (n) k_gather<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, perm, n);
+  return cudaGetLastError();
+}
+cudaError_t gather_i32(const int32_t* in, int32_t* out, const uint32_t* perm, size_t n, cudaStream_t st) {
+  if (n) k_gather<int32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, perm, n);
+  return cudaGetLastError();
+}
+cudaError_t gather_u8(const uint8_t* in, uint8_t* out, const uint32_t* perm, size_t n, cudaStream_t st) {
+  if (n) k_gather<uint8_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, perm, n);
+  return cudaGetLastError();
+}
+cudaError_t gather_i64(const int64_t* in, int64_t* out, const uint32_t* perm, size_t n, cudaStream_t st) {
+  if (n) k_gather<int64_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, perm, n);
+  return cudaGetLastError();
+}
+
+cudaError_t segment_offsets(const uint32_t* sortedKeys, size_t n, uint32_t nKeys, int64_t* off, cudaStream_t st) {
+  k_segment_offsets<<<(nKeys + 1 + 255) / 256, 256, 0, st>>>(sortedKeys, n, nKeys, off);
+  return cudaGetLastError();
+}

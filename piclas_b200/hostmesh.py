@@ -1,0 +1,454 @@
+"""Host-side particle-mesh tables for straight-sided (NGeo=1) hexahedral meshes.
+
+In a PICLas run these tables are produced once by the Fortran host
+(`InitParticleMesh`, reference src/particles/particle_mesh/particle_mesh.f90:141-531, and
+`InitializeDeposition`, src/particles/pic/deposition/pic_depo.f90:83-626) and handed to the
+device layer through `piclas_gpu_init` (include/piclas_gpu.h).  This module builds the same
+tables for stand-alone use (tests, bench, oracle) from a conforming hex mesh given as corner
+coordinates + CGNS-ordered element connectivity, which covers every mesh of the five configs
+(`hopr.ini` Corner/nElems boxes).  Memory layout: every array is C-contiguous with the Fortran
+index order reversed, i.e. byte-identical to the Fortran column-major array it mirrors.
+
+Builders restated here (the construction itself stays a host job):
+  ElemInfo/SideInfo incl. SIDE_ELEMID/LOCALID/NBSIDEID  particle_mesh_readin.f90:386-419, piclas.h:149-176
+  ElemNodeID, CGNS corner/side node maps                 mesh/mesh_tools.f90:634-769
+  ElemSideNodeID, ConcaveElemSide                        particle_mesh_tools.f90:1800-1954
+  XCL_NGeo, dXCL_NGeo, XiCL/wBaryCL                      mesh/metrics.f90:250-336
+  ElemBaryNGeo, ElemRadius2NGeo (TriaTracking)           particle_mesh_build.f90:217-302
+  XiEtaZetaBasis, slenXiEtaZetaBasis                     particle_mesh_build.f90:407-433
+  NodeVolume                                             pic_depo_tools.f90:224-355
+  periodic node partners (result of)                     pic_depo.f90:1218-2089
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+import numpy as np
+from scipy.spatial import cKDTree
+
+from . import basis
+
+# piclas.h:204-209
+ZETA_MINUS, ETA_MINUS, XI_PLUS, ETA_PLUS, XI_MINUS, ZETA_PLUS = 1, 2, 3, 4, 5, 6
+# tracking ids piclas.h:357-359
+REFMAPPING, TRACING, TRIATRACKING = 1, 2, 3
+# PartBound%TargetBoundCond values used on this path (particle_boundary_condition.f90:167-214)
+BC_OPEN, BC_REFLECTIVE, BC_PERIODIC = 1, 2, 3
+
+# CGNS corner c (0-based) -> tensor (i,j,k) of the NGeo=1 node block (mesh_tools.f90:742-749)
+_CGNS_IJK = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0],
+                      [0, 0, 1], [1, 0, 1], [1, 1, 1], [0, 1, 1]], dtype=np.int64)
+# tensor-local node number (0-based, i fastest) of CGNS corner c: CNS(:)-1
+_CNS0 = _CGNS_IJK[:, 0] + 2 * _CGNS_IJK[:, 1] + 4 * _CGNS_IJK[:, 2]
+# NodeMapCGNS(1:4, locSide) expressed in 0-based CGNS corner numbers (mesh_tools.f90:761-766)
+_NODEMAP_CGNS0 = np.array([[0, 3, 2, 1],
+                           [0, 1, 5, 4],
+                           [1, 2, 6, 5],
+                           [2, 3, 7, 6],
+                           [0, 4, 7, 3],
+                           [4, 5, 6, 7]], dtype=np.int64)
+
+
+@dataclass
+class ParticleMesh:
+    """All device-layer inputs that describe mesh + basis (see include/piclas_gpu.h: pgpu_mesh_t)."""
+    N: int
+    NGeo: int
+    tracking: int
+    nElems: int
+    nSides: int
+    nNonUniqueNodes: int
+    nUniqueNodes: int
+    ElemInfo: np.ndarray          # (nElems, 8) int32
+    SideInfo: np.ndarray          # (nSides, 8) int32
+    NodeCoords: np.ndarray        # (nNonUniqueNodes, 3) f64
+    NodeInfo: np.ndarray          # (nNonUniqueNodes,) int32, 1-based unique node id
+    ElemNodeID: np.ndarray        # (nElems, 8) int32, 1-based non-unique node index, CGNS order
+    ElemSideNodeID: np.ndarray    # (nElems, 6, 4) int32, 0-based non-unique node index
+    ConcaveElemSide: np.ndarray   # (nElems, 6) int32 (Fortran LOGICAL)
+    XCL_NGeo: np.ndarray          # (nElems, NGeo+1, NGeo+1, NGeo+1, 3)
+    dXCL_NGeo: np.ndarray         # (nElems, NGeo+1, NGeo+1, NGeo+1, 3, 3)  [e,k,j,i,nn,dd]
+    XiCL_NGeo: np.ndarray
+    wBaryCL_NGeo: np.ndarray
+    ElemBaryNGeo: np.ndarray      # (nElems, 3)
+    ElemRadius2NGeo: np.ndarray   # (nElems,)
+    XiEtaZetaBasis: np.ndarray    # (nElems, 6, 3)
+    slenXiEtaZetaBasis: np.ndarray  # (nElems, 6)
+    xGP: np.ndarray
+    wGP: np.ndarray
+    wBary: np.ndarray
+    Elem_xGP: np.ndarray          # (nElems, N+1, N+1, N+1, 3)  [e,k,j,i,:]
+    sJ: np.ndarray                # (nElems, N+1, N+1, N+1)
+    nBCs: int
+    bc_kind: np.ndarray           # (nBCs,) int32  PartBound%TargetBoundCond(MapToPartBC(BCID))
+    bc_alpha: np.ndarray          # (nBCs,) int32  BoundaryType(BCID,BC_ALPHA)
+    PeriodicVectors: np.ndarray   # (nPV, 3)
+    Periodic_nNodes: np.ndarray   # (nUniqueNodes,) int32
+    Periodic_offsetNode: np.ndarray  # (nUniqueNodes,) int32
+    Periodic_Nodes: np.ndarray    # (sum,) int32 1-based unique ids
+    NodeVolume: np.ndarray        # (nUniqueNodes,)
+    xyz_min: np.ndarray
+    xyz_max: np.ndarray
+    unique_coords: np.ndarray     # (nUniqueNodes, 3) convenience (not part of the reference tables)
+    elem_nodes: np.ndarray        # (nElems, 8) 0-based unique ids, CGNS order (convenience)
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def nPeriodicVectors(self) -> int:
+        return int(self.PeriodicVectors.shape[0])
+
+
+def _det3(a):
+    """getDet (eval_xyz.f90:448-468) on arrays a[...,r,c]."""
+    return ((a[..., 0, 0] * a[..., 1, 1] - a[..., 0, 1] * a[..., 1, 0]) * a[..., 2, 2]
+            + (a[..., 0, 1] * a[..., 1, 2] - a[..., 0, 2] * a[..., 1, 1]) * a[..., 2, 0]
+            + (a[..., 0, 2] * a[..., 1, 0] - a[..., 0, 0] * a[..., 1, 2]) * a[..., 2, 1])
+
+
+def build_mesh(coords, elem_nodes, N, bcs, bc_of_face, periodic_vectors=(),
+               tracking=TRIATRACKING) -> ParticleMesh:
+    """Build all particle-mesh tables.
+
+    coords        (nU,3) unique node coordinates
+    elem_nodes    (nE,8) 0-based unique node ids per element in CGNS corner order
+    bcs           list of (kind, alpha): kind in {BC_OPEN, BC_REFLECTIVE, BC_PERIODIC},
+                  alpha = signed 1-based periodic-vector id (BoundaryType(:,BC_ALPHA)), 0 otherwise
+    bc_of_face    callable(centroids (m,3), face_node_ids (m,4)) -> (m,) 1-based BCID of every unmatched face
+    """
+    coords = np.ascontiguousarray(coords, dtype=np.float64)
+    elem_nodes = np.ascontiguousarray(elem_nodes, dtype=np.int64)
+    nE = elem_nodes.shape[0]
+    nU = coords.shape[0]
+    nS = 6 * nE
+    PV = np.ascontiguousarray(np.asarray(periodic_vectors, dtype=np.float64).reshape(-1, 3))
+    bc_kind = np.array([b[0] for b in bcs], dtype=np.int32)
+    bc_alpha = np.array([b[1] for b in bcs], dtype=np.int32)
+
+    # ---- per-element node block in tensor order (HOPR NodeCoords of an NGeo=1 hex) -------------------
+    Xc = coords[elem_nodes]                                   # (nE, 8 cgns, 3)
+    NodeCoords = np.empty((nE, 8, 3))
+    NodeCoords[:, _CNS0, :] = Xc
+    NodeInfo = np.empty((nE, 8), dtype=np.int32)
+    NodeInfo[:, _CNS0] = (elem_nodes + 1).astype(np.int32)
+    first_node = 8 * np.arange(nE, dtype=np.int64)
+    ElemNodeID = (first_node[:, None] + (_CNS0[None, :] + 1)).astype(np.int32)
+
+    ElemInfo = np.zeros((nE, 8), dtype=np.int32)
+    ElemInfo[:, 0] = 108
+    ElemInfo[:, 1] = 1
+    ElemInfo[:, 2] = 6 * np.arange(nE)
+    ElemInfo[:, 3] = 6 * (np.arange(nE) + 1)
+    ElemInfo[:, 4] = first_node
+    ElemInfo[:, 5] = first_node + 8
+    ElemInfo[:, 6] = 0      # ELEM_RANK (filled by partition())
+    ElemInfo[:, 7] = 1      # ELEM_HALOFLAG
+
+    # ---- face connectivity ---------------------------------------------------------------------------
+    face_nodes = elem_nodes[:, _NODEMAP_CGNS0]                # (nE, 6, 4) unique ids in NodeMap order
+    fn = face_nodes.reshape(nS, 4)
+    key = np.sort(fn, axis=1)
+    order = np.lexsort((key[:, 3], key[:, 2], key[:, 1], key[:, 0]))
+    ks = key[order]
+    same = np.all(ks[1:] == ks[:-1], axis=1)
+    partner = np.full(nS, -1, dtype=np.int64)
+    ia = order[:-1][same]
+    ib = order[1:][same]
+    partner[ia] = ib
+    partner[ib] = ia
+    if np.any(same[1:] & same[:-1]):
+        raise ValueError("non-manifold mesh: a face is shared by more than two elements")
+
+    bcid = np.zeros(nS, dtype=np.int32)
+    bnd = np.nonzero(partner < 0)[0]
+    centroid = coords[fn].mean(axis=1)
+    if bnd.size:
+        bcid[bnd] = np.asarray(bc_of_face(centroid[bnd], fn[bnd]), dtype=np.int32)
+        if np.any(bcid[bnd] < 1) or np.any(bcid[bnd] > len(bcs)):
+            raise ValueError("bc_of_face returned an invalid BCID")
+    # periodic pairing of boundary faces by shifted centroid
+    shift = np.zeros((nS, 3))
+    per = bnd[bc_kind[bcid[bnd] - 1] == BC_PERIODIC] if bnd.size else bnd
+    if per.size:
+        a = bc_alpha[bcid[per] - 1]
+        shift[per] = np.sign(a)[:, None] * PV[np.abs(a) - 1]
+        tree = cKDTree(centroid[per])
+        ext = np.linalg.norm(coords.max(axis=0) - coords.min(axis=0))
+        d, j = tree.query(centroid[per] + shift[per])
+        if np.any(d > 1e-8 * ext):
+            raise ValueError("periodic face without partner")
+        tgt = per[j]
+        if np.any(bc_alpha[bcid[tgt] - 1] != -a):
+            raise ValueError("periodic partner has inconsistent BC_ALPHA")
+        partner[per] = tgt
+
+    # master / slave, unique side ids, flip
+    sidx = np.arange(nS)
+    has_nb = partner >= 0
+    is_master = (~has_nb) | (sidx <= partner)
+    side_uid = np.zeros(nS, dtype=np.int64)
+    masters = np.nonzero(is_master)[0]
+    side_uid[masters] = np.arange(1, masters.size + 1)
+    slaves = np.nonzero(~is_master)[0]
+    side_uid[slaves] = -side_uid[partner[slaves]]
+    flip = np.zeros(nS, dtype=np.int64)
+    if slaves.size:
+        m = partner[slaves]
+        p_first = coords[fn[m, 0]] + shift[m]                 # master's first node seen from the slave side
+        ps = coords[fn[slaves]]                               # (ns, 4, 3)
+        dist = np.linalg.norm(ps - p_first[:, None, :], axis=2)
+        flip[slaves] = np.argmin(dist, axis=1) + 1
+    loc_side = (sidx % 6) + 1
+    nb_loc = np.where(has_nb, (partner % 6) + 1, 0)
+
+    SideInfo = np.zeros((nS, 8), dtype=np.int32)
+    SideInfo[:, 0] = 4                                         # SIDE_TYPE (<=100: not a mortar)
+    SideInfo[:, 1] = side_uid                                  # SIDE_ID
+    SideInfo[:, 2] = np.where(has_nb, partner // 6 + 1, 0)     # SIDE_NBELEMID
+    SideInfo[:, 3] = 10 * nb_loc + flip                        # SIDE_FLIP
+    SideInfo[:, 4] = bcid                                      # SIDE_BCID
+    SideInfo[:, 5] = sidx // 6 + 1                             # SIDE_ELEMID
+    SideInfo[:, 6] = loc_side                                  # SIDE_LOCALID
+    # SIDE_NBSIDEID: first side of the neighbour element with the same |SIDE_ID| (readin.f90:399-411)
+    nbside = np.zeros(nS, dtype=np.int64)
+    if has_nb.any():
+        h = np.nonzero(has_nb)[0]
+        nbe = partner[h] // 6
+        cand = np.abs(side_uid.reshape(nE, 6)[nbe])           # (nh, 6)
+        hit = cand == np.abs(side_uid[h])[:, None]
+        nbside[h] = 6 * nbe + np.argmax(hit, axis=1) + 1       # 1-based SideInfo index
+    SideInfo[:, 7] = nbside
+
+    # ---- ElemSideNodeID / ConcaveElemSide --------------------------------------------------------------
+    nstart = np.where(side_uid > 0, 0, np.maximum(0, (SideInfo[:, 3] % 10) - 1)).reshape(nE, 6)
+    rot = (nstart[:, :, None] + np.arange(4)[None, None, :]) % 4            # (nE,6,4)
+    nm_tensor0 = _CNS0[_NODEMAP_CGNS0]                                       # NodeMap(:,side)-1 (tensor local)
+    loc = nm_tensor0[np.arange(6)[None, :, None], rot]                       # (nE,6,4)
+    ElemSideNodeID = (first_node[:, None, None] + loc).astype(np.int32)      # 0-based non-unique index
+    NC = NodeCoords.reshape(nE * 8, 3)
+    P = NC[ElemSideNodeID]                                                   # (nE,6,4,3)
+    A = P[:, :, 0:3, :] - P[:, :, 3:4, :]                                    # A(:,NodeNum) = node - node4
+    # detcon (particle_mesh_tools.f90:1918-1921); A(x,n) -> A[..., n-1, x-1]
+    detcon = ((A[..., 0, 1] * A[..., 1, 2] - A[..., 0, 2] * A[..., 1, 1]) * A[..., 2, 0]
+              + (A[..., 0, 2] * A[..., 1, 0] - A[..., 0, 0] * A[..., 1, 2]) * A[..., 2, 1]
+              + (A[..., 0, 0] * A[..., 1, 1] - A[..., 0, 1] * A[..., 1, 0]) * A[..., 2, 2])
+    gsid = (sidx + 1).reshape(nE, 6)
+    Concave = (detcon < 0) | ((detcon == 0.0) & (gsid < SideInfo[:, 7].reshape(nE, 6)))
+    ConcaveElemSide = Concave.astype(np.int32)
+
+    # ---- geometry for the Newton reference mapping ------------------------------------------------------
+    NGeo = 1
+    XiCL = basis.cheb_gauss_lobatto_nodes(NGeo)
+    wBaryCL = basis.barycentric_weights(XiCL)
+    XCL = np.ascontiguousarray(NodeCoords.reshape(nE, 2, 2, 2, 3))           # [e,k,j,i,:]
+    D = basis.poly_derivative_matrix(XiCL)
+    dXCL = np.zeros((nE, 2, 2, 2, 3, 3))                                     # [e,k,j,i,nn,dd]
+    for k in range(2):
+        for j in range(2):
+            for i in range(2):
+                for ll in range(2):
+                    dXCL[:, k, j, i, :, 0] += D[i, ll] * XCL[:, k, j, ll, :]
+                    dXCL[:, k, j, i, :, 1] += D[j, ll] * XCL[:, k, ll, i, :]
+                    dXCL[:, k, j, i, :, 2] += D[k, ll] * XCL[:, ll, j, i, :]
+
+    if tracking == TRIATRACKING:
+        # BuildElementRadiusTria (particle_mesh_build.f90:286-301): mean of the first 8 element nodes
+        xs = np.zeros((nE, 3))
+        for n in range(8):
+            xs = xs + NodeCoords[:, n, :]
+        Bary = xs / 8.0
+        rad = np.zeros(nE)
+        for n in range(8):
+            v = NodeCoords[:, n, :] - Bary
+            rad = np.maximum(rad, np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2]))
+        Radius2 = rad * rad
+    else:
+        # BuildElementOriginShared (particle_mesh_build.f90:1387-1470): X(xi=0)
+        L0 = basis.lagrange_polys(0.0, XiCL, wBaryCL)
+        Bary = np.zeros((nE, 3))
+        for k in range(2):
+            for j in range(2):
+                for i in range(2):
+                    Bary = Bary + XCL[:, k, j, i, :] * L0[i] * L0[j] * L0[k]
+        rad = np.zeros(nE)
+        for k in range(2):
+            for j in range(2):
+                for i in range(2):
+                    v = XCL[:, k, j, i, :] - Bary
+                    rad = np.maximum(rad, np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2]))
+        Radius2 = rad * rad
+
+    XiDirs = np.array([[1., 0., 0.], [0., 1., 0.], [0., 0., 1.],
+                       [-1., 0., 0.], [0., -1., 0.], [0., 0., -1.]])
+    XEZ = np.zeros((nE, 6, 3))
+    slen = np.zeros((nE, 6))
+    for d in range(6):
+        Lg = [basis.lagrange_polys(XiDirs[d, c], XiCL, wBaryCL) for c in range(3)]
+        xPos = np.zeros((nE, 3))
+        for k in range(2):
+            for j in range(2):
+                for i in range(2):
+                    xPos = xPos + XCL[:, k, j, i, :] * Lg[0][i] * Lg[1][j] * Lg[2][k]
+        XEZ[:, d, :] = xPos - Bary
+        slen[:, d] = 1.0 / (XEZ[:, d, 0] * XEZ[:, d, 0] + XEZ[:, d, 1] * XEZ[:, d, 1] + XEZ[:, d, 2] * XEZ[:, d, 2])
+
+    # ---- solution basis, Gauss-point coordinates, inverse Jacobian ----------------------------------------
+    xGP, wGP = basis.legendre_gauss_nodes_weights(N)
+    wBary = basis.barycentric_weights(xGP)
+    LG = np.array([basis.lagrange_polys(x, XiCL, wBaryCL) for x in xGP])    # (N+1, 2)
+    # trilinear blend weights of the 8 CL corners at every Gauss point: W[(k,j,i), (kc,jc,ic)]
+    W = (LG[:, None, None, :, None, None] * LG[None, :, None, None, :, None]
+         * LG[None, None, :, None, None, :]).reshape((N + 1) ** 3, 8)
+    Elem_xGP = np.einsum("qc,ecx->eqx", W, XCL.reshape(nE, 8, 3), optimize=True).reshape(nE, N + 1, N + 1, N + 1, 3)
+    Jac = np.einsum("qc,ecx->eqx", W, dXCL.reshape(nE, 8, 9), optimize=True).reshape(nE, N + 1, N + 1, N + 1, 3, 3)
+    detJ = _det3(Jac)
+    if np.any(detJ <= 0):
+        raise ValueError("mesh has elements with non-positive Jacobian")
+    sJ = 1.0 / detJ
+
+    # ---- periodic node partners (CSR, 1-based) ---------------------------------------------------------------
+    Periodic_nNodes = np.zeros(nU, dtype=np.int32)
+    Periodic_offset = np.zeros(nU, dtype=np.int32)
+    Periodic_Nodes = np.zeros(0, dtype=np.int32)
+    nPV = PV.shape[0]
+    if nPV > 0:
+        cand = np.unique(fn[per]) if per.size else np.zeros(0, dtype=np.int64)   # only BC nodes have images
+        tree = cKDTree(coords[cand]) if cand.size else None
+        ext = np.linalg.norm(coords.max(axis=0) - coords.min(axis=0))
+        rows, cols = [np.zeros(0, dtype=np.int64)], [np.zeros(0, dtype=np.int64)]
+        import itertools
+        for s in itertools.product((-1, 0, 1), repeat=nPV):
+            if not any(s):
+                continue
+            sh = np.zeros(3)
+            for c, sv in zip(s, PV):
+                sh = sh + c * sv
+            if tree is None:
+                break
+            d, j = tree.query(coords[cand] + sh)
+            ok = d <= 1e-8 * ext
+            rows.append(cand[ok])
+            cols.append(cand[j[ok]])
+        rows = np.concatenate(rows)
+        cols = np.concatenate(cols)
+        o = np.lexsort((cols, rows))
+        rows, cols = rows[o], cols[o]
+        Periodic_nNodes = np.bincount(rows, minlength=nU).astype(np.int32)
+        Periodic_offset = (np.cumsum(Periodic_nNodes) - Periodic_nNodes).astype(np.int32)
+        Periodic_Nodes = (cols + 1).astype(np.int32)
+
+    # ---- NodeVolume (pic_depo_tools.f90:282-338) -----------------------------------------------------------------
+    NodeVolume = np.zeros(nU)
+    uid = NodeInfo[np.arange(nE)[:, None], _CNS0[None, :]].astype(np.int64) - 1     # (nE, 8 cgns)
+    sgn = 2.0 * _CGNS_IJK - 1.0                                                       # (8,3) +-1
+    F = np.zeros((N + 1, N + 1, N + 1, 8))                                            # [k,j,i,c]
+    for k in range(N + 1):
+        for j in range(N + 1):
+            for i in range(N + 1):
+                for c in range(8):
+                    F[k, j, i, c] = ((1. + sgn[c, 0] * xGP[i]) * (1. + sgn[c, 1] * xGP[j]) * (1. + sgn[c, 2] * xGP[k])
+                                     * wGP[i] * wGP[j] * wGP[k] / 8.)
+    vol_ec = (1.0 / sJ).reshape(nE, -1) @ F.reshape(-1, 8)                             # (nE, 8)
+    for c in range(8):
+        NodeVolume += np.bincount(uid[:, c], weights=vol_ec[:, c], minlength=nU)
+    if nPV > 0 and Periodic_Nodes.size:
+        add = np.zeros(nU)
+        src = np.repeat(np.arange(nU), Periodic_nNodes)
+        add = np.bincount(src, weights=NodeVolume[Periodic_Nodes - 1], minlength=nU)
+        NodeVolume = NodeVolume + add
+
+    return ParticleMesh(
+        N=N, NGeo=NGeo, tracking=tracking, nElems=nE, nSides=nS, nNonUniqueNodes=8 * nE, nUniqueNodes=nU,
+        ElemInfo=ElemInfo, SideInfo=SideInfo, NodeCoords=np.ascontiguousarray(NC),
+        NodeInfo=np.ascontiguousarray(NodeInfo.reshape(-1)), ElemNodeID=np.ascontiguousarray(ElemNodeID),
+        ElemSideNodeID=np.ascontiguousarray(ElemSideNodeID), ConcaveElemSide=np.ascontiguousarray(ConcaveElemSide),
+        XCL_NGeo=XCL, dXCL_NGeo=np.ascontiguousarray(dXCL), XiCL_NGeo=XiCL, wBaryCL_NGeo=wBaryCL,
+        ElemBaryNGeo=np.ascontiguousarray(Bary), ElemRadius2NGeo=np.ascontiguousarray(Radius2),
+        XiEtaZetaBasis=np.ascontiguousarray(XEZ), slenXiEtaZetaBasis=np.ascontiguousarray(slen),
+        xGP=xGP, wGP=wGP, wBary=wBary, Elem_xGP=np.ascontiguousarray(Elem_xGP), sJ=np.ascontiguousarray(sJ),
+        nBCs=len(bcs), bc_kind=bc_kind, bc_alpha=bc_alpha, PeriodicVectors=PV,
+        Periodic_nNodes=Periodic_nNodes, Periodic_offsetNode=Periodic_offset, Periodic_Nodes=Periodic_Nodes,
+        NodeVolume=NodeVolume, xyz_min=coords.min(axis=0), xyz_max=coords.max(axis=0),
+        unique_coords=coords, elem_nodes=elem_nodes.astype(np.int32))
+
+
+def structured_connectivity(nx, ny, nz):
+    """Unique-node ids (0-based, x fastest) of every element of an nx*ny*nz block, CGNS corner order."""
+    i, j, k = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    i = i.transpose(2, 1, 0).reshape(-1)   # element order: i fastest, then j, then k
+    j = j.transpose(2, 1, 0).reshape(-1)
+    k = k.transpose(2, 1, 0).reshape(-1)
+    en = np.empty((nx * ny * nz, 8), dtype=np.int64)
+    for c in range(8):
+        a, b, cc = _CGNS_IJK[c]
+        en[:, c] = (i + a) + (nx + 1) * ((j + b) + (ny + 1) * (k + cc))
+    return en
+
+
+def box_mesh(xmin, xmax, nelems, N, periodic=(True, True, True), wall_kind=BC_OPEN,
+             tracking=TRIATRACKING, deform=None) -> ParticleMesh:
+    """Cartesian hopr-style box (`Corner` = box, `nElems` = nelems), optionally deformed.
+
+    periodic[d]   periodic in direction d (BC pair with BC_ALPHA = +-(index of its periodic vector))
+    deform        optional callable(coords (n,3)) -> coords, applied to the unique grid nodes
+                  (must keep opposite periodic faces congruent)
+    BCIDs: 1..6 = x-, x+, y-, y+, z-, z+.
+    """
+    xmin = np.asarray(xmin, dtype=np.float64)
+    xmax = np.asarray(xmax, dtype=np.float64)
+    nx, ny, nz = (int(v) for v in nelems)
+    gx = xmin[0] + (xmax[0] - xmin[0]) * (np.arange(nx + 1) / nx)
+    gy = xmin[1] + (xmax[1] - xmin[1]) * (np.arange(ny + 1) / ny)
+    gz = xmin[2] + (xmax[2] - xmin[2]) * (np.arange(nz + 1) / nz)
+    gx[-1], gy[-1], gz[-1] = xmax
+    Z, Y, X = np.meshgrid(gz, gy, gx, indexing="ij")
+    coords = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], axis=1)
+    ideal = coords.copy()
+    if deform is not None:
+        coords = np.asarray(deform(coords), dtype=np.float64)
+    en = structured_connectivity(nx, ny, nz)
+
+    pvs, bcs = [], []
+    L = xmax - xmin
+    for d in range(3):
+        if periodic[d]:
+            v = np.zeros(3)
+            v[d] = L[d]
+            pvs.append(v)
+            pid = len(pvs)
+            bcs += [(BC_PERIODIC, pid), (BC_PERIODIC, -pid)]
+        else:
+            bcs += [(wall_kind, 0), (wall_kind, 0)]
+
+    # boundary faces are identified on the undeformed grid
+    tol = 1e-9 * np.linalg.norm(L)
+
+    def bc_of_face(cent, face_ids):
+        ic = ideal[face_ids].mean(axis=1)
+        out = np.zeros(cent.shape[0], dtype=np.int32)
+        for d in range(3):
+            out[np.abs(ic[:, d] - xmin[d]) <= tol] = 2 * d + 1
+            out[np.abs(ic[:, d] - xmax[d]) <= tol] = 2 * d + 2
+        return out
+
+    m = build_mesh(coords, en, N, bcs, bc_of_face, periodic_vectors=pvs, tracking=tracking)
+    m.extra.update(dict(nelems=(nx, ny, nz), box=(xmin.copy(), xmax.copy()), cartesian=deform is None))
+    return m
+
+
+def cartesian_locate(mesh: ParticleMesh, pos):
+    """1-based global element id of points in an undeformed box_mesh (harness helper)."""
+    nx, ny, nz = mesh.extra["nelems"]
+    xmin, xmax = mesh.extra["box"]
+    h = (xmax - xmin) / np.array([nx, ny, nz])
+    ijk = np.floor((pos - xmin) / h).astype(np.int64)
+    ijk = np.clip(ijk, 0, np.array([nx, ny, nz]) - 1)
+    return (1 + ijk[:, 0] + nx * (ijk[:, 1] + ny * ijk[:, 2])).astype(np.int32)
+
+
+def partition(mesh: ParticleMesh, nprocs: int):
+    """Equal split of the element range (loadbalance/loaddistribution.f90:362-369); fills ELEM_RANK."""
+    nG = mesh.nElems
+    off = np.array([(nG // nprocs) * p + min(p, nG % nprocs) for p in range(nprocs + 1)], dtype=np.int64)
+    off[nprocs] = nG
+    rank = np.searchsorted(off, np.arange(nG), side="right") - 1
+    mesh.ElemInfo[:, 6] = rank.astype(np.int32)
+    return off

@@ -1,0 +1,83 @@
+"""Seeded synthetic cases shared by the CPU and GPU tests (shapes follow BASELINE.json `configs`)."""
+from __future__ import annotations
+
+import numpy as np
+
+from piclas_b200 import hostmesh as hm
+from piclas_b200.abi import Params, DEPO_CVWM, TIMEDISC_BORIS_LEAPFROG, TIMEDISC_LEAPFROG
+
+QE = 1.60217653e-19
+ME = 9.1093826e-31
+
+
+def sphere_points(rng, n, r):
+    pts = np.zeros((0, 3))
+    while pts.shape[0] < n:
+        q = rng.uniform(-r, r, (2 * n, 3))
+        q = q[(q * q).sum(axis=1) <= r * r]
+        pts = np.concatenate([pts, q])
+    return pts[:n].copy()
+
+
+def plasma_ball_cvwm():
+    """regressioncheck/NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean: 10^3 box [-1,1]^3, N=1, TriaTracking, CVWM,
+    3333 particles in a sphere r=0.5, q=1.60217653e-5, MPF=200 (parameter.ini, hopr.ini)."""
+    mesh = hm.box_mesh([-1, -1, -1], [1, 1, 1], (10, 10, 10), 1)
+    prm = Params(ChargeIC=(1.60217653e-5, -QE), MassIC=(1.0, ME), MacroParticleFactor=(200.0, 200.0),
+                 DepositionType=DEPO_CVWM, carryParticleIDs=1)
+    rng = np.random.default_rng(20261017)
+    x = sphere_points(rng, 3333, 0.5)
+    PS = np.zeros((3333, 6))
+    PS[:, :3] = x
+    return mesh, prm, PS, np.ones(3333, dtype=np.int32), hm.cartesian_locate(mesh, x)
+
+
+def smooth_field(mesh, amp=1.0):
+    """Smooth analytic E sampled at the Gauss points, [nElems,k,j,i,3]."""
+    X = mesh.Elem_xGP
+    lo, hi = mesh.xyz_min, mesh.xyz_max
+    L = hi - lo
+    s = 2 * np.pi * (X - lo) / L
+    E = np.zeros(X.shape)
+    E[..., 0] = amp * np.sin(s[..., 0]) * np.cos(s[..., 1])
+    E[..., 1] = amp * 0.5 * np.cos(s[..., 1] + 0.3) * np.sin(s[..., 2])
+    E[..., 2] = amp * 0.25 * np.sin(s[..., 2] + s[..., 0])
+    return np.ascontiguousarray(E)
+
+
+def wavy(amplitude, lo, hi):
+    """Smooth deformation that vanishes on the box boundary (keeps periodic faces congruent, faces become non-planar)."""
+    lo = np.asarray(lo, float)
+    hi = np.asarray(hi, float)
+
+    def f(c):
+        s = np.pi * (c - lo) / (hi - lo)
+        bump = np.sin(s[:, 0]) * np.sin(s[:, 1]) * np.sin(s[:, 2])
+        out = c.copy()
+        out[:, 0] += amplitude * (hi[0] - lo[0]) * bump * np.cos(3 * s[:, 1])
+        out[:, 1] += amplitude * (hi[1] - lo[1]) * bump * np.cos(2 * s[:, 2] + 0.5)
+        out[:, 2] += amplitude * (hi[2] - lo[2]) * bump * np.cos(2 * s[:, 0] + 1.0)
+        return out
+    return f
+
+
+def uniform_plasma(mesh, n, seed, vth_cells=0.2, dt=1.0, species=1, nspecies=1):
+    """Uniform positions, Maxwellian velocities with sigma*dt = vth_cells * h (SURVEY.md §8d synthetic input)."""
+    rng = np.random.default_rng(seed)
+    lo, hi = mesh.xyz_min, mesh.xyz_max
+    x = lo + (hi - lo) * rng.random((n, 3))
+    h = ((hi - lo) / np.array(mesh.extra["nelems"])).min()
+    v = rng.normal(0.0, vth_cells * h / dt, (n, 3))
+    PS = np.ascontiguousarray(np.concatenate([x, v], axis=1))
+    if nspecies > 1:
+        spec = rng.integers(1, nspecies + 1, n).astype(np.int32)
+    else:
+        spec = np.full(n, species, dtype=np.int32)
+    return PS, spec
+
+
+def electron_params(**kw):
+    d = dict(ChargeIC=(-QE,), MassIC=(ME,), MacroParticleFactor=(1.0e3,), DepositionType=DEPO_CVWM,
+             TimeDiscMethod=TIMEDISC_BORIS_LEAPFROG, carryParticleIDs=1)
+    d.update(kw)
+    return Params(**d)

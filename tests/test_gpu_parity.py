@@ -1,0 +1,171 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): element ownership bit-exact; positions, velocities and deposited charge
+within 1e-12 relative in FP64.
+"""
+import numpy as np
+import pytest
+
+import cases
+from oracle_lib import Oracle
+from piclas_b200 import hostmesh as hm
+from piclas_b200.abi import TIMEDISC_LEAPFROG
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def _by_id(d):
+    o = np.argsort(d["ids"], kind="stable")
+    return {k: (v[o] if v is not None else None) for k, v in d.items()}
+
+
+def _rel(a, b, scale=None):
+    s = np.abs(b).max() if scale is None else scale
+    return np.abs(a - b).max() / (s if s > 0 else 1.0)
+
+
+def run_parity(mesh, prm, PS0, spec, elem0, E, dt, nsteps, check_deposit=True):
+    from piclas_b200.particle_step import ParticleStep
+    n = PS0.shape[0]
+    orc = Oracle(mesh, prm)
+    PSo = PS0.copy()
+    elo = elem0.copy()
+    inside = np.ones(n, dtype=np.int32)
+    isnew = np.ones(n, dtype=np.int32)
+    ids = np.arange(n, dtype=np.int64)
+    worst = dict(x=0.0, v=0.0, ns=0.0, ps=0.0)
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(PS0, spec, elem0, IsNewPart=isnew, ids=ids)
+        gpu.SetField(E)
+        for it in range(nsteps):
+            if check_deposit:
+                alive = inside.astype(bool)
+                PSr, NSr = orc.deposit(PSo, spec, elo, inside)
+                PSg, NSg = gpu.Deposition()
+                for c in range(4):
+                    worst["ns"] = max(worst["ns"], _rel(NSg[:, c], NSr[:, c]))
+                    worst["ps"] = max(worst["ps"], _rel(PSg[..., c], PSr[..., c]))
+                assert worst["ns"] <= RTOL and worst["ps"] <= RTOL, (it, worst)
+                assert alive.sum() == gpu.NumParticles()
+            nlo, _, _ = orc.push_track(dt, PSo, spec, elo, inside, isnew, E)
+            nlg = gpu.PushAndTrack(dt, it)
+            assert nlg == nlo
+            d = _by_id(gpu.DownloadParticles())
+            alive = np.nonzero(inside)[0]
+            assert np.array_equal(d["ids"], alive), "surviving particle set differs"
+            assert np.array_equal(d["GlobalElemID"], elo[alive]), "element ownership differs (step %d)" % it
+            worst["x"] = max(worst["x"], _rel(d["PartState"][:, :3], PSo[alive, :3]))
+            worst["v"] = max(worst["v"], _rel(d["PartState"][:, 3:], PSo[alive, 3:]))
+            assert worst["x"] <= RTOL and worst["v"] <= RTOL, (it, worst)
+    orc.close()
+    return worst
+
+
+def test_plasma_ball_cvwm_known_answer():
+    """NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean: deposited charge 10.68010874898 within 5e-13 (analyze.ini)."""
+    from piclas_b200.particle_step import ParticleStep
+    mesh, prm, PS, spec, elem = cases.plasma_ball_cvwm()
+    orc = Oracle(mesh, prm)
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(PS, spec, elem)
+        PSg, NSg = gpu.Deposition()
+    q = orc.deposited_charge(PSg)
+    assert abs(q - 1.06801087489800E+01) <= 5e-13
+    PSr, NSr = orc.deposit(PS, spec, elem, np.ones(len(spec), dtype=np.int32))
+    assert _rel(NSg[:, 3], NSr[:, 3]) <= RTOL
+    assert _rel(PSg[..., 3], PSr[..., 3]) <= RTOL
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5])
+def test_cartesian_box_steps(N):
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (6, 5, 4), N)
+    prm = cases.electron_params()
+    dt = 1e-9
+    PS, spec = cases.uniform_plasma(mesh, 20000, seed=11 + N, vth_cells=0.35, dt=dt)
+    E = cases.smooth_field(mesh, amp=2.0e-3)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    w = run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=6)
+    print("worst rel diffs", w)
+
+
+def test_deformed_box_steps():
+    """Non-planar faces, non-affine elements: concave/convex side logic and a Newton that really iterates."""
+    lo, hi = [-1, -1, -1], [1, 1, 1]
+    mesh = hm.box_mesh(lo, hi, (5, 5, 5), 3, deform=cases.wavy(0.06, lo, hi))
+    prm = cases.electron_params()
+    dt = 1e-9
+    PS, spec = cases.uniform_plasma(mesh, 20000, seed=5, vth_cells=0.3, dt=dt)
+    orc = Oracle(mesh, prm)
+    elem = orc.locate(PS[:, :3])
+    assert (elem > 0).all()
+    orc.close()
+    E = cases.smooth_field(mesh, amp=1.0e-3)
+    w = run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5)
+    print("worst rel diffs", w)
+
+
+def test_tsi_like_leapfrog_thin_mesh():
+    """tutorials/pic-poisson-TSI shape: n x 1 x 1 periodic mesh, N=2, TriaTracking + CVWM, two species, Leapfrog (509)."""
+    mesh = hm.box_mesh([0, 0, 0], [4 * np.pi, 0.03, 0.03], (201, 1, 1), 2)
+    prm = cases.electron_params(TimeDiscMethod=TIMEDISC_LEAPFROG, ChargeIC=(-cases.QE, cases.QE),
+                                MassIC=(cases.ME, 1.6726e-27), MacroParticleFactor=(2.0e6, 2.0e6))
+    rng = np.random.default_rng(3)
+    n = 30000
+    x = mesh.xyz_min + (mesh.xyz_max - mesh.xyz_min) * rng.random((n, 3))
+    v = np.zeros((n, 3))
+    v[:, 0] = np.where(rng.random(n) < 0.5, 1.0, -1.0) * 1.06e7 + rng.normal(0, 1e5, n)
+    v[:, 1:] = rng.normal(0, 2e5, (n, 2))
+    PS = np.ascontiguousarray(np.concatenate([x, v], axis=1))
+    spec = np.where(rng.random(n) < 0.9, 1, 2).astype(np.int32)
+    elem = hm.cartesian_locate(mesh, x)
+    E = cases.smooth_field(mesh, amp=50.0)
+    w = run_parity(mesh, prm, PS, spec, elem, E, 2e-9, nsteps=6)
+    print("worst rel diffs", w)
+
+
+def test_open_boundaries_remove_particles():
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 4, 4), 2, periodic=(False, True, False), wall_kind=hm.BC_OPEN)
+    prm = cases.electron_params()
+    dt = 1e-9
+    PS, spec = cases.uniform_plasma(mesh, 8000, seed=21, vth_cells=0.5, dt=dt)
+    E = cases.smooth_field(mesh, amp=1.0e-3)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5)
+
+
+def test_neutral_species_and_external_field():
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 4, 4), 3)
+    prm = cases.electron_params(ChargeIC=(-cases.QE, 0.0), MassIC=(cases.ME, 6.6e-26), MacroParticleFactor=(10.0, 10.0),
+                                externalField=(1e-3, -2e-3, 5e-4, 0.0, 0.0, 2e-4))
+    dt = 1e-9
+    PS, spec = cases.uniform_plasma(mesh, 8000, seed=8, vth_cells=0.3, dt=dt, nspecies=2)
+    E = cases.smooth_field(mesh, amp=1.0e-3)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    # B != 0: tan() differs between libm and CUDA by <= 2 ulp, still far inside 1e-12
+    run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=4)
+
+
+def test_upload_append_and_empty():
+    from piclas_b200.particle_step import ParticleStep
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (3, 3, 3), 2)
+    prm = cases.electron_params()
+    PS, spec = cases.uniform_plasma(mesh, 1000, seed=2)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.SetField(np.zeros((mesh.nElems, 3, 3, 3, 3)))
+        assert gpu.NumParticles() == 0
+        assert gpu.PushAndTrack(1e-9) == 0          # empty population
+        PSg, NSg = gpu.Deposition()
+        assert not PSg.any() and not NSg.any()
+        inside = np.ones(1000, dtype=np.int32)
+        inside[::7] = 0                              # holes in the host array (PDM%ParticleInside = F)
+        gpu.UploadParticles(PS[:600], spec[:600], elem[:600], ParticleInside=inside[:600], ids=np.arange(600))
+        gpu.UploadParticles(PS[600:], spec[600:], elem[600:], ParticleInside=inside[600:], ids=np.arange(600, 1000), append=True)
+        assert gpu.NumParticles() == inside.sum()
+        d = _by_id(gpu.DownloadParticles())
+        keep = np.nonzero(inside)[0]
+        assert np.array_equal(d["ids"], keep)
+        assert np.array_equal(d["PartState"], PS[keep])
+        assert np.array_equal(d["GlobalElemID"], elem[keep])
