@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the PIC-Poisson particle step (interp + push + track + deposit) on B200.
+
+Workload (BASELINE.json configs[4]): synthetic 3-periodic unit box, 64^3 hexahedra, N=3, NGeo=1,
+5e8 electrons uniform in space, Maxwellian with v_th*dt = 0.2 h, smooth analytic E sampled at the Gauss points,
+B = 0, TriaTracking + cell_volweight_mean, Boris-Leapfrog (508).  One "step" = Deposition() + the particle half of
+TimeStepPoissonByBorisLeapfrog (interpolate, push, track, re-sort by element).
+
+  value     : particle-steps/s with everything resident in HBM (wall clock between device synchronisations)
+  e2e       : same step through the C ABI with HOST buffers: E host->device before the push, PartSource device->host
+              after the deposition, both inside the timed region
+  roofline  : dominant kernel (interpolate+push+track) algorithmic bytes / its CUDA-event time vs measured HBM peak
+  cpu_baseline / --impl reference : the CPU oracle (restated reference path; the Fortran reference cannot be built
+              in this image) on the box's host cores, on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ALG_BYTES_PER_PARTICLE_STEP = 104.0   # read PartState 48 + elem 4, write PartState 48 + elem 4
+QE, ME = 1.60217653e-19, 9.1093826e-31
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nelem", type=int, default=64, help="elements per direction")
+    ap.add_argument("--N", type=int, default=3)
+    ap.add_argument("--particles", type=float, default=5e8, help="total particles (all GPUs)")
+    ap.add_argument("--cpu-particles", type=float, default=4e6, help="particles of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=20261017)
+    return ap.parse_args()
+
+
+def workload(nelem, N):
+    from piclas_b200 import hostmesh as hm
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (nelem, nelem, nelem), N)
+    h = 1.0 / nelem
+    dt = 1.0e-9
+    vth = 0.2 * h / dt
+    # E amplitude: velocity kick per step = 5 % of v_th
+    amp = 0.05 * vth / (QE / ME * dt)
+    X = mesh.Elem_xGP
+    s = 2 * np.pi * X
+    E = np.empty(X.shape)
+    E[..., 0] = amp * np.sin(s[..., 0]) * np.cos(s[..., 1])
+    E[..., 1] = amp * 0.5 * np.cos(s[..., 1] + 0.3) * np.sin(s[..., 2])
+    E[..., 2] = amp * 0.25 * np.sin(s[..., 2] + s[..., 0])
+    return mesh, np.ascontiguousarray(E), dt, vth
+
+
+def gen_particles(rng, n, nelem, vth, lo=(0., 0., 0.), hi=(1., 1., 1.)):
+    lo = np.asarray(lo)
+    hi = np.asarray(hi)
+    x = lo + (hi - lo) * rng.random((n, 3))
+    v = rng.normal(0.0, vth, (n, 3))
+    PS = np.concatenate([x, v], axis=1)
+    ijk = np.minimum((x * nelem).astype(np.int64), nelem - 1)
+    elem = (1 + ijk[:, 0] + nelem * (ijk[:, 1] + nelem * ijk[:, 2])).astype(np.int32)
+    return np.ascontiguousarray(PS), elem
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [a.strip() for a in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "power_w_max": float(max(pw)) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(args, N, threads=None):
+    """Oracle (restated CPU path, -O3) on a bounded sample: same particles/element as the GPU workload."""
+    from oracle_lib import Oracle
+    from piclas_b200.abi import Params
+    threads = threads or (os.cpu_count() or 1)
+    ppe = args.particles / args.nelem ** 3
+    ne = max(2, int(round((args.cpu_particles / ppe) ** (1.0 / 3.0))))
+    mesh, E, dt, vth = workload(ne, N)
+    # scale so that h matches: sample box has ne^3 elements of the unit box -> v_th scaled by the workload() helper
+    n = int(ppe * ne ** 3)
+    rng = np.random.default_rng(args.seed)
+    PS, elem = gen_particles(rng, n, ne, vth)
+    prm = Params(ChargeIC=(-QE,), MassIC=(ME,), MacroParticleFactor=(1.0e3,))
+    orc = Oracle(mesh, prm, fast=True)
+    spec = np.ones(n, dtype=np.int32)
+    inside = np.ones(n, dtype=np.int32)
+    isnew = np.zeros(n, dtype=np.int32)
+    # untimed warm-up step
+    orc.deposit(PS, spec, elem, inside, threads=threads)
+    orc.push_track(dt, PS, spec, elem, inside, isnew, E, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.cpu_steps):
+        orc.deposit(PS, spec, elem, inside, threads=threads)
+        orc.push_track(dt, PS, spec, elem, inside, isnew, E, threads=threads)
+    t = time.perf_counter() - t0
+    orc.close()
+    return {"value": n * args.cpu_steps / t, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+            "sample": "%d^3 elements N=%d, %d particles (%.0f per element, as the GPU workload), %d steps, %.1f s"
+                      % (ne, N, n, ppe, args.cpu_steps, t)}
+
+
+def config_dict(args, n_total):
+    return {"workload": "synthetic 3-periodic box %d^3 hexahedra N=%d NGeo=1, %.3g electrons, TriaTracking + "
+                        "cell_volweight_mean, Boris-Leapfrog (BASELINE.json configs[4])" % (args.nelem, args.N, n_total),
+            "elements": args.nelem ** 3, "N": args.N, "particles": int(n_total),
+            "tracking": "triatracking", "deposition": "cell_volweight_mean", "timedisc": "Boris-Leapfrog (508)",
+            "l2": "inputs (>=26 GB of particle state at full size) exceed the 126 MB L2; no flush needed"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args, args.N)
+    line = {"impl": "reference", "metric": "particle-steps/s (interp+push+track+depo)", "value": cb["value"],
+            "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.cpu_steps, "warmup": 1,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args, args.particles), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "restated CPU path (oracle port, -O3, std::thread); the Fortran/MPI/HDF5 reference cannot be built here"}
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        from piclas_b200.multi import run_bench_multi
+        return run_bench_multi(args, rank, world, local)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the particle step has no CPU fallback")
+    from piclas_b200.abi import Params
+    from piclas_b200.particle_step import ParticleStep
+
+    mesh, E, dt, vth = workload(args.nelem, args.N)
+    n_total = int(args.particles)
+    prm = Params(ChargeIC=(-QE,), MassIC=(ME,), MacroParticleFactor=(1.0e3,), device=local, maxParticleNumber=n_total + 1024)
+    gpu = ParticleStep(mesh, prm)
+    rng = np.random.default_rng(args.seed)
+    chunk = 10_000_000
+    done = 0
+    while done < n_total:
+        m = min(chunk, n_total - done)
+        PS, elem = gen_particles(rng, m, args.nelem, vth)
+        gpu.UploadParticles(PS, np.ones(m, dtype=np.int32), elem, append=done > 0)
+        done += m
+    assert gpu.NumParticles() == n_total
+    gpu.SetField(E)
+
+    def step_resident():
+        gpu.Deposition(want_partsource=False, want_nodesource=False)
+        ph_d = gpu.PhaseTiming().copy()
+        ms_d, nl_d = gpu.LastTiming()
+        lost = gpu.PushAndTrack(dt)
+        ph_p = gpu.PhaseTiming().copy()
+        ms_p, nl_p = gpu.LastTiming()
+        return ms_d + ms_p, nl_d + nl_p, np.array([ph_d[0], ph_d[1], ph_p[2], ph_p[3]]), lost
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev_ms, launches, phases, lost = 0.0, 0, np.zeros(4), 0
+    for _ in range(args.steps):
+        a, b, c, d = step_resident()
+        ev_ms += a; launches += b; phases += c; lost += d
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    n_now = gpu.NumParticles()
+    value = n_total * args.steps / wall
+    phases /= args.steps
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n1 = args.N + 1
+        E_pin = torch.from_numpy(E).pin_memory()
+        PS_pin = torch.empty((mesh.nElems, n1, n1, n1, 4), dtype=torch.float64).pin_memory()
+        E_h, PS_h = E_pin.numpy(), PS_pin.numpy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            gpu.Deposition(out_partsource=PS_h, want_nodesource=False)      # PartSource -> host (HDG input)
+            gpu.SetField(E_h)                                              # E from the host (HDG output)
+            gpu.PushAndTrack(dt)
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        e2e = {"value": n_total * args.e2e_steps / t_e2e, "unit": "particle-steps/s",
+               "h2d_bytes_per_step": int(E_h.nbytes), "d2h_bytes_per_step": int(PS_h.nbytes), "steps": args.e2e_steps,
+               "ms_per_step": 1e3 * t_e2e / args.e2e_steps}
+    gpu.close()
+
+    peak, peak_src = hbm_peak()
+    t_push = phases[2] * 1e-3
+    achieved = ALG_BYTES_PER_PARTICLE_STEP * n_total / t_push / 1e9 if t_push > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_push_track_tria (interpolate+push+track)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": ALG_BYTES_PER_PARTICLE_STEP * n_total, "ms_per_launch": phases[2],
+                "step_frac": (ALG_BYTES_PER_PARTICLE_STEP * n_total * args.steps / wall / 1e9) / peak,
+                "phase_ms": {"deposit_particles": phases[0], "deposit_nodes_dofs": phases[1], "interp_push_track": phases[2],
+                             "sort_permute": phases[3]}}
+    line = {"metric": "particle-steps/s (interp+push+track+depo)", "value": value, "unit": "particle-steps/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, n_total), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "event_ms_per_step": ev_ms / args.steps, "particles_end": int(n_now), "lost": int(lost), "roofline": roofline}
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args, args.N)
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

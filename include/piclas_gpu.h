@@ -192,6 +192,11 @@ int piclas_gpu_deposit_finish(double *PartSource, double *NodeSource);
 
 /* timing of the last call's kernels (ms, CUDA events on the launch stream) and launch count */
 int piclas_gpu_last_timing(double *ms_kernels, int32_t *nLaunches);
+/* CUDA-event durations (ms) of the phases of the most recent deposit / push_track call:
+ * [0] deposition particle kernel, [1] node + DOF kernels, [2] interpolate+push+track kernel, [3] sort + permute.
+ * The replaced code feeds the same sections into LB_DEPO_*, LB_INTERPOLATION+LB_PUSH+LB_TRACK, LB_UNFP
+ * (loadbalance/loadbalance_timers.f90:70-266). */
+int piclas_gpu_phase_timing(double *ms4);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,13 @@
 // elements, grid = a multiple of the SM count), stages that element's geometry / field tile / corner table in shared
 // memory and lets its threads stride over the element's particle segment.  Particle state is SoA FP64, read and
 // written fully coalesced.
+//
+// Structure of the step (r1 profile: one fused kernel was instruction-cache bound — 20k SASS lines, 66 % no_inst
+// stalls, SIMD efficiency 45 %, profiles/r1_v1_push_track_stalls.txt):
+//   k_interp_push   all particles: field evaluation, push, ParticleInsideQuad3D in the own element (the common exit of
+//                   SingleParticleTriaTracking3D).  Particles that left the element are appended to a leaver list.
+//   k_track_leavers one thread per leaver: the element walk of SingleParticleTriaTracking3D on the global tables.
+// Loops that do not need unrolling are kept rolled so that each kernel's hot loop stays inside the instruction caches.
 #pragma once
 #include "math.cuh"
 
@@ -16,27 +23,59 @@ __device__ __forceinline__ void stage_words(void* dst, const void* src, int nbyt
   for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 }
 
-// ---- Newton mapping for all particles of an element + optional CVWM accumulation ------------------------------------------
+// ParticleInsideQuad3D without the determinant output (rolled over the six sides)
+__device__ __forceinline__ bool inside_quad3d_flag(const TriaElem* __restrict__ te, const double x[3]) {
+  bool inElem = true;
+  const unsigned conc = te->concave;
+#pragma unroll 1
+  for (int s = 0; s < 6; ++s) {
+    double A[4][3];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const double* c = te->corner[te->sideNode[s][n]];
+      A[n][0] = c[0] - x[0];
+      A[n][1] = c[1] - x[1];
+      A[n][2] = c[2] - x[2];
+    }
+    const double c0 = A[0][1] * A[2][2] - A[0][2] * A[2][1];
+    const double c1 = A[0][2] * A[2][0] - A[0][0] * A[2][2];
+    const double c2 = A[0][0] * A[2][1] - A[0][1] * A[2][0];
+    double d1 = (c0 * A[1][0] + c1 * A[1][1]) + c2 * A[1][2];
+    d1 = -d1;
+    const double d2 = (c0 * A[3][0] + c1 * A[3][1]) + c2 * A[3][2];
+    const bool neg = (d1 < 0) || (d2 < 0);
+    const bool pos = !(d1 < 0) || !(d2 < 0);
+    if ((conc >> s) & 1u) {
+      if (!pos) inElem = false;
+    } else {
+      if (neg) inElem = false;
+    }
+  }
+  return inElem;
+}
+
+// ---- Newton mapping for all particles of an element + CVWM accumulation -----------------------------------------------------
 // DepositionMethod_CVWM particle loop, pic_depo_method.f90:471-544.  elemAcc[e][node 0..7 (CGNS)][0..3] receives the
 // element-local sums of TSource*weight; xi and the SucRefPos flag are cached for the interpolation of the same step.
-__global__ void __launch_bounds__(STEP_NT) k_deposit_cvwm(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems, int offsetElem,
-                                                          const GeoElem* __restrict__ geo, const TriaElem* __restrict__ tria,
-                                                          double* __restrict__ elemAcc, int* __restrict__ errFlag) {
+// The 32 per-thread accumulators live in shared memory ([a][thread], conflict free) so that the Newton iteration keeps
+// the register file; they are reduced in a fixed order (deterministic, independent of scheduling).
+__global__ void __launch_bounds__(STEP_NT, 4) k_deposit_cvwm(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems,
+                                                             int offsetElem, const GeoElem* __restrict__ geo,
+                                                             const TriaElem* __restrict__ tria, double* __restrict__ elemAcc) {
   __shared__ GeoElem sg;
-  __shared__ TriaElem st;
-  __shared__ double red[STEP_NT / 32][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ double corner[8][3];
+  __shared__ double sAcc[32][STEP_NT];
+  const int tid = threadIdx.x;
   for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
     const int64_t p0 = elemOff[e], p1 = elemOff[e + 1];
-    double acc[32];
 #pragma unroll
-    for (int a = 0; a < 32; ++a) acc[a] = 0.;
+    for (int a = 0; a < 32; ++a) sAcc[a][tid] = 0.;
     if (p1 > p0) {
       __syncthreads();
       stage_words(&sg, geo + (offsetElem + e), sizeof(GeoElem));
-      stage_words(&st, tria + (offsetElem + e), sizeof(TriaElem));
+      if (tid < 24) corner[tid / 3][tid % 3] = tria[offsetElem + e].corner[tid / 3][tid % 3];
       __syncthreads();
-      for (int64_t p = p0 + threadIdx.x; p < p1; p += STEP_NT) {
+      for (int64_t p = p0 + tid; p < p1; p += STEP_NT) {
         const double x[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};
         uint8_t meta = pb.meta[p];
         const int spec = meta & META_SPEC_MASK;
@@ -46,8 +85,8 @@ __global__ void __launch_bounds__(STEP_NT) k_deposit_cvwm(PartBuf pb, const int6
         pb.xi[0][p] = xi[0];
         pb.xi[1][p] = xi[1];
         pb.xi[2][p] = xi[2];
-        meta = suc ? (meta & ~META_XIFAIL) : (meta | META_XIFAIL);
-        pb.meta[p] = meta;
+        const uint8_t nmeta = suc ? (meta & ~META_XIFAIL) : (meta | META_XIFAIL);
+        if (nmeta != meta) pb.meta[p] = nmeta;
         const double q = cst.ChargeIC[spec];
         if (!(fabs(q) > 0.0)) continue;  // isDepositParticle
         const double Charge = q * cst.MPF[spec];
@@ -66,13 +105,13 @@ __global__ void __launch_bounds__(STEP_NT) k_deposit_cvwm(PartBuf pb, const int6
 #pragma unroll
           for (int n = 0; n < 8; ++n)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[n * 4 + c] = acc[n * 4 + c] + (T[c] * w[n]);
+            for (int c = 0; c < 4; ++c) sAcc[n * 4 + c][tid] = sAcc[n * 4 + c][tid] + (T[c] * w[n]);
         } else {
           // inverse-distance fallback, :512-538.  CGNS corner n is tensor node cns[n]
           const int cns[8] = {0, 1, 3, 2, 4, 5, 7, 6};
           bool hit = false;
           for (int n = 0; n < 8 && !hit; ++n) {
-            const double* c = st.corner[cns[n]];
+            const double* c = corner[cns[n]];
             const double d0 = c[0] - x[0], d1 = c[1] - x[1], d2 = c[2] - x[2];
             const double norm = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
             if (norm > 0.) w[n] = 1. / norm;
@@ -82,32 +121,27 @@ __global__ void __launch_bounds__(STEP_NT) k_deposit_cvwm(PartBuf pb, const int6
               hit = true;
             }
           }
-          // after the EXIT the entries behind the hit keep the 0. written by PartDistDepo(:) = 0. (already set above)
           double DistSum = 0.;
           for (int n = 0; n < 8; ++n) DistSum = DistSum + w[n];
           for (int n = 0; n < 8; ++n)
-            for (int c = 0; c < 4; ++c) acc[n * 4 + c] = acc[n * 4 + c] + w[n] / DistSum * T[c];
+            for (int c = 0; c < 4; ++c) sAcc[n * 4 + c][tid] = sAcc[n * 4 + c][tid] + w[n] / DistSum * T[c];
         }
       }
     }
-    // deterministic block reduction of the 32 accumulators (fixed shuffle tree, then warps in order)
+    // deterministic block reduction: accumulator a is summed over threads by warp a/8.. in a fixed tree
     __syncthreads();
+    {
+      const int lane = tid & 31, warp = tid >> 5;  // 4 warps, each reduces 8 accumulators
+#pragma unroll 1
+      for (int a = warp * 8; a < warp * 8 + 8; ++a) {
+        double v = ((sAcc[a][lane] + sAcc[a][lane + 32]) + sAcc[a][lane + 64]) + sAcc[a][lane + 96];
 #pragma unroll
-    for (int a = 0; a < 32; ++a) {
-      double v = acc[a];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) red[warp][a] = v;
+        for (int o = 16; o > 0; o >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) elemAcc[(size_t)e * 32 + a] = v;
+      }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-      double s = red[0][threadIdx.x];
-#pragma unroll
-      for (int w = 1; w < STEP_NT / 32; ++w) s = s + red[w][threadIdx.x];
-      elemAcc[(size_t)e * 32 + threadIdx.x] = s;
-    }
   }
-  (void)errFlag;
 }
 
 // S[n][c] = sum over the (element, corner) pairs adjacent to unique node n, fixed order (ascending element, corner)
@@ -167,16 +201,49 @@ __global__ void k_nodes_to_dofs(const double* __restrict__ NodeSource, const int
   PartSource[t] = v;
 }
 
-// ---- interpolate + push + TriaTracking ---------------------------------------------------------------------------------------
-// timedisc_TimeStepPoissonByBorisLeapfrog.f90:109-211 for the particles of one element per CTA iteration.
-// Writes the new state in place and the sort key of the new owner element.
+// field tile in shared memory: sE[((k*NP + j)*3 + c)*NP + i]  (rows of NP contiguous i-values per component)
 template <int NP>
-__global__ void __launch_bounds__(STEP_NT) k_push_track_tria(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems,
-                                                             int offsetElem, const GeoElem* __restrict__ geo,
-                                                             const TriaElem* __restrict__ tria, const double* __restrict__ E,
-                                                             const double* __restrict__ Elem_xGP, const int32_t* __restrict__ elemRank,
-                                                             uint32_t* __restrict__ keys, double dt, int xiValid,
-                                                             int* __restrict__ counters /*[0]=lost,[1]=error code*/) {
+__device__ __forceinline__ void evaluate_field_tile(const double xi[3], const double* __restrict__ sE, double out[3]) {
+  double L0[NP], L1[NP], L2[NP];
+  lagrange_polys<NP>(xi[0], cst.xGP, cst.wBary, L0);
+  lagrange_polys<NP>(xi[1], cst.xGP, cst.wBary, L1);
+  lagrange_polys<NP>(xi[2], cst.xGP, cst.wBary, L2);
+  double o0 = 0., o1 = 0., o2 = 0.;
+#pragma unroll 1
+  for (int k = 0; k < NP; ++k) {
+    double lz = L2[0];
+#pragma unroll
+    for (int q = 1; q < NP; ++q) lz = (k == q) ? L2[q] : lz;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const double lez = L1[j] * lz;
+      const double* row = sE + ((k * NP + j) * 3) * NP;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) {
+        o0 = fma(row[i] * L0[i], lez, o0);  // U_OUT + U_IN*L_xi(1,i)*L_Eta_Zeta, eval_xyz.f90:207-215
+        o1 = fma(row[NP + i] * L0[i], lez, o1);
+        o2 = fma(row[2 * NP + i] * L0[i], lez, o2);
+      }
+    }
+  }
+  out[0] = o0;
+  out[1] = o1;
+  out[2] = o2;
+}
+
+// ---- interpolate + push + own-element inside test --------------------------------------------------------------------------------
+// timedisc_TimeStepPoissonByBorisLeapfrog.f90:109-198 and the first iteration of SingleParticleTriaTracking3D
+// (particle_triatracking.f90:203-218) for the particles of one element per CTA iteration.
+// Stayers: x, v written in place, key = own element.  Leavers: v written in place, the pushed position goes to xNew
+// (the idle half of the double buffer) while pb.x keeps LastPartPos; their index is appended to leaverIdx.
+template <int NP>
+__global__ void __launch_bounds__(STEP_NT, 4) k_interp_push(PartBuf pb, double* __restrict__ xn0, double* __restrict__ xn1,
+                                                            double* __restrict__ xn2, const int64_t* __restrict__ elemOff, int nElems,
+                                                            int offsetElem, const GeoElem* __restrict__ geo,
+                                                            const TriaElem* __restrict__ tria, const double* __restrict__ E,
+                                                            const double* __restrict__ Elem_xGP, uint32_t* __restrict__ keys,
+                                                            uint32_t* __restrict__ leaverIdx, double dt, int xiValid,
+                                                            int* __restrict__ counters /*[0]=lost,[1]=error,[2]=nLeavers*/) {
   constexpr int ND = NP * NP * NP;
   __shared__ GeoElem sg;
   __shared__ TriaElem st;
@@ -188,15 +255,18 @@ __global__ void __launch_bounds__(STEP_NT) k_push_track_tria(PartBuf pb, const i
     __syncthreads();
     if (!xiValid) stage_words(&sg, geo + (gElem - 1), sizeof(GeoElem));
     stage_words(&st, tria + (gElem - 1), sizeof(TriaElem));
-    for (int i = threadIdx.x; i < ND * 3; i += STEP_NT) sE[i] = __ldg(E + (size_t)e * ND * 3 + i);
+    for (int t = threadIdx.x; t < ND * 3; t += STEP_NT) {
+      const int c = t % 3, node = t / 3;
+      const int i = node % NP, kj = node / NP;
+      sE[(kj * 3 + c) * NP + i] = __ldg(E + (size_t)e * ND * 3 + t);
+    }
     __syncthreads();
     for (int64_t p = p0 + threadIdx.x; p < p1; p += STEP_NT) {
       double x[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};
       double v[3] = {pb.v[0][p], pb.v[1][p], pb.v[2][p]};
-      uint8_t meta = pb.meta[p];
+      const uint8_t meta = pb.meta[p];
       const int spec = meta & META_SPEC_MASK;
       bool isNew = (meta & META_ISNEW) != 0;
-      double lp[3] = {x[0], x[1], x[2]};  // LastPartPos
       double F[6];
 #pragma unroll
       for (int c = 0; c < 6; ++c) F[c] = 0.;
@@ -212,9 +282,9 @@ __global__ void __launch_bounds__(STEP_NT) k_push_track_tria(PartBuf pb, const i
         }
         double f3[3];
         if (!suc && cst.DepositionType == PGPU_DEPO_CVWM)
-          field_inverse_distance<NP>(x, sE, Elem_xGP + (size_t)(gElem - 1) * ND * 3, f3);
+          field_inverse_distance<NP>(x, E + (size_t)e * ND * 3, Elem_xGP + (size_t)(gElem - 1) * ND * 3, f3);
         else
-          evaluate_field<NP>(xi, sE, f3);
+          evaluate_field_tile<NP>(xi, sE, f3);
 #pragma unroll
         for (int c = 0; c < 6; ++c) F[c] = cst.externalField[c];
         F[0] = F[0] + f3[0];
@@ -223,27 +293,50 @@ __global__ void __launch_bounds__(STEP_NT) k_push_track_tria(PartBuf pb, const i
         F[3] = F[3] + 0.; F[4] = F[4] + 0.; F[5] = F[5] + 0.;
       }
       push_particle(x, v, F, spec, isNew, dt);
-      // PerformTracking -> SingleParticleTriaTracking3D
-      int newElem = gElem;
-      double det[6][2];
-      int status = TRK_OK;
-      if (!inside_quad3d(&st, x, det)) status = tria_track_walk(tria, x, lp, newElem, det);
-      uint32_t key;
-      if (status == TRK_OK) {
-        const int rk = elemRank[newElem - 1];
-        key = (rk == cst.myRank) ? (uint32_t)(newElem - 1 - offsetElem) : (uint32_t)(nElems + rk);
-      } else {
-        key = (uint32_t)(nElems + cst.nRanks);  // removed
-        newElem = 0;
-        if (status == TRK_LOST) atomicAdd(&counters[0], 1);
-        else if (status != TRK_REMOVED) atomicMax(&counters[1], status);
-      }
-      pb.x[0][p] = x[0]; pb.x[1][p] = x[1]; pb.x[2][p] = x[2];
       pb.v[0][p] = v[0]; pb.v[1][p] = v[1]; pb.v[2][p] = v[2];
-      pb.elem[p] = newElem;
-      pb.meta[p] = (uint8_t)((meta & META_SPEC_MASK) | (isNew ? META_ISNEW : 0));
-      keys[p] = key;
+      const uint8_t nmeta = (uint8_t)(meta & META_SPEC_MASK);  // IsNewPart and the xi flag are consumed
+      if (nmeta != meta) pb.meta[p] = nmeta;
+      if (inside_quad3d_flag(&st, x)) {
+        pb.x[0][p] = x[0]; pb.x[1][p] = x[1]; pb.x[2][p] = x[2];
+        keys[p] = (uint32_t)e;
+      } else {
+        xn0[p] = x[0]; xn1[p] = x[1]; xn2[p] = x[2];
+        const int slot = atomicAdd(&counters[2], 1);
+        leaverIdx[slot] = (uint32_t)p;
+      }
     }
+  }
+}
+
+// ---- SingleParticleTriaTracking3D for the particles that left their element (particle_triatracking.f90:137-484) --------------------
+__global__ void __launch_bounds__(128) k_track_leavers(PartBuf pb, const double* __restrict__ xn0, const double* __restrict__ xn1,
+                                                       const double* __restrict__ xn2, const uint32_t* __restrict__ leaverIdx,
+                                                       const TriaElem* __restrict__ tria, const int32_t* __restrict__ elemRank,
+                                                       uint32_t* __restrict__ keys, int nElems, int offsetElem,
+                                                       int* __restrict__ counters) {
+  const int nLeavers = counters[2];
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < nLeavers; l += gridDim.x * blockDim.x) {
+    const int64_t p = leaverIdx[l];
+    double x[3] = {xn0[p], xn1[p], xn2[p]};
+    double lp[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};  // LastPartPos
+    int newElem = pb.elem[p];                              // LastGlobalElemID
+    double det[6][2];
+    int status = TRK_OK;
+    // the inside test of the start element is repeated here to recover its determinants (same bits as in k_interp_push)
+    if (!inside_quad3d(tria + (newElem - 1), x, det)) status = tria_track_walk(tria, x, lp, newElem, det);
+    uint32_t key;
+    if (status == TRK_OK) {
+      const int rk = elemRank[newElem - 1];
+      key = (rk == cst.myRank) ? (uint32_t)(newElem - 1 - offsetElem) : (uint32_t)(nElems + rk);
+    } else {
+      key = (uint32_t)(nElems + cst.nRanks);  // removed
+      newElem = 0;
+      if (status == TRK_LOST) atomicAdd(&counters[0], 1);
+      else if (status != TRK_REMOVED) atomicMax(&counters[1], status);
+    }
+    pb.x[0][p] = x[0]; pb.x[1][p] = x[1]; pb.x[2][p] = x[2];
+    pb.elem[p] = newElem;
+    keys[p] = key;
   }
 }
 

@@ -208,7 +208,7 @@ __device__ __forceinline__ int ref_elem_newton(const GeoElem* __restrict__ g, co
 }
 
 // eval_xyz.f90:35-123 GetPositionInRefElem without DoReUseMap
-__device__ __forceinline__ int position_in_ref_elem(const GeoElem* __restrict__ g, const double x[3], double xi[3], bool forceMode,
+__device__ __noinline__ int position_in_ref_elem(const GeoElem* __restrict__ g, const double x[3], double xi[3], bool forceMode,
                                                     bool hasSuccess) {
   newton_start_value(g, x, xi);
   return ref_elem_newton(g, x, xi, forceMode ? 1 : 2, hasSuccess);
@@ -311,21 +311,24 @@ __device__ __forceinline__ void push_particle(double x[3], double v[3], const do
       for (int d = 0; d < 3; ++d) vm[d] = v[d] * gamma + c_1 * F[d];
       const double gamma_minus = sqrt(1 + ((vm[0] * vm[0] + vm[1] * vm[1]) + vm[2] * vm[2]) * c2_inv);
       const double Bn = sqrt((F[3] * F[3] + F[4] * F[4]) + F[5] * F[5]);  // VECNORM3D
-      double u[3] = {0., 0., 0.};
-      if (fabs(Bn) > 0.0) {  // UNITVECTOR
-        const double invL = 1. / Bn;
-        u[0] = F[3] * invL; u[1] = F[4] * invL; u[2] = F[5] * invL;
-      }
-      const double tn = tan(c_1 / gamma_minus * Bn);
+      if (fabs(Bn) > 0.0) {
+        const double invL = 1. / Bn;  // UNITVECTOR
+        const double u[3] = {F[3] * invL, F[4] * invL, F[5] * invL};
+        const double tn = tan(c_1 / gamma_minus * Bn);
 #pragma unroll
-      for (int d = 0; d < 3; ++d) t[d] = tn * u[d];
-      vp[0] = vm[0] + (vm[1] * t[2] - vm[2] * t[1]);
-      vp[1] = vm[1] + (vm[2] * t[0] - vm[0] * t[2]);
-      vp[2] = vm[2] + (vm[0] * t[1] - vm[1] * t[0]);
-      const double fac = 2.0 / (1. + ((t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]));
-      vn[0] = (vm[0] + fac * (vp[1] * t[2] - vp[2] * t[1])) + c_1 * F[0];
-      vn[1] = (vm[1] + fac * (vp[2] * t[0] - vp[0] * t[2])) + c_1 * F[1];
-      vn[2] = (vm[2] + fac * (vp[0] * t[1] - vp[1] * t[0])) + c_1 * F[2];
+        for (int d = 0; d < 3; ++d) t[d] = tn * u[d];
+        vp[0] = vm[0] + (vm[1] * t[2] - vm[2] * t[1]);
+        vp[1] = vm[1] + (vm[2] * t[0] - vm[0] * t[2]);
+        vp[2] = vm[2] + (vm[0] * t[1] - vm[1] * t[0]);
+        const double fac = 2.0 / (1. + ((t[0] * t[0] + t[1] * t[1]) + t[2] * t[2]));
+        vn[0] = (vm[0] + fac * (vp[1] * t[2] - vp[2] * t[1])) + c_1 * F[0];
+        vn[1] = (vm[1] + fac * (vp[2] * t[0] - vp[0] * t[2])) + c_1 * F[1];
+        vn[2] = (vm[2] + fac * (vp[0] * t[1] - vp[1] * t[0])) + c_1 * F[2];
+      } else {
+        // B = 0: UNITVECTOR(0) = 0 and TAN(0) = 0, so t_vec = 0, v_prime = v_plus = v_minus exactly
+#pragma unroll
+        for (int d = 0; d < 3; ++d) vn[d] = vm[d] + c_1 * F[d];
+      }
       const double s = sqrt(1 + ((vn[0] * vn[0] + vn[1] * vn[1]) + vn[2] * vn[2]) * c2_inv);
 #pragma unroll
       for (int d = 0; d < 3; ++d) v[d] = vn[d] / s;
@@ -528,7 +531,6 @@ __device__ __noinline__ int tria_track_walk(const TriaElem* __restrict__ tria, d
     const int gside = te->sideID[side];
     const int bc = te->bcid[side];
     const int oldElem = ElemID;
-    bool clearDone = false;
     if (bc > 0) {
       const int kind = cst.bc_kind[bc - 1];
       if (kind == PGPU_BC_OPEN) return TRK_REMOVED;
@@ -544,7 +546,6 @@ __device__ __noinline__ int tria_track_walk(const TriaElem* __restrict__ tria, d
         x[d] = lp[d] + (len - alpha) * V[d];
       }
       ElemID = te->nbElem[side];
-      (void)clearDone;
     } else {
       ElemID = te->nbElem[side];
     }

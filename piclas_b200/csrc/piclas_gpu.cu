@@ -18,6 +18,8 @@ struct Ctx {
   int device = 0;
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase marks
+  double phaseMs[4] = {0., 0., 0., 0.};  // deposit particle kernel, deposit node/DOF kernels, push+track kernel, sort+permute
   pgpu_params_t prm;
   int nGlobalElems = 0, nElems = 0, offsetElem = 0, N = 0, NP = 0, ND = 0, nNodes = 0, nRanks = 1, myRank = 0;
   int nSMs = 148;
@@ -211,8 +213,13 @@ int sort_and_permute(int64_t nIn) {
 template <int NP>
 void launch_push_track(double dt) {
   const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
-  k_push_track_tria<NP><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dE, g.dElemXGP,
-                                                   g.dElemRank, g.dKeys, dt, g.xiValid ? 1 : 0, g.dCounters);
+  const PartBuf& o = g.buf[g.cur ^ 1];
+  uint32_t* leaverIdx = g.sortws.permB;  // idle until the sort that follows
+  k_interp_push<NP><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem, g.dGeo,
+                                               g.dTria, g.dE, g.dElemXGP, g.dKeys, leaverIdx, dt, g.xiValid ? 1 : 0, g.dCounters);
+  k_track_leavers<<<g.nSMs * 8, 128, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, g.dTria, g.dElemRank, g.dKeys,
+                                                g.nElems, g.offsetElem, g.dCounters);
+  g.lastLaunches += 2;
 }
 template <int NP>
 void launch_dofs() {
@@ -253,6 +260,7 @@ int piclas_gpu_finalize(void) {
   }
   for (int d = 0; d < 3; ++d) cudaFree(g.dXi[d]);
   sort_workspace_free(g.sortws);
+  for (int i = 0; i < 6; ++i) if (g.evp[i]) cudaEventDestroy(g.evp[i]);
   if (g.ev0) cudaEventDestroy(g.ev0);
   if (g.ev1) cudaEventDestroy(g.ev1);
   if (g.st) cudaStreamDestroy(g.st);
@@ -291,6 +299,7 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   CK(cudaStreamCreate(&g.st));
   CK(cudaEventCreate(&g.ev0));
   CK(cudaEventCreate(&g.ev1));
+  for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&g.evp[i]));
   g.prm = *p;
   g.prm.ChargeIC = g.prm.MassIC = g.prm.MacroParticleFactor = nullptr;
   g.nGlobalElems = m->nGlobalElems;
@@ -499,10 +508,12 @@ int piclas_gpu_set_field(const double* E) {
 
 static int deposit_local() {
   const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
+  cudaEventRecord(g.evp[0], g.st);
   if (grid > 0) {
-    k_deposit_cvwm<<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dElemAcc, g.dCounters);
+    k_deposit_cvwm<<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dElemAcc);
     ++g.lastLaunches;
   }
+  cudaEventRecord(g.evp[1], g.st);
   k_node_sum<<<(g.nNodes * 4 + 255) / 256, 256, 0, g.st>>>(g.dAdjOff, g.dAdj, g.dElemAcc, g.dS, g.nNodes);
   ++g.lastLaunches;
   CK(cudaGetLastError());
@@ -527,7 +538,15 @@ static int deposit_finish(double* PartSource, double* NodeSource) {
     ++g.lastLaunches;
   }
   CK(cudaGetLastError());
+  cudaEventRecord(g.evp[2], g.st);
   end_timing();
+  {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, g.evp[0], g.evp[1]);
+    cudaEventElapsedTime(&b, g.evp[1], g.evp[2]);
+    g.phaseMs[0] = a;
+    g.phaseMs[1] = b;
+  }
   if (PartSource) CK(cudaMemcpyAsync(PartSource, g.dPartSource, (size_t)g.nElems * g.ND * 4 * 8, cudaMemcpyDeviceToHost, g.st));
   if (NodeSource) CK(cudaMemcpyAsync(NodeSource, g.dNodeSource, (size_t)g.nNodes * 4 * 8, cudaMemcpyDeviceToHost, g.st));
   CK(cudaStreamSynchronize(g.st));
@@ -573,6 +592,7 @@ int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
   if (g.prm.DoInterpolation && !g.haveField) return fail("piclas_gpu_push_track: no field set (piclas_gpu_set_field)");
   begin_timing();
   CK(cudaMemsetAsync(g.dCounters, 0, 4 * sizeof(int), g.st));
+  cudaEventRecord(g.evp[3], g.st);
   if (g.nPart > 0) {
     switch (g.NP) {
       case 2: launch_push_track<2>(dt); break;
@@ -583,13 +603,21 @@ int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
       case 7: launch_push_track<7>(dt); break;
       case 8: launch_push_track<8>(dt); break;
     }
-    ++g.lastLaunches;
     CK(cudaGetLastError());
   }
+  cudaEventRecord(g.evp[4], g.st);
   int hc[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
   if (sort_and_permute(g.nPart)) return 1;   // also synchronises
+  cudaEventRecord(g.evp[5], g.st);
   end_timing();
+  {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, g.evp[3], g.evp[4]);
+    cudaEventElapsedTime(&b, g.evp[4], g.evp[5]);
+    g.phaseMs[2] = a;
+    g.phaseMs[3] = b;
+  }
   if (nLost) *nLost = hc[0];
   if (hc[1] == TRK_ERR_BC) return fail("piclas_gpu_push_track: particle hit a boundary condition that is not supported");
   if (hc[1] == TRK_ERR_ELEM) return fail("piclas_gpu_push_track: ERROR: Element not defined! Please increase the size of the halo region (HaloEpsVelo)!");
@@ -610,6 +638,11 @@ int piclas_gpu_exchange_finish(int64_t) { return fail("piclas_gpu_exchange_finis
 int piclas_gpu_last_timing(double* ms_kernels, int32_t* nLaunches) {
   if (ms_kernels) *ms_kernels = g.lastMs;
   if (nLaunches) *nLaunches = g.lastLaunches;
+  return 0;
+}
+
+int piclas_gpu_phase_timing(double* ms4) {
+  for (int i = 0; i < 4; ++i) ms4[i] = g.phaseMs[i];
   return 0;
 }
 

@@ -128,6 +128,12 @@ class ParticleStep:
         self.lib.piclas_gpu_last_timing(C.byref(ms), C.byref(nl))
         return ms.value, nl.value
 
+    def PhaseTiming(self):
+        """ms of [deposit particle kernel, node+DOF kernels, interpolate+push+track kernel, sort+permute]."""
+        a = np.zeros(4)
+        self.lib.piclas_gpu_phase_timing(_f(a))
+        return a
+
     # ------------------------------------------------------------------------------------------------------
     def TimeStep(self, dt, field_solver, iter=0):
         """One pass of TimeStepPoissonByBorisLeapfrog with the HDG solve left to `field_solver(PartSource) -> E`."""
