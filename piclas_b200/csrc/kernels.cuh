@@ -23,26 +23,34 @@ __device__ __forceinline__ void stage_words(void* dst, const void* src, int nbyt
   for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 }
 
-// ParticleInsideQuad3D without the determinant output (rolled over the six sides)
-__device__ __forceinline__ bool inside_quad3d_flag(const TriaElem* __restrict__ te, const double x[3]) {
+// determinants of the two triangles of local side s (particle_mesh_tools.f90:187-199)
+__device__ __forceinline__ void side_dets(const TriaElem* __restrict__ te, const double x[3], int s, double& d1, double& d2) {
+  double A[4][3];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const double* c = te->corner[te->sideNode[s][n]];
+    A[n][0] = c[0] - x[0];
+    A[n][1] = c[1] - x[1];
+    A[n][2] = c[2] - x[2];
+  }
+  const double c0 = A[0][1] * A[2][2] - A[0][2] * A[2][1];
+  const double c1 = A[0][2] * A[2][0] - A[0][0] * A[2][2];
+  const double c2 = A[0][0] * A[2][1] - A[0][1] * A[2][0];
+  d1 = (c0 * A[1][0] + c1 * A[1][1]) + c2 * A[1][2];
+  d1 = -d1;
+  d2 = (c0 * A[3][0] + c1 * A[3][1]) + c2 * A[3][2];
+}
+
+// ParticleInsideQuad3D (rolled over the six sides).  Returns InElementCheck; mask bit 2*s+t-1 is set when the
+// determinant of triangle t of local side s+1 is <= 0 (the triangles SingleParticleTriaTracking3D then examines).
+__device__ __forceinline__ bool inside_quad3d_mask(const TriaElem* __restrict__ te, const double x[3], uint32_t& mask) {
   bool inElem = true;
   const unsigned conc = te->concave;
+  uint32_t m = 0;
 #pragma unroll 1
   for (int s = 0; s < 6; ++s) {
-    double A[4][3];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      const double* c = te->corner[te->sideNode[s][n]];
-      A[n][0] = c[0] - x[0];
-      A[n][1] = c[1] - x[1];
-      A[n][2] = c[2] - x[2];
-    }
-    const double c0 = A[0][1] * A[2][2] - A[0][2] * A[2][1];
-    const double c1 = A[0][2] * A[2][0] - A[0][0] * A[2][2];
-    const double c2 = A[0][0] * A[2][1] - A[0][1] * A[2][0];
-    double d1 = (c0 * A[1][0] + c1 * A[1][1]) + c2 * A[1][2];
-    d1 = -d1;
-    const double d2 = (c0 * A[3][0] + c1 * A[3][1]) + c2 * A[3][2];
+    double d1, d2;
+    side_dets(te, x, s, d1, d2);
     const bool neg = (d1 < 0) || (d2 < 0);
     const bool pos = !(d1 < 0) || !(d2 < 0);
     if ((conc >> s) & 1u) {
@@ -50,7 +58,10 @@ __device__ __forceinline__ bool inside_quad3d_flag(const TriaElem* __restrict__ 
     } else {
       if (neg) inElem = false;
     }
+    if (d1 <= 0.0) m |= 1u << (2 * s);
+    if (d2 <= 0.0) m |= 2u << (2 * s);
   }
+  mask = m;
   return inElem;
 }
 
@@ -296,11 +307,13 @@ __global__ void __launch_bounds__(STEP_NT, 4) k_interp_push(PartBuf pb, double* 
       pb.v[0][p] = v[0]; pb.v[1][p] = v[1]; pb.v[2][p] = v[2];
       const uint8_t nmeta = (uint8_t)(meta & META_SPEC_MASK);  // IsNewPart and the xi flag are consumed
       if (nmeta != meta) pb.meta[p] = nmeta;
-      if (inside_quad3d_flag(&st, x)) {
+      uint32_t mask;
+      if (inside_quad3d_mask(&st, x, mask)) {
         pb.x[0][p] = x[0]; pb.x[1][p] = x[1]; pb.x[2][p] = x[2];
         keys[p] = (uint32_t)e;
       } else {
         xn0[p] = x[0]; xn1[p] = x[1]; xn2[p] = x[2];
+        keys[p] = mask;  // handed to k_track_leavers, which overwrites it with the final key
         const int slot = atomicAdd(&counters[2], 1);
         leaverIdx[slot] = (uint32_t)p;
       }
@@ -309,6 +322,8 @@ __global__ void __launch_bounds__(STEP_NT, 4) k_interp_push(PartBuf pb, double* 
 }
 
 // ---- SingleParticleTriaTracking3D for the particles that left their element (particle_triatracking.f90:137-484) --------------------
+// One thread per leaver, element records read from global memory (L2 resident).  All loops are rolled and the candidate
+// triangles are visited through a bit mask so that the lanes of a warp run the same through-side test at the same time.
 __global__ void __launch_bounds__(128) k_track_leavers(PartBuf pb, const double* __restrict__ xn0, const double* __restrict__ xn1,
                                                        const double* __restrict__ xn2, const uint32_t* __restrict__ leaverIdx,
                                                        const TriaElem* __restrict__ tria, const int32_t* __restrict__ elemRank,
@@ -319,12 +334,106 @@ __global__ void __launch_bounds__(128) k_track_leavers(PartBuf pb, const double*
     const int64_t p = leaverIdx[l];
     double x[3] = {xn0[p], xn1[p], xn2[p]};
     double lp[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};  // LastPartPos
-    int newElem = pb.elem[p];                              // LastGlobalElemID
-    double det[6][2];
-    int status = TRK_OK;
-    // the inside test of the start element is repeated here to recover its determinants (same bits as in k_interp_push)
-    if (!inside_quad3d(tria + (newElem - 1), x, det)) status = tria_track_walk(tria, x, lp, newElem, det);
+    int ElemID = pb.elem[p];                               // LastGlobalElemID
+    uint32_t mask = keys[p];                               // det <= 0 triangles of the start element (k_interp_push)
+    int status = TRK_ERR_LOOP;
+    // DoneLastElem(1:4,1:6): last six crossings (element, side id, triangle); entry 0 is the most recent
+    int dE0 = 0, dE1 = 0, dE2 = 0, dE3 = 0, dE4 = 0, dE5 = 0;
+    int dS0 = 0, dS1 = 0, dS2 = 0, dS3 = 0, dS4 = 0, dS5 = 0;
+    int dT0 = 0, dT1 = 0, dT2 = 0, dT3 = 0, dT4 = 0, dT5 = 0;
+#pragma unroll 1
+    for (int guard = 0; guard < 100000; ++guard) {
+      const TriaElem* te = tria + (ElemID - 1);
+      // 2b) crossed triangles among those with det <= 0
+      double V[3] = {x[0] - lp[0], x[1] - lp[1], x[2] - lp[2]};
+      const double len = sqrt((V[0] * V[0] + V[1] * V[1]) + V[2] * V[2]);
+      if (fabs(len) > 0.) {
+        V[0] = V[0] / len; V[1] = V[1] / len; V[2] = V[2] / len;
+      }
+      uint32_t thr = 0;
+      int nThrough = 0;
+      uint32_t cand = mask;
+#pragma unroll 1
+      while (cand) {
+        const int b = __ffs(cand) - 1;
+        cand &= cand - 1;
+        if (through_side_check_fast(te, lp, V, b >> 1, (b & 1) + 1)) {
+          thr |= 1u << b;
+          ++nThrough;
+        }
+      }
+      if (nThrough == 0) { status = TRK_LOST; break; }
+      int side, tri;
+      if (nThrough == 1) {
+        const int b = __ffs(thr) - 1;
+        side = b >> 1;
+        tri = (b & 1) + 1;
+      } else {
+        // several candidate sides: the one crossed first has the largest |det(PartPos)/det(LastPartPos)| (:309-405)
+        int second = 0;
+        double minRatio = 0;
+        side = -1; tri = 0;
+        uint32_t c2 = thr;
+#pragma unroll 1
+        while (c2) {
+          const int b = __ffs(c2) - 1;
+          c2 &= c2 - 1;
+          const int s = b >> 1, t = (b & 1) + 1;
+          const int gs = te->sideID[s];
+          const bool treated = (dE1 == ElemID && dS1 == gs && dT1 == t) || (dE2 == ElemID && dS2 == gs && dT2 == t) ||
+                               (dE3 == ElemID && dS3 == gs && dT3 == t) || (dE4 == ElemID && dS4 == gs && dT4 == t) ||
+                               (dE5 == ElemID && dS5 == gs && dT5 == t);
+          if (treated) continue;
+          double detM;
+          if (!through_side_lastpos_check(te, lp, s, t, detM)) continue;
+          double d1, d2;
+          side_dets(te, x, s, d1, d2);
+          const double dS = (t == 1) ? d1 : d2;
+          if (detM == 0 && dS == 0) continue;
+          if (detM == 0 && minRatio == 0) {
+            ++second; side = s; tri = t;
+          } else {
+            if (detM == 0) continue;
+            const double ratio = dS / detM;
+            if (ratio < minRatio) {
+              minRatio = ratio;
+              ++second; side = s; tri = t;
+            }
+          }
+        }
+        if (second == 0) { status = TRK_LOST; break; }
+      }
+      // 3) boundary interaction or step into the neighbour
+      const int gside = te->sideID[side];
+      const int bc = te->bcid[side];
+      const int oldElem = ElemID;
+      if (bc > 0) {
+        const int kind = cst.bc_kind[bc - 1];
+        if (kind == PGPU_BC_OPEN) { status = TRK_REMOVED; break; }
+        if (kind != PGPU_BC_PERIODIC) { status = TRK_ERR_BC; break; }
+        const double alpha = intersection_with_wall(te, lp, V, side, tri);
+        const int pvid = cst.bc_alpha[bc - 1];  // PeriodicBoundary, particle_boundary_condition.f90:224-284
+        const int pv = (pvid < 0 ? -pvid : pvid) - 1;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          lp[d] = lp[d] + V[d] * alpha;
+          lp[d] = lp[d] + copysign(cst.PeriodicVectors[pv][d], (double)pvid);
+          x[d] = lp[d] + (len - alpha) * V[d];
+        }
+      }
+      ElemID = te->nbElem[side];
+      dE5 = dE4; dS5 = dS4; dT5 = dT4;
+      dE4 = dE3; dS4 = dS3; dT4 = dT3;
+      dE3 = dE2; dS3 = dS2; dT3 = dT2;
+      dE2 = dE1; dS2 = dS1; dT2 = dT1;
+      dE1 = dE0; dS1 = dS0; dT1 = dT0;
+      dE0 = oldElem; dS0 = gside; dT0 = tri;
+      if (ElemID < 1) { status = TRK_ERR_ELEM; break; }
+      // 2a) inside test in the new element
+      if (inside_quad3d_mask(tria + (ElemID - 1), x, mask)) { status = TRK_OK; break; }
+    }
     uint32_t key;
+    int newElem = ElemID;
     if (status == TRK_OK) {
       const int rk = elemRank[newElem - 1];
       key = (rk == cst.myRank) ? (uint32_t)(newElem - 1 - offsetElem) : (uint32_t)(nElems + rk);
