@@ -885,6 +885,25 @@ int oracle_deposit(void* h, int64_t n, const double* PartState, const int32_t* P
   return 0;
 }
 
+// Multi-rank building blocks: the particle loop of DepositionMethod_CVWM without the division (rank-local NodeSource,
+// pic_depo_method.f90:465-544) and the part after the MPI exchange (:692-733).
+int oracle_deposit_raw(void* h, int64_t n, const double* PartState, const int32_t* PartSpecies, const int32_t* GlobalElemID,
+                       const int32_t* ParticleInside, double* NodeSource) {
+  Oracle& o = *(Oracle*)h;
+  if (o.p.DepositionType != PGPU_DEPO_CVWM) { o.err = "deposition type not supported by the oracle yet"; return 4; }
+  std::fill(NodeSource, NodeSource + (size_t)o.m.nUniqueGlobalNodes * 4, 0.0);
+  for (int64_t i = 0; i < n; ++i) {
+    if (!ParticleInside[i]) continue;
+    int rc = depositParticleCVWM(o, PartState + 6 * i, PartSpecies[i], GlobalElemID[i], NodeSource);
+    if (rc) { o.err = "GetPositionInRefElem aborted in deposition"; return rc; }
+  }
+  return 0;
+}
+int oracle_deposit_finish(void* h, double* NodeSource, double* PartSource) {
+  cvwmNodesToDofs(*(Oracle*)h, NodeSource, PartSource);
+  return 0;
+}
+
 // threaded deposition baseline: per-thread NodeSource, summed in thread order (as ranks would, :659-673)
 int oracle_deposit_mt(void* h, int nThreads, int64_t n, const double* PartState, const int32_t* PartSpecies,
                       const int32_t* GlobalElemID, const int32_t* ParticleInside, double* PartSource, double* NodeSource) {

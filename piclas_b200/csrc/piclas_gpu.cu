@@ -53,6 +53,10 @@ struct Ctx {
   int32_t* dStageI = nullptr;
   int64_t* dStageL = nullptr;
   int64_t stageCap = 0;
+  // particle exchange between ranks (AoS messages as particle_mpi.f90:472-502)
+  double *dCommSend = nullptr, *dCommRecv = nullptr;
+  int64_t commSendCap = 0, commRecvCap = 0;
+  int commSize = 8;
   // timing
   double lastMs = 0.;
   int lastLaunches = 0;
@@ -183,6 +187,39 @@ __global__ void k_soa_to_aos(PartBuf pb, int64_t src0, int64_t n, double* __rest
   if (ids) ids[i] = pb.id ? pb.id[p] : -1;
 }
 
+// message layout of one migrating particle (particle_mpi.f90:472-502, TriaTracking, no LSERK/vMPF/DSMC):
+// PartState(1:6), REAL(PartSpecies), REAL(PEM%GlobalElemID) [, particle id bits when ids are carried]
+__global__ void k_pack_emigrants(PartBuf pb, int64_t src0, int64_t n, int cs, double* __restrict__ buf) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = src0 + i;
+  double* b = buf + i * cs;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    b[d] = pb.x[d][p];
+    b[3 + d] = pb.v[d][p];
+  }
+  b[6] = (double)((pb.meta[p] & META_SPEC_MASK) + 1);
+  b[7] = (double)pb.elem[p];
+  if (cs > 8) b[8] = __longlong_as_double(pb.id ? pb.id[p] : -1);
+}
+
+// MPIParticleRecv unpack (particle_mpi.f90:831-989): received particles are appended; IsNewPart = F
+__global__ void k_unpack_immigrants(PartBuf pb, int64_t dst0, int64_t n, int cs, const double* __restrict__ buf) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = dst0 + i;
+  const double* b = buf + i * cs;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    pb.x[d][p] = b[d];
+    pb.v[d][p] = b[3 + d];
+  }
+  pb.meta[p] = (uint8_t)(((int)b[6] - 1) & META_SPEC_MASK);
+  pb.elem[p] = (int)b[7];
+  if (pb.id) pb.id[p] = (cs > 8) ? __double_as_longlong(b[8]) : -1;
+}
+
 // sort the first nIn particles of the current buffer by key (keys already in g.dKeys), gather into the other buffer
 int sort_and_permute(int64_t nIn) {
   uint32_t *sk = nullptr, *perm = nullptr;
@@ -254,6 +291,7 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dNodeVolume); cudaFree(g.dElemAcc); cudaFree(g.dS); cudaFree(g.dNodeSource); cudaFree(g.dPartSource);
   cudaFree(g.dE); cudaFree(g.dElemOff); cudaFree(g.dKeys); cudaFree(g.dCounters);
   cudaFree(g.dStage); cudaFree(g.dStageI); cudaFree(g.dStageL);
+  cudaFree(g.dCommSend); cudaFree(g.dCommRecv);
   if (g.cap > 0) {
     free_partbuf(g.buf[0]);
     free_partbuf(g.buf[1]);
@@ -312,6 +350,7 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   g.nRanks = p->nRanks;
   g.myRank = p->myRank;
   g.carryIDs = p->carryParticleIDs != 0;
+  g.commSize = g.carryIDs ? 9 : 8;
   const int nG = m->nGlobalElems;
 
   // ---- per-element records ------------------------------------------------------------------------------------
@@ -627,13 +666,61 @@ int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
 
 int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void** devSendBuf) {
   if (!g.ready) return fail("piclas_gpu_exchange_info: not initialised");
-  if (partCommSize) *partCommSize = 8;  // PartState(1:6), Species, GlobalElemID as REAL (particle_mpi.f90:158-183)
+  CK(cudaSetDevice(g.device));
+  if (partCommSize) *partCommSize = g.commSize;
   for (int r = 0; r < g.nRanks; ++r) nSendPerRank[r] = g.hTailOff[r + 1] - g.hTailOff[r];
-  if (devSendBuf) *devSendBuf = nullptr;
-  return fail("piclas_gpu_exchange_info: multi-rank exchange not implemented yet");
+  const int64_t nSend = g.nTotalSorted - g.nPart;
+  if (nSendPerRank[g.myRank] != 0) return fail("piclas_gpu_exchange_info: internal error, emigrants addressed to the own rank");
+  if (nSend > g.commSendCap) {
+    cudaFree(g.dCommSend);
+    g.commSendCap = nSend + nSend / 4 + 1024;
+    CK(cudaMalloc((void**)&g.dCommSend, g.commSendCap * g.commSize * 8));
+  }
+  if (nSend > 0) {
+    k_pack_emigrants<<<(unsigned)((nSend + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.nPart, nSend, g.commSize, g.dCommSend);
+    ++g.lastLaunches;
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(g.st));
+  if (devSendBuf) *devSendBuf = g.dCommSend;
+  return 0;
 }
-int piclas_gpu_exchange_recv_buffer(int64_t, void**) { return fail("piclas_gpu_exchange_recv_buffer: not implemented yet"); }
-int piclas_gpu_exchange_finish(int64_t) { return fail("piclas_gpu_exchange_finish: not implemented yet"); }
+
+int piclas_gpu_exchange_recv_buffer(int64_t nRecvTotal, void** devRecvBuf) {
+  if (!g.ready) return fail("piclas_gpu_exchange_recv_buffer: not initialised");
+  CK(cudaSetDevice(g.device));
+  if (nRecvTotal > g.commRecvCap || !g.dCommRecv) {
+    cudaFree(g.dCommRecv);
+    g.commRecvCap = nRecvTotal + nRecvTotal / 4 + 1024;
+    CK(cudaMalloc((void**)&g.dCommRecv, g.commRecvCap * g.commSize * 8));
+  }
+  *devRecvBuf = g.dCommRecv;
+  return 0;
+}
+
+int piclas_gpu_exchange_finish(int64_t nRecvTotal) {
+  if (!g.ready) return fail("piclas_gpu_exchange_finish: not initialised");
+  CK(cudaSetDevice(g.device));
+  const int64_t nEmig = g.nTotalSorted - g.nPart;
+  if (nRecvTotal == 0) {  // nothing arrives: the emigrants behind nPart are simply dropped
+    g.nTotalSorted = g.nPart;
+    for (int r = 0; r <= g.nRanks; ++r) g.hTailOff[r] = g.nPart;
+    return 0;
+  }
+  if (nRecvTotal > g.commRecvCap) return fail("piclas_gpu_exchange_finish: receive buffer too small");
+  if (g.nPart + nRecvTotal >= (int64_t)0x7fffffff) return fail("piclas_gpu_exchange_finish: more than 2^31-1 particles on one GPU");
+  if (reserve_particles(g.nPart + nRecvTotal)) return 1;
+  (void)nEmig;
+  k_unpack_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.nPart, nRecvTotal, g.commSize, g.dCommRecv);
+  const int64_t nIn = g.nPart + nRecvTotal;
+  k_keys_from_elem<<<(unsigned)((nIn + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur].elem, g.dElemRank, g.dKeys, nIn, g.nElems,
+                                                                    g.offsetElem, g.myRank, g.nRanks);
+  g.lastLaunches += 2;
+  CK(cudaGetLastError());
+  if (sort_and_permute(nIn)) return 1;
+  if (g.nTotalSorted != g.nPart) return fail("piclas_gpu_exchange_finish: received particles that belong to another rank");
+  return 0;
+}
 
 int piclas_gpu_last_timing(double* ms_kernels, int32_t* nLaunches) {
   if (ms_kernels) *ms_kernels = g.lastMs;

@@ -1,0 +1,234 @@
+"""Multi-GPU driver of the particle step: one process per GPU, element partition as PICLas' MPI decomposition.
+
+What is exchanged, all through torch.distributed (NCCL on GPUs, gloo in the CPU tests):
+  * particle migration after tracking (reference particle_mpi.f90:202-1024): per-destination counts, then the
+    AoS particle messages (PartCommSize doubles each) with one all-to-all-v;
+  * cell_volweight_mean node halo (pic_depo_method.f90:565-673): the rank-local node sums are added over ranks
+    before the division by NodeVolume.
+The element partition is the reference's equal split of the element range (loadbalance/loaddistribution.f90:362-369),
+written into ElemInfo(ELEM_RANK,:) by hostmesh.partition().
+
+The device work is behind the C ABI (piclas_gpu_exchange_* / piclas_gpu_nodesource_device / piclas_gpu_deposit_finish);
+this module is transport plumbing only and is shared by the CPU (gloo) tests, which drive it with a CPU engine.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import hostmesh as hm
+from .abi import Params
+
+
+class _DevPtr:
+    """Expose a raw device pointer to torch through __cuda_array_interface__ (no copy, no ownership)."""
+
+    def __init__(self, ptr, nelem, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(nelem),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr, nelem, device, typestr="<f8"):
+    if nelem == 0 or not ptr:
+        return torch.empty(0, dtype=torch.float64, device=device)
+    return torch.as_tensor(_DevPtr(ptr, nelem, typestr), device=device)
+
+
+# ---- transport (works for NCCL/cuda tensors and gloo/cpu tensors) -------------------------------------------------------
+def exchange_counts(send_counts, device, group=None):
+    """IRecvNbOfParticles / SendNbOfParticles (particle_mpi.f90:202-342): counts to / from every rank."""
+    world = dist.get_world_size(group)
+    s = torch.tensor(list(send_counts), dtype=torch.int64, device=device)
+    r = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_to_all_single(r, s, group=group)
+    return [int(v) for v in r.tolist()]
+
+
+def exchange_particles(send_buf, send_counts, recv_buf, recv_counts, comm_size, group=None):
+    """MPIParticleSend / MPIParticleRecv (particle_mpi.f90:344-1024): flat double buffers, comm_size doubles/particle."""
+    ins = [int(c) * comm_size for c in send_counts]
+    outs = [int(c) * comm_size for c in recv_counts]
+    dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=outs, input_split_sizes=ins, group=group)
+
+
+def halo_sum(node_tensor, group=None):
+    """cell_volweight_mean node halo (pic_depo_method.f90:565-673) as a sum over all ranks."""
+    dist.all_reduce(node_tensor, op=dist.ReduceOp.SUM, group=group)
+
+
+# ---- the GPU rank --------------------------------------------------------------------------------------------------------
+class ParticleStepRank:
+    """ParticleStep of one rank + the exchanges that follow its operators (GPU, NCCL)."""
+
+    def __init__(self, mesh, params: Params, rank, world, local_rank=0, group=None):
+        from .particle_step import ParticleStep
+        self.rank, self.world, self.group = rank, world, group
+        self.device = torch.device("cuda", local_rank)
+        off = hm.partition(mesh, world)
+        self.offsets = off
+        params.myRank, params.nRanks, params.device = rank, world, local_rank
+        self.step = ParticleStep(mesh, params, offsetElem=int(off[rank]), nElems=int(off[rank + 1] - off[rank]))
+        self.lib = self.step.lib
+        self.mesh = mesh
+        self.migrated = 0
+
+    def close(self):
+        self.step.close()
+
+    def _check(self, rc):
+        self.step._check(rc)
+
+    def exchange(self):
+        world = self.world
+        cs = C.c_int32(0)
+        nsend = (C.c_int64 * world)()
+        sp = C.c_void_p(0)
+        self._check(self.lib.piclas_gpu_exchange_info(C.byref(cs), nsend, C.byref(sp)))
+        send_counts = [int(nsend[r]) for r in range(world)]
+        recv_counts = exchange_counts(send_counts, self.device, self.group)
+        nrecv = sum(recv_counts)
+        rp = C.c_void_p(0)
+        self._check(self.lib.piclas_gpu_exchange_recv_buffer(C.c_int64(nrecv), C.byref(rp)))
+        sbuf = device_tensor(sp.value, sum(send_counts) * cs.value, self.device)
+        rbuf = device_tensor(rp.value, nrecv * cs.value, self.device)
+        exchange_particles(sbuf, send_counts, rbuf, recv_counts, cs.value, self.group)
+        torch.cuda.synchronize(self.device)
+        self._check(self.lib.piclas_gpu_exchange_finish(C.c_int64(nrecv)))
+        self.migrated = sum(send_counts)
+        return sum(send_counts), nrecv
+
+    def PushAndTrack(self, dt, it=0):
+        lost = self.step.PushAndTrack(dt, it)
+        self.exchange()
+        return lost
+
+    def Deposition(self, want_partsource=True, want_nodesource=True, out_partsource=None):
+        from .particle_step import _f
+        self._check(self.lib.piclas_gpu_deposit(_f(None), _f(None)))       # rank-local node sums
+        p = C.c_void_p(0)
+        self._check(self.lib.piclas_gpu_nodesource_device(C.byref(p)))
+        t = device_tensor(p.value, self.mesh.nUniqueNodes * 4, self.device)
+        halo_sum(t, self.group)
+        torch.cuda.synchronize(self.device)
+        PS = out_partsource if out_partsource is not None else (np.empty(self.step._ps_shape) if want_partsource else None)
+        NS = np.empty((self.mesh.nUniqueNodes, 4)) if want_nodesource else None
+        self._check(self.lib.piclas_gpu_deposit_finish(_f(PS), _f(NS)))
+        return PS, NS
+
+
+# ---- bench.py --gpus N (N > 1) -------------------------------------------------------------------------------------------
+def run_bench_multi(args, rank, world, local):
+    import bench as B
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mesh, E, dt, vth = B.workload(args.nelem, args.N)
+    n_total = int(args.particles)
+    prm = Params(ChargeIC=(-B.QE,), MassIC=(B.ME,), MacroParticleFactor=(1.0e3,), device=local)
+    off = hm.partition(mesh, world)
+    n_loc_elems = int(off[rank + 1] - off[rank])
+    # particles of this rank: uniform in its element range (z-slabs for the i-fastest element order)
+    n_loc = n_total // world + (1 if rank < n_total % world else 0)
+    prm.maxParticleNumber = int(n_loc * 1.15) + 4096
+    R = ParticleStepRank(mesh, prm, rank, world, local)
+    rng = np.random.default_rng(args.seed + 1000 * rank)
+    ne = args.nelem
+    layer = ne * ne
+    done = 0
+    chunk = 10_000_000
+    while done < n_loc:
+        m = min(chunk, n_loc - done)
+        # pick elements uniformly from the local range, then a uniform point inside the element
+        el = rng.integers(int(off[rank]), int(off[rank + 1]), m)
+        ijk = np.stack([el % ne, (el // ne) % ne, el // layer], axis=1)
+        x = (ijk + rng.random((m, 3))) / ne
+        v = rng.normal(0.0, vth, (m, 3))
+        PS = np.ascontiguousarray(np.concatenate([x, v], axis=1))
+        ijk2 = np.minimum((x * ne).astype(np.int64), ne - 1)
+        elem = (1 + ijk2[:, 0] + ne * (ijk2[:, 1] + ne * ijk2[:, 2])).astype(np.int32)
+        elem = np.clip(elem, int(off[rank]) + 1, int(off[rank + 1])).astype(np.int32)
+        R.step.UploadParticles(PS, np.ones(m, dtype=np.int32), elem, append=done > 0)
+        done += m
+    E_loc = np.ascontiguousarray(E[int(off[rank]):int(off[rank + 1])])
+    R.step.SetField(E_loc)
+
+    def one_step():
+        R.Deposition(want_partsource=False, want_nodesource=False)
+        ph_d = R.step.PhaseTiming().copy()
+        _, nl_d = R.step.LastTiming()
+        R.PushAndTrack(dt)
+        ph_p = R.step.PhaseTiming().copy()
+        _, nl_p = R.step.LastTiming()
+        return nl_d + nl_p, np.array([ph_d[0], ph_d[1], ph_p[2], ph_p[3]])
+
+    for _ in range(args.warmup):
+        one_step()
+    sampler = B.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    launches, phases, migrated = 0, np.zeros(4), 0
+    for _ in range(args.steps):
+        a, b = one_step()
+        launches += a
+        phases += b
+        migrated += R.migrated
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    tmax = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    cnt = torch.tensor([R.step.NumParticles(), migrated, launches], dtype=torch.int64, device="cuda")
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    phs = torch.tensor(phases / args.steps, dtype=torch.float64, device="cuda")
+    dist.all_reduce(phs, op=dist.ReduceOp.MAX)
+    wall = float(tmax.item())
+
+    # end to end with host buffers (each rank moves its own E / PartSource slices)
+    e2e = None
+    if not args.no_e2e:
+        n1 = args.N + 1
+        E_pin = torch.from_numpy(E_loc).pin_memory()
+        PS_pin = torch.empty((n_loc_elems, n1, n1, n1, 4), dtype=torch.float64).pin_memory()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            R.Deposition(out_partsource=PS_pin.numpy(), want_nodesource=False)
+            R.step.SetField(E_pin.numpy())
+            R.PushAndTrack(dt)
+        torch.cuda.synchronize()
+        dist.barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_total * args.e2e_steps / float(te.item()), "unit": "particle-steps/s",
+               "h2d_bytes_per_step": int(E.nbytes), "d2h_bytes_per_step": int(mesh.nElems * n1 ** 3 * 4 * 8),
+               "steps": args.e2e_steps, "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps}
+    R.close()
+    if rank == 0:
+        peak, peak_src = B.hbm_peak()
+        ph = phs.tolist()
+        t_push = ph[2] * 1e-3
+        per_gpu = n_total / world
+        achieved = B.ALG_BYTES_PER_PARTICLE_STEP * per_gpu / t_push / 1e9 if t_push > 0 else 0.0
+        line = {"metric": "particle-steps/s (interp+push+track+depo)", "value": n_total * args.steps / wall,
+                "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": B.config_dict(args, n_total), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": int(cnt[2].item()), "particles_end": int(cnt[0].item()),
+                "migrated_per_step": int(cnt[1].item()) // max(args.steps, 1),
+                "roofline": {"bound": "hbm", "kernel": "k_interp_push + k_track_leavers (per GPU, slowest rank)",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": peak_src,
+                             "step_frac": (B.ALG_BYTES_PER_PARTICLE_STEP * per_gpu * args.steps / wall / 1e9) / peak,
+                             "phase_ms": {"deposit_particles": ph[0], "deposit_nodes_dofs": ph[1],
+                                          "interp_push_track": ph[2], "sort_permute": ph[3]}}}
+        print(json.dumps(line))
+    dist.destroy_process_group()

@@ -132,5 +132,17 @@ class Oracle:
         self._check(rc)
         return PS, NS
 
+    def deposit_raw(self, PartState, PartSpecies, GlobalElemID, ParticleInside):
+        NS = np.zeros((self.msh.nUniqueNodes, 4))
+        self._check(self.lib.oracle_deposit_raw(self.h, C.c_int64(len(PartSpecies)), _f(PartState), _i(PartSpecies),
+                                                _i(GlobalElemID), _i(ParticleInside), _f(NS)))
+        return NS
+
+    def deposit_finish(self, NS):
+        n1 = self.msh.N + 1
+        PS = np.zeros((self.nloc, n1, n1, n1, 4))
+        self._check(self.lib.oracle_deposit_finish(self.h, _f(NS), _f(PS)))
+        return PS, NS
+
     def deposited_charge(self, PartSource):
         return float(self.lib.oracle_deposited_charge(self.h, _f(PartSource)))

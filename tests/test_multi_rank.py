@@ -1,0 +1,34 @@
+"""N>1 path: element partition, particle migration and node halo sum must reproduce the single-rank result.
+
+CPU: world_size 2 and 3 over gloo with the oracle as the per-rank engine (host/transport logic of piclas_b200.multi).
+GPU: world_size 2 over NCCL with libpiclas_gpu.so (needs 2 GPUs: `gpurun --gpus 2`).
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WORKER = os.path.join(ROOT, "tests", "multi_worker.py")
+
+
+def _run(world, engine, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, "--engine", engine]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_gloo_oracle(world):
+    _run(world, "oracle", 29611 + world)
+
+
+@pytest.mark.gpu
+def test_multi_rank_gpu_nccl():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run(2, "gpu", 29631)
