@@ -82,9 +82,9 @@ def test_plasma_ball_cvwm_known_answer():
 def test_cartesian_box_steps(N):
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (6, 5, 4), N)
     prm = cases.electron_params()
-    dt = 1e-9
+    dt = 1e-8   # Maxwellian tail stays far below c
     PS, spec = cases.uniform_plasma(mesh, 20000, seed=11 + N, vth_cells=0.35, dt=dt)
-    E = cases.smooth_field(mesh, amp=2.0e-3)
+    E = cases.smooth_field(mesh, amp=2.0e-4)
     elem = hm.cartesian_locate(mesh, PS[:, :3])
     w = run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=6)
     print("worst rel diffs", w)
@@ -95,13 +95,13 @@ def test_deformed_box_steps():
     lo, hi = [-1, -1, -1], [1, 1, 1]
     mesh = hm.box_mesh(lo, hi, (5, 5, 5), 3, deform=cases.wavy(0.06, lo, hi))
     prm = cases.electron_params()
-    dt = 1e-9
+    dt = 1e-8   # Maxwellian tail stays far below c
     PS, spec = cases.uniform_plasma(mesh, 20000, seed=5, vth_cells=0.3, dt=dt)
     orc = Oracle(mesh, prm)
     elem = orc.locate(PS[:, :3])
     assert (elem > 0).all()
     orc.close()
-    E = cases.smooth_field(mesh, amp=1.0e-3)
+    E = cases.smooth_field(mesh, amp=1.0e-4)
     w = run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5)
     print("worst rel diffs", w)
 
@@ -128,9 +128,9 @@ def test_tsi_like_leapfrog_thin_mesh():
 def test_open_boundaries_remove_particles():
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 4, 4), 2, periodic=(False, True, False), wall_kind=hm.BC_OPEN)
     prm = cases.electron_params()
-    dt = 1e-9
+    dt = 1e-8   # Maxwellian tail stays far below c
     PS, spec = cases.uniform_plasma(mesh, 8000, seed=21, vth_cells=0.5, dt=dt)
-    E = cases.smooth_field(mesh, amp=1.0e-3)
+    E = cases.smooth_field(mesh, amp=1.0e-4)
     elem = hm.cartesian_locate(mesh, PS[:, :3])
     run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5)
 
@@ -139,9 +139,9 @@ def test_neutral_species_and_external_field():
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 4, 4), 3)
     prm = cases.electron_params(ChargeIC=(-cases.QE, 0.0), MassIC=(cases.ME, 6.6e-26), MacroParticleFactor=(10.0, 10.0),
                                 externalField=(1e-3, -2e-3, 5e-4, 0.0, 0.0, 2e-4))
-    dt = 1e-9
+    dt = 1e-8   # Maxwellian tail stays far below c
     PS, spec = cases.uniform_plasma(mesh, 8000, seed=8, vth_cells=0.3, dt=dt, nspecies=2)
-    E = cases.smooth_field(mesh, amp=1.0e-3)
+    E = cases.smooth_field(mesh, amp=1.0e-4)
     elem = hm.cartesian_locate(mesh, PS[:, :3])
     # B != 0: tan() differs between libm and CUDA by <= 2 ulp, still far inside 1e-12
     run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=4)
