@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--arithmetic", type=int, default=1, help="0: reference operation order, 1: restructured (<=1e-12)")
     return ap.parse_args()
 
 
@@ -206,7 +207,8 @@ def run_b200(args):
 
     mesh, E, dt, vth = workload(args.nelem, args.N)
     n_total = int(args.particles)
-    prm = Params(ChargeIC=(-QE,), MassIC=(ME,), MacroParticleFactor=(1.0e3,), device=local, maxParticleNumber=n_total + 1024)
+    prm = Params(ChargeIC=(-QE,), MassIC=(ME,), MacroParticleFactor=(1.0e3,), device=local, maxParticleNumber=n_total + 1024,
+                 arithmetic=args.arithmetic)
     gpu = ParticleStep(mesh, prm)
     rng = np.random.default_rng(args.seed)
     chunk = 10_000_000

@@ -32,6 +32,23 @@ struct __align__(16) GeoElem {
   double pad;              // keep sizeof a multiple of 16
 };
 
+// Fast-arithmetic records (params.arithmetic == 1), derived at init from the tables above.
+// PlaneElem: inward unit normal and offset of the 12 side triangles: the determinant of ParticleInsideQuad3D for triangle
+// t equals (n_t . x - d_t) * |N_t|, so its sign is known without evaluating it whenever |n_t . x - d_t| > tol.
+struct __align__(16) PlaneElem {
+  double n[12][3];   // index 2*s + (tri-1)
+  double d[12];
+  double tol;        // 1e-8 * element diameter: far above the rounding error of either formula
+  double pad;
+};
+// AffElem: elements whose trilinear map is affine (parallelepipeds): xi = A (x - x0) - 1 solves the Newton problem exactly
+struct __align__(16) AffElem {
+  double x0[3];
+  double A[3][3];
+  double affine;     // 1.0 if the shortcut applies
+  double pad[3];
+};
+
 // small read-only tables in constant memory
 struct ConstTables {
   double xGP[PGPU_MAX_N + 1], wGP[PGPU_MAX_N + 1], wBary[PGPU_MAX_N + 1];
@@ -49,6 +66,7 @@ struct ConstTables {
   int32_t nPeriodicVectors;
   double PeriodicVectors[8][3];
   int32_t nGlobalElems, nElems, offsetElem, N, nRanks, myRank;
+  int32_t arithmetic;
 };
 
 // particle SoA (one of two buffers)

@@ -13,8 +13,15 @@
 // Loops that do not need unrolling are kept rolled so that each kernel's hot loop stays inside the instruction caches.
 #pragma once
 #include "math.cuh"
+#include "fastmath.cuh"
 
 constexpr int STEP_NT = 128;  // threads per CTA of the per-element kernels
+#ifndef KA_MINB
+#define KA_MINB 4   // min resident CTAs/SM of k_interp_push (register cap = 65536 / (128 * KA_MINB))
+#endif
+#ifndef DEP_MINB
+#define DEP_MINB 4
+#endif
 
 __device__ __forceinline__ void stage_words(void* dst, const void* src, int nbytes) {
   // cooperative copy of a 16-byte aligned record into shared memory with 128-bit loads
@@ -23,57 +30,18 @@ __device__ __forceinline__ void stage_words(void* dst, const void* src, int nbyt
   for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 }
 
-// determinants of the two triangles of local side s (particle_mesh_tools.f90:187-199)
-__device__ __forceinline__ void side_dets(const TriaElem* __restrict__ te, const double x[3], int s, double& d1, double& d2) {
-  double A[4][3];
-#pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    const double* c = te->corner[te->sideNode[s][n]];
-    A[n][0] = c[0] - x[0];
-    A[n][1] = c[1] - x[1];
-    A[n][2] = c[2] - x[2];
-  }
-  const double c0 = A[0][1] * A[2][2] - A[0][2] * A[2][1];
-  const double c1 = A[0][2] * A[2][0] - A[0][0] * A[2][2];
-  const double c2 = A[0][0] * A[2][1] - A[0][1] * A[2][0];
-  d1 = (c0 * A[1][0] + c1 * A[1][1]) + c2 * A[1][2];
-  d1 = -d1;
-  d2 = (c0 * A[3][0] + c1 * A[3][1]) + c2 * A[3][2];
-}
-
-// ParticleInsideQuad3D (rolled over the six sides).  Returns InElementCheck; mask bit 2*s+t-1 is set when the
-// determinant of triangle t of local side s+1 is <= 0 (the triangles SingleParticleTriaTracking3D then examines).
-__device__ __forceinline__ bool inside_quad3d_mask(const TriaElem* __restrict__ te, const double x[3], uint32_t& mask) {
-  bool inElem = true;
-  const unsigned conc = te->concave;
-  uint32_t m = 0;
-#pragma unroll 1
-  for (int s = 0; s < 6; ++s) {
-    double d1, d2;
-    side_dets(te, x, s, d1, d2);
-    const bool neg = (d1 < 0) || (d2 < 0);
-    const bool pos = !(d1 < 0) || !(d2 < 0);
-    if ((conc >> s) & 1u) {
-      if (!pos) inElem = false;
-    } else {
-      if (neg) inElem = false;
-    }
-    if (d1 <= 0.0) m |= 1u << (2 * s);
-    if (d2 <= 0.0) m |= 2u << (2 * s);
-  }
-  mask = m;
-  return inElem;
-}
-
 // ---- Newton mapping for all particles of an element + CVWM accumulation -----------------------------------------------------
 // DepositionMethod_CVWM particle loop, pic_depo_method.f90:471-544.  elemAcc[e][node 0..7 (CGNS)][0..3] receives the
 // element-local sums of TSource*weight; xi and the SucRefPos flag are cached for the interpolation of the same step.
 // The 32 per-thread accumulators live in shared memory ([a][thread], conflict free) so that the Newton iteration keeps
 // the register file; they are reduced in a fixed order (deterministic, independent of scheduling).
-__global__ void __launch_bounds__(STEP_NT, 4) k_deposit_cvwm(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems,
+template <bool FAST>
+__global__ void __launch_bounds__(STEP_NT, DEP_MINB) k_deposit_cvwm(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems,
                                                              int offsetElem, const GeoElem* __restrict__ geo,
-                                                             const TriaElem* __restrict__ tria, double* __restrict__ elemAcc) {
+                                                             const TriaElem* __restrict__ tria, const AffElem* __restrict__ aff,
+                                                             double* __restrict__ elemAcc) {
   __shared__ GeoElem sg;
+  __shared__ AffElem sa;
   __shared__ double corner[8][3];
   __shared__ double sAcc[32][STEP_NT];
   const int tid = threadIdx.x;
@@ -84,6 +52,7 @@ __global__ void __launch_bounds__(STEP_NT, 4) k_deposit_cvwm(PartBuf pb, const i
     if (p1 > p0) {
       __syncthreads();
       stage_words(&sg, geo + (offsetElem + e), sizeof(GeoElem));
+      if (FAST) stage_words(&sa, aff + (offsetElem + e), sizeof(AffElem));
       if (tid < 24) corner[tid / 3][tid % 3] = tria[offsetElem + e].corner[tid / 3][tid % 3];
       __syncthreads();
       for (int64_t p = p0 + tid; p < p1; p += STEP_NT) {
@@ -91,8 +60,9 @@ __global__ void __launch_bounds__(STEP_NT, 4) k_deposit_cvwm(PartBuf pb, const i
         uint8_t meta = pb.meta[p];
         const int spec = meta & META_SPEC_MASK;
         double xi[3];
-        const int r = position_in_ref_elem(&sg, x, xi, true, true);
-        const bool suc = (r & 1) != 0;
+        bool suc;
+        if (FAST) suc = ref_position_fast(&sa, &sg, x, xi, true);
+        else suc = (position_in_ref_elem(&sg, x, xi, true, true) & 1) != 0;
         pb.xi[0][p] = xi[0];
         pb.xi[1][p] = xi[1];
         pb.xi[2][p] = xi[2];
@@ -116,7 +86,8 @@ __global__ void __launch_bounds__(STEP_NT, 4) k_deposit_cvwm(PartBuf pb, const i
 #pragma unroll
           for (int n = 0; n < 8; ++n)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) sAcc[n * 4 + c][tid] = sAcc[n * 4 + c][tid] + (T[c] * w[n]);
+            for (int c = 0; c < 4; ++c)
+              sAcc[n * 4 + c][tid] = FAST ? fma(T[c], w[n], sAcc[n * 4 + c][tid]) : sAcc[n * 4 + c][tid] + (T[c] * w[n]);
         } else {
           // inverse-distance fallback, :512-538.  CGNS corner n is tensor node cns[n]
           const int cns[8] = {0, 1, 3, 2, 4, 5, 7, 6};
@@ -247,24 +218,31 @@ __device__ __forceinline__ void evaluate_field_tile(const double xi[3], const do
 // (particle_triatracking.f90:203-218) for the particles of one element per CTA iteration.
 // Stayers: x, v written in place, key = own element.  Leavers: v written in place, the pushed position goes to xNew
 // (the idle half of the double buffer) while pb.x keeps LastPartPos; their index is appended to leaverIdx.
-template <int NP>
-__global__ void __launch_bounds__(STEP_NT, 4) k_interp_push(PartBuf pb, double* __restrict__ xn0, double* __restrict__ xn1,
+template <int NP, bool FAST>
+__global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, double* __restrict__ xn0, double* __restrict__ xn1,
                                                             double* __restrict__ xn2, const int64_t* __restrict__ elemOff, int nElems,
                                                             int offsetElem, const GeoElem* __restrict__ geo,
-                                                            const TriaElem* __restrict__ tria, const double* __restrict__ E,
+                                                            const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ planes,
+                                                            const AffElem* __restrict__ aff, const double* __restrict__ E,
                                                             const double* __restrict__ Elem_xGP, uint32_t* __restrict__ keys,
                                                             uint32_t* __restrict__ leaverIdx, double dt, int xiValid,
                                                             int* __restrict__ counters /*[0]=lost,[1]=error,[2]=nLeavers*/) {
   constexpr int ND = NP * NP * NP;
   __shared__ GeoElem sg;
   __shared__ TriaElem st;
+  __shared__ PlaneElem sp;
+  __shared__ AffElem sa;
   __shared__ __align__(16) double sE[ND * 3];
   for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
     const int64_t p0 = elemOff[e], p1 = elemOff[e + 1];
     if (p1 <= p0) continue;
     const int gElem = offsetElem + e + 1;
     __syncthreads();
-    if (!xiValid) stage_words(&sg, geo + (gElem - 1), sizeof(GeoElem));
+    if (!xiValid) {
+      stage_words(&sg, geo + (gElem - 1), sizeof(GeoElem));
+      if (FAST) stage_words(&sa, aff + (gElem - 1), sizeof(AffElem));
+    }
+    if (FAST) stage_words(&sp, planes + (gElem - 1), sizeof(PlaneElem));
     stage_words(&st, tria + (gElem - 1), sizeof(TriaElem));
     for (int t = threadIdx.x; t < ND * 3; t += STEP_NT) {
       const int c = t % 3, node = t / 3;
@@ -288,12 +266,16 @@ __global__ void __launch_bounds__(STEP_NT, 4) k_interp_push(PartBuf pb, double* 
         if (xiValid) {
           xi[0] = pb.xi[0][p]; xi[1] = pb.xi[1][p]; xi[2] = pb.xi[2][p];
           suc = !(meta & META_XIFAIL);
+        } else if (FAST) {
+          suc = ref_position_fast(&sa, &sg, x, xi, false);
         } else {
           suc = (position_in_ref_elem(&sg, x, xi, false, true) & 1) != 0;
         }
         double f3[3];
         if (!suc && cst.DepositionType == PGPU_DEPO_CVWM)
           field_inverse_distance<NP>(x, E + (size_t)e * ND * 3, Elem_xGP + (size_t)(gElem - 1) * ND * 3, f3);
+        else if (FAST)
+          evaluate_field_fast<NP>(xi, sE, f3);
         else
           evaluate_field_tile<NP>(xi, sE, f3);
 #pragma unroll
@@ -303,12 +285,14 @@ __global__ void __launch_bounds__(STEP_NT, 4) k_interp_push(PartBuf pb, double* 
         F[2] = F[2] + f3[2];
         F[3] = F[3] + 0.; F[4] = F[4] + 0.; F[5] = F[5] + 0.;
       }
-      push_particle(x, v, F, spec, isNew, dt);
+      if (FAST) push_particle_fast(x, v, F, spec, isNew, dt);
+      else push_particle(x, v, F, spec, isNew, dt);
       pb.v[0][p] = v[0]; pb.v[1][p] = v[1]; pb.v[2][p] = v[2];
       const uint8_t nmeta = (uint8_t)(meta & META_SPEC_MASK);  // IsNewPart and the xi flag are consumed
       if (nmeta != meta) pb.meta[p] = nmeta;
       uint32_t mask;
-      if (inside_quad3d_mask(&st, x, mask)) {
+      const bool inElem = FAST ? inside_fast(&sp, &st, x, mask) : inside_quad3d_mask(&st, x, mask);
+      if (inElem) {
         pb.x[0][p] = x[0]; pb.x[1][p] = x[1]; pb.x[2][p] = x[2];
         keys[p] = (uint32_t)e;
       } else {
@@ -324,9 +308,11 @@ __global__ void __launch_bounds__(STEP_NT, 4) k_interp_push(PartBuf pb, double* 
 // ---- SingleParticleTriaTracking3D for the particles that left their element (particle_triatracking.f90:137-484) --------------------
 // One thread per leaver, element records read from global memory (L2 resident).  All loops are rolled and the candidate
 // triangles are visited through a bit mask so that the lanes of a warp run the same through-side test at the same time.
+template <bool FAST>
 __global__ void __launch_bounds__(128) k_track_leavers(PartBuf pb, const double* __restrict__ xn0, const double* __restrict__ xn1,
                                                        const double* __restrict__ xn2, const uint32_t* __restrict__ leaverIdx,
-                                                       const TriaElem* __restrict__ tria, const int32_t* __restrict__ elemRank,
+                                                       const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ planes,
+                                                       const int32_t* __restrict__ elemRank,
                                                        uint32_t* __restrict__ keys, int nElems, int offsetElem,
                                                        int* __restrict__ counters) {
   const int nLeavers = counters[2];
@@ -430,7 +416,9 @@ __global__ void __launch_bounds__(128) k_track_leavers(PartBuf pb, const double*
       dE0 = oldElem; dS0 = gside; dT0 = tri;
       if (ElemID < 1) { status = TRK_ERR_ELEM; break; }
       // 2a) inside test in the new element
-      if (inside_quad3d_mask(tria + (ElemID - 1), x, mask)) { status = TRK_OK; break; }
+      const bool inNew = FAST ? inside_fast(planes + (ElemID - 1), tria + (ElemID - 1), x, mask)
+                              : inside_quad3d_mask(tria + (ElemID - 1), x, mask);
+      if (inNew) { status = TRK_OK; break; }
     }
     uint32_t key;
     int newElem = ElemID;

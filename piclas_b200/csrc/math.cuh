@@ -465,6 +465,48 @@ __device__ __forceinline__ double intersection_with_wall(const TriaElem* __restr
   return alpha;
 }
 
+// determinants of the two triangles of local side s (particle_mesh_tools.f90:187-199)
+__device__ __forceinline__ void side_dets(const TriaElem* __restrict__ te, const double x[3], int s, double& d1, double& d2) {
+  double A[4][3];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const double* c = te->corner[te->sideNode[s][n]];
+    A[n][0] = c[0] - x[0];
+    A[n][1] = c[1] - x[1];
+    A[n][2] = c[2] - x[2];
+  }
+  const double c0 = A[0][1] * A[2][2] - A[0][2] * A[2][1];
+  const double c1 = A[0][2] * A[2][0] - A[0][0] * A[2][2];
+  const double c2 = A[0][0] * A[2][1] - A[0][1] * A[2][0];
+  d1 = (c0 * A[1][0] + c1 * A[1][1]) + c2 * A[1][2];
+  d1 = -d1;
+  d2 = (c0 * A[3][0] + c1 * A[3][1]) + c2 * A[3][2];
+}
+
+// ParticleInsideQuad3D (rolled over the six sides).  Returns InElementCheck; mask bit 2*s+t-1 is set when the
+// determinant of triangle t of local side s+1 is <= 0 (the triangles SingleParticleTriaTracking3D then examines).
+__device__ __forceinline__ bool inside_quad3d_mask(const TriaElem* __restrict__ te, const double x[3], uint32_t& mask) {
+  bool inElem = true;
+  const unsigned conc = te->concave;
+  uint32_t m = 0;
+#pragma unroll 1
+  for (int s = 0; s < 6; ++s) {
+    double d1, d2;
+    side_dets(te, x, s, d1, d2);
+    const bool neg = (d1 < 0) || (d2 < 0);
+    const bool pos = !(d1 < 0) || !(d2 < 0);
+    if ((conc >> s) & 1u) {
+      if (!pos) inElem = false;
+    } else {
+      if (neg) inElem = false;
+    }
+    if (d1 <= 0.0) m |= 1u << (2 * s);
+    if (d2 <= 0.0) m |= 2u << (2 * s);
+  }
+  mask = m;
+  return inElem;
+}
+
 enum { TRK_OK = 0, TRK_LOST = 1, TRK_REMOVED = 2, TRK_ERR_BC = 3, TRK_ERR_ELEM = 4, TRK_ERR_LOOP = 5 };
 
 // ---- particle_triatracking.f90:137-484 SingleParticleTriaTracking3D, continued after the first (failed) inside test ----------

@@ -1,4 +1,6 @@
 // piclas_gpu.cu — C ABI (include/piclas_gpu.h) of the B200 particle step: context, host<->device transfers, step driver.
+#include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +28,9 @@ struct Ctx {
   // mesh records
   TriaElem* dTria = nullptr;
   GeoElem* dGeo = nullptr;
+  PlaneElem* dPlanes = nullptr;   // arithmetic == 1 only
+  AffElem* dAff = nullptr;        // arithmetic == 1 only
+  bool fast = false;
   int32_t* dElemRank = nullptr;
   double* dElemXGP = nullptr;   // Elem_xGP (global) — inverse-distance fallback only
   // CVWM
@@ -247,16 +252,22 @@ int sort_and_permute(int64_t nIn) {
   return 0;
 }
 
-template <int NP>
-void launch_push_track(double dt) {
+template <int NP, bool FAST>
+void launch_push_track_t(double dt) {
   const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
   const PartBuf& o = g.buf[g.cur ^ 1];
   uint32_t* leaverIdx = g.sortws.permB;  // idle until the sort that follows
-  k_interp_push<NP><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem, g.dGeo,
-                                               g.dTria, g.dE, g.dElemXGP, g.dKeys, leaverIdx, dt, g.xiValid ? 1 : 0, g.dCounters);
-  k_track_leavers<<<g.nSMs * 8, 128, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, g.dTria, g.dElemRank, g.dKeys,
-                                                g.nElems, g.offsetElem, g.dCounters);
+  k_interp_push<NP, FAST><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem,
+                                                     g.dGeo, g.dTria, g.dPlanes, g.dAff, g.dE, g.dElemXGP, g.dKeys, leaverIdx, dt,
+                                                     g.xiValid ? 1 : 0, g.dCounters);
+  k_track_leavers<FAST><<<g.nSMs * 8, 128, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, g.dTria, g.dPlanes,
+                                                      g.dElemRank, g.dKeys, g.nElems, g.offsetElem, g.dCounters);
   g.lastLaunches += 2;
+}
+template <int NP>
+void launch_push_track(double dt) {
+  if (g.fast) launch_push_track_t<NP, true>(dt);
+  else launch_push_track_t<NP, false>(dt);
 }
 template <int NP>
 void launch_dofs() {
@@ -286,7 +297,7 @@ int piclas_gpu_finalize(void) {
   if (!g.ready && !g.st) return 0;
   cudaSetDevice(g.device);
   cudaDeviceSynchronize();
-  cudaFree(g.dTria); cudaFree(g.dGeo); cudaFree(g.dElemRank); cudaFree(g.dElemXGP);
+  cudaFree(g.dTria); cudaFree(g.dGeo); cudaFree(g.dPlanes); cudaFree(g.dAff); cudaFree(g.dElemRank); cudaFree(g.dElemXGP);
   cudaFree(g.dAdjOff); cudaFree(g.dAdj); cudaFree(g.dElemNodeU); cudaFree(g.dPerN); cudaFree(g.dPerOff); cudaFree(g.dPerNodes);
   cudaFree(g.dNodeVolume); cudaFree(g.dElemAcc); cudaFree(g.dS); cudaFree(g.dNodeSource); cudaFree(g.dPartSource);
   cudaFree(g.dE); cudaFree(g.dElemOff); cudaFree(g.dKeys); cudaFree(g.dCounters);
@@ -393,6 +404,65 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     memcpy(ge.xez, m->XiEtaZetaBasis + (size_t)e * 18, 18 * 8);
     memcpy(ge.slen, m->slenXiEtaZetaBasis + (size_t)e * 6, 6 * 8);
   }
+  g.fast = p->arithmetic != 0;
+  if (g.fast) {
+    std::vector<PlaneElem> planes(nG);
+    std::vector<AffElem> affs(nG);
+    for (int e = 0; e < nG; ++e) {
+      const TriaElem& t = tria[e];
+      PlaneElem& pl = planes[e];
+      memset(&pl, 0, sizeof(pl));
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int n = 0; n < 8; ++n)
+        for (int d = 0; d < 3; ++d) { lo[d] = std::min(lo[d], t.corner[n][d]); hi[d] = std::max(hi[d], t.corner[n][d]); }
+      const double diam = sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+      pl.tol = 1e-8 * diam;
+      for (int s = 0; s < 6; ++s)
+        for (int tr = 0; tr < 2; ++tr) {
+          // triangle (node1, node_{tr+2}, node_{tr+3}); det = -(x - P1) . N with N = (Pb - P1) x (Pc - P1)
+          const double* P1 = t.corner[t.sideNode[s][0]];
+          const double* Pb = t.corner[t.sideNode[s][tr + 1]];
+          const double* Pc = t.corner[t.sideNode[s][tr + 2]];
+          const double u[3] = {Pb[0] - P1[0], Pb[1] - P1[1], Pb[2] - P1[2]}, w[3] = {Pc[0] - P1[0], Pc[1] - P1[1], Pc[2] - P1[2]};
+          double N[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+          const double len = sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+          if (!(len > 0.)) return fail("piclas_gpu_init: element %d has a degenerate side triangle", e + 1);
+          const int k = 2 * s + tr;
+          for (int d = 0; d < 3; ++d) pl.n[k][d] = -N[d] / len;
+          pl.d[k] = pl.n[k][0] * P1[0] + pl.n[k][1] * P1[1] + pl.n[k][2] * P1[2];
+        }
+      // affine test on the trilinear map X(i,j,k): all mixed differences vanish
+      AffElem& a = affs[e];
+      memset(&a, 0, sizeof(a));
+      const double(*X)[3] = geo[e].XCL;  // node i + 2j + 4k
+      double ea[3], eb[3], ec[3], dev = 0.;
+      for (int d = 0; d < 3; ++d) {
+        ea[d] = X[1][d] - X[0][d]; eb[d] = X[2][d] - X[0][d]; ec[d] = X[4][d] - X[0][d];
+        dev = std::max(dev, fabs(X[3][d] - (X[0][d] + ea[d] + eb[d])));
+        dev = std::max(dev, fabs(X[5][d] - (X[0][d] + ea[d] + ec[d])));
+        dev = std::max(dev, fabs(X[6][d] - (X[0][d] + eb[d] + ec[d])));
+        dev = std::max(dev, fabs(X[7][d] - (X[0][d] + ea[d] + eb[d] + ec[d])));
+      }
+      if (dev <= 1e-14 * diam) {
+        // x = X0 + M (xi + 1)/2 with M = [ea eb ec]  =>  xi = 2 M^-1 (x - X0) - 1
+        const double M[3][3] = {{ea[0], eb[0], ec[0]}, {ea[1], eb[1], ec[1]}, {ea[2], eb[2], ec[2]}};
+        const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                           M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+        if (det > 0.) {
+          const double id = 2.0 / det;
+          a.A[0][0] = (M[1][1] * M[2][2] - M[1][2] * M[2][1]) * id; a.A[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) * id;
+          a.A[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) * id; a.A[1][0] = (M[1][2] * M[2][0] - M[1][0] * M[2][2]) * id;
+          a.A[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) * id; a.A[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) * id;
+          a.A[2][0] = (M[1][0] * M[2][1] - M[1][1] * M[2][0]) * id; a.A[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) * id;
+          a.A[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) * id;
+          for (int d = 0; d < 3; ++d) a.x0[d] = X[0][d];
+          a.affine = 1.0;
+        }
+      }
+    }
+    if (upload(&g.dPlanes, planes.data(), (size_t)nG)) return 1;
+    if (upload(&g.dAff, affs.data(), (size_t)nG)) return 1;
+  }
   if (upload(&g.dTria, tria.data(), (size_t)nG)) return 1;
   if (upload(&g.dGeo, geo.data(), (size_t)nG)) return 1;
   if (upload(&g.dElemRank, rank.data(), (size_t)nG)) return 1;
@@ -455,6 +525,7 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   h.nPeriodicVectors = m->nPeriodicVectors;
   for (int v = 0; v < m->nPeriodicVectors; ++v)
     for (int d = 0; d < 3; ++d) h.PeriodicVectors[v][d] = m->PeriodicVectors[v * 3 + d];
+  h.arithmetic = p->arithmetic;
   h.nGlobalElems = nG; h.nElems = g.nElems; h.offsetElem = g.offsetElem; h.N = g.N; h.nRanks = g.nRanks; h.myRank = g.myRank;
   CK(cudaMemcpyToSymbol(cst, &h, sizeof(h)));
   CK(cudaDeviceSynchronize());
@@ -549,7 +620,10 @@ static int deposit_local() {
   const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
   cudaEventRecord(g.evp[0], g.st);
   if (grid > 0) {
-    k_deposit_cvwm<<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dElemAcc);
+    if (g.fast)
+      k_deposit_cvwm<true><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dAff, g.dElemAcc);
+    else
+      k_deposit_cvwm<false><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dAff, g.dElemAcc);
     ++g.lastLaunches;
   }
   cudaEventRecord(g.evp[1], g.st);

@@ -8,7 +8,7 @@ import os
 from .abi import pgpu_mesh_t, pgpu_params_t, c_f64p, c_i32p, c_i64p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpiclas_gpu.so")
+LIB_PATH = os.environ.get("PICLAS_GPU_LIB") or os.path.join(HERE, "libpiclas_gpu.so")  # env override: kernel-variant experiments
 
 EXPORTS = [
     "piclas_gpu_init", "piclas_gpu_finalize", "piclas_gpu_last_error", "piclas_gpu_upload_particles",

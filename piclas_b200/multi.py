@@ -128,7 +128,7 @@ def run_bench_multi(args, rank, world, local):
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mesh, E, dt, vth = B.workload(args.nelem, args.N)
     n_total = int(args.particles)
-    prm = Params(ChargeIC=(-B.QE,), MassIC=(B.ME,), MacroParticleFactor=(1.0e3,), device=local)
+    prm = Params(ChargeIC=(-B.QE,), MassIC=(B.ME,), MacroParticleFactor=(1.0e3,), device=local, arithmetic=args.arithmetic)
     off = hm.partition(mesh, world)
     n_loc_elems = int(off[rank + 1] - off[rank])
     # particles of this rank: uniform in its element range (z-slabs for the i-fastest element order)

@@ -16,6 +16,12 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
+@pytest.fixture(params=[0, 1], ids=["reference-order", "restructured"])
+def arith(request):
+    """params.arithmetic: 0 = reference operation order (bitwise equal to the oracle), 1 = restructured (<= 1e-12)."""
+    return request.param
+
+
 def _by_id(d):
     o = np.argsort(d["ids"], kind="stable")
     return {k: (v[o] if v is not None else None) for k, v in d.items()}
@@ -63,10 +69,11 @@ def run_parity(mesh, prm, PS0, spec, elem0, E, dt, nsteps, check_deposit=True):
     return worst
 
 
-def test_plasma_ball_cvwm_known_answer():
+def test_plasma_ball_cvwm_known_answer(arith):
     """NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean: deposited charge 10.68010874898 within 5e-13 (analyze.ini)."""
     from piclas_b200.particle_step import ParticleStep
     mesh, prm, PS, spec, elem = cases.plasma_ball_cvwm()
+    prm.arithmetic = arith
     orc = Oracle(mesh, prm)
     with ParticleStep(mesh, prm) as gpu:
         gpu.UploadParticles(PS, spec, elem)
@@ -79,9 +86,9 @@ def test_plasma_ball_cvwm_known_answer():
 
 
 @pytest.mark.parametrize("N", [1, 2, 3, 5])
-def test_cartesian_box_steps(N):
+def test_cartesian_box_steps(N, arith):
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (6, 5, 4), N)
-    prm = cases.electron_params()
+    prm = cases.electron_params(arithmetic=arith)
     dt = 1e-8   # Maxwellian tail stays far below c
     PS, spec = cases.uniform_plasma(mesh, 20000, seed=11 + N, vth_cells=0.35, dt=dt)
     E = cases.smooth_field(mesh, amp=2.0e-4)
@@ -90,11 +97,11 @@ def test_cartesian_box_steps(N):
     print("worst rel diffs", w)
 
 
-def test_deformed_box_steps():
+def test_deformed_box_steps(arith):
     """Non-planar faces, non-affine elements: concave/convex side logic and a Newton that really iterates."""
     lo, hi = [-1, -1, -1], [1, 1, 1]
     mesh = hm.box_mesh(lo, hi, (5, 5, 5), 3, deform=cases.wavy(0.06, lo, hi))
-    prm = cases.electron_params()
+    prm = cases.electron_params(arithmetic=arith)
     dt = 1e-8   # Maxwellian tail stays far below c
     PS, spec = cases.uniform_plasma(mesh, 20000, seed=5, vth_cells=0.3, dt=dt)
     orc = Oracle(mesh, prm)
@@ -106,10 +113,10 @@ def test_deformed_box_steps():
     print("worst rel diffs", w)
 
 
-def test_tsi_like_leapfrog_thin_mesh():
+def test_tsi_like_leapfrog_thin_mesh(arith):
     """tutorials/pic-poisson-TSI shape: n x 1 x 1 periodic mesh, N=2, TriaTracking + CVWM, two species, Leapfrog (509)."""
     mesh = hm.box_mesh([0, 0, 0], [4 * np.pi, 0.03, 0.03], (201, 1, 1), 2)
-    prm = cases.electron_params(TimeDiscMethod=TIMEDISC_LEAPFROG, ChargeIC=(-cases.QE, cases.QE),
+    prm = cases.electron_params(arithmetic=arith, TimeDiscMethod=TIMEDISC_LEAPFROG, ChargeIC=(-cases.QE, cases.QE),
                                 MassIC=(cases.ME, 1.6726e-27), MacroParticleFactor=(2.0e6, 2.0e6))
     rng = np.random.default_rng(3)
     n = 30000
@@ -125,9 +132,9 @@ def test_tsi_like_leapfrog_thin_mesh():
     print("worst rel diffs", w)
 
 
-def test_open_boundaries_remove_particles():
+def test_open_boundaries_remove_particles(arith):
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 4, 4), 2, periodic=(False, True, False), wall_kind=hm.BC_OPEN)
-    prm = cases.electron_params()
+    prm = cases.electron_params(arithmetic=arith)
     dt = 1e-8   # Maxwellian tail stays far below c
     PS, spec = cases.uniform_plasma(mesh, 8000, seed=21, vth_cells=0.5, dt=dt)
     E = cases.smooth_field(mesh, amp=1.0e-4)
@@ -135,9 +142,9 @@ def test_open_boundaries_remove_particles():
     run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5)
 
 
-def test_neutral_species_and_external_field():
+def test_neutral_species_and_external_field(arith):
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 4, 4), 3)
-    prm = cases.electron_params(ChargeIC=(-cases.QE, 0.0), MassIC=(cases.ME, 6.6e-26), MacroParticleFactor=(10.0, 10.0),
+    prm = cases.electron_params(arithmetic=arith, ChargeIC=(-cases.QE, 0.0), MassIC=(cases.ME, 6.6e-26), MacroParticleFactor=(10.0, 10.0),
                                 externalField=(1e-3, -2e-3, 5e-4, 0.0, 0.0, 2e-4))
     dt = 1e-8   # Maxwellian tail stays far below c
     PS, spec = cases.uniform_plasma(mesh, 8000, seed=8, vth_cells=0.3, dt=dt, nspecies=2)
