@@ -65,11 +65,32 @@ __device__ __forceinline__ void evaluate_field_fast(const double xi[3], const do
   out[2] = o2;
 }
 
+// cold paths kept out of line so that their registers do not count against the hot loop
+struct PushOut { double x0, x1, x2, v0, v1, v2; int isNew; };
+__device__ __noinline__ PushOut push_particle_cold(double x0, double x1, double x2, double v0, double v1, double v2, double F0, double F1,
+                                                   double F2, double F3, double F4, double F5, int spec0, int isNewIn, double dt) {
+  double x[3] = {x0, x1, x2}, v[3] = {v0, v1, v2};
+  const double F[6] = {F0, F1, F2, F3, F4, F5};
+  bool isNew = isNewIn != 0;
+  push_particle(x, v, F, spec0, isNew, dt);
+  PushOut o;
+  o.x0 = x[0]; o.x1 = x[1]; o.x2 = x[2]; o.v0 = v[0]; o.v1 = v[1]; o.v2 = v[2]; o.isNew = isNew ? 1 : 0;
+  return o;
+}
+__device__ __noinline__ uint32_t inside_exact_cold(const TriaElem* __restrict__ te, double x0, double x1, double x2) {
+  const double x[3] = {x0, x1, x2};
+  uint32_t mask;
+  const bool in = inside_quad3d_mask(te, x, mask);
+  return mask | (in ? 0x80000000u : 0u);
+}
+
 // Boris-Leapfrog / Leapfrog push with fused multiply-adds; the B != 0 rotation is delegated to the reference-order code
 __device__ __forceinline__ void push_particle_fast(double x[3], double v[3], const double F[6], int spec0, bool& isNew, double dt) {
   const double Bn2 = (F[3] * F[3] + F[4] * F[4]) + F[5] * F[5];
   if (cst.TimeDiscMethod != PGPU_TIMEDISC_BORIS_LEAPFROG || Bn2 > 0.0) {
-    push_particle(x, v, F, spec0, isNew, dt);
+    const PushOut o = push_particle_cold(x[0], x[1], x[2], v[0], v[1], v[2], F[0], F[1], F[2], F[3], F[4], F[5], spec0, isNew ? 1 : 0, dt);
+    x[0] = o.x0; x[1] = o.x1; x[2] = o.x2; v[0] = o.v0; v[1] = o.v1; v[2] = o.v2;
+    isNew = o.isNew != 0;
     return;
   }
   const double q = cst.ChargeIC[spec0], mass = cst.MassIC[spec0];
@@ -109,7 +130,11 @@ __device__ __forceinline__ bool inside_fast(const PlaneElem* __restrict__ pl, co
     ambiguous |= fabs(dist) <= tol;
     if (dist < 0.) neg |= 1u << t;
   }
-  if (ambiguous) return inside_quad3d_mask(te, x, mask);
+  if (ambiguous) {
+    const uint32_t r = inside_exact_cold(te, x[0], x[1], x[2]);
+    mask = r & 0x7fffffffu;
+    return (r >> 31) != 0;
+  }
   mask = neg;
   const uint32_t lo = 0x555u;
   const uint32_t any = (neg | (neg >> 1)) & lo, both = (neg & (neg >> 1)) & lo;

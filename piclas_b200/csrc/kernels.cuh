@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(STEP_NT, DEP_MINB) k_deposit_cvwm(PartBuf pb, 
       if (tid < 24) corner[tid / 3][tid % 3] = tria[offsetElem + e].corner[tid / 3][tid % 3];
       __syncthreads();
       for (int64_t p = p0 + tid; p < p1; p += STEP_NT) {
+        asm volatile("" ::: "memory");  // no hoisting of shared-memory loads over the particle loop
         const double x[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};
         uint8_t meta = pb.meta[p];
         const int spec = meta & META_SPEC_MASK;
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
     }
     __syncthreads();
     for (int64_t p = p0 + threadIdx.x; p < p1; p += STEP_NT) {
+      asm volatile("" ::: "memory");  // keep the shared-memory tiles out of the registers (no hoisting over the loop)
       double x[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};
       double v[3] = {pb.v[0][p], pb.v[1][p], pb.v[2][p]};
       const uint8_t meta = pb.meta[p];

@@ -208,10 +208,23 @@ __device__ __forceinline__ int ref_elem_newton(const GeoElem* __restrict__ g, co
 }
 
 // eval_xyz.f90:35-123 GetPositionInRefElem without DoReUseMap
-__device__ __noinline__ int position_in_ref_elem(const GeoElem* __restrict__ g, const double x[3], double xi[3], bool forceMode,
-                                                    bool hasSuccess) {
+struct RefPos { double xi0, xi1, xi2; int status; };
+__device__ __noinline__ RefPos position_in_ref_elem_worker(const GeoElem* __restrict__ g, double x0, double x1, double x2, bool forceMode,
+                                                           bool hasSuccess) {
+  const double x[3] = {x0, x1, x2};
+  double xi[3];
   newton_start_value(g, x, xi);
-  return ref_elem_newton(g, x, xi, forceMode ? 1 : 2, hasSuccess);
+  RefPos r;
+  r.status = ref_elem_newton(g, x, xi, forceMode ? 1 : 2, hasSuccess);
+  r.xi0 = xi[0]; r.xi1 = xi[1]; r.xi2 = xi[2];
+  return r;
+}
+// the caller's x/xi stay in registers: only scalars cross the call
+__device__ __forceinline__ int position_in_ref_elem(const GeoElem* __restrict__ g, const double x[3], double xi[3], bool forceMode,
+                                                    bool hasSuccess) {
+  const RefPos r = position_in_ref_elem_worker(g, x[0], x[1], x[2], forceMode, hasSuccess);
+  xi[0] = r.xi0; xi[1] = r.xi1; xi[2] = r.xi2;
+  return r.status;
 }
 
 // ---- eval_xyz.f90:167-295 EvaluateFieldAtRefPos (E only; PP_nVar == 1) -----------------------------------------------------
@@ -243,10 +256,11 @@ __device__ __forceinline__ void evaluate_field(const double xi[3], const double*
 
 // pic_interpolation_tools.f90:458-572 GetEMFieldDW: inverse-distance weighting over the element's Gauss points
 // (only reached when the Newton mapping failed and the deposition is cell_volweight_mean)
+struct Vec3 { double a, b, c; };
 template <int NP>
-__device__ __noinline__ void field_inverse_distance(const double pos[3], const double* __restrict__ U,
-                                                    const double* __restrict__ xgp /* Elem_xGP tile [(k*NP+j)*NP+i][3] */,
-                                                    double out[3]) {
+__device__ __noinline__ Vec3 field_inverse_distance_worker(double p0, double p1, double p2, const double* __restrict__ U,
+                                                           const double* __restrict__ xgp /* Elem_xGP tile [(k*NP+j)*NP+i][3] */) {
+  const double pos[3] = {p0, p1, p2};
   // two passes instead of a temporary array; weights are recomputed bit-identically
   int hk = -1, hl = -1, hm = -1;  // last exact hit (norm == 0)
   double DistSum = 0.0;
@@ -286,7 +300,15 @@ __device__ __noinline__ void field_inverse_distance(const double pos[3], const d
         o1 = o1 + ww * u[1];
         o2 = o2 + ww * u[2];
       }
-  out[0] = o0; out[1] = o1; out[2] = o2;
+  Vec3 r;
+  r.a = o0; r.b = o1; r.c = o2;
+  return r;
+}
+template <int NP>
+__device__ __forceinline__ void field_inverse_distance(const double pos[3], const double* __restrict__ U,
+                                                       const double* __restrict__ xgp, double out[3]) {
+  const Vec3 r = field_inverse_distance_worker<NP>(pos[0], pos[1], pos[2], U, xgp);
+  out[0] = r.a; out[1] = r.b; out[2] = r.c;
 }
 
 // ---- particle push: timedisc_TimeStepPoissonByBorisLeapfrog.f90:128-198 (508), timedisc_TimeStepPoisson.f90:111-181 (509)

@@ -231,14 +231,8 @@ int sort_and_permute(int64_t nIn) {
   CK(radix_sort_by_key(g.sortws, g.dKeys, (size_t)nIn, g.keyBits, g.st, &sk, &perm, &g.lastLaunches));
   const PartBuf& a = g.buf[g.cur];
   PartBuf& b = g.buf[g.cur ^ 1];
-  for (int d = 0; d < 3; ++d) {
-    CK(gather_f64(a.x[d], b.x[d], perm, (size_t)nIn, g.st));
-    CK(gather_f64(a.v[d], b.v[d], perm, (size_t)nIn, g.st));
-  }
-  CK(gather_i32(a.elem, b.elem, perm, (size_t)nIn, g.st));
-  CK(gather_u8(a.meta, b.meta, perm, (size_t)nIn, g.st));
-  g.lastLaunches += 8;
-  if (g.carryIDs) { CK(gather_i64(a.id, b.id, perm, (size_t)nIn, g.st)); ++g.lastLaunches; }
+  CK(gather_particles(a.x, a.v, a.elem, a.meta, g.carryIDs ? a.id : nullptr, b.x, b.v, b.elem, b.meta, b.id, perm, (size_t)nIn, g.st));
+  ++g.lastLaunches;
   const uint32_t nKeys = (uint32_t)(g.nElems + g.nRanks + 1);
   CK(segment_offsets(sk, (size_t)nIn, nKeys, g.dElemOff, g.st));
   ++g.lastLaunches;

@@ -31,5 +31,10 @@ cudaError_t gather_i32(const int32_t* in, int32_t* out, const uint32_t* perm, si
 cudaError_t gather_u8(const uint8_t* in, uint8_t* out, const uint32_t* perm, size_t n, cudaStream_t st);
 cudaError_t gather_i64(const int64_t* in, int64_t* out, const uint32_t* perm, size_t n, cudaStream_t st);
 
+// out[i] = in[perm[i]] for every particle array in one kernel (id/idOut may be null)
+cudaError_t gather_particles(const double* const x[3], const double* const v[3], const int32_t* elem, const uint8_t* meta,
+                             const int64_t* id, double* const y[3], double* const w[3], int32_t* elemOut, uint8_t* metaOut,
+                             int64_t* idOut, const uint32_t* perm, size_t n, cudaStream_t st);
+
 // off[k] = first index i with sortedKeys[i] >= k, k = 0..nKeys (nKeys+1 entries)
 cudaError_t segment_offsets(const uint32_t* sortedKeys, size_t n, uint32_t nKeys, int64_t* off, cudaStream_t st);
