@@ -110,6 +110,8 @@ typedef struct pgpu_mesh {
   const double  *BaseVectorsScale;/* [nSides]                                                            */
   /* shape function */
   const double  *SFElemr2;        /* [nGlobalElems][2] adaptive radius (r, r^2) or NULL                  */
+  const double  *ElemRadiusNGeo;  /* [nGlobalElems] (particle_mesh_build.f90:300)                        */
+  const int32_t *ElemToBGM;       /* [nGlobalElems][6] FIBGM cell box imin,imax,jmin,jmax,kmin,kmax (particle_bgm.f90:517-522) */
 } pgpu_mesh_t;
 
 /* ---- already-parsed run-time parameters (parameter.ini keys in the comments) -------------------------- */

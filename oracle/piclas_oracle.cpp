@@ -725,6 +725,283 @@ void cvwmNodesToDofs(const Oracle& o, double* NodeSource, double* PartSource) {
   }
 }
 
+
+// ============================================================================================================
+// Shape-function deposition: pic_depo_method.f90:851-1003 DepositionMethod_SF and
+// pic_depo_shapefunction_tools.f90 (calcSfSource :30-164, depoChargeOnDOFsSF :292-422, calcTotalChargePeriodic_cc
+// :425-555, depoChargeOnDOFsSFChargeCon :558-755, UpdatePartSource :911-967, SFNorm/SFRadius2 :997-1058,
+// GetPartPosShifted :1061-1124); InitPeriodicSFCaseMatrix pic_depo.f90:828-910.
+struct SFState {
+  int NbrOfPeriodicSFCases = 0;
+  int caseMatrix[27][3];
+  int dim_sf_dir1 = 0, dim_sf_dir2 = 0, dim_periodic_vec1 = 0, dim_periodic_vec2 = 0;
+  double r2_sf = 0., r2_sf_inv = 0.;
+  std::vector<char> ChargeSFDone;
+};
+
+void initSF(const Oracle& o, SFState& sf) {
+  const int dim_sf = o.p.dim_sf, dir = o.p.dim_sf_dir;
+  sf.dim_sf_dir1 = (dir == 2) ? 1 : 2;          // MERGE(1,2,dim_sf_dir.EQ.2)
+  sf.dim_sf_dir2 = (dir == 3) ? 1 : 3;          // MERGE(1,MERGE(3,3,..),dim_sf_dir.EQ.3)
+  std::memset(sf.caseMatrix, 0, sizeof(sf.caseMatrix));
+  if (o.m.nPeriodicVectors <= 0) {
+    sf.NbrOfPeriodicSFCases = 0;
+  } else {
+    int n = 1;
+    for (int d = 0; d < dim_sf; ++d) n *= 3;
+    sf.NbrOfPeriodicSFCases = n;
+    auto M = [&](int i1, int c1) -> int& { return sf.caseMatrix[i1 - 1][c1 - 1]; };
+    if (dim_sf == 1) { M(1, 1) = 1; M(3, 1) = -1; }
+    if (dim_sf == 2) {
+      for (int i = 1; i <= 3; ++i) M(i, 1) = 1;
+      for (int i = 7; i <= 9; ++i) M(i, 1) = -1;
+      for (int I = 1; I <= 3; ++I) { M(I * 3 - 2, 2) = 1; M(I * 3, 2) = -1; }
+    }
+    if (dim_sf == 3) {
+      for (int i = 1; i <= 9; ++i) M(i, 1) = 1;
+      for (int i = 19; i <= 27; ++i) M(i, 1) = -1;
+      for (int I = 1; I <= 3; ++I) {
+        for (int i = I * 9 - 8; i <= I * 9 - 6; ++i) M(i, 2) = 1;
+        for (int i = I * 9 - 2; i <= I * 9; ++i) M(i, 2) = -1;
+        for (int J = 1; J <= 3; ++J) { M((J * 3 - 2) + (I - 1) * 9, 3) = 1; M((J * 3) + (I - 1) * 9, 3) = -1; }
+      }
+    }
+    if (dim_sf == 2) {
+      if (o.m.nPeriodicVectors == 1) { sf.dim_periodic_vec1 = 1; sf.dim_periodic_vec2 = 0; }
+      else if (o.m.nPeriodicVectors == 2) { sf.dim_periodic_vec1 = 1; sf.dim_periodic_vec2 = 2; }
+      else { sf.dim_periodic_vec1 = sf.dim_sf_dir1; sf.dim_periodic_vec2 = sf.dim_sf_dir2; }
+    }
+  }
+  sf.r2_sf = o.p.r_sf * o.p.r_sf;
+  sf.r2_sf_inv = 1. / sf.r2_sf;
+  sf.ChargeSFDone.assign(o.m.nGlobalElems, 0);
+}
+
+inline double SFNorm(const Oracle& o, const SFState& sf, const double* v1) {
+  switch (o.p.dim_sf) {
+    case 1: return std::fabs(v1[o.p.dim_sf_dir - 1]);
+    case 2: return std::sqrt(v1[sf.dim_sf_dir1 - 1] * v1[sf.dim_sf_dir1 - 1] + v1[sf.dim_sf_dir2 - 1] * v1[sf.dim_sf_dir2 - 1]);
+    case 3: return VECNORM3D(v1);
+    default: return 0.;
+  }
+}
+inline double SFRadius2(const Oracle& o, const SFState& sf, const double* v1) {
+  switch (o.p.dim_sf) {
+    case 1: return v1[o.p.dim_sf_dir - 1] * v1[o.p.dim_sf_dir - 1];
+    case 2: return v1[sf.dim_sf_dir1 - 1] * v1[sf.dim_sf_dir1 - 1] + v1[sf.dim_sf_dir2 - 1] * v1[sf.dim_sf_dir2 - 1];
+    case 3: return (v1[0] * v1[0] + v1[1] * v1[1]) + v1[2] * v1[2];  // SUM(v1(1:3)**2)
+    default: return 0.;
+  }
+}
+// GEO%PeriodicVectors(I, iVec), both 1-based
+inline double PV(const Oracle& o, int I, int iVec) { return o.m.PeriodicVectors[(size_t)(iVec - 1) * 3 + (I - 1)]; }
+
+void getPartPosShifted(const Oracle& o, const SFState& sf, int iCase, const double* PartPos, double* out) {
+  const int* cm = sf.caseMatrix[iCase - 1];
+  switch (o.p.dim_sf) {
+    case 1: {
+      out[0] = out[1] = out[2] = 0.;
+      const int d = o.p.dim_sf_dir;
+      out[d - 1] = PartPos[d - 1] + cm[0] * PV(o, d, d);
+      break;
+    }
+    case 2: {
+      const int d = o.p.dim_sf_dir, d1 = sf.dim_sf_dir1, d2 = sf.dim_sf_dir2;
+      out[d - 1] = PartPos[d - 1];
+      out[d1 - 1] = PartPos[d1 - 1] + cm[0] * PV(o, d1, sf.dim_periodic_vec1);
+      out[d2 - 1] = PartPos[d2 - 1] + cm[0] * PV(o, d2, sf.dim_periodic_vec1);
+      if (sf.dim_periodic_vec2 > 0) {
+        out[d1 - 1] = out[d1 - 1] + cm[1] * PV(o, d1, sf.dim_periodic_vec2);
+        out[d2 - 1] = out[d2 - 1] + cm[1] * PV(o, d2, sf.dim_periodic_vec2);
+      }
+      break;
+    }
+    default:
+      for (int I = 1; I <= 3; ++I)
+        out[I - 1] = ((PartPos[I - 1] + cm[0] * PV(o, I, 1)) + cm[1] * PV(o, I, 2)) + cm[2] * PV(o, I, 3);
+  }
+}
+
+struct BGMRange { int kmin, kmax, lmin, lmax, mmin, mmax; };
+BGMRange sfRange(const Oracle& o, const double* Position, double r_sf) {
+  BGMRange b;
+  const double* d = o.m.FIBGMdeltas;
+  b.kmax = (int)std::ceil((Position[0] + r_sf - o.m.xyzminglob[0]) / d[0]);
+  b.kmin = (int)std::floor((Position[0] - r_sf - o.m.xyzminglob[0]) / d[0] + 1);
+  b.lmax = (int)std::ceil((Position[1] + r_sf - o.m.xyzminglob[1]) / d[1]);
+  b.lmin = (int)std::floor((Position[1] - r_sf - o.m.xyzminglob[1]) / d[1] + 1);
+  b.mmax = (int)std::ceil((Position[2] + r_sf - o.m.xyzminglob[2]) / d[2]);
+  b.mmin = (int)std::floor((Position[2] - r_sf - o.m.xyzminglob[2]) / d[2] + 1);
+  const int* mn = o.m.FIBGMmin; const int* mx = o.m.FIBGMmax;
+  if (o.p.dim_sf == 2) {
+    if (o.p.dim_sf_dir == 1) { b.kmax = mx[0]; b.kmin = mn[0]; }
+    else if (o.p.dim_sf_dir == 2) { b.lmax = mx[1]; b.lmin = mn[1]; }
+    else { b.mmax = mx[2]; b.mmin = mn[2]; }
+  } else if (o.p.dim_sf == 1) {
+    if (o.p.dim_sf_dir == 1) { b.lmax = mx[1]; b.lmin = mn[1]; b.mmax = mx[2]; b.mmin = mn[2]; }
+    else if (o.p.dim_sf_dir == 2) { b.kmax = mx[0]; b.kmin = mn[0]; b.mmax = mx[2]; b.mmin = mn[2]; }
+    else { b.kmax = mx[0]; b.kmin = mn[0]; b.lmax = mx[1]; b.lmin = mn[1]; }
+  }
+  b.kmax = std::min(b.kmax, mx[0]); b.kmin = std::max(b.kmin, mn[0]);
+  b.lmax = std::min(b.lmax, mx[1]); b.lmin = std::max(b.lmin, mn[1]);
+  b.mmax = std::min(b.mmax, mx[2]); b.mmin = std::max(b.mmin, mn[2]);
+  return b;
+}
+inline size_t bgmCell(const Oracle& o, int kk, int ll, int mm) {
+  const int ni = o.m.FIBGMmax[0] - o.m.FIBGMmin[0] + 1, nj = o.m.FIBGMmax[1] - o.m.FIBGMmin[1] + 1;
+  return (size_t)(kk - o.m.FIBGMmin[0]) + (size_t)ni * ((size_t)(ll - o.m.FIBGMmin[1]) + (size_t)nj * (size_t)(mm - o.m.FIBGMmin[2]));
+}
+inline double sfKernel(double S, int alpha_sf) {
+  double S1 = S * S;
+  for (int expo = 3; expo <= alpha_sf; ++expo) S1 = S * S1;
+  return S1;
+}
+
+// visits every element reached from the FIBGM range once (ChargeSFDone) and calls f(globElemID, k, l, m, radius2)
+template <class F>
+void sfForEachDof(const Oracle& o, SFState& sf, const double* Position, double r_sf, double r2_sf, F&& f) {
+  std::fill(sf.ChargeSFDone.begin(), sf.ChargeSFDone.end(), 0);
+  const BGMRange b = sfRange(o, Position, r_sf);
+  const int N = o.N, n1 = N + 1;
+  for (int kk = b.kmin; kk <= b.kmax; ++kk) for (int ll = b.lmin; ll <= b.lmax; ++ll) for (int mm = b.mmin; mm <= b.mmax; ++mm) {
+    const size_t c = bgmCell(o, kk, ll, mm);
+    for (int ppp = 1; ppp <= o.m.FIBGM_nElems[c]; ++ppp) {
+      const int globElemID = o.m.FIBGM_Element[o.m.FIBGM_offsetElem[c] + ppp - 1];
+      if (sf.ChargeSFDone[globElemID - 1]) continue;
+      const double* bary = o.m.ElemBaryNGeo + (size_t)(globElemID - 1) * 3;
+      const double dv[3] = {Position[0] - bary[0], Position[1] - bary[1], Position[2] - bary[2]};
+      if (SFNorm(o, sf, dv) > (r_sf + o.m.ElemRadiusNGeo[globElemID - 1])) continue;
+      const double* xgp = o.m.Elem_xGP + (size_t)(globElemID - 1) * n1 * n1 * n1 * 3;
+      for (int m = 0; m <= N; ++m) for (int l = 0; l <= N; ++l) for (int k = 0; k <= N; ++k) {
+        const double* g = xgp + (size_t)((m * n1 + l) * n1 + k) * 3;
+        const double dd[3] = {Position[0] - g[0], Position[1] - g[1], Position[2] - g[2]};
+        const double radius2 = SFRadius2(o, sf, dd);
+        if (radius2 <= r2_sf) f(globElemID, k, l, m, radius2);
+      }
+      sf.ChargeSFDone[globElemID - 1] = 1;
+    }
+  }
+}
+
+inline void updatePartSource(const Oracle& o, double* PartSource, int globElemID, int k, int l, int m, const double* Source4) {
+  const int localElem = globElemID - o.m.offsetElem;
+  if (localElem < 1 || localElem > o.m.nElems) return;  // other rank's element: SendBuffer in the reference (:948-964)
+  const int n1 = o.N + 1;
+  double* ps = PartSource + ((((size_t)(localElem - 1) * n1 + m) * n1 + l) * n1 + k) * 4;
+  for (int c = 0; c < 4; ++c) ps[c] = ps[c] + Source4[c];
+}
+
+void depoChargeOnDOFsSF(const Oracle& o, SFState& sf, double* PartSource, const double* Position, const double* Fac4, double r_sf,
+                        double r2_sf, double r2_sf_inv) {
+  sfForEachDof(o, sf, Position, r_sf, r2_sf, [&](int e, int k, int l, int m, double radius2) {
+    const double S = 1. - r2_sf_inv * radius2;
+    const double S1 = sfKernel(S, o.p.alpha_sf);
+    const double src[4] = {S1 * Fac4[0], S1 * Fac4[1], S1 * Fac4[2], S1 * Fac4[3]};
+    updatePartSource(o, PartSource, e, k, l, m, src);
+  });
+}
+
+void calcTotalChargePeriodic_cc(const Oracle& o, SFState& sf, const double* Position, double Fac, double* totalCharge, double r_sf,
+                                double r2_sf, double r2_sf_inv) {
+  const int n1 = o.N + 1;
+  sfForEachDof(o, sf, Position, r_sf, r2_sf, [&](int e, int k, int l, int m, double radius2) {
+    const double S = 1. - r2_sf_inv * radius2;
+    const double S1 = sfKernel(S, o.p.alpha_sf);
+    const double sJ = o.m.ElemsJ[(size_t)(e - 1) * n1 * n1 * n1 + (size_t)((m * n1 + l) * n1 + k)];
+    *totalCharge = *totalCharge + o.m.wGP[k] * o.m.wGP[l] * o.m.wGP[m] * Fac * S1 / sJ;
+  });
+}
+
+void depoChargeOnDOFsSFChargeCon(const Oracle& o, SFState& sf, double* PartSource, const double* Position, const double* Fac4,
+                                 double r_sf, double r2_sf, double r2_sf_inv) {
+  struct Hit { int e, k, l, m; double s[4]; };
+  std::vector<Hit> hits;
+  double totalCharge = 0.0;
+  const int n1 = o.N + 1;
+  sfForEachDof(o, sf, Position, r_sf, r2_sf, [&](int e, int k, int l, int m, double radius2) {
+    const double S = 1. - r2_sf_inv * radius2;
+    const double S1 = sfKernel(S, o.p.alpha_sf);
+    Hit h; h.e = e; h.k = k; h.l = l; h.m = m;
+    for (int c = 0; c < 4; ++c) h.s[c] = Fac4[c] * S1;
+    const double sJ = o.m.ElemsJ[(size_t)(e - 1) * n1 * n1 * n1 + (size_t)((m * n1 + l) * n1 + k)];
+    totalCharge = totalCharge + o.m.wGP[k] * o.m.wGP[l] * o.m.wGP[m] * h.s[3] / sJ;
+    hits.push_back(h);
+  });
+  if (!hits.empty()) {
+    const double alpha = Fac4[3] / totalCharge;
+    for (const Hit& h : hits) {
+      const double src[4] = {alpha * h.s[0], alpha * h.s[1], alpha * h.s[2], alpha * h.s[3]};
+      updatePartSource(o, PartSource, h.e, h.k, h.l, h.m, src);
+    }
+  }
+}
+
+int calcSfSource(const Oracle& o, SFState& sf, double* PartSource, double ChargeMPF, const double* PartPos, const double* PartVelo,
+                 int GlobalElemID) {
+  double Fac[4] = {PartVelo[0] * ChargeMPF, PartVelo[1] * ChargeMPF, PartVelo[2] * ChargeMPF, ChargeMPF};
+  double r_sf = o.p.r_sf, r2_sf = sf.r2_sf, r2_sf_inv = sf.r2_sf_inv;
+  const bool adaptive = o.p.DepositionType == PGPU_DEPO_SF_ADAPTIVE;
+  if (adaptive) {
+    if (!o.m.SFElemr2) return 5;
+    r_sf = o.m.SFElemr2[(size_t)(GlobalElemID - 1) * 2 + 0];
+    r2_sf = o.m.SFElemr2[(size_t)(GlobalElemID - 1) * 2 + 1];
+    r2_sf_inv = 1. / r2_sf;
+  }
+  double PartPosShifted[3];
+  if (sf.NbrOfPeriodicSFCases > 1) {
+    if (o.p.DepositionType == PGPU_DEPO_SF) {
+      for (int c = 0; c < 4; ++c) Fac[c] = Fac[c] * o.p.w_sf;
+    } else {
+      double totalChargePeriodicSF = 0.;
+      for (int iCase = 1; iCase <= sf.NbrOfPeriodicSFCases; ++iCase) {
+        getPartPosShifted(o, sf, iCase, PartPos, PartPosShifted);
+        calcTotalChargePeriodic_cc(o, sf, PartPosShifted, Fac[3], &totalChargePeriodicSF, r_sf, r2_sf, r2_sf_inv);
+      }
+      if (!o.p.sfDepo3D) totalChargePeriodicSF = totalChargePeriodicSF / o.p.dimFactorSF;
+      const double f4 = Fac[3];
+      for (int c = 0; c < 4; ++c) Fac[c] = Fac[c] * f4 / totalChargePeriodicSF;
+    }
+    for (int iCase = 1; iCase <= sf.NbrOfPeriodicSFCases; ++iCase) {
+      getPartPosShifted(o, sf, iCase, PartPos, PartPosShifted);
+      depoChargeOnDOFsSF(o, sf, PartSource, PartPosShifted, Fac, r_sf, r2_sf, r2_sf_inv);
+    }
+  } else {
+    switch (o.p.DepositionType) {
+      case PGPU_DEPO_SF: {
+        double F2[4] = {Fac[0] * o.p.w_sf, Fac[1] * o.p.w_sf, Fac[2] * o.p.w_sf, Fac[3] * o.p.w_sf};
+        depoChargeOnDOFsSF(o, sf, PartSource, PartPos, F2, o.p.r_sf, sf.r2_sf, sf.r2_sf_inv);
+        break;
+      }
+      case PGPU_DEPO_SF_CC:
+        depoChargeOnDOFsSFChargeCon(o, sf, PartSource, PartPos, Fac, o.p.r_sf, sf.r2_sf, sf.r2_sf_inv);
+        break;
+      case PGPU_DEPO_SF_ADAPTIVE:  // SFAdaptiveSmoothing = T branch (:149-156); the neighbour-list variant is not restated
+        depoChargeOnDOFsSFChargeCon(o, sf, PartSource, PartPos, Fac, r_sf, r2_sf, r2_sf_inv);
+        break;
+      default: return 4;
+    }
+  }
+  return 0;
+}
+
+int depositSF(Oracle& o, int64_t n, const double* PartState, const int32_t* PartSpecies, const int32_t* GlobalElemID,
+              const int32_t* ParticleInside, double* PartSource) {
+  if (!o.m.FIBGM_nElems || !o.m.ElemRadiusNGeo) { o.err = "shape function deposition needs the FIBGM tables"; return 6; }
+  SFState sf;
+  initSF(o, sf);
+  const int n1 = o.N + 1;
+  std::fill(PartSource, PartSource + (size_t)o.m.nElems * n1 * n1 * n1 * 4, 0.0);   // pic_depo.f90:1005-1007
+  for (int64_t i = 0; i < n; ++i) {
+    if (!ParticleInside[i]) continue;
+    const double q = o.ChargeIC[PartSpecies[i] - 1];
+    if (!(std::fabs(q) > 0.0)) continue;
+    const double Charge = q * o.MPF[PartSpecies[i] - 1];
+    int rc = calcSfSource(o, sf, PartSource, Charge, PartState + 6 * i, PartState + 6 * i + 3, GlobalElemID[i]);
+    if (rc) { o.err = "calcSfSource failed (unsupported shape function setup)"; return rc; }
+  }
+  return 0;
+}
+
 }  // namespace
 
 // ================================================================================================================
@@ -874,6 +1151,8 @@ int oracle_deposit(void* h, int64_t n, const double* PartState, const int32_t* P
                    const int32_t* ParticleInside, const double* PartPosRef, double* PartSource, double* NodeSource) {
   Oracle& o = *(Oracle*)h;
   (void)PartPosRef;
+  if (o.p.DepositionType == PGPU_DEPO_SF || o.p.DepositionType == PGPU_DEPO_SF_CC || o.p.DepositionType == PGPU_DEPO_SF_ADAPTIVE)
+    return depositSF(o, n, PartState, PartSpecies, GlobalElemID, ParticleInside, PartSource);
   if (o.p.DepositionType != PGPU_DEPO_CVWM) { o.err = "deposition type not supported by the oracle yet"; return 4; }
   std::fill(NodeSource, NodeSource + (size_t)o.m.nUniqueGlobalNodes * 4, 0.0);
   for (int64_t i = 0; i < n; ++i) {

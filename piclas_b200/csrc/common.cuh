@@ -67,6 +67,12 @@ struct ConstTables {
   double PeriodicVectors[8][3];
   int32_t nGlobalElems, nElems, offsetElem, N, nRanks, myRank;
   int32_t arithmetic;
+  // shape function (pic_depo.f90:828-910, pic_depo_shapefunction_tools.f90:1131-1294)
+  int32_t dim_sf, dim_sf_dir, dim_sf_dir1, dim_sf_dir2, dim_periodic_vec1, dim_periodic_vec2, nSFCases, alpha_sf, sfDepo3D;
+  int32_t sfCase[27][3];
+  double r_sf, r2_sf, r2_sf_inv, w_sf, dimFactorSF;
+  double FIBGMdeltas[3], xyzminglob[3];
+  int32_t FIBGMmin[3], FIBGMmax[3];
 };
 
 // particle SoA (one of two buffers)

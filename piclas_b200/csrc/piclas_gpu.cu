@@ -1,5 +1,6 @@
 // piclas_gpu.cu — C ABI (include/piclas_gpu.h) of the B200 particle step: context, host<->device transfers, step driver.
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -8,6 +9,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "sf.cuh"
 #include "sort.cuh"
 
 namespace {
@@ -37,6 +39,14 @@ struct Ctx {
   int32_t *dAdjOff = nullptr, *dAdj = nullptr, *dElemNodeU = nullptr;
   int32_t *dPerN = nullptr, *dPerOff = nullptr, *dPerNodes = nullptr;
   double *dNodeVolume = nullptr, *dElemAcc = nullptr, *dS = nullptr, *dNodeSource = nullptr, *dPartSource = nullptr;
+  // shape function
+  bool sfActive = false;
+  SFTables sfT;
+  int32_t *dFibN = nullptr, *dFibOff = nullptr, *dFibElem = nullptr, *dElemToBGM = nullptr, *dCandOff = nullptr, *dCandSrc = nullptr;
+  uint8_t* dCandCase = nullptr;
+  double *dElemBary = nullptr, *dElemRadius = nullptr, *dElemsJ = nullptr, *dSFElemr2 = nullptr;
+  double* dSfFac[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t sfFacCap = 0;
   // field
   double* dE = nullptr;
   bool haveField = false;
@@ -297,6 +307,9 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dE); cudaFree(g.dElemOff); cudaFree(g.dKeys); cudaFree(g.dCounters);
   cudaFree(g.dStage); cudaFree(g.dStageI); cudaFree(g.dStageL);
   cudaFree(g.dCommSend); cudaFree(g.dCommRecv);
+  cudaFree(g.dFibN); cudaFree(g.dFibOff); cudaFree(g.dFibElem); cudaFree(g.dElemToBGM); cudaFree(g.dCandOff); cudaFree(g.dCandSrc);
+  cudaFree(g.dCandCase); cudaFree(g.dElemBary); cudaFree(g.dElemRadius); cudaFree(g.dElemsJ); cudaFree(g.dSFElemr2);
+  for (int c = 0; c < 4; ++c) cudaFree(g.dSfFac[c]);
   if (g.cap > 0) {
     free_partbuf(g.buf[0]);
     free_partbuf(g.buf[1]);
@@ -319,7 +332,18 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   if (m->NGeo != 1) return fail("piclas_gpu_init: NGeo=%d not supported (straight-sided NGeo=1 meshes only)", m->NGeo);
   if (m->N < 1 || m->N > PGPU_MAX_N) return fail("piclas_gpu_init: N=%d outside 1..%d", m->N, PGPU_MAX_N);
   if (p->TrackingMethod != PGPU_TRIATRACKING) return fail("piclas_gpu_init: TrackingMethod=%d not supported yet (triatracking only)", p->TrackingMethod);
-  if (p->DoDeposition && p->DepositionType != PGPU_DEPO_CVWM) return fail("piclas_gpu_init: PIC-Deposition-Type %d not supported yet (cell_volweight_mean only)", p->DepositionType);
+  const bool isSF = p->DepositionType == PGPU_DEPO_SF || p->DepositionType == PGPU_DEPO_SF_CC || p->DepositionType == PGPU_DEPO_SF_ADAPTIVE;
+  if (p->DoDeposition && p->DepositionType != PGPU_DEPO_CVWM && !isSF)
+    return fail("piclas_gpu_init: PIC-Deposition-Type %d not supported (cell_volweight_mean, shape_function, shape_function_cc, shape_function_adaptive)", p->DepositionType);
+  if (p->DoDeposition && isSF) {
+    if (p->nRanks != 1) return fail("piclas_gpu_init: shape-function deposition is single-rank in this build (DOF halo exchange not implemented)");
+    if (!m->FIBGM_nElems || !m->FIBGM_offsetElem || !m->FIBGM_Element || !m->ElemToBGM || !m->ElemRadiusNGeo)
+      return fail("piclas_gpu_init: shape-function deposition needs FIBGM_nElems/offsetElem/Element, ElemToBGM and ElemRadiusNGeo");
+    if (p->dim_sf < 1 || p->dim_sf > 3 || p->dim_sf_dir < 1 || p->dim_sf_dir > 3) return fail("piclas_gpu_init: bad shape-function dimension/direction");
+    if (p->DepositionType == PGPU_DEPO_SF_ADAPTIVE && !m->SFElemr2) return fail("piclas_gpu_init: shape_function_adaptive needs SFElemr2");
+    if (p->DepositionType != PGPU_DEPO_SF_ADAPTIVE && !(p->r_sf > 0.)) return fail("piclas_gpu_init: PIC-shapefunction-radius must be > 0");
+    if (p->alpha_sf < 1) return fail("piclas_gpu_init: PIC-shapefunction-alpha must be >= 1");
+  }
   if (p->TimeDiscMethod != PGPU_TIMEDISC_BORIS_LEAPFROG && p->TimeDiscMethod != PGPU_TIMEDISC_LEAPFROG)
     return fail("piclas_gpu_init: TimeDiscMethod=%d not supported (508 Boris-Leapfrog, 509 Leapfrog)", p->TimeDiscMethod);
   if (p->CartesianPeriodic) return fail("piclas_gpu_init: CartesianPeriodic=T not supported");
@@ -488,6 +512,126 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     CK(cudaMalloc((void**)&g.dNodeSource, (size_t)g.nNodes * 4 * 8));
     CK(cudaMalloc((void**)&g.dPartSource, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 4 * 8));
   }
+
+  // ---- shape-function tables and gather candidates ------------------------------------------------------------------
+  g.sfActive = p->DoDeposition && isSF;
+  int sfCaseM[27][3];
+  memset(sfCaseM, 0, sizeof(sfCaseM));
+  int nSFCases = 0, sfDir1 = (p->dim_sf_dir == 2) ? 1 : 2, sfDir2 = (p->dim_sf_dir == 3) ? 1 : 3, pvec1 = 0, pvec2 = 0;
+  if (g.sfActive) {
+    const int dim_sf = p->dim_sf;
+    if (m->nPeriodicVectors > 0) {  // InitPeriodicSFCaseMatrix, pic_depo.f90:828-910
+      nSFCases = 1;
+      for (int d = 0; d < dim_sf; ++d) nSFCases *= 3;
+      auto M = [&](int i1, int c1) -> int& { return sfCaseM[i1 - 1][c1 - 1]; };
+      if (dim_sf == 1) { M(1, 1) = 1; M(3, 1) = -1; }
+      if (dim_sf == 2) {
+        for (int i = 1; i <= 3; ++i) M(i, 1) = 1;
+        for (int i = 7; i <= 9; ++i) M(i, 1) = -1;
+        for (int I = 1; I <= 3; ++I) { M(I * 3 - 2, 2) = 1; M(I * 3, 2) = -1; }
+        if (m->nPeriodicVectors == 1) { pvec1 = 1; pvec2 = 0; }
+        else if (m->nPeriodicVectors == 2) { pvec1 = 1; pvec2 = 2; }
+        else { pvec1 = sfDir1; pvec2 = sfDir2; }
+      }
+      if (dim_sf == 3) {
+        for (int i = 1; i <= 9; ++i) M(i, 1) = 1;
+        for (int i = 19; i <= 27; ++i) M(i, 1) = -1;
+        for (int I = 1; I <= 3; ++I) {
+          for (int i = I * 9 - 8; i <= I * 9 - 6; ++i) M(i, 2) = 1;
+          for (int i = I * 9 - 2; i <= I * 9; ++i) M(i, 2) = -1;
+          for (int J = 1; J <= 3; ++J) { M((J * 3 - 2) + (I - 1) * 9, 3) = 1; M((J * 3) + (I - 1) * 9, 3) = -1; }
+        }
+        if (m->nPeriodicVectors < 3) return fail("piclas_gpu_init: 3-D shape function with periodic sides needs three periodic vectors");
+      }
+    }
+    const int ni = m->FIBGMmax[0] - m->FIBGMmin[0] + 1, nj = m->FIBGMmax[1] - m->FIBGMmin[1] + 1, nk = m->FIBGMmax[2] - m->FIBGMmin[2] + 1;
+    const size_t nCells = (size_t)ni * nj * nk;
+    if (upload(&g.dFibN, m->FIBGM_nElems, nCells)) return 1;
+    if (upload(&g.dFibOff, m->FIBGM_offsetElem, nCells)) return 1;
+    if (upload(&g.dFibElem, m->FIBGM_Element, (size_t)m->nFIBGMElemsTotal)) return 1;
+    if (upload(&g.dElemToBGM, m->ElemToBGM, (size_t)nG * 6)) return 1;
+    if (upload(&g.dElemBary, m->ElemBaryNGeo, (size_t)nG * 3)) return 1;
+    if (upload(&g.dElemRadius, m->ElemRadiusNGeo, (size_t)nG)) return 1;
+    if (upload(&g.dElemsJ, m->ElemsJ, (size_t)nG * g.ND)) return 1;
+    if (m->SFElemr2 && upload(&g.dSFElemr2, m->SFElemr2, (size_t)nG * 2)) return 1;
+    // candidates: (source element s, case c) can reach target e iff SFNorm(bary_e - (bary_s + shift_c)) <= r + R_e + R_s
+    double rmax = p->r_sf;
+    if (p->DepositionType == PGPU_DEPO_SF_ADAPTIVE) {
+      rmax = 0.;
+      for (int e = 0; e < nG; ++e) rmax = std::max(rmax, m->SFElemr2[(size_t)e * 2]);
+    }
+    auto sfnorm = [&](const double* v) {
+      if (dim_sf == 1) return fabs(v[p->dim_sf_dir - 1]);
+      if (dim_sf == 2) return sqrt(v[sfDir1 - 1] * v[sfDir1 - 1] + v[sfDir2 - 1] * v[sfDir2 - 1]);
+      return sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    };
+    auto PVc = [&](int I, int iVec) { return m->PeriodicVectors[(size_t)(iVec - 1) * 3 + (I - 1)]; };
+    const int nCaseLoop = nSFCases > 1 ? nSFCases : 1;
+    std::vector<std::array<double, 3>> shift(nCaseLoop);
+    for (int c = 0; c < nCaseLoop; ++c) {
+      shift[c] = {0., 0., 0.};
+      if (nSFCases > 1) {
+        const int* cm = sfCaseM[c];
+        if (dim_sf == 1) shift[c][p->dim_sf_dir - 1] = cm[0] * PVc(p->dim_sf_dir, p->dim_sf_dir);
+        else if (dim_sf == 2) {
+          shift[c][sfDir1 - 1] = cm[0] * PVc(sfDir1, pvec1) + (pvec2 > 0 ? cm[1] * PVc(sfDir1, pvec2) : 0.);
+          shift[c][sfDir2 - 1] = cm[0] * PVc(sfDir2, pvec1) + (pvec2 > 0 ? cm[1] * PVc(sfDir2, pvec2) : 0.);
+        } else for (int I = 1; I <= 3; ++I) shift[c][I - 1] = cm[0] * PVc(I, 1) + cm[1] * PVc(I, 2) + cm[2] * PVc(I, 3);
+      }
+    }
+    std::vector<int32_t> candOff(g.nElems + 1, 0), candSrc;
+    std::vector<uint8_t> candCase;
+    // uniform grid over source barycentres would be faster; the local element count times cases is small enough for a
+    // direct scan up to ~1e5 elements, beyond that the FIBGM is used to prefilter
+    std::vector<int> stamp(nG, -1);
+    double RsMaxAll = 0.;
+    for (int s2 = 0; s2 < nG; ++s2) RsMaxAll = std::max(RsMaxAll, m->ElemRadiusNGeo[s2]);
+    for (int e = 0; e < g.nElems; ++e) {
+      const int ge = g.offsetElem + e;
+      const double* be = m->ElemBaryNGeo + (size_t)ge * 3;
+      const double Re = m->ElemRadiusNGeo[ge];
+      for (int c = 0; c < nCaseLoop; ++c) {
+        // sources must satisfy |be - shift - bs| <= rmax + Re + Rs  -> query point q = be - shift
+        const double q[3] = {be[0] - shift[c][0], be[1] - shift[c][1], be[2] - shift[c][2]};
+        double Rq = rmax + Re;
+        // prefilter through the FIBGM cells overlapped by q +- (Rq + largest element radius), full range in unused directions
+        const double Rs_max = RsMaxAll;
+        int lo[3], hi[3];
+        for (int d = 0; d < 3; ++d) {
+          lo[d] = (int)floor((q[d] - (Rq + Rs_max) - m->xyzminglob[d]) / m->FIBGMdeltas[d]) + 1;
+          hi[d] = (int)floor((q[d] + (Rq + Rs_max) - m->xyzminglob[d]) / m->FIBGMdeltas[d]) + 1;
+          bool used = (dim_sf == 3) || (dim_sf == 1 && d == p->dim_sf_dir - 1) || (dim_sf == 2 && d != p->dim_sf_dir - 1);
+          if (!used) { lo[d] = m->FIBGMmin[d]; hi[d] = m->FIBGMmax[d]; }
+          lo[d] = std::max(lo[d], m->FIBGMmin[d]);
+          hi[d] = std::min(hi[d], m->FIBGMmax[d]);
+        }
+        const int tag = e * nCaseLoop + c;
+        std::vector<int> found;
+        for (int kk = lo[0]; kk <= hi[0]; ++kk) for (int ll = lo[1]; ll <= hi[1]; ++ll) for (int mm = lo[2]; mm <= hi[2]; ++mm) {
+          const size_t cell = (size_t)(kk - m->FIBGMmin[0]) + (size_t)ni * ((size_t)(ll - m->FIBGMmin[1]) + (size_t)nj * (size_t)(mm - m->FIBGMmin[2]));
+          for (int k2 = 0; k2 < m->FIBGM_nElems[cell]; ++k2) {
+            const int gs = m->FIBGM_Element[m->FIBGM_offsetElem[cell] + k2] - 1;
+            if (stamp[gs] == tag) continue;
+            stamp[gs] = tag;
+            const int ls = gs - g.offsetElem;
+            if (ls < 0 || ls >= g.nElems) continue;  // particles live in local elements only
+            const double* bs = m->ElemBaryNGeo + (size_t)gs * 3;
+            const double dv[3] = {q[0] - bs[0], q[1] - bs[1], q[2] - bs[2]};
+            if (sfnorm(dv) <= 1.0000001 * (rmax + Re + m->ElemRadiusNGeo[gs])) found.push_back(ls);
+          }
+        }
+        std::sort(found.begin(), found.end());
+        for (int ls : found) { candSrc.push_back(ls); candCase.push_back((uint8_t)(nSFCases > 1 ? c + 1 : 0)); }
+      }
+      candOff[e + 1] = (int32_t)candSrc.size();
+    }
+    if (upload(&g.dCandOff, candOff.data(), candOff.size())) return 1;
+    if (upload(&g.dCandSrc, candSrc.data(), candSrc.size())) return 1;
+    if (upload(&g.dCandCase, candCase.data(), candCase.size())) return 1;
+    g.sfT.FIBGM_nElems = g.dFibN; g.sfT.FIBGM_offsetElem = g.dFibOff; g.sfT.FIBGM_Element = g.dFibElem; g.sfT.ElemToBGM = g.dElemToBGM;
+    g.sfT.ElemBary = g.dElemBary; g.sfT.ElemRadius = g.dElemRadius; g.sfT.Elem_xGP = g.dElemXGP; g.sfT.ElemsJ = g.dElemsJ;
+    g.sfT.SFElemr2 = g.dSFElemr2; g.sfT.candOff = g.dCandOff; g.sfT.candSrc = g.dCandSrc; g.sfT.candCase = g.dCandCase;
+  }
   CK(cudaMalloc((void**)&g.dE, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
   CK(cudaMemset(g.dE, 0, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
   CK(cudaMalloc((void**)&g.dElemOff, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
@@ -520,6 +664,12 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   for (int v = 0; v < m->nPeriodicVectors; ++v)
     for (int d = 0; d < 3; ++d) h.PeriodicVectors[v][d] = m->PeriodicVectors[v * 3 + d];
   h.arithmetic = p->arithmetic;
+  h.dim_sf = p->dim_sf; h.dim_sf_dir = p->dim_sf_dir; h.dim_sf_dir1 = sfDir1; h.dim_sf_dir2 = sfDir2;
+  h.dim_periodic_vec1 = pvec1; h.dim_periodic_vec2 = pvec2; h.nSFCases = nSFCases; h.alpha_sf = p->alpha_sf; h.sfDepo3D = p->sfDepo3D;
+  memcpy(h.sfCase, sfCaseM, sizeof(sfCaseM));
+  h.r_sf = p->r_sf; h.r2_sf = p->r_sf * p->r_sf; h.r2_sf_inv = (p->r_sf > 0.) ? 1. / (p->r_sf * p->r_sf) : 0.;
+  h.w_sf = p->w_sf; h.dimFactorSF = p->dimFactorSF;
+  for (int d = 0; d < 3; ++d) { h.FIBGMdeltas[d] = m->FIBGMdeltas[d]; h.xyzminglob[d] = m->xyzminglob[d]; h.FIBGMmin[d] = m->FIBGMmin[d]; h.FIBGMmax[d] = m->FIBGMmax[d]; }
   h.nGlobalElems = nG; h.nElems = g.nElems; h.offsetElem = g.offsetElem; h.N = g.N; h.nRanks = g.nRanks; h.myRank = g.myRank;
   CK(cudaMemcpyToSymbol(cst, &h, sizeof(h)));
   CK(cudaDeviceSynchronize());
@@ -660,11 +810,55 @@ static int deposit_finish(double* PartSource, double* NodeSource) {
   return 0;
 }
 
+static int deposit_sf(double* PartSource) {
+  if (g.nPart > g.sfFacCap) {
+    for (int c = 0; c < 4; ++c) { cudaFree(g.dSfFac[c]); g.dSfFac[c] = nullptr; }
+    g.sfFacCap = g.cap > g.nPart ? g.cap : g.nPart;
+    for (int c = 0; c < 4; ++c) CK(cudaMalloc((void**)&g.dSfFac[c], (size_t)g.sfFacCap * 8));
+  }
+  CK(cudaMemsetAsync(g.dCounters, 0, 4 * sizeof(int), g.st));
+  cudaEventRecord(g.evp[0], g.st);
+  if (g.nPart > 0) {
+    k_sf_prepare<<<(unsigned)((g.nPart + 127) / 128), 128, 0, g.st>>>(g.buf[g.cur], g.nPart, g.sfT, g.dSfFac[0], g.dSfFac[1], g.dSfFac[2],
+                                                                    g.dSfFac[3], g.dCounters + 3);
+    ++g.lastLaunches;
+  }
+  cudaEventRecord(g.evp[1], g.st);
+  if (g.nElems > 0) {
+    int nt = ((g.ND + 31) / 32) * 32;
+    if (nt < 64) nt = 64;
+    const int grid = g.nElems < g.nSMs * 16 ? g.nElems : g.nSMs * 16;
+    k_sf_gather<<<grid, nt, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.sfT, g.dSfFac[0], g.dSfFac[1], g.dSfFac[2],
+                                       g.dSfFac[3], g.dPartSource);
+    ++g.lastLaunches;
+  }
+  CK(cudaGetLastError());
+  cudaEventRecord(g.evp[2], g.st);
+  end_timing();
+  {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, g.evp[0], g.evp[1]);
+    cudaEventElapsedTime(&b, g.evp[1], g.evp[2]);
+    g.phaseMs[0] = a;
+    g.phaseMs[1] = b;
+  }
+  int hc[4] = {0, 0, 0, 0};
+  CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
+  if (PartSource) CK(cudaMemcpyAsync(PartSource, g.dPartSource, (size_t)g.nElems * g.ND * 4 * 8, cudaMemcpyDeviceToHost, g.st));
+  CK(cudaStreamSynchronize(g.st));
+  if (hc[3]) return fail("piclas_gpu_deposit: charge-conserving shape function found no DOF within the radius of a particle");
+  return 0;
+}
+
 int piclas_gpu_deposit(double* PartSource, double* NodeSource) {
   if (!g.ready) return fail("piclas_gpu_deposit: not initialised");
   if (!g.prm.DoDeposition) return fail("piclas_gpu_deposit: PIC-DoDeposition=F");
   CK(cudaSetDevice(g.device));
   begin_timing();
+  if (g.sfActive) {
+    if (NodeSource) return fail("piclas_gpu_deposit: NodeSource exists for cell_volweight_mean only");
+    return deposit_sf(PartSource);
+  }
   if (deposit_local()) return 1;
   if (g.nRanks > 1) {  // caller sums the node array over ranks, then piclas_gpu_deposit_finish
     end_timing();

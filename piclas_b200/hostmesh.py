@@ -452,3 +452,69 @@ def partition(mesh: ParticleMesh, nprocs: int):
     rank = np.searchsorted(off, np.arange(nG), side="right") - 1
     mesh.ElemInfo[:, 6] = rank.astype(np.int32)
     return off
+
+
+def add_fibgm(mesh: ParticleMesh, deltas=None, factor=(1.0, 1.0, 1.0)):
+    """Fast-init background mesh (particle_bgm.f90:327-339, 441-450, 517-522): GEO%FIBGMdeltas = Part-FIBGMdeltas /
+    Part-FactorFIBGM, cells 1..ceil(L/delta) per direction, every element registered in the cells its bounding box
+    overlaps (ascending element id inside a cell).  deltas defaults to the mean element bounding-box size."""
+    NC = mesh.NodeCoords.reshape(mesh.nElems, 8, 3)
+    lo, hi = NC.min(axis=1), NC.max(axis=1)
+    if deltas is None:
+        deltas = (hi - lo).mean(axis=0)
+    deltas = np.asarray(deltas, dtype=np.float64) / np.asarray(factor, dtype=np.float64)
+    L = mesh.xyz_max - mesh.xyz_min
+    deltas = np.minimum(deltas, L)
+    nmax = np.floor(L / deltas).astype(np.int64) + 1
+    nmax = np.where(np.mod(L, deltas) != 0, nmax, nmax - 1)                       # BGMimaxglob
+    cmin = np.maximum(np.floor((lo - mesh.xyz_min) / deltas), 0).astype(np.int64) + 1
+    cmax = np.minimum(np.floor((hi - mesh.xyz_min) / deltas).astype(np.int64) + 1, nmax[None, :])
+    ElemToBGM = np.stack([cmin[:, 0], cmax[:, 0], cmin[:, 1], cmax[:, 1], cmin[:, 2], cmax[:, 2]], axis=1).astype(np.int32)
+    ni, nj, nk = (int(v) for v in nmax)
+    span = (cmax - cmin + 1)
+    tot = span.prod(axis=1)
+    e_rep = np.repeat(np.arange(mesh.nElems), tot)
+    loc = np.arange(tot.sum()) - np.repeat(np.cumsum(tot) - tot, tot)
+    sx, sy = span[e_rep, 0], span[e_rep, 1]
+    ci = cmin[e_rep, 0] + loc % sx
+    cj = cmin[e_rep, 1] + (loc // sx) % sy
+    ck = cmin[e_rep, 2] + loc // (sx * sy)
+    cell = (ci - 1) + ni * ((cj - 1) + nj * (ck - 1))
+    order = np.lexsort((e_rep, cell))
+    cnt = np.bincount(cell, minlength=ni * nj * nk)
+    mesh.extra["FIBGM"] = dict(deltas=deltas, min=(1, 1, 1), max=(ni, nj, nk),
+                               nElems=cnt.reshape(nk, nj, ni).astype(np.int32),
+                               offsetElem=(np.cumsum(cnt) - cnt).reshape(nk, nj, ni).astype(np.int32),
+                               Element=(e_rep[order] + 1).astype(np.int32))
+    mesh.extra["ElemToBGM"] = np.ascontiguousarray(ElemToBGM)
+    rad = np.zeros(mesh.nElems)
+    for n in range(8):
+        v = NC[:, n, :] - mesh.ElemBaryNGeo
+        rad = np.maximum(rad, np.sqrt(v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1] + v[:, 2] * v[:, 2]))
+    mesh.extra["ElemRadiusNGeo"] = rad
+    return mesh
+
+
+def shape_function_setup(mesh: ParticleMesh, params, r_sf, alpha_sf, dim_sf=3, dim_sf_dir=1, sfDepo3D=True):
+    """InitShapeFunctionDimensionalty (pic_depo_shapefunction_tools.f90:1131-1294): w_sf and dimFactorSF for the
+    fixed-radius shape functions; fills the shape-function fields of `params`."""
+    import math
+    ext = mesh.xyz_max - mesh.xyz_min
+    dimFactorSF = 1.0
+    if dim_sf == 1:
+        o = [d for d in range(3) if d != dim_sf_dir - 1]
+        dimFactorSF = ext[o[0]] * ext[o[1]]
+        w = math.gamma(float(alpha_sf) + 1.5) / (math.sqrt(math.pi) * r_sf * math.gamma(float(alpha_sf + 1)))
+        w_sf = w / dimFactorSF if sfDepo3D else w
+        if sfDepo3D:
+            w_sf = math.gamma(float(alpha_sf) + 1.5) / (math.sqrt(math.pi) * r_sf * math.gamma(float(alpha_sf + 1)) * dimFactorSF)
+    elif dim_sf == 2:
+        dimFactorSF = ext[dim_sf_dir - 1]
+        r2 = r_sf * r_sf
+        w_sf = (float(alpha_sf) + 1.0) / (math.pi * r2 * dimFactorSF) if sfDepo3D else (float(alpha_sf) + 1.0) / (math.pi * r2)
+    else:
+        beta = math.gamma(1.5) * math.gamma(float(alpha_sf) + 1.0) / math.gamma(1.5 + float(alpha_sf) + 1.0)
+        w_sf = 1.0 / (2.0 * beta * float(alpha_sf) + 2 * beta) * (float(alpha_sf) + 1.0) / (math.pi * (r_sf ** 3))
+    params.r_sf, params.alpha_sf, params.dim_sf, params.dim_sf_dir = float(r_sf), int(alpha_sf), int(dim_sf), int(dim_sf_dir)
+    params.sfDepo3D, params.w_sf, params.dimFactorSF = int(bool(sfDepo3D)), float(w_sf), float(dimFactorSF)
+    return params

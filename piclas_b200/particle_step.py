@@ -17,7 +17,7 @@ from __future__ import annotations
 import ctypes as C
 import numpy as np
 
-from .abi import Marshalled, Params, c_f64p, c_i32p, c_i64p
+from .abi import Marshalled, Params, DEPO_CVWM, c_f64p, c_i32p, c_i64p
 from .hostmesh import ParticleMesh
 from . import lib as _lib
 
@@ -104,6 +104,8 @@ class ParticleStep:
     def Deposition(self, want_partsource=True, want_nodesource=True, out_partsource=None, out_nodesource=None):
         """CALL Deposition() (pic_depo.f90:944-1018): returns (PartSource[nElems,k,j,i,4], NodeSource[nNodes,4])."""
         PS = out_partsource if out_partsource is not None else (np.empty(self._ps_shape) if want_partsource else None)
+        if self.params.DepositionType != DEPO_CVWM:
+            want_nodesource, out_nodesource = False, None      # NodeSource exists for cell_volweight_mean only
         NS = out_nodesource if out_nodesource is not None else (
             np.empty((self.mesh.nUniqueNodes, 4)) if want_nodesource else None)
         self._check(self.lib.piclas_gpu_deposit(_f(PS), _f(NS)))

@@ -234,3 +234,27 @@ def test_product_path_has_no_cpu_fallback():
         mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (2, 2, 2), 1)
         with pytest.raises(ps.PiclasGpuError):
             ps.ParticleStep(mesh, Params())
+
+
+# ---- shape function known answers (NIG_PIC_Deposition/Plasma_Ball_Shape-function-*) ---------------------------------------
+@pytest.mark.parametrize("dim,direction,kind", [(1, 1, "sf"), (1, 1, "cc"), (2, 3, "sf"), (2, 3, "cc")])
+def test_oracle_shape_function_known_answers(dim, direction, kind):
+    from piclas_b200.abi import DEPO_SF, DEPO_SF_CC
+    k = GOLD["NIG_PIC_Deposition/Plasma_Ball_Shape-function"]
+    mesh = hm.box_mesh([-5, -5, -5], [5, 5, 5], (4, 4, 1), 3)
+    hm.add_fibgm(mesh)
+    n = 20000                                     # the charge is linear in the particle number: scale the known answer
+    x = cases.sphere_points(np.random.default_rng(1), n, 0.5)
+    PS = np.zeros((n, 6))
+    PS[:, :3] = x
+    prm = Params(ChargeIC=(1.60217653e-5,), MassIC=(1.0,), MacroParticleFactor=(200.0,),
+                 DepositionType=DEPO_SF if kind == "sf" else DEPO_SF_CC)
+    hm.shape_function_setup(mesh, prm, 2.0, 2, dim_sf=dim, dim_sf_dir=direction, sfDepo3D=True)
+    o = Oracle(mesh, prm)
+    PSrc, _ = o.deposit(PS, np.ones(n, dtype=np.int32), hm.cartesian_locate(mesh, x), np.ones(n, dtype=np.int32))
+    q = o.deposited_charge(PSrc) * (100000 / n)
+    if kind == "cc":
+        assert abs(q - k["charge_cc_adaptive"]) <= k["abs_tol_cc_adaptive"]
+    else:
+        ref = k["charge_sf_1D_x"] if dim == 1 else k["charge_sf_2D_z"]
+        assert abs(q - ref) <= k["rel_tol_sf"] * ref
