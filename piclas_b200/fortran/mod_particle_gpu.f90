@@ -1,0 +1,156 @@
+!==================================================================================================================================
+! MOD_Particle_GPU — ISO_C_BINDING glue between PICLas and libpiclas_gpu.so (include/piclas_gpu.h).
+!
+! Not compiled in this repository (no Fortran compiler in the build image); this is the binding a PICLas maintainer adds to
+! src/particles/ and the #if USE_GPU variant of the particle half of TimeStepPoissonByBorisLeapfrog
+! (src/timedisc/timedisc_TimeStepPoissonByBorisLeapfrog.f90:93-279).  Style follows the only in-tree BIND(C) precedent,
+! src/output/output.f90:33-48.  Every function returns 0 on success; on error the glue calls Abort(__STAMP__,...).
+!==================================================================================================================================
+MODULE MOD_Particle_GPU
+USE ISO_C_BINDING
+IMPLICIT NONE
+PRIVATE
+
+TYPE, BIND(C) :: pgpu_mesh_t            ! field order == include/piclas_gpu.h
+  INTEGER(C_INT32_T) :: nGlobalElems, nSides, nNonUniqueNodes, nUniqueGlobalNodes
+  INTEGER(C_INT32_T) :: NGeo, N, offsetElem, nElems, elemInfoSize, sideInfoSize
+  TYPE(C_PTR) :: ElemInfo, SideInfo, NodeCoords, NodeInfo, ElemNodeID, ElemSideNodeID, ConcaveElemSide
+  TYPE(C_PTR) :: XCL_NGeo, dXCL_NGeo, XiCL_NGeo, wBaryCL_NGeo, ElemBaryNGeo, ElemRadius2NGeo, XiEtaZetaBasis, slenXiEtaZetaBasis
+  TYPE(C_PTR) :: xGP, wGP, wBary, Elem_xGP, ElemsJ
+  INTEGER(C_INT32_T) :: nBCs
+  TYPE(C_PTR) :: bc_kind, bc_alpha
+  INTEGER(C_INT32_T) :: nPeriodicVectors
+  TYPE(C_PTR) :: PeriodicVectors, Periodic_nNodes, Periodic_offsetNode, Periodic_Nodes
+  INTEGER(C_INT32_T) :: nPeriodicNodesTotal
+  TYPE(C_PTR) :: NodeVolume
+  REAL(C_DOUBLE) :: FIBGMdeltas(3), xyzminglob(3), xyzmaxglob(3)
+  INTEGER(C_INT32_T) :: FIBGMmin(3), FIBGMmax(3)
+  TYPE(C_PTR) :: FIBGM_nElems, FIBGM_offsetElem, FIBGM_Element
+  INTEGER(C_INT32_T) :: nFIBGMElemsTotal
+  TYPE(C_PTR) :: ElemEpsOneCell, ElemToBCSides, SideBCMetrics
+  INTEGER(C_INT32_T) :: nBCSidesTotal
+  TYPE(C_PTR) :: SideType, SideNormVec, SideDistance, BaseVectors0, BaseVectors1, BaseVectors2, BaseVectorsScale
+  TYPE(C_PTR) :: SFElemr2, ElemRadiusNGeo, ElemToBGM
+END TYPE
+
+TYPE, BIND(C) :: pgpu_params_t
+  INTEGER(C_INT32_T) :: TrackingMethod, RefMappingGuess
+  REAL(C_DOUBLE)     :: RefMappingEps
+  INTEGER(C_INT32_T) :: CartesianPeriodic, TimeDiscMethod, DoInterpolation, DoDeposition, DepositionType
+  REAL(C_DOUBLE)     :: externalField(6), c2_inv
+  INTEGER(C_INT32_T) :: nSpecies
+  TYPE(C_PTR)        :: ChargeIC, MassIC, MacroParticleFactor
+  REAL(C_DOUBLE)     :: r_sf
+  INTEGER(C_INT32_T) :: alpha_sf, dim_sf, dim_sf_dir, sfDepo3D
+  REAL(C_DOUBLE)     :: w_sf, dimFactorSF
+  INTEGER(C_INT32_T) :: device, myRank, nRanks
+  INTEGER(C_INT64_T) :: maxParticleNumber
+  INTEGER(C_INT32_T) :: carryParticleIDs, arithmetic
+END TYPE
+
+INTERFACE
+  FUNCTION piclas_gpu_init(mesh,params) BIND(C,NAME='piclas_gpu_init')
+    IMPORT :: C_INT, pgpu_mesh_t, pgpu_params_t
+    TYPE(pgpu_mesh_t),INTENT(IN)   :: mesh
+    TYPE(pgpu_params_t),INTENT(IN) :: params
+    INTEGER(C_INT)                 :: piclas_gpu_init
+  END FUNCTION
+  FUNCTION piclas_gpu_finalize() BIND(C,NAME='piclas_gpu_finalize')
+    IMPORT :: C_INT
+    INTEGER(C_INT) :: piclas_gpu_finalize
+  END FUNCTION
+  FUNCTION piclas_gpu_last_error() BIND(C,NAME='piclas_gpu_last_error')
+    IMPORT :: C_PTR
+    TYPE(C_PTR) :: piclas_gpu_last_error
+  END FUNCTION
+  FUNCTION piclas_gpu_upload_particles(n,PartState,PartSpecies,GlobalElemID,ParticleInside,IsNewPart,PartPosRef,ids,append) &
+      BIND(C,NAME='piclas_gpu_upload_particles')
+    IMPORT :: C_INT, C_INT32_T, C_INT64_T, C_DOUBLE, C_PTR
+    INTEGER(C_INT64_T),VALUE :: n
+    REAL(C_DOUBLE),INTENT(IN)     :: PartState(6,*)
+    INTEGER(C_INT32_T),INTENT(IN) :: PartSpecies(*),GlobalElemID(*),ParticleInside(*),IsNewPart(*)
+    TYPE(C_PTR),VALUE             :: PartPosRef, ids           ! C_NULL_PTR unless RefMapping / id tracking
+    INTEGER(C_INT32_T),VALUE      :: append
+    INTEGER(C_INT)                :: piclas_gpu_upload_particles
+  END FUNCTION
+  FUNCTION piclas_gpu_deposit(PartSource,NodeSource) BIND(C,NAME='piclas_gpu_deposit')
+    IMPORT :: C_INT, C_PTR
+    TYPE(C_PTR),VALUE :: PartSource, NodeSource                  ! packed [4,nDOF_local] / [4,nUniqueGlobalNodes] or C_NULL_PTR
+    INTEGER(C_INT)    :: piclas_gpu_deposit
+  END FUNCTION
+  FUNCTION piclas_gpu_set_field(E) BIND(C,NAME='piclas_gpu_set_field')
+    IMPORT :: C_INT, C_DOUBLE
+    REAL(C_DOUBLE),INTENT(IN) :: E(3,*)                          ! packed [3,nDOF_local]
+    INTEGER(C_INT)            :: piclas_gpu_set_field
+  END FUNCTION
+  FUNCTION piclas_gpu_push_track(dt,iter,nLost) BIND(C,NAME='piclas_gpu_push_track')
+    IMPORT :: C_INT, C_INT32_T, C_INT64_T, C_DOUBLE
+    REAL(C_DOUBLE),VALUE     :: dt
+    INTEGER(C_INT64_T),VALUE :: iter
+    INTEGER(C_INT32_T),INTENT(OUT) :: nLost
+    INTEGER(C_INT)           :: piclas_gpu_push_track
+  END FUNCTION
+  FUNCTION piclas_gpu_num_particles() BIND(C,NAME='piclas_gpu_num_particles')
+    IMPORT :: C_INT64_T
+    INTEGER(C_INT64_T) :: piclas_gpu_num_particles
+  END FUNCTION
+  FUNCTION piclas_gpu_download_particles(nmax,PartState,PartSpecies,GlobalElemID,PartPosRef,ids,n_out) &
+      BIND(C,NAME='piclas_gpu_download_particles')
+    IMPORT :: C_INT, C_INT32_T, C_INT64_T, C_DOUBLE, C_PTR
+    INTEGER(C_INT64_T),VALUE :: nmax
+    REAL(C_DOUBLE),INTENT(OUT)     :: PartState(6,*)
+    INTEGER(C_INT32_T),INTENT(OUT) :: PartSpecies(*),GlobalElemID(*)
+    TYPE(C_PTR),VALUE              :: PartPosRef, ids
+    INTEGER(C_INT64_T),INTENT(OUT) :: n_out
+    INTEGER(C_INT)                 :: piclas_gpu_download_particles
+  END FUNCTION
+END INTERFACE
+
+PUBLIC :: pgpu_mesh_t, pgpu_params_t
+PUBLIC :: piclas_gpu_init, piclas_gpu_finalize, piclas_gpu_upload_particles, piclas_gpu_deposit, piclas_gpu_set_field
+PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles
+PUBLIC :: ParticleStepGPU, GPUAbortOnError
+
+CONTAINS
+
+SUBROUTINE GPUAbortOnError(rc,stamp)
+! mirrors every CALL abort(__STAMP__,...) of the replaced code (globals/globals.f90:322-397)
+USE MOD_Globals ,ONLY: abort
+INTEGER(C_INT),INTENT(IN)   :: rc
+CHARACTER(LEN=*),INTENT(IN) :: stamp
+CHARACTER(KIND=C_CHAR),POINTER :: msg(:)
+CHARACTER(LEN=1024) :: text
+INTEGER :: i
+IF (rc.EQ.0) RETURN
+CALL C_F_POINTER(piclas_gpu_last_error(),msg,(/1024/))
+text=''
+DO i=1,1024
+  IF (msg(i).EQ.C_NULL_CHAR) EXIT
+  text(i:i)=msg(i)
+END DO
+CALL abort(__STAMP__,TRIM(stamp)//': '//TRIM(text))
+END SUBROUTINE GPUAbortOnError
+
+!==================================================================================================================================
+! Particle half of TimeStepPoissonByBorisLeapfrog with the device layer (replaces :93, :109-215, :270 of the original).
+! PS_N / U_N are packed through N_DG_Mapping(1,elem) offsets exactly like Elem_xGP_Shared (particle_mesh_tools.f90:1586-1593).
+!==================================================================================================================================
+SUBROUTINE ParticleStepGPU(PartSourcePacked,EPacked,dt,iter)
+USE MOD_HDG ,ONLY: HDG
+REAL(C_DOUBLE),INTENT(INOUT),TARGET :: PartSourcePacked(:,:) ! (4,nDOF_local)
+REAL(C_DOUBLE),INTENT(INOUT)        :: EPacked(:,:)          ! (3,nDOF_local)
+REAL,INTENT(IN)                     :: dt
+INTEGER(KIND=8),INTENT(IN)          :: iter
+INTEGER(C_INT32_T) :: nLost
+REAL               :: time
+time=0.
+! Deposition()  -> PartSource on the host for the HDG right-hand side (equations/poisson/equation.f90:1043)
+CALL GPUAbortOnError(piclas_gpu_deposit(C_LOC(PartSourcePacked),C_NULL_PTR),'piclas_gpu_deposit')
+! ... unpack PartSourcePacked into PS_N(iElem)%PartSource, CALL HDG(time,iter), pack U_N(iElem)%E into EPacked ...
+CALL GPUAbortOnError(piclas_gpu_set_field(EPacked),'piclas_gpu_set_field')
+! LastPartPos/LastGlobalElemID copy, InterpolateFieldToParticle, push, PerformTracking, UpdateNextFreePosition
+CALL GPUAbortOnError(piclas_gpu_push_track(REAL(dt,C_DOUBLE),INT(iter,C_INT64_T),nLost),'piclas_gpu_push_track')
+! NbrOfLostParticles = NbrOfLostParticles + nLost   (particle_tracking_vars)
+END SUBROUTINE ParticleStepGPU
+
+END MODULE MOD_Particle_GPU
