@@ -1002,6 +1002,267 @@ int depositSF(Oracle& o, int64_t n, const double* PartState, const int32_t* Part
   return 0;
 }
 
+
+// ============================================================================================================
+// RefMapping tracking: particle_reftracking.f90:30-414 ParticleRefTracking, :417-694 ParticleBCTracking,
+// particle_intersection.f90:515-684 ComputePlanarRectIntersection, particle_localization.f90:447-469 PARTHASMOVED,
+// particle_boundary_condition.f90:35-221 GetBoundaryInteraction (REFMAPPING branch), utils.f90:52-101 InsertionSort.
+// CartesianPeriodic = F (default, particle_mesh.f90:97-98).  Only PLANAR_RECT sides (straight-sided boxes).
+constexpr double epsilontol = 100. * epsMach;  // particle_surfaces.f90:143-147
+
+inline bool ALMOSTZERO(double x) { return std::fabs(x) <= 2.22e-16; }  // piclas.h:83
+
+void insertionSort(double* a, int* id, int len) {  // utils.f90:52-101 (1-based in the reference)
+  for (int i = 1; i < len; ++i) {
+    int j = i - 1;
+    const double tmpR = a[i];
+    const int tmpI = id[i];
+    while (j >= 0) {
+      if (a[j] <= tmpR) break;
+      a[j + 1] = a[j];
+      id[j + 1] = id[j];
+      --j;
+    }
+    a[j + 1] = tmpR;
+    id[j + 1] = tmpI;
+  }
+}
+
+struct RefCtx {
+  double* PartState;   // this particle (6)
+  double* LastPartPos; // (3)
+  bool inside = true;  // PDM%ParticleInside
+};
+
+// ComputePlanarRectIntersection
+void computePlanarRectIntersection(const Oracle& o, bool* isHit, const double* PartTrajectory, double lengthPartTrajectory, double* alpha,
+                                   double* xi, double* eta, const double* LastPartPos, int flip, int SideID) {
+  *alpha = -1.0; *xi = -2.; *eta = -2.; *isHit = false;
+  double NormVec[3], locDistance;
+  const double* nv = o.m.SideNormVec + (size_t)(SideID - 1) * 3;
+  if (flip == 0) { NormVec[0] = nv[0]; NormVec[1] = nv[1]; NormVec[2] = nv[2]; locDistance = o.m.SideDistance[SideID - 1]; }
+  else { NormVec[0] = -nv[0]; NormVec[1] = -nv[1]; NormVec[2] = -nv[2]; locDistance = -o.m.SideDistance[SideID - 1]; }
+  const double coeffA = NormVec[0] * PartTrajectory[0] + NormVec[1] * PartTrajectory[1] + NormVec[2] * PartTrajectory[2];
+  const bool CriticalParallelInSide = ALMOSTZERO(coeffA);
+  const double locSideDistance = locDistance - (LastPartPos[0] * NormVec[0] + LastPartPos[1] * NormVec[1] + LastPartPos[2] * NormVec[2]);
+  if (CriticalParallelInSide) { *alpha = -1.; return; }
+  *alpha = locSideDistance / coeffA;
+  if (locSideDistance < -100 * epsMach) { *alpha = -1.; *isHit = false; return; }
+  const double alphaNorm = *alpha / lengthPartTrajectory;
+  if ((alphaNorm > 1.0) || (alphaNorm < -epsilontol)) { *alpha = -1.0; *isHit = false; return; }
+  double Inter1[3], P0[3], P1[3], P2[3];
+  const double* b0 = o.m.BaseVectors0 + (size_t)(SideID - 1) * 3;
+  const double* b1 = o.m.BaseVectors1 + (size_t)(SideID - 1) * 3;
+  const double* b2 = o.m.BaseVectors2 + (size_t)(SideID - 1) * 3;
+  for (int d = 0; d < 3; ++d) {
+    Inter1[d] = LastPartPos[d] + *alpha * PartTrajectory[d];
+    P0[d] = -0.25 * b0[d] + Inter1[d];
+    P1[d] = 0.25 * b1[d];
+    P2[d] = 0.25 * b2[d];
+  }
+  const double A1 = P1[0] * P1[0] + P1[1] * P1[1] + P1[2] * P1[2];
+  const double B1 = P2[0] * P1[0] + P2[1] * P1[1] + P2[2] * P1[2];
+  const double C1 = P1[0] * P0[0] + P1[1] * P0[1] + P1[2] * P0[2];
+  const double A2 = B1;
+  const double B2 = P2[0] * P2[0] + P2[1] * P2[1] + P2[2] * P2[2];
+  const double C2 = P2[0] * P0[0] + P2[1] * P0[1] + P2[2] * P0[2];
+  double sdet = A1 * B2 - A2 * B1;
+  sdet = 1.0 / sdet;  // ABS(sdet).EQ.0 aborts in the reference: excluded by the side-type check at init
+  const double epsLoc = 1.0 + 100. * epsMach;
+  *xi = (B2 * C1 - B1 * C2) * sdet;
+  if (std::fabs(*xi) > epsLoc) { *alpha = -1.0; return; }
+  *eta = (-A2 * C1 + A1 * C2) * sdet;
+  if (std::fabs(*eta) > epsLoc) { *alpha = -1.0; return; }
+  *isHit = true;
+}
+
+enum { BCSIDE_SIDEID = 0, BCSIDE_ELEMID = 1, BCSIDE_DISTANCE = 2 };
+
+// ParticleBCTracking with the tail recursion (:642-665) turned into a loop.  Returns nonzero on unsupported side/BC.
+int particleBCTracking(Oracle& o, double lengthPartTrajectory0, int* ElemID, RefCtx& c, bool* PartisDone, bool* PartisMoved,
+                       int* GlobalElemID) {
+  for (int iCount = 1;; ++iCount) {
+    if (iCount > 100000) { o.err = "ParticleBCTracking: recursion does not terminate"; return 3; }
+    const int32_t* e2s = o.m.ElemToBCSides + (size_t)(*ElemID - 1) * 2;
+    const int nlocSides = e2s[0];
+    const int firstSide = e2s[1] + 1, lastSide = e2s[1] + nlocSides;
+    double PartTrajectory[3] = {c.PartState[0] - c.LastPartPos[0], c.PartState[1] - c.LastPartPos[1], c.PartState[2] - c.LastPartPos[2]};
+    double lengthPartTrajectory = VECNORM3D(PartTrajectory);
+    if (ALMOSTZERO(lengthPartTrajectory / o.m.ElemRadiusNGeo[*ElemID - 1])) {  // .NOT.PARTHASMOVED
+      *GlobalElemID = *ElemID;
+      *PartisDone = true;
+      return 0;
+    }
+    for (int d = 0; d < 3; ++d) PartTrajectory[d] = PartTrajectory[d] / lengthPartTrajectory;
+    *PartisMoved = false;
+    bool DoTracing = true;
+    lengthPartTrajectory0 = std::max(lengthPartTrajectory0, lengthPartTrajectory);
+    bool doubleCheck = false;
+    bool recurse = false;
+    std::vector<double> locAlpha(std::max(nlocSides, 1)), xi(std::max(nlocSides, 1)), eta(std::max(nlocSides, 1));
+    std::vector<int> locSideList(std::max(nlocSides, 1));
+    while (DoTracing) {
+      const bool PeriMoved = false;  // CartesianPeriodic = F
+      std::fill(locAlpha.begin(), locAlpha.end(), -1.0);
+      int nInter = 0;
+      for (int ilocSide = firstSide; ilocSide <= lastSide; ++ilocSide) {
+        const double* bm = o.m.SideBCMetrics + (size_t)(ilocSide - 1) * 7;
+        if (bm[BCSIDE_DISTANCE] > lengthPartTrajectory0) break;
+        const int SideID = (int)bm[BCSIDE_SIDEID];
+        locSideList[ilocSide - firstSide] = ilocSide;
+        const int flip = (o.SideInfo(SIDE_ID, SideID) > 0) ? 0 : (o.SideInfo(SIDE_FLIP, SideID) % 10);
+        if (o.m.SideType[SideID - 1] != 0) { o.err = "ParticleBCTracking: only PLANAR_RECT sides are supported"; return 4; }
+        bool isHit;
+        computePlanarRectIntersection(o, &isHit, PartTrajectory, lengthPartTrajectory, &locAlpha[ilocSide - firstSide],
+                                      &xi[ilocSide - firstSide], &eta[ilocSide - firstSide], c.LastPartPos, flip, SideID);
+        if (locAlpha[ilocSide - firstSide] > -1.0) nInter++;
+      }
+      if (nInter == 0) {
+        if (!PeriMoved) DoTracing = false;
+      } else {
+        *PartisMoved = true;
+        insertionSort(locAlpha.data(), locSideList.data(), nlocSides);
+        bool reflected = false;
+        for (int il = 0; il < nlocSides; ++il) {
+          if (locAlpha[il] > -1) {
+            const int hitlocSide = locSideList[il];
+            const int SideID = (int)o.m.SideBCMetrics[(size_t)(hitlocSide - 1) * 7 + BCSIDE_SIDEID];
+            const int flip = (o.SideInfo(SIDE_ID, SideID) > 0) ? 0 : (o.SideInfo(SIDE_FLIP, SideID) % 10);
+            const int OldElemID = *ElemID;
+            TrackInfo ti;
+            for (int d = 0; d < 3; ++d) ti.PartTrajectory[d] = PartTrajectory[d];
+            ti.lengthPartTrajectory = lengthPartTrajectory;
+            ti.alpha = locAlpha[il];
+            // GetBoundaryInteraction, REFMAPPING branch (:110-144): outward normal, ignore sides the particle enters through
+            reflected = false;  // crossedBC
+            double n_loc[3] = {o.m.SideNormVec[(size_t)(SideID - 1) * 3], o.m.SideNormVec[(size_t)(SideID - 1) * 3 + 1],
+                               o.m.SideNormVec[(size_t)(SideID - 1) * 3 + 2]};
+            if (flip != 0) { n_loc[0] = -n_loc[0]; n_loc[1] = -n_loc[1]; n_loc[2] = -n_loc[2]; }
+            if (!((n_loc[0] * ti.PartTrajectory[0] + n_loc[1] * ti.PartTrajectory[1] + n_loc[2] * ti.PartTrajectory[2]) <= 0.)) {
+              reflected = true;
+              const int BCType = o.m.bc_kind[o.SideInfo(SIDE_BCID, SideID) - 1];
+              if (BCType == PGPU_BC_OPEN) c.inside = false;
+              else if (BCType == PGPU_BC_PERIODIC) periodicBoundary(o, c.PartState, c.LastPartPos, ti, SideID, ElemID);
+              else { o.err = "ParticleBCTracking: boundary condition type not supported"; return 5; }
+            }
+            for (int d = 0; d < 3; ++d) PartTrajectory[d] = ti.PartTrajectory[d];
+            lengthPartTrajectory = ti.lengthPartTrajectory;
+            locAlpha[il] = ti.alpha;
+            if (*ElemID != OldElemID) {
+              if (o.m.nPeriodicVectors > 0) {
+                const int32_t* oe = o.m.ElemToBCSides + (size_t)(OldElemID - 1) * 2;
+                double mx = -HUGE_D;
+                for (int k = oe[1] + 1; k <= oe[1] + oe[0]; ++k) mx = std::max(mx, o.m.SideBCMetrics[(size_t)(k - 1) * 7 + BCSIDE_DISTANCE]);
+                lengthPartTrajectory0 = mx;
+              }
+              recurse = true;
+              break;
+            }
+            if (reflected) break;
+          }
+        }
+        if (recurse) break;
+        if (!c.inside) { *PartisDone = true; return 0; }
+        if (!reflected) {
+          if (!doubleCheck) doubleCheck = true;
+          else DoTracing = false;
+        }
+      }
+    }
+    if (!recurse) return 0;
+    // CALL ParticleBCTracking(... new element ...); PartisMoved = .TRUE.; RETURN
+  }
+}
+
+// ParticleRefTracking for one particle.  PartPosRef in/out.  Returns TrackResult.
+TrackResult singleParticleRefTracking(Oracle& o, double* PartState, double* LastPartPos, double* PartPosRef, int LastGlobalElemID,
+                                      int* GlobalElemID, bool* inside) {
+  int ElemID = LastGlobalElemID;
+  bool PartIsDone = false, PartIsMoved = false;
+  RefCtx c; c.PartState = PartState; c.LastPartPos = LastPartPos;
+  auto maxabs = [](const double* v) { return std::max(std::fabs(v[0]), std::max(std::fabs(v[1]), std::fabs(v[2]))); };
+  if (o.m.ElemToBCSides[(size_t)(ElemID - 1) * 2] > 0) {
+    if (particleBCTracking(o, 0., &ElemID, c, &PartIsDone, &PartIsMoved, GlobalElemID)) return TRACK_ERROR;
+    if (PartIsDone) { *inside = c.inside; return c.inside ? TRACK_OK : TRACK_REMOVED_BC; }
+    bool dummy;
+    if (getPositionInRefElem(o, PartState, PartPosRef, ElemID, false, false, false, &dummy) != NEWTON_OK) return TRACK_ERROR;
+    if (maxabs(PartPosRef) < 1.0) { *GlobalElemID = ElemID; return TRACK_OK; }
+  } else {
+    bool dummy;
+    getPositionInRefElem(o, PartState, PartPosRef, ElemID, true, false, false, &dummy);   // DoReUseMap=.TRUE. (result overwritten)
+    if (getPositionInRefElem(o, PartState, PartPosRef, ElemID, false, false, false, &dummy) != NEWTON_OK) return TRACK_ERROR;
+    if (maxabs(PartPosRef) < 1.0) { *GlobalElemID = ElemID; return TRACK_OK; }
+  }
+  // relocate particle
+  int oldElemID = LastGlobalElemID;
+  const int* mx = o.m.FIBGMmax;
+  int CellX = std::max((int)std::floor((PartState[0] - o.m.xyzminglob[0]) / o.m.FIBGMdeltas[0]), 0) + 1; CellX = std::min(mx[0], CellX);
+  int CellY = std::max((int)std::floor((PartState[1] - o.m.xyzminglob[1]) / o.m.FIBGMdeltas[1]), 0) + 1; CellY = std::min(mx[1], CellY);
+  int CellZ = std::max((int)std::floor((PartState[2] - o.m.xyzminglob[2]) / o.m.FIBGMdeltas[2]), 0) + 1; CellZ = std::min(mx[2], CellZ);
+  const size_t cell = bgmCell(o, CellX, CellY, CellZ);
+  const int nBGMElems = o.m.FIBGM_nElems[cell];
+  std::vector<double> Distance(std::max(nBGMElems, 1));
+  std::vector<int> ListDistance(std::max(nBGMElems, 1));
+  if (nBGMElems > 1) {
+    for (int i = 0; i < nBGMElems; ++i) {
+      const int e = o.m.FIBGM_Element[o.m.FIBGM_offsetElem[cell] + i];
+      ListDistance[i] = e;
+      if (e == oldElemID) Distance[i] = -HUGE_D;
+      else {
+        const double* b = o.m.ElemBaryNGeo + (size_t)(e - 1) * 3;
+        const double d0 = PartState[0] - b[0], d1 = PartState[1] - b[1], d2 = PartState[2] - b[2];
+        Distance[i] = (d0 * d0 + d1 * d1) + d2 * d2;
+        if (Distance[i] > o.m.ElemRadius2NGeo[e - 1]) Distance[i] = -HUGE_D;
+      }
+    }
+    insertionSort(Distance.data(), ListDistance.data(), nBGMElems);
+  } else if (nBGMElems == 1) {
+    Distance[0] = 0.;
+    ListDistance[0] = o.m.FIBGM_Element[o.m.FIBGM_offsetElem[cell]];
+  }
+  double OldXi[3] = {PartPosRef[0], PartPosRef[1], PartPosRef[2]};
+  double newXi[3] = {HUGE_D, HUGE_D, HUGE_D};
+  int newElemID = -1;
+  for (int i = 0; i < nBGMElems; ++i) {
+    if (Distance[i] == -HUGE_D) continue;
+    ElemID = ListDistance[i];
+    bool dummy;
+    if (getPositionInRefElem(o, PartState, PartPosRef, ElemID, false, false, false, &dummy) != NEWTON_OK) return TRACK_ERROR;
+    if (maxabs(PartPosRef) < 1.0) { *GlobalElemID = ElemID; PartIsDone = true; break; }
+    if (maxabs(PartPosRef) < maxabs(newXi)) { newXi[0] = PartPosRef[0]; newXi[1] = PartPosRef[1]; newXi[2] = PartPosRef[2]; newElemID = ElemID; }
+  }
+  if (!PartIsDone) {
+    if (maxabs(OldXi) < maxabs(newXi)) {
+      PartPosRef[0] = OldXi[0]; PartPosRef[1] = OldXi[1]; PartPosRef[2] = OldXi[2];
+      *GlobalElemID = oldElemID;
+    } else {
+      PartPosRef[0] = newXi[0]; PartPosRef[1] = newXi[1]; PartPosRef[2] = newXi[2];
+      *GlobalElemID = newElemID;
+      oldElemID = newElemID;
+    }
+    int TestElem = *GlobalElemID;
+    if (TestElem < 1) { o.err = "ParticleRefTracking: particle could not be relocated"; return TRACK_ERROR; }
+    const double epsElement = o.m.ElemEpsOneCell[TestElem - 1];
+    if (maxabs(PartPosRef) > epsElement) {
+      if (o.m.ElemToBCSides[(size_t)(TestElem - 1) * 2] <= 0) {
+        o.err = "Particle not inside of Element (tolerance issue with internal element)";   // :311-313 abort
+        return TRACK_ERROR;
+      }
+      PartIsDone = false;
+      if (particleBCTracking(o, 0., &TestElem, c, &PartIsDone, &PartIsMoved, GlobalElemID)) return TRACK_ERROR;
+      if (PartIsDone) { *inside = c.inside; return c.inside ? TRACK_OK : TRACK_REMOVED_BC; }
+      bool dummy;
+      if (getPositionInRefElem(o, PartState, PartPosRef, TestElem, false, false, false, &dummy) != NEWTON_OK) return TRACK_ERROR;
+      if (maxabs(PartPosRef) > o.m.ElemEpsOneCell[TestElem - 1]) {
+        o.err = "ParticleRefTracking: tolerance issue with BC element (LocateParticleInElement fallback not restated)";
+        return TRACK_ERROR;
+      }
+      *GlobalElemID = TestElem;
+    }
+  }
+  return TRACK_OK;
+}
+
 }  // namespace
 
 // ================================================================================================================
@@ -1106,8 +1367,16 @@ static int push_track_range(Oracle& o, double dt, int64_t i0, int64_t i1, double
         else if (tr == TRACK_REMOVED_BC) { ParticleInside[i] = 0; }
         else GlobalElemID[i] = newElem;
       }
+    } else if (o.p.TrackingMethod == PGPU_REFMAPPING) {
+      if (!PartPosRef) { o.err = "RefMapping needs PartPosRef"; return 4; }
+      int newElem = GlobalElemID[i];
+      bool in = true;
+      TrackResult tr = singleParticleRefTracking(o, ps, lp, PartPosRef + 3 * i, LastGlobalElemID, &newElem, &in);
+      if (tr == TRACK_ERROR) return 3;
+      if (tr == TRACK_REMOVED_BC) ParticleInside[i] = 0;
+      else GlobalElemID[i] = newElem;
     } else {
-      o.err = "tracking method not supported by the oracle yet";
+      o.err = "tracking method not supported by the oracle";
       return 4;
     }
   }

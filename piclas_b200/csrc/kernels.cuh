@@ -219,7 +219,9 @@ __device__ __forceinline__ void evaluate_field_tile(const double xi[3], const do
 // (particle_triatracking.f90:203-218) for the particles of one element per CTA iteration.
 // Stayers: x, v written in place, key = own element.  Leavers: v written in place, the pushed position goes to xNew
 // (the idle half of the double buffer) while pb.x keeps LastPartPos; their index is appended to leaverIdx.
-template <int NP, bool FAST>
+// REF (TrackingMethod = refmapping): the reference coordinates are the stored PartPosRef (pic_interpolation_tools.f90:243), the
+// pushed position of every particle goes to xn and pb.x keeps LastPartPos for k_track_ref (no inside test here).
+template <int NP, bool FAST, bool REF>
 __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, double* __restrict__ xn0, double* __restrict__ xn1,
                                                             double* __restrict__ xn2, const int64_t* __restrict__ elemOff, int nElems,
                                                             int offsetElem, const GeoElem* __restrict__ geo,
@@ -239,12 +241,12 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
     if (p1 <= p0) continue;
     const int gElem = offsetElem + e + 1;
     __syncthreads();
-    if (!xiValid) {
+    if (!xiValid && !REF) {
       stage_words(&sg, geo + (gElem - 1), sizeof(GeoElem));
       if (FAST) stage_words(&sa, aff + (gElem - 1), sizeof(AffElem));
     }
-    if (FAST) stage_words(&sp, planes + (gElem - 1), sizeof(PlaneElem));
-    stage_words(&st, tria + (gElem - 1), sizeof(TriaElem));
+    if (FAST && !REF) stage_words(&sp, planes + (gElem - 1), sizeof(PlaneElem));
+    if (!REF) stage_words(&st, tria + (gElem - 1), sizeof(TriaElem));
     for (int t = threadIdx.x; t < ND * 3; t += STEP_NT) {
       const int c = t % 3, node = t / 3;
       const int i = node % NP, kj = node / NP;
@@ -265,7 +267,10 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
       if (cst.DoInterpolation && fabs(q) > 0.0) {  // isInterpolateParticle
         double xi[3];
         bool suc;
-        if (xiValid) {
+        if (REF) {
+          xi[0] = pb.xi[0][p]; xi[1] = pb.xi[1][p]; xi[2] = pb.xi[2][p];
+          suc = true;
+        } else if (xiValid) {
           xi[0] = pb.xi[0][p]; xi[1] = pb.xi[1][p]; xi[2] = pb.xi[2][p];
           suc = !(meta & META_XIFAIL);
         } else if (FAST) {
@@ -292,6 +297,10 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
       pb.v[0][p] = v[0]; pb.v[1][p] = v[1]; pb.v[2][p] = v[2];
       const uint8_t nmeta = (uint8_t)(meta & META_SPEC_MASK);  // IsNewPart and the xi flag are consumed
       if (nmeta != meta) pb.meta[p] = nmeta;
+      if (REF) {
+        xn0[p] = x[0]; xn1[p] = x[1]; xn2[p] = x[2];
+        continue;
+      }
       uint32_t mask;
       const bool inElem = FAST ? inside_fast(&sp, &st, x, mask) : inside_quad3d_mask(&st, x, mask);
       if (inElem) {

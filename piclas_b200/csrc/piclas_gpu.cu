@@ -10,6 +10,7 @@
 
 #include "kernels.cuh"
 #include "sf.cuh"
+#include "ref.cuh"
 #include "sort.cuh"
 
 namespace {
@@ -39,6 +40,13 @@ struct Ctx {
   int32_t *dAdjOff = nullptr, *dAdj = nullptr, *dElemNodeU = nullptr;
   int32_t *dPerN = nullptr, *dPerOff = nullptr, *dPerNodes = nullptr;
   double *dNodeVolume = nullptr, *dElemAcc = nullptr, *dS = nullptr, *dNodeSource = nullptr, *dPartSource = nullptr;
+  // RefMapping
+  bool ref = false;
+  RefTables refT;
+  double* dXiB[3] = {nullptr, nullptr, nullptr};   // second PartPosRef buffer (RefMapping: PartPosRef is particle state)
+  int32_t *dElemToBCSides = nullptr, *dSideInfo = nullptr;
+  double *dSideBCMetrics = nullptr, *dSideNormVec = nullptr, *dSideDistance = nullptr, *dBV0 = nullptr, *dBV1 = nullptr, *dBV2 = nullptr;
+  double *dElemRadius2 = nullptr, *dElemEpsOneCell = nullptr;
   // shape function
   bool sfActive = false;
   SFTables sfT;
@@ -127,6 +135,8 @@ int reserve_particles(int64_t need) {
   int64_t ncap = need + need / 8 + 1024;
   if (g.prm.maxParticleNumber > ncap) ncap = g.prm.maxParticleNumber;
   PartBuf nb[2];
+  double* oldXi[3] = {nullptr, nullptr, nullptr};
+  if (g.cap > 0) for (int d = 0; d < 3; ++d) oldXi[d] = g.buf[g.cur].xi[d];
   if (alloc_partbuf(nb[0], ncap, g.carryIDs)) return 1;
   if (alloc_partbuf(nb[1], ncap, g.carryIDs)) return 1;
   if (g.cap > 0 && g.nPart > 0) {
@@ -144,9 +154,17 @@ int reserve_particles(int64_t need) {
     free_partbuf(g.buf[1]);
   }
   for (int d = 0; d < 3; ++d) {
+    double* nx = nullptr;
+    CK(cudaMalloc((void**)&nx, ncap * 8));
+    if (g.ref && g.cap > 0 && g.nPart > 0 && oldXi[d]) CK(cudaMemcpy(nx, oldXi[d], g.nPart * 8, cudaMemcpyDeviceToDevice));
     cudaFree(g.dXi[d]);
-    CK(cudaMalloc((void**)&g.dXi[d], ncap * 8));
+    g.dXi[d] = nx;
     nb[0].xi[d] = nb[1].xi[d] = g.dXi[d];
+    if (g.ref) {
+      cudaFree(g.dXiB[d]);
+      CK(cudaMalloc((void**)&g.dXiB[d], ncap * 8));
+      nb[1].xi[d] = g.dXiB[d];
+    }
   }
   g.buf[0] = nb[0];
   g.buf[1] = nb[1];
@@ -171,7 +189,7 @@ int reserve_stage(int64_t n) {
 
 __global__ void k_aos_to_soa(PartBuf pb, int64_t dst0, int64_t n, const double* __restrict__ ps, const int32_t* __restrict__ spec,
                              const int32_t* __restrict__ elem, const int32_t* __restrict__ inside, const int32_t* __restrict__ isnew,
-                             const int64_t* __restrict__ ids, int64_t idBase) {
+                             const int64_t* __restrict__ ids, int64_t idBase, const double* __restrict__ ref) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t p = dst0 + i;
@@ -184,6 +202,10 @@ __global__ void k_aos_to_soa(PartBuf pb, int64_t dst0, int64_t n, const double* 
   pb.elem[p] = in ? elem[i] : 0;
   pb.meta[p] = (uint8_t)(((spec[i] - 1) & META_SPEC_MASK) | ((isnew && isnew[i]) ? META_ISNEW : 0));
   if (pb.id) pb.id[p] = ids ? ids[i] : (idBase + i);
+  if (ref) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) pb.xi[d][p] = ref[i * 3 + d];
+  }
 }
 
 __global__ void k_soa_to_aos(PartBuf pb, int64_t src0, int64_t n, double* __restrict__ ps, int32_t* __restrict__ spec,
@@ -204,7 +226,7 @@ __global__ void k_soa_to_aos(PartBuf pb, int64_t src0, int64_t n, double* __rest
 
 // message layout of one migrating particle (particle_mpi.f90:472-502, TriaTracking, no LSERK/vMPF/DSMC):
 // PartState(1:6), REAL(PartSpecies), REAL(PEM%GlobalElemID) [, particle id bits when ids are carried]
-__global__ void k_pack_emigrants(PartBuf pb, int64_t src0, int64_t n, int cs, double* __restrict__ buf) {
+__global__ void k_pack_emigrants(PartBuf pb, int64_t src0, int64_t n, int cs, int withRef, double* __restrict__ buf) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t p = src0 + i;
@@ -214,13 +236,15 @@ __global__ void k_pack_emigrants(PartBuf pb, int64_t src0, int64_t n, int cs, do
     b[d] = pb.x[d][p];
     b[3 + d] = pb.v[d][p];
   }
-  b[6] = (double)((pb.meta[p] & META_SPEC_MASK) + 1);
-  b[7] = (double)pb.elem[p];
-  if (cs > 8) b[8] = __longlong_as_double(pb.id ? pb.id[p] : -1);
+  int o = 6;
+  if (withRef) { b[6] = pb.xi[0][p]; b[7] = pb.xi[1][p]; b[8] = pb.xi[2][p]; o = 9; }   // PartPosRef (RefMapping)
+  b[o] = (double)((pb.meta[p] & META_SPEC_MASK) + 1);
+  b[o + 1] = (double)pb.elem[p];
+  if (cs > o + 2) b[o + 2] = __longlong_as_double(pb.id ? pb.id[p] : -1);
 }
 
 // MPIParticleRecv unpack (particle_mpi.f90:831-989): received particles are appended; IsNewPart = F
-__global__ void k_unpack_immigrants(PartBuf pb, int64_t dst0, int64_t n, int cs, const double* __restrict__ buf) {
+__global__ void k_unpack_immigrants(PartBuf pb, int64_t dst0, int64_t n, int cs, int withRef, const double* __restrict__ buf) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t p = dst0 + i;
@@ -230,9 +254,11 @@ __global__ void k_unpack_immigrants(PartBuf pb, int64_t dst0, int64_t n, int cs,
     pb.x[d][p] = b[d];
     pb.v[d][p] = b[3 + d];
   }
-  pb.meta[p] = (uint8_t)(((int)b[6] - 1) & META_SPEC_MASK);
-  pb.elem[p] = (int)b[7];
-  if (pb.id) pb.id[p] = (cs > 8) ? __double_as_longlong(b[8]) : -1;
+  int o = 6;
+  if (withRef) { pb.xi[0][p] = b[6]; pb.xi[1][p] = b[7]; pb.xi[2][p] = b[8]; o = 9; }
+  pb.meta[p] = (uint8_t)(((int)b[o] - 1) & META_SPEC_MASK);
+  pb.elem[p] = (int)b[o + 1];
+  if (pb.id) pb.id[p] = (cs > o + 2) ? __double_as_longlong(b[o + 2]) : -1;
 }
 
 // sort the first nIn particles of the current buffer by key (keys already in g.dKeys), gather into the other buffer
@@ -243,6 +269,10 @@ int sort_and_permute(int64_t nIn) {
   PartBuf& b = g.buf[g.cur ^ 1];
   CK(gather_particles(a.x, a.v, a.elem, a.meta, g.carryIDs ? a.id : nullptr, b.x, b.v, b.elem, b.meta, b.id, perm, (size_t)nIn, g.st));
   ++g.lastLaunches;
+  if (g.ref) {
+    for (int d = 0; d < 3; ++d) CK(gather_f64(a.xi[d], b.xi[d], perm, (size_t)nIn, g.st));
+    g.lastLaunches += 3;
+  }
   const uint32_t nKeys = (uint32_t)(g.nElems + g.nRanks + 1);
   CK(segment_offsets(sk, (size_t)nIn, nKeys, g.dElemOff, g.st));
   ++g.lastLaunches;
@@ -261,11 +291,19 @@ void launch_push_track_t(double dt) {
   const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
   const PartBuf& o = g.buf[g.cur ^ 1];
   uint32_t* leaverIdx = g.sortws.permB;  // idle until the sort that follows
-  k_interp_push<NP, FAST><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem,
-                                                     g.dGeo, g.dTria, g.dPlanes, g.dAff, g.dE, g.dElemXGP, g.dKeys, leaverIdx, dt,
-                                                     g.xiValid ? 1 : 0, g.dCounters);
-  k_track_leavers<FAST><<<g.nSMs * 8, 128, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, g.dTria, g.dPlanes,
-                                                      g.dElemRank, g.dKeys, g.nElems, g.offsetElem, g.dCounters);
+  if (g.ref) {
+    k_interp_push<NP, FAST, true><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem,
+                                                             g.dGeo, g.dTria, g.dPlanes, g.dAff, g.dE, g.dElemXGP, g.dKeys, leaverIdx,
+                                                             dt, 1, g.dCounters);
+    k_track_ref<<<g.nSMs * 8, 128, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.nPart, g.refT, g.dElemRank, g.dKeys, g.nElems,
+                                              g.offsetElem, g.dCounters);
+  } else {
+    k_interp_push<NP, FAST, false><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem,
+                                                              g.dGeo, g.dTria, g.dPlanes, g.dAff, g.dE, g.dElemXGP, g.dKeys, leaverIdx,
+                                                              dt, g.xiValid ? 1 : 0, g.dCounters);
+    k_track_leavers<FAST><<<g.nSMs * 8, 128, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, g.dTria, g.dPlanes,
+                                                        g.dElemRank, g.dKeys, g.nElems, g.offsetElem, g.dCounters);
+  }
   g.lastLaunches += 2;
 }
 template <int NP>
@@ -310,6 +348,9 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dFibN); cudaFree(g.dFibOff); cudaFree(g.dFibElem); cudaFree(g.dElemToBGM); cudaFree(g.dCandOff); cudaFree(g.dCandSrc);
   cudaFree(g.dCandCase); cudaFree(g.dElemBary); cudaFree(g.dElemRadius); cudaFree(g.dElemsJ); cudaFree(g.dSFElemr2);
   for (int c = 0; c < 4; ++c) cudaFree(g.dSfFac[c]);
+  for (int d = 0; d < 3; ++d) cudaFree(g.dXiB[d]);
+  cudaFree(g.dElemToBCSides); cudaFree(g.dSideInfo); cudaFree(g.dSideBCMetrics); cudaFree(g.dSideNormVec); cudaFree(g.dSideDistance);
+  cudaFree(g.dBV0); cudaFree(g.dBV1); cudaFree(g.dBV2); cudaFree(g.dElemRadius2); cudaFree(g.dElemEpsOneCell);
   if (g.cap > 0) {
     free_partbuf(g.buf[0]);
     free_partbuf(g.buf[1]);
@@ -331,7 +372,23 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   // ---- what this build supports; everything else aborts loudly ----------------------
   if (m->NGeo != 1) return fail("piclas_gpu_init: NGeo=%d not supported (straight-sided NGeo=1 meshes only)", m->NGeo);
   if (m->N < 1 || m->N > PGPU_MAX_N) return fail("piclas_gpu_init: N=%d outside 1..%d", m->N, PGPU_MAX_N);
-  if (p->TrackingMethod != PGPU_TRIATRACKING) return fail("piclas_gpu_init: TrackingMethod=%d not supported yet (triatracking only)", p->TrackingMethod);
+  if (p->TrackingMethod != PGPU_TRIATRACKING && p->TrackingMethod != PGPU_REFMAPPING)
+    return fail("piclas_gpu_init: TrackingMethod=%d not supported (triatracking, refmapping)", p->TrackingMethod);
+  const bool isRef = p->TrackingMethod == PGPU_REFMAPPING;
+  if (isRef) {
+    if (p->DoDeposition && p->DepositionType == PGPU_DEPO_CVWM)
+      return fail("piclas_gpu_init: cell_volweight_mean requires TrackingMethod=triatracking (pic_depo_method.f90:127-129)");
+    if (!m->ElemToBCSides || !m->SideBCMetrics || !m->SideType || !m->SideNormVec || !m->SideDistance || !m->BaseVectors0 ||
+        !m->BaseVectors1 || !m->BaseVectors2 || !m->ElemEpsOneCell || !m->ElemRadiusNGeo || !m->FIBGM_nElems || !m->FIBGM_offsetElem ||
+        !m->FIBGM_Element)
+      return fail("piclas_gpu_init: refmapping needs ElemToBCSides, SideBCMetrics, SideType, SideNormVec, SideDistance, BaseVectors0-2, "
+                  "ElemEpsOneCell, ElemRadiusNGeo and the FIBGM tables");
+    for (int b = 0; b < m->nBCSidesTotal; ++b) {
+      const int sid = (int)m->SideBCMetrics[(size_t)b * 7];
+      if (sid < 1 || sid > m->nSides) return fail("piclas_gpu_init: SideBCMetrics holds an invalid side id");
+      if (m->SideType[sid - 1] != 0) return fail("piclas_gpu_init: BC side %d is not PLANAR_RECT (bilinear/curved intersections are not supported)", sid);
+    }
+  }
   const bool isSF = p->DepositionType == PGPU_DEPO_SF || p->DepositionType == PGPU_DEPO_SF_CC || p->DepositionType == PGPU_DEPO_SF_ADAPTIVE;
   if (p->DoDeposition && p->DepositionType != PGPU_DEPO_CVWM && !isSF)
     return fail("piclas_gpu_init: PIC-Deposition-Type %d not supported (cell_volweight_mean, shape_function, shape_function_cc, shape_function_adaptive)", p->DepositionType);
@@ -379,7 +436,7 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   g.nRanks = p->nRanks;
   g.myRank = p->myRank;
   g.carryIDs = p->carryParticleIDs != 0;
-  g.commSize = g.carryIDs ? 9 : 8;
+  g.commSize = 8 + (p->TrackingMethod == PGPU_REFMAPPING ? 3 : 0) + (g.carryIDs ? 1 : 0);  // particle_mpi.f90:158-183
   const int nG = m->nGlobalElems;
 
   // ---- per-element records ------------------------------------------------------------------------------------
@@ -513,8 +570,36 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     CK(cudaMalloc((void**)&g.dPartSource, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 4 * 8));
   }
 
-  // ---- shape-function tables and gather candidates ------------------------------------------------------------------
+  // ---- tables shared by RefMapping and the shape functions -----------------------------------------------------------
   g.sfActive = p->DoDeposition && isSF;
+  g.ref = isRef;
+  if (g.sfActive || g.ref) {
+    const int ni0 = m->FIBGMmax[0] - m->FIBGMmin[0] + 1, nj0 = m->FIBGMmax[1] - m->FIBGMmin[1] + 1, nk0 = m->FIBGMmax[2] - m->FIBGMmin[2] + 1;
+    const size_t nCells0 = (size_t)ni0 * nj0 * nk0;
+    if (upload(&g.dFibN, m->FIBGM_nElems, nCells0)) return 1;
+    if (upload(&g.dFibOff, m->FIBGM_offsetElem, nCells0)) return 1;
+    if (upload(&g.dFibElem, m->FIBGM_Element, (size_t)m->nFIBGMElemsTotal)) return 1;
+    if (upload(&g.dElemBary, m->ElemBaryNGeo, (size_t)nG * 3)) return 1;
+    if (upload(&g.dElemRadius, m->ElemRadiusNGeo, (size_t)nG)) return 1;
+  }
+  if (g.ref) {
+    if (upload(&g.dElemToBCSides, m->ElemToBCSides, (size_t)nG * 2)) return 1;
+    if (upload(&g.dSideBCMetrics, m->SideBCMetrics, (size_t)m->nBCSidesTotal * 7)) return 1;
+    if (upload(&g.dSideInfo, m->SideInfo, (size_t)m->nSides * m->sideInfoSize)) return 1;
+    if (upload(&g.dSideNormVec, m->SideNormVec, (size_t)m->nSides * 3)) return 1;
+    if (upload(&g.dSideDistance, m->SideDistance, (size_t)m->nSides)) return 1;
+    if (upload(&g.dBV0, m->BaseVectors0, (size_t)m->nSides * 3)) return 1;
+    if (upload(&g.dBV1, m->BaseVectors1, (size_t)m->nSides * 3)) return 1;
+    if (upload(&g.dBV2, m->BaseVectors2, (size_t)m->nSides * 3)) return 1;
+    if (upload(&g.dElemRadius2, m->ElemRadius2NGeo, (size_t)nG)) return 1;
+    if (upload(&g.dElemEpsOneCell, m->ElemEpsOneCell, (size_t)nG)) return 1;
+    g.refT.geo = g.dGeo; g.refT.ElemToBCSides = g.dElemToBCSides; g.refT.SideBCMetrics = g.dSideBCMetrics; g.refT.SideInfo = g.dSideInfo;
+    g.refT.sideInfoSize = m->sideInfoSize; g.refT.SideNormVec = g.dSideNormVec; g.refT.SideDistance = g.dSideDistance;
+    g.refT.BaseVectors0 = g.dBV0; g.refT.BaseVectors1 = g.dBV1; g.refT.BaseVectors2 = g.dBV2; g.refT.ElemBary = g.dElemBary;
+    g.refT.ElemRadius = g.dElemRadius; g.refT.ElemRadius2 = g.dElemRadius2; g.refT.ElemEpsOneCell = g.dElemEpsOneCell;
+    g.refT.FIBGM_nElems = g.dFibN; g.refT.FIBGM_offsetElem = g.dFibOff; g.refT.FIBGM_Element = g.dFibElem;
+  }
+  // ---- shape-function tables and gather candidates ------------------------------------------------------------------
   int sfCaseM[27][3];
   memset(sfCaseM, 0, sizeof(sfCaseM));
   int nSFCases = 0, sfDir1 = (p->dim_sf_dir == 2) ? 1 : 2, sfDir2 = (p->dim_sf_dir == 3) ? 1 : 3, pvec1 = 0, pvec2 = 0;
@@ -546,12 +631,8 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     }
     const int ni = m->FIBGMmax[0] - m->FIBGMmin[0] + 1, nj = m->FIBGMmax[1] - m->FIBGMmin[1] + 1, nk = m->FIBGMmax[2] - m->FIBGMmin[2] + 1;
     const size_t nCells = (size_t)ni * nj * nk;
-    if (upload(&g.dFibN, m->FIBGM_nElems, nCells)) return 1;
-    if (upload(&g.dFibOff, m->FIBGM_offsetElem, nCells)) return 1;
-    if (upload(&g.dFibElem, m->FIBGM_Element, (size_t)m->nFIBGMElemsTotal)) return 1;
+    (void)nCells;
     if (upload(&g.dElemToBGM, m->ElemToBGM, (size_t)nG * 6)) return 1;
-    if (upload(&g.dElemBary, m->ElemBaryNGeo, (size_t)nG * 3)) return 1;
-    if (upload(&g.dElemRadius, m->ElemRadiusNGeo, (size_t)nG)) return 1;
     if (upload(&g.dElemsJ, m->ElemsJ, (size_t)nG * g.ND)) return 1;
     if (m->SFElemr2 && upload(&g.dSFElemr2, m->SFElemr2, (size_t)nG * 2)) return 1;
     // candidates: (source element s, case c) can reach target e iff SFNorm(bary_e - (bary_s + shift_c)) <= r + R_e + R_s
@@ -684,7 +765,6 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
                                 const int32_t* ParticleInside, const int32_t* IsNewPart, const double* PartPosRef,
                                 const int64_t* ids, int32_t append) {
   if (!g.ready) return fail("piclas_gpu_upload_particles: not initialised");
-  (void)PartPosRef;
   CK(cudaSetDevice(g.device));
   if (n < 0) return fail("piclas_gpu_upload_particles: n < 0");
   if (n > 0 && (!PartState || !PartSpecies || !GlobalElemID)) return fail("piclas_gpu_upload_particles: null array");
@@ -703,11 +783,19 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
     if (ParticleInside) CK(cudaMemcpyAsync(dI + 2 * g.stageCap, ParticleInside + c0, m * 4, cudaMemcpyHostToDevice, g.st));
     if (IsNewPart) CK(cudaMemcpyAsync(dI + 3 * g.stageCap, IsNewPart + c0, m * 4, cudaMemcpyHostToDevice, g.st));
     if (ids && g.carryIDs) CK(cudaMemcpyAsync(g.dStageL, ids + c0, m * 8, cudaMemcpyHostToDevice, g.st));
+    double* dRef = g.dStage + 6 * g.stageCap;
+    const bool haveRef = g.ref && PartPosRef;
+    if (haveRef) CK(cudaMemcpyAsync(dRef, PartPosRef + c0 * 3, m * 3 * 8, cudaMemcpyHostToDevice, g.st));
     k_aos_to_soa<<<(unsigned)((m + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], base + c0, m, g.dStage, dI, dI + g.stageCap,
                                                                ParticleInside ? dI + 2 * g.stageCap : nullptr,
                                                                IsNewPart ? dI + 3 * g.stageCap : nullptr,
-                                                               (ids && g.carryIDs) ? g.dStageL : nullptr, base + c0);
+                                                               (ids && g.carryIDs) ? g.dStageL : nullptr, base + c0,
+                                                               haveRef ? dRef : nullptr);
     ++g.lastLaunches;
+    if (g.ref && !PartPosRef) {  // as at emission: PartPosRef from GetPositionInRefElem in the particle's element
+      k_init_posref<<<(unsigned)((m + 127) / 128), 128, 0, g.st>>>(g.buf[g.cur], base + c0, m, g.dGeo);
+      ++g.lastLaunches;
+    }
     CK(cudaStreamSynchronize(g.st));
   }
   const int64_t nIn = base + n;
@@ -732,7 +820,7 @@ int piclas_gpu_download_particles(int64_t nmax, double* PartState, int32_t* Part
   const int64_t n = g.nPart;
   if (n_out) *n_out = n;
   if (n > nmax) return fail("piclas_gpu_download_particles: %lld particles do not fit into nmax=%lld", (long long)n, (long long)nmax);
-  if (PartPosRef && !g.xiValid) return fail("piclas_gpu_download_particles: reference positions are not current (call deposit first)");
+  if (PartPosRef && !g.xiValid && !g.ref) return fail("piclas_gpu_download_particles: reference positions are not current (call deposit first)");
   const int64_t chunk = 1 << 22;
   if (reserve_stage(n < chunk ? (n ? n : 1) : chunk)) return 1;
   for (int64_t c0 = 0; c0 < n; c0 += chunk) {
@@ -939,7 +1027,7 @@ int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void*
     CK(cudaMalloc((void**)&g.dCommSend, g.commSendCap * g.commSize * 8));
   }
   if (nSend > 0) {
-    k_pack_emigrants<<<(unsigned)((nSend + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.nPart, nSend, g.commSize, g.dCommSend);
+    k_pack_emigrants<<<(unsigned)((nSend + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.nPart, nSend, g.commSize, g.ref ? 1 : 0, g.dCommSend);
     ++g.lastLaunches;
     CK(cudaGetLastError());
   }
@@ -973,7 +1061,7 @@ int piclas_gpu_exchange_finish(int64_t nRecvTotal) {
   if (g.nPart + nRecvTotal >= (int64_t)0x7fffffff) return fail("piclas_gpu_exchange_finish: more than 2^31-1 particles on one GPU");
   if (reserve_particles(g.nPart + nRecvTotal)) return 1;
   (void)nEmig;
-  k_unpack_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.nPart, nRecvTotal, g.commSize, g.dCommRecv);
+  k_unpack_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.nPart, nRecvTotal, g.commSize, g.ref ? 1 : 0, g.dCommRecv);
   const int64_t nIn = g.nPart + nRecvTotal;
   k_keys_from_elem<<<(unsigned)((nIn + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur].elem, g.dElemRank, g.dKeys, nIn, g.nElems,
                                                                     g.offsetElem, g.myRank, g.nRanks);

@@ -518,3 +518,107 @@ def shape_function_setup(mesh: ParticleMesh, params, r_sf, alpha_sf, dim_sf=3, d
     params.r_sf, params.alpha_sf, params.dim_sf, params.dim_sf_dir = float(r_sf), int(alpha_sf), int(dim_sf), int(dim_sf_dir)
     params.sfDepo3D, params.w_sf, params.dimFactorSF = int(bool(sfDepo3D)), float(w_sf), float(dimFactorSF)
     return params
+
+
+def add_refmapping_tables(mesh: ParticleMesh, bc_halo_eps=None, RefMappingEps=1e-4):
+    """Side and BC-side tables of the RefMapping tracking (TrackingMethod = refmapping), straight-sided NGeo = 1 meshes.
+
+    BaseVectors0/1/2            particle_mesh_build.f90:1833-1940 (Bezier control points of an NGeo = 1 side = its 4 corners)
+    SideType/NormVec/Distance   particle_mesh_tools.f90:848-1056 (IdentifyElemAndSideType, linear-element branch)
+    BCSideMetrics               particle_mesh_build.f90:1688-1830 (side origin = bilinear centre, radius = farthest corner)
+    ElemToBCSides/SideBCMetrics particle_mesh_build.f90:645-1092  (BuildBCElemDistance; every SIDE_BCID>0 side is a BC side,
+                                periodic ones included; an element lists its own BC sides and those within BC_halo_eps,
+                                sorted by distance with the stable InsertionSort of utils.f90:52-101)
+    ElemEpsOneCell              particle_mesh_build.f90:447-642   (1 + sqrt(3 scaleJ RefMappingEps))
+    bc_halo_eps: halo_eps_velo*dt*SafetyFactor of the MPI build; None -> every element sees every BC side (the fullMesh
+    branch, which is also what the single-rank build of the reference does).
+    """
+    if mesh.tracking != REFMAPPING:
+        raise ValueError("build the mesh with tracking=REFMAPPING (ElemBaryNGeo = X(xi=0))")
+    if "FIBGM" not in mesh.extra:
+        add_fibgm(mesh)
+    nE, nS = mesh.nElems, mesh.nSides
+    P = mesh.NodeCoords[mesh.ElemSideNodeID.reshape(nS, 4)]             # p00, p10, p11, p01 = side nodes 1..4
+    p00, p10, p11, p01 = P[:, 0], P[:, 1], P[:, 2], P[:, 3]
+    BV0 = (+p00 + p10 + p01 + p11)
+    BV1 = (-p00 + p10 - p01 + p11)
+    BV2 = (-p00 - p10 + p01 + p11)
+    cr = np.cross(BV1, BV2)
+    nrm = cr / np.sqrt((cr * cr).sum(axis=1))[:, None]                   # CROSSNORM(v1,v2)
+    centre = 0.25 * (p00 + p10 + p01 + p11)
+    elem_of_side = np.arange(nS) // 6
+    v2 = centre - mesh.ElemBaryNGeo[elem_of_side]
+    S = mesh.SideInfo
+    flip = np.where(S[:, 1] > 0, 0, S[:, 3] % 10)
+    dot = (v2 * nrm).sum(axis=1)
+    sign = np.where(flip == 0, np.where(dot < 0, -1.0, 1.0), np.where(dot > 0, -1.0, 1.0))
+    SideNormVec = nrm * sign[:, None]
+    SideDistance = (centre * SideNormVec).sum(axis=1)
+
+    def unit(v):
+        n = np.sqrt((v * v).sum(axis=1))
+        return np.where(n[:, None] > 0, v / np.where(n > 0, n, 1.0)[:, None], 0.0)
+    az = lambda a: np.abs(a) <= 2.22e-16                                  # ALMOSTZERO, piclas.h:83
+    e1, e2, e3, e4 = unit(p01 - p00), unit(p10 - p00), unit(p11 - p01), unit(p11 - p10)
+    rect = az((e1 * e2).sum(1)) & az((e1 * e3).sum(1)) & az((e4 * e2).sum(1)) & az((e4 * e3).sum(1))
+    # planarity: the 4th corner lies in the plane of the other three
+    planar = np.abs(((p11 - p00) * np.cross(p10 - p00, p01 - p00)).sum(1)) <= 1e-12 * np.abs(cr).max()
+    SideType = np.where(planar & rect, 0, np.where(planar, 1, 2)).astype(np.int32)   # PLANAR_RECT / PLANAR_NONRECT / BILINEAR
+
+    # BC sides (periodic included)
+    bc_sides = np.nonzero(S[:, 4] > 0)[0]                                 # 0-based side index, ascending == BCSide order
+    origin = centre[bc_sides]
+    radius = np.sqrt(np.max(((P[bc_sides] - origin[:, None, :]) ** 2).sum(axis=2), axis=1))
+    ElemRadius = mesh.extra["ElemRadiusNGeo"] if "ElemRadiusNGeo" in mesh.extra else np.sqrt(mesh.ElemRadius2NGeo)
+    bary = mesh.ElemBaryNGeo
+    diag = np.linalg.norm(mesh.xyz_max - mesh.xyz_min)
+    full = bc_halo_eps is None or bc_halo_eps >= diag
+    tree = None if full else cKDTree(origin)
+    maxr = radius.max() if radius.size else 0.0
+    ElemToBCSides = np.full((nE, 2), -1, dtype=np.int32)
+    rows = []
+    off = 0
+    bc_elem = bc_sides // 6
+    for e in range(nE):
+        own = bc_sides[bc_elem == e] if bc_sides.size else bc_sides
+        if full:
+            other_idx = np.nonzero(bc_elem != e)[0]
+        else:
+            cand = np.array(sorted(tree.query_ball_point(bary[e], bc_halo_eps + ElemRadius[e] + maxr)), dtype=np.int64)
+            if cand.size:
+                cand = cand[bc_elem[cand] != e]
+                be = bc_elem[cand]
+                ok = np.linalg.norm(bary[e] - bary[be], axis=1) <= bc_halo_eps + ElemRadius[e] + ElemRadius[be]
+                ok &= np.linalg.norm(bary[e] - origin[cand], axis=1) <= bc_halo_eps + ElemRadius[e] + radius[cand]
+                other_idx = cand[ok]
+            else:
+                other_idx = cand
+        sides = np.concatenate([own, bc_sides[other_idx]]) if own.size or other_idx.size else np.zeros(0, dtype=np.int64)
+        if sides.size == 0:
+            continue
+        # map side -> BC index for origin/radius
+        bidx = np.searchsorted(bc_sides, sides)
+        vec = bary[e][None, :] - origin[bidx]
+        dist = np.sqrt((vec * vec).sum(axis=1)) - ElemRadius[e] - radius[bidx]
+        order = np.argsort(dist, kind="stable")                          # InsertionSort is stable
+        m = np.zeros((sides.size, 7))
+        m[:, 0] = sides[order] + 1
+        m[:, 1] = e + 1
+        m[:, 2] = dist[order]
+        m[:, 3] = radius[bidx][order]
+        m[:, 4:7] = origin[bidx][order]
+        rows.append(m)
+        ElemToBCSides[e, 0] = sides.size                                  # ELEM_NBR_BCSIDES
+        ElemToBCSides[e, 1] = off                                         # ELEM_FIRST_BCSIDE
+        off += sides.size
+    SideBCMetrics = np.concatenate(rows) if rows else np.zeros((0, 7))
+    n1 = mesh.N + 1
+    sJ = mesh.sJ.reshape(nE, -1)
+    scaleJ = sJ.max(axis=1) / sJ.min(axis=1)
+    mesh.extra.update(dict(BaseVectors0=np.ascontiguousarray(BV0), BaseVectors1=np.ascontiguousarray(BV1),
+                           BaseVectors2=np.ascontiguousarray(BV2), SideNormVec=np.ascontiguousarray(SideNormVec),
+                           SideDistance=np.ascontiguousarray(SideDistance), SideType=SideType,
+                           ElemToBCSides=ElemToBCSides, SideBCMetrics=np.ascontiguousarray(SideBCMetrics),
+                           ElemEpsOneCell=1.0 + np.sqrt(3.0 * scaleJ * RefMappingEps),
+                           BaseVectorsScale=0.25 * np.sqrt((cr * cr).sum(axis=1))))
+    return mesh
