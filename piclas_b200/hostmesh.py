@@ -622,3 +622,80 @@ def add_refmapping_tables(mesh: ParticleMesh, bc_halo_eps=None, RefMappingEps=1e
                            ElemEpsOneCell=1.0 + np.sqrt(3.0 * scaleJ * RefMappingEps),
                            BaseVectorsScale=0.25 * np.sqrt((cr * cr).sum(axis=1))))
     return mesh
+
+
+def shape_function_adaptive_setup(mesh: ParticleMesh, params, alpha_sf, dim_sf=3, dim_sf_dir=1, sfDepo3D=True,
+                                  SFAdaptiveDOF=None, smoothing=False):
+    """shape_function_adaptive: per-element radius SFElemr2 (InitShapeFunctionAdaptive, pic_depo.f90:632-823) and the
+    dimensional factors (InitShapeFunctionDimensionalty with r_sf_loc = 1).  Element neighbours are the elements sharing a
+    unique node (BuildNodeNeighbourhood, particle_mesh_build.f90:1095-1382).  Supported on the device for periodic meshes
+    or with smoothing (the paths that use the element radius of the particle's element)."""
+    import math
+    shape_function_setup(mesh, params, 1.0, alpha_sf, dim_sf=dim_sf, dim_sf_dir=dim_sf_dir, sfDepo3D=sfDepo3D)
+    dimFactorSF = params.dimFactorSF
+    Nmax = mesh.N
+    if dim_sf == 1:
+        default, DOFMax = 2.0 * (1. + 1.), 2.0 * (Nmax + 1.)
+    elif dim_sf == 2:
+        default, DOFMax = math.pi * (1. + 1.) ** 2, math.pi * (Nmax + 1.) ** 2
+    else:
+        default, DOFMax = (4. / 3.) * math.pi * (1. + 1.) ** 3, (4. / 3.) * math.pi * (Nmax + 1.) ** 3
+    dof = default if SFAdaptiveDOF is None else float(SFAdaptiveDOF)
+    if dof > DOFMax:
+        raise ValueError("PIC-shapefunction-adaptive-DOF too large")
+    scaling = dof / 2.0 if dim_sf == 1 else (math.sqrt(dof / math.pi) if dim_sf == 2 else (3. * dof / (4. * math.pi)) ** (1. / 3.))
+    d1 = 1 if dim_sf_dir == 2 else 2
+    d2 = 1 if dim_sf_dir == 3 else 3
+
+    def sfnorm(v):
+        if dim_sf == 1:
+            return np.abs(v[..., dim_sf_dir - 1])
+        if dim_sf == 2:
+            return np.sqrt(v[..., d1 - 1] ** 2 + v[..., d2 - 1] ** 2)
+        return np.sqrt((v * v).sum(axis=-1))
+
+    def aer(a, b, tol):   # ALMOSTEQUALRELATIVE, piclas.h:79
+        return np.abs(a - b) <= np.maximum(np.abs(a), np.abs(b)) * tol
+
+    def measure(v1, v2):
+        if dim_sf == 1:
+            return ~aer(v1[..., dim_sf_dir - 1], v2[..., dim_sf_dir - 1], 1e-6)
+        if dim_sf == 2:
+            return ~(aer(v1[..., d1 - 1], v2[..., d1 - 1], 1e-6) & aer(v1[..., d2 - 1], v2[..., d2 - 1], 1e-6))
+        return np.ones(v1.shape[:-1], dtype=bool)
+
+    nE = mesh.nElems
+    en = mesh.elem_nodes.astype(np.int64)                        # unique ids, CGNS order
+    node2elem = [[] for _ in range(mesh.nUniqueNodes)]
+    for e in range(nE):
+        for u in en[e]:
+            node2elem[u].append(e)
+    X = mesh.unique_coords
+    NC = mesh.NodeCoords.reshape(nE, 8, 3)
+    r = np.full(nE, np.finfo(np.float64).max)
+    for e in range(nE):
+        mine = set(en[e].tolist())
+        neigh = sorted({n for u in en[e] for n in node2elem[u]} - {e})
+        done = False
+        for nb in neigh:
+            for ju in en[nb]:
+                if ju in mine:
+                    continue
+                done = True
+                v2 = X[ju]
+                v1 = X[en[e]]
+                ok = measure(v1, np.broadcast_to(v2, v1.shape))
+                if ok.any():
+                    r[e] = min(r[e], sfnorm(v1[ok] - v2).min())
+        if not done:
+            mid = NC[e].sum(axis=0) / 8.0
+            r[e] = min(r[e], sfnorm(mid - NC[e]).min())
+        bb = NC[e].max(axis=0) - NC[e].min(axis=0)
+        vol = bb[0] * bb[1] * bb[2]
+        cl = vol / dimFactorSF if dim_sf == 1 else (math.sqrt(vol / dimFactorSF) if dim_sf == 2 else vol ** (1. / 3.))
+        if cl < r[e] or smoothing:
+            r[e] = (r[e] + cl) / 2.0
+        r[e] = r[e] * scaling / (mesh.N + 1.)
+    mesh.extra["SFElemr2"] = np.ascontiguousarray(np.stack([r, r * r], axis=1))
+    params.r_sf = float(r.max())
+    return params

@@ -258,3 +258,29 @@ def test_oracle_shape_function_known_answers(dim, direction, kind):
     else:
         ref = k["charge_sf_1D_x"] if dim == 1 else k["charge_sf_2D_z"]
         assert abs(q - ref) <= k["rel_tol_sf"] * ref
+
+
+# ---- RefMapping tracking ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(6, 5, 4), (4, 4, 1), (12, 1, 1)])
+def test_refmapping_agrees_with_triatracking_and_floor(shape):
+    """On Cartesian periodic boxes both tracking methods must put every particle into the same element, including the
+    1-element-thick tutorial meshes where every element is a BC element (ParticleBCTracking path)."""
+    mt = hm.box_mesh([0, 0, 0], [1, 1, 1], shape, 2)
+    mr = hm.box_mesh([0, 0, 0], [1, 1, 1], shape, 2, tracking=hm.REFMAPPING)
+    hm.add_fibgm(mr)
+    hm.add_refmapping_tables(mr)
+    ot, orr = Oracle(mt, cases.electron_params()), Oracle(mr, cases.electron_params(TrackingMethod=hm.REFMAPPING))
+    n, dt = 5000, 1e-8
+    PS, spec = cases.uniform_plasma(mt, n, seed=3, vth_cells=0.6, dt=dt)
+    el = hm.cartesian_locate(mt, PS[:, :3])
+    E = cases.smooth_field(mt, 1e-4)
+    xi, _, _ = orr.position_in_ref_elem(PS[:, :3], el, force=False)
+    A = [PS.copy(), el.copy(), np.ones(n, dtype=np.int32), np.ones(n, dtype=np.int32)]
+    B = [PS.copy(), el.copy(), np.ones(n, dtype=np.int32), np.ones(n, dtype=np.int32)]
+    for _ in range(5):
+        ot.push_track(dt, A[0], spec, A[1], A[2], A[3], E)
+        orr.push_track(dt, B[0], spec, B[1], B[2], B[3], E, PartPosRef=xi)
+        assert np.array_equal(A[1], B[1])
+        assert np.array_equal(B[1], hm.cartesian_locate(mr, B[0][:, :3]))
+        assert np.abs(A[0] - B[0]).max() <= 1e-12 * np.abs(A[0]).max()
+        assert np.abs(xi).max() < 1.0
