@@ -270,7 +270,7 @@ def run_b200(args):
     peak, peak_src = hbm_peak()
     t_push = phases[2] * 1e-3
     achieved = ALG_BYTES_PER_PARTICLE_STEP * n_total / t_push / 1e9 if t_push > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_push_track_tria (interpolate+push+track)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_interp_push + k_track_leavers (interpolate+push+track phase)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "alg_bytes_per_launch": ALG_BYTES_PER_PARTICLE_STEP * n_total, "ms_per_launch": phases[2],
                 "step_frac": (ALG_BYTES_PER_PARTICLE_STEP * n_total * args.steps / wall / 1e9) / peak,

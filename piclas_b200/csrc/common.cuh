@@ -77,6 +77,9 @@ struct ConstTables {
 
 // particle SoA (one of two buffers)
 struct PartBuf {
+  double *f;          // one block [6][stride]: x0,x1,x2,v0,v1,v2 (x[d] and v[d] below point into it)
+  double *xif;        // one block [3][stride] behind xi[d]
+  int64_t stride;
   double *x[3];
   double *v[3];
   double *xi[3];      // cached reference position of the current (x, elem); valid iff Ctx::xiValid

@@ -40,6 +40,9 @@ __global__ void __launch_bounds__(STEP_NT, DEP_MINB) k_deposit_cvwm(PartBuf pb, 
                                                              int offsetElem, const GeoElem* __restrict__ geo,
                                                              const TriaElem* __restrict__ tria, const AffElem* __restrict__ aff,
                                                              double* __restrict__ elemAcc) {
+  double* __restrict__ const PF = pb.f;
+  double* __restrict__ const PXI = pb.xif;
+  const int64_t PS_ = pb.stride;
   __shared__ GeoElem sg;
   __shared__ AffElem sa;
   __shared__ double corner[8][3];
@@ -57,22 +60,22 @@ __global__ void __launch_bounds__(STEP_NT, DEP_MINB) k_deposit_cvwm(PartBuf pb, 
       __syncthreads();
       for (int64_t p = p0 + tid; p < p1; p += STEP_NT) {
         asm volatile("" ::: "memory");  // no hoisting of shared-memory loads over the particle loop
-        const double x[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};
+        const double x[3] = {PF[p], PF[1 * PS_ + p], PF[2 * PS_ + p]};
         uint8_t meta = pb.meta[p];
         const int spec = meta & META_SPEC_MASK;
         double xi[3];
         bool suc;
         if (FAST) suc = ref_position_fast(&sa, &sg, x, xi, true);
         else suc = (position_in_ref_elem(&sg, x, xi, true, true) & 1) != 0;
-        pb.xi[0][p] = xi[0];
-        pb.xi[1][p] = xi[1];
-        pb.xi[2][p] = xi[2];
+        PXI[p] = xi[0];
+        PXI[1 * PS_ + p] = xi[1];
+        PXI[2 * PS_ + p] = xi[2];
         const uint8_t nmeta = suc ? (meta & ~META_XIFAIL) : (meta | META_XIFAIL);
         if (nmeta != meta) pb.meta[p] = nmeta;
         const double q = cst.ChargeIC[spec];
         if (!(fabs(q) > 0.0)) continue;  // isDepositParticle
         const double Charge = q * cst.MPF[spec];
-        const double T[4] = {pb.v[0][p] * Charge, pb.v[1][p] * Charge, pb.v[2][p] * Charge, Charge};
+        const double T[4] = {PF[3 * PS_ + p] * Charge, PF[4 * PS_ + p] * Charge, PF[5 * PS_ + p] * Charge, Charge};
         double w[8];
         if (suc) {
           const double a1 = 0.5 * (xi[0] + 1.0), a2 = 0.5 * (xi[1] + 1.0), a3 = 0.5 * (xi[2] + 1.0);
@@ -231,6 +234,9 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
                                                             uint32_t* __restrict__ leaverIdx, double dt, int xiValid,
                                                             int* __restrict__ counters /*[0]=lost,[1]=error,[2]=nLeavers*/) {
   constexpr int ND = NP * NP * NP;
+  double* __restrict__ const PF = pb.f;
+  const double* __restrict__ const PXI = pb.xif;
+  const int64_t PS_ = pb.stride;
   __shared__ GeoElem sg;
   __shared__ TriaElem st;
   __shared__ PlaneElem sp;
@@ -255,8 +261,8 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
     __syncthreads();
     for (int64_t p = p0 + threadIdx.x; p < p1; p += STEP_NT) {
       asm volatile("" ::: "memory");  // keep the shared-memory tiles out of the registers (no hoisting over the loop)
-      double x[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};
-      double v[3] = {pb.v[0][p], pb.v[1][p], pb.v[2][p]};
+      double x[3] = {PF[p], PF[1 * PS_ + p], PF[2 * PS_ + p]};
+      double v[3] = {PF[3 * PS_ + p], PF[4 * PS_ + p], PF[5 * PS_ + p]};
       const uint8_t meta = pb.meta[p];
       const int spec = meta & META_SPEC_MASK;
       bool isNew = (meta & META_ISNEW) != 0;
@@ -268,10 +274,10 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
         double xi[3];
         bool suc;
         if (REF) {
-          xi[0] = pb.xi[0][p]; xi[1] = pb.xi[1][p]; xi[2] = pb.xi[2][p];
+          xi[0] = PXI[p]; xi[1] = PXI[1 * PS_ + p]; xi[2] = PXI[2 * PS_ + p];
           suc = true;
         } else if (xiValid) {
-          xi[0] = pb.xi[0][p]; xi[1] = pb.xi[1][p]; xi[2] = pb.xi[2][p];
+          xi[0] = PXI[p]; xi[1] = PXI[1 * PS_ + p]; xi[2] = PXI[2 * PS_ + p];
           suc = !(meta & META_XIFAIL);
         } else if (FAST) {
           suc = ref_position_fast(&sa, &sg, x, xi, false);
@@ -294,7 +300,7 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
       }
       if (FAST) push_particle_fast(x, v, F, spec, isNew, dt);
       else push_particle(x, v, F, spec, isNew, dt);
-      pb.v[0][p] = v[0]; pb.v[1][p] = v[1]; pb.v[2][p] = v[2];
+      PF[3 * PS_ + p] = v[0]; PF[4 * PS_ + p] = v[1]; PF[5 * PS_ + p] = v[2];
       const uint8_t nmeta = (uint8_t)(meta & META_SPEC_MASK);  // IsNewPart and the xi flag are consumed
       if (nmeta != meta) pb.meta[p] = nmeta;
       if (REF) {
@@ -304,13 +310,17 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
       uint32_t mask;
       const bool inElem = FAST ? inside_fast(&sp, &st, x, mask) : inside_quad3d_mask(&st, x, mask);
       if (inElem) {
-        pb.x[0][p] = x[0]; pb.x[1][p] = x[1]; pb.x[2][p] = x[2];
+        PF[p] = x[0]; PF[1 * PS_ + p] = x[1]; PF[2 * PS_ + p] = x[2];
         keys[p] = (uint32_t)e;
       } else {
         xn0[p] = x[0]; xn1[p] = x[1]; xn2[p] = x[2];
         keys[p] = mask;  // handed to k_track_leavers, which overwrites it with the final key
-        const int slot = atomicAdd(&counters[2], 1);
-        leaverIdx[slot] = (uint32_t)p;
+        const unsigned act = __activemask();   // warp-aggregated append: one atomic per warp, consecutive slots
+        const int ln = threadIdx.x & 31, leader = __ffs(act) - 1;
+        int slot0 = 0;
+        if (ln == leader) slot0 = atomicAdd(&counters[2], __popc(act));
+        slot0 = __shfl_sync(act, slot0, leader);
+        leaverIdx[slot0 + __popc(act & ((1u << ln) - 1u))] = (uint32_t)p;
       }
     }
   }
@@ -319,132 +329,173 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
 // ---- SingleParticleTriaTracking3D for the particles that left their element (particle_triatracking.f90:137-484) --------------------
 // One thread per leaver, element records read from global memory (L2 resident).  All loops are rolled and the candidate
 // triangles are visited through a bit mask so that the lanes of a warp run the same through-side test at the same time.
+// (r1 profile of the first version, which looped per thread until done: every warp ran 2-3 rounds for 1.1 hops per particle,
+// 12 of 32 lanes active; a shared-memory re-queue with block barriers was slower still.)
+constexpr int LV_NT = 128;
+
 template <bool FAST>
-__global__ void __launch_bounds__(128) k_track_leavers(PartBuf pb, const double* __restrict__ xn0, const double* __restrict__ xn1,
-                                                       const double* __restrict__ xn2, const uint32_t* __restrict__ leaverIdx,
-                                                       const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ planes,
-                                                       const int32_t* __restrict__ elemRank,
-                                                       uint32_t* __restrict__ keys, int nElems, int offsetElem,
-                                                       int* __restrict__ counters) {
+__global__ void __launch_bounds__(LV_NT) k_track_leavers(PartBuf pb, const double* __restrict__ xn0, const double* __restrict__ xn1,
+                                                         const double* __restrict__ xn2, const uint32_t* __restrict__ leaverIdx,
+                                                         const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ planes,
+                                                         const int32_t* __restrict__ elemRank, uint32_t* __restrict__ keys, int nElems,
+                                                         int offsetElem, int* __restrict__ counters) {
+  double* __restrict__ const PF = pb.f;
+  const int64_t PS_ = pb.stride;
   const int nLeavers = counters[2];
-  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < nLeavers; l += gridDim.x * blockDim.x) {
-    const int64_t p = leaverIdx[l];
-    double x[3] = {xn0[p], xn1[p], xn2[p]};
-    double lp[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};  // LastPartPos
-    int ElemID = pb.elem[p];                               // LastGlobalElemID
-    uint32_t mask = keys[p];                               // det <= 0 triangles of the start element (k_interp_push)
-    int status = TRK_ERR_LOOP;
-    // DoneLastElem(1:4,1:6): last six crossings (element, side id, triangle); entry 0 is the most recent
-    int dE0 = 0, dE1 = 0, dE2 = 0, dE3 = 0, dE4 = 0, dE5 = 0;
-    int dS0 = 0, dS1 = 0, dS2 = 0, dS3 = 0, dS4 = 0, dS5 = 0;
-    int dT0 = 0, dT1 = 0, dT2 = 0, dT3 = 0, dT4 = 0, dT5 = 0;
-#pragma unroll 1
-    for (int guard = 0; guard < 100000; ++guard) {
-      const TriaElem* te = tria + (ElemID - 1);
-      // 2b) crossed triangles among those with det <= 0
-      double V[3] = {x[0] - lp[0], x[1] - lp[1], x[2] - lp[2]};
-      const double len = sqrt((V[0] * V[0] + V[1] * V[1]) + V[2] * V[2]);
-      if (fabs(len) > 0.) {
-        V[0] = V[0] / len; V[1] = V[1] / len; V[2] = V[2] / len;
-      }
-      uint32_t thr = 0;
-      int nThrough = 0;
-      uint32_t cand = mask;
-#pragma unroll 1
-      while (cand) {
-        const int b = __ffs(cand) - 1;
-        cand &= cand - 1;
-        if (through_side_check_fast(te, lp, V, b >> 1, (b & 1) + 1)) {
-          thr |= 1u << b;
-          ++nThrough;
+  const int lane = threadIdx.x & 31;
+  bool active = false;
+  int p = 0, ElemID = 0, guard = 0;
+  uint32_t mask = 0;
+  double x[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
+  int dE0 = 0, dE1 = 0, dE2 = 0, dE3 = 0, dE4 = 0, dE5 = 0;  // DoneLastElem(1:4,1:6); entry 0 is the most recent crossing
+  int dS0 = 0, dS1 = 0, dS2 = 0, dS3 = 0, dS4 = 0, dS5 = 0;
+  int dT0 = 0, dT1 = 0, dT2 = 0, dT3 = 0, dT4 = 0, dT5 = 0;
+  // persistent warps: a lane performs one element crossing ("hop") per round and fetches the next leaver as soon as its
+  // particle is localised, so that lanes stay busy while a neighbour lane walks through several elements
+  while (true) {
+    {
+      const unsigned need = __ballot_sync(0xffffffffu, !active);
+      if (need) {
+        int first = 0;
+        if (lane == __ffs(need) - 1) first = atomicAdd(&counters[3], __popc(need));
+        first = __shfl_sync(0xffffffffu, first, __ffs(need) - 1);
+        const int mine = first + __popc(need & ((1u << lane) - 1u));
+        if (!active && mine < nLeavers) {
+          active = true;
+          p = (int)leaverIdx[mine];
+          x[0] = xn0[p]; x[1] = xn1[p]; x[2] = xn2[p];
+          lp[0] = PF[p]; lp[1] = PF[1 * PS_ + p]; lp[2] = PF[2 * PS_ + p];  // LastPartPos
+          ElemID = pb.elem[p];                                               // LastGlobalElemID
+          mask = keys[p];                                                    // det <= 0 triangles of the start element
+          guard = 0;
+          dE0 = dE1 = dE2 = dE3 = dE4 = dE5 = 0;
+          dS0 = dS1 = dS2 = dS3 = dS4 = dS5 = 0;
+          dT0 = dT1 = dT2 = dT3 = dT4 = dT5 = 0;
         }
       }
-      if (nThrough == 0) { status = TRK_LOST; break; }
-      int side, tri;
-      if (nThrough == 1) {
-        const int b = __ffs(thr) - 1;
-        side = b >> 1;
-        tri = (b & 1) + 1;
-      } else {
-        // several candidate sides: the one crossed first has the largest |det(PartPos)/det(LastPartPos)| (:309-405)
-        int second = 0;
-        double minRatio = 0;
-        side = -1; tri = 0;
-        uint32_t c2 = thr;
+      if (__ballot_sync(0xffffffffu, active) == 0) break;
+    }
+    {
+      int status = -1;  // -1: needs another hop
+      if (active) {
+        const TriaElem* te = tria + (ElemID - 1);
+        // 2b) crossed triangles among those with det <= 0
+        double V[3] = {x[0] - lp[0], x[1] - lp[1], x[2] - lp[2]};
+        const double len = sqrt((V[0] * V[0] + V[1] * V[1]) + V[2] * V[2]);
+        if (fabs(len) > 0.) {
+          V[0] = V[0] / len; V[1] = V[1] / len; V[2] = V[2] / len;
+        }
+        uint32_t thr = 0;
+        int nThrough = 0;
+        uint32_t cand = mask;
 #pragma unroll 1
-        while (c2) {
-          const int b = __ffs(c2) - 1;
-          c2 &= c2 - 1;
-          const int s = b >> 1, t = (b & 1) + 1;
-          const int gs = te->sideID[s];
-          const bool treated = (dE1 == ElemID && dS1 == gs && dT1 == t) || (dE2 == ElemID && dS2 == gs && dT2 == t) ||
-                               (dE3 == ElemID && dS3 == gs && dT3 == t) || (dE4 == ElemID && dS4 == gs && dT4 == t) ||
-                               (dE5 == ElemID && dS5 == gs && dT5 == t);
-          if (treated) continue;
-          double detM;
-          if (!through_side_lastpos_check(te, lp, s, t, detM)) continue;
-          double d1, d2;
-          side_dets(te, x, s, d1, d2);
-          const double dS = (t == 1) ? d1 : d2;
-          if (detM == 0 && dS == 0) continue;
-          if (detM == 0 && minRatio == 0) {
-            ++second; side = s; tri = t;
-          } else {
-            if (detM == 0) continue;
-            const double ratio = dS / detM;
-            if (ratio < minRatio) {
-              minRatio = ratio;
+        while (cand) {
+          const int b = __ffs(cand) - 1;
+          cand &= cand - 1;
+          if (through_side_check_fast(te, lp, V, b >> 1, (b & 1) + 1)) {
+            thr |= 1u << b;
+            ++nThrough;
+          }
+        }
+        int side = -1, tri = 0;
+        if (nThrough == 0) {
+          status = TRK_LOST;
+        } else if (nThrough == 1) {
+          const int b = __ffs(thr) - 1;
+          side = b >> 1;
+          tri = (b & 1) + 1;
+        } else {
+          // several candidate sides: the one crossed first has the largest |det(PartPos)/det(LastPartPos)| (:309-405)
+          int second = 0;
+          double minRatio = 0;
+          uint32_t c2 = thr;
+#pragma unroll 1
+          while (c2) {
+            const int b = __ffs(c2) - 1;
+            c2 &= c2 - 1;
+            const int s = b >> 1, t = (b & 1) + 1;
+            const int gs = te->sideID[s];
+            const bool treated = (dE1 == ElemID && dS1 == gs && dT1 == t) || (dE2 == ElemID && dS2 == gs && dT2 == t) ||
+                                 (dE3 == ElemID && dS3 == gs && dT3 == t) || (dE4 == ElemID && dS4 == gs && dT4 == t) ||
+                                 (dE5 == ElemID && dS5 == gs && dT5 == t);
+            if (treated) continue;
+            double detM;
+            if (!through_side_lastpos_check(te, lp, s, t, detM)) continue;
+            double d1, d2;
+            side_dets(te, x, s, d1, d2);
+            const double dS = (t == 1) ? d1 : d2;
+            if (detM == 0 && dS == 0) continue;
+            if (detM == 0 && minRatio == 0) {
               ++second; side = s; tri = t;
+            } else {
+              if (detM == 0) continue;
+              const double ratio = dS / detM;
+              if (ratio < minRatio) {
+                minRatio = ratio;
+                ++second; side = s; tri = t;
+              }
+            }
+          }
+          if (second == 0) status = TRK_LOST;
+        }
+        if (status == -1) {
+          // 3) boundary interaction or step into the neighbour
+          const int gside = te->sideID[side];
+          const int bc = te->bcid[side];
+          const int oldElem = ElemID;
+          if (bc > 0) {
+            const int kind = cst.bc_kind[bc - 1];
+            if (kind == PGPU_BC_OPEN) status = TRK_REMOVED;
+            else if (kind != PGPU_BC_PERIODIC) status = TRK_ERR_BC;
+            else {
+              const double alpha = intersection_with_wall(te, lp, V, side, tri);
+              const int pvid = cst.bc_alpha[bc - 1];  // PeriodicBoundary, particle_boundary_condition.f90:224-284
+              const int pv = (pvid < 0 ? -pvid : pvid) - 1;
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                lp[d] = lp[d] + V[d] * alpha;
+                lp[d] = lp[d] + copysign(cst.PeriodicVectors[pv][d], (double)pvid);
+                x[d] = lp[d] + (len - alpha) * V[d];
+              }
+            }
+          }
+          if (status == -1) {
+            ElemID = te->nbElem[side];
+            dE5 = dE4; dS5 = dS4; dT5 = dT4;
+            dE4 = dE3; dS4 = dS3; dT4 = dT3;
+            dE3 = dE2; dS3 = dS2; dT3 = dT2;
+            dE2 = dE1; dS2 = dS1; dT2 = dT1;
+            dE1 = dE0; dS1 = dS0; dT1 = dT0;
+            dE0 = oldElem; dS0 = gside; dT0 = tri;
+            if (ElemID < 1) status = TRK_ERR_ELEM;
+            else {
+              // 2a) inside test in the new element
+              const bool inNew = FAST ? inside_fast(planes + (ElemID - 1), tria + (ElemID - 1), x, mask)
+                                      : inside_quad3d_mask(tria + (ElemID - 1), x, mask);
+              if (inNew) status = TRK_OK;
+              else if (++guard > 100000) status = TRK_ERR_LOOP;
             }
           }
         }
-        if (second == 0) { status = TRK_LOST; break; }
-      }
-      // 3) boundary interaction or step into the neighbour
-      const int gside = te->sideID[side];
-      const int bc = te->bcid[side];
-      const int oldElem = ElemID;
-      if (bc > 0) {
-        const int kind = cst.bc_kind[bc - 1];
-        if (kind == PGPU_BC_OPEN) { status = TRK_REMOVED; break; }
-        if (kind != PGPU_BC_PERIODIC) { status = TRK_ERR_BC; break; }
-        const double alpha = intersection_with_wall(te, lp, V, side, tri);
-        const int pvid = cst.bc_alpha[bc - 1];  // PeriodicBoundary, particle_boundary_condition.f90:224-284
-        const int pv = (pvid < 0 ? -pvid : pvid) - 1;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          lp[d] = lp[d] + V[d] * alpha;
-          lp[d] = lp[d] + copysign(cst.PeriodicVectors[pv][d], (double)pvid);
-          x[d] = lp[d] + (len - alpha) * V[d];
+        if (status != -1) {
+          uint32_t key;
+          int newElem = ElemID;
+          if (status == TRK_OK) {
+            const int rk = elemRank[newElem - 1];
+            key = (rk == cst.myRank) ? (uint32_t)(newElem - 1 - offsetElem) : (uint32_t)(nElems + rk);
+          } else {
+            key = (uint32_t)(nElems + cst.nRanks);  // removed
+            newElem = 0;
+            if (status == TRK_LOST) atomicAdd(&counters[0], 1);
+            else if (status != TRK_REMOVED) atomicMax(&counters[1], status);
+          }
+          PF[p] = x[0]; PF[1 * PS_ + p] = x[1]; PF[2 * PS_ + p] = x[2];
+          pb.elem[p] = newElem;
+          keys[p] = key;
         }
       }
-      ElemID = te->nbElem[side];
-      dE5 = dE4; dS5 = dS4; dT5 = dT4;
-      dE4 = dE3; dS4 = dS3; dT4 = dT3;
-      dE3 = dE2; dS3 = dS2; dT3 = dT2;
-      dE2 = dE1; dS2 = dS1; dT2 = dT1;
-      dE1 = dE0; dS1 = dS0; dT1 = dT0;
-      dE0 = oldElem; dS0 = gside; dT0 = tri;
-      if (ElemID < 1) { status = TRK_ERR_ELEM; break; }
-      // 2a) inside test in the new element
-      const bool inNew = FAST ? inside_fast(planes + (ElemID - 1), tria + (ElemID - 1), x, mask)
-                              : inside_quad3d_mask(tria + (ElemID - 1), x, mask);
-      if (inNew) { status = TRK_OK; break; }
+      if (active && status != -1) active = false;
     }
-    uint32_t key;
-    int newElem = ElemID;
-    if (status == TRK_OK) {
-      const int rk = elemRank[newElem - 1];
-      key = (rk == cst.myRank) ? (uint32_t)(newElem - 1 - offsetElem) : (uint32_t)(nElems + rk);
-    } else {
-      key = (uint32_t)(nElems + cst.nRanks);  // removed
-      newElem = 0;
-      if (status == TRK_LOST) atomicAdd(&counters[0], 1);
-      else if (status != TRK_REMOVED) atomicMax(&counters[1], status);
-    }
-    pb.x[0][p] = x[0]; pb.x[1][p] = x[1]; pb.x[2][p] = x[2];
-    pb.elem[p] = newElem;
-    keys[p] = key;
   }
 }
 

@@ -113,9 +113,14 @@ int upload(T** d, const T* h, size_t n) {
 }
 
 int alloc_partbuf(PartBuf& b, int64_t cap, bool ids) {
+  const int64_t stride = (cap + 31) & ~(int64_t)31;   // keeps every component 256-byte aligned
+  b.f = nullptr;
+  CK(cudaMalloc((void**)&b.f, (size_t)stride * 6 * 8));
+  b.stride = stride;
+  b.xif = nullptr;
   for (int d = 0; d < 3; ++d) {
-    CK(cudaMalloc((void**)&b.x[d], cap * 8));
-    CK(cudaMalloc((void**)&b.v[d], cap * 8));
+    b.x[d] = b.f + (size_t)d * stride;
+    b.v[d] = b.f + (size_t)(3 + d) * stride;
     b.xi[d] = nullptr;
   }
   CK(cudaMalloc((void**)&b.elem, cap * 4));
@@ -125,7 +130,9 @@ int alloc_partbuf(PartBuf& b, int64_t cap, bool ids) {
   return 0;
 }
 void free_partbuf(PartBuf& b) {
-  for (int d = 0; d < 3; ++d) { cudaFree(b.x[d]); cudaFree(b.v[d]); b.x[d] = b.v[d] = b.xi[d] = nullptr; }
+  cudaFree(b.f);
+  b.f = nullptr;
+  for (int d = 0; d < 3; ++d) { b.x[d] = b.v[d] = b.xi[d] = nullptr; }
   cudaFree(b.elem); cudaFree(b.meta); cudaFree(b.id);
   b.elem = nullptr; b.meta = nullptr; b.id = nullptr;
 }
@@ -153,17 +160,24 @@ int reserve_particles(int64_t need) {
     free_partbuf(g.buf[0]);
     free_partbuf(g.buf[1]);
   }
-  for (int d = 0; d < 3; ++d) {
+  {
+    const int64_t stride = nb[0].stride;
     double* nx = nullptr;
-    CK(cudaMalloc((void**)&nx, ncap * 8));
-    if (g.ref && g.cap > 0 && g.nPart > 0 && oldXi[d]) CK(cudaMemcpy(nx, oldXi[d], g.nPart * 8, cudaMemcpyDeviceToDevice));
-    cudaFree(g.dXi[d]);
-    g.dXi[d] = nx;
-    nb[0].xi[d] = nb[1].xi[d] = g.dXi[d];
+    CK(cudaMalloc((void**)&nx, (size_t)stride * 3 * 8));
+    for (int d = 0; d < 3; ++d)
+      if (g.ref && g.cap > 0 && g.nPart > 0 && oldXi[d]) CK(cudaMemcpy(nx + (size_t)d * stride, oldXi[d], g.nPart * 8, cudaMemcpyDeviceToDevice));
+    cudaFree(g.dXi[0]);
+    for (int d = 0; d < 3; ++d) {
+      g.dXi[d] = nx + (size_t)d * stride;
+      nb[0].xi[d] = nb[1].xi[d] = g.dXi[d];
+    }
+    nb[0].xif = nb[1].xif = nx;
     if (g.ref) {
-      cudaFree(g.dXiB[d]);
-      CK(cudaMalloc((void**)&g.dXiB[d], ncap * 8));
-      nb[1].xi[d] = g.dXiB[d];
+      cudaFree(g.dXiB[0]);
+      double* nb2 = nullptr;
+      CK(cudaMalloc((void**)&nb2, (size_t)stride * 3 * 8));
+      for (int d = 0; d < 3; ++d) { g.dXiB[d] = nb2 + (size_t)d * stride; nb[1].xi[d] = g.dXiB[d]; }
+      nb[1].xif = nb2;
     }
   }
   g.buf[0] = nb[0];
@@ -301,7 +315,7 @@ void launch_push_track_t(double dt) {
     k_interp_push<NP, FAST, false><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem,
                                                               g.dGeo, g.dTria, g.dPlanes, g.dAff, g.dE, g.dElemXGP, g.dKeys, leaverIdx,
                                                               dt, g.xiValid ? 1 : 0, g.dCounters);
-    k_track_leavers<FAST><<<g.nSMs * 8, 128, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, g.dTria, g.dPlanes,
+    k_track_leavers<FAST><<<g.nSMs * 8, LV_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, g.dTria, g.dPlanes,
                                                         g.dElemRank, g.dKeys, g.nElems, g.offsetElem, g.dCounters);
   }
   g.lastLaunches += 2;
@@ -348,14 +362,14 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dFibN); cudaFree(g.dFibOff); cudaFree(g.dFibElem); cudaFree(g.dElemToBGM); cudaFree(g.dCandOff); cudaFree(g.dCandSrc);
   cudaFree(g.dCandCase); cudaFree(g.dElemBary); cudaFree(g.dElemRadius); cudaFree(g.dElemsJ); cudaFree(g.dSFElemr2);
   for (int c = 0; c < 4; ++c) cudaFree(g.dSfFac[c]);
-  for (int d = 0; d < 3; ++d) cudaFree(g.dXiB[d]);
+  cudaFree(g.dXiB[0]);
   cudaFree(g.dElemToBCSides); cudaFree(g.dSideInfo); cudaFree(g.dSideBCMetrics); cudaFree(g.dSideNormVec); cudaFree(g.dSideDistance);
   cudaFree(g.dBV0); cudaFree(g.dBV1); cudaFree(g.dBV2); cudaFree(g.dElemRadius2); cudaFree(g.dElemEpsOneCell);
   if (g.cap > 0) {
     free_partbuf(g.buf[0]);
     free_partbuf(g.buf[1]);
   }
-  for (int d = 0; d < 3; ++d) cudaFree(g.dXi[d]);
+  cudaFree(g.dXi[0]);
   sort_workspace_free(g.sortws);
   for (int i = 0; i < 6; ++i) if (g.evp[i]) cudaEventDestroy(g.evp[i]);
   if (g.ev0) cudaEventDestroy(g.ev0);
