@@ -192,6 +192,14 @@ int piclas_gpu_exchange_finish(int64_t nRecvTotal);
 int piclas_gpu_nodesource_device(void **devNodeSource /* double[nUniqueGlobalNodes][4] */);
 int piclas_gpu_deposit_finish(double *PartSource, double *NodeSource);
 
+/* ---- shape-function DOF halo (replaces pic_depo_method.f90:940-996, ShapeMapping Send/RecvBuffer) ---------------
+ * Multi-rank runs: deposit() also forms the contributions of local particles to elements of other ranks.
+ * nSend/nRecvElemsPerRank[nRanks] are element counts (fixed by the geometry at init), each element carries
+ * doublesPerElem = 4*(N+1)^3 doubles; exchange devSend -> devRecv (rank-ordered blocks), then call
+ * piclas_gpu_deposit_finish(PartSource, NULL), which adds the received blocks rank after rank. */
+int piclas_gpu_sf_halo_info(int64_t *nSendElemsPerRank, int64_t *nRecvElemsPerRank, int32_t *doublesPerElem,
+                            void **devSend, void **devRecv);
+
 /* timing of the last call's kernels (ms, CUDA events on the launch stream) and launch count */
 int piclas_gpu_last_timing(double *ms_kernels, int32_t *nLaunches);
 /* CUDA-event durations (ms) of the phases of the most recent deposit / push_track call:

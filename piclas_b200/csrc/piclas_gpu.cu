@@ -54,6 +54,11 @@ struct Ctx {
   uint8_t* dCandCase = nullptr;
   double *dElemBary = nullptr, *dElemRadius = nullptr, *dElemsJ = nullptr, *dSFElemr2 = nullptr;
   double* dSfFac[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nSfTargets = 0, nSfHalo = 0;               // gather targets: nElems local + nSfHalo elements of other ranks
+  int32_t *dSfTarget = nullptr, *dSfRecvLocal = nullptr;
+  double* dSfRecv = nullptr;                       // received halo contributions [nRecvElems][ND][4]
+  std::vector<int64_t> sfSendCount, sfRecvCount;   // elements per rank
+  int64_t sfRecvTotal = 0;
   int64_t sfFacCap = 0;
   // field
   double* dE = nullptr;
@@ -362,6 +367,7 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dFibN); cudaFree(g.dFibOff); cudaFree(g.dFibElem); cudaFree(g.dElemToBGM); cudaFree(g.dCandOff); cudaFree(g.dCandSrc);
   cudaFree(g.dCandCase); cudaFree(g.dElemBary); cudaFree(g.dElemRadius); cudaFree(g.dElemsJ); cudaFree(g.dSFElemr2);
   for (int c = 0; c < 4; ++c) cudaFree(g.dSfFac[c]);
+  cudaFree(g.dSfTarget); cudaFree(g.dSfRecvLocal); cudaFree(g.dSfRecv);
   cudaFree(g.dXiB[0]);
   cudaFree(g.dElemToBCSides); cudaFree(g.dSideInfo); cudaFree(g.dSideBCMetrics); cudaFree(g.dSideNormVec); cudaFree(g.dSideDistance);
   cudaFree(g.dBV0); cudaFree(g.dBV1); cudaFree(g.dBV2); cudaFree(g.dElemRadius2); cudaFree(g.dElemEpsOneCell);
@@ -407,7 +413,6 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   if (p->DoDeposition && p->DepositionType != PGPU_DEPO_CVWM && !isSF)
     return fail("piclas_gpu_init: PIC-Deposition-Type %d not supported (cell_volweight_mean, shape_function, shape_function_cc, shape_function_adaptive)", p->DepositionType);
   if (p->DoDeposition && isSF) {
-    if (p->nRanks != 1) return fail("piclas_gpu_init: shape-function deposition is single-rank in this build (DOF halo exchange not implemented)");
     if (!m->FIBGM_nElems || !m->FIBGM_offsetElem || !m->FIBGM_Element || !m->ElemToBGM || !m->ElemRadiusNGeo)
       return fail("piclas_gpu_init: shape-function deposition needs FIBGM_nElems/offsetElem/Element, ElemToBGM and ElemRadiusNGeo");
     if (p->dim_sf < 1 || p->dim_sf > 3 || p->dim_sf_dir < 1 || p->dim_sf_dir > 3) return fail("piclas_gpu_init: bad shape-function dimension/direction");
@@ -674,33 +679,33 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
         } else for (int I = 1; I <= 3; ++I) shift[c][I - 1] = cm[0] * PVc(I, 1) + cm[1] * PVc(I, 2) + cm[2] * PVc(I, 3);
       }
     }
-    std::vector<int32_t> candOff(g.nElems + 1, 0), candSrc;
+    // gather targets: the local elements plus, for multi-rank runs, every element of another rank that a local particle
+    // can reach (sorted by owner rank, then element id, so that each rank's part of the halo buffer is contiguous)
+    std::vector<int32_t> targets(g.nElems);
+    for (int e = 0; e < g.nElems; ++e) targets[e] = g.offsetElem + e + 1;
+    std::vector<int32_t> candOff, candSrc;
     std::vector<uint8_t> candCase;
-    // uniform grid over source barycentres would be faster; the local element count times cases is small enough for a
-    // direct scan up to ~1e5 elements, beyond that the FIBGM is used to prefilter
     std::vector<int> stamp(nG, -1);
     double RsMaxAll = 0.;
     for (int s2 = 0; s2 < nG; ++s2) RsMaxAll = std::max(RsMaxAll, m->ElemRadiusNGeo[s2]);
-    for (int e = 0; e < g.nElems; ++e) {
-      const int ge = g.offsetElem + e;
+    int tagCounter = 0;
+    // sources (restricted to [srcLo, srcHi) global 0-based) that reach global element ge; appended to `out` as (src, case)
+    auto reach = [&](int ge, int srcLo, int srcHi, std::vector<std::pair<int, int>>& out) {
       const double* be = m->ElemBaryNGeo + (size_t)ge * 3;
       const double Re = m->ElemRadiusNGeo[ge];
       for (int c = 0; c < nCaseLoop; ++c) {
-        // sources must satisfy |be - shift - bs| <= rmax + Re + Rs  -> query point q = be - shift
         const double q[3] = {be[0] - shift[c][0], be[1] - shift[c][1], be[2] - shift[c][2]};
-        double Rq = rmax + Re;
-        // prefilter through the FIBGM cells overlapped by q +- (Rq + largest element radius), full range in unused directions
-        const double Rs_max = RsMaxAll;
+        const double Rq = rmax + Re;
         int lo[3], hi[3];
         for (int d = 0; d < 3; ++d) {
-          lo[d] = (int)floor((q[d] - (Rq + Rs_max) - m->xyzminglob[d]) / m->FIBGMdeltas[d]) + 1;
-          hi[d] = (int)floor((q[d] + (Rq + Rs_max) - m->xyzminglob[d]) / m->FIBGMdeltas[d]) + 1;
-          bool used = (dim_sf == 3) || (dim_sf == 1 && d == p->dim_sf_dir - 1) || (dim_sf == 2 && d != p->dim_sf_dir - 1);
+          lo[d] = (int)floor((q[d] - (Rq + RsMaxAll) - m->xyzminglob[d]) / m->FIBGMdeltas[d]) + 1;
+          hi[d] = (int)floor((q[d] + (Rq + RsMaxAll) - m->xyzminglob[d]) / m->FIBGMdeltas[d]) + 1;
+          const bool used = (dim_sf == 3) || (dim_sf == 1 && d == p->dim_sf_dir - 1) || (dim_sf == 2 && d != p->dim_sf_dir - 1);
           if (!used) { lo[d] = m->FIBGMmin[d]; hi[d] = m->FIBGMmax[d]; }
           lo[d] = std::max(lo[d], m->FIBGMmin[d]);
           hi[d] = std::min(hi[d], m->FIBGMmax[d]);
         }
-        const int tag = e * nCaseLoop + c;
+        const int tag = tagCounter++;
         std::vector<int> found;
         for (int kk = lo[0]; kk <= hi[0]; ++kk) for (int ll = lo[1]; ll <= hi[1]; ++ll) for (int mm = lo[2]; mm <= hi[2]; ++mm) {
           const size_t cell = (size_t)(kk - m->FIBGMmin[0]) + (size_t)ni * ((size_t)(ll - m->FIBGMmin[1]) + (size_t)nj * (size_t)(mm - m->FIBGMmin[2]));
@@ -708,23 +713,63 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
             const int gs = m->FIBGM_Element[m->FIBGM_offsetElem[cell] + k2] - 1;
             if (stamp[gs] == tag) continue;
             stamp[gs] = tag;
-            const int ls = gs - g.offsetElem;
-            if (ls < 0 || ls >= g.nElems) continue;  // particles live in local elements only
+            if (gs < srcLo || gs >= srcHi) continue;
             const double* bs = m->ElemBaryNGeo + (size_t)gs * 3;
             const double dv[3] = {q[0] - bs[0], q[1] - bs[1], q[2] - bs[2]};
-            if (sfnorm(dv) <= 1.0000001 * (rmax + Re + m->ElemRadiusNGeo[gs])) found.push_back(ls);
+            if (sfnorm(dv) <= 1.0000001 * (rmax + Re + m->ElemRadiusNGeo[gs])) found.push_back(gs);
           }
         }
         std::sort(found.begin(), found.end());
-        for (int ls : found) { candSrc.push_back(ls); candCase.push_back((uint8_t)(nSFCases > 1 ? c + 1 : 0)); }
+        for (int gs : found) out.emplace_back(gs, nSFCases > 1 ? c + 1 : 0);
       }
-      candOff[e + 1] = (int32_t)candSrc.size();
+    };
+    const int myLo = g.offsetElem, myHi = g.offsetElem + g.nElems;
+    // halo targets and the mirror-image receive lists (both follow from the geometry, no communication needed)
+    g.sfSendCount.assign(g.nRanks, 0);
+    g.sfRecvCount.assign(g.nRanks, 0);
+    std::vector<int32_t> recvLocal;
+    if (g.nRanks > 1) {
+      std::vector<int> rlo(g.nRanks, nG), rhi(g.nRanks, 0);
+      for (int e = 0; e < nG; ++e) { rlo[rank[e]] = std::min(rlo[rank[e]], e); rhi[rank[e]] = std::max(rhi[rank[e]], e + 1); }
+      std::vector<std::pair<int, int>> tmp;
+      for (int r = 0; r < g.nRanks; ++r) {
+        if (r == g.myRank) continue;
+        for (int ge = rlo[r]; ge < rhi[r]; ++ge) {          // elements of rank r reached by my particles -> I send
+          tmp.clear();
+          reach(ge, myLo, myHi, tmp);
+          if (!tmp.empty()) { targets.push_back(ge + 1); g.sfSendCount[r]++; }
+        }
+        for (int ge = myLo; ge < myHi; ++ge) {              // my elements reached by particles of rank r -> I receive
+          tmp.clear();
+          reach(ge, rlo[r], rhi[r], tmp);
+          if (!tmp.empty()) { recvLocal.push_back(ge - g.offsetElem); g.sfRecvCount[r]++; }
+        }
+      }
     }
+    g.nSfTargets = (int)targets.size();
+    g.nSfHalo = g.nSfTargets - g.nElems;
+    g.sfRecvTotal = (int64_t)recvLocal.size();
+    candOff.assign(1, 0);
+    {
+      std::vector<std::pair<int, int>> tmp;
+      for (int t = 0; t < g.nSfTargets; ++t) {
+        tmp.clear();
+        reach(targets[t] - 1, myLo, myHi, tmp);
+        for (auto& sc : tmp) { candSrc.push_back(sc.first - g.offsetElem); candCase.push_back((uint8_t)sc.second); }
+        candOff.push_back((int32_t)candSrc.size());
+      }
+    }
+    if (upload(&g.dSfTarget, targets.data(), targets.size())) return 1;
+    if (upload(&g.dSfRecvLocal, recvLocal.data(), recvLocal.size())) return 1;
+    CK(cudaMalloc((void**)&g.dSfRecv, (size_t)(recvLocal.size() ? recvLocal.size() : 1) * g.ND * 4 * 8));
+    cudaFree(g.dPartSource);   // local elements followed by the halo targets
+    CK(cudaMalloc((void**)&g.dPartSource, (size_t)(g.nSfTargets ? g.nSfTargets : 1) * g.ND * 4 * 8));
     if (upload(&g.dCandOff, candOff.data(), candOff.size())) return 1;
     if (upload(&g.dCandSrc, candSrc.data(), candSrc.size())) return 1;
     if (upload(&g.dCandCase, candCase.data(), candCase.size())) return 1;
     g.sfT.FIBGM_nElems = g.dFibN; g.sfT.FIBGM_offsetElem = g.dFibOff; g.sfT.FIBGM_Element = g.dFibElem; g.sfT.ElemToBGM = g.dElemToBGM;
     g.sfT.ElemBary = g.dElemBary; g.sfT.ElemRadius = g.dElemRadius; g.sfT.Elem_xGP = g.dElemXGP; g.sfT.ElemsJ = g.dElemsJ;
+    g.sfT.target = g.dSfTarget;
     g.sfT.SFElemr2 = g.dSFElemr2; g.sfT.candOff = g.dCandOff; g.sfT.candSrc = g.dCandSrc; g.sfT.candCase = g.dCandCase;
   }
   CK(cudaMalloc((void**)&g.dE, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
@@ -926,11 +971,11 @@ static int deposit_sf(double* PartSource) {
     ++g.lastLaunches;
   }
   cudaEventRecord(g.evp[1], g.st);
-  if (g.nElems > 0) {
+  if (g.nSfTargets > 0) {
     int nt = ((g.ND + 31) / 32) * 32;
     if (nt < 64) nt = 64;
-    const int grid = g.nElems < g.nSMs * 16 ? g.nElems : g.nSMs * 16;
-    k_sf_gather<<<grid, nt, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.sfT, g.dSfFac[0], g.dSfFac[1], g.dSfFac[2],
+    const int grid = g.nSfTargets < g.nSMs * 16 ? g.nSfTargets : g.nSMs * 16;
+    k_sf_gather<<<grid, nt, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nSfTargets, g.offsetElem, g.sfT, g.dSfFac[0], g.dSfFac[1], g.dSfFac[2],
                                        g.dSfFac[3], g.dPartSource);
     ++g.lastLaunches;
   }
@@ -946,10 +991,10 @@ static int deposit_sf(double* PartSource) {
   }
   int hc[4] = {0, 0, 0, 0};
   CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
-  if (PartSource) CK(cudaMemcpyAsync(PartSource, g.dPartSource, (size_t)g.nElems * g.ND * 4 * 8, cudaMemcpyDeviceToHost, g.st));
+  if (PartSource && g.nRanks == 1) CK(cudaMemcpyAsync(PartSource, g.dPartSource, (size_t)g.nElems * g.ND * 4 * 8, cudaMemcpyDeviceToHost, g.st));
   CK(cudaStreamSynchronize(g.st));
   if (hc[3]) return fail("piclas_gpu_deposit: charge-conserving shape function found no DOF within the radius of a particle");
-  return 0;
+  return 0;   // multi-rank: piclas_gpu_sf_halo_info -> exchange -> piclas_gpu_deposit_finish
 }
 
 int piclas_gpu_deposit(double* PartSource, double* NodeSource) {
@@ -976,9 +1021,30 @@ int piclas_gpu_nodesource_device(void** devNodeSource) {
   return 0;
 }
 
+int piclas_gpu_sf_halo_info(int64_t* nSendElemsPerRank, int64_t* nRecvElemsPerRank, int32_t* doublesPerElem, void** devSend,
+                            void** devRecv) {
+  if (!g.ready || !g.sfActive) return fail("piclas_gpu_sf_halo_info: shape-function deposition is not active");
+  for (int r = 0; r < g.nRanks; ++r) { nSendElemsPerRank[r] = g.sfSendCount[r]; nRecvElemsPerRank[r] = g.sfRecvCount[r]; }
+  *doublesPerElem = g.ND * 4;
+  *devSend = g.dPartSource + (size_t)g.nElems * g.ND * 4;   // halo targets follow the local elements, grouped by owner rank
+  *devRecv = g.dSfRecv;
+  return 0;
+}
+
 int piclas_gpu_deposit_finish(double* PartSource, double* NodeSource) {
   if (!g.ready) return fail("piclas_gpu_deposit_finish: not initialised");
   CK(cudaSetDevice(g.device));
+  if (g.sfActive) {
+    if (g.sfRecvTotal > 0) {
+      const int nd4 = g.ND * 4;
+      k_sf_add_halo<<<(nd4 + 127) / 128, 128, 0, g.st>>>(g.dPartSource, g.dSfRecv, g.dSfRecvLocal, (int)g.sfRecvTotal, nd4);
+      ++g.lastLaunches;
+      CK(cudaGetLastError());
+    }
+    if (PartSource) CK(cudaMemcpyAsync(PartSource, g.dPartSource, (size_t)g.nElems * g.ND * 4 * 8, cudaMemcpyDeviceToHost, g.st));
+    CK(cudaStreamSynchronize(g.st));
+    return 0;
+  }
   const int keep = g.lastLaunches;
   const double ms = g.lastMs;
   begin_timing();

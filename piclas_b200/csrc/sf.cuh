@@ -14,7 +14,8 @@
 struct SFTables {
   const int32_t *FIBGM_nElems, *FIBGM_offsetElem, *FIBGM_Element, *ElemToBGM;
   const double *ElemBary, *ElemRadius, *Elem_xGP, *ElemsJ, *SFElemr2;
-  const int32_t* candOff;   // [nElems+1]
+  const int32_t* target;    // [nTargets] global element id of every gather target: the local elements, then halo elements
+  const int32_t* candOff;   // [nTargets+1]
   const int32_t* candSrc;   // local source element
   const uint8_t* candCase;  // periodic case (1-based), 0 = unshifted position
 };
@@ -172,7 +173,21 @@ __global__ void k_sf_prepare(PartBuf pb, int64_t n, SFTables T, double* __restri
 
 constexpr int SF_CHUNK = 128;
 
+// halo sum of the DOF contributions received from the other ranks (pic_depo_method.f90:983-996), rank after rank
+__global__ void k_sf_add_halo(double* __restrict__ PartSource, const double* __restrict__ recv, const int32_t* __restrict__ recvElemLocal,
+                              int nRecvElems, int nd4) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= (int64_t)nd4) return;
+  // one thread per (dof, component): contributions of all senders are added in the order of the receive list (= rank order)
+  for (int i = 0; i < nRecvElems; ++i) {
+    const int e = recvElemLocal[i];
+    PartSource[(size_t)e * nd4 + t] = PartSource[(size_t)e * nd4 + t] + recv[(size_t)i * nd4 + t];
+  }
+}
+
 // PartSource of one target element per CTA; thread t < ND owns DOF t (k fastest)
+// targets 0..nElems-1 are the local elements; further targets are elements of other ranks reached by local particles
+// (the reference's SendBuffer for ShapeMapping, pic_depo_shapefunction_tools.f90:948-964)
 __global__ void k_sf_gather(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems, int offsetElem, SFTables T,
                             const double* __restrict__ f0, const double* __restrict__ f1, const double* __restrict__ f2,
                             const double* __restrict__ f3, double* __restrict__ PartSource) {
@@ -181,7 +196,7 @@ __global__ void k_sf_gather(PartBuf pb, const int64_t* __restrict__ elemOff, int
   const int NP = cst.N + 1, ND = NP * NP * NP;
   const int t = threadIdx.x;
   for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
-    const int g = offsetElem + e + 1;
+    const int g = T.target[e];
     double xd[3] = {0., 0., 0.};
     if (t < ND) {
       const double* xg = T.Elem_xGP + ((size_t)(g - 1) * ND + t) * 3;
