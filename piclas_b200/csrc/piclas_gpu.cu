@@ -55,7 +55,8 @@ struct Ctx {
   double *dElemBary = nullptr, *dElemRadius = nullptr, *dElemsJ = nullptr, *dSFElemr2 = nullptr;
   double* dSfFac[4] = {nullptr, nullptr, nullptr, nullptr};
   int nSfTargets = 0, nSfHalo = 0;               // gather targets: nElems local + nSfHalo elements of other ranks
-  int32_t *dSfTarget = nullptr, *dSfRecvLocal = nullptr;
+  int32_t *dSfTarget = nullptr, *dSfRecvElem = nullptr, *dSfRecvOff = nullptr, *dSfRecvIdx = nullptr;
+  int nSfRecvElems = 0;                            // distinct local elements that receive halo contributions
   double* dSfRecv = nullptr;                       // received halo contributions [nRecvElems][ND][4]
   std::vector<int64_t> sfSendCount, sfRecvCount;   // elements per rank
   int64_t sfRecvTotal = 0;
@@ -367,7 +368,7 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dFibN); cudaFree(g.dFibOff); cudaFree(g.dFibElem); cudaFree(g.dElemToBGM); cudaFree(g.dCandOff); cudaFree(g.dCandSrc);
   cudaFree(g.dCandCase); cudaFree(g.dElemBary); cudaFree(g.dElemRadius); cudaFree(g.dElemsJ); cudaFree(g.dSFElemr2);
   for (int c = 0; c < 4; ++c) cudaFree(g.dSfFac[c]);
-  cudaFree(g.dSfTarget); cudaFree(g.dSfRecvLocal); cudaFree(g.dSfRecv);
+  cudaFree(g.dSfTarget); cudaFree(g.dSfRecvElem); cudaFree(g.dSfRecvOff); cudaFree(g.dSfRecvIdx); cudaFree(g.dSfRecv);
   cudaFree(g.dXiB[0]);
   cudaFree(g.dElemToBCSides); cudaFree(g.dSideInfo); cudaFree(g.dSideBCMetrics); cudaFree(g.dSideNormVec); cudaFree(g.dSideDistance);
   cudaFree(g.dBV0); cudaFree(g.dBV1); cudaFree(g.dBV2); cudaFree(g.dElemRadius2); cudaFree(g.dElemEpsOneCell);
@@ -760,7 +761,19 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
       }
     }
     if (upload(&g.dSfTarget, targets.data(), targets.size())) return 1;
-    if (upload(&g.dSfRecvLocal, recvLocal.data(), recvLocal.size())) return 1;
+    {  // receive list grouped by local element (CSR), entries of one element in rank order
+      std::vector<int32_t> cnt(g.nElems + 1, 0), rElem, rOff(1, 0), rIdx(recvLocal.size());
+      for (int32_t e : recvLocal) cnt[e + 1]++;
+      for (int e = 0; e < g.nElems; ++e) cnt[e + 1] += cnt[e];
+      std::vector<int32_t> fill(cnt.begin(), cnt.end() - 1);
+      for (size_t i = 0; i < recvLocal.size(); ++i) rIdx[fill[recvLocal[i]]++] = (int32_t)i;
+      for (int e = 0; e < g.nElems; ++e)
+        if (cnt[e + 1] > cnt[e]) { rElem.push_back(e); rOff.push_back(cnt[e + 1]); }
+      g.nSfRecvElems = (int)rElem.size();
+      if (upload(&g.dSfRecvElem, rElem.data(), rElem.size())) return 1;
+      if (upload(&g.dSfRecvOff, rOff.data(), rOff.size())) return 1;
+      if (upload(&g.dSfRecvIdx, rIdx.data(), rIdx.size())) return 1;
+    }
     CK(cudaMalloc((void**)&g.dSfRecv, (size_t)(recvLocal.size() ? recvLocal.size() : 1) * g.ND * 4 * 8));
     cudaFree(g.dPartSource);   // local elements followed by the halo targets
     CK(cudaMalloc((void**)&g.dPartSource, (size_t)(g.nSfTargets ? g.nSfTargets : 1) * g.ND * 4 * 8));
@@ -1035,9 +1048,9 @@ int piclas_gpu_deposit_finish(double* PartSource, double* NodeSource) {
   if (!g.ready) return fail("piclas_gpu_deposit_finish: not initialised");
   CK(cudaSetDevice(g.device));
   if (g.sfActive) {
-    if (g.sfRecvTotal > 0) {
+    if (g.nSfRecvElems > 0) {
       const int nd4 = g.ND * 4;
-      k_sf_add_halo<<<(nd4 + 127) / 128, 128, 0, g.st>>>(g.dPartSource, g.dSfRecv, g.dSfRecvLocal, (int)g.sfRecvTotal, nd4);
+      k_sf_add_halo<<<g.nSfRecvElems, 128, 0, g.st>>>(g.dPartSource, g.dSfRecv, g.dSfRecvElem, g.dSfRecvOff, g.dSfRecvIdx, nd4);
       ++g.lastLaunches;
       CK(cudaGetLastError());
     }

@@ -174,14 +174,14 @@ __global__ void k_sf_prepare(PartBuf pb, int64_t n, SFTables T, double* __restri
 constexpr int SF_CHUNK = 128;
 
 // halo sum of the DOF contributions received from the other ranks (pic_depo_method.f90:983-996), rank after rank
-__global__ void k_sf_add_halo(double* __restrict__ PartSource, const double* __restrict__ recv, const int32_t* __restrict__ recvElemLocal,
-                              int nRecvElems, int nd4) {
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (t >= (int64_t)nd4) return;
-  // one thread per (dof, component): contributions of all senders are added in the order of the receive list (= rank order)
-  for (int i = 0; i < nRecvElems; ++i) {
-    const int e = recvElemLocal[i];
-    PartSource[(size_t)e * nd4 + t] = PartSource[(size_t)e * nd4 + t] + recv[(size_t)i * nd4 + t];
+__global__ void k_sf_add_halo(double* __restrict__ PartSource, const double* __restrict__ recv, const int32_t* __restrict__ recvElem,
+                              const int32_t* __restrict__ recvOff, const int32_t* __restrict__ recvIdx, int nd4) {
+  // one CTA per receiving element; the blocks of the sending ranks are added in rank order (recvIdx is sorted)
+  const int e = recvElem[blockIdx.x];
+  for (int t = threadIdx.x; t < nd4; t += blockDim.x) {
+    double a = PartSource[(size_t)e * nd4 + t];
+    for (int i = recvOff[blockIdx.x]; i < recvOff[blockIdx.x + 1]; ++i) a = a + recv[(size_t)recvIdx[i] * nd4 + t];
+    PartSource[(size_t)e * nd4 + t] = a;
   }
 }
 

@@ -104,11 +104,56 @@ INTERFACE
     INTEGER(C_INT64_T),INTENT(OUT) :: n_out
     INTEGER(C_INT)                 :: piclas_gpu_download_particles
   END FUNCTION
+  ! ---- multi-rank: particle migration (particle_mpi.f90:202-1024), device buffers for CUDA-aware MPI / NCCL
+  FUNCTION piclas_gpu_exchange_info(partCommSize,nSendPerRank,devSendBuf) BIND(C,NAME='piclas_gpu_exchange_info')
+    IMPORT :: C_INT, C_INT32_T, C_INT64_T, C_PTR
+    INTEGER(C_INT32_T),INTENT(OUT) :: partCommSize
+    INTEGER(C_INT64_T),INTENT(OUT) :: nSendPerRank(*)            ! [nProcessors]
+    TYPE(C_PTR),INTENT(OUT)        :: devSendBuf
+    INTEGER(C_INT)                 :: piclas_gpu_exchange_info
+  END FUNCTION
+  FUNCTION piclas_gpu_exchange_recv_buffer(nRecvTotal,devRecvBuf) BIND(C,NAME='piclas_gpu_exchange_recv_buffer')
+    IMPORT :: C_INT, C_INT64_T, C_PTR
+    INTEGER(C_INT64_T),VALUE :: nRecvTotal
+    TYPE(C_PTR),INTENT(OUT)  :: devRecvBuf
+    INTEGER(C_INT)           :: piclas_gpu_exchange_recv_buffer
+  END FUNCTION
+  FUNCTION piclas_gpu_exchange_finish(nRecvTotal) BIND(C,NAME='piclas_gpu_exchange_finish')
+    IMPORT :: C_INT, C_INT64_T
+    INTEGER(C_INT64_T),VALUE :: nRecvTotal
+    INTEGER(C_INT)           :: piclas_gpu_exchange_finish
+  END FUNCTION
+  ! ---- multi-rank deposition: node halo of cell_volweight_mean (pic_depo_method.f90:565-673), DOF halo of the shape functions (:940-996)
+  FUNCTION piclas_gpu_nodesource_device(devNodeSource) BIND(C,NAME='piclas_gpu_nodesource_device')
+    IMPORT :: C_INT, C_PTR
+    TYPE(C_PTR),INTENT(OUT) :: devNodeSource                     ! [4,nUniqueGlobalNodes] doubles on the device
+    INTEGER(C_INT)          :: piclas_gpu_nodesource_device
+  END FUNCTION
+  FUNCTION piclas_gpu_sf_halo_info(nSendElemsPerRank,nRecvElemsPerRank,doublesPerElem,devSend,devRecv) &
+      BIND(C,NAME='piclas_gpu_sf_halo_info')
+    IMPORT :: C_INT, C_INT32_T, C_INT64_T, C_PTR
+    INTEGER(C_INT64_T),INTENT(OUT) :: nSendElemsPerRank(*),nRecvElemsPerRank(*)
+    INTEGER(C_INT32_T),INTENT(OUT) :: doublesPerElem
+    TYPE(C_PTR),INTENT(OUT)        :: devSend,devRecv
+    INTEGER(C_INT)                 :: piclas_gpu_sf_halo_info
+  END FUNCTION
+  FUNCTION piclas_gpu_deposit_finish(PartSource,NodeSource) BIND(C,NAME='piclas_gpu_deposit_finish')
+    IMPORT :: C_INT, C_PTR
+    TYPE(C_PTR),VALUE :: PartSource, NodeSource
+    INTEGER(C_INT)    :: piclas_gpu_deposit_finish
+  END FUNCTION
+  FUNCTION piclas_gpu_phase_timing(ms4) BIND(C,NAME='piclas_gpu_phase_timing')
+    IMPORT :: C_INT, C_DOUBLE
+    REAL(C_DOUBLE),INTENT(OUT) :: ms4(4)                         ! -> LBSplitTime(LB_DEPO / LB_INTERPOLATION+LB_PUSH+LB_TRACK / LB_UNFP)
+    INTEGER(C_INT)             :: piclas_gpu_phase_timing
+  END FUNCTION
 END INTERFACE
 
 PUBLIC :: pgpu_mesh_t, pgpu_params_t
 PUBLIC :: piclas_gpu_init, piclas_gpu_finalize, piclas_gpu_upload_particles, piclas_gpu_deposit, piclas_gpu_set_field
 PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles
+PUBLIC :: piclas_gpu_exchange_info, piclas_gpu_exchange_recv_buffer, piclas_gpu_exchange_finish
+PUBLIC :: piclas_gpu_nodesource_device, piclas_gpu_sf_halo_info, piclas_gpu_deposit_finish, piclas_gpu_phase_timing
 PUBLIC :: ParticleStepGPU, GPUAbortOnError
 
 CONTAINS

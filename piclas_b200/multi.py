@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import hostmesh as hm
-from .abi import Params
+from .abi import DEPO_CVWM, Params
 
 
 class _DevPtr:
@@ -59,6 +59,14 @@ def exchange_particles(send_buf, send_counts, recv_buf, recv_counts, comm_size, 
 def halo_sum(node_tensor, group=None):
     """cell_volweight_mean node halo (pic_depo_method.f90:565-673) as a sum over all ranks."""
     dist.all_reduce(node_tensor, op=dist.ReduceOp.SUM, group=group)
+
+
+def exchange_sf_halo(send_buf, send_elems, recv_buf, recv_elems, doubles_per_elem, group=None):
+    """Shape-function DOF halo (pic_depo_method.f90:940-996, ShapeMapping Send/RecvBuffer): every rank sends the
+    PartSource blocks its particles formed on elements of other ranks; blocks are ordered by owner rank."""
+    ins = [int(c) * doubles_per_elem for c in send_elems]
+    outs = [int(c) * doubles_per_elem for c in recv_elems]
+    dist.all_to_all_single(recv_buf, send_buf, output_split_sizes=outs, input_split_sizes=ins, group=group)
 
 
 # ---- the GPU rank --------------------------------------------------------------------------------------------------------
@@ -109,6 +117,21 @@ class ParticleStepRank:
 
     def Deposition(self, want_partsource=True, want_nodesource=True, out_partsource=None):
         from .particle_step import _f
+        if self.step.params.DepositionType != DEPO_CVWM:                            # shape functions: DOF halo
+            self._check(self.lib.piclas_gpu_deposit(_f(None), _f(None)))
+            ns = (C.c_int64 * self.world)()
+            nr = (C.c_int64 * self.world)()
+            dpe = C.c_int32(0)
+            sp, rp = C.c_void_p(0), C.c_void_p(0)
+            self._check(self.lib.piclas_gpu_sf_halo_info(ns, nr, C.byref(dpe), C.byref(sp), C.byref(rp)))
+            ns, nr = [int(v) for v in ns], [int(v) for v in nr]
+            sbuf = device_tensor(sp.value, sum(ns) * dpe.value, self.device)
+            rbuf = device_tensor(rp.value, sum(nr) * dpe.value, self.device)
+            exchange_sf_halo(sbuf, ns, rbuf, nr, dpe.value, self.group)
+            torch.cuda.synchronize(self.device)
+            PS = out_partsource if out_partsource is not None else (np.empty(self.step._ps_shape) if want_partsource else None)
+            self._check(self.lib.piclas_gpu_deposit_finish(_f(PS), _f(None)))
+            return PS, None
         self._check(self.lib.piclas_gpu_deposit(_f(None), _f(None)))       # rank-local node sums
         p = C.c_void_p(0)
         self._check(self.lib.piclas_gpu_nodesource_device(C.byref(p)))

@@ -21,6 +21,7 @@ import cases  # noqa: E402
 from oracle_lib import Oracle  # noqa: E402
 from piclas_b200 import hostmesh as hm  # noqa: E402
 from piclas_b200 import multi  # noqa: E402
+from piclas_b200.abi import DEPO_CVWM, DEPO_SF, DEPO_SF_CC  # noqa: E402
 
 
 class OracleRank:
@@ -32,6 +33,9 @@ class OracleRank:
         self.mesh = mesh
         self.orc = Oracle(mesh, prm, offsetElem=int(self.off[rank]), nElems=int(self.off[rank + 1] - self.off[rank]))
         self.dev = torch.device("cpu")
+        self.sf = prm.DepositionType != DEPO_CVWM
+        if self.sf:
+            self.orc_full = Oracle(mesh, prm)
 
     def upload(self, PS, spec, elem, ids):
         self.PS, self.spec, self.elem, self.ids = PS.copy(), spec.copy(), elem.copy(), ids.copy()
@@ -42,6 +46,25 @@ class OracleRank:
 
     def deposition(self):
         inside = np.ones(len(self.spec), dtype=np.int32)
+        if self.sf:
+            # the local particles' contributions to every element, then the DOF halo: the blocks of foreign elements go to
+            # their owners, which add them rank after rank (pic_depo_method.f90:940-996)
+            full, _ = self.orc_full.deposit(self.PS, self.spec, self.elem, inside)
+            off, w = self.off, self.world
+            dpe = int(np.prod(full.shape[1:]))
+            others = [r for r in range(w) if r != self.rank]
+            send = [int(off[r + 1] - off[r]) if r != self.rank else 0 for r in range(w)]
+            mine = int(off[self.rank + 1] - off[self.rank])
+            recv = [mine if r != self.rank else 0 for r in range(w)]
+            sb = np.concatenate([full[int(off[r]):int(off[r + 1])].reshape(-1) for r in others]) if others else np.zeros(0)
+            sbuf = torch.from_numpy(np.ascontiguousarray(sb))
+            rbuf = torch.empty(sum(recv) * dpe, dtype=torch.float64)
+            multi.exchange_sf_halo(sbuf, send, rbuf, recv, dpe)
+            out = full[int(off[self.rank]):int(off[self.rank + 1])].copy()
+            rb = rbuf.numpy().reshape((len(others),) + out.shape)
+            for i in range(len(others)):
+                out = out + rb[i]
+            return out, None
         NS = self.orc.deposit_raw(self.PS, self.spec, self.elem, inside)
         t = torch.from_numpy(NS.reshape(-1))
         multi.halo_sum(t)
@@ -108,6 +131,7 @@ def main():
     ap.add_argument("--engine", default="oracle")
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--particles", type=int, default=12000)
+    ap.add_argument("--depo", default="cvwm", choices=["cvwm", "sf", "cc"])
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -118,7 +142,15 @@ def main():
         dist.init_process_group("gloo")
 
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 3, 6), 2)
-    prm = cases.electron_params()
+    def params():
+        if a.depo == "cvwm":
+            return cases.electron_params()
+        q = cases.electron_params(DepositionType=DEPO_SF if a.depo == "sf" else DEPO_SF_CC)
+        hm.shape_function_setup(mesh, q, 0.3, 2, dim_sf=3)
+        return q
+    if a.depo != "cvwm":
+        hm.add_fibgm(mesh)
+    prm = params()
     dt = 2e-8   # keeps the Maxwellian tail far below c (gamma stays finite)
     PS, spec = cases.uniform_plasma(mesh, a.particles, seed=77, vth_cells=0.45, dt=dt)   # identical on every rank
     elem = hm.cartesian_locate(mesh, PS[:, :3])
@@ -132,7 +164,7 @@ def main():
 
     # single-rank reference on rank 0
     if rank == 0:
-        ref = Oracle(mesh, cases.electron_params())
+        ref = Oracle(mesh, params())
         PSr, elr = PS.copy(), elem.copy()
         inside = np.ones(len(spec), dtype=np.int32)
         isnew = np.ones(len(spec), dtype=np.int32)
@@ -156,7 +188,7 @@ def main():
             ex = np.abs(allps[o] - PSr).max() / np.abs(PSr).max()
             assert ex <= 1e-12, ex
             for r, p in enumerate(parts):   # every rank holds the complete NodeSource after the halo sum
-                for c in range(4):
+                for c in range(4 if p[3] is not None else 0):
                     en = np.abs(p[3][:, c] - NSo[:, c]).max() / max(np.abs(NSo[:, c]).max(), 1e-300)
                     assert en <= 1e-12, (r, c, en)
                 sl = slice(int(off[r]), int(off[r + 1]))
@@ -165,7 +197,7 @@ def main():
                 own = (p[2] > off[r]) & (p[2] <= off[r + 1])
                 assert own.all(), "rank holds particles of elements it does not own"
     if rank == 0:
-        print("MULTI_OK engine=%s world=%d steps=%d" % (a.engine, world, a.steps))
+        print("MULTI_OK engine=%s world=%d steps=%d depo=%s" % (a.engine, world, a.steps, a.depo))
     if a.engine == "gpu":
         eng.R.close()
     dist.destroy_process_group()

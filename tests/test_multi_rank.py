@@ -13,9 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "multi_worker.py")
 
 
-def _run(world, engine, port):
+def _run(world, engine, port, depo="cvwm"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, "--engine", engine]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, "--engine", engine, "--depo", depo]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
@@ -26,9 +26,15 @@ def test_multi_rank_gloo_oracle(world):
     _run(world, "oracle", 29611 + world)
 
 
+def test_multi_rank_gloo_oracle_shape_function():
+    """DOF halo of the shape-function deposition over gloo."""
+    _run(2, "oracle", 29617, depo="sf")
+
+
 @pytest.mark.gpu
-def test_multi_rank_gpu_nccl():
+@pytest.mark.parametrize("depo", ["cvwm", "sf", "cc"])
+def test_multi_rank_gpu_nccl(depo):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    _run(2, "gpu", 29631)
+    _run(2, "gpu", 29631 + ["cvwm", "sf", "cc"].index(depo), depo=depo)
