@@ -30,11 +30,99 @@ __device__ __forceinline__ void stage_words(void* dst, const void* src, int nbyt
   for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x) d[i] = __ldg(s + i);
 }
 
+// ---- asynchronous staging of the next particle tile (cp.async, one 8-byte copy per thread and array) ---------------------------
+// The per-element kernels run 16 warps per SM (128 registers per thread), too few to hide the DRAM latency of the
+// particle loads behind arithmetic (r1v5 profile: 32 % of k_interp_push's stall samples sat on the first use of the
+// loaded particle).  Each thread therefore copies its particle of the NEXT loop iteration into a private shared-memory
+// slot while it works on the current one; slots are private to the thread, so no barrier is needed.
+__device__ __forceinline__ void cp_async8(double* smemDst, const double* gmemSrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 // ---- Newton mapping for all particles of an element + CVWM accumulation -----------------------------------------------------
 // DepositionMethod_CVWM particle loop, pic_depo_method.f90:471-544.  elemAcc[e][node 0..7 (CGNS)][0..3] receives the
 // element-local sums of TSource*weight; xi and the SucRefPos flag are cached for the interpolation of the same step.
-// The 32 per-thread accumulators live in shared memory ([a][thread], conflict free) so that the Newton iteration keeps
-// the register file; they are reduced in a fixed order (deterministic, independent of scheduling).
+// Two accumulation paths, both reduced over the CTA in a fixed order (deterministic, independent of scheduling):
+//   * general: the 32 per-thread accumulators live in shared memory ([a][thread], conflict free) so that the Newton
+//     iteration keeps the register file;
+//   * restructured arithmetic on an affine element (CTA-uniform): closed-form xi, accumulators in registers, no calls in
+//     the loop; the (never observed) particles whose closed-form xi is far outside the element take the general path
+//     in a second sweep.
+typedef double DepAcc[32][STEP_NT];
+
+// one particle through the general path.  x, xi: position and (output) reference position
+__device__ __forceinline__ void deposit_particle_general(const PartBuf& pb, int64_t p, const GeoElem* sg, const double (*corner)[3],
+                                                         DepAcc& sAcc, int tid) {
+  double* __restrict__ const PF = pb.f;
+  double* __restrict__ const PXI = pb.xif;
+  const int64_t PS_ = pb.stride;
+  const double x[3] = {PF[p], PF[1 * PS_ + p], PF[2 * PS_ + p]};
+  const uint8_t meta = pb.meta[p];
+  const int spec = meta & META_SPEC_MASK;
+  double xi[3];
+  const bool suc = (position_in_ref_elem(sg, x, xi, true, true) & 1) != 0;
+  PXI[p] = xi[0];
+  PXI[1 * PS_ + p] = xi[1];
+  PXI[2 * PS_ + p] = xi[2];
+  const uint8_t nmeta = suc ? (meta & ~META_XIFAIL) : (meta | META_XIFAIL);
+  if (nmeta != meta) pb.meta[p] = nmeta;
+  const double q = cst.ChargeIC[spec];
+  if (!(fabs(q) > 0.0)) return;  // isDepositParticle
+  const double Charge = q * cst.MPF[spec];
+  const double T[4] = {PF[3 * PS_ + p] * Charge, PF[4 * PS_ + p] * Charge, PF[5 * PS_ + p] * Charge, Charge};
+  double w[8];
+  if (suc) {
+    const double a1 = 0.5 * (xi[0] + 1.0), a2 = 0.5 * (xi[1] + 1.0), a3 = 0.5 * (xi[2] + 1.0);
+    w[0] = ((1 - a1) * (1 - a2)) * (1 - a3);
+    w[1] = ((a1) * (1 - a2)) * (1 - a3);
+    w[2] = ((a1) * (a2)) * (1 - a3);
+    w[3] = ((1 - a1) * (a2)) * (1 - a3);
+    w[4] = ((1 - a1) * (1 - a2)) * (a3);
+    w[5] = ((a1) * (1 - a2)) * (a3);
+    w[6] = ((a1) * (a2)) * (a3);
+    w[7] = ((1 - a1) * (a2)) * (a3);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sAcc[n * 4 + c][tid] = sAcc[n * 4 + c][tid] + (T[c] * w[n]);
+  } else {
+    // inverse-distance fallback, :512-538.  CGNS corner n is tensor node cns[n]
+    const int cns[8] = {0, 1, 3, 2, 4, 5, 7, 6};
+    bool hit = false;
+    for (int n = 0; n < 8 && !hit; ++n) {
+      const double* c = corner[cns[n]];
+      const double d0 = c[0] - x[0], d1 = c[1] - x[1], d2 = c[2] - x[2];
+      const double norm = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+      if (norm > 0.) w[n] = 1. / norm;
+      else {
+        for (int j = 0; j < 8; ++j) w[j] = 0.;
+        w[n] = 1.0;
+        hit = true;
+      }
+    }
+    double DistSum = 0.;
+    for (int n = 0; n < 8; ++n) DistSum = DistSum + w[n];
+    for (int n = 0; n < 8; ++n)
+      for (int c = 0; c < 4; ++c) sAcc[n * 4 + c][tid] = sAcc[n * 4 + c][tid] + w[n] / DistSum * T[c];
+  }
+}
+
+__device__ __noinline__ void deposit_particle_cold(const PartBuf* pb, int64_t p, const GeoElem* sg, const double (*corner)[3],
+                                                   DepAcc* sAcc, int tid) {
+  deposit_particle_general(*pb, p, sg, corner, *sAcc, tid);
+}
+
+// closed-form reference position on an affine element (fastmath.cuh ref_position_fast); false: take the general path
+__device__ __forceinline__ bool affine_xi(const AffElem* af, const double x[3], double xi[3]) {
+  const double r0 = x[0] - af->x0[0], r1 = x[1] - af->x0[1], r2 = x[2] - af->x0[2];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) xi[d] = fma(af->A[d][0], r0, fma(af->A[d][1], r1, af->A[d][2] * r2)) - 1.0;
+  return fabs(xi[0]) <= 1.5 && fabs(xi[1]) <= 1.5 && fabs(xi[2]) <= 1.5;
+}
+
 template <bool FAST>
 __global__ void __launch_bounds__(STEP_NT, DEP_MINB) k_deposit_cvwm(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems,
                                                              int offsetElem, const GeoElem* __restrict__ geo,
@@ -46,71 +134,86 @@ __global__ void __launch_bounds__(STEP_NT, DEP_MINB) k_deposit_cvwm(PartBuf pb, 
   __shared__ GeoElem sg;
   __shared__ AffElem sa;
   __shared__ double corner[8][3];
-  __shared__ double sAcc[32][STEP_NT];
+  __shared__ DepAcc sAcc;
+  __shared__ double sP[FAST ? 2 : 1][FAST ? 6 : 1][FAST ? STEP_NT : 1];   // x, v of the current / next particle of every thread
   const int tid = threadIdx.x;
   for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
     const int64_t p0 = elemOff[e], p1 = elemOff[e + 1];
-#pragma unroll
-    for (int a = 0; a < 32; ++a) sAcc[a][tid] = 0.;
+    bool staged = false;
     if (p1 > p0) {
       __syncthreads();
-      stage_words(&sg, geo + (offsetElem + e), sizeof(GeoElem));
       if (FAST) stage_words(&sa, aff + (offsetElem + e), sizeof(AffElem));
-      if (tid < 24) corner[tid / 3][tid % 3] = tria[offsetElem + e].corner[tid / 3][tid % 3];
       __syncthreads();
-      for (int64_t p = p0 + tid; p < p1; p += STEP_NT) {
-        asm volatile("" ::: "memory");  // no hoisting of shared-memory loads over the particle loop
-        const double x[3] = {PF[p], PF[1 * PS_ + p], PF[2 * PS_ + p]};
-        uint8_t meta = pb.meta[p];
-        const int spec = meta & META_SPEC_MASK;
+    }
+    if (FAST && p1 > p0 && sa.affine != 0.0) {
+      double acc[32];
+#pragma unroll
+      for (int a = 0; a < 32; ++a) acc[a] = 0.;
+      int nGeneral = 0;
+      int64_t p = p0 + tid;
+      int stage = 0;
+      uint8_t meta = 0, metaNext = 0;
+      if (p < p1) {
+#pragma unroll
+        for (int a = 0; a < 6; ++a) cp_async8(&sP[0][a][tid], PF + a * PS_ + p);
+        meta = pb.meta[p];
+      }
+      cp_async_commit();
+      for (; p < p1; p += STEP_NT, stage ^= 1, meta = metaNext) {
+        const int64_t pn = p + STEP_NT;
+        if (pn < p1) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) cp_async8(&sP[stage ^ 1][a][tid], PF + a * PS_ + pn);
+          metaNext = pb.meta[pn];
+        }
+        cp_async_commit();
+        cp_async_wait_prev();
+        const double x[3] = {sP[stage][0][tid], sP[stage][1][tid], sP[stage][2][tid]};
         double xi[3];
-        bool suc;
-        if (FAST) suc = ref_position_fast(&sa, &sg, x, xi, true);
-        else suc = (position_in_ref_elem(&sg, x, xi, true, true) & 1) != 0;
+        if (!affine_xi(&sa, x, xi)) { ++nGeneral; continue; }
         PXI[p] = xi[0];
         PXI[1 * PS_ + p] = xi[1];
         PXI[2 * PS_ + p] = xi[2];
-        const uint8_t nmeta = suc ? (meta & ~META_XIFAIL) : (meta | META_XIFAIL);
-        if (nmeta != meta) pb.meta[p] = nmeta;
+        if (meta & META_XIFAIL) pb.meta[p] = meta & ~META_XIFAIL;
+        const int spec = meta & META_SPEC_MASK;
         const double q = cst.ChargeIC[spec];
         if (!(fabs(q) > 0.0)) continue;  // isDepositParticle
         const double Charge = q * cst.MPF[spec];
-        const double T[4] = {PF[3 * PS_ + p] * Charge, PF[4 * PS_ + p] * Charge, PF[5 * PS_ + p] * Charge, Charge};
-        double w[8];
-        if (suc) {
-          const double a1 = 0.5 * (xi[0] + 1.0), a2 = 0.5 * (xi[1] + 1.0), a3 = 0.5 * (xi[2] + 1.0);
-          w[0] = ((1 - a1) * (1 - a2)) * (1 - a3);
-          w[1] = ((a1) * (1 - a2)) * (1 - a3);
-          w[2] = ((a1) * (a2)) * (1 - a3);
-          w[3] = ((1 - a1) * (a2)) * (1 - a3);
-          w[4] = ((1 - a1) * (1 - a2)) * (a3);
-          w[5] = ((a1) * (1 - a2)) * (a3);
-          w[6] = ((a1) * (a2)) * (a3);
-          w[7] = ((1 - a1) * (a2)) * (a3);
+        const double T[4] = {sP[stage][3][tid] * Charge, sP[stage][4][tid] * Charge, sP[stage][5][tid] * Charge, Charge};
+        const double a1 = 0.5 * (xi[0] + 1.0), a2 = 0.5 * (xi[1] + 1.0), a3 = 0.5 * (xi[2] + 1.0);
+        const double b1 = 1 - a1, b2 = 1 - a2, b3 = 1 - a3;
+        const double w[8] = {(b1 * b2) * b3, (a1 * b2) * b3, (a1 * a2) * b3, (b1 * a2) * b3,
+                             (b1 * b2) * a3, (a1 * b2) * a3, (a1 * a2) * a3, (b1 * a2) * a3};
 #pragma unroll
-          for (int n = 0; n < 8; ++n)
+        for (int n = 0; n < 8; ++n)
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              sAcc[n * 4 + c][tid] = FAST ? fma(T[c], w[n], sAcc[n * 4 + c][tid]) : sAcc[n * 4 + c][tid] + (T[c] * w[n]);
-        } else {
-          // inverse-distance fallback, :512-538.  CGNS corner n is tensor node cns[n]
-          const int cns[8] = {0, 1, 3, 2, 4, 5, 7, 6};
-          bool hit = false;
-          for (int n = 0; n < 8 && !hit; ++n) {
-            const double* c = corner[cns[n]];
-            const double d0 = c[0] - x[0], d1 = c[1] - x[1], d2 = c[2] - x[2];
-            const double norm = sqrt((d0 * d0 + d1 * d1) + d2 * d2);
-            if (norm > 0.) w[n] = 1. / norm;
-            else {
-              for (int j = 0; j < 8; ++j) w[j] = 0.;
-              w[n] = 1.0;
-              hit = true;
-            }
-          }
-          double DistSum = 0.;
-          for (int n = 0; n < 8; ++n) DistSum = DistSum + w[n];
-          for (int n = 0; n < 8; ++n)
-            for (int c = 0; c < 4; ++c) sAcc[n * 4 + c][tid] = sAcc[n * 4 + c][tid] + w[n] / DistSum * T[c];
+          for (int c = 0; c < 4; ++c) acc[n * 4 + c] = fma(T[c], w[n], acc[n * 4 + c]);
+      }
+#pragma unroll
+      for (int a = 0; a < 32; ++a) sAcc[a][tid] = acc[a];
+      if (__syncthreads_or(nGeneral)) {
+        stage_words(&sg, geo + (offsetElem + e), sizeof(GeoElem));
+        if (tid < 24) corner[tid / 3][tid % 3] = tria[offsetElem + e].corner[tid / 3][tid % 3];
+        __syncthreads();
+        for (int64_t p = p0 + tid; p < p1; p += STEP_NT) {
+          const double x[3] = {PF[p], PF[1 * PS_ + p], PF[2 * PS_ + p]};
+          double xi[3];
+          if (!affine_xi(&sa, x, xi)) deposit_particle_cold(&pb, p, &sg, corner, &sAcc, tid);
+        }
+      }
+      staged = true;
+    }
+    if (!staged) {
+#pragma unroll
+      for (int a = 0; a < 32; ++a) sAcc[a][tid] = 0.;
+      if (p1 > p0) {
+        stage_words(&sg, geo + (offsetElem + e), sizeof(GeoElem));
+        if (tid < 24) corner[tid / 3][tid % 3] = tria[offsetElem + e].corner[tid / 3][tid % 3];
+        __syncthreads();
+        for (int64_t p = p0 + tid; p < p1; p += STEP_NT) {
+          asm volatile("" ::: "memory");
+          if (FAST) deposit_particle_cold(&pb, p, &sg, corner, &sAcc, tid);   // non-affine element: keep the hot loop's registers
+          else deposit_particle_general(pb, p, &sg, corner, sAcc, tid);
         }
       }
     }
@@ -242,6 +345,8 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
   __shared__ PlaneElem sp;
   __shared__ AffElem sa;
   __shared__ __align__(16) double sE[ND * 3];
+  __shared__ double sP[2][9][STEP_NT];   // x, v, xi of the current / next particle of every thread (cp.async staging)
+  const int tid = threadIdx.x;
   for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
     const int64_t p0 = elemOff[e], p1 = elemOff[e + 1];
     if (p1 <= p0) continue;
@@ -259,11 +364,35 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
       sE[(kj * 3 + c) * NP + i] = __ldg(E + (size_t)e * ND * 3 + t);
     }
     __syncthreads();
-    for (int64_t p = p0 + threadIdx.x; p < p1; p += STEP_NT) {
-      asm volatile("" ::: "memory");  // keep the shared-memory tiles out of the registers (no hoisting over the loop)
-      double x[3] = {PF[p], PF[1 * PS_ + p], PF[2 * PS_ + p]};
-      double v[3] = {PF[3 * PS_ + p], PF[4 * PS_ + p], PF[5 * PS_ + p]};
-      const uint8_t meta = pb.meta[p];
+    const bool useXi = REF || xiValid;
+    int64_t p = p0 + tid;
+    int stage = 0;
+    uint8_t meta = 0, metaNext = 0;
+    if (p < p1) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) cp_async8(&sP[0][a][tid], PF + a * PS_ + p);
+      if (useXi) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) cp_async8(&sP[0][6 + a][tid], PXI + a * PS_ + p);
+      }
+      meta = pb.meta[p];
+    }
+    cp_async_commit();
+    for (; p < p1; p += STEP_NT, stage ^= 1, meta = metaNext) {
+      const int64_t pn = p + STEP_NT;
+      if (pn < p1) {   // next particle of this thread: copies overlap the arithmetic below
+#pragma unroll
+        for (int a = 0; a < 6; ++a) cp_async8(&sP[stage ^ 1][a][tid], PF + a * PS_ + pn);
+        if (useXi) {
+#pragma unroll
+          for (int a = 0; a < 3; ++a) cp_async8(&sP[stage ^ 1][6 + a][tid], PXI + a * PS_ + pn);
+        }
+        metaNext = pb.meta[pn];
+      }
+      cp_async_commit();
+      cp_async_wait_prev();   // (memory clobber: also keeps the shared-memory tiles out of the registers, no hoisting over the loop)
+      double x[3] = {sP[stage][0][tid], sP[stage][1][tid], sP[stage][2][tid]};
+      double v[3] = {sP[stage][3][tid], sP[stage][4][tid], sP[stage][5][tid]};
       const int spec = meta & META_SPEC_MASK;
       bool isNew = (meta & META_ISNEW) != 0;
       double F[6];
@@ -274,10 +403,10 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
         double xi[3];
         bool suc;
         if (REF) {
-          xi[0] = PXI[p]; xi[1] = PXI[1 * PS_ + p]; xi[2] = PXI[2 * PS_ + p];
+          xi[0] = sP[stage][6][tid]; xi[1] = sP[stage][7][tid]; xi[2] = sP[stage][8][tid];
           suc = true;
         } else if (xiValid) {
-          xi[0] = PXI[p]; xi[1] = PXI[1 * PS_ + p]; xi[2] = PXI[2 * PS_ + p];
+          xi[0] = sP[stage][6][tid]; xi[1] = sP[stage][7][tid]; xi[2] = sP[stage][8][tid];
           suc = !(meta & META_XIFAIL);
         } else if (FAST) {
           suc = ref_position_fast(&sa, &sg, x, xi, false);
