@@ -11,9 +11,9 @@
 // ---- per-element records, built once at init from the host tables ---------------------------------------------
 // Tria record: everything ParticleInsideQuad3D / ThroughSideCheck3DFast / IntersectionWithWall need for one
 // element (reference tables ElemInfo/SideInfo/ElemSideNodeID/NodeCoords/ConcaveElemSide),
-// flattened so that a CTA can stage it with one coalesced copy.  40 doubles = 320 B.
-struct __align__(16) TriaElem {
-  double corner[8][3];     // the element's 8 non-unique nodes in storage (tensor) order: NodeCoords(:,first+1..first+8)
+// flattened so that a CTA can stage it with one coalesced copy.  352 B; a corner is one aligned 32-byte unit (256-bit loads).
+struct __align__(32) TriaElem {
+  double corner[8][4];     // the element's 8 non-unique nodes in storage (tensor) order: NodeCoords(:,first+1..first+8), [3] = pad
   int32_t nbElem[6];       // SIDE_NBELEMID of local side 1..6 (global id, 0 = none)
   int32_t sideID[6];       // global SideInfo index (1-based) of local side 1..6
   uint8_t sideNode[6][4];  // ElemSideNodeID(1:4,side) - ELEM_FIRSTNODEIND  (0..7)
@@ -35,11 +35,11 @@ struct __align__(16) GeoElem {
 // Fast-arithmetic records (params.arithmetic == 1), derived at init from the tables above.
 // PlaneElem: inward unit normal and offset of the 12 side triangles: the determinant of ParticleInsideQuad3D for triangle
 // t equals (n_t . x - d_t) * |N_t|, so its sign is known without evaluating it whenever |n_t . x - d_t| > tol.
-struct __align__(16) PlaneElem {
-  double n[12][3];   // index 2*s + (tri-1)
-  double d[12];
+struct __align__(32) PlaneElem {
+  double pl[12][4];  // index 2*s + (tri-1): (n_x, n_y, n_z, d), one aligned 32-byte unit per plane
   double tol;        // 1e-8 * element diameter: far above the rounding error of either formula
-  double pad;
+  uint32_t concave2; // bit 2*s set when ConcaveElemSide(s+1)
+  uint32_t pad[5];
 };
 // AffElem: elements whose trilinear map is affine (parallelepipeds): xi = A (x - x0) - 1 solves the Newton problem exactly
 struct __align__(16) AffElem {

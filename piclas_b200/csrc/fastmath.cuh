@@ -77,10 +77,11 @@ __device__ __noinline__ PushOut push_particle_cold(double x0, double x1, double 
   o.x0 = x[0]; o.x1 = x[1]; o.x2 = x[2]; o.v0 = v[0]; o.v1 = v[1]; o.v2 = v[2]; o.isNew = isNew ? 1 : 0;
   return o;
 }
+template <bool G>
 __device__ __noinline__ uint32_t inside_exact_cold(const TriaElem* __restrict__ te, double x0, double x1, double x2) {
   const double x[3] = {x0, x1, x2};
   uint32_t mask;
-  const bool in = inside_quad3d_mask(te, x, mask);
+  const bool in = inside_quad3d_mask<G>(te, x, mask);
   return mask | (in ? 0x80000000u : 0u);
 }
 
@@ -119,29 +120,30 @@ __device__ __forceinline__ void push_particle_fast(double x[3], double v[3], con
 }
 
 // ParticleInsideQuad3D through the triangle planes.  Exact fallback (determinants) within tol of any plane.
+template <bool G = false>
 __device__ __forceinline__ bool inside_fast(const PlaneElem* __restrict__ pl, const TriaElem* __restrict__ te, const double x[3],
                                             uint32_t& mask) {
   uint32_t neg = 0;
   bool ambiguous = false;
-  const double tol = pl->tol;
+  const double tol = G ? __ldg(&pl->tol) : pl->tol;
+  const uint32_t c2 = G ? __ldg(&pl->concave2) : pl->concave2;
 #pragma unroll
   for (int t = 0; t < 12; ++t) {
-    const double dist = fma(pl->n[t][0], x[0], fma(pl->n[t][1], x[1], fma(pl->n[t][2], x[2], -pl->d[t])));
+    double n0, n1, n2, d;
+    if (G) asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(n0), "=d"(n1), "=d"(n2), "=d"(d) : "l"(&pl->pl[t][0]));
+    else { n0 = pl->pl[t][0]; n1 = pl->pl[t][1]; n2 = pl->pl[t][2]; d = pl->pl[t][3]; }
+    const double dist = fma(n0, x[0], fma(n1, x[1], fma(n2, x[2], -d)));
     ambiguous |= fabs(dist) <= tol;
     if (dist < 0.) neg |= 1u << t;
   }
   if (ambiguous) {
-    const uint32_t r = inside_exact_cold(te, x[0], x[1], x[2]);
+    const uint32_t r = inside_exact_cold<G>(te, x[0], x[1], x[2]);
     mask = r & 0x7fffffffu;
     return (r >> 31) != 0;
   }
   mask = neg;
   const uint32_t lo = 0x555u;
   const uint32_t any = (neg | (neg >> 1)) & lo, both = (neg & (neg >> 1)) & lo;
-  uint32_t c2 = 0;
-  const uint32_t conc = te->concave;
-#pragma unroll
-  for (int s = 0; s < 6; ++s) c2 |= ((conc >> s) & 1u) << (2 * s);
   return ((any & ~c2) | (both & c2)) == 0;
 }
 

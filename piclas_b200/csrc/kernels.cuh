@@ -461,9 +461,12 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
 // (r1 profile of the first version, which looped per thread until done: every warp ran 2-3 rounds for 1.1 hops per particle,
 // 12 of 32 lanes active; a shared-memory re-queue with block barriers was slower still.)
 constexpr int LV_NT = 128;
+#ifndef LV_MINB
+#define LV_MINB 4
+#endif
 
 template <bool FAST>
-__global__ void __launch_bounds__(LV_NT) k_track_leavers(PartBuf pb, const double* __restrict__ xn0, const double* __restrict__ xn1,
+__global__ void __launch_bounds__(LV_NT, LV_MINB) k_track_leavers(PartBuf pb, const double* __restrict__ xn0, const double* __restrict__ xn1,
                                                          const double* __restrict__ xn2, const uint32_t* __restrict__ leaverIdx,
                                                          const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ planes,
                                                          const int32_t* __restrict__ elemRank, uint32_t* __restrict__ keys, int nElems,
@@ -521,7 +524,7 @@ __global__ void __launch_bounds__(LV_NT) k_track_leavers(PartBuf pb, const doubl
         while (cand) {
           const int b = __ffs(cand) - 1;
           cand &= cand - 1;
-          if (through_side_check_fast(te, lp, V, b >> 1, (b & 1) + 1)) {
+          if (through_side_check_fast<true>(te, lp, V, b >> 1, (b & 1) + 1)) {
             thr |= 1u << b;
             ++nThrough;
           }
@@ -549,9 +552,9 @@ __global__ void __launch_bounds__(LV_NT) k_track_leavers(PartBuf pb, const doubl
                                  (dE5 == ElemID && dS5 == gs && dT5 == t);
             if (treated) continue;
             double detM;
-            if (!through_side_lastpos_check(te, lp, s, t, detM)) continue;
+            if (!through_side_lastpos_check<true>(te, lp, s, t, detM)) continue;
             double d1, d2;
-            side_dets(te, x, s, d1, d2);
+            side_dets<true>(te, x, s, d1, d2);
             const double dS = (t == 1) ? d1 : d2;
             if (detM == 0 && dS == 0) continue;
             if (detM == 0 && minRatio == 0) {
@@ -577,7 +580,7 @@ __global__ void __launch_bounds__(LV_NT) k_track_leavers(PartBuf pb, const doubl
             if (kind == PGPU_BC_OPEN) status = TRK_REMOVED;
             else if (kind != PGPU_BC_PERIODIC) status = TRK_ERR_BC;
             else {
-              const double alpha = intersection_with_wall(te, lp, V, side, tri);
+              const double alpha = intersection_with_wall<true>(te, lp, V, side, tri);
               const int pvid = cst.bc_alpha[bc - 1];  // PeriodicBoundary, particle_boundary_condition.f90:224-284
               const int pv = (pvid < 0 ? -pvid : pvid) - 1;
 #pragma unroll
@@ -599,8 +602,8 @@ __global__ void __launch_bounds__(LV_NT) k_track_leavers(PartBuf pb, const doubl
             if (ElemID < 1) status = TRK_ERR_ELEM;
             else {
               // 2a) inside test in the new element
-              const bool inNew = FAST ? inside_fast(planes + (ElemID - 1), tria + (ElemID - 1), x, mask)
-                                      : inside_quad3d_mask(tria + (ElemID - 1), x, mask);
+              const bool inNew = FAST ? inside_fast<true>(planes + (ElemID - 1), tria + (ElemID - 1), x, mask)
+                                      : inside_quad3d_mask<true>(tria + (ElemID - 1), x, mask);
               if (inNew) status = TRK_OK;
               else if (++guard > 100000) status = TRK_ERR_LOOP;
             }

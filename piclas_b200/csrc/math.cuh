@@ -380,51 +380,38 @@ __device__ __forceinline__ void push_particle(double x[3], double v[3], const do
   }
 }
 
-// ---- particle_mesh_tools.f90:78-222 ParticleInsideQuad3D (regular sides) --------------------------------------------------------
-// det[s][t]: determinant of triangle t of local side s+1.  Returns InElementCheck.
-__device__ __forceinline__ bool inside_quad3d(const TriaElem* __restrict__ te, const double x[3], double det[6][2]) {
-  bool inElem = true;
-  const unsigned conc = te->concave;
-#pragma unroll
-  for (int s = 0; s < 6; ++s) {
-    double A[4][3];
-#pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      const double* c = te->corner[te->sideNode[s][n]];
-      A[n][0] = c[0] - x[0];
-      A[n][1] = c[1] - x[1];
-      A[n][2] = c[2] - x[2];
-    }
-    const double c0 = A[0][1] * A[2][2] - A[0][2] * A[2][1];
-    const double c1 = A[0][2] * A[2][0] - A[0][0] * A[2][2];
-    const double c2 = A[0][0] * A[2][1] - A[0][1] * A[2][0];
-    double d1 = (c0 * A[1][0] + c1 * A[1][1]) + c2 * A[1][2];
-    d1 = -d1;
-    const double d2 = (c0 * A[3][0] + c1 * A[3][1]) + c2 * A[3][2];
-    det[s][0] = d1;
-    det[s][1] = d2;
-    const bool neg = (d1 < 0) || (d2 < 0);
-    const bool pos = !(d1 < 0) || !(d2 < 0);
-    if ((conc >> s) & 1u) {
-      if (!pos) inElem = false;
-    } else {
-      if (neg) inElem = false;
-    }
+// ---- element-record access -------------------------------------------------------------------------------------------------------
+// The tria records are read either from a CTA's shared-memory copy (G = false) or, in the leaver walk, straight from global
+// memory with every lane on a different element (G = true).  There each 8-byte load is its own L1 wavefront (r1v6 profile: the
+// walk ran at 82 % of the LSU wavefront peak), so a corner (x, y, z, pad) is fetched with ONE 256-bit load and the four node
+// indices of a side with one 32-bit load.
+template <bool G>
+__device__ __forceinline__ void load_corner(const TriaElem* __restrict__ te, int n, double c[3]) {
+  if (G) {
+    double w;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c[0]), "=d"(c[1]), "=d"(c[2]), "=d"(w) : "l"(&te->corner[n][0]));
+  } else {
+    c[0] = te->corner[n][0]; c[1] = te->corner[n][1]; c[2] = te->corner[n][2];
   }
-  return inElem;
+}
+// ElemSideNodeID(1:4,side) packed: byte n = node n
+template <bool G>
+__device__ __forceinline__ uint32_t load_side_nodes(const TriaElem* __restrict__ te, int s) {
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(&te->sideNode[s][0]);
+  return G ? __ldg(q) : *q;
 }
 
 // ---- particle_intersection.f90:167-280 ParticleThroughSideCheck3DFast (regular side) -------------------------------------------
+template <bool G = false>
 __device__ __forceinline__ bool through_side_check_fast(const TriaElem* __restrict__ te, const double lp[3], const double V[3],
                                                         int s /*0-based local side*/, int tri /*1|2*/) {
   double Ax[3], Ay[3], Az[3];
-  {
-    const double* c = te->corner[te->sideNode[s][0]];
-    Ax[0] = c[0] - lp[0]; Ay[0] = c[1] - lp[1]; Az[0] = c[2] - lp[2];
-  }
+  const uint32_t sn = load_side_nodes<G>(te, s);
 #pragma unroll
-  for (int n = 1; n < 3; ++n) {
-    const double* c = te->corner[te->sideNode[s][n + tri - 1]];
+  for (int n = 0; n < 3; ++n) {
+    const int node = (n == 0) ? 0 : n + tri - 1;
+    double c[3];
+    load_corner<G>(te, (sn >> (8 * node)) & 0xffu, c);
     Ax[n] = c[0] - lp[0]; Ay[n] = c[1] - lp[1]; Az[n] = c[2] - lp[2];
   }
   const double Vx = V[0], Vy = V[1], Vz = V[2];
@@ -448,13 +435,16 @@ __device__ __forceinline__ bool through_side_check_fast(const TriaElem* __restri
 }
 
 // ---- particle_intersection.f90:430-512 ParticleThroughSideLastPosCheck (regular side) -------------------------------------------
+template <bool G = false>
 __device__ __forceinline__ bool through_side_lastpos_check(const TriaElem* __restrict__ te, const double lp[3], int s, int tri,
                                                            double& det) {
   double Ax[3], Ay[3], Az[3];
+  const uint32_t sn = load_side_nodes<G>(te, s);
 #pragma unroll
   for (int n = 0; n < 3; ++n) {
     const int node = (n == 0) ? 0 : n + tri - 1;
-    const double* c = te->corner[te->sideNode[s][node]];
+    double c[3];
+    load_corner<G>(te, (sn >> (8 * node)) & 0xffu, c);
     Ax[n] = c[0] - lp[0]; Ay[n] = c[1] - lp[1]; Az[n] = c[2] - lp[2];
   }
   det = ((Ay[0] * Az[1] - Az[0] * Ay[1]) * Ax[2] + (Az[0] * Ax[1] - Ax[0] * Az[1]) * Ay[2]) +
@@ -463,11 +453,14 @@ __device__ __forceinline__ bool through_side_lastpos_check(const TriaElem* __res
 }
 
 // ---- particle_intersection.f90:79-164 IntersectionWithWall: returns TrackInfo%alpha ------------------------------------------------
+template <bool G = false>
 __device__ __forceinline__ double intersection_with_wall(const TriaElem* __restrict__ te, const double lp[3], const double V[3],
                                                          int s, int tri) {
-  const double* n0 = te->corner[te->sideNode[s][0]];
-  const double* n1 = te->corner[te->sideNode[s][tri]];
-  const double* n2 = te->corner[te->sideNode[s][tri + 1]];
+  const uint32_t sn = load_side_nodes<G>(te, s);
+  double n0[3], n1[3], n2[3];
+  load_corner<G>(te, sn & 0xffu, n0);
+  load_corner<G>(te, (sn >> (8 * tri)) & 0xffu, n1);
+  load_corner<G>(te, (sn >> (8 * (tri + 1))) & 0xffu, n2);
   const double xN = n0[0], yN = n0[1], zN = n0[2];
   const double v1x = n1[0] - xN, v1y = n1[1] - yN, v1z = n1[2] - zN;
   const double v2x = n2[0] - xN, v2y = n2[1] - yN, v2z = n2[2] - zN;
@@ -488,11 +481,14 @@ __device__ __forceinline__ double intersection_with_wall(const TriaElem* __restr
 }
 
 // determinants of the two triangles of local side s (particle_mesh_tools.f90:187-199)
+template <bool G = false>
 __device__ __forceinline__ void side_dets(const TriaElem* __restrict__ te, const double x[3], int s, double& d1, double& d2) {
   double A[4][3];
+  const uint32_t sn = load_side_nodes<G>(te, s);
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
-    const double* c = te->corner[te->sideNode[s][n]];
+    double c[3];
+    load_corner<G>(te, (sn >> (8 * n)) & 0xffu, c);
     A[n][0] = c[0] - x[0];
     A[n][1] = c[1] - x[1];
     A[n][2] = c[2] - x[2];
@@ -507,6 +503,7 @@ __device__ __forceinline__ void side_dets(const TriaElem* __restrict__ te, const
 
 // ParticleInsideQuad3D (rolled over the six sides).  Returns InElementCheck; mask bit 2*s+t-1 is set when the
 // determinant of triangle t of local side s+1 is <= 0 (the triangles SingleParticleTriaTracking3D then examines).
+template <bool G = false>
 __device__ __forceinline__ bool inside_quad3d_mask(const TriaElem* __restrict__ te, const double x[3], uint32_t& mask) {
   bool inElem = true;
   const unsigned conc = te->concave;
@@ -514,7 +511,7 @@ __device__ __forceinline__ bool inside_quad3d_mask(const TriaElem* __restrict__ 
 #pragma unroll 1
   for (int s = 0; s < 6; ++s) {
     double d1, d2;
-    side_dets(te, x, s, d1, d2);
+    side_dets<G>(te, x, s, d1, d2);
     const bool neg = (d1 < 0) || (d2 < 0);
     const bool pos = !(d1 < 0) || !(d2 < 0);
     if ((conc >> s) & 1u) {
@@ -531,98 +528,3 @@ __device__ __forceinline__ bool inside_quad3d_mask(const TriaElem* __restrict__ 
 
 enum { TRK_OK = 0, TRK_LOST = 1, TRK_REMOVED = 2, TRK_ERR_BC = 3, TRK_ERR_ELEM = 4, TRK_ERR_LOOP = 5 };
 
-// ---- particle_triatracking.f90:137-484 SingleParticleTriaTracking3D, continued after the first (failed) inside test ----------
-// x: pushed position (may be shifted by periodic BCs), lp: LastPartPos.  elem: in = element whose inside test failed with
-// determinants det, out = new element.  tria: global TriaElem array (index = global element id - 1).
-__device__ __noinline__ int tria_track_walk(const TriaElem* __restrict__ tria, double x[3], double lp[3], int& elem,
-                                            double det[6][2]) {
-  int done[6][4];  // DoneLastElem(1:4,1:6) -> [slot][entry]
-#pragma unroll
-  for (int a = 0; a < 6; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) done[a][b] = 0;
-  int ElemID = elem;
-  const TriaElem* te = tria + (ElemID - 1);
-  for (int guard = 0; guard < 100000; ++guard) {
-    // 2b) find the crossed side
-    double V[3] = {x[0] - lp[0], x[1] - lp[1], x[2] - lp[2]};
-    double len = sqrt((V[0] * V[0] + V[1] * V[1]) + V[2] * V[2]);
-    if (fabs(len) > 0.) {
-      V[0] = V[0] / len; V[1] = V[1] / len; V[2] = V[2] / len;
-    }
-    int nThrough = 0;
-    int locS[6], triN[6];
-    int side = -1, tri = 0;
-    for (int s = 0; s < 6; ++s)
-      for (int t = 1; t <= 2; ++t)
-        if (det[s][t - 1] <= -0.0) {
-          if (through_side_check_fast(te, lp, V, s, t)) {
-            if (nThrough < 6) { locS[nThrough] = s; triN[nThrough] = t; }
-            ++nThrough;
-            side = s;
-          }
-        }
-    if (nThrough > 6) nThrough = 6;  // cannot happen for a hexahedron with consistent orientation (LocSidesTemp(1:6))
-    tri = (nThrough > 0) ? triN[0] : 0;
-    if (nThrough != 1) {
-      if (nThrough == 0) return TRK_LOST;
-      int second = 0;
-      double minRatio = 0;
-      for (int i2 = 0; i2 < nThrough; ++i2) {
-        bool doCheck = true;
-        const int gside = te->sideID[locS[i2]];
-        for (int is = 1; is < 6; ++is)
-          if (done[is][0] == ElemID && done[is][3] == gside && done[is][2] == triN[i2]) doCheck = false;
-        if (!doCheck) continue;
-        double detM;
-        if (!through_side_lastpos_check(te, lp, locS[i2], triN[i2], detM)) continue;
-        const double dS = det[locS[i2]][triN[i2] - 1];
-        if (detM == 0 && dS == 0) continue;
-        if (detM == 0 && minRatio == 0) {
-          ++second; side = locS[i2]; tri = triN[i2];
-        } else {
-          if (detM == 0) continue;
-          const double ratio = dS / detM;
-          if (ratio < minRatio) {
-            minRatio = ratio;
-            ++second; side = locS[i2]; tri = triN[i2];
-          }
-        }
-      }
-      if (second == 0) return TRK_LOST;
-    }
-    // 3) boundary interaction or step into the neighbour
-    const int gside = te->sideID[side];
-    const int bc = te->bcid[side];
-    const int oldElem = ElemID;
-    if (bc > 0) {
-      const int kind = cst.bc_kind[bc - 1];
-      if (kind == PGPU_BC_OPEN) return TRK_REMOVED;
-      if (kind != PGPU_BC_PERIODIC) return TRK_ERR_BC;
-      const double alpha = intersection_with_wall(te, lp, V, side, tri);
-      // PeriodicBoundary, particle_boundary_condition.f90:224-284
-      const int pvid = cst.bc_alpha[bc - 1];
-      const int pv = (pvid < 0 ? -pvid : pvid) - 1;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        lp[d] = lp[d] + V[d] * alpha;
-        lp[d] = lp[d] + copysign(cst.PeriodicVectors[pv][d], (double)pvid);
-        x[d] = lp[d] + (len - alpha) * V[d];
-      }
-      ElemID = te->nbElem[side];
-    } else {
-      ElemID = te->nbElem[side];
-    }
-    for (int a = 5; a >= 1; --a)
-      for (int b = 0; b < 4; ++b) done[a][b] = done[a - 1][b];
-    done[0][0] = oldElem; done[0][1] = side + 1; done[0][2] = tri; done[0][3] = gside;
-    if (ElemID < 1) return TRK_ERR_ELEM;
-    te = tria + (ElemID - 1);
-    // 2a) inside test in the new element
-    if (inside_quad3d(te, x, det)) {
-      elem = ElemID;
-      return TRK_OK;
-    }
-  }
-  return TRK_ERR_LOOP;
-}

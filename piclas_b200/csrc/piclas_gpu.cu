@@ -523,9 +523,10 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
           const double len = sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
           if (!(len > 0.)) return fail("piclas_gpu_init: element %d has a degenerate side triangle", e + 1);
           const int k = 2 * s + tr;
-          for (int d = 0; d < 3; ++d) pl.n[k][d] = -N[d] / len;
-          pl.d[k] = pl.n[k][0] * P1[0] + pl.n[k][1] * P1[1] + pl.n[k][2] * P1[2];
+          for (int d = 0; d < 3; ++d) pl.pl[k][d] = -N[d] / len;
+          pl.pl[k][3] = pl.pl[k][0] * P1[0] + pl.pl[k][1] * P1[1] + pl.pl[k][2] * P1[2];
         }
+      for (int s = 0; s < 6; ++s) pl.concave2 |= (uint32_t)((t.concave >> s) & 1u) << (2 * s);
       // affine test on the trilinear map X(i,j,k): all mixed differences vanish
       AffElem& a = affs[e];
       memset(&a, 0, sizeof(a));
