@@ -39,7 +39,10 @@ struct __align__(32) PlaneElem {
   double pl[12][4];  // index 2*s + (tri-1): (n_x, n_y, n_z, d), one aligned 32-byte unit per plane
   double tol;        // 1e-8 * element diameter: far above the rounding error of either formula
   uint32_t concave2; // bit 2*s set when ConcaveElemSide(s+1)
-  uint32_t pad[5];
+  uint32_t planar;   // 1: convex element whose six sides are planar (both triangles in one plane): exit-side shortcut allowed
+  uint32_t pad[4];
+  double dg[6][4];   // per side: plane through the triangle diagonal (node 1 -> node 3) normal to the side, positive towards
+                     // node 2, i.e. towards triangle 1; decides which triangle of a planar side a crossing point lies in
 };
 // AffElem: elements whose trilinear map is affine (parallelepipeds): xi = A (x - x0) - 1 solves the Newton problem exactly
 struct __align__(16) AffElem {

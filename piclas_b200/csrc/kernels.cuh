@@ -12,16 +12,24 @@
 //   k_track_leavers one thread per leaver: the element walk of SingleParticleTriaTracking3D on the global tables.
 // Loops that do not need unrolling are kept rolled so that each kernel's hot loop stays inside the instruction caches.
 #pragma once
+#include <type_traits>
 #include "math.cuh"
 #include "fastmath.cuh"
 
 constexpr int STEP_NT = 128;  // threads per CTA of the per-element kernels
 #ifndef KA_MINB
-#define KA_MINB 4   // min resident CTAs/SM of k_interp_push (register cap = 65536 / (128 * KA_MINB))
+#define KA_MINB 3   // min resident CTAs/SM of k_interp_push (register cap = 65536 / (128 * KA_MINB)); 3 -> 168 registers, no spills
 #endif
 #ifndef DEP_MINB
 #define DEP_MINB 4
 #endif
+#ifndef KA_WARPQ
+#define KA_WARPQ 0   // 1: leaver queues private to each warp (no block barriers between the phases of k_interp_push)
+#endif
+#ifndef KA_CHUNKF
+#define KA_CHUNKF 8
+#endif
+constexpr int KA_CHUNK = KA_CHUNKF * STEP_NT;   // particles per phase-1 sweep of k_interp_push (bounds the shared-memory leaver queue)
 
 __device__ __forceinline__ void stage_words(void* dst, const void* src, int nbytes) {
   // cooperative copy of a 16-byte aligned record into shared memory with 128-bit loads
@@ -320,6 +328,195 @@ __device__ __forceinline__ void evaluate_field_tile(const double xi[3], const do
   out[2] = o2;
 }
 
+// ---- one element crossing of SingleParticleTriaTracking3D (particle_triatracking.f90:220-470) ------------------------------------
+// DoneLastElem(1:4,1:6): the last six crossings (element, global side, triangle); entry 0 is the most recent one
+struct HopHist {
+  int e0, e1, e2, e3, e4, e5, s0, s1, s2, s3, s4, s5, t0, t1, t2, t3, t4, t5;
+  __device__ __forceinline__ void clear() { e0 = e1 = e2 = e3 = e4 = e5 = s0 = s1 = s2 = s3 = s4 = s5 = t0 = t1 = t2 = t3 = t4 = t5 = 0; }
+  __device__ __forceinline__ void push(int e, int s, int t) {
+    e5 = e4; s5 = s4; t5 = t4;
+    e4 = e3; s4 = s3; t4 = t3;
+    e3 = e2; s3 = s2; t3 = t2;
+    e2 = e1; s2 = s1; t2 = t1;
+    e1 = e0; s1 = s0; t1 = t0;
+    e0 = e; s0 = s; t0 = t;
+  }
+  __device__ __forceinline__ bool treated(int e, int s, int t) const {
+    return (e1 == e && s1 == s && t1 == t) || (e2 == e && s2 == s && t2 == t) || (e3 == e && s3 == s && t3 == t) ||
+           (e4 == e && s4 == s && t4 == t) || (e5 == e && s5 == s && t5 == t);
+  }
+};
+
+// The particle sits in element ElemID (record te) whose inside test failed with `mask` (triangles with det <= 0); x is the
+// pushed position, lp LastPartPos.  Finds the crossed side, applies the boundary condition or steps into the neighbour and
+// runs the inside test there.  Returns TRK_OK (localised in ElemID), -1 (another hop is needed from ElemID / mask), or the
+// removal / error status.  G: te and the records of the new element are read from global memory with one element per lane;
+// otherwise te is a shared-memory copy and planeOf(side) returns the staged planes of the neighbour behind local side `side`.
+template <bool G>
+__device__ __forceinline__ void load_plane4(const double* __restrict__ q, double& a, double& b, double& c, double& d) {
+  if (G) asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(q));
+  else { a = q[0]; b = q[1]; c = q[2]; d = q[3]; }
+}
+
+// Exit side of a convex element with planar sides from the side planes (restructured arithmetic).  Applies when the pushed
+// position is beyond exactly one side plane: the flight then leaves through that side, and the reference's through-side
+// tests single out the triangle the crossing point lies in.  Every decision is taken with a margin of PlaneElem::tol (start
+// point clearly inside, crossing point clearly inside the side polygon and clearly off the triangle diagonal); otherwise
+// false is returned and the determinant tests of ParticleThroughSideCheck3DFast decide.
+template <bool G>
+__device__ __forceinline__ bool exit_side_planar(const PlaneElem* __restrict__ pc, const double x[3], const double lp[3], uint32_t mask,
+                                                 int& side, int& tri) {
+  const uint32_t ns = (mask | (mask >> 1)) & 0x555u;   // bit 2s: side s has a triangle with det <= 0
+  if (__popc(ns) != 1) return false;
+  if ((G ? __ldg(&pc->planar) : pc->planar) == 0u) return false;
+  const int s = (__ffs(ns) - 1) >> 1;
+  const double tol = G ? __ldg(&pc->tol) : pc->tol;
+  double a, b, c, d;
+  load_plane4<G>(pc->pl[2 * s], a, b, c, d);
+  const double dl = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
+  const double dx = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));
+  if (!(dl > tol && dx < -tol)) return false;
+  const double alpha = dl / (dl - dx);   // crossing point = lp + alpha (x - lp)
+  bool ok = true;
+#pragma unroll
+  for (int o = 0; o < 6; ++o) {
+    load_plane4<G>(pc->pl[2 * o], a, b, c, d);
+    const double ol = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
+    const double ox = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));
+    const double oc = fma(alpha, ox - ol, ol);
+    if (o != s && !(oc > tol)) ok = false;
+  }
+  load_plane4<G>(pc->dg[s], a, b, c, d);
+  const double gl = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
+  const double gx = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));
+  const double gc = fma(alpha, gx - gl, gl);
+  if (!(fabs(gc) > tol)) ok = false;
+  side = s;
+  tri = gc > 0. ? 1 : 2;
+  return ok;
+}
+
+// MODE 0: determinant tests only; 1: exit-side shortcut only (returns HOP_NO_SHORTCUT when it does not apply); 2: shortcut, then
+// the determinant tests if it does not apply.
+constexpr int HOP_NO_SHORTCUT = -2;
+template <bool FAST, bool G, int MODE, class PlaneOf>
+__device__ __forceinline__ int tria_hop(const TriaElem* __restrict__ te, const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ plCur,
+                                        PlaneOf planeOf, double x[3], double lp[3], int& ElemID, uint32_t& mask, HopHist& h) {
+  int side = -1, tri = 0;
+  bool shortcut = false;
+  if (FAST && MODE != 0) shortcut = exit_side_planar<G>(plCur, x, lp, mask, side, tri);
+  if (MODE == 1 && !shortcut) return HOP_NO_SHORTCUT;
+  // unit vector and length of the flight (particle_triatracking.f90:171-173): needed by the determinant tests and the BCs
+  double V[3] = {x[0] - lp[0], x[1] - lp[1], x[2] - lp[2]};
+  double len = 0.;
+  bool haveV = false;
+  auto flight = [&]() {
+    if (haveV) return;
+    haveV = true;
+    len = sqrt((V[0] * V[0] + V[1] * V[1]) + V[2] * V[2]);
+    if (fabs(len) > 0.) {
+      V[0] = V[0] / len; V[1] = V[1] / len; V[2] = V[2] / len;
+    }
+  };
+  if (MODE != 1 && !shortcut) {
+  flight();
+  // 2b) crossed triangles among those with det <= 0
+  uint32_t thr = 0;
+  int nThrough = 0;
+  uint32_t cand = mask;
+#pragma unroll 1
+  while (cand) {
+    const int b = __ffs(cand) - 1;
+    cand &= cand - 1;
+    if (through_side_check_fast<G>(te, lp, V, b >> 1, (b & 1) + 1)) {
+      thr |= 1u << b;
+      ++nThrough;
+    }
+  }
+  if (nThrough == 0) return TRK_LOST;
+  if (nThrough == 1) {
+    const int b = __ffs(thr) - 1;
+    side = b >> 1;
+    tri = (b & 1) + 1;
+  } else {
+    // several candidate sides: the one crossed first has the largest |det(PartPos)/det(LastPartPos)| (:309-405)
+    int second = 0;
+    double minRatio = 0;
+    uint32_t c2 = thr;
+#pragma unroll 1
+    while (c2) {
+      const int b = __ffs(c2) - 1;
+      c2 &= c2 - 1;
+      const int s = b >> 1, t = (b & 1) + 1;
+      if (h.treated(ElemID, te->sideID[s], t)) continue;
+      double detM;
+      if (!through_side_lastpos_check<G>(te, lp, s, t, detM)) continue;
+      double d1, d2;
+      side_dets<G>(te, x, s, d1, d2);
+      const double dS = (t == 1) ? d1 : d2;
+      if (detM == 0 && dS == 0) continue;
+      if (detM == 0 && minRatio == 0) {
+        ++second; side = s; tri = t;
+      } else {
+        if (detM == 0) continue;
+        const double ratio = dS / detM;
+        if (ratio < minRatio) {
+          minRatio = ratio;
+          ++second; side = s; tri = t;
+        }
+      }
+    }
+    if (second == 0) return TRK_LOST;
+  }
+  }  // determinant tests
+  // 3) boundary interaction or step into the neighbour
+  const int gside = te->sideID[side];
+  const int bc = te->bcid[side];
+  const int oldElem = ElemID;
+  if (bc > 0) {
+    const int kind = cst.bc_kind[bc - 1];
+    if (kind == PGPU_BC_OPEN) return TRK_REMOVED;
+    if (kind != PGPU_BC_PERIODIC) return TRK_ERR_BC;
+    flight();
+    const double alpha = intersection_with_wall<G>(te, lp, V, side, tri);
+    const int pvid = cst.bc_alpha[bc - 1];  // PeriodicBoundary, particle_boundary_condition.f90:224-284
+    const int pv = (pvid < 0 ? -pvid : pvid) - 1;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lp[d] = lp[d] + V[d] * alpha;
+      lp[d] = lp[d] + copysign(cst.PeriodicVectors[pv][d], (double)pvid);
+      x[d] = lp[d] + (len - alpha) * V[d];
+    }
+  }
+  ElemID = te->nbElem[side];
+  h.push(oldElem, gside, tri);
+  if (ElemID < 1) return TRK_ERR_ELEM;
+  // 2a) inside test in the new element
+  const bool inNew = FAST ? inside_fast<G>(planeOf(side, ElemID), tria + (ElemID - 1), x, mask)
+                          : inside_quad3d_mask<G>(tria + (ElemID - 1), x, mask);
+  return inNew ? TRK_OK : -1;
+}
+
+// end of the walk of one particle: final position, element and sort key (emigrants: nElems + rank, removed: nElems + nRanks)
+__device__ __forceinline__ void tria_finish(const PartBuf& pb, int64_t p, int status, int ElemID, const double x[3],
+                                            const int32_t* __restrict__ elemRank, uint32_t* __restrict__ keys, int nElems, int offsetElem,
+                                            int* __restrict__ counters) {
+  uint32_t key;
+  int newElem = ElemID;
+  if (status == TRK_OK) {
+    const int rk = (cst.nRanks == 1) ? cst.myRank : elemRank[newElem - 1];
+    key = (rk == cst.myRank) ? (uint32_t)(newElem - 1 - offsetElem) : (uint32_t)(nElems + rk);
+  } else {
+    key = (uint32_t)(nElems + cst.nRanks);  // removed
+    newElem = 0;
+    if (status == TRK_LOST) atomicAdd(&counters[0], 1);
+    else if (status != TRK_REMOVED) atomicMax(&counters[1], status);
+  }
+  pb.f[p] = x[0]; pb.f[1 * pb.stride + p] = x[1]; pb.f[2 * pb.stride + p] = x[2];
+  pb.elem[p] = newElem;
+  keys[p] = key;
+}
+
 // ---- interpolate + push + own-element inside test --------------------------------------------------------------------------------
 // timedisc_TimeStepPoissonByBorisLeapfrog.f90:109-198 and the first iteration of SingleParticleTriaTracking3D
 // (particle_triatracking.f90:203-218) for the particles of one element per CTA iteration.
@@ -334,7 +531,9 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
                                                             const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ planes,
                                                             const AffElem* __restrict__ aff, const double* __restrict__ E,
                                                             const double* __restrict__ Elem_xGP, uint32_t* __restrict__ keys,
-                                                            uint32_t* __restrict__ leaverIdx, double dt, int xiValid,
+                                                            uint32_t* __restrict__ leaverIdx, uint32_t* __restrict__ leaverHistE,
+                                                            uint32_t* __restrict__ leaverHistS, const int32_t* __restrict__ elemRank,
+                                                            double dt, int xiValid,
                                                             int* __restrict__ counters /*[0]=lost,[1]=error,[2]=nLeavers*/) {
   constexpr int ND = NP * NP * NP;
   double* __restrict__ const PF = pb.f;
@@ -346,6 +545,25 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
   __shared__ AffElem sa;
   __shared__ __align__(16) double sE[ND * 3];
   __shared__ double sP[2][9][STEP_NT];   // x, v, xi of the current / next particle of every thread (cp.async staging)
+  constexpr bool QUEUE = FAST && !REF;
+  __shared__ PlaneElem spn[QUEUE ? 6 : 1];   // planes of the six face neighbours: first element crossing without global loads
+  // leaver queues, private to each warp (no block barriers between the phases): queue A grows from the front, B from the
+  // back; A entries may move to B.  Entry: (offset in the chunk) << 12 | det <= 0 mask of the 12 triangles
+#if KA_WARPQ
+  constexpr int NQ = STEP_NT / 32, QSTRIDE = 32;
+#define KA_QSYNC() __syncwarp()
+  const int qg = threadIdx.x >> 5, qid = threadIdx.x & 31;
+#else
+  constexpr int NQ = 1, QSTRIDE = STEP_NT;
+#define KA_QSYNC() __syncthreads()
+  const int qg = 0, qid = threadIdx.x;
+#endif
+  constexpr int QCAP = 2 * KA_CHUNK / NQ;
+  __shared__ uint32_t sQw[QUEUE ? NQ : 1][QUEUE ? QCAP : 1];
+  __shared__ int sQnw[NQ], sQnBw[NQ];
+  uint32_t* const sQ = sQw[QUEUE ? qg : 0];
+  int& sQn = sQnw[qg];
+  int& sQnB = sQnBw[qg];
   const int tid = threadIdx.x;
   for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
     const int64_t p0 = elemOff[e], p1 = elemOff[e + 1];
@@ -356,7 +574,15 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
       stage_words(&sg, geo + (gElem - 1), sizeof(GeoElem));
       if (FAST) stage_words(&sa, aff + (gElem - 1), sizeof(AffElem));
     }
-    if (FAST && !REF) stage_words(&sp, planes + (gElem - 1), sizeof(PlaneElem));
+    if (FAST && !REF) {
+      stage_words(&sp, planes + (gElem - 1), sizeof(PlaneElem));
+      constexpr int W = (int)(sizeof(PlaneElem) / 16);
+      for (int t = tid; t < 6 * W; t += STEP_NT) {
+        const int sd = t / W, w = t - sd * W;
+        const int nb = __ldg(&tria[gElem - 1].nbElem[sd]);
+        if (nb >= 1) reinterpret_cast<int4*>(&spn[sd])[w] = __ldg(reinterpret_cast<const int4*>(planes + (nb - 1)) + w);
+      }
+    }
     if (!REF) stage_words(&st, tria + (gElem - 1), sizeof(TriaElem));
     for (int t = threadIdx.x; t < ND * 3; t += STEP_NT) {
       const int c = t % 3, node = t / 3;
@@ -365,10 +591,19 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
     }
     __syncthreads();
     const bool useXi = REF || xiValid;
-    int64_t p = p0 + tid;
+    // the segment is worked off in chunks: phase 1 runs interpolation, push and the own-element inside test for every particle
+    // of the chunk and queues the leavers in shared memory; phase 2 does their first element crossing with dense warps on the
+    // staged records (restructured arithmetic only; otherwise the leavers go straight to k_track_leavers)
+    for (int64_t c0 = p0; c0 < p1; c0 += KA_CHUNK) {
+    const int64_t c1 = (c0 + KA_CHUNK < p1) ? c0 + KA_CHUNK : p1;
+    if (QUEUE) {
+      if (qid == 0) { sQn = 0; sQnB = 0; }
+      KA_QSYNC();
+    }
+    int64_t p = c0 + tid;
     int stage = 0;
     uint8_t meta = 0, metaNext = 0;
-    if (p < p1) {
+    if (p < c1) {
 #pragma unroll
       for (int a = 0; a < 6; ++a) cp_async8(&sP[0][a][tid], PF + a * PS_ + p);
       if (useXi) {
@@ -378,9 +613,9 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
       meta = pb.meta[p];
     }
     cp_async_commit();
-    for (; p < p1; p += STEP_NT, stage ^= 1, meta = metaNext) {
+    for (; p < c1; p += STEP_NT, stage ^= 1, meta = metaNext) {
       const int64_t pn = p + STEP_NT;
-      if (pn < p1) {   // next particle of this thread: copies overlap the arithmetic below
+      if (pn < c1) {   // next particle of this thread: copies overlap the arithmetic below
 #pragma unroll
         for (int a = 0; a < 6; ++a) cp_async8(&sP[stage ^ 1][a][tid], PF + a * PS_ + pn);
         if (useXi) {
@@ -443,15 +678,105 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
         keys[p] = (uint32_t)e;
       } else {
         xn0[p] = x[0]; xn1[p] = x[1]; xn2[p] = x[2];
-        keys[p] = mask;  // handed to k_track_leavers, which overwrites it with the final key
         const unsigned act = __activemask();   // warp-aggregated append: one atomic per warp, consecutive slots
+        const int ln = threadIdx.x & 31, leader = __ffs(act) - 1;
+        int slot0 = 0;
+        if (QUEUE) {
+          // queue A (front): beyond exactly one side plane of a planar-sided element -> exit-side shortcut; queue B (back): the rest
+          const bool isA = sp.planar != 0u && __popc((mask | (mask >> 1)) & 0x555u) == 1;
+          const unsigned balA = __ballot_sync(act, isA);
+          const unsigned grp = isA ? balA : (act & ~balA);
+          const int gl = __ffs(grp) - 1;
+          if (ln == gl) slot0 = atomicAdd(isA ? &sQn : &sQnB, __popc(grp));
+          slot0 = __shfl_sync(act, slot0, gl);
+          int slot = slot0 + __popc(grp & ((1u << ln) - 1u));
+          if (!isA) slot = QCAP - 1 - slot;
+          sQ[slot] = ((uint32_t)(p - c0) << 12) | mask;
+        } else {
+          keys[p] = mask;  // handed to k_track_leavers, which overwrites it with the final key
+          if (ln == leader) slot0 = atomicAdd(&counters[2], __popc(act));
+          slot0 = __shfl_sync(act, slot0, leader);
+          const int slot = slot0 + __popc(act & ((1u << ln) - 1u));
+          leaverIdx[slot] = (uint32_t)p;
+          leaverHistE[slot] = 0u;   // no crossing done yet
+          leaverHistS[slot] = 0u;
+        }
+      }
+    }
+    if (QUEUE) {
+      // phase 2: first element crossing of the chunk's leavers on the staged records, queue A then queue B
+      // pushed position and LastPartPos of a queued leaver come back through the (now idle) cp.async staging slots
+      auto fetch = [&](int stg, uint32_t qe) {
+        const int64_t q = c0 + (qe >> 12);
+        cp_async8(&sP[stg][0][tid], xn0 + q);
+        cp_async8(&sP[stg][1][tid], xn1 + q);
+        cp_async8(&sP[stg][2][tid], xn2 + q);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) cp_async8(&sP[stg][3 + a][tid], PF + a * PS_ + q);
+      };
+      auto crossing = [&](int64_t q, uint32_t mask, int stg, auto modeTag) -> bool {
+        constexpr int MODE = decltype(modeTag)::value;
+        double x[3] = {sP[stg][0][tid], sP[stg][1][tid], sP[stg][2][tid]};
+        double lp[3] = {sP[stg][3][tid], sP[stg][4][tid], sP[stg][5][tid]};   // LastPartPos
+        int ElemID = gElem;
+        HopHist h;
+        h.clear();
+        const int status = tria_hop<true, false, MODE>(&st, tria, &sp, [&](int sd, int) { return (const PlaneElem*)&spn[sd]; }, x, lp,
+                                                       ElemID, mask, h);
+        if (status == HOP_NO_SHORTCUT) return false;
+        if (status != -1) {
+          tria_finish(pb, q, status, ElemID, x, elemRank, keys, nElems, offsetElem, counters);
+          return true;
+        }
+        // not localised in the face neighbour: the walk continues in k_track_leavers from ElemID
+        PF[q] = lp[0]; PF[1 * PS_ + q] = lp[1]; PF[2 * PS_ + q] = lp[2];   // LastPartPos after a periodic shift
+        xn0[q] = x[0]; xn1[q] = x[1]; xn2[q] = x[2];
+        pb.elem[q] = ElemID;
+        keys[q] = mask;
+        const unsigned act = __activemask();
         const int ln = threadIdx.x & 31, leader = __ffs(act) - 1;
         int slot0 = 0;
         if (ln == leader) slot0 = atomicAdd(&counters[2], __popc(act));
         slot0 = __shfl_sync(act, slot0, leader);
-        leaverIdx[slot0 + __popc(act & ((1u << ln) - 1u))] = (uint32_t)p;
+        const int slot = slot0 + __popc(act & ((1u << ln) - 1u));
+        leaverIdx[slot] = (uint32_t)q;
+        leaverHistE[slot] = (uint32_t)h.e0;                       // DoneLastElem entry of the crossing done here
+        leaverHistS[slot] = (uint32_t)(h.s0 * 2 + (h.t0 == 2 ? 1 : 0));
+        return true;
+      };
+      KA_QSYNC();
+      const int nA = sQn;
+      {
+        int i = qid, stg = 0;
+        if (i < nA) fetch(0, sQ[i]);
+        cp_async_commit();
+        for (; i < nA; i += QSTRIDE, stg ^= 1) {
+          if (i + QSTRIDE < nA) fetch(stg ^ 1, sQ[i + QSTRIDE]);
+          cp_async_commit();
+          cp_async_wait_prev();
+          const uint32_t qe = sQ[i];
+          if (!crossing(c0 + (qe >> 12), qe & 0xfffu, stg, std::integral_constant<int, 1>()))   // margin not met: determinant tests
+            sQ[QCAP - 1 - atomicAdd(&sQnB, 1)] = qe;
+        }
       }
+      KA_QSYNC();
+      const int nB = sQnB;
+      if (qid == 0) { atomicAdd(&counters[4], nA); atomicAdd(&counters[5], nB); }   // diagnostics (PICLAS_GPU_DEBUG)
+      {
+        int i = qid, stg = 0;
+        if (i < nB) fetch(0, sQ[QCAP - 1 - i]);
+        cp_async_commit();
+        for (; i < nB; i += QSTRIDE, stg ^= 1) {
+          if (i + QSTRIDE < nB) fetch(stg ^ 1, sQ[QCAP - 1 - (i + QSTRIDE)]);
+          cp_async_commit();
+          cp_async_wait_prev();
+          const uint32_t qe = sQ[QCAP - 1 - i];
+          crossing(c0 + (qe >> 12), qe & 0xfffu, stg, std::integral_constant<int, 0>());
+        }
+      }
+      KA_QSYNC();
     }
+    }  // chunks
   }
 }
 
@@ -460,6 +785,8 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
 // triangles are visited through a bit mask so that the lanes of a warp run the same through-side test at the same time.
 // (r1 profile of the first version, which looped per thread until done: every warp ran 2-3 rounds for 1.1 hops per particle,
 // 12 of 32 lanes active; a shared-memory re-queue with block barriers was slower still.)
+// With the restructured arithmetic k_interp_push has already done the first crossing; the list then holds only the particles
+// that were not localised in a face neighbour (edge / corner crossings, multi-element flights).
 constexpr int LV_NT = 128;
 #ifndef LV_MINB
 #define LV_MINB 4
@@ -468,6 +795,7 @@ constexpr int LV_NT = 128;
 template <bool FAST>
 __global__ void __launch_bounds__(LV_NT, LV_MINB) k_track_leavers(PartBuf pb, const double* __restrict__ xn0, const double* __restrict__ xn1,
                                                          const double* __restrict__ xn2, const uint32_t* __restrict__ leaverIdx,
+                                                         const uint32_t* __restrict__ leaverHistE, const uint32_t* __restrict__ leaverHistS,
                                                          const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ planes,
                                                          const int32_t* __restrict__ elemRank, uint32_t* __restrict__ keys, int nElems,
                                                          int offsetElem, int* __restrict__ counters) {
@@ -479,9 +807,8 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_track_leavers(PartBuf pb, co
   int p = 0, ElemID = 0, guard = 0;
   uint32_t mask = 0;
   double x[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
-  int dE0 = 0, dE1 = 0, dE2 = 0, dE3 = 0, dE4 = 0, dE5 = 0;  // DoneLastElem(1:4,1:6); entry 0 is the most recent crossing
-  int dS0 = 0, dS1 = 0, dS2 = 0, dS3 = 0, dS4 = 0, dS5 = 0;
-  int dT0 = 0, dT1 = 0, dT2 = 0, dT3 = 0, dT4 = 0, dT5 = 0;
+  HopHist h;
+  h.clear();
   // persistent warps: a lane performs one element crossing ("hop") per round and fetches the next leaver as soon as its
   // particle is localised, so that lanes stay busy while a neighbour lane walks through several elements
   while (true) {
@@ -497,136 +824,24 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_track_leavers(PartBuf pb, co
           p = (int)leaverIdx[mine];
           x[0] = xn0[p]; x[1] = xn1[p]; x[2] = xn2[p];
           lp[0] = PF[p]; lp[1] = PF[1 * PS_ + p]; lp[2] = PF[2 * PS_ + p];  // LastPartPos
-          ElemID = pb.elem[p];                                               // LastGlobalElemID
-          mask = keys[p];                                                    // det <= 0 triangles of the start element
+          ElemID = pb.elem[p];                                               // element the walk has reached
+          mask = keys[p];                                                    // det <= 0 triangles of that element
           guard = 0;
-          dE0 = dE1 = dE2 = dE3 = dE4 = dE5 = 0;
-          dS0 = dS1 = dS2 = dS3 = dS4 = dS5 = 0;
-          dT0 = dT1 = dT2 = dT3 = dT4 = dT5 = 0;
+          h.clear();
+          const uint32_t he = leaverHistE[mine], hs = leaverHistS[mine];
+          h.e0 = (int)he; h.s0 = (int)(hs >> 1); h.t0 = he ? (int)(hs & 1u) + 1 : 0;
         }
       }
       if (__ballot_sync(0xffffffffu, active) == 0) break;
     }
-    {
-      int status = -1;  // -1: needs another hop
-      if (active) {
-        const TriaElem* te = tria + (ElemID - 1);
-        // 2b) crossed triangles among those with det <= 0
-        double V[3] = {x[0] - lp[0], x[1] - lp[1], x[2] - lp[2]};
-        const double len = sqrt((V[0] * V[0] + V[1] * V[1]) + V[2] * V[2]);
-        if (fabs(len) > 0.) {
-          V[0] = V[0] / len; V[1] = V[1] / len; V[2] = V[2] / len;
-        }
-        uint32_t thr = 0;
-        int nThrough = 0;
-        uint32_t cand = mask;
-#pragma unroll 1
-        while (cand) {
-          const int b = __ffs(cand) - 1;
-          cand &= cand - 1;
-          if (through_side_check_fast<true>(te, lp, V, b >> 1, (b & 1) + 1)) {
-            thr |= 1u << b;
-            ++nThrough;
-          }
-        }
-        int side = -1, tri = 0;
-        if (nThrough == 0) {
-          status = TRK_LOST;
-        } else if (nThrough == 1) {
-          const int b = __ffs(thr) - 1;
-          side = b >> 1;
-          tri = (b & 1) + 1;
-        } else {
-          // several candidate sides: the one crossed first has the largest |det(PartPos)/det(LastPartPos)| (:309-405)
-          int second = 0;
-          double minRatio = 0;
-          uint32_t c2 = thr;
-#pragma unroll 1
-          while (c2) {
-            const int b = __ffs(c2) - 1;
-            c2 &= c2 - 1;
-            const int s = b >> 1, t = (b & 1) + 1;
-            const int gs = te->sideID[s];
-            const bool treated = (dE1 == ElemID && dS1 == gs && dT1 == t) || (dE2 == ElemID && dS2 == gs && dT2 == t) ||
-                                 (dE3 == ElemID && dS3 == gs && dT3 == t) || (dE4 == ElemID && dS4 == gs && dT4 == t) ||
-                                 (dE5 == ElemID && dS5 == gs && dT5 == t);
-            if (treated) continue;
-            double detM;
-            if (!through_side_lastpos_check<true>(te, lp, s, t, detM)) continue;
-            double d1, d2;
-            side_dets<true>(te, x, s, d1, d2);
-            const double dS = (t == 1) ? d1 : d2;
-            if (detM == 0 && dS == 0) continue;
-            if (detM == 0 && minRatio == 0) {
-              ++second; side = s; tri = t;
-            } else {
-              if (detM == 0) continue;
-              const double ratio = dS / detM;
-              if (ratio < minRatio) {
-                minRatio = ratio;
-                ++second; side = s; tri = t;
-              }
-            }
-          }
-          if (second == 0) status = TRK_LOST;
-        }
-        if (status == -1) {
-          // 3) boundary interaction or step into the neighbour
-          const int gside = te->sideID[side];
-          const int bc = te->bcid[side];
-          const int oldElem = ElemID;
-          if (bc > 0) {
-            const int kind = cst.bc_kind[bc - 1];
-            if (kind == PGPU_BC_OPEN) status = TRK_REMOVED;
-            else if (kind != PGPU_BC_PERIODIC) status = TRK_ERR_BC;
-            else {
-              const double alpha = intersection_with_wall<true>(te, lp, V, side, tri);
-              const int pvid = cst.bc_alpha[bc - 1];  // PeriodicBoundary, particle_boundary_condition.f90:224-284
-              const int pv = (pvid < 0 ? -pvid : pvid) - 1;
-#pragma unroll
-              for (int d = 0; d < 3; ++d) {
-                lp[d] = lp[d] + V[d] * alpha;
-                lp[d] = lp[d] + copysign(cst.PeriodicVectors[pv][d], (double)pvid);
-                x[d] = lp[d] + (len - alpha) * V[d];
-              }
-            }
-          }
-          if (status == -1) {
-            ElemID = te->nbElem[side];
-            dE5 = dE4; dS5 = dS4; dT5 = dT4;
-            dE4 = dE3; dS4 = dS3; dT4 = dT3;
-            dE3 = dE2; dS3 = dS2; dT3 = dT2;
-            dE2 = dE1; dS2 = dS1; dT2 = dT1;
-            dE1 = dE0; dS1 = dS0; dT1 = dT0;
-            dE0 = oldElem; dS0 = gside; dT0 = tri;
-            if (ElemID < 1) status = TRK_ERR_ELEM;
-            else {
-              // 2a) inside test in the new element
-              const bool inNew = FAST ? inside_fast<true>(planes + (ElemID - 1), tria + (ElemID - 1), x, mask)
-                                      : inside_quad3d_mask<true>(tria + (ElemID - 1), x, mask);
-              if (inNew) status = TRK_OK;
-              else if (++guard > 100000) status = TRK_ERR_LOOP;
-            }
-          }
-        }
-        if (status != -1) {
-          uint32_t key;
-          int newElem = ElemID;
-          if (status == TRK_OK) {
-            const int rk = elemRank[newElem - 1];
-            key = (rk == cst.myRank) ? (uint32_t)(newElem - 1 - offsetElem) : (uint32_t)(nElems + rk);
-          } else {
-            key = (uint32_t)(nElems + cst.nRanks);  // removed
-            newElem = 0;
-            if (status == TRK_LOST) atomicAdd(&counters[0], 1);
-            else if (status != TRK_REMOVED) atomicMax(&counters[1], status);
-          }
-          PF[p] = x[0]; PF[1 * PS_ + p] = x[1]; PF[2 * PS_ + p] = x[2];
-          pb.elem[p] = newElem;
-          keys[p] = key;
-        }
+    if (active) {
+      int status = tria_hop<FAST, true, FAST ? 2 : 0>(tria + (ElemID - 1), tria, FAST ? planes + (ElemID - 1) : nullptr,
+                                         [&](int, int ne) { return planes + (ne - 1); }, x, lp, ElemID, mask, h);
+      if (status == -1 && ++guard > 100000) status = TRK_ERR_LOOP;
+      if (status != -1) {
+        tria_finish(pb, p, status, ElemID, x, elemRank, keys, nElems, offsetElem, counters);
+        active = false;
       }
-      if (active && status != -1) active = false;
     }
   }
 }

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -74,7 +75,7 @@ struct Ctx {
   int64_t* dElemOff = nullptr;        // [nElems + nRanks + 2]
   std::vector<int64_t> hTailOff;      // host copy of elemOff[nElems .. nElems+nRanks+1]
   uint32_t* dKeys = nullptr;          // [cap]
-  int* dCounters = nullptr;           // [4]
+  int* dCounters = nullptr;           // [8]: lost, error, leavers handed to the walk kernel, work counter, queue A, queue B, -, -
   SortWorkspace sortws;
   int keyBits = 1;
   // staging for AoS transfers
@@ -311,17 +312,18 @@ void launch_push_track_t(double dt) {
   const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
   const PartBuf& o = g.buf[g.cur ^ 1];
   uint32_t* leaverIdx = g.sortws.permB;  // idle until the sort that follows
+  uint32_t *leaverHistE = g.sortws.keysB, *leaverHistS = g.sortws.permA;
   if (g.ref) {
     k_interp_push<NP, FAST, true><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem,
                                                              g.dGeo, g.dTria, g.dPlanes, g.dAff, g.dE, g.dElemXGP, g.dKeys, leaverIdx,
-                                                             dt, 1, g.dCounters);
+                                                             leaverHistE, leaverHistS, g.dElemRank, dt, 1, g.dCounters);
     k_track_ref<<<g.nSMs * 8, 128, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.nPart, g.refT, g.dElemRank, g.dKeys, g.nElems,
                                               g.offsetElem, g.dCounters);
   } else {
     k_interp_push<NP, FAST, false><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], g.dElemOff, g.nElems, g.offsetElem,
                                                               g.dGeo, g.dTria, g.dPlanes, g.dAff, g.dE, g.dElemXGP, g.dKeys, leaverIdx,
-                                                              dt, g.xiValid ? 1 : 0, g.dCounters);
-    k_track_leavers<FAST><<<g.nSMs * 8, LV_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, g.dTria, g.dPlanes,
+                                                              leaverHistE, leaverHistS, g.dElemRank, dt, g.xiValid ? 1 : 0, g.dCounters);
+    k_track_leavers<FAST><<<g.nSMs * 8, LV_NT, 0, g.st>>>(g.buf[g.cur], o.x[0], o.x[1], o.x[2], leaverIdx, leaverHistE, leaverHistS, g.dTria, g.dPlanes,
                                                         g.dElemRank, g.dKeys, g.nElems, g.offsetElem, g.dCounters);
   }
   g.lastLaunches += 2;
@@ -527,6 +529,30 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
           pl.pl[k][3] = pl.pl[k][0] * P1[0] + pl.pl[k][1] * P1[1] + pl.pl[k][2] * P1[2];
         }
       for (int s = 0; s < 6; ++s) pl.concave2 |= (uint32_t)((t.concave >> s) & 1u) << (2 * s);
+      // planar sides (ConcaveElemSide is then irrelevant: both triangles lie in one plane) and all corners inside all
+      // side planes: convex polyhedron
+      bool planar = true;
+      for (int k = 0; k < 12; ++k)
+        for (int n = 0; n < 8; ++n)
+          if (pl.pl[k][0] * t.corner[n][0] + pl.pl[k][1] * t.corner[n][1] + pl.pl[k][2] * t.corner[n][2] - pl.pl[k][3] < -1e-12 * diam)
+            planar = false;
+      for (int s = 0; s < 6; ++s) {
+        const double *a = pl.pl[2 * s], *b = pl.pl[2 * s + 1];
+        if (fabs(a[0] - b[0]) > 1e-12 || fabs(a[1] - b[1]) > 1e-12 || fabs(a[2] - b[2]) > 1e-12 || fabs(a[3] - b[3]) > 1e-12 * diam)
+          planar = false;
+        // diagonal plane: normal = n_side x (P3 - P1), oriented towards node 2
+        const double* P1 = t.corner[t.sideNode[s][0]];
+        const double* P2 = t.corner[t.sideNode[s][1]];
+        const double* P3 = t.corner[t.sideNode[s][2]];
+        const double dgn[3] = {P3[0] - P1[0], P3[1] - P1[1], P3[2] - P1[2]};
+        double mm[3] = {a[1] * dgn[2] - a[2] * dgn[1], a[2] * dgn[0] - a[0] * dgn[2], a[0] * dgn[1] - a[1] * dgn[0]};
+        const double ml = sqrt(mm[0] * mm[0] + mm[1] * mm[1] + mm[2] * mm[2]);
+        if (!(ml > 0.)) { planar = false; continue; }
+        double sgn = (mm[0] * (P2[0] - P1[0]) + mm[1] * (P2[1] - P1[1]) + mm[2] * (P2[2] - P1[2])) >= 0. ? 1. : -1.;
+        for (int d = 0; d < 3; ++d) pl.dg[s][d] = sgn * mm[d] / ml;
+        pl.dg[s][3] = pl.dg[s][0] * P1[0] + pl.dg[s][1] * P1[1] + pl.dg[s][2] * P1[2];
+      }
+      pl.planar = planar ? 1u : 0u;
       // affine test on the trilinear map X(i,j,k): all mixed differences vanish
       AffElem& a = affs[e];
       memset(&a, 0, sizeof(a));
@@ -790,7 +816,7 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   CK(cudaMemset(g.dE, 0, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
   CK(cudaMalloc((void**)&g.dElemOff, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
   CK(cudaMemset(g.dElemOff, 0, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
-  CK(cudaMalloc((void**)&g.dCounters, 4 * sizeof(int)));
+  CK(cudaMalloc((void**)&g.dCounters, 8 * sizeof(int)));
   g.keyBits = 1;
   while ((1u << g.keyBits) < (uint32_t)(g.nElems + g.nRanks + 1)) ++g.keyBits;
 
@@ -1074,7 +1100,7 @@ int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
   CK(cudaSetDevice(g.device));
   if (g.prm.DoInterpolation && !g.haveField) return fail("piclas_gpu_push_track: no field set (piclas_gpu_set_field)");
   begin_timing();
-  CK(cudaMemsetAsync(g.dCounters, 0, 4 * sizeof(int), g.st));
+  CK(cudaMemsetAsync(g.dCounters, 0, 8 * sizeof(int), g.st));
   cudaEventRecord(g.evp[3], g.st);
   if (g.nPart > 0) {
     switch (g.NP) {
@@ -1089,9 +1115,13 @@ int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
     CK(cudaGetLastError());
   }
   cudaEventRecord(g.evp[4], g.st);
-  int hc[4] = {0, 0, 0, 0};
+  int hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
+  const int64_t nBefore = g.nPart;
   if (sort_and_permute(g.nPart)) return 1;   // also synchronises
+  if (getenv("PICLAS_GPU_DEBUG"))
+    fprintf(stderr, "[piclas_gpu] push_track: %lld particles, first crossing in-kernel: %d by side planes, %d by determinants; %d to the walk kernel\n",
+            (long long)nBefore, hc[4], hc[5], hc[2]);
   cudaEventRecord(g.evp[5], g.st);
   end_timing();
   {
