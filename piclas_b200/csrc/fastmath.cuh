@@ -127,14 +127,28 @@ __device__ __forceinline__ bool inside_fast(const PlaneElem* __restrict__ pl, co
   bool ambiguous = false;
   const double tol = G ? __ldg(&pl->tol) : pl->tol;
   const uint32_t c2 = G ? __ldg(&pl->concave2) : pl->concave2;
+  const uint32_t planar = G ? __ldg(&pl->planar) : pl->planar;
+  if (planar) {
+    // both triangles of a side lie in one plane (to 1e-12, far inside tol): one evaluation per side decides both signs
 #pragma unroll
-  for (int t = 0; t < 12; ++t) {
-    double n0, n1, n2, d;
-    if (G) asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(n0), "=d"(n1), "=d"(n2), "=d"(d) : "l"(&pl->pl[t][0]));
-    else { n0 = pl->pl[t][0]; n1 = pl->pl[t][1]; n2 = pl->pl[t][2]; d = pl->pl[t][3]; }
-    const double dist = fma(n0, x[0], fma(n1, x[1], fma(n2, x[2], -d)));
-    ambiguous |= fabs(dist) <= tol;
-    if (dist < 0.) neg |= 1u << t;
+    for (int s = 0; s < 6; ++s) {
+      double n0, n1, n2, d;
+      if (G) asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(n0), "=d"(n1), "=d"(n2), "=d"(d) : "l"(&pl->pl[2 * s][0]));
+      else { n0 = pl->pl[2 * s][0]; n1 = pl->pl[2 * s][1]; n2 = pl->pl[2 * s][2]; d = pl->pl[2 * s][3]; }
+      const double dist = fma(n0, x[0], fma(n1, x[1], fma(n2, x[2], -d)));
+      ambiguous |= fabs(dist) <= tol;
+      if (dist < 0.) neg |= 3u << (2 * s);
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < 12; ++t) {
+      double n0, n1, n2, d;
+      if (G) asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(n0), "=d"(n1), "=d"(n2), "=d"(d) : "l"(&pl->pl[t][0]));
+      else { n0 = pl->pl[t][0]; n1 = pl->pl[t][1]; n2 = pl->pl[t][2]; d = pl->pl[t][3]; }
+      const double dist = fma(n0, x[0], fma(n1, x[1], fma(n2, x[2], -d)));
+      ambiguous |= fabs(dist) <= tol;
+      if (dist < 0.) neg |= 1u << t;
+    }
   }
   if (ambiguous) {
     const uint32_t r = inside_exact_cold<G>(te, x[0], x[1], x[2]);
