@@ -1,4 +1,4 @@
-// sort.cu — stable LSD radix sort (8-bit digits), exclusive scan, permutation gathers, segment offsets.
+// sort.cu — stable LSD radix sort (8- or 10-bit digits), permutation gathers, segment offsets.
 #include "sort.cuh"
 
 namespace {
@@ -8,15 +8,10 @@ constexpr int SORT_IPT = 16;              // keys per thread
 constexpr int SORT_TILE = SORT_NT * SORT_IPT;
 constexpr int SORT_WARPS = SORT_NT / 32;
 
-__global__ void k_iota(uint32_t* p, size_t n) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i < n) p[i] = (uint32_t)i;
-}
-
-// per-tile digit histogram -> blockHist[digit * nBlocks + block]
+// per-tile digit histogram -> blockHist[block][digit] (block-major: every table access below is a coalesced row)
 template <int RADIX>
 __global__ void __launch_bounds__(SORT_NT) k_hist(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t mask,
-                                                  uint32_t* __restrict__ blockHist, uint32_t nBlocks) {
+                                                  uint32_t* __restrict__ blockHist) {
   __shared__ uint32_t h[RADIX];
   for (int i = threadIdx.x; i < RADIX; i += SORT_NT) h[i] = 0;
   __syncthreads();
@@ -27,142 +22,117 @@ __global__ void __launch_bounds__(SORT_NT) k_hist(const uint32_t* __restrict__ k
     if (i < n) atomicAdd(&h[(keys[i] >> shift) & mask], 1u);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < RADIX; i += SORT_NT) blockHist[(size_t)i * nBlocks + blockIdx.x] = h[i];
+  for (int i = threadIdx.x; i < RADIX; i += SORT_NT) blockHist[(size_t)blockIdx.x * RADIX + i] = h[i];
 }
 
-// stable scatter: rank of a key among equal digits = (#equal digits earlier in memory order)
+// Column scan of the table: entry (block b, digit d) becomes the first output index of the keys with digit d in tile b,
+//   sum_{d' < d} total[d'] + sum_{b' < b} hist[b'][d]     (stable: tiles in order within a digit)
+// in three sweeps over groups of COL_GB tiles; thread <-> digit, so every access is a coalesced row.
+constexpr int COL_GB = 256;
+
+template <int RADIX>
+__global__ void __launch_bounds__(256) k_col_reduce(const uint32_t* __restrict__ hist, uint32_t nBlocks, uint32_t* __restrict__ groupSum) {
+  const uint32_t b0 = blockIdx.x * COL_GB, b1 = min(b0 + COL_GB, nBlocks);
+  for (int d = threadIdx.x; d < RADIX; d += 256) {
+    uint32_t sum = 0;
+    for (uint32_t b = b0; b < b1; ++b) sum += hist[(size_t)b * RADIX + d];
+    groupSum[(size_t)blockIdx.x * RADIX + d] = sum;
+  }
+}
+
+template <int RADIX>
+__global__ void __launch_bounds__(RADIX) k_col_scan(uint32_t* __restrict__ groupSum, uint32_t nGroups) {
+  __shared__ uint32_t tot[RADIX];
+  const int d = threadIdx.x;
+  uint32_t run = 0;
+  for (uint32_t g = 0; g < nGroups; ++g) {
+    const uint32_t t = groupSum[(size_t)g * RADIX + d];
+    groupSum[(size_t)g * RADIX + d] = run;
+    run += t;
+  }
+  tot[d] = run;
+  __syncthreads();
+  // exclusive scan of the digit totals (Hillis-Steele in shared memory, RADIX <= 1024 threads)
+  for (int o = 1; o < RADIX; o <<= 1) {
+    const uint32_t t = (d >= o) ? tot[d - o] : 0u;
+    __syncthreads();
+    tot[d] += t;
+    __syncthreads();
+  }
+  const uint32_t base = tot[d] - run;
+  for (uint32_t g = 0; g < nGroups; ++g) groupSum[(size_t)g * RADIX + d] += base;
+}
+
+template <int RADIX>
+__global__ void __launch_bounds__(256) k_col_apply(uint32_t* __restrict__ hist, uint32_t nBlocks, const uint32_t* __restrict__ groupSum) {
+  const uint32_t b0 = blockIdx.x * COL_GB, b1 = min(b0 + COL_GB, nBlocks);
+  for (int d = threadIdx.x; d < RADIX; d += 256) {
+    uint32_t run = groupSum[(size_t)blockIdx.x * RADIX + d];
+    for (uint32_t b = b0; b < b1; ++b) {
+      const uint32_t t = hist[(size_t)b * RADIX + d];
+      hist[(size_t)b * RADIX + d] = run;
+      run += t;
+    }
+  }
+}
+
+// Stable scatter.  A warp owns SORT_IPT * 32 consecutive keys of the tile and keeps them in registers; ranks among equal
+// digits come from __match_any_sync, the per-warp digit counters live in shared memory and are private to the warp, so the
+// two sweeps over the keys need no block barrier (the first version synchronised the block four times per 256 keys and sat
+// at 53 % of the shared-memory pipe).  permIn == nullptr: identity (first pass).
 template <int RADIX>
 __global__ void __launch_bounds__(SORT_NT) k_scatter(const uint32_t* __restrict__ keysIn, const uint32_t* __restrict__ permIn,
                                                      uint32_t* __restrict__ keysOut, uint32_t* __restrict__ permOut, size_t n,
-                                                     int shift, uint32_t mask, const uint32_t* __restrict__ blockOff,
-                                                     uint32_t nBlocks) {
-  __shared__ uint32_t base[RADIX];                 // running output offset per digit
-  __shared__ uint32_t warpCnt[SORT_WARPS][RADIX];  // per round: count per warp and digit, then exclusive over warps (<= 32 KB)
+                                                     int shift, uint32_t mask, const uint32_t* __restrict__ blockOff) {
+  __shared__ uint32_t warpCnt[SORT_WARPS][RADIX];  // count per warp and digit, then running output offset
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < RADIX; i += SORT_NT) base[i] = blockOff[(size_t)i * nBlocks + blockIdx.x];
-  const size_t tile = (size_t)blockIdx.x * SORT_TILE;
+  for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_NT) (&warpCnt[0][0])[i] = 0;
+  __syncthreads();
+  const size_t wbase = (size_t)blockIdx.x * SORT_TILE + (size_t)warp * (SORT_IPT * 32);
+  uint32_t key[SORT_IPT], src[SORT_IPT], peers[SORT_IPT];
+#pragma unroll
   for (int r = 0; r < SORT_IPT; ++r) {
-    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_NT) (&warpCnt[0][0])[i] = 0;
-    __syncthreads();
-    const size_t i = tile + (size_t)r * SORT_NT + threadIdx.x;
-    const bool valid = i < n;
-    uint32_t key = 0, src = 0, digit = RADIX;  // invalid lanes get a digit outside the table
+    const size_t i = wbase + (size_t)r * 32 + lane;
+    key[r] = 0xffffffffu;
+    src[r] = 0;
+    if (i < n) {
+      key[r] = keysIn[i];
+      src[r] = permIn ? permIn[i] : (uint32_t)i;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < SORT_IPT; ++r) {
+    const bool valid = wbase + (size_t)r * 32 + lane < n;
+    const uint32_t digit = valid ? ((key[r] >> shift) & mask) : (uint32_t)RADIX;  // invalid lanes match among themselves only
+    peers[r] = __match_any_sync(0xffffffffu, digit);
+    if (valid && lane == __ffs(peers[r]) - 1) warpCnt[warp][digit] += __popc(peers[r]);
+    __syncwarp();
+  }
+  __syncthreads();
+  // exclusive prefix over the warps for each digit on top of the tile's first output index
+  for (int d = threadIdx.x; d < RADIX; d += SORT_NT) {
+    uint32_t run = blockOff[(size_t)blockIdx.x * RADIX + d];
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      const uint32_t c = warpCnt[w][d];
+      warpCnt[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < SORT_IPT; ++r) {
+    const bool valid = wbase + (size_t)r * 32 + lane < n;
+    const uint32_t digit = (key[r] >> shift) & mask;
     if (valid) {
-      key = keysIn[i];
-      src = permIn[i];
-      digit = (key >> shift) & mask;
+      const uint32_t dst = warpCnt[warp][digit] + __popc(peers[r] & ((1u << lane) - 1u));
+      keysOut[dst] = key[r];
+      permOut[dst] = src[r];
     }
-    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
-    const uint32_t rankInWarp = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rankInWarp == 0) warpCnt[warp][digit] = __popc(peers);
-    __syncthreads();
-    // exclusive prefix over warps for each digit, advancing the running base (one thread per digit)
-    for (int d = threadIdx.x; d < RADIX; d += SORT_NT) {
-      uint32_t run = base[d];
-#pragma unroll
-      for (int w = 0; w < SORT_WARPS; ++w) {
-        const uint32_t c = warpCnt[w][d];
-        warpCnt[w][d] = run;
-        run += c;
-      }
-      base[d] = run;
-    }
-    __syncthreads();
-    if (valid) {
-      const uint32_t dst = warpCnt[warp][digit] + rankInWarp;
-      keysOut[dst] = key;
-      permOut[dst] = src;
-    }
-    __syncthreads();
+    __syncwarp();
+    if (valid && lane == __ffs(peers[r]) - 1) warpCnt[warp][digit] += __popc(peers[r]);
+    __syncwarp();
   }
-}
-
-// ---- exclusive scan (3 phases, recursive on the block sums) --------------------------------------------------------
-constexpr int SCAN_NT = 256;
-constexpr int SCAN_IPT = 8;
-constexpr int SCAN_TILE = SCAN_NT * SCAN_IPT;
-
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
-  __shared__ uint32_t ws[SCAN_NT / 32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) ws[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t s = (lane < SCAN_NT / 32) ? ws[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
-    }
-    if (lane < SCAN_NT / 32) ws[lane] = s;
-  }
-  __syncthreads();
-  const uint32_t warpOff = warp ? ws[warp - 1] : 0;
-  *total = ws[SCAN_NT / 32 - 1];
-  __syncthreads();
-  return warpOff + inc - v;
-}
-
-__global__ void __launch_bounds__(SCAN_NT) k_scan_reduce(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ sums) {
-  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_IPT;
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_IPT; ++k)
-    if (base + k < n) s += in[base + k];
-  uint32_t tot;
-  block_exclusive_scan(s, &tot);
-  if (threadIdx.x == 0) sums[blockIdx.x] = tot;
-}
-
-__global__ void __launch_bounds__(SCAN_NT) k_scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n,
-                                                        const uint32_t* __restrict__ blockOff) {
-  const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_IPT;
-  uint32_t v[SCAN_IPT];
-  uint32_t s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_IPT; ++k) {
-    v[k] = (base + k < n) ? in[base + k] : 0;
-    s += v[k];
-  }
-  uint32_t tot;
-  uint32_t off = block_exclusive_scan(s, &tot) + (blockOff ? blockOff[blockIdx.x] : 0);
-#pragma unroll
-  for (int k = 0; k < SCAN_IPT; ++k) {
-    if (base + k < n) out[base + k] = off;
-    off += v[k];
-  }
-}
-
-cudaError_t exclusive_scan(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tmp1, uint32_t* tmp2, cudaStream_t st,
-                           int* nLaunches) {
-  const size_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-  if (nb <= 1) {
-    k_scan_apply<<<1, SCAN_NT, 0, st>>>(in, out, n, nullptr);
-    ++*nLaunches;
-    return cudaGetLastError();
-  }
-  k_scan_reduce<<<(unsigned)nb, SCAN_NT, 0, st>>>(in, n, tmp1);
-  ++*nLaunches;
-  // scan the block sums (in place in tmp1) using tmp2 for the next level
-  const size_t nb2 = (nb + SCAN_TILE - 1) / SCAN_TILE;
-  if (nb2 <= 1) {
-    k_scan_apply<<<1, SCAN_NT, 0, st>>>(tmp1, tmp1, nb, nullptr);
-    ++*nLaunches;
-  } else {
-    k_scan_reduce<<<(unsigned)nb2, SCAN_NT, 0, st>>>(tmp1, nb, tmp2);
-    k_scan_apply<<<1, SCAN_NT, 0, st>>>(tmp2, tmp2, nb2, nullptr);  // nb2 <= SCAN_TILE guaranteed by reserve()
-    k_scan_apply<<<(unsigned)nb2, SCAN_NT, 0, st>>>(tmp1, tmp1, nb, tmp2);
-    *nLaunches += 3;
-  }
-  k_scan_apply<<<(unsigned)nb, SCAN_NT, 0, st>>>(in, out, n, tmp1);
-  ++*nLaunches;
-  return cudaGetLastError();
 }
 
 template <typename T>
@@ -191,27 +161,21 @@ cudaError_t sort_workspace_reserve(SortWorkspace& ws, size_t n) {
   if (n == 0) n = 1;
   cudaError_t e;
   const size_t nBlocks = (n + SORT_TILE - 1) / SORT_TILE;
-  const size_t nh = nBlocks * 256;
-  const size_t t1 = (nh + SCAN_TILE - 1) / SCAN_TILE + 1;
-  const size_t t2 = (t1 + SCAN_TILE - 1) / SCAN_TILE + 1;
-  if (t2 > (size_t)SCAN_TILE) return cudaErrorInvalidValue;  // > 2^33 histogram entries: not reachable
+  const size_t nh = nBlocks * 1024;   // up to 10-bit digits
   if ((e = cudaMalloc(&ws.keysA, n * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&ws.keysB, n * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&ws.permA, n * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&ws.permB, n * 4)) != cudaSuccess) return e;
   if ((e = cudaMalloc(&ws.blockHist, nh * 4)) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&ws.scanTmp1, t1 * 4)) != cudaSuccess) return e;
-  if ((e = cudaMalloc(&ws.scanTmp2, t2 * 4)) != cudaSuccess) return e;
+  if ((e = cudaMalloc(&ws.groupSum, ((nBlocks + COL_GB - 1) / COL_GB) * 1024 * 4)) != cudaSuccess) return e;
   ws.capacity = n;
   ws.histCapacity = nh;
-  ws.tmp1Capacity = t1;
-  ws.tmp2Capacity = t2;
   return cudaSuccess;
 }
 
 void sort_workspace_free(SortWorkspace& ws) {
   cudaFree(ws.keysA); cudaFree(ws.keysB); cudaFree(ws.permA); cudaFree(ws.permB);
-  cudaFree(ws.blockHist); cudaFree(ws.scanTmp1); cudaFree(ws.scanTmp2);
+  cudaFree(ws.blockHist); cudaFree(ws.groupSum);
   ws = SortWorkspace();
 }
 
@@ -219,27 +183,27 @@ template <int RADIX_BITS>
 static cudaError_t sort_passes(SortWorkspace& ws, const uint32_t* keys, size_t n, int passes, cudaStream_t st, uint32_t** sortedKeys,
                                uint32_t** perm, int* nLaunches) {
   constexpr int RADIX = 1 << RADIX_BITS;
-  cudaError_t e;
   const uint32_t nBlocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+  const uint32_t nGroups = (nBlocks + COL_GB - 1) / COL_GB;
   const uint32_t* kin = keys;
-  uint32_t* pin = ws.permA;
+  const uint32_t* pin = nullptr;   // identity
   uint32_t* kout = ws.keysB;
   uint32_t* pout = ws.permB;
   for (int p = 0; p < passes; ++p) {
     const int shift = p * RADIX_BITS;
-    k_hist<RADIX><<<nBlocks, SORT_NT, 0, st>>>(kin, n, shift, RADIX - 1, ws.blockHist, nBlocks);
-    ++*nLaunches;
-    if ((e = exclusive_scan(ws.blockHist, ws.blockHist, (size_t)nBlocks * RADIX, ws.scanTmp1, ws.scanTmp2, st, nLaunches)) !=
-        cudaSuccess)
-      return e;
-    k_scatter<RADIX><<<nBlocks, SORT_NT, 0, st>>>(kin, pin, kout, pout, n, shift, RADIX - 1, ws.blockHist, nBlocks);
-    ++*nLaunches;
+    k_hist<RADIX><<<nBlocks, SORT_NT, 0, st>>>(kin, n, shift, RADIX - 1, ws.blockHist);
+    k_col_reduce<RADIX><<<nGroups, 256, 0, st>>>(ws.blockHist, nBlocks, ws.groupSum);
+    k_col_scan<RADIX><<<1, RADIX, 0, st>>>(ws.groupSum, nGroups);
+    k_col_apply<RADIX><<<nGroups, 256, 0, st>>>(ws.blockHist, nBlocks, ws.groupSum);
+    k_scatter<RADIX><<<nBlocks, SORT_NT, 0, st>>>(kin, pin, kout, pout, n, shift, RADIX - 1, ws.blockHist);
+    *nLaunches += 5;
     kin = kout;
-    uint32_t* tp = pin; pin = pout; pout = tp;
+    pin = pout;
+    pout = (pout == ws.permB) ? ws.permA : ws.permB;
     kout = (kout == ws.keysB) ? ws.keysA : ws.keysB;
   }
   *sortedKeys = const_cast<uint32_t*>(kin);
-  *perm = pin;
+  *perm = const_cast<uint32_t*>(pin);
   return cudaGetLastError();
 }
 
@@ -251,13 +215,13 @@ cudaError_t radix_sort_by_key(SortWorkspace& ws, const uint32_t* keys, size_t n,
     *perm = ws.permA;
     return cudaSuccess;
   }
-  k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws.permA, n);
-  ++*nLaunches;
-  // 8-bit digits: measured on B200 at 64^3 elements (19 key bits), 3 x 8-bit passes beat 2 x 10-bit passes (13.0 vs 17.2 ms
-  // for 2.5e8 particles) because the per-round shared-memory prefix grows with the digit count
+  // digit widths: as few passes as the key width allows with 8- or 10-bit digits (64^3 elements: 19 key bits -> 2 x 10)
   if (bits <= 8) return sort_passes<8>(ws, keys, n, 1, st, sortedKeys, perm, nLaunches);
+  if (bits <= 10) return sort_passes<10>(ws, keys, n, 1, st, sortedKeys, perm, nLaunches);
   if (bits <= 16) return sort_passes<8>(ws, keys, n, 2, st, sortedKeys, perm, nLaunches);
+  if (bits <= 20) return sort_passes<10>(ws, keys, n, 2, st, sortedKeys, perm, nLaunches);
   if (bits <= 24) return sort_passes<8>(ws, keys, n, 3, st, sortedKeys, perm, nLaunches);
+  if (bits <= 30) return sort_passes<10>(ws, keys, n, 3, st, sortedKeys, perm, nLaunches);
   return sort_passes<8>(ws, keys, n, 4, st, sortedKeys, perm, nLaunches);
 }
 

@@ -1,4 +1,4 @@
-// sort.cuh — hand-written stable LSD radix sort of particles by element key (sm_100a).
+// sort.cuh — hand-written stable LSD radix sort (8- or 10-bit digits) of particles by element key (sm_100a).
 //
 // The particle step keeps the particle SoA sorted by (local) element so that one CTA can stage its element's
 // field tile and geometry in shared memory and so that deposition is a deterministic segmented sum.  The sort
@@ -10,9 +10,9 @@
 struct SortWorkspace {
   uint32_t *keysA = nullptr, *keysB = nullptr;  // ping-pong keys
   uint32_t *permA = nullptr, *permB = nullptr;  // ping-pong source indices
-  uint32_t *blockHist = nullptr;                // [RADIX][nBlocks] digit-major
-  uint32_t *scanTmp1 = nullptr, *scanTmp2 = nullptr;
-  size_t capacity = 0, histCapacity = 0, tmp1Capacity = 0, tmp2Capacity = 0;
+  uint32_t *blockHist = nullptr;                // [nBlocks][RADIX] block-major
+  uint32_t *groupSum = nullptr;                 // [nGroups][RADIX] column-scan partials
+  size_t capacity = 0, histCapacity = 0;
 };
 
 // allocate for up to n keys
