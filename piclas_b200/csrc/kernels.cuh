@@ -135,7 +135,9 @@ template <bool FAST>
 __global__ void __launch_bounds__(STEP_NT, DEP_MINB) k_deposit_cvwm(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems,
                                                              int offsetElem, const GeoElem* __restrict__ geo,
                                                              const TriaElem* __restrict__ tria, const AffElem* __restrict__ aff,
-                                                             double* __restrict__ elemAcc) {
+                                                             double* __restrict__ elemAcc, int storeAffineXi) {
+  // storeAffineXi = 0: on affine elements the closed-form xi is not written back; k_interp_push recomputes it from the
+  // same position (9 multiply-adds instead of 24 B written here and read there)
   double* __restrict__ const PF = pb.f;
   double* __restrict__ const PXI = pb.xif;
   const int64_t PS_ = pb.stride;
@@ -179,9 +181,11 @@ __global__ void __launch_bounds__(STEP_NT, DEP_MINB) k_deposit_cvwm(PartBuf pb, 
         const double x[3] = {sP[stage][0][tid], sP[stage][1][tid], sP[stage][2][tid]};
         double xi[3];
         if (!affine_xi(&sa, x, xi)) { ++nGeneral; continue; }
-        PXI[p] = xi[0];
-        PXI[1 * PS_ + p] = xi[1];
-        PXI[2 * PS_ + p] = xi[2];
+        if (storeAffineXi) {
+          PXI[p] = xi[0];
+          PXI[1 * PS_ + p] = xi[1];
+          PXI[2 * PS_ + p] = xi[2];
+        }
         if (meta & META_XIFAIL) pb.meta[p] = meta & ~META_XIFAIL;
         const int spec = meta & META_SPEC_MASK;
         const double q = cst.ChargeIC[spec];
@@ -570,10 +574,8 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
     if (p1 <= p0) continue;
     const int gElem = offsetElem + e + 1;
     __syncthreads();
-    if (!xiValid && !REF) {
-      stage_words(&sg, geo + (gElem - 1), sizeof(GeoElem));
-      if (FAST) stage_words(&sa, aff + (gElem - 1), sizeof(AffElem));
-    }
+    if (!xiValid && !REF) stage_words(&sg, geo + (gElem - 1), sizeof(GeoElem));
+    if (FAST && !REF) stage_words(&sa, aff + (gElem - 1), sizeof(AffElem));
     if (FAST && !REF) {
       stage_words(&sp, planes + (gElem - 1), sizeof(PlaneElem));
       constexpr int W = (int)(sizeof(PlaneElem) / 16);
@@ -590,7 +592,9 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
       sE[(kj * 3 + c) * NP + i] = __ldg(E + (size_t)e * ND * 3 + t);
     }
     __syncthreads();
-    const bool useXi = REF || xiValid;
+    // restructured arithmetic on an affine element: xi is recomputed from x in closed form (k_deposit_cvwm did not store it)
+    const bool affineXi = FAST && !REF && sa.affine != 0.0;
+    const bool useXi = REF || (xiValid && !affineXi);
     // the segment is worked off in chunks: phase 1 runs interpolation, push and the own-element inside test for every particle
     // of the chunk and queues the leavers in shared memory; phase 2 does their first element crossing with dense warps on the
     // staged records (restructured arithmetic only; otherwise the leavers go straight to k_track_leavers)
@@ -640,8 +644,11 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
         if (REF) {
           xi[0] = sP[stage][6][tid]; xi[1] = sP[stage][7][tid]; xi[2] = sP[stage][8][tid];
           suc = true;
+        } else if (affineXi && affine_xi(&sa, x, xi)) {
+          suc = true;
         } else if (xiValid) {
-          xi[0] = sP[stage][6][tid]; xi[1] = sP[stage][7][tid]; xi[2] = sP[stage][8][tid];
+          if (useXi) { xi[0] = sP[stage][6][tid]; xi[1] = sP[stage][7][tid]; xi[2] = sP[stage][8][tid]; }
+          else { xi[0] = PXI[p]; xi[1] = PXI[1 * PS_ + p]; xi[2] = PXI[2 * PS_ + p]; }   // general path of the deposition
           suc = !(meta & META_XIFAIL);
         } else if (FAST) {
           suc = ref_position_fast(&sa, &sg, x, xi, false);

@@ -952,9 +952,10 @@ static int deposit_local() {
   cudaEventRecord(g.evp[0], g.st);
   if (grid > 0) {
     if (g.fast)
-      k_deposit_cvwm<true><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dAff, g.dElemAcc);
+      k_deposit_cvwm<true><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dAff, g.dElemAcc,
+                                                       g.ref ? 1 : 0);
     else
-      k_deposit_cvwm<false><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dAff, g.dElemAcc);
+      k_deposit_cvwm<false><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dAff, g.dElemAcc, 1);
     ++g.lastLaunches;
   }
   cudaEventRecord(g.evp[1], g.st);
