@@ -180,8 +180,11 @@ int piclas_gpu_download_particles(int64_t nmax, double *PartState, int32_t *Part
                                   int32_t *GlobalElemID, double *PartPosRef, int64_t *ids, int64_t *n_out);
 
 /* ---- particle exchange between ranks (replaces particle_mpi.f90:202-1024, message layout :158-183) ------
- * After push_track the emigrants of this rank are grouped by destination rank in a device buffer of
- * PartCommSize doubles per particle.  The transport (NCCL/MPI/P2P) is the caller's; see INTEGRATION.md. */
+ * nRanks > 1: push_track leaves the step open.  exchange_info extracts the emigrants of this rank, grouped by
+ * destination rank, into a device buffer of PartCommSize doubles per particle; the transport (NCCL/MPI/P2P) is
+ * the caller's; exchange_finish appends the immigrants and runs the one sort of the step
+ * (UpdateNextFreePosition).  Both calls are mandatory after every push_track on every rank, also when nothing
+ * migrates; deposit / download / the next push_track fail while the step is open. */
 int piclas_gpu_exchange_info(int32_t *partCommSize, int64_t *nSendPerRank /*[nRanks]*/, void **devSendBuf);
 int piclas_gpu_exchange_recv_buffer(int64_t nRecvTotal, void **devRecvBuf);
 int piclas_gpu_exchange_finish(int64_t nRecvTotal);

@@ -24,7 +24,7 @@ struct Ctx {
   int device = 0;
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t evp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase marks
+  cudaEvent_t evp[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // phase marks
   double phaseMs[4] = {0., 0., 0., 0.};  // deposit particle kernel, deposit node/DOF kernels, push+track kernel, sort+permute
   pgpu_params_t prm;
   int nGlobalElems = 0, nElems = 0, offsetElem = 0, N = 0, NP = 0, ND = 0, nNodes = 0, nRanks = 1, myRank = 0;
@@ -85,6 +85,12 @@ struct Ctx {
   int64_t stageCap = 0;
   // particle exchange between ranks (AoS messages as particle_mpi.f90:472-502)
   double *dCommSend = nullptr, *dCommRecv = nullptr;
+  // multi-rank: emigrants are extracted from the unsorted arrays after tracking, the one sort of the step follows the exchange
+  bool exchangePending = false;
+  int64_t nUnsorted = 0, nEmig = 0;
+  uint32_t *dTileCnt = nullptr, *dEmigIdx = nullptr, *dEmigKey = nullptr;
+  int64_t tileCntCap = 0, emigCap = 0;
+  int64_t* dEmigOff = nullptr;   // [nRanks+1]
   int64_t commSendCap = 0, commRecvCap = 0;
   int commSize = 8;
   // timing
@@ -191,8 +197,13 @@ int reserve_particles(int64_t need) {
   g.buf[1] = nb[1];
   g.cur = 0;
   g.cap = ncap;
-  cudaFree(g.dKeys);
-  CK(cudaMalloc((void**)&g.dKeys, ncap * 4));
+  {
+    uint32_t* nk = nullptr;
+    CK(cudaMalloc((void**)&nk, ncap * 4));
+    if (g.exchangePending && g.dKeys) CK(cudaMemcpy(nk, g.dKeys, g.nUnsorted * 4, cudaMemcpyDeviceToDevice));   // keys of the open step
+    cudaFree(g.dKeys);
+    g.dKeys = nk;
+  }
   CK(sort_workspace_reserve(g.sortws, (size_t)ncap));
   g.xiValid = false;
   return 0;
@@ -282,6 +293,111 @@ __global__ void k_unpack_immigrants(PartBuf pb, int64_t dst0, int64_t n, int cs,
   if (pb.id) pb.id[p] = (cs > o + 2) ? __double_as_longlong(b[o + 2]) : -1;
 }
 
+// ---- emigrant extraction (multi-rank): stable compaction of the particles whose key addresses another rank -----------------------
+constexpr int EM_NT = 256, EM_IPT = 8, EM_TILE = EM_NT * EM_IPT;
+
+__global__ void __launch_bounds__(EM_NT) k_emig_count(const uint32_t* __restrict__ keys, int64_t n, uint32_t lo, uint32_t hi,
+                                                      uint32_t* __restrict__ tileCnt) {
+  __shared__ uint32_t ws[EM_NT / 32];
+  const int64_t base = (int64_t)blockIdx.x * EM_TILE;
+  uint32_t c = 0;
+#pragma unroll
+  for (int r = 0; r < EM_IPT; ++r) {
+    const int64_t i = base + (int64_t)r * EM_NT + threadIdx.x;
+    if (i < n) {
+      const uint32_t k = keys[i];
+      c += (k >= lo && k < hi) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < EM_NT / 32; ++w) t += ws[w];
+    tileCnt[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the tile counts by one CTA; total -> *total
+__global__ void __launch_bounds__(1024) k_emig_scan(uint32_t* __restrict__ tileCnt, uint32_t nTiles, int64_t* __restrict__ total) {
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t b0 = 0; b0 < nTiles; b0 += 1024) {
+    const uint32_t i = b0 + threadIdx.x;
+    const uint32_t v = i < nTiles ? tileCnt[i] : 0u;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0u;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nTiles) tileCnt[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+// emigIdx / emigKey in particle order (thread t owns EM_IPT consecutive keys of the tile)
+__global__ void __launch_bounds__(EM_NT) k_emig_compact(const uint32_t* __restrict__ keys, int64_t n, uint32_t lo, uint32_t hi,
+                                                        const uint32_t* __restrict__ tileOff, uint32_t* __restrict__ emigIdx,
+                                                        uint32_t* __restrict__ emigKey) {
+  __shared__ uint32_t ws[EM_NT / 32];
+  const int64_t base = (int64_t)blockIdx.x * EM_TILE + (int64_t)threadIdx.x * EM_IPT;
+  uint32_t k[EM_IPT];
+  uint32_t c = 0;
+#pragma unroll
+  for (int r = 0; r < EM_IPT; ++r) {
+    k[r] = (base + r < n) ? keys[base + r] : 0xffffffffu;
+    c += (k[r] >= lo && k[r] < hi) ? 1u : 0u;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) ws[warp] = inc;
+  __syncthreads();
+  uint32_t off = tileOff[blockIdx.x] + inc - c;
+  for (int w = 0; w < warp; ++w) off += ws[w];
+#pragma unroll
+  for (int r = 0; r < EM_IPT; ++r)
+    if (k[r] >= lo && k[r] < hi) {
+      emigIdx[off] = (uint32_t)(base + r);
+      emigKey[off] = k[r] - lo;   // destination rank
+      ++off;
+    }
+}
+
+// message i <- particle emigIdx[perm[i]] (grouped by destination rank); the particle's key becomes "removed"
+__global__ void k_pack_emigrants_idx(PartBuf pb, const uint32_t* __restrict__ emigIdx, const uint32_t* __restrict__ perm, int64_t n, int cs,
+                                     int withRef, double* __restrict__ buf, uint32_t* __restrict__ keys, uint32_t removedKey) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = emigIdx[perm[i]];
+  double* b = buf + i * cs;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    b[d] = pb.x[d][p];
+    b[3 + d] = pb.v[d][p];
+  }
+  int o = 6;
+  if (withRef) { b[6] = pb.xi[0][p]; b[7] = pb.xi[1][p]; b[8] = pb.xi[2][p]; o = 9; }   // PartPosRef (RefMapping)
+  b[o] = (double)((pb.meta[p] & META_SPEC_MASK) + 1);
+  b[o + 1] = (double)pb.elem[p];
+  if (cs > o + 2) b[o + 2] = __longlong_as_double(pb.id ? pb.id[p] : -1);
+  keys[p] = removedKey;
+}
+
 // sort the first nIn particles of the current buffer by key (keys already in g.dKeys), gather into the other buffer
 int sort_and_permute(int64_t nIn) {
   uint32_t *sk = nullptr, *perm = nullptr;
@@ -367,6 +483,7 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dE); cudaFree(g.dElemOff); cudaFree(g.dKeys); cudaFree(g.dCounters);
   cudaFree(g.dStage); cudaFree(g.dStageI); cudaFree(g.dStageL);
   cudaFree(g.dCommSend); cudaFree(g.dCommRecv);
+  cudaFree(g.dTileCnt); cudaFree(g.dEmigIdx); cudaFree(g.dEmigKey); cudaFree(g.dEmigOff);
   cudaFree(g.dFibN); cudaFree(g.dFibOff); cudaFree(g.dFibElem); cudaFree(g.dElemToBGM); cudaFree(g.dCandOff); cudaFree(g.dCandSrc);
   cudaFree(g.dCandCase); cudaFree(g.dElemBary); cudaFree(g.dElemRadius); cudaFree(g.dElemsJ); cudaFree(g.dSFElemr2);
   for (int c = 0; c < 4; ++c) cudaFree(g.dSfFac[c]);
@@ -380,7 +497,7 @@ int piclas_gpu_finalize(void) {
   }
   cudaFree(g.dXi[0]);
   sort_workspace_free(g.sortws);
-  for (int i = 0; i < 6; ++i) if (g.evp[i]) cudaEventDestroy(g.evp[i]);
+  for (int i = 0; i < 10; ++i) if (g.evp[i]) cudaEventDestroy(g.evp[i]);
   if (g.ev0) cudaEventDestroy(g.ev0);
   if (g.ev1) cudaEventDestroy(g.ev1);
   if (g.st) cudaStreamDestroy(g.st);
@@ -445,7 +562,7 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   CK(cudaStreamCreate(&g.st));
   CK(cudaEventCreate(&g.ev0));
   CK(cudaEventCreate(&g.ev1));
-  for (int i = 0; i < 6; ++i) CK(cudaEventCreate(&g.evp[i]));
+  for (int i = 0; i < 10; ++i) CK(cudaEventCreate(&g.evp[i]));
   g.prm = *p;
   g.prm.ChargeIC = g.prm.MassIC = g.prm.MacroParticleFactor = nullptr;
   g.nGlobalElems = m->nGlobalElems;
@@ -864,6 +981,7 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
                                 const int32_t* ParticleInside, const int32_t* IsNewPart, const double* PartPosRef,
                                 const int64_t* ids, int32_t append) {
   if (!g.ready) return fail("piclas_gpu_upload_particles: not initialised");
+  if (g.exchangePending) return fail("piclas_gpu_upload_particles: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
   CK(cudaSetDevice(g.device));
   if (n < 0) return fail("piclas_gpu_upload_particles: n < 0");
   if (n > 0 && (!PartState || !PartSpecies || !GlobalElemID)) return fail("piclas_gpu_upload_particles: null array");
@@ -915,6 +1033,7 @@ int64_t piclas_gpu_num_particles(void) { return g.ready ? g.nPart : -1; }
 int piclas_gpu_download_particles(int64_t nmax, double* PartState, int32_t* PartSpecies, int32_t* GlobalElemID, double* PartPosRef,
                                   int64_t* ids, int64_t* n_out) {
   if (!g.ready) return fail("piclas_gpu_download_particles: not initialised");
+  if (g.exchangePending) return fail("piclas_gpu_download_particles: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
   CK(cudaSetDevice(g.device));
   const int64_t n = g.nPart;
   if (n_out) *n_out = n;
@@ -1041,6 +1160,7 @@ static int deposit_sf(double* PartSource) {
 int piclas_gpu_deposit(double* PartSource, double* NodeSource) {
   if (!g.ready) return fail("piclas_gpu_deposit: not initialised");
   if (!g.prm.DoDeposition) return fail("piclas_gpu_deposit: PIC-DoDeposition=F");
+  if (g.exchangePending) return fail("piclas_gpu_deposit: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
   CK(cudaSetDevice(g.device));
   begin_timing();
   if (g.sfActive) {
@@ -1100,6 +1220,7 @@ int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
   if (!g.ready) return fail("piclas_gpu_push_track: not initialised");
   CK(cudaSetDevice(g.device));
   if (g.prm.DoInterpolation && !g.haveField) return fail("piclas_gpu_push_track: no field set (piclas_gpu_set_field)");
+  if (g.exchangePending) return fail("piclas_gpu_push_track: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
   begin_timing();
   CK(cudaMemsetAsync(g.dCounters, 0, 8 * sizeof(int), g.st));
   cudaEventRecord(g.evp[3], g.st);
@@ -1119,7 +1240,14 @@ int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
   int hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
   const int64_t nBefore = g.nPart;
-  if (sort_and_permute(g.nPart)) return 1;   // also synchronises
+  if (g.nRanks > 1) {
+    // several ranks: the emigrants are taken out of the unsorted arrays (piclas_gpu_exchange_info) and the one sort of the
+    // step runs after the immigrants have arrived (piclas_gpu_exchange_finish)
+    CK(cudaStreamSynchronize(g.st));
+    g.exchangePending = true;
+    g.nUnsorted = g.nPart;
+    g.xiValid = false;
+  } else if (sort_and_permute(g.nPart)) return 1;   // also synchronises
   if (getenv("PICLAS_GPU_DEBUG"))
     fprintf(stderr, "[piclas_gpu] push_track: %lld particles, first crossing in-kernel: %d by side planes, %d by determinants; %d to the walk kernel\n",
             (long long)nBefore, hc[4], hc[5], hc[2]);
@@ -1143,20 +1271,59 @@ int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void*
   if (!g.ready) return fail("piclas_gpu_exchange_info: not initialised");
   CK(cudaSetDevice(g.device));
   if (partCommSize) *partCommSize = g.commSize;
-  for (int r = 0; r < g.nRanks; ++r) nSendPerRank[r] = g.hTailOff[r + 1] - g.hTailOff[r];
-  const int64_t nSend = g.nTotalSorted - g.nPart;
-  if (nSendPerRank[g.myRank] != 0) return fail("piclas_gpu_exchange_info: internal error, emigrants addressed to the own rank");
-  if (nSend > g.commSendCap) {
+  for (int r = 0; r < g.nRanks; ++r) nSendPerRank[r] = 0;
+  if (devSendBuf) *devSendBuf = g.dCommSend;
+  g.nEmig = 0;
+  if (!g.exchangePending) return 0;   // no step since the last exchange: nothing to send
+  cudaEventRecord(g.evp[6], g.st);
+  const int64_t n = g.nUnsorted;
+  const uint32_t lo = (uint32_t)g.nElems, hi = (uint32_t)(g.nElems + g.nRanks);
+  const int64_t nTiles = (n + EM_TILE - 1) / EM_TILE;
+  if (!g.dEmigOff) CK(cudaMalloc((void**)&g.dEmigOff, (size_t)(g.nRanks + 2) * sizeof(int64_t)));
+  if (nTiles > g.tileCntCap) {
+    cudaFree(g.dTileCnt);
+    g.tileCntCap = nTiles + nTiles / 4 + 16;
+    CK(cudaMalloc((void**)&g.dTileCnt, (size_t)g.tileCntCap * 4));
+  }
+  int64_t nEmig = 0;
+  if (n > 0) {
+    k_emig_count<<<(unsigned)nTiles, EM_NT, 0, g.st>>>(g.dKeys, n, lo, hi, g.dTileCnt);
+    k_emig_scan<<<1, 1024, 0, g.st>>>(g.dTileCnt, (uint32_t)nTiles, g.dEmigOff);
+    g.lastLaunches += 2;
+    CK(cudaMemcpyAsync(&nEmig, g.dEmigOff, sizeof(int64_t), cudaMemcpyDeviceToHost, g.st));
+    CK(cudaStreamSynchronize(g.st));
+  }
+  if (nEmig > g.emigCap) {
+    cudaFree(g.dEmigIdx); cudaFree(g.dEmigKey);
+    g.emigCap = nEmig + nEmig / 4 + 1024;
+    CK(cudaMalloc((void**)&g.dEmigIdx, (size_t)g.emigCap * 4));
+    CK(cudaMalloc((void**)&g.dEmigKey, (size_t)g.emigCap * 4));
+  }
+  if (nEmig > g.commSendCap) {
     cudaFree(g.dCommSend);
-    g.commSendCap = nSend + nSend / 4 + 1024;
+    g.commSendCap = nEmig + nEmig / 4 + 1024;
     CK(cudaMalloc((void**)&g.dCommSend, g.commSendCap * g.commSize * 8));
   }
-  if (nSend > 0) {
-    k_pack_emigrants<<<(unsigned)((nSend + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.nPart, nSend, g.commSize, g.ref ? 1 : 0, g.dCommSend);
+  if (nEmig > 0) {
+    k_emig_compact<<<(unsigned)nTiles, EM_NT, 0, g.st>>>(g.dKeys, n, lo, hi, g.dTileCnt, g.dEmigIdx, g.dEmigKey);
     ++g.lastLaunches;
+    int rankBits = 1;
+    while ((1 << rankBits) < g.nRanks) ++rankBits;
+    uint32_t *sk = nullptr, *perm = nullptr;
+    CK(radix_sort_by_key(g.sortws, g.dEmigKey, (size_t)nEmig, rankBits, g.st, &sk, &perm, &g.lastLaunches));   // stable: by rank, then particle order
+    CK(segment_offsets(sk, (size_t)nEmig, (uint32_t)g.nRanks, g.dEmigOff, g.st));
+    k_pack_emigrants_idx<<<(unsigned)((nEmig + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.dEmigIdx, perm, nEmig, g.commSize, g.ref ? 1 : 0,
+                                                                             g.dCommSend, g.dKeys, (uint32_t)(g.nElems + g.nRanks));
+    g.lastLaunches += 2;
     CK(cudaGetLastError());
+    std::vector<int64_t> off(g.nRanks + 1, 0);
+    CK(cudaMemcpyAsync(off.data(), g.dEmigOff, (size_t)(g.nRanks + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, g.st));
+    CK(cudaStreamSynchronize(g.st));
+    for (int r = 0; r < g.nRanks; ++r) nSendPerRank[r] = off[r + 1] - off[r];
+    if (nSendPerRank[g.myRank] != 0) return fail("piclas_gpu_exchange_info: internal error, emigrants addressed to the own rank");
   }
-  CK(cudaStreamSynchronize(g.st));
+  g.nEmig = nEmig;
+  cudaEventRecord(g.evp[7], g.st);
   if (devSendBuf) *devSendBuf = g.dCommSend;
   return 0;
 }
@@ -1176,23 +1343,33 @@ int piclas_gpu_exchange_recv_buffer(int64_t nRecvTotal, void** devRecvBuf) {
 int piclas_gpu_exchange_finish(int64_t nRecvTotal) {
   if (!g.ready) return fail("piclas_gpu_exchange_finish: not initialised");
   CK(cudaSetDevice(g.device));
-  const int64_t nEmig = g.nTotalSorted - g.nPart;
-  if (nRecvTotal == 0) {  // nothing arrives: the emigrants behind nPart are simply dropped
-    g.nTotalSorted = g.nPart;
-    for (int r = 0; r <= g.nRanks; ++r) g.hTailOff[r] = g.nPart;
+  if (!g.exchangePending) {
+    if (nRecvTotal != 0) return fail("piclas_gpu_exchange_finish: particles arrive but no step is open on this rank");
     return 0;
   }
-  if (nRecvTotal > g.commRecvCap) return fail("piclas_gpu_exchange_finish: receive buffer too small");
-  if (g.nPart + nRecvTotal >= (int64_t)0x7fffffff) return fail("piclas_gpu_exchange_finish: more than 2^31-1 particles on one GPU");
-  if (reserve_particles(g.nPart + nRecvTotal)) return 1;
-  (void)nEmig;
-  k_unpack_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.nPart, nRecvTotal, g.commSize, g.ref ? 1 : 0, g.dCommRecv);
-  const int64_t nIn = g.nPart + nRecvTotal;
-  k_keys_from_elem<<<(unsigned)((nIn + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur].elem, g.dElemRank, g.dKeys, nIn, g.nElems,
-                                                                    g.offsetElem, g.myRank, g.nRanks);
-  g.lastLaunches += 2;
-  CK(cudaGetLastError());
-  if (sort_and_permute(nIn)) return 1;
+  if (nRecvTotal > 0 && nRecvTotal > g.commRecvCap) return fail("piclas_gpu_exchange_finish: receive buffer too small");
+  const int64_t nIn0 = g.nUnsorted, nIn = nIn0 + nRecvTotal;
+  if (nIn >= (int64_t)0x7fffffff) return fail("piclas_gpu_exchange_finish: more than 2^31-1 particles on one GPU");
+  if (reserve_particles(nIn)) return 1;
+  cudaEventRecord(g.evp[8], g.st);
+  if (nRecvTotal > 0) {
+    // immigrants behind the particles of the open step; emigrants and removed particles carry the "removed" key
+    k_unpack_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], nIn0, nRecvTotal, g.commSize, g.ref ? 1 : 0, g.dCommRecv);
+    k_keys_from_elem<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur].elem + nIn0, g.dElemRank, g.dKeys + nIn0, nRecvTotal,
+                                                                             g.nElems, g.offsetElem, g.myRank, g.nRanks);
+    g.lastLaunches += 2;
+    CK(cudaGetLastError());
+  }
+  g.exchangePending = false;
+  if (sort_and_permute(nIn)) return 1;   // the one sort of the step; also synchronises
+  cudaEventRecord(g.evp[9], g.st);
+  cudaEventSynchronize(g.evp[9]);
+  {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, g.evp[6], g.evp[7]);   // emigrant extraction + pack
+    cudaEventElapsedTime(&b, g.evp[8], g.evp[9]);   // unpack + sort + permute
+    g.phaseMs[3] = a + b;
+  }
   if (g.nTotalSorted != g.nPart) return fail("piclas_gpu_exchange_finish: received particles that belong to another rank");
   return 0;
 }

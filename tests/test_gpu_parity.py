@@ -176,3 +176,33 @@ def test_upload_append_and_empty():
         assert np.array_equal(d["ids"], keep)
         assert np.array_equal(d["PartState"], PS[keep])
         assert np.array_equal(d["GlobalElemID"], elem[keep])
+
+
+def test_degenerate_flights(arith):
+    """Particles that start on faces / edges / corners of their element and flights that pass exactly through edges and
+    corners or along faces: the cases in which the plane-based shortcuts of the restructured arithmetic must hand over to the
+    determinant tests of ParticleInsideQuad3D / ParticleThroughSideCheck3DFast.  No field: straight flights, ownership exact."""
+    ne = 4
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (ne, ne, ne), 1)
+    prm = cases.electron_params(arithmetic=arith, DoInterpolation=0, DoDeposition=0)
+    h = 1.0 / ne
+    dt = 1.0
+    rng = np.random.default_rng(5)
+    pts, vel = [], []
+    centres = (np.stack(np.meshgrid(*[np.arange(ne)] * 3, indexing="ij"), -1).reshape(-1, 3) + 0.5) * h
+    for c in centres:
+        for d in [(1, 0, 0), (1, 1, 0), (1, 1, 1), (-1, 1, 0), (-1, -1, -1), (0, 1, -1), (2, 1, 0), (1, 2, 3)]:
+            pts.append(c)                       # centre -> centre of face / edge / corner neighbour: through face centres,
+            vel.append(np.array(d) * h)         # edge midpoints and corners exactly
+        for d in [(1, 0, 0), (0, -1, 0), (1, 1, 0)]:
+            pts.append(c + np.array([0.5, 0.0, 0.0]) * h * 0.999999999)   # a hair inside a face, flight along / through it
+            vel.append(np.array(d) * h * 0.7)
+        pts.append(c + rng.uniform(-0.5, 0.5, 3) * h * np.array([1, 1, 0]))   # in the mid plane, moving within it
+        vel.append(np.array([0.3, -0.6, 0.0]) * h)
+    X = np.array(pts)
+    V = np.array(vel) / dt
+    PS = np.ascontiguousarray(np.concatenate([X, V], axis=1))
+    spec = np.ones(len(PS), dtype=np.int32)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    E = np.zeros(mesh.Elem_xGP.shape)
+    run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=3, check_deposit=False)
