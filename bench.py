@@ -139,6 +139,18 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(n_particles):
+    """DRAM bytes of the dominant phase per launch: dram__bytes_read+write per particle from the committed `ncu --set full`
+    capture (profiles/r1_traffic.json, taken at the same particles per element) times the particles of this launch."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_particle_interp_push_track"]) * n_particles, t["source"]
+    except Exception:
+        return None, "no ncu capture committed"
+
+
 def cpu_baseline(args, N, threads=None):
     """Oracle (restated CPU path, -O3) on a bounded sample: same particles/element as the GPU workload."""
     from oracle_lib import Oracle
@@ -270,8 +282,9 @@ def run_b200(args):
     peak, peak_src = hbm_peak()
     t_push = phases[2] * 1e-3
     achieved = ALG_BYTES_PER_PARTICLE_STEP * n_total / t_push / 1e9 if t_push > 0 else 0.0
+    traffic, traffic_src = measured_traffic(n_total)
     roofline = {"bound": "hbm", "kernel": "k_interp_push + k_track_leavers (interpolate+push+track phase)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_launch": ALG_BYTES_PER_PARTICLE_STEP * n_total, "ms_per_launch": phases[2],
                 "step_frac": (ALG_BYTES_PER_PARTICLE_STEP * n_total * args.steps / wall / 1e9) / peak,
                 "phase_ms": {"deposit_particles": phases[0], "deposit_nodes_dofs": phases[1], "interp_push_track": phases[2],

@@ -16,10 +16,15 @@ __global__ void __launch_bounds__(SORT_NT) k_hist(const uint32_t* __restrict__ k
   for (int i = threadIdx.x; i < RADIX; i += SORT_NT) h[i] = 0;
   __syncthreads();
   const size_t base = (size_t)blockIdx.x * SORT_TILE;
+  const int lane = threadIdx.x & 31;
 #pragma unroll 4
   for (int r = 0; r < SORT_IPT; ++r) {
     const size_t i = base + (size_t)r * SORT_NT + threadIdx.x;
-    if (i < n) atomicAdd(&h[(keys[i] >> shift) & mask], 1u);
+    // the particles arrive almost sorted by element: neighbouring keys share the digit, so one atomic per group of equal
+    // digits in the warp instead of 32 serialised atomics on one shared-memory word
+    const uint32_t digit = (i < n) ? ((keys[i] >> shift) & mask) : (uint32_t)RADIX;
+    const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    if (i < n && lane == __ffs(peers) - 1) atomicAdd(&h[digit], (uint32_t)__popc(peers));
   }
   __syncthreads();
   for (int i = threadIdx.x; i < RADIX; i += SORT_NT) blockHist[(size_t)blockIdx.x * RADIX + i] = h[i];

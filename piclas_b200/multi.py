@@ -248,7 +248,8 @@ def run_bench_multi(args, rank, world, local):
                 "gpu_launches": int(cnt[2].item()), "particles_end": int(cnt[0].item()),
                 "migrated_per_step": int(cnt[1].item()) // max(args.steps, 1),
                 "roofline": {"bound": "hbm", "kernel": "k_interp_push + k_track_leavers (per GPU, slowest rank)",
-                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": B.measured_traffic(per_gpu)[0],
+                             "traffic_source": B.measured_traffic(per_gpu)[1],
                              "peak_source": peak_src,
                              "step_frac": (B.ALG_BYTES_PER_PARTICLE_STEP * per_gpu * args.steps / wall / 1e9) / peak,
                              "phase_ms": {"deposit_particles": ph[0], "deposit_nodes_dofs": ph[1],

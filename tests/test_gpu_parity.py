@@ -206,3 +206,16 @@ def test_degenerate_flights(arith):
     elem = hm.cartesian_locate(mesh, PS[:, :3])
     E = np.zeros(mesh.Elem_xGP.shape)
     run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=3, check_deposit=False)
+
+
+@pytest.mark.parametrize("shape", [(12, 12, 12), (41, 40, 40)], ids=["11-bit-keys", "17-bit-keys"])
+def test_sort_key_widths(shape):
+    """Element counts that take the two-pass paths of the radix sort (2 x 8-bit and 2 x 10-bit digits); the small meshes of
+    the other tests sort in one pass.  Ownership and order-dependent deposition sums must still match the oracle."""
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], shape, 1)
+    prm = cases.electron_params(arithmetic=1)
+    dt = 1e-9
+    PS, spec = cases.uniform_plasma(mesh, 150000, seed=3, vth_cells=0.3, dt=dt)
+    E = cases.smooth_field(mesh, amp=1.0e-3)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=2)
