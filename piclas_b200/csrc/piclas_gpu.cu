@@ -398,13 +398,22 @@ __global__ void k_pack_emigrants_idx(PartBuf pb, const uint32_t* __restrict__ em
   keys[p] = removedKey;
 }
 
+// PEM%GlobalElemID of the sorted particles follows from their segment: cheaper to write than to gather (a gathered mover costs a
+// 32-byte sector for 4 bytes)
+__global__ void k_fill_elem(const int64_t* __restrict__ elemOff, int nElems, int offsetElem, int32_t* __restrict__ elem) {
+  for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
+    const int64_t p0 = elemOff[e], p1 = elemOff[e + 1];
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) elem[p] = offsetElem + e + 1;
+  }
+}
+
 // sort the first nIn particles of the current buffer by key (keys already in g.dKeys), gather into the other buffer
 int sort_and_permute(int64_t nIn) {
   uint32_t *sk = nullptr, *perm = nullptr;
   CK(radix_sort_by_key(g.sortws, g.dKeys, (size_t)nIn, g.keyBits, g.st, &sk, &perm, &g.lastLaunches));
   const PartBuf& a = g.buf[g.cur];
   PartBuf& b = g.buf[g.cur ^ 1];
-  CK(gather_particles(a.x, a.v, a.elem, a.meta, g.carryIDs ? a.id : nullptr, b.x, b.v, b.elem, b.meta, b.id, perm, (size_t)nIn, g.st));
+  CK(gather_particles(a.x, a.v, nullptr, a.meta, g.carryIDs ? a.id : nullptr, b.x, b.v, b.elem, b.meta, b.id, perm, (size_t)nIn, g.st));
   ++g.lastLaunches;
   if (g.ref) {
     for (int d = 0; d < 3; ++d) CK(gather_f64(a.xi[d], b.xi[d], perm, (size_t)nIn, g.st));
@@ -412,7 +421,8 @@ int sort_and_permute(int64_t nIn) {
   }
   const uint32_t nKeys = (uint32_t)(g.nElems + g.nRanks + 1);
   CK(segment_offsets(sk, (size_t)nIn, nKeys, g.dElemOff, g.st));
-  ++g.lastLaunches;
+  if (g.nElems > 0) k_fill_elem<<<g.nElems < g.nSMs * 16 ? g.nElems : g.nSMs * 16, 128, 0, g.st>>>(g.dElemOff, g.nElems, g.offsetElem, b.elem);
+  g.lastLaunches += 2;
   g.hTailOff.assign(g.nRanks + 2, 0);
   CK(cudaMemcpyAsync(g.hTailOff.data(), g.dElemOff + g.nElems, (g.nRanks + 2) * sizeof(int64_t), cudaMemcpyDeviceToHost, g.st));
   CK(cudaStreamSynchronize(g.st));

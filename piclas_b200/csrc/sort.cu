@@ -241,11 +241,10 @@ __global__ void k_gather_particles(const double* __restrict__ x0, const double* 
   if (i >= n) return;
   const uint32_t s = perm[i];
   const double a0 = x0[s], a1 = x1[s], a2 = x2[s], b0 = v0[s], b1 = v1[s], b2 = v2[s];
-  const int32_t el = elem[s];
   const uint8_t m = meta[s];
   y0[i] = a0; y1[i] = a1; y2[i] = a2;
   w0[i] = b0; w1[i] = b1; w2[i] = b2;
-  elemOut[i] = el;
+  if (elem) elemOut[i] = elem[s];   // null: the caller regenerates the element ids from the sorted segments
   metaOut[i] = m;
   if (id) idOut[i] = id[s];
 }
