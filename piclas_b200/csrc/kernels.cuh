@@ -477,6 +477,9 @@ __device__ __forceinline__ int tria_hop(const TriaElem* __restrict__ te, const T
   const int gside = te->sideID[side];
   const int bc = te->bcid[side];
   const int oldElem = ElemID;
+  // shortcut-only instantiation: boundary sides (few) are left to the general one, so that the warps of the common case do
+  // not run through the periodic-shift arithmetic (square root, divisions, IntersectionWithWall) for a single lane
+  if (MODE == 1 && bc > 0) return HOP_NO_SHORTCUT;
   if (bc > 0) {
     const int kind = cst.bc_kind[bc - 1];
     if (kind == PGPU_BC_OPEN) return TRK_REMOVED;
