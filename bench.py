@@ -42,8 +42,8 @@ def parse():
     ap.add_argument("--nelem", type=int, default=64, help="elements per direction")
     ap.add_argument("--N", type=int, default=3)
     ap.add_argument("--particles", type=float, default=5e8, help="total particles (all GPUs)")
-    ap.add_argument("--cpu-particles", type=float, default=4e6, help="particles of the bounded CPU sample")
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-particles", type=float, default=1.6e7, help="particles of the bounded CPU sample")
+    ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -151,8 +151,9 @@ def measured_traffic(n_particles):
         return None, "no ncu capture committed"
 
 
-def cpu_baseline(args, N, threads=None):
+def cpu_baseline(args, N, threads=None, steps=None, warmup=1):
     """Oracle (restated CPU path, -O3) on a bounded sample: same particles/element as the GPU workload."""
+    steps = steps or args.cpu_steps
     from oracle_lib import Oracle
     from piclas_b200.abi import Params
     threads = threads or (os.cpu_count() or 1)
@@ -168,18 +169,18 @@ def cpu_baseline(args, N, threads=None):
     spec = np.ones(n, dtype=np.int32)
     inside = np.ones(n, dtype=np.int32)
     isnew = np.zeros(n, dtype=np.int32)
-    # untimed warm-up step
-    orc.deposit(PS, spec, elem, inside, threads=threads)
-    orc.push_track(dt, PS, spec, elem, inside, isnew, E, threads=threads)
+    for _ in range(max(warmup, 1)):   # untimed warm-up steps
+        orc.deposit(PS, spec, elem, inside, threads=threads)
+        orc.push_track(dt, PS, spec, elem, inside, isnew, E, threads=threads)
     t0 = time.perf_counter()
-    for _ in range(args.cpu_steps):
+    for _ in range(steps):
         orc.deposit(PS, spec, elem, inside, threads=threads)
         orc.push_track(dt, PS, spec, elem, inside, isnew, E, threads=threads)
     t = time.perf_counter() - t0
     orc.close()
-    return {"value": n * args.cpu_steps / t, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-            "sample": "%d^3 elements N=%d, %d particles (%.0f per element, as the GPU workload), %d steps, %.1f s"
-                      % (ne, N, n, ppe, args.cpu_steps, t)}
+    return {"value": n * steps / t, "unit": "particle-steps/s", "cores": threads, "kind": "port", "ms_per_step": 1e3 * t / steps,
+            "sample": "%d^3 elements N=%d, %d particles (%.0f per element, as the GPU workload), %d steps, %.1f s wall on %d threads"
+                      % (ne, N, n, ppe, steps, t, threads)}
 
 
 def config_dict(args, n_total):
@@ -194,10 +195,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args, args.N)
+    cb = cpu_baseline(args, args.N, steps=args.steps, warmup=args.warmup)   # each step = one pass over the bounded sample
     line = {"impl": "reference", "metric": "particle-steps/s (interp+push+track+depo)", "value": cb["value"],
-            "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.cpu_steps, "warmup": 1,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config_dict(args, args.particles), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "restated CPU path (oracle port, -O3, std::thread); the Fortran/MPI/HDF5 reference cannot be built here"}
