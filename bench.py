@@ -278,6 +278,21 @@ def run_b200(args):
         e2e = {"value": n_total * args.e2e_steps / t_e2e, "unit": "particle-steps/s",
                "h2d_bytes_per_step": int(E_h.nbytes), "d2h_bytes_per_step": int(PS_h.nbytes), "steps": args.e2e_steps,
                "ms_per_step": 1e3 * t_e2e / args.e2e_steps}
+        # the same loop when the host takes only the charge density, all the Poisson source term reads
+        # (equations/poisson/equation.f90:1043): a quarter of the device->host bytes.  Reported beside, not instead of, e2e.
+        rho_pin = torch.empty((mesh.nElems, n1, n1, n1), dtype=torch.float64).pin_memory()
+        rho_h = rho_pin.numpy()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            gpu.Deposition(want_partsource=False, want_nodesource=False)
+            gpu.ChargeDensity(out=rho_h)
+            gpu.SetField(E_h)
+            gpu.PushAndTrack(dt)
+        torch.cuda.synchronize()
+        t_rho = time.perf_counter() - t0
+        e2e["charge_only"] = {"value": n_total * args.e2e_steps / t_rho, "ms_per_step": 1e3 * t_rho / args.e2e_steps,
+                              "d2h_bytes_per_step": int(rho_h.nbytes)}
     gpu.close()
 
     peak, peak_src = hbm_peak()

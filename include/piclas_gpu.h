@@ -165,6 +165,11 @@ int piclas_gpu_upload_particles(int64_t n, const double *PartState, const int32_
  * NodeSource: [nUniqueGlobalNodes][4] (cell_volweight_mean only) or NULL.  Either may be NULL. */
 int piclas_gpu_deposit(double *PartSource, double *NodeSource);
 
+/* The HDG source term of the Poisson solve reads only the charge density, PS_N(iElem)%PartSource(4,i,j,k)
+ * (equations/poisson/equation.f90:1043, CalcSourceHDG).  After piclas_gpu_deposit(NULL, NULL) (or deposit_finish) this
+ * copies that one component, LOCAL [nElems][N+1][N+1][N+1], a quarter of the PartSource transfer. */
+int piclas_gpu_get_charge(double *ChargeDensity);
+
 /* after CALL HDG(time,iter): E == U_N(iElem)%E(1:3,i,j,k) packed, LOCAL [nElems][N+1][N+1][N+1][3] */
 int piclas_gpu_set_field(const double *E);
 

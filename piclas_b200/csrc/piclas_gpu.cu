@@ -41,6 +41,7 @@ struct Ctx {
   int32_t *dAdjOff = nullptr, *dAdj = nullptr, *dElemNodeU = nullptr;
   int32_t *dPerN = nullptr, *dPerOff = nullptr, *dPerNodes = nullptr;
   double *dNodeVolume = nullptr, *dElemAcc = nullptr, *dS = nullptr, *dNodeSource = nullptr, *dPartSource = nullptr;
+  double* dCharge = nullptr;   // PartSource(4,:) of the local elements, compact (piclas_gpu_get_charge)
   // RefMapping
   bool ref = false;
   RefTables refT;
@@ -489,7 +490,7 @@ int piclas_gpu_finalize(void) {
   cudaDeviceSynchronize();
   cudaFree(g.dTria); cudaFree(g.dGeo); cudaFree(g.dPlanes); cudaFree(g.dAff); cudaFree(g.dElemRank); cudaFree(g.dElemXGP);
   cudaFree(g.dAdjOff); cudaFree(g.dAdj); cudaFree(g.dElemNodeU); cudaFree(g.dPerN); cudaFree(g.dPerOff); cudaFree(g.dPerNodes);
-  cudaFree(g.dNodeVolume); cudaFree(g.dElemAcc); cudaFree(g.dS); cudaFree(g.dNodeSource); cudaFree(g.dPartSource);
+  cudaFree(g.dNodeVolume); cudaFree(g.dElemAcc); cudaFree(g.dS); cudaFree(g.dNodeSource); cudaFree(g.dPartSource); cudaFree(g.dCharge);
   cudaFree(g.dE); cudaFree(g.dElemOff); cudaFree(g.dKeys); cudaFree(g.dCounters);
   cudaFree(g.dStage); cudaFree(g.dStageI); cudaFree(g.dStageL);
   cudaFree(g.dCommSend); cudaFree(g.dCommRecv);
@@ -1184,6 +1185,26 @@ int piclas_gpu_deposit(double* PartSource, double* NodeSource) {
     return 0;
   }
   return deposit_finish(PartSource, NodeSource);
+}
+
+__global__ void k_extract_component(const double* __restrict__ src4, double* __restrict__ dst, int64_t n, int comp) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src4[i * 4 + comp];
+}
+
+int piclas_gpu_get_charge(double* ChargeDensity) {
+  if (!g.ready) return fail("piclas_gpu_get_charge: not initialised");
+  if (!g.prm.DoDeposition) return fail("piclas_gpu_get_charge: PIC-DoDeposition=F");
+  if (!ChargeDensity) return fail("piclas_gpu_get_charge: null array");
+  CK(cudaSetDevice(g.device));
+  const int64_t n = (int64_t)g.nElems * g.ND;
+  if (n == 0) return 0;
+  if (!g.dCharge) CK(cudaMalloc((void**)&g.dCharge, (size_t)n * 8));
+  k_extract_component<<<(unsigned)((n + 255) / 256), 256, 0, g.st>>>(g.dPartSource, g.dCharge, n, 3);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(ChargeDensity, g.dCharge, (size_t)n * 8, cudaMemcpyDeviceToHost, g.st));
+  CK(cudaStreamSynchronize(g.st));
+  return 0;
 }
 
 int piclas_gpu_nodesource_device(void** devNodeSource) {

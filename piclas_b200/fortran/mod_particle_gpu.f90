@@ -78,6 +78,11 @@ INTERFACE
     TYPE(C_PTR),VALUE :: PartSource, NodeSource                  ! packed [4,nDOF_local] / [4,nUniqueGlobalNodes] or C_NULL_PTR
     INTEGER(C_INT)    :: piclas_gpu_deposit
   END FUNCTION
+  FUNCTION piclas_gpu_get_charge(ChargeDensity) BIND(C,NAME='piclas_gpu_get_charge')
+    IMPORT :: C_INT, C_DOUBLE
+    REAL(C_DOUBLE),INTENT(OUT) :: ChargeDensity(*)               ! packed [nDOF_local] == PS_N(iElem)%PartSource(4,i,j,k)
+    INTEGER(C_INT)             :: piclas_gpu_get_charge
+  END FUNCTION
   FUNCTION piclas_gpu_set_field(E) BIND(C,NAME='piclas_gpu_set_field')
     IMPORT :: C_INT, C_DOUBLE
     REAL(C_DOUBLE),INTENT(IN) :: E(3,*)                          ! packed [3,nDOF_local]
@@ -151,7 +156,7 @@ END INTERFACE
 
 PUBLIC :: pgpu_mesh_t, pgpu_params_t
 PUBLIC :: piclas_gpu_init, piclas_gpu_finalize, piclas_gpu_upload_particles, piclas_gpu_deposit, piclas_gpu_set_field
-PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles
+PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles, piclas_gpu_get_charge
 PUBLIC :: piclas_gpu_exchange_info, piclas_gpu_exchange_recv_buffer, piclas_gpu_exchange_finish
 PUBLIC :: piclas_gpu_nodesource_device, piclas_gpu_sf_halo_info, piclas_gpu_deposit_finish, piclas_gpu_phase_timing
 PUBLIC :: ParticleStepGPU, GPUAbortOnError

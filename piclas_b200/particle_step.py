@@ -111,6 +111,12 @@ class ParticleStep:
         self._check(self.lib.piclas_gpu_deposit(_f(PS), _f(NS)))
         return PS, NS
 
+    def ChargeDensity(self, out=None):
+        """PartSource(4,:,:,:) of the last Deposition: all the HDG source term reads (equations/poisson/equation.f90:1043)."""
+        rho = out if out is not None else np.empty(self._ps_shape[:-1])
+        self._check(self.lib.piclas_gpu_get_charge(_f(rho)))
+        return rho
+
     def SetField(self, E):
         """U_N(iElem)%E(1:3,i,j,k) packed as [nElems,k,j,i,3] after CALL HDG (hdg/elem_mat.f90:709)."""
         E = np.ascontiguousarray(E, dtype=np.float64)

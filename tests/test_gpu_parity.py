@@ -50,6 +50,7 @@ def run_parity(mesh, prm, PS0, spec, elem0, E, dt, nsteps, check_deposit=True):
                 alive = inside.astype(bool)
                 PSr, NSr = orc.deposit(PSo, spec, elo, inside)
                 PSg, NSg = gpu.Deposition()
+                assert np.array_equal(gpu.ChargeDensity(), PSg[..., 3]), "piclas_gpu_get_charge differs from PartSource(4,:)"
                 for c in range(4):
                     worst["ns"] = max(worst["ns"], _rel(NSg[:, c], NSr[:, c]))
                     worst["ps"] = max(worst["ps"], _rel(PSg[..., c], PSr[..., c]))
