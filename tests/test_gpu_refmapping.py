@@ -69,3 +69,23 @@ def test_refmapping_halo_limited_bc_lists_and_open_walls():
     elem = hm.cartesian_locate(mesh, PS[:, :3])
     E = cases.smooth_field(mesh, 1e-4)
     run_ref_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5, deposit=False)
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+def test_refmapping_deformed_mesh(arith):
+    """Unstructured-like mesh: trilinear elements with non-planar inner sides (planar box boundary), RefMapping tracking through
+    the Newton mapping and the FIBGM, shape-function deposition — the closest stand-in for the NIG_PIC_Deposition meshes."""
+    lo, hi = [0, 0, 0], [1, 1, 1]
+    mesh = hm.box_mesh(lo, hi, (5, 4, 4), 2, tracking=hm.REFMAPPING, deform=cases.wavy(0.05, lo, hi))
+    hm.add_fibgm(mesh)
+    hm.add_refmapping_tables(mesh)
+    prm = cases.electron_params(TrackingMethod=hm.REFMAPPING, DepositionType=DEPO_SF, MacroParticleFactor=(1e9,), arithmetic=arith)
+    hm.shape_function_setup(mesh, prm, 0.25, 2, dim_sf=3)
+    dt = 1e-8
+    PS, spec = cases.uniform_plasma(mesh, 8000, seed=33, vth_cells=0.4, dt=dt)
+    orc = Oracle(mesh, prm)
+    elem = orc.locate(PS[:, :3])
+    orc.close()
+    assert (elem > 0).all()
+    E = cases.smooth_field(mesh, 1e-4)
+    run_ref_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=4)
