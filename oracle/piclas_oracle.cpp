@@ -459,6 +459,42 @@ void periodicBoundary(const Oracle& o, double* PartState, double* LastPartPos, T
   *ElemID = o.SideInfo(SIDE_NBELEMID, SideID);
 }
 
+// particle_surfaces.f90:256-401 CalcNormAndTangTriangle, nVec only (outward unit normal of triangle TriNum of a local side)
+void calcNormTriangle(const Oracle& o, int iLocSide, int Element, int TriNum, double* nVec) {
+  const double* nd = o.NodeCoords(o.ElemSideNodeID(1, iLocSide, Element) + 1);
+  double xNod = nd[0], yNod = nd[1], zNod = nd[2];
+  int Node1 = TriNum + 1, Node2 = TriNum + 2;
+  const double* a1 = o.NodeCoords(o.ElemSideNodeID(Node1, iLocSide, Element) + 1);
+  const double* a2 = o.NodeCoords(o.ElemSideNodeID(Node2, iLocSide, Element) + 1);
+  double V1[3] = {a1[0] - xNod, a1[1] - yNod, a1[2] - zNod};
+  double V2[3] = {a2[0] - xNod, a2[1] - yNod, a2[2] - zNod};
+  double nx = -V1[1] * V2[2] + V1[2] * V2[1];  // NV (inwards)
+  double ny = -V1[2] * V2[0] + V1[0] * V2[2];
+  double nz = -V1[0] * V2[1] + V1[1] * V2[0];
+  double nVal = std::sqrt(nx * nx + ny * ny + nz * nz);
+  nVec[0] = -nx / nVal;
+  nVec[1] = -ny / nVal;
+  nVec[2] = -nz / nVal;
+}
+
+// surfacemodel_tools.f90:81-256 PerfectReflection for a wall at rest (WallVelo = 0), no rotating frame, no LSERK history.
+// Reached through GetBoundaryInteraction case 2 -> SurfaceModelling -> MaxwellScattering (SurfaceModel 0) with
+// MomentumACC = 0, for which the drawn random number always selects the specular branch.
+void perfectReflection(double* PartState, double* LastPartPos, TrackInfo& ti, const double* n_loc) {
+  double POI_vec[3];
+  for (int d = 0; d < 3; ++d) POI_vec[d] = LastPartPos[d] + ti.PartTrajectory[d] * ti.alpha;                       // :132
+  double vn = (PartState[3] * n_loc[0] + PartState[4] * n_loc[1]) + PartState[5] * n_loc[2];
+  for (int d = 0; d < 3; ++d) PartState[3 + d] = PartState[3 + d] - 2. * vn * n_loc[d];                            // :177
+  for (int d = 0; d < 3; ++d) LastPartPos[d] = POI_vec[d];                                                          // :191
+  double tn = (ti.PartTrajectory[0] * n_loc[0] + ti.PartTrajectory[1] * n_loc[1]) + ti.PartTrajectory[2] * n_loc[2];
+  for (int d = 0; d < 3; ++d) ti.PartTrajectory[d] = ti.PartTrajectory[d] - 2. * tn * n_loc[d];                    // :192
+  for (int d = 0; d < 3; ++d) PartState[d] = LastPartPos[d] + ti.PartTrajectory[d] * (ti.lengthPartTrajectory - ti.alpha);  // :194
+  for (int d = 0; d < 3; ++d) ti.PartTrajectory[d] = PartState[d] - LastPartPos[d];                                // :221
+  ti.lengthPartTrajectory = VECNORM3D(ti.PartTrajectory);
+  if (std::fabs(ti.lengthPartTrajectory) <= 2.22e-16) ti.lengthPartTrajectory = 0.0;                               // ALMOSTZERO
+  else for (int d = 0; d < 3; ++d) ti.PartTrajectory[d] = ti.PartTrajectory[d] / ti.lengthPartTrajectory;
+}
+
 enum TrackResult { TRACK_OK = 0, TRACK_LOST = 1, TRACK_REMOVED_BC = 2, TRACK_ERROR = 3 };
 
 // particle_triatracking.f90:137-484 SingleParticleTriaTracking3D (no mortars, no rot. ref. frame)
@@ -557,6 +593,12 @@ TrackResult singleParticleTriaTracking3D(Oracle& o, double* PartState, double* L
         switch (BCType) {
           case PGPU_BC_OPEN: inside = false; break;                       // RemoveParticle
           case PGPU_BC_PERIODIC: periodicBoundary(o, PartState, LastPartPos, ti, SideID, &ElemID); break;
+          case PGPU_BC_REFLECTIVE: {   // CalcNormAndTangTriangle + SurfaceModelling -> PerfectReflection (specular wall)
+            double n_loc[3];
+            calcNormTriangle(o, LocalSide, ElemID, TriNum, n_loc);
+            perfectReflection(PartState, LastPartPos, ti, n_loc);
+            break;
+          }
           default: o.err = "TriaTracking: boundary condition type not supported"; return TRACK_ERROR;
         }
         if (!inside) return TRACK_REMOVED_BC;

@@ -403,9 +403,11 @@ __device__ __forceinline__ bool exit_side_planar(const PlaneElem* __restrict__ p
 // MODE 0: determinant tests only; 1: exit-side shortcut only (returns HOP_NO_SHORTCUT when it does not apply); 2: shortcut, then
 // the determinant tests if it does not apply.
 constexpr int HOP_NO_SHORTCUT = -2;
-template <bool FAST, bool G, int MODE, class PlaneOf>
+// reflectV(n): mirrors the particle's velocity at a wall with outward unit normal n (PerfectReflection, wall at rest).
+template <bool FAST, bool G, int MODE, class PlaneOf, class ReflectV>
 __device__ __forceinline__ int tria_hop(const TriaElem* __restrict__ te, const TriaElem* __restrict__ tria, const PlaneElem* __restrict__ plCur,
-                                        PlaneOf planeOf, double x[3], double lp[3], int& ElemID, uint32_t& mask, HopHist& h) {
+                                        PlaneOf planeOf, ReflectV reflectV, double x[3], double lp[3], int& ElemID, uint32_t& mask,
+                                        HopHist& h) {
   int side = -1, tri = 0;
   bool shortcut = false;
   if (FAST && MODE != 0) shortcut = exit_side_planar<G>(plCur, x, lp, mask, side, tri);
@@ -483,6 +485,25 @@ __device__ __forceinline__ int tria_hop(const TriaElem* __restrict__ te, const T
   if (bc > 0) {
     const int kind = cst.bc_kind[bc - 1];
     if (kind == PGPU_BC_OPEN) return TRK_REMOVED;
+    if (kind == PGPU_BC_REFLECTIVE) {
+      // GetBoundaryInteraction case 2 -> SurfaceModelling -> PerfectReflection (surfacemodel_tools.f90:81-256): specular wall at
+      // rest.  The particle stays in ElemID; DoneLastElem is cleared (particle_triatracking.f90:426-427).
+      flight();
+      const double alpha = intersection_with_wall<G>(te, lp, V, side, tri);
+      double n[3];
+      triangle_normal<G>(te, side, tri, n);
+      reflectV(n);
+      const double tn = (V[0] * n[0] + V[1] * n[1]) + V[2] * n[2];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        lp[d] = lp[d] + V[d] * alpha;          // point of impact
+        V[d] = V[d] - 2. * tn * n[d];
+        x[d] = lp[d] + V[d] * (len - alpha);
+      }
+      h.clear();
+      const bool inSame = FAST ? inside_fast<G>(plCur, te, x, mask) : inside_quad3d_mask<G>(te, x, mask);
+      return inSame ? TRK_OK : -1;
+    }
     if (kind != PGPU_BC_PERIODIC) return TRK_ERR_BC;
     flight();
     const double alpha = intersection_with_wall<G>(te, lp, V, side, tri);
@@ -732,8 +753,14 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
         int ElemID = gElem;
         HopHist h;
         h.clear();
-        const int status = tria_hop<true, false, MODE>(&st, tria, &sp, [&](int sd, int) { return (const PlaneElem*)&spn[sd]; }, x, lp,
-                                                       ElemID, mask, h);
+        const int status = tria_hop<true, false, MODE>(
+            &st, tria, &sp, [&](int sd, int) { return (const PlaneElem*)&spn[sd]; },
+            [&](const double n[3]) {   // the velocity has been written already: mirror it in place
+              const double v0 = PF[3 * PS_ + q], v1 = PF[4 * PS_ + q], v2 = PF[5 * PS_ + q];
+              const double vn = (v0 * n[0] + v1 * n[1]) + v2 * n[2];
+              PF[3 * PS_ + q] = v0 - 2. * vn * n[0]; PF[4 * PS_ + q] = v1 - 2. * vn * n[1]; PF[5 * PS_ + q] = v2 - 2. * vn * n[2];
+            },
+            x, lp, ElemID, mask, h);
         if (status == HOP_NO_SHORTCUT) return false;
         if (status != -1) {
           tria_finish(pb, q, status, ElemID, x, elemRank, keys, nElems, offsetElem, counters);
@@ -846,8 +873,14 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_track_leavers(PartBuf pb, co
       if (__ballot_sync(0xffffffffu, active) == 0) break;
     }
     if (active) {
-      int status = tria_hop<FAST, true, FAST ? 2 : 0>(tria + (ElemID - 1), tria, FAST ? planes + (ElemID - 1) : nullptr,
-                                         [&](int, int ne) { return planes + (ne - 1); }, x, lp, ElemID, mask, h);
+      int status = tria_hop<FAST, true, FAST ? 2 : 0>(
+          tria + (ElemID - 1), tria, FAST ? planes + (ElemID - 1) : nullptr, [&](int, int ne) { return planes + (ne - 1); },
+          [&](const double n[3]) {
+            const double v0 = PF[3 * PS_ + p], v1 = PF[4 * PS_ + p], v2 = PF[5 * PS_ + p];
+            const double vn = (v0 * n[0] + v1 * n[1]) + v2 * n[2];
+            PF[3 * PS_ + p] = v0 - 2. * vn * n[0]; PF[4 * PS_ + p] = v1 - 2. * vn * n[1]; PF[5 * PS_ + p] = v2 - 2. * vn * n[2];
+          },
+          x, lp, ElemID, mask, h);
       if (status == -1 && ++guard > 100000) status = TRK_ERR_LOOP;
       if (status != -1) {
         tria_finish(pb, p, status, ElemID, x, elemRank, keys, nElems, offsetElem, counters);

@@ -480,6 +480,25 @@ __device__ __forceinline__ double intersection_with_wall(const TriaElem* __restr
   return alpha;
 }
 
+// ---- particle_surfaces.f90:256-401 CalcNormAndTangTriangle, nVec only: outward unit normal of triangle tri of local side s --------
+template <bool G = false>
+__device__ __forceinline__ void triangle_normal(const TriaElem* __restrict__ te, int s, int tri, double n[3]) {
+  const uint32_t sn = load_side_nodes<G>(te, s);
+  double p0[3], p1[3], p2[3];
+  load_corner<G>(te, sn & 0xffu, p0);
+  load_corner<G>(te, (sn >> (8 * tri)) & 0xffu, p1);
+  load_corner<G>(te, (sn >> (8 * (tri + 1))) & 0xffu, p2);
+  const double a0 = p1[0] - p0[0], a1 = p1[1] - p0[1], a2 = p1[2] - p0[2];
+  const double b0 = p2[0] - p0[0], b1 = p2[1] - p0[1], b2 = p2[2] - p0[2];
+  double nx = -a1 * b2 + a2 * b1;   // NV (inwards)
+  double ny = -a2 * b0 + a0 * b2;
+  double nz = -a0 * b1 + a1 * b0;
+  const double nVal = sqrt((nx * nx + ny * ny) + nz * nz);
+  n[0] = -nx / nVal;
+  n[1] = -ny / nVal;
+  n[2] = -nz / nVal;
+}
+
 // determinants of the two triangles of local side s (particle_mesh_tools.f90:187-199)
 template <bool G = false>
 __device__ __forceinline__ void side_dets(const TriaElem* __restrict__ te, const double x[3], int s, double& d1, double& d2) {

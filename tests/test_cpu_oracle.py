@@ -211,6 +211,32 @@ def test_open_boundary_removes_and_counts_nothing_lost():
     assert lost == 0 and np.array_equal(inside == 0, out)
 
 
+def test_reflective_walls_fold_the_free_flight():
+    """Specular walls at rest (PerfectReflection): without a field the flight in a box is the folded straight line, speeds are
+    conserved and nobody leaves; several reflections per step and corner hits included."""
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (3, 2, 4), 1, periodic=(False, False, False), wall_kind=hm.BC_REFLECTIVE)
+    o = Oracle(mesh, cases.electron_params(DoInterpolation=0, DoDeposition=0))
+    n = 3000
+    rng = np.random.default_rng(21)
+    x0 = rng.uniform(0.02, 0.98, (n, 3))
+    v0 = rng.normal(0.0, 0.9, (n, 3))          # up to a few box lengths per step
+    PS = np.ascontiguousarray(np.concatenate([x0, v0], axis=1))
+    spec = np.ones(n, dtype=np.int32)
+    el = hm.cartesian_locate(mesh, x0)
+    inside = np.ones(n, dtype=np.int32)
+    E = np.zeros((mesh.nElems, 2, 2, 2, 3))
+    t = 0.0
+    for _ in range(3):
+        lost, _, _ = o.push_track(1.0, PS, spec, el, inside, np.zeros(n, dtype=np.int32), E)
+        t += 1.0
+        assert lost == 0 and inside.all()
+        y = np.mod(x0 + v0 * t, 2.0)
+        fold = np.where(y > 1.0, 2.0 - y, y)
+        assert np.abs(PS[:, :3] - fold).max() < 1e-12
+        assert np.abs(np.abs(PS[:, 3:]) - np.abs(v0)).max() < 1e-14
+        assert np.array_equal(el, hm.cartesian_locate(mesh, PS[:, :3]))
+
+
 # ---- C ABI surface ---------------------------------------------------------------------------------------------------------
 def test_library_exports_every_symbol_of_the_header():
     from piclas_b200 import build, lib

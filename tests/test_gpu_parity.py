@@ -220,3 +220,15 @@ def test_sort_key_widths(shape):
     E = cases.smooth_field(mesh, amp=1.0e-3)
     elem = hm.cartesian_locate(mesh, PS[:, :3])
     run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=2)
+
+
+def test_reflective_walls(arith):
+    """Specular walls at rest (GetBoundaryInteraction case 2 -> PerfectReflection): positions, mirrored velocities and ownership
+    against the oracle, several wall hits per step for the fast particles, deposition next to the walls."""
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 3, 5), 2, periodic=(False, True, False), wall_kind=hm.BC_REFLECTIVE)
+    prm = cases.electron_params(arithmetic=arith)
+    dt = 1e-8
+    PS, spec = cases.uniform_plasma(mesh, 15000, seed=41, vth_cells=0.8, dt=dt)
+    E = cases.smooth_field(mesh, amp=2.0e-4)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5)
