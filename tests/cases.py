@@ -32,6 +32,35 @@ def plasma_ball_cvwm():
     return mesh, prm, PS, np.ones(3333, dtype=np.int32), hm.cartesian_locate(mesh, x)
 
 
+def plasma_ball_two_elements(deformed):
+    """regressioncheck/NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM: two hexahedra in [-1,1]^3 (corners of
+    hopr.ini; `deformed`: the shared side is strongly twisted, which triggers the SucRefPos=F inverse-distance fallback of
+    DepositionMethod_CVWM), reflective walls, N=1, TriaTracking, 3333 particles in a sphere r=0.5."""
+    lx = 0.4 if deformed else 0.0
+    li = 1.0
+    z1 = [(-li, -li, -li), (lx, -li, -li), (-lx, li, -li), (-li, li, -li), (-li, -li, li), (-lx, -li, li), (lx, li, li), (-li, li, li)]
+    z2 = [(lx, -li, -li), (li, -li, -li), (li, li, -li), (-lx, li, -li), (-lx, -li, li), (li, -li, li), (li, li, li), (lx, li, li)]
+    pts, ids = [], {}
+    elems = []
+    for zone in (z1, z2):
+        e = []
+        for c in zone:
+            if c not in ids:
+                ids[c] = len(pts)
+                pts.append(c)
+            e.append(ids[c])
+        elems.append(e)
+    mesh = hm.build_mesh(np.array(pts, float), np.array(elems), 1, [(hm.BC_REFLECTIVE, 0)],
+                         lambda cen, fid: np.ones(len(cen), dtype=np.int32))
+    prm = Params(ChargeIC=(1.60217653e-5, -QE), MassIC=(1.0, ME), MacroParticleFactor=(200.0, 200.0),
+                 DepositionType=DEPO_CVWM, carryParticleIDs=1)
+    rng = np.random.default_rng(20261018)
+    x = sphere_points(rng, 3333, 0.5)
+    PS = np.zeros((3333, 6))
+    PS[:, :3] = x
+    return mesh, prm, PS, np.ones(3333, dtype=np.int32)
+
+
 def smooth_field(mesh, amp=1.0):
     """Smooth analytic E sampled at the Gauss points, [nElems,k,j,i,3]."""
     X = mesh.Elem_xGP

@@ -237,6 +237,23 @@ def test_reflective_walls_fold_the_free_flight():
         assert np.array_equal(el, hm.cartesian_locate(mesh, PS[:, :3]))
 
 
+@pytest.mark.parametrize("deformed", [False, True])
+def test_plasma_ball_two_elements_known_answer(deformed):
+    """NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM (analyze.ini: Charge 10.68010874898 at 5e-13 on the Cartesian
+    and 1e-3 on the deformed two-element mesh).  The twisted interface makes Newton leave [-1,1]^3 for particles that the
+    triangle test assigns to the convex element: the SucRefPos=F inverse-distance branch (pic_depo_method.f90:512-538)."""
+    mesh, prm, PS, spec = cases.plasma_ball_two_elements(deformed)
+    o = Oracle(mesh, prm)
+    el = o.locate(PS[:, :3])
+    assert (el > 0).all()
+    _, suc, _ = o.position_in_ref_elem(PS[:, :3], el, force=True)
+    assert ((np.asarray(suc) == 0).sum() > 50) == deformed          # the fallback is exercised on the deformed mesh only
+    src, _ = o.deposit(PS, spec, el, np.ones(len(spec), dtype=np.int32))
+    k = GOLD["NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM"]
+    ref, tol = (k["charge_deformed"], k["abs_tol_deformed"]) if deformed else (k["charge_cartesian"], k["abs_tol_cartesian"])
+    assert abs(o.deposited_charge(src) - ref) <= tol
+
+
 # ---- C ABI surface ---------------------------------------------------------------------------------------------------------
 def test_library_exports_every_symbol_of_the_header():
     from piclas_b200 import build, lib

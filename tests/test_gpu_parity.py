@@ -232,3 +232,20 @@ def test_reflective_walls(arith):
     E = cases.smooth_field(mesh, amp=2.0e-4)
     elem = hm.cartesian_locate(mesh, PS[:, :3])
     run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5)
+
+
+def test_two_element_twisted_mesh_fallback_and_walls(arith):
+    """NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM on the deformed mesh: the SucRefPos=F inverse-distance branch
+    of the deposition and of the interpolation, concave / convex triangle sides in the tracking, reflective walls."""
+    mesh, prm, PS, spec = cases.plasma_ball_two_elements(True)
+    prm.arithmetic = arith
+    orc = Oracle(mesh, prm)
+    elem = orc.locate(PS[:, :3])
+    orc.close()
+    rng = np.random.default_rng(3)
+    dt = 1e-8
+    PS[:, 3:] = rng.normal(0.0, 0.3 / dt, (len(spec), 3))
+    X = mesh.Elem_xGP
+    E = 1e-3 * np.stack([np.sin(X[..., 1]), np.cos(X[..., 2]), X[..., 0]], axis=-1)
+    w = run_parity(mesh, prm, PS, spec, elem, np.ascontiguousarray(E), dt, nsteps=5)
+    print(w)
