@@ -3,12 +3,17 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
 // library.  The product path (piclas_b200/csrc, libpiclas_gpu.so) never links, loads or calls it.
 //
-// PARITY UNPINNED: the reference (Fortran 2008 + MPI-3 + HDF5) cannot be compiled in the build container
-// (no gfortran/mpif90/HDF5) and its own tests hold no per-particle golden vectors, so this
-// restatement is pinned only by (a) the integrated known-answer values of the reference's regression checks
-// (total deposited charge, tests/test_oracle_kat.py) and (b) analytic self-checks.  It follows the Fortran
-// routine by routine, loop by loop and operator by operator; every function cites the lines it restates
-// (paths relative to the reference root).
+// PARITY: the reference (Fortran 2008 + MPI-3 + HDF5) cannot be compiled in the build container (no
+// gfortran/mpif90/HDF5), so there is no oracle/_ref.  What the reference's own tests hold for this path pins:
+//   * cell_volweight_mean deposition PER DOF: the restart state of regressioncheck/NIG_PIC_Deposition/
+//     Plasma_Ball_cell_volweight_mean carries the 3333 particles and the DG_Source the reference deposited from
+//     them; this restatement reproduces all 8000 values to 3e-15 relative (tests/golden/make_reference_vectors.py,
+//     tests/test_cpu_oracle.py::test_oracle_reproduces_the_references_deposited_source_per_dof);
+//   * the integrated known answers of all NIG_PIC_Deposition checks (21 values, tests/golden/reference_known_answers.json).
+// PARITY UNPINNED for everything else: the reference's tests hold no per-particle positions, velocities or element
+// ids; interpolation, push and tracking are pinned only by analytic self-checks.  The
+// restatement follows the Fortran routine by routine, loop by loop and operator by operator; every function
+// cites the lines it restates (paths relative to the reference root).
 //
 // Arithmetic contract: IEEE binary64, built with -ffp-contract=off, expressions evaluated in the Fortran
 // source order (left to right for equal precedence, Appendix A.14 of SURVEY.md).  The reference's Release

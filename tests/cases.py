@@ -32,6 +32,24 @@ def plasma_ball_cvwm():
     return mesh, prm, PS, np.ones(3333, dtype=np.int32), hm.cartesian_locate(mesh, x)
 
 
+def reference_plasma_ball():
+    """The reference's own particles and its deposited charge density (tests/golden/make_reference_vectors.py): returns the
+    10^3 mesh, parameters, PartState, species, element ids and DG_Source(4,:) reordered from HOPR's element order to ours."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "plasma_ball_cvwm_reference.npz"))
+    mesh = hm.box_mesh([-1, -1, -1], [1, 1, 1], (10, 10, 10), 1)
+    prm = Params(ChargeIC=(1.60217653e-5, -QE), MassIC=(1.0, ME), MacroParticleFactor=(200.0, 200.0),
+                 DepositionType=DEPO_CVWM, carryParticleIDs=1)
+    ijk = np.floor((g["ElemBarycenters"] + 1.0) / 0.2).astype(np.int64)
+    ours = ijk[:, 0] + 10 * (ijk[:, 1] + 10 * ijk[:, 2])            # HOPR element -> our element
+    assert len(np.unique(ours)) == 1000
+    rho = np.empty((1000, 2, 2, 2))
+    rho[ours] = g["DG_Source_charge"]
+    PS = np.ascontiguousarray(g["PartData"][:, :6])
+    spec = g["PartData"][:, 6].astype(np.int32)
+    return mesh, prm, PS, spec, hm.cartesian_locate(mesh, PS[:, :3]), rho, g
+
+
 def plasma_ball_two_elements(deformed):
     """regressioncheck/NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM: two hexahedra in [-1,1]^3 (corners of
     hopr.ini; `deformed`: the shared side is strongly twisted, which triggers the SucRefPos=F inverse-distance fallback of

@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Extracts golden vectors from files the reference's own regression checks hold (run where /root/reference is mounted):
+
+  regressioncheck/NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean/
+      plasma_wave_State_000.00000000000000000_restart.h5   the reference state its h5diff check compares against
+                                                           (analyze.ini: DG_Source, DG_Solution): PartData = the 3333
+                                                           particles, DG_Source = PartSource(1:4,i,j,k,iElem) as deposited
+                                                           by the reference's cell_volweight_mean
+      Box_mesh.h5                                          HOPR mesh (element order along the space-filling curve)
+  regressioncheck/NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM/Box_deformed_mesh.h5
+                                                           corner nodes of the two-element twisted mesh
+
+-> tests/golden/plasma_ball_cvwm_reference.npz (committed; the tests never read /root/reference).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from h5mini import H5File  # noqa: E402
+
+REF = "/root/reference/regressioncheck/NIG_PIC_Deposition"
+
+
+def main():
+    d = os.path.join(REF, "Plasma_Ball_cell_volweight_mean")
+    st = H5File(os.path.join(d, "plasma_wave_State_000.00000000000000000_restart.h5"))
+    me = H5File(os.path.join(d, "Box_mesh.h5"))
+    part = st.read("PartData")                   # (3333, 7): PartState(1:6), species
+    src = st.read("DG_Source")                   # (nElems, k, j, i, 4)
+    bary = me.read("ElemBarycenters")            # (nElems, 3), HOPR element order
+    nodes = me.read("NodeCoords").reshape(-1, 8, 3)
+    assert part.shape == (3333, 7) and src.shape == (1000, 2, 2, 2, 4) and bary.shape == (1000, 3)
+    assert not src[..., :3].any()                # particles at rest: no current density
+    # the elements of this Cartesian HOPR mesh are aligned with the axes (xi = x, eta = y, zeta = z)
+    assert np.allclose(nodes[:, 1] - nodes[:, 0], [0.2, 0, 0]) and np.allclose(nodes[:, 2] - nodes[:, 0], [0, 0.2, 0])
+    assert np.allclose(nodes[:, 4] - nodes[:, 0], [0, 0, 0.2])
+    dm = H5File(os.path.join(REF, "Plasma_Ball_cell_volweight_mean_save_CVWM", "Box_deformed_mesh.h5"))
+    dnodes = dm.read("NodeCoords").reshape(-1, 8, 3)     # (2, 8, 3) tensor-ordered corner nodes of the two elements
+    out = os.path.join(HERE, "plasma_ball_cvwm_reference.npz")
+    np.savez_compressed(out, PartData=part, DG_Source_charge=np.ascontiguousarray(src[..., 3]), ElemBarycenters=bary,
+                        deformed_mesh_NodeCoords=dnodes)
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
+if __name__ == "__main__":
+    main()

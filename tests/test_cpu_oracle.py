@@ -237,6 +237,28 @@ def test_reflective_walls_fold_the_free_flight():
         assert np.array_equal(el, hm.cartesian_locate(mesh, PS[:, :3]))
 
 
+def test_oracle_reproduces_the_references_deposited_source_per_dof():
+    """The one per-DOF vector the reference's regression checks hold for this path: its restart state of
+    NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean (h5diff reference for DG_Source) with the 3333 particles and the charge
+    density the reference deposited from them.  The oracle must reproduce all 8000 values."""
+    mesh, prm, PS, spec, el, rho_ref, _ = cases.reference_plasma_ball()
+    o = Oracle(mesh, prm)
+    assert np.array_equal(el, o.locate(PS[:, :3]))
+    src, _ = o.deposit(PS, spec, el, np.ones(len(spec), dtype=np.int32))
+    assert not src[..., :3].any()
+    assert np.abs(src[..., 3] - rho_ref).max() <= 1e-13 * np.abs(rho_ref).max()       # measured 3e-15
+    assert abs(o.deposited_charge(src) - GOLD["NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean"]["charge"]) <= 5e-13
+
+
+def test_two_element_mesh_matches_the_references_mesh_file():
+    """Corner nodes of cases.plasma_ball_two_elements(True) against Box_deformed_mesh.h5 of the regression check."""
+    mesh, _, _, _ = cases.plasma_ball_two_elements(True)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plasma_ball_cvwm_reference.npz"))
+    ref = g["deformed_mesh_NodeCoords"]                               # (2, 8, 3), tensor order
+    ours = np.asarray(mesh.NodeCoords).reshape(2, 8, 3)
+    assert np.abs(ours - ref).max() <= 1e-15          # same corners in the same tensor order (HOPR's 0.4 is off by one ulp)
+
+
 @pytest.mark.parametrize("deformed", [False, True])
 def test_plasma_ball_two_elements_known_answer(deformed):
     """NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM (analyze.ini: Charge 10.68010874898 at 5e-13 on the Cartesian
@@ -279,28 +301,34 @@ def test_product_path_has_no_cpu_fallback():
             ps.ParticleStep(mesh, Params())
 
 
-# ---- shape function known answers (NIG_PIC_Deposition/Plasma_Ball_Shape-function-*) ---------------------------------------
-@pytest.mark.parametrize("dim,direction,kind", [(1, 1, "sf"), (1, 1, "cc"), (2, 3, "sf"), (2, 3, "cc")])
-def test_oracle_shape_function_known_answers(dim, direction, kind):
-    from piclas_b200.abi import DEPO_SF, DEPO_SF_CC
+# ---- shape function known answers (NIG_PIC_Deposition/Plasma_Ball_Shape-function-{x,y,z}Dir) --------------------------------
+_SF_CASES = GOLD["NIG_PIC_Deposition/Plasma_Ball_Shape-function"]["cases"]
+
+
+@pytest.mark.parametrize("kind", ["sf", "cc", "adaptive"])
+@pytest.mark.parametrize("case", _SF_CASES, ids=[c["case"].replace(" ", "-") for c in _SF_CASES])
+def test_oracle_shape_function_known_answers(case, kind):
+    """All 18 reference values of the three regression directories: 1-D and 2-D shape functions in every direction,
+    shape_function (5 % relative), shape_function_cc and shape_function_adaptive with smoothing (1e-9 absolute)."""
+    from piclas_b200.abi import DEPO_SF, DEPO_SF_CC, DEPO_SF_ADAPTIVE
     k = GOLD["NIG_PIC_Deposition/Plasma_Ball_Shape-function"]
-    mesh = hm.box_mesh([-5, -5, -5], [5, 5, 5], (4, 4, 1), 3)
+    mesh = hm.box_mesh([-5, -5, -5], [5, 5, 5], tuple(case["nelems"]), 3)
     hm.add_fibgm(mesh)
     n = 20000                                     # the charge is linear in the particle number: scale the known answer
     x = cases.sphere_points(np.random.default_rng(1), n, 0.5)
     PS = np.zeros((n, 6))
     PS[:, :3] = x
     prm = Params(ChargeIC=(1.60217653e-5,), MassIC=(1.0,), MacroParticleFactor=(200.0,),
-                 DepositionType=DEPO_SF if kind == "sf" else DEPO_SF_CC)
-    hm.shape_function_setup(mesh, prm, 2.0, 2, dim_sf=dim, dim_sf_dir=direction, sfDepo3D=True)
+                 DepositionType={"sf": DEPO_SF, "cc": DEPO_SF_CC, "adaptive": DEPO_SF_ADAPTIVE}[kind])
+    if kind == "adaptive":
+        hm.shape_function_adaptive_setup(mesh, prm, 2, dim_sf=case["dim"], dim_sf_dir=case["dir"], sfDepo3D=True, smoothing=True)
+    else:
+        hm.shape_function_setup(mesh, prm, 2.0, 2, dim_sf=case["dim"], dim_sf_dir=case["dir"], sfDepo3D=True)
     o = Oracle(mesh, prm)
     PSrc, _ = o.deposit(PS, np.ones(n, dtype=np.int32), hm.cartesian_locate(mesh, x), np.ones(n, dtype=np.int32))
     q = o.deposited_charge(PSrc) * (100000 / n)
-    if kind == "cc":
-        assert abs(q - k["charge_cc_adaptive"]) <= k["abs_tol_cc_adaptive"]
-    else:
-        ref = k["charge_sf_1D_x"] if dim == 1 else k["charge_sf_2D_z"]
-        assert abs(q - ref) <= k["rel_tol_sf"] * ref
+    tol = k["tolerances"][kind]
+    assert abs(q - case[kind]) <= (tol["value"] * case[kind] if tol["type"] == "relative" else tol["value"])
 
 
 # ---- RefMapping tracking ----------------------------------------------------------------------------------------------------

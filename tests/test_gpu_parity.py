@@ -249,3 +249,17 @@ def test_two_element_twisted_mesh_fallback_and_walls(arith):
     E = 1e-3 * np.stack([np.sin(X[..., 1]), np.cos(X[..., 2]), X[..., 0]], axis=-1)
     w = run_parity(mesh, prm, PS, spec, elem, np.ascontiguousarray(E), dt, nsteps=5)
     print(w)
+
+
+def test_reference_dg_source_per_dof(arith):
+    """CUDA deposition of the reference's own 3333 particles against the charge density the reference wrote for them
+    (restart state of NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean, tests/golden/make_reference_vectors.py)."""
+    from piclas_b200.particle_step import ParticleStep
+    mesh, prm, PS, spec, elem, rho_ref, _ = cases.reference_plasma_ball()
+    prm.arithmetic = arith
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(PS, spec, elem)
+        PSg, _ = gpu.Deposition()
+        rho = gpu.ChargeDensity()
+    assert not PSg[..., :3].any()
+    assert np.abs(rho - rho_ref).max() <= 1e-12 * np.abs(rho_ref).max()

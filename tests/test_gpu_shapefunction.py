@@ -34,8 +34,8 @@ def _deposit_both(mesh, prm, PS, spec, elem):
     return q
 
 
-def plasma_ball(n=100000):
-    mesh = hm.box_mesh([-5, -5, -5], [5, 5, 5], (4, 4, 1), 3)
+def plasma_ball(nelems=(4, 4, 1), n=100000):
+    mesh = hm.box_mesh([-5, -5, -5], [5, 5, 5], tuple(nelems), 3)
     hm.add_fibgm(mesh)
     rng = np.random.default_rng(20261017)
     x = cases.sphere_points(rng, n, 0.5)
@@ -45,20 +45,21 @@ def plasma_ball(n=100000):
     return mesh, PS, np.ones(n, dtype=np.int32), hm.cartesian_locate(mesh, x)
 
 
-@pytest.mark.parametrize("dim,direction", [(1, 1), (2, 3)])
-@pytest.mark.parametrize("kind", ["sf", "cc"])
-def test_plasma_ball_shape_function_known_answers(dim, direction, kind):
-    """NIG_PIC_Deposition/Plasma_Ball_Shape-function-{x,z}Dir: 4x4x1 periodic box, N=3, r_sf=2, alpha=2, 100000 particles."""
-    mesh, PS, spec, elem = plasma_ball()
+@pytest.mark.parametrize("kind", ["sf", "cc", "adaptive"])
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["case"].replace(" ", "-") for c in GOLD["cases"]])
+def test_plasma_ball_shape_function_known_answers(case, kind):
+    """NIG_PIC_Deposition/Plasma_Ball_Shape-function-{x,y,z}Dir: periodic box of 16 elements, N=3, r_sf=2, alpha=2, 100000
+    particles; all 18 reference values (1-D / 2-D in every direction; shape_function 5 % relative, _cc and _adaptive 1e-9)."""
+    mesh, PS, spec, elem = plasma_ball(case["nelems"])
     prm = Params(ChargeIC=(1.60217653e-5,), MassIC=(1.0,), MacroParticleFactor=(200.0,),
-                 DepositionType=DEPO_SF if kind == "sf" else DEPO_SF_CC)
-    hm.shape_function_setup(mesh, prm, 2.0, 2, dim_sf=dim, dim_sf_dir=direction, sfDepo3D=True)
-    q = _deposit_both(mesh, prm, PS, spec, elem)
-    if kind == "cc":
-        assert abs(q - GOLD["charge_cc_adaptive"]) <= GOLD["abs_tol_cc_adaptive"]
+                 DepositionType={"sf": DEPO_SF, "cc": DEPO_SF_CC, "adaptive": DEPO_SF_ADAPTIVE}[kind])
+    if kind == "adaptive":
+        hm.shape_function_adaptive_setup(mesh, prm, 2, dim_sf=case["dim"], dim_sf_dir=case["dir"], sfDepo3D=True, smoothing=True)
     else:
-        ref = GOLD["charge_sf_1D_x"] if dim == 1 else GOLD["charge_sf_2D_z"]
-        assert abs(q - ref) <= GOLD["rel_tol_sf"] * ref
+        hm.shape_function_setup(mesh, prm, 2.0, 2, dim_sf=case["dim"], dim_sf_dir=case["dir"], sfDepo3D=True)
+    q = _deposit_both(mesh, prm, PS, spec, elem)
+    tol = GOLD["tolerances"][kind]
+    assert abs(q - case[kind]) <= (tol["value"] * case[kind] if tol["type"] == "relative" else tol["value"])
 
 
 @pytest.mark.parametrize("kind", [DEPO_SF, DEPO_SF_CC])
