@@ -1,8 +1,8 @@
-"""Minimal reader for the HDF5 files of the reference's regression checks (no HDF5 library in this image).
+"""Minimal reader for HOPR mesh files and PICLas state files (no HDF5 library in this image).
 
 Handles what those files use: superblock version 0, old-style groups (B-tree v1 + symbol-table nodes + local heap), object
-headers version 1 with continuation blocks, simple dataspaces, fixed-point / IEEE float datatypes, contiguous and (uncompressed)
-chunked layouts.  Only used by tests/golden/make_reference_vectors.py, which runs where /root/reference is mounted."""
+headers version 1 with continuation blocks, simple dataspaces, fixed-point / IEEE float / fixed-length string datatypes,
+contiguous and (uncompressed) chunked layouts.  Used by hostmesh.from_hopr_file and tests/golden/make_reference_vectors.py."""
 import struct
 
 import numpy as np

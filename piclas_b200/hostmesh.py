@@ -105,8 +105,13 @@ def _det3(a):
 
 
 def build_mesh(coords, elem_nodes, N, bcs, bc_of_face, periodic_vectors=(),
-               tracking=TRIATRACKING) -> ParticleMesh:
+               tracking=TRIATRACKING, hopr_sides=None) -> ParticleMesh:
     """Build all particle-mesh tables.
+
+    hopr_sides    optional (6*nE, 5) SideInfo of a HOPR mesh file (SideType, SIDE_ID, nbElemID, 10*nbLocSide+flip, BCID): side
+                  ids, master/slave, flips and BC ids are then taken from the file (they fix which diagonal splits a shared
+                  quadrilateral and which element owns a planar face, particle_mesh_readin.f90:386-419) instead of being derived
+                  from the geometry; bc_of_face is not called.
 
     coords        (nU,3) unique node coordinates
     elem_nodes    (nE,8) 0-based unique node ids per element in CGNS corner order
@@ -157,47 +162,70 @@ def build_mesh(coords, elem_nodes, N, bcs, bc_of_face, periodic_vectors=(),
     if np.any(same[1:] & same[:-1]):
         raise ValueError("non-manifold mesh: a face is shared by more than two elements")
 
-    bcid = np.zeros(nS, dtype=np.int32)
-    bnd = np.nonzero(partner < 0)[0]
     centroid = coords[fn].mean(axis=1)
-    if bnd.size:
-        bcid[bnd] = np.asarray(bc_of_face(centroid[bnd], fn[bnd]), dtype=np.int32)
-        if np.any(bcid[bnd] < 1) or np.any(bcid[bnd] > len(bcs)):
-            raise ValueError("bc_of_face returned an invalid BCID")
-    # periodic pairing of boundary faces by shifted centroid
     shift = np.zeros((nS, 3))
-    per = bnd[bc_kind[bcid[bnd] - 1] == BC_PERIODIC] if bnd.size else bnd
-    if per.size:
-        a = bc_alpha[bcid[per] - 1]
-        shift[per] = np.sign(a)[:, None] * PV[np.abs(a) - 1]
-        tree = cKDTree(centroid[per])
-        ext = np.linalg.norm(coords.max(axis=0) - coords.min(axis=0))
-        d, j = tree.query(centroid[per] + shift[per])
-        if np.any(d > 1e-8 * ext):
-            raise ValueError("periodic face without partner")
-        tgt = per[j]
-        if np.any(bc_alpha[bcid[tgt] - 1] != -a):
-            raise ValueError("periodic partner has inconsistent BC_ALPHA")
-        partner[per] = tgt
-
-    # master / slave, unique side ids, flip
     sidx = np.arange(nS)
-    has_nb = partner >= 0
-    is_master = (~has_nb) | (sidx <= partner)
-    side_uid = np.zeros(nS, dtype=np.int64)
-    masters = np.nonzero(is_master)[0]
-    side_uid[masters] = np.arange(1, masters.size + 1)
-    slaves = np.nonzero(~is_master)[0]
-    side_uid[slaves] = -side_uid[partner[slaves]]
-    flip = np.zeros(nS, dtype=np.int64)
-    if slaves.size:
-        m = partner[slaves]
-        p_first = coords[fn[m, 0]] + shift[m]                 # master's first node seen from the slave side
-        ps = coords[fn[slaves]]                               # (ns, 4, 3)
-        dist = np.linalg.norm(ps - p_first[:, None, :], axis=2)
-        flip[slaves] = np.argmin(dist, axis=1) + 1
+    if hopr_sides is not None:
+        H = np.asarray(hopr_sides, dtype=np.int64)
+        if H.shape != (nS, 5):
+            raise ValueError("hopr_sides must have shape (6*nElems, 5)")
+        if np.any(H[:, 0] > 100) or np.any(H[:, 2] < 0):
+            raise ValueError("mortar sides are not supported")
+        bcid = H[:, 4].astype(np.int32)
+        side_uid = H[:, 1].copy()
+        flip = np.where(side_uid > 0, 0, H[:, 3] % 10)
+        has_nb = H[:, 2] > 0
+        nb_loc = np.where(has_nb, H[:, 3] // 10, 0)
+        partner = np.where(has_nb, 6 * (H[:, 2] - 1) + (nb_loc - 1), -1)
+        if np.any(bcid > len(bcs)) or np.any(bcid < 0):
+            raise ValueError("BCID outside the boundary list")
+        isper = (bcid > 0) & (bc_kind[np.maximum(bcid, 1) - 1] == BC_PERIODIC)
+        per = np.nonzero(isper)[0]
+        if per.size:
+            a = bc_alpha[bcid[per] - 1]
+            shift[per] = np.sign(a)[:, None] * PV[np.abs(a) - 1]
+            ext = np.linalg.norm(coords.max(axis=0) - coords.min(axis=0))
+            if np.any(np.linalg.norm(centroid[per] + shift[per] - centroid[partner[per]], axis=1) > 1e-8 * ext):
+                raise ValueError("periodic vectors do not map the periodic sides onto their partners")
+    else:
+        bcid = np.zeros(nS, dtype=np.int32)
+        bnd = np.nonzero(partner < 0)[0]
+        if bnd.size:
+            bcid[bnd] = np.asarray(bc_of_face(centroid[bnd], fn[bnd]), dtype=np.int32)
+            if np.any(bcid[bnd] < 1) or np.any(bcid[bnd] > len(bcs)):
+                raise ValueError("bc_of_face returned an invalid BCID")
+        # periodic pairing of boundary faces by shifted centroid
+        per = bnd[bc_kind[bcid[bnd] - 1] == BC_PERIODIC] if bnd.size else bnd
+        if per.size:
+            a = bc_alpha[bcid[per] - 1]
+            shift[per] = np.sign(a)[:, None] * PV[np.abs(a) - 1]
+            tree = cKDTree(centroid[per])
+            ext = np.linalg.norm(coords.max(axis=0) - coords.min(axis=0))
+            d, j = tree.query(centroid[per] + shift[per])
+            if np.any(d > 1e-8 * ext):
+                raise ValueError("periodic face without partner")
+            tgt = per[j]
+            if np.any(bc_alpha[bcid[tgt] - 1] != -a):
+                raise ValueError("periodic partner has inconsistent BC_ALPHA")
+            partner[per] = tgt
+
+        # master / slave, unique side ids, flip
+        has_nb = partner >= 0
+        is_master = (~has_nb) | (sidx <= partner)
+        side_uid = np.zeros(nS, dtype=np.int64)
+        masters = np.nonzero(is_master)[0]
+        side_uid[masters] = np.arange(1, masters.size + 1)
+        slaves = np.nonzero(~is_master)[0]
+        side_uid[slaves] = -side_uid[partner[slaves]]
+        flip = np.zeros(nS, dtype=np.int64)
+        if slaves.size:
+            m = partner[slaves]
+            p_first = coords[fn[m, 0]] + shift[m]                 # master's first node seen from the slave side
+            ps = coords[fn[slaves]]                               # (ns, 4, 3)
+            dist = np.linalg.norm(ps - p_first[:, None, :], axis=2)
+            flip[slaves] = np.argmin(dist, axis=1) + 1
+        nb_loc = np.where(has_nb, (partner % 6) + 1, 0)
     loc_side = (sidx % 6) + 1
-    nb_loc = np.where(has_nb, (partner % 6) + 1, 0)
 
     SideInfo = np.zeros((nS, 8), dtype=np.int32)
     SideInfo[:, 0] = 4                                         # SIDE_TYPE (<=100: not a mortar)
@@ -368,6 +396,68 @@ def build_mesh(coords, elem_nodes, N, bcs, bc_of_face, periodic_vectors=(),
         Periodic_nNodes=Periodic_nNodes, Periodic_offsetNode=Periodic_offset, Periodic_Nodes=Periodic_Nodes,
         NodeVolume=NodeVolume, xyz_min=coords.min(axis=0), xyz_max=coords.max(axis=0),
         unique_coords=coords, elem_nodes=elem_nodes.astype(np.int32))
+
+
+def from_hopr_arrays(ElemInfo, SideInfo, NodeCoords, GlobalNodeIDs, BCType, BCNames, N, part_bc=None,
+                     tracking=TRIATRACKING) -> ParticleMesh:
+    """Particle-mesh tables from the datasets of a HOPR mesh file (mesh/mesh_readin.f90, particle_mesh_readin.f90): elements,
+    sides, side ids / flips and unique node ids are used as stored, so that element order, triangle diagonals and the owner
+    of planar faces are those of the reference run on the same file.
+
+    Hexahedra with 8 nodes (NGeo = 1, element types 108 / 118) without mortars.  BCType rows (type, curve, state, alpha):
+    type 1 is periodic with alpha = +-vector id; every other boundary takes its particle condition from
+    part_bc[name] (BC_OPEN / BC_REFLECTIVE, the Part-Boundary<n>-Condition of parameter.ini; default BC_OPEN).
+    The periodic vectors are the offsets between paired periodic sides (GetPeriodicVectors)."""
+    EI = np.asarray(ElemInfo, dtype=np.int64)
+    SI = np.asarray(SideInfo, dtype=np.int64)
+    NC = np.asarray(NodeCoords, dtype=np.float64)
+    G = np.asarray(GlobalNodeIDs, dtype=np.int64)
+    nE = EI.shape[0]
+    if np.any((EI[:, 0] != 108) & (EI[:, 0] != 118)):
+        raise ValueError("only 8-node hexahedra (element types 108, 118) are supported")
+    if np.any(EI[:, 3] - EI[:, 2] != 6) or np.any(EI[:, 5] - EI[:, 4] != 8):
+        raise ValueError("elements must have 6 sides and 8 nodes (NGeo = 1, no mortars)")
+    if EI[0, 2] != 0 or np.any(EI[1:, 2] != EI[:-1, 3]) or EI[0, 4] != 0 or np.any(EI[1:, 4] != EI[:-1, 5]):
+        raise ValueError("ElemInfo offsets are not contiguous")
+    if SI.shape != (6 * nE, 5) or NC.shape != (8 * nE, 3) or G.shape != (8 * nE,):
+        raise ValueError("SideInfo / NodeCoords / GlobalNodeIDs do not match ElemInfo")
+    uniq, first, inv = np.unique(G, return_index=True, return_inverse=True)
+    coords = NC[first]
+    if np.abs(coords[inv] - NC).max() > 1e-12 * max(1.0, np.abs(NC).max()):
+        raise ValueError("nodes with the same GlobalNodeID have different coordinates")
+    tens = inv.reshape(nE, 8)                                  # unique id per element node, tensor order
+    elem_nodes = tens[:, _CNS0]                                # CGNS corner order
+    names = [(b.decode() if isinstance(b, bytes) else str(b)).strip() for b in BCNames]
+    BT = np.asarray(BCType, dtype=np.int64).reshape(-1, 4)
+    part_bc = part_bc or {}
+    bcs = []
+    for nme, row in zip(names, BT):
+        bcs.append((BC_PERIODIC, int(row[3])) if row[0] == 1 else (part_bc.get(nme, BC_OPEN), 0))
+    # periodic vectors from the paired sides
+    nPV = int(np.abs(BT[BT[:, 0] == 1, 3]).max()) if np.any(BT[:, 0] == 1) else 0
+    PV = np.zeros((nPV, 3))
+    if nPV:
+        fn = elem_nodes[:, _NODEMAP_CGNS0].reshape(6 * nE, 4)
+        cen = coords[fn].mean(axis=1)
+        alpha = np.where(SI[:, 4] > 0, BT[np.maximum(SI[:, 4], 1) - 1, 3] * (BT[np.maximum(SI[:, 4], 1) - 1, 0] == 1), 0)
+        for k in range(1, nPV + 1):
+            sd = np.nonzero(alpha == k)[0]
+            if sd.size == 0:
+                raise ValueError("periodic vector %d has no side with BC_ALPHA=+%d" % (k, k))
+            nb = 6 * (SI[sd, 2] - 1) + (SI[sd, 3] // 10 - 1)
+            v = cen[nb] - cen[sd]
+            if np.abs(v - v[0]).max() > 1e-10 * max(1.0, np.abs(v).max()):
+                raise ValueError("periodic sides of vector %d are not congruent" % k)
+            PV[k - 1] = np.where(np.abs(v[0]) > 1e-12 * np.abs(v[0]).max(), v[0], 0.0)   # centroid means carry rounding fuzz
+    return build_mesh(coords, elem_nodes, N, bcs, None, periodic_vectors=PV, tracking=tracking, hopr_sides=SI)
+
+
+def from_hopr_file(path, N, part_bc=None, tracking=TRIATRACKING) -> ParticleMesh:
+    """ParticleMesh from a HOPR *_mesh.h5 (read with the built-in minimal HDF5 reader, h5mini.py)."""
+    from .h5mini import H5File
+    f = H5File(path)
+    return from_hopr_arrays(f.read("ElemInfo"), f.read("SideInfo"), f.read("NodeCoords"), f.read("GlobalNodeIDs"),
+                            f.read("BCType"), f.read("BCNames"), N, part_bc=part_bc, tracking=tracking)
 
 
 def structured_connectivity(nx, ny, nz):

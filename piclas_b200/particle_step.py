@@ -100,6 +100,20 @@ class ParticleStep:
                                                            C.byref(nout)))
         return dict(PartState=PS, PartSpecies=spec, GlobalElemID=elem, PartPosRef=ref, ids=ids)
 
+    def FillParticleData(self, offsetnPart=0):
+        """PartInt / PartData of WriteParticleToHDF5 (io_hdf5/hdf5_output_particle.f90:1595-1670, FillParticleData):
+        PartInt[iElem] = (first, last) offsets of the element's particles, PartData[iPart] = (PartState(1:6), species).  The
+        device keeps the particles sorted by element, so the downloaded order already is the file order."""
+        d = self.DownloadParticles()
+        loc = d["GlobalElemID"].astype(np.int64) - self.offsetElem - 1
+        if loc.size and (np.any(np.diff(loc) < 0) or loc.min() < 0 or loc.max() >= self.nElems):
+            raise PiclasGpuError("FillParticleData: particles are not sorted by local element")
+        cnt = np.bincount(loc, minlength=self.nElems).astype(np.int64)
+        last = offsetnPart + np.cumsum(cnt)
+        PartInt = np.stack([last - cnt, last], axis=1)
+        PartData = np.concatenate([d["PartState"], d["PartSpecies"].astype(np.float64)[:, None]], axis=1)
+        return PartInt, np.ascontiguousarray(PartData)
+
     # ------------------------------------------------------------------------------------------------------
     def Deposition(self, want_partsource=True, want_nodesource=True, out_partsource=None, out_nodesource=None):
         """CALL Deposition() (pic_depo.f90:944-1018): returns (PartSource[nElems,k,j,i,4], NodeSource[nNodes,4])."""

@@ -10,7 +10,7 @@
   regressioncheck/NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM/Box_deformed_mesh.h5
                                                            corner nodes of the two-element twisted mesh
 
--> tests/golden/plasma_ball_cvwm_reference.npz (committed; the tests never read /root/reference).
+-> tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz (committed; the tests never read /root/reference).
 """
 import os
 import sys
@@ -18,8 +18,8 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, HERE)
-from h5mini import H5File  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from piclas_b200.h5mini import H5File  # noqa: E402
 
 REF = "/root/reference/regressioncheck/NIG_PIC_Deposition"
 
@@ -39,9 +39,17 @@ def main():
     assert np.allclose(nodes[:, 4] - nodes[:, 0], [0, 0, 0.2])
     dm = H5File(os.path.join(REF, "Plasma_Ball_cell_volweight_mean_save_CVWM", "Box_deformed_mesh.h5"))
     dnodes = dm.read("NodeCoords").reshape(-1, 8, 3)     # (2, 8, 3) tensor-ordered corner nodes of the two elements
+    # the two HOPR mesh files themselves (datasets hostmesh.from_hopr_arrays consumes)
+    meshes = {}
+    for tag, f in (("box", me), ("deformed", dm)):
+        for ds in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames"):
+            meshes[tag + "_" + ds] = f.read(ds)
+    mout = os.path.join(HERE, "hopr_meshes.npz")
+    np.savez_compressed(mout, **meshes)
+    print("wrote", mout, os.path.getsize(mout), "bytes")
     out = os.path.join(HERE, "plasma_ball_cvwm_reference.npz")
     np.savez_compressed(out, PartData=part, DG_Source_charge=np.ascontiguousarray(src[..., 3]), ElemBarycenters=bary,
-                        deformed_mesh_NodeCoords=dnodes)
+                        deformed_mesh_NodeCoords=dnodes, PartInt=st.read("PartInt"))
     print("wrote", out, os.path.getsize(out), "bytes")
 
 

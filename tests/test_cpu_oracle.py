@@ -250,6 +250,60 @@ def test_oracle_reproduces_the_references_deposited_source_per_dof():
     assert abs(o.deposited_charge(src) - GOLD["NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean"]["charge"]) <= 5e-13
 
 
+def _hopr(tag, N, **kw):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hopr_meshes.npz"))
+    return hm.from_hopr_arrays(*[g[tag + "_" + d] for d in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames")],
+                               N, **kw)
+
+
+def test_hopr_mesh_file_in_its_own_element_order_reproduces_dg_source():
+    """hostmesh.from_hopr_arrays on the datasets of the regression check's Box_mesh.h5 (element order along HOPR's space-filling
+    curve, its side ids and flips): the reference's DG_Source is reproduced in file order, and the tables agree with the
+    generated box mesh element by element."""
+    mesh = _hopr("box", 1)
+    assert mesh.nElems == 1000 and mesh.nUniqueNodes == 1331
+    assert np.array_equal(mesh.PeriodicVectors, 2.0 * np.eye(3))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plasma_ball_cvwm_reference.npz"))
+    PS = np.ascontiguousarray(g["PartData"][:, :6])
+    spec = g["PartData"][:, 6].astype(np.int32)
+    prm = Params(ChargeIC=(1.60217653e-5, -cases.QE), MassIC=(1.0, cases.ME), MacroParticleFactor=(200.0, 200.0))
+    o = Oracle(mesh, prm)
+    el = o.locate(PS[:, :3])
+    # PartInt of the state file: the particles are stored element by element in the file's element order
+    pi = g["PartInt"].T
+    assert np.array_equal(np.repeat(np.arange(1, 1001), pi[:, 1] - pi[:, 0]), el)
+    src, _ = o.deposit(PS, spec, el, np.ones(len(spec), dtype=np.int32))
+    ref = g["DG_Source_charge"]
+    assert np.abs(src[..., 3] - ref).max() <= 1e-13 * np.abs(ref).max()
+    # same geometry as the generated mesh, element by element
+    box = hm.box_mesh([-1, -1, -1], [1, 1, 1], (10, 10, 10), 1)
+    ijk = np.floor((mesh.ElemBaryNGeo + 1.0) / 0.2).astype(int)
+    ours = ijk[:, 0] + 10 * (ijk[:, 1] + 10 * ijk[:, 2])
+    assert np.abs(mesh.XCL_NGeo - box.XCL_NGeo[ours]).max() < 1e-14
+    nb_file = mesh.SideInfo[:, 2].reshape(1000, 6)
+    nb_box = box.SideInfo[:, 2].reshape(1000, 6)[ours]
+    assert np.array_equal(ours[nb_file - 1] + 1, nb_box)          # same neighbour through every local side
+    nv = np.zeros(box.nUniqueNodes)
+    key = lambda c: np.round((c + 1.0) / 0.2).astype(int) @ np.array([1, 11, 121])
+    nv[key(box.unique_coords)] = box.NodeVolume
+    assert np.abs(mesh.NodeVolume - nv[key(mesh.unique_coords)]).max() < 1e-15
+
+
+def test_twisted_mesh_from_the_hopr_file_known_answer():
+    """Box_deformed_mesh.h5 as written by HOPR (its master / slave choice fixes the diagonal of the twisted interface; BC 7 is the
+    inner dielectric boundary of that case): deposited charge within the regression check's 1e-3."""
+    mesh = _hopr("deformed", 1, part_bc={n: hm.BC_REFLECTIVE for n in
+                                          ("BC_x+", "BC_x-", "BC_y+", "BC_y-", "BC_z+", "BC_z-", "BC_DIELECTRIC")})
+    assert mesh.nElems == 2 and int(mesh.SideInfo[2, 4]) == 7 and int(mesh.SideInfo[2, 1]) == -3
+    _, prm, PS, spec = cases.plasma_ball_two_elements(True)
+    o = Oracle(mesh, prm)
+    el = o.locate(PS[:, :3])
+    assert (el > 0).all()
+    src, _ = o.deposit(PS, spec, el, np.ones(len(spec), dtype=np.int32))
+    k = GOLD["NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM"]
+    assert abs(o.deposited_charge(src) - k["charge_deformed"]) <= k["abs_tol_deformed"]
+
+
 def test_two_element_mesh_matches_the_references_mesh_file():
     """Corner nodes of cases.plasma_ball_two_elements(True) against Box_deformed_mesh.h5 of the regression check."""
     mesh, _, _, _ = cases.plasma_ball_two_elements(True)

@@ -263,3 +263,30 @@ def test_reference_dg_source_per_dof(arith):
         rho = gpu.ChargeDensity()
     assert not PSg[..., :3].any()
     assert np.abs(rho - rho_ref).max() <= 1e-12 * np.abs(rho_ref).max()
+
+
+def test_hopr_mesh_and_particle_output_layout():
+    """The reference's mesh file (datasets of Box_mesh.h5 through hostmesh.from_hopr_arrays) and its particles, uploaded in random
+    order: the device's element sort must yield the PartInt of the reference's state file, the same particles per element, and the
+    charge density in file order."""
+    import os
+    from piclas_b200.particle_step import ParticleStep
+    from piclas_b200.abi import Params
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gm, g = np.load(os.path.join(gold, "hopr_meshes.npz")), np.load(os.path.join(gold, "plasma_ball_cvwm_reference.npz"))
+    mesh = hm.from_hopr_arrays(*[gm["box_" + d] for d in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames")], 1)
+    prm = Params(ChargeIC=(1.60217653e-5, -cases.QE), MassIC=(1.0, cases.ME), MacroParticleFactor=(200.0, 200.0))
+    PD = g["PartData"]
+    pi_ref = g["PartInt"].T
+    elem_ref = np.repeat(np.arange(1, 1001), pi_ref[:, 1] - pi_ref[:, 0]).astype(np.int32)
+    perm = np.random.default_rng(9).permutation(len(PD))
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(np.ascontiguousarray(PD[perm, :6]), PD[perm, 6].astype(np.int32), elem_ref[perm])
+        PartInt, PartData = gpu.FillParticleData()
+        gpu.Deposition(want_partsource=False, want_nodesource=False)
+        rho = gpu.ChargeDensity()
+    assert np.array_equal(PartInt, pi_ref)
+    for a, b in pi_ref[pi_ref[:, 1] > pi_ref[:, 0]][:50]:                      # same particles in every element (any order)
+        assert np.array_equal(np.sort(PartData[a:b], axis=0), np.sort(PD[a:b], axis=0))
+    ref = g["DG_Source_charge"]
+    assert np.abs(rho - ref).max() <= 1e-12 * np.abs(ref).max()
