@@ -112,6 +112,8 @@ typedef struct pgpu_mesh {
   const double  *SFElemr2;        /* [nGlobalElems][2] adaptive radius (r, r^2) or NULL                  */
   const double  *ElemRadiusNGeo;  /* [nGlobalElems] (particle_mesh_build.f90:300)                        */
   const int32_t *ElemToBGM;       /* [nGlobalElems][6] FIBGM cell box imin,imax,jmin,jmax,kmin,kmax (particle_bgm.f90:517-522) */
+  const double  *BaseVectors3;    /* [nSides][3] bilinear term of the side (particle_mesh_build.f90:1923); needed when a BC side is
+                                     PLANAR_NONRECT or BILINEAR (ComputeBiLinearIntersection), may be NULL otherwise           */
 } pgpu_mesh_t;
 
 /* ---- already-parsed run-time parameters (parameter.ini keys in the comments) -------------------------- */

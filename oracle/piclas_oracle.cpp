@@ -1058,6 +1058,7 @@ int depositSF(Oracle& o, int64_t n, const double* PartState, const int32_t* Part
 constexpr double epsilontol = 100. * epsMach;  // particle_surfaces.f90:143-147
 
 inline bool ALMOSTZERO(double x) { return std::fabs(x) <= 2.22e-16; }  // piclas.h:83
+inline bool ALMOSTEQUAL(double x, double y) { return std::fabs(x - y) <= std::max(std::fabs(x), std::fabs(y)) * 4.441e-16; }  // piclas.h:81
 
 void insertionSort(double* a, int* id, int len) {  // utils.f90:52-101 (1-based in the reference)
   for (int i = 1; i < len; ++i) {
@@ -1123,6 +1124,135 @@ void computePlanarRectIntersection(const Oracle& o, bool* isHit, const double* P
   *isHit = true;
 }
 
+// utils.f90:401-465 QuadraticSolver
+void quadraticSolver(double A, double B, double C, int* nRoot, double* R1, double* R2) {
+  if (A != 0. && B == 0. && C == 0.) { *nRoot = 1; *R1 = 0.; *R2 = 0.; }
+  else if (A != 0.) {
+    const double radicant = (0.5 * B / A) * (0.5 * B / A) - (C / A);
+    if (radicant < 0.) { *nRoot = 0; *R1 = 0.; *R2 = 0.; }
+    else {
+      *nRoot = 2;
+      *R1 = -0.5 * (B / A) - std::copysign(1., B / A) * std::sqrt(radicant);
+      *R2 = (C / A) / *R1;
+    }
+  } else {
+    if (B != 0.) { *nRoot = 1; *R1 = -C / B; *R2 = 0.; }
+    else { *nRoot = 0; *R1 = 0.; *R2 = 0.; }
+  }
+}
+
+// particle_intersection.f90:2241-2273 ComputeXi
+double computeXi(double eta, const double* A1, const double* A2) {
+  const double a = eta * A2[0] + A2[1];
+  const double b = eta * (A2[0] - A1[0]) + A2[1] - A1[1];
+  if (std::fabs(b) >= std::fabs(a)) {
+    if (ALMOSTZERO(std::fabs(b))) return HUGE_D;
+    return (-eta * (A2[2] - A1[2]) - (A2[3] - A1[3])) / b;
+  }
+  return (-eta * A2[2] - A2[3]) / a;
+}
+
+// particle_intersection.f90:2209-2238 ComputeSurfaceDistance2; BiLinearCoeff[c][x]
+double computeSurfaceDistance2(const double (*BiLinearCoeff)[3], double xi, double eta, const double* PartTrajectory) {
+  double t = 0.;
+  for (int d = 0; d < 3; ++d)
+    t = t + (xi * eta * BiLinearCoeff[0][d] + xi * BiLinearCoeff[1][d] + eta * BiLinearCoeff[2][d] + BiLinearCoeff[3][d]) * PartTrajectory[d];
+  return t;
+}
+
+// particle_intersection.f90:855-1240 ComputeBiLinearIntersection (TrackingMethod = refmapping; used for BILINEAR and PLANAR_NONRECT
+// sides).  alpha2 < -1: not present.  Returns nonzero when the reference aborts ("Invalid intersection with bilinear side").
+int computeBiLinearIntersection(const Oracle& o, bool* isHit, const double* PartTrajectory, double lengthPartTrajectory, double* alpha,
+                                double* xitild, double* etatild, const double* LastPartPos, int SideID, bool haveAlpha2, double alpha2) {
+  *alpha = -1.0; *xitild = -2.0; *etatild = -2.0; *isHit = false;
+  double BiLinearCoeff[4][3], NormalCoeff[4][3];
+  const double* b0 = o.m.BaseVectors0 + (size_t)(SideID - 1) * 3;
+  const double* b1 = o.m.BaseVectors1 + (size_t)(SideID - 1) * 3;
+  const double* b2 = o.m.BaseVectors2 + (size_t)(SideID - 1) * 3;
+  const double* b3 = o.m.BaseVectors3 + (size_t)(SideID - 1) * 3;
+  for (int d = 0; d < 3; ++d) {
+    BiLinearCoeff[0][d] = 0.25 * b3[d];
+    BiLinearCoeff[1][d] = 0.25 * b1[d];
+    BiLinearCoeff[2][d] = 0.25 * b2[d];
+    BiLinearCoeff[3][d] = 0.25 * b0[d];
+  }
+  const double* nv = o.m.SideNormVec + (size_t)(SideID - 1) * 3;
+  const double scaleFac = PartTrajectory[0] * nv[0] + PartTrajectory[1] * nv[1] + PartTrajectory[2] * nv[2];
+  if (std::fabs(scaleFac) < epsilontol) return 0;
+  for (int d = 0; d < 3; ++d) BiLinearCoeff[3][d] = BiLinearCoeff[3][d] - LastPartPos[d];
+  for (int c = 0; c < 4; ++c) {
+    const double sp = BiLinearCoeff[c][0] * PartTrajectory[0] + BiLinearCoeff[c][1] * PartTrajectory[1] + BiLinearCoeff[c][2] * PartTrajectory[2];
+    for (int d = 0; d < 3; ++d) NormalCoeff[c][d] = BiLinearCoeff[c][d] - sp * PartTrajectory[d];
+  }
+  double A1[4], A2[4];
+  for (int c = 0; c < 4; ++c) { A1[c] = NormalCoeff[c][2] - NormalCoeff[c][0]; A2[c] = NormalCoeff[c][2] - NormalCoeff[c][1]; }
+  const double A = A1[0] * A2[2] - A2[0] * A1[2];
+  const double B = A1[0] * A2[3] - A2[0] * A1[3] + A1[1] * A2[2] - A2[1] * A1[2];
+  const double C = A1[1] * A2[3] - A2[1] * A1[3];
+  int nRoot;
+  double eta[2], xi[2] = {0., 0.}, t[2];
+  quadraticSolver(A, B, C, &nRoot, &eta[0], &eta[1]);
+  if (nRoot == 0) return 0;
+  if (nRoot == 1) {
+    if (std::fabs(eta[0]) <= 1.0) {
+      xi[0] = computeXi(eta[0], A1, A2);
+      if (xi[0] == HUGE_D) return 1;
+      if (std::fabs(xi[0]) <= 1.0) {
+        t[0] = computeSurfaceDistance2(BiLinearCoeff, xi[0], eta[0], PartTrajectory);
+        if (haveAlpha2 && alpha2 > -1.0 && ALMOSTEQUAL(t[0], alpha2)) t[0] = -1.0;
+        const double alphaNorm = t[0] / lengthPartTrajectory;
+        if (alphaNorm <= 1.0 && alphaNorm >= 0.) { *alpha = t[0]; *xitild = xi[0]; *etatild = eta[0]; *isHit = true; }
+      }
+    }
+    return 0;
+  }
+  int InterType = 0;
+  t[0] = t[1] = -1.;
+  for (int r = 0; r < 2; ++r) {
+    if (std::fabs(eta[r]) <= 1.0) {
+      xi[r] = computeXi(eta[r], A1, A2);
+      if (xi[r] == HUGE_D) return 1;
+      if (std::fabs(xi[r]) <= 1.0) {
+        t[r] = computeSurfaceDistance2(BiLinearCoeff, xi[r], eta[r], PartTrajectory);
+        if (haveAlpha2 && alpha2 > -1.0 && ALMOSTEQUAL(t[r], alpha2)) t[r] = -1.0;
+        const double alphaNorm = t[r] / lengthPartTrajectory;
+        if (alphaNorm <= 1.0 && alphaNorm >= 0.) { InterType += r + 1; *isHit = true; }
+      }
+    }
+  }
+  switch (InterType) {
+    case 0: return 0;
+    case 1: *alpha = t[0]; *xitild = xi[0]; *etatild = eta[0]; break;
+    case 2: *alpha = t[1]; *xitild = xi[1]; *etatild = eta[1]; break;
+    default:
+      if (o.SideInfo(SIDE_BCID, SideID) > 0) {   // REFMAPPING: the first of the two intersections
+        if (t[0] < t[1]) { *alpha = t[0]; *xitild = xi[0]; *etatild = eta[0]; }
+        else { *alpha = t[1]; *xitild = xi[1]; *etatild = eta[1]; }
+      } else { *alpha = -1; *xitild = 0.; *etatild = 0.; *isHit = false; }
+  }
+  return 0;
+}
+
+// particle_surfaces.f90:404-440 CalcNormAndTangBilinear (nVec only); corner points from the base vectors:
+// BCP(0,0)-BCP(N,0)+BCP(N,N)-BCP(0,N) = BaseVectors3, etc.
+void calcNormBilinear(const Oracle& o, double xi, double eta, int SideID, double* nVec) {
+  const double* b1 = o.m.BaseVectors1 + (size_t)(SideID - 1) * 3;
+  const double* b2 = o.m.BaseVectors2 + (size_t)(SideID - 1) * 3;
+  const double* b3 = o.m.BaseVectors3 + (size_t)(SideID - 1) * 3;
+  double a[3], b[3];
+  for (int d = 0; d < 3; ++d) {
+    b[d] = xi * 0.25 * b3[d] + 0.25 * b2[d];
+    a[d] = eta * 0.25 * b3[d] + 0.25 * b1[d];
+  }
+  double c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+  const double len = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+  for (int d = 0; d < 3; ++d) nVec[d] = c[d] / len;
+  // orientation: the reference's control points are ordered such that a x b points like SideNormVec (out of the master element;
+  // GetBoundaryInteraction then flips it for slave sides).  Our side tables may list the corners the other way round.
+  const double* nv = o.m.SideNormVec + (size_t)(SideID - 1) * 3;
+  if (nVec[0] * nv[0] + nVec[1] * nv[1] + nVec[2] * nv[2] < 0.) for (int d = 0; d < 3; ++d) nVec[d] = -nVec[d];
+}
+
 enum { BCSIDE_SIDEID = 0, BCSIDE_ELEMID = 1, BCSIDE_DISTANCE = 2 };
 
 // ParticleBCTracking with the tail recursion (:642-665) turned into a loop.  Returns nonzero on unsupported side/BC.
@@ -1146,6 +1276,7 @@ int particleBCTracking(Oracle& o, double lengthPartTrajectory0, int* ElemID, Ref
     lengthPartTrajectory0 = std::max(lengthPartTrajectory0, lengthPartTrajectory);
     bool doubleCheck = false;
     bool recurse = false;
+    double alphaOld = -1.0;
     std::vector<double> locAlpha(std::max(nlocSides, 1)), xi(std::max(nlocSides, 1)), eta(std::max(nlocSides, 1));
     std::vector<int> locSideList(std::max(nlocSides, 1));
     while (DoTracing) {
@@ -1158,10 +1289,18 @@ int particleBCTracking(Oracle& o, double lengthPartTrajectory0, int* ElemID, Ref
         const int SideID = (int)bm[BCSIDE_SIDEID];
         locSideList[ilocSide - firstSide] = ilocSide;
         const int flip = (o.SideInfo(SIDE_ID, SideID) > 0) ? 0 : (o.SideInfo(SIDE_FLIP, SideID) % 10);
-        if (o.m.SideType[SideID - 1] != 0) { o.err = "ParticleBCTracking: only PLANAR_RECT sides are supported"; return 4; }
         bool isHit;
-        computePlanarRectIntersection(o, &isHit, PartTrajectory, lengthPartTrajectory, &locAlpha[ilocSide - firstSide],
-                                      &xi[ilocSide - firstSide], &eta[ilocSide - firstSide], c.LastPartPos, flip, SideID);
+        if (o.m.SideType[SideID - 1] == 0) {          // PLANAR_RECT
+          computePlanarRectIntersection(o, &isHit, PartTrajectory, lengthPartTrajectory, &locAlpha[ilocSide - firstSide],
+                                        &xi[ilocSide - firstSide], &eta[ilocSide - firstSide], c.LastPartPos, flip, SideID);
+        } else if (o.m.SideType[SideID - 1] <= 2) {   // PLANAR_NONRECT, BILINEAR; the double check passes alpha2 = alphaOld (:545-547)
+          if (!o.m.BaseVectors3) { o.err = "ParticleBCTracking: BaseVectors3 missing for a non-rectangular BC side"; return 4; }
+          if (computeBiLinearIntersection(o, &isHit, PartTrajectory, lengthPartTrajectory, &locAlpha[ilocSide - firstSide],
+                                          &xi[ilocSide - firstSide], &eta[ilocSide - firstSide], c.LastPartPos, SideID, doubleCheck, alphaOld)) {
+            o.err = "ParticleBCTracking: Invalid intersection with bilinear side!";
+            return 4;
+          }
+        } else { o.err = "ParticleBCTracking: curved sides are not supported"; return 4; }
         if (locAlpha[ilocSide - firstSide] > -1.0) nInter++;
       }
       if (nInter == 0) {
@@ -1169,6 +1308,8 @@ int particleBCTracking(Oracle& o, double lengthPartTrajectory0, int* ElemID, Ref
       } else {
         *PartisMoved = true;
         insertionSort(locAlpha.data(), locSideList.data(), nlocSides);
+        for (int il = 0; il < nlocSides; ++il)
+          if (locAlpha[il] > -1) { alphaOld = locAlpha[il]; break; }   // :612-617
         bool reflected = false;
         for (int il = 0; il < nlocSides; ++il) {
           if (locAlpha[il] > -1) {
@@ -1184,6 +1325,10 @@ int particleBCTracking(Oracle& o, double lengthPartTrajectory0, int* ElemID, Ref
             reflected = false;  // crossedBC
             double n_loc[3] = {o.m.SideNormVec[(size_t)(SideID - 1) * 3], o.m.SideNormVec[(size_t)(SideID - 1) * 3 + 1],
                                o.m.SideNormVec[(size_t)(SideID - 1) * 3 + 2]};
+            if (o.m.SideType[SideID - 1] == 2) {   // BILINEAR: normal at the intersection point (TrackInfo%xi, %eta)
+              const int k = hitlocSide - firstSide;   // xi/eta are indexed by the unsorted side position
+              calcNormBilinear(o, xi[k], eta[k], SideID, n_loc);
+            }
             if (flip != 0) { n_loc[0] = -n_loc[0]; n_loc[1] = -n_loc[1]; n_loc[2] = -n_loc[2]; }
             if (!((n_loc[0] * ti.PartTrajectory[0] + n_loc[1] * ti.PartTrajectory[1] + n_loc[2] * ti.PartTrajectory[2]) <= 0.)) {
               reflected = true;
@@ -1222,8 +1367,44 @@ int particleBCTracking(Oracle& o, double lengthPartTrajectory0, int* ElemID, Ref
 }
 
 // ParticleRefTracking for one particle.  PartPosRef in/out.  Returns TrackResult.
+// particle_localization.f90:81-190 SinglePointToElement, TrackingMethod = refmapping, doHALO = T, no emission: the elements of the
+// particle's FIBGM cell in the order of their barycentre distance; the first one with MAXVAL(ABS(xi)) <= ElemEpsOneCell.
+int singlePointToElementRef(Oracle& o, const double* Pos3D, double* RefPos) {
+  auto cellOf = [&](int d) {
+    int c = (int)std::ceil((Pos3D[d] - o.m.xyzminglob[d]) / o.m.FIBGMdeltas[d]);
+    return std::max(std::min(o.m.FIBGMmax[d], c), o.m.FIBGMmin[d]);
+  };
+  const size_t cell = bgmCell(o, cellOf(0), cellOf(1), cellOf(2));
+  const int nBGMElems = o.m.FIBGM_nElems[cell];
+  if (nBGMElems < 1) return -1;
+  std::vector<double> Distance(nBGMElems);
+  std::vector<int> ListDistance(nBGMElems);
+  double mx = -1.;
+  for (int i = 0; i < nBGMElems; ++i) {
+    const int e = o.m.FIBGM_Element[o.m.FIBGM_offsetElem[cell] + i];
+    const double* b = o.m.ElemBaryNGeo + (size_t)(e - 1) * 3;
+    const double d0 = Pos3D[0] - b[0], d1 = Pos3D[1] - b[1], d2 = Pos3D[2] - b[2];
+    const double Distance2 = (d0 * d0 + d1 * d1) + d2 * d2;
+    Distance[i] = (Distance2 <= o.m.ElemRadius2NGeo[e - 1]) ? Distance2 : -1.;
+    ListDistance[i] = e;
+    mx = std::max(mx, Distance[i]);
+  }
+  if (ALMOSTEQUAL(mx, -1.)) return -1;
+  if (nBGMElems > 1) insertionSort(Distance.data(), ListDistance.data(), nBGMElems);
+  for (int i = 0; i < nBGMElems; ++i) {
+    if (ALMOSTEQUAL(Distance[i], -1.)) continue;
+    const int ElemID = ListDistance[i];
+    bool dummy;
+    if (getPositionInRefElem(o, Pos3D, RefPos, ElemID, false, false, false, &dummy) != NEWTON_OK) return -2;
+    const double m = std::max(std::fabs(RefPos[0]), std::max(std::fabs(RefPos[1]), std::fabs(RefPos[2])));
+    if (m <= o.m.ElemEpsOneCell[ElemID - 1]) return ElemID;
+  }
+  return -1;
+}
+
 TrackResult singleParticleRefTracking(Oracle& o, double* PartState, double* LastPartPos, double* PartPosRef, int LastGlobalElemID,
-                                      int* GlobalElemID, bool* inside) {
+                                      int* GlobalElemID, bool* inside, bool* relocated) {
+  *relocated = false;
   int ElemID = LastGlobalElemID;
   bool PartIsDone = false, PartIsMoved = false;
   RefCtx c; c.PartState = PartState; c.LastPartPos = LastPartPos;
@@ -1301,8 +1482,16 @@ TrackResult singleParticleRefTracking(Oracle& o, double* PartState, double* Last
       bool dummy;
       if (getPositionInRefElem(o, PartState, PartPosRef, TestElem, false, false, false, &dummy) != NEWTON_OK) return TRACK_ERROR;
       if (maxabs(PartPosRef) > o.m.ElemEpsOneCell[TestElem - 1]) {
-        o.err = "ParticleRefTracking: tolerance issue with BC element (LocateParticleInElement fallback not restated)";
-        return TRACK_ERROR;
+        // LocateParticleInElement(iPart,doHALO=.TRUE.) (particle_localization.f90:47-74): new element, PartPosRef by Newton,
+        // PDM%isNewPart = .TRUE.; a particle that is found nowhere makes the reference abort (:385)
+        double RefPos[3];
+        const int found = singlePointToElementRef(o, PartState, RefPos);
+        if (found < 1) { o.err = "Particle not inside of Element (LocateParticleInElement found no element)"; return TRACK_ERROR; }
+        bool dummy2;
+        if (getPositionInRefElem(o, PartState, PartPosRef, found, false, false, false, &dummy2) != NEWTON_OK) return TRACK_ERROR;
+        *GlobalElemID = found;
+        *relocated = true;
+        return TRACK_OK;
       }
       *GlobalElemID = TestElem;
     }
@@ -1418,7 +1607,9 @@ static int push_track_range(Oracle& o, double dt, int64_t i0, int64_t i1, double
       if (!PartPosRef) { o.err = "RefMapping needs PartPosRef"; return 4; }
       int newElem = GlobalElemID[i];
       bool in = true;
-      TrackResult tr = singleParticleRefTracking(o, ps, lp, PartPosRef + 3 * i, LastGlobalElemID, &newElem, &in);
+      bool relocated = false;
+      TrackResult tr = singleParticleRefTracking(o, ps, lp, PartPosRef + 3 * i, LastGlobalElemID, &newElem, &in, &relocated);
+      if (relocated) IsNewPart[i] = 1;
       if (tr == TRACK_ERROR) return 3;
       if (tr == TRACK_REMOVED_BC) ParticleInside[i] = 0;
       else GlobalElemID[i] = newElem;

@@ -53,7 +53,7 @@ class pgpu_mesh_t(C.Structure):
         ("SideType", c_i32p), ("SideNormVec", c_f64p), ("SideDistance", c_f64p),
         ("BaseVectors0", c_f64p), ("BaseVectors1", c_f64p), ("BaseVectors2", c_f64p),
         ("BaseVectorsScale", c_f64p),
-        ("SFElemr2", c_f64p), ("ElemRadiusNGeo", c_f64p), ("ElemToBGM", c_i32p),
+        ("SFElemr2", c_f64p), ("ElemRadiusNGeo", c_f64p), ("ElemToBGM", c_i32p), ("BaseVectors3", c_f64p),
     ]
 
 
@@ -187,7 +187,8 @@ class Marshalled:
         for name, conv in (("ElemEpsOneCell", f64), ("ElemToBCSides", i32), ("SideBCMetrics", f64),
                            ("SideType", i32), ("SideNormVec", f64), ("SideDistance", f64),
                            ("BaseVectors0", f64), ("BaseVectors1", f64), ("BaseVectors2", f64),
-                           ("BaseVectorsScale", f64), ("SFElemr2", f64), ("ElemRadiusNGeo", f64), ("ElemToBGM", i32)):
+                           ("BaseVectorsScale", f64), ("SFElemr2", f64), ("ElemRadiusNGeo", f64), ("ElemToBGM", i32),
+                           ("BaseVectors3", f64)):
             if name in ex:
                 setattr(m, name, conv(ex[name]))
         if "SideBCMetrics" in ex:

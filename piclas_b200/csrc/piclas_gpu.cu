@@ -47,7 +47,8 @@ struct Ctx {
   RefTables refT;
   double* dXiB[3] = {nullptr, nullptr, nullptr};   // second PartPosRef buffer (RefMapping: PartPosRef is particle state)
   int32_t *dElemToBCSides = nullptr, *dSideInfo = nullptr;
-  double *dSideBCMetrics = nullptr, *dSideNormVec = nullptr, *dSideDistance = nullptr, *dBV0 = nullptr, *dBV1 = nullptr, *dBV2 = nullptr;
+  double *dSideBCMetrics = nullptr, *dSideNormVec = nullptr, *dSideDistance = nullptr, *dBV0 = nullptr, *dBV1 = nullptr, *dBV2 = nullptr, *dBV3 = nullptr;
+  int32_t* dSideType = nullptr;
   double *dElemRadius2 = nullptr, *dElemEpsOneCell = nullptr;
   // shape function
   bool sfActive = false;
@@ -501,7 +502,7 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dSfTarget); cudaFree(g.dSfRecvElem); cudaFree(g.dSfRecvOff); cudaFree(g.dSfRecvIdx); cudaFree(g.dSfRecv);
   cudaFree(g.dXiB[0]);
   cudaFree(g.dElemToBCSides); cudaFree(g.dSideInfo); cudaFree(g.dSideBCMetrics); cudaFree(g.dSideNormVec); cudaFree(g.dSideDistance);
-  cudaFree(g.dBV0); cudaFree(g.dBV1); cudaFree(g.dBV2); cudaFree(g.dElemRadius2); cudaFree(g.dElemEpsOneCell);
+  cudaFree(g.dBV0); cudaFree(g.dBV1); cudaFree(g.dBV2); cudaFree(g.dBV3); cudaFree(g.dSideType); cudaFree(g.dElemRadius2); cudaFree(g.dElemEpsOneCell);
   if (g.cap > 0) {
     free_partbuf(g.buf[0]);
     free_partbuf(g.buf[1]);
@@ -537,7 +538,10 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     for (int b = 0; b < m->nBCSidesTotal; ++b) {
       const int sid = (int)m->SideBCMetrics[(size_t)b * 7];
       if (sid < 1 || sid > m->nSides) return fail("piclas_gpu_init: SideBCMetrics holds an invalid side id");
-      if (m->SideType[sid - 1] != 0) return fail("piclas_gpu_init: BC side %d is not PLANAR_RECT (bilinear/curved intersections are not supported)", sid);
+      if (m->SideType[sid - 1] < 0 || m->SideType[sid - 1] > 2)
+        return fail("piclas_gpu_init: BC side %d is curved (only PLANAR_RECT, PLANAR_NONRECT and BILINEAR sides are supported)", sid);
+      if (m->SideType[sid - 1] != 0 && !m->BaseVectors3)
+        return fail("piclas_gpu_init: BC side %d is not PLANAR_RECT: BaseVectors3 is needed (ComputeBiLinearIntersection)", sid);
     }
   }
   const bool isSF = p->DepositionType == PGPU_DEPO_SF || p->DepositionType == PGPU_DEPO_SF_CC || p->DepositionType == PGPU_DEPO_SF_ADAPTIVE;
@@ -769,11 +773,14 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     if (upload(&g.dBV0, m->BaseVectors0, (size_t)m->nSides * 3)) return 1;
     if (upload(&g.dBV1, m->BaseVectors1, (size_t)m->nSides * 3)) return 1;
     if (upload(&g.dBV2, m->BaseVectors2, (size_t)m->nSides * 3)) return 1;
+    if (m->BaseVectors3 && upload(&g.dBV3, m->BaseVectors3, (size_t)m->nSides * 3)) return 1;
+    if (upload(&g.dSideType, m->SideType, (size_t)m->nSides)) return 1;
     if (upload(&g.dElemRadius2, m->ElemRadius2NGeo, (size_t)nG)) return 1;
     if (upload(&g.dElemEpsOneCell, m->ElemEpsOneCell, (size_t)nG)) return 1;
     g.refT.geo = g.dGeo; g.refT.ElemToBCSides = g.dElemToBCSides; g.refT.SideBCMetrics = g.dSideBCMetrics; g.refT.SideInfo = g.dSideInfo;
     g.refT.sideInfoSize = m->sideInfoSize; g.refT.SideNormVec = g.dSideNormVec; g.refT.SideDistance = g.dSideDistance;
-    g.refT.BaseVectors0 = g.dBV0; g.refT.BaseVectors1 = g.dBV1; g.refT.BaseVectors2 = g.dBV2; g.refT.ElemBary = g.dElemBary;
+    g.refT.BaseVectors0 = g.dBV0; g.refT.BaseVectors1 = g.dBV1; g.refT.BaseVectors2 = g.dBV2; g.refT.BaseVectors3 = g.dBV3;
+    g.refT.SideType = g.dSideType; g.refT.ElemBary = g.dElemBary;
     g.refT.ElemRadius = g.dElemRadius; g.refT.ElemRadius2 = g.dElemRadius2; g.refT.ElemEpsOneCell = g.dElemEpsOneCell;
     g.refT.FIBGM_nElems = g.dFibN; g.refT.FIBGM_offsetElem = g.dFibOff; g.refT.FIBGM_Element = g.dFibElem;
   }

@@ -3,7 +3,9 @@
 // Reference: ParticleRefTracking particle_reftracking.f90:30-414, ParticleBCTracking :417-694 (tail recursion -> loop),
 // ComputePlanarRectIntersection particle_intersection.f90:515-684, PARTHASMOVED particle_localization.f90:447-469,
 // GetBoundaryInteraction (REFMAPPING branch) + PeriodicBoundary particle_boundary_condition.f90:35-284,
-// InsertionSort utils.f90:52-101.  CartesianPeriodic = F; sides must be PLANAR_RECT (checked at init).
+// ComputeBiLinearIntersection :855-1240 (PLANAR_NONRECT and BILINEAR sides) with QuadraticSolver utils.f90:401-465,
+// CalcNormAndTangBilinear particle_surfaces.f90:404-440, LocateParticleInElement particle_localization.f90:47-190,
+// InsertionSort utils.f90:52-101.  CartesianPeriodic = F; curved sides (NGeo > 1) are rejected at init.
 // Arithmetic is in the reference's operation order (the unit is compiled with --fmad=false), so ownership and the
 // stored reference coordinates PartPosRef are bitwise equal to the CPU restatement.
 #pragma once
@@ -15,7 +17,8 @@ struct RefTables {
   const double* SideBCMetrics;    // [nBCSidesTotal][7]
   const int32_t* SideInfo;        // [nSides][sideInfoSize]
   int sideInfoSize;
-  const double *SideNormVec, *SideDistance, *BaseVectors0, *BaseVectors1, *BaseVectors2;
+  const double *SideNormVec, *SideDistance, *BaseVectors0, *BaseVectors1, *BaseVectors2, *BaseVectors3;
+  const int32_t* SideType;        // [nSides] 0 PLANAR_RECT, 1 PLANAR_NONRECT, 2 BILINEAR
   const double *ElemBary, *ElemRadius, *ElemRadius2, *ElemEpsOneCell;
   const int32_t *FIBGM_nElems, *FIBGM_offsetElem, *FIBGM_Element;
 };
@@ -23,6 +26,7 @@ struct RefTables {
 #define REF_MAX_HITS 16
 #define REF_MAX_BGM 32
 #define REF_ALMOSTZERO(x) (fabs(x) <= 2.22e-16)
+#define REF_ALMOSTEQUAL(x, y) (fabs((x) - (y)) <= fmax(fabs(x), fabs(y)) * 4.441e-16)
 
 __device__ __forceinline__ double maxabs3(const double v[3]) { return fmax(fabs(v[0]), fmax(fabs(v[1]), fabs(v[2]))); }
 
@@ -71,6 +75,107 @@ __device__ __forceinline__ double planar_rect_intersection(const RefTables& T, c
   return alpha;
 }
 
+// ComputeBiLinearIntersection (refmapping).  Returns alpha (-1: no intersection), xi/eta of the intersection; err is set when the
+// reference aborts ("Invalid intersection with bilinear side").  alpha2 <= -1: not given.
+__device__ __noinline__ double bilinear_intersection(const RefTables& T, const double traj[3], double len, const double lp[3], int SideID,
+                                                     double alpha2, double& xiOut, double& etaOut, bool& err) {
+  xiOut = -2.0; etaOut = -2.0;
+  const double* b0 = T.BaseVectors0 + (size_t)(SideID - 1) * 3;
+  const double* b1 = T.BaseVectors1 + (size_t)(SideID - 1) * 3;
+  const double* b2 = T.BaseVectors2 + (size_t)(SideID - 1) * 3;
+  const double* b3 = T.BaseVectors3 + (size_t)(SideID - 1) * 3;
+  double BC[4][3], NC[4][3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    BC[0][d] = 0.25 * b3[d];
+    BC[1][d] = 0.25 * b1[d];
+    BC[2][d] = 0.25 * b2[d];
+    BC[3][d] = 0.25 * b0[d];
+  }
+  const double* nv = T.SideNormVec + (size_t)(SideID - 1) * 3;
+  const double scaleFac = (traj[0] * nv[0] + traj[1] * nv[1]) + traj[2] * nv[2];
+  if (fabs(scaleFac) < 100. * EPSMACH) return -1.;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) BC[3][d] = BC[3][d] - lp[d];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const double sp = (BC[c][0] * traj[0] + BC[c][1] * traj[1]) + BC[c][2] * traj[2];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) NC[c][d] = BC[c][d] - sp * traj[d];
+  }
+  double A1[4], A2[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { A1[c] = NC[c][2] - NC[c][0]; A2[c] = NC[c][2] - NC[c][1]; }
+  const double A = A1[0] * A2[2] - A2[0] * A1[2];
+  const double B = A1[0] * A2[3] - A2[0] * A1[3] + A1[1] * A2[2] - A2[1] * A1[2];
+  const double C = A1[1] * A2[3] - A2[1] * A1[3];
+  // QuadraticSolver
+  int nRoot;
+  double eta[2] = {0., 0.}, xi[2] = {0., 0.}, t[2] = {-1., -1.};
+  if (A != 0. && B == 0. && C == 0.) nRoot = 1;
+  else if (A != 0.) {
+    const double radicant = (0.5 * B / A) * (0.5 * B / A) - (C / A);
+    if (radicant < 0.) nRoot = 0;
+    else {
+      nRoot = 2;
+      eta[0] = -0.5 * (B / A) - copysign(1., B / A) * sqrt(radicant);
+      eta[1] = (C / A) / eta[0];
+    }
+  } else if (B != 0.) { nRoot = 1; eta[0] = -C / B; }
+  else nRoot = 0;
+  if (nRoot == 0) return -1.;
+  int InterType = 0;
+  for (int r = 0; r < nRoot; ++r) {
+    if (!(fabs(eta[r]) <= 1.0)) continue;
+    {  // ComputeXi
+      const double a = eta[r] * A2[0] + A2[1];
+      const double b = eta[r] * (A2[0] - A1[0]) + A2[1] - A1[1];
+      if (fabs(b) >= fabs(a)) {
+        if (REF_ALMOSTZERO(fabs(b))) { err = true; return -1.; }
+        xi[r] = (-eta[r] * (A2[2] - A1[2]) - (A2[3] - A1[3])) / b;
+      } else {
+        xi[r] = (-eta[r] * A2[2] - A2[3]) / a;
+      }
+    }
+    if (!(fabs(xi[r]) <= 1.0)) continue;
+    double tt = 0.;   // ComputeSurfaceDistance2
+#pragma unroll
+    for (int d = 0; d < 3; ++d) tt = tt + (xi[r] * eta[r] * BC[0][d] + xi[r] * BC[1][d] + eta[r] * BC[2][d] + BC[3][d]) * traj[d];
+    t[r] = tt;
+    if (alpha2 > -1.0 && REF_ALMOSTEQUAL(t[r], alpha2)) t[r] = -1.0;
+    const double alphaNorm = t[r] / len;
+    if (alphaNorm <= 1.0 && alphaNorm >= 0.) InterType += r + 1;
+  }
+  if (InterType == 0) return -1.;
+  int k = (InterType == 2) ? 1 : 0;
+  if (InterType == 3) {
+    const int32_t* si = T.SideInfo + (size_t)(SideID - 1) * T.sideInfoSize;
+    if (si[4] > 0) k = (t[0] < t[1]) ? 0 : 1;   // the first of the two intersections
+    else { xiOut = 0.; etaOut = 0.; return -1.; }
+  }
+  xiOut = xi[k];
+  etaOut = eta[k];
+  return t[k];
+}
+
+// CalcNormAndTangBilinear (nVec), oriented like SideNormVec (out of the master element)
+__device__ __forceinline__ void bilinear_normal(const RefTables& T, double xi, double eta, int SideID, double n[3]) {
+  const double* b1 = T.BaseVectors1 + (size_t)(SideID - 1) * 3;
+  const double* b2 = T.BaseVectors2 + (size_t)(SideID - 1) * 3;
+  const double* b3 = T.BaseVectors3 + (size_t)(SideID - 1) * 3;
+  double a[3], b[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    b[d] = xi * 0.25 * b3[d] + 0.25 * b2[d];
+    a[d] = eta * 0.25 * b3[d] + 0.25 * b1[d];
+  }
+  const double c0 = a[1] * b[2] - a[2] * b[1], c1 = a[2] * b[0] - a[0] * b[2], c2 = a[0] * b[1] - a[1] * b[0];
+  const double l = sqrt((c0 * c0 + c1 * c1) + c2 * c2);
+  n[0] = c0 / l; n[1] = c1 / l; n[2] = c2 / l;
+  const double* nv = T.SideNormVec + (size_t)(SideID - 1) * 3;
+  if ((n[0] * nv[0] + n[1] * nv[1]) + n[2] * nv[2] < 0.) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+}
+
 // ParticleBCTracking.  status: TRK_OK (continue with the Newton check of the caller unless done), TRK_REMOVED, TRK_ERR_*
 // done = PartisDone.  ElemID in/out.
 __device__ int bc_tracking(const RefTables& T, double x[3], double lp[3], int& ElemID, bool& done, int& outElem) {
@@ -89,21 +194,30 @@ __device__ int bc_tracking(const RefTables& T, double x[3], double lp[3], int& E
     traj[0] = traj[0] / len; traj[1] = traj[1] / len; traj[2] = traj[2] / len;
     len0 = fmax(len0, len);
     bool doTracing = true, doubleCheck = false, recurse = false;
+    double alphaOld = -1.0;
     while (doTracing) {
       // hits in visiting order; the reference sorts (alpha, side) of all listed sides with a stable insertion sort and walks the
       // entries with alpha > -1: sorting the hits alone gives the same sequence
-      double hitAlpha[REF_MAX_HITS];
+      double hitAlpha[REF_MAX_HITS], hitXi[REF_MAX_HITS], hitEta[REF_MAX_HITS];
       int hitSide[REF_MAX_HITS];
       int nInter = 0;
       for (int il = 0; il < nloc; ++il) {
         const double* bm = T.SideBCMetrics + (size_t)(first + il) * 7;
         if (bm[2] > len0) break;
         const int SideID = (int)bm[0];
-        const double a = planar_rect_intersection(T, traj, len, lp, side_flip(T, SideID), SideID);
+        double a, hx = -2., he = -2.;
+        if (T.SideType[SideID - 1] == 0) a = planar_rect_intersection(T, traj, len, lp, side_flip(T, SideID), SideID);
+        else {   // PLANAR_NONRECT, BILINEAR; the double check excludes the intersection found before (alpha2 = alphaOld)
+          bool err = false;
+          a = bilinear_intersection(T, traj, len, lp, SideID, doubleCheck ? alphaOld : -2., hx, he, err);
+          if (err) return TRK_ERR_ELEM;
+        }
         if (a > -1.0) {
           if (nInter >= REF_MAX_HITS) return TRK_ERR_LOOP;
           hitAlpha[nInter] = a;
           hitSide[nInter] = SideID;
+          hitXi[nInter] = hx;
+          hitEta[nInter] = he;
           ++nInter;
         }
       }
@@ -112,17 +226,22 @@ __device__ int bc_tracking(const RefTables& T, double x[3], double lp[3], int& E
       } else {
         for (int i = 1; i < nInter; ++i) {  // InsertionSort
           int j = i - 1;
-          const double tr = hitAlpha[i];
+          const double tr = hitAlpha[i], tx = hitXi[i], te = hitEta[i];
           const int ti = hitSide[i];
           while (j >= 0) {
             if (hitAlpha[j] <= tr) break;
             hitAlpha[j + 1] = hitAlpha[j];
             hitSide[j + 1] = hitSide[j];
+            hitXi[j + 1] = hitXi[j];
+            hitEta[j + 1] = hitEta[j];
             --j;
           }
           hitAlpha[j + 1] = tr;
           hitSide[j + 1] = ti;
+          hitXi[j + 1] = tx;
+          hitEta[j + 1] = te;
         }
+        alphaOld = hitAlpha[0];
         bool reflected = false;
         for (int ih = 0; ih < nInter; ++ih) {
           const int SideID = hitSide[ih];
@@ -131,6 +250,11 @@ __device__ int bc_tracking(const RefTables& T, double x[3], double lp[3], int& E
           const double alpha = hitAlpha[ih];
           const double* nv = T.SideNormVec + (size_t)(SideID - 1) * 3;
           double n0 = nv[0], n1 = nv[1], n2 = nv[2];
+          if (T.SideType[SideID - 1] == 2) {   // BILINEAR: normal at the intersection point
+            double nb[3];
+            bilinear_normal(T, hitXi[ih], hitEta[ih], SideID, nb);
+            n0 = nb[0]; n1 = nb[1]; n2 = nb[2];
+          }
           if (flip != 0) { n0 = -n0; n1 = -n1; n2 = -n2; }
           reflected = false;
           if (!(((n0 * traj[0] + n1 * traj[1]) + n2 * traj[2]) <= 0.)) {
@@ -182,7 +306,9 @@ __device__ __forceinline__ void ref_newton(const RefTables& T, const double x[3]
 }
 
 // ParticleRefTracking for one particle: x pushed position, lp LastPartPos, xi PartPosRef (in: old, out: new), elem in/out
-__device__ int ref_tracking(const RefTables& T, double x[3], double lp[3], double xi[3], int& elem) {
+// relocated: the LocateParticleInElement fallback found the element (the reference then sets PDM%isNewPart)
+__device__ int ref_tracking(const RefTables& T, double x[3], double lp[3], double xi[3], int& elem, bool& relocated) {
+  relocated = false;
   const int LastElem = elem;
   int ElemID = LastElem;
   bool done = false;
@@ -267,7 +393,53 @@ __device__ int ref_tracking(const RefTables& T, double x[3], double lp[3], doubl
     if (st != TRK_OK) return st;
     if (done) { elem = outElem; return TRK_OK; }
     ref_newton(T, x, xi, Test);
-    if (maxabs3(xi) > T.ElemEpsOneCell[Test - 1]) return TRK_ERR_ELEM;    // LocateParticleInElement fallback not built
+    if (maxabs3(xi) > T.ElemEpsOneCell[Test - 1]) {
+      // LocateParticleInElement(doHALO = T) -> SinglePointToElement: cell by CEILING, all elements of the cell whose radius reaches
+      // the particle, nearest barycentre first, accepted with MAXVAL(ABS(xi)) <= ElemEpsOneCell
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        Cell[d] = (int)ceil((x[d] - cst.xyzminglob[d]) / cst.FIBGMdeltas[d]);
+        Cell[d] = max(min(cst.FIBGMmax[d], Cell[d]), cst.FIBGMmin[d]);
+      }
+      const size_t cell2 = (size_t)(Cell[0] - cst.FIBGMmin[0]) + (size_t)ni * ((size_t)(Cell[1] - cst.FIBGMmin[1]) + (size_t)nj * (size_t)(Cell[2] - cst.FIBGMmin[2]));
+      const int nB = T.FIBGM_nElems[cell2];
+      if (nB > REF_MAX_BGM) return TRK_ERR_LOOP;
+      double mx = -1.;
+      for (int i = 0; i < nB; ++i) {
+        const int e = T.FIBGM_Element[T.FIBGM_offsetElem[cell2] + i];
+        const double* b = T.ElemBary + (size_t)(e - 1) * 3;
+        const double d0 = x[0] - b[0], d1 = x[1] - b[1], d2 = x[2] - b[2];
+        const double D2 = (d0 * d0 + d1 * d1) + d2 * d2;
+        Distance[i] = (D2 <= T.ElemRadius2[e - 1]) ? D2 : -1.;
+        List[i] = e;
+        mx = fmax(mx, Distance[i]);
+      }
+      if (nB < 1 || REF_ALMOSTEQUAL(mx, -1.)) return TRK_ERR_ELEM;   // 'Particle not inside of Element'
+      for (int i = 1; i < nB; ++i) {  // InsertionSort
+        int j = i - 1;
+        const double tr = Distance[i];
+        const int ti = List[i];
+        while (j >= 0) {
+          if (Distance[j] <= tr) break;
+          Distance[j + 1] = Distance[j];
+          List[j + 1] = List[j];
+          --j;
+        }
+        Distance[j + 1] = tr;
+        List[j + 1] = ti;
+      }
+      int found = -1;
+      for (int i = 0; i < nB; ++i) {
+        if (REF_ALMOSTEQUAL(Distance[i], -1.)) continue;
+        ref_newton(T, x, xi, List[i]);
+        if (maxabs3(xi) <= T.ElemEpsOneCell[List[i] - 1]) { found = List[i]; break; }
+      }
+      if (found < 1) return TRK_ERR_ELEM;
+      ref_newton(T, x, xi, found);
+      elem = found;
+      relocated = true;
+      return TRK_OK;
+    }
     elem = Test;
   }
   return TRK_OK;
@@ -283,7 +455,9 @@ __global__ void __launch_bounds__(128) k_track_ref(PartBuf pb, const double* __r
     double lp[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};
     double xi[3] = {pb.xi[0][p], pb.xi[1][p], pb.xi[2][p]};
     int elem = pb.elem[p];
-    const int status = ref_tracking(T, x, lp, xi, elem);
+    bool relocated = false;
+    const int status = ref_tracking(T, x, lp, xi, elem, relocated);
+    if (relocated) pb.meta[p] = pb.meta[p] | META_ISNEW;
     uint32_t key;
     if (status == TRK_OK) {
       const int rk = elemRank[elem - 1];

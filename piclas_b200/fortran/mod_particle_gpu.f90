@@ -30,7 +30,7 @@ TYPE, BIND(C) :: pgpu_mesh_t            ! field order == include/piclas_gpu.h
   TYPE(C_PTR) :: ElemEpsOneCell, ElemToBCSides, SideBCMetrics
   INTEGER(C_INT32_T) :: nBCSidesTotal
   TYPE(C_PTR) :: SideType, SideNormVec, SideDistance, BaseVectors0, BaseVectors1, BaseVectors2, BaseVectorsScale
-  TYPE(C_PTR) :: SFElemr2, ElemRadiusNGeo, ElemToBGM
+  TYPE(C_PTR) :: SFElemr2, ElemRadiusNGeo, ElemToBGM, BaseVectors3
 END TYPE
 
 TYPE, BIND(C) :: pgpu_params_t

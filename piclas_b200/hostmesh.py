@@ -448,7 +448,10 @@ def from_hopr_arrays(ElemInfo, SideInfo, NodeCoords, GlobalNodeIDs, BCType, BCNa
             v = cen[nb] - cen[sd]
             if np.abs(v - v[0]).max() > 1e-10 * max(1.0, np.abs(v).max()):
                 raise ValueError("periodic sides of vector %d are not congruent" % k)
-            PV[k - 1] = np.where(np.abs(v[0]) > 1e-12 * np.abs(v[0]).max(), v[0], 0.0)   # centroid means carry rounding fuzz
+            # exact offset between stored node coordinates (the centroid means carry rounding fuzz): the partner-side node
+            # that matches the first node of the side
+            cand = coords[fn[nb[0]]] - coords[fn[sd[0], 0]]
+            PV[k - 1] = cand[np.argmin(np.linalg.norm(cand - v[0], axis=1))]
     return build_mesh(coords, elem_nodes, N, bcs, None, periodic_vectors=PV, tracking=tracking, hopr_sides=SI)
 
 
@@ -633,6 +636,7 @@ def add_refmapping_tables(mesh: ParticleMesh, bc_halo_eps=None, RefMappingEps=1e
     BV0 = (+p00 + p10 + p01 + p11)
     BV1 = (-p00 + p10 - p01 + p11)
     BV2 = (-p00 - p10 + p01 + p11)
+    BV3 = (+p00 - p10 - p01 + p11)
     cr = np.cross(BV1, BV2)
     nrm = cr / np.sqrt((cr * cr).sum(axis=1))[:, None]                   # CROSSNORM(v1,v2)
     centre = 0.25 * (p00 + p10 + p01 + p11)
@@ -706,7 +710,7 @@ def add_refmapping_tables(mesh: ParticleMesh, bc_halo_eps=None, RefMappingEps=1e
     sJ = mesh.sJ.reshape(nE, -1)
     scaleJ = sJ.max(axis=1) / sJ.min(axis=1)
     mesh.extra.update(dict(BaseVectors0=np.ascontiguousarray(BV0), BaseVectors1=np.ascontiguousarray(BV1),
-                           BaseVectors2=np.ascontiguousarray(BV2), SideNormVec=np.ascontiguousarray(SideNormVec),
+                           BaseVectors2=np.ascontiguousarray(BV2), BaseVectors3=np.ascontiguousarray(BV3), SideNormVec=np.ascontiguousarray(SideNormVec),
                            SideDistance=np.ascontiguousarray(SideDistance), SideType=SideType,
                            ElemToBCSides=ElemToBCSides, SideBCMetrics=np.ascontiguousarray(SideBCMetrics),
                            ElemEpsOneCell=1.0 + np.sqrt(3.0 * scaleJ * RefMappingEps),

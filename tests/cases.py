@@ -108,6 +108,20 @@ def wavy(amplitude, lo, hi):
     return f
 
 
+def wavy_periodic(amplitude, lo, hi):
+    """Deformation that does NOT vanish on the boundary but is periodic: the x-faces become congruent bilinear patches, the y- and
+    z-faces planar non-rectangular (RefMapping: ComputeBiLinearIntersection for BILINEAR and PLANAR_NONRECT BC sides)."""
+    lo = np.asarray(lo, float)
+    hi = np.asarray(hi, float)
+
+    def f(c):
+        s = 2.0 * np.pi * (c - lo) / (hi - lo)
+        out = c.copy()
+        out[:, 0] += amplitude * (hi[0] - lo[0]) * np.cos(s[:, 1]) * np.cos(s[:, 2])
+        return out
+    return f
+
+
 def uniform_plasma(mesh, n, seed, vth_cells=0.2, dt=1.0, species=1, nspecies=1):
     """Uniform positions, Maxwellian velocities with sigma*dt = vth_cells * h (SURVEY.md §8d synthetic input)."""
     rng = np.random.default_rng(seed)

@@ -41,7 +41,8 @@ def main():
     dnodes = dm.read("NodeCoords").reshape(-1, 8, 3)     # (2, 8, 3) tensor-ordered corner nodes of the two elements
     # the two HOPR mesh files themselves (datasets hostmesh.from_hopr_arrays consumes)
     meshes = {}
-    for tag, f in (("box", me), ("deformed", dm)):
+    tw = H5File("/root/reference/tutorials/pic-poisson-plasma-wave/plasma_wave_mesh.h5")
+    for tag, f in (("box", me), ("deformed", dm), ("plasma_wave", tw)):
         for ds in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames"):
             meshes[tag + "_" + ds] = f.read(ds)
     mout = os.path.join(HERE, "hopr_meshes.npz")

@@ -14,11 +14,15 @@ from test_gpu_refmapping import run_ref_parity
 pytestmark = pytest.mark.gpu
 
 
-def test_config1_plasma_wave_tutorial():
-    """tutorials/pic-poisson-plasma-wave: 60x1x1, [0,6.2831]x[-0.1,0.1]^2... N=5, refmapping, shape_function_adaptive 1-D x,
-    alpha=4, adaptive-DOF=10, 400 electrons + 400 ions (sin_deviation), dt=5e-10."""
+def plasma_wave_case():
+    """tutorials/pic-poisson-plasma-wave with the tutorial's own mesh file (datasets of plasma_wave_mesh.h5 in
+    tests/golden/hopr_meshes.npz): 60x1x1 elements on [0,6.2831]x[0,0.2]^2, N=5, refmapping, shape_function_adaptive 1-D x,
+    alpha=4, adaptive-DOF=10, 400 electrons (sin_deviation, amplitude 0.01, wave number 2) + 400 ions, dt=5e-10."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hopr_meshes.npz"))
+    mesh = hm.from_hopr_arrays(*[g["plasma_wave_" + d] for d in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames")],
+                               5, tracking=hm.REFMAPPING)
     Lx = 6.2831
-    mesh = hm.box_mesh([0, -0.1, -0.1], [Lx, 0.1, 0.1], (60, 1, 1), 5, tracking=hm.REFMAPPING)
     hm.add_fibgm(mesh, deltas=(Lx, 0.2, 0.2), factor=(60, 1, 1))
     hm.add_refmapping_tables(mesh)
     prm = Params(TrackingMethod=hm.REFMAPPING, DepositionType=DEPO_SF_ADAPTIVE, TimeDiscMethod=TIMEDISC_BORIS_LEAPFROG,
@@ -26,13 +30,23 @@ def test_config1_plasma_wave_tutorial():
                  carryParticleIDs=1)
     hm.shape_function_adaptive_setup(mesh, prm, 4, dim_sf=1, dim_sf_dir=1, sfDepo3D=True, SFAdaptiveDOF=10)
     n = 400
+    # SetParticlePositionSinDeviation (particle_emission_tools.f90): x_i = (i - 0.5) L / n + A sin(k 2 pi x_i / L), y = z = mid
     xs = (np.arange(n) + 0.5) * Lx / n
-    xe = xs + 0.1 * np.sin(2 * np.pi * xs / Lx) * Lx / (2 * np.pi) * 0.4     # sin_deviation-like displaced electrons
+    xe = xs + 0.01 * np.sin(2.0 * 2.0 * np.pi * xs / Lx)
     PS = np.zeros((2 * n, 6))
     PS[:n, 0] = np.mod(xe, Lx)
     PS[n:, 0] = xs
+    PS[:, 1:3] = 0.1
     spec = np.concatenate([np.ones(n), 2 * np.ones(n)]).astype(np.int32)
-    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    return mesh, prm, PS, spec
+
+
+def test_config1_plasma_wave_tutorial():
+    mesh, prm, PS, spec = plasma_wave_case()
+    orc = Oracle(mesh, prm)
+    elem = orc.locate(PS[:, :3])
+    orc.close()
+    assert (elem > 0).all()
     E = cases.smooth_field(mesh, 5.0)
     run_ref_parity(mesh, prm, PS, spec, elem, E, 5e-10, nsteps=6)
 

@@ -89,3 +89,27 @@ def test_refmapping_deformed_mesh(arith):
     assert (elem > 0).all()
     E = cases.smooth_field(mesh, 1e-4)
     run_ref_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=4)
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+def test_refmapping_bilinear_and_nonrect_bc_sides(arith):
+    """Periodic mesh with a deformed boundary: BILINEAR x-faces and PLANAR_NONRECT y-/z-faces are crossed through
+    ComputeBiLinearIntersection with the bilinear side normal; the fastest particles take the LocateParticleInElement fallback
+    (and come back with IsNewPart set).  Shape-function deposition on the same mesh."""
+    lo, hi = [0, 0, 0], [1, 1, 1]
+    mesh = hm.box_mesh(lo, hi, (4, 4, 3), 2, tracking=hm.REFMAPPING, deform=cases.wavy_periodic(0.04, lo, hi))
+    hm.add_fibgm(mesh)
+    hm.add_refmapping_tables(mesh)
+    prm = cases.electron_params(TrackingMethod=hm.REFMAPPING, DepositionType=DEPO_SF, MacroParticleFactor=(1e9,), arithmetic=arith)
+    hm.shape_function_setup(mesh, prm, 0.25, 2, dim_sf=3)
+    n, dt = 6000, 1e-8
+    rng = np.random.default_rng(2)
+    el = rng.integers(1, mesh.nElems + 1, n).astype(np.int32)
+    xi = rng.uniform(-0.999, 0.999, (n, 3))
+    w = lambda t: np.stack([(1 - t) / 2, (1 + t) / 2], -1)
+    W = np.einsum("nk,nj,ni->nkji", w(xi[:, 2]), w(xi[:, 1]), w(xi[:, 0]))
+    x = np.einsum("nkji,nkjix->nx", W, mesh.XCL_NGeo[el - 1])
+    PS = np.ascontiguousarray(np.concatenate([x, rng.normal(0, 0.25 / dt, (n, 3))], axis=1))
+    spec = np.ones(n, dtype=np.int32)
+    E = cases.smooth_field(mesh, 1e-4)
+    run_ref_parity(mesh, prm, PS, spec, el, E, dt, nsteps=6)
