@@ -47,7 +47,7 @@ extern "C" {
 
 /* PartBound%TargetBoundCond, particle_boundary_condition.f90:167-214 */
 #define PGPU_BC_OPEN        1
-#define PGPU_BC_REFLECTIVE  2   /* specular wall at rest (MomentumACC = 0, WallVelo = 0), TriaTracking only */
+#define PGPU_BC_REFLECTIVE  2   /* specular wall at rest (MomentumACC = 0, WallVelo = 0) */
 #define PGPU_BC_PERIODIC    3
 
 /* ---- mesh + basis tables (built once by InitParticleMesh / InitializeDeposition) ----------------------

@@ -1335,6 +1335,7 @@ int particleBCTracking(Oracle& o, double lengthPartTrajectory0, int* ElemID, Ref
               const int BCType = o.m.bc_kind[o.SideInfo(SIDE_BCID, SideID) - 1];
               if (BCType == PGPU_BC_OPEN) c.inside = false;
               else if (BCType == PGPU_BC_PERIODIC) periodicBoundary(o, c.PartState, c.LastPartPos, ti, SideID, ElemID);
+              else if (BCType == PGPU_BC_REFLECTIVE) perfectReflection(c.PartState, c.LastPartPos, ti, n_loc);   // specular wall at rest
               else { o.err = "ParticleBCTracking: boundary condition type not supported"; return 5; }
             }
             for (int d = 0; d < 3; ++d) PartTrajectory[d] = ti.PartTrajectory[d];

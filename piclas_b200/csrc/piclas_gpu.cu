@@ -566,8 +566,6 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   if (m->elemInfoSize < 7 || m->sideInfoSize < 8) return fail("piclas_gpu_init: ElemInfo/SideInfo leading dimension too small");
   if (p->nRanks < 1 || p->myRank < 0 || p->myRank >= p->nRanks) return fail("piclas_gpu_init: bad rank layout");
   for (int b = 0; b < m->nBCs; ++b) {
-    if (m->bc_kind[b] == PGPU_BC_REFLECTIVE && p->TrackingMethod != PGPU_TRIATRACKING)
-      return fail("piclas_gpu_init: boundary %d is reflective; reflective walls are implemented for TrackingMethod=triatracking only", b + 1);
     if (m->bc_kind[b] != PGPU_BC_OPEN && m->bc_kind[b] != PGPU_BC_PERIODIC && m->bc_kind[b] != PGPU_BC_REFLECTIVE)
       return fail("piclas_gpu_init: boundary %d has TargetBoundCond=%d; only open (1), reflective (2, specular) and periodic (3) are supported", b + 1, m->bc_kind[b]);
   }

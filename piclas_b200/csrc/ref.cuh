@@ -178,7 +178,8 @@ __device__ __forceinline__ void bilinear_normal(const RefTables& T, double xi, d
 
 // ParticleBCTracking.  status: TRK_OK (continue with the Newton check of the caller unless done), TRK_REMOVED, TRK_ERR_*
 // done = PartisDone.  ElemID in/out.
-__device__ int bc_tracking(const RefTables& T, double x[3], double lp[3], int& ElemID, bool& done, int& outElem) {
+__device__ int bc_tracking(const RefTables& T, const PartBuf& pb, int64_t p, double x[3], double lp[3], int& ElemID, bool& done,
+                           int& outElem) {
   double len0 = 0.;
   done = false;
   for (int iCount = 0; iCount < 100000; ++iCount) {
@@ -263,6 +264,25 @@ __device__ int bc_tracking(const RefTables& T, double x[3], double lp[3], int& E
             const int bc = si[4];
             const int kind = cst.bc_kind[bc - 1];
             if (kind == PGPU_BC_OPEN) return TRK_REMOVED;
+            if (kind == PGPU_BC_REFLECTIVE) {
+              // PerfectReflection (surfacemodel_tools.f90:81-256), wall at rest: mirrored velocity and trajectory, the rest of the
+              // flight from the point of impact; the particle stays in ElemID and the side loop starts again
+              const double nn[3] = {n0, n1, n2};
+              double v[3] = {pb.v[0][p], pb.v[1][p], pb.v[2][p]};
+              const double vn = (v[0] * nn[0] + v[1] * nn[1]) + v[2] * nn[2];
+              const double tn = (traj[0] * nn[0] + traj[1] * nn[1]) + traj[2] * nn[2];
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                pb.v[d][p] = v[d] - 2. * vn * nn[d];
+                lp[d] = lp[d] + traj[d] * alpha;
+                traj[d] = traj[d] - 2. * tn * nn[d];
+                x[d] = lp[d] + traj[d] * (len - alpha);
+                traj[d] = x[d] - lp[d];
+              }
+              len = sqrt((traj[0] * traj[0] + traj[1] * traj[1]) + traj[2] * traj[2]);
+              if (REF_ALMOSTZERO(len)) len = 0.0;
+              else { traj[0] = traj[0] / len; traj[1] = traj[1] / len; traj[2] = traj[2] / len; }
+            } else {
             if (kind != PGPU_BC_PERIODIC) return TRK_ERR_BC;
             const int pvid = cst.bc_alpha[bc - 1];
             const int pv = (pvid < 0 ? -pvid : pvid) - 1;
@@ -274,6 +294,7 @@ __device__ int bc_tracking(const RefTables& T, double x[3], double lp[3], int& E
             }
             len = len - alpha;
             ElemID = si[2];  // SIDE_NBELEMID
+            }
           }
           if (ElemID != OldElemID) {
             if (cst.nPeriodicVectors > 0) {
@@ -307,14 +328,15 @@ __device__ __forceinline__ void ref_newton(const RefTables& T, const double x[3]
 
 // ParticleRefTracking for one particle: x pushed position, lp LastPartPos, xi PartPosRef (in: old, out: new), elem in/out
 // relocated: the LocateParticleInElement fallback found the element (the reference then sets PDM%isNewPart)
-__device__ int ref_tracking(const RefTables& T, double x[3], double lp[3], double xi[3], int& elem, bool& relocated) {
+__device__ int ref_tracking(const RefTables& T, const PartBuf& pb, int64_t p, double x[3], double lp[3], double xi[3], int& elem,
+                            bool& relocated) {
   relocated = false;
   const int LastElem = elem;
   int ElemID = LastElem;
   bool done = false;
   if (T.ElemToBCSides[(size_t)(ElemID - 1) * 2] > 0) {
     int outElem = ElemID;
-    const int st = bc_tracking(T, x, lp, ElemID, done, outElem);
+    const int st = bc_tracking(T, pb, p, x, lp, ElemID, done, outElem);
     if (st != TRK_OK) return st;
     if (done) { elem = outElem; return TRK_OK; }
     ref_newton(T, x, xi, ElemID);
@@ -389,7 +411,7 @@ __device__ int ref_tracking(const RefTables& T, double x[3], double lp[3], doubl
   if (maxabs3(xi) > T.ElemEpsOneCell[Test - 1]) {
     if (T.ElemToBCSides[(size_t)(Test - 1) * 2] <= 0) return TRK_ERR_ELEM;  // tolerance issue with internal element: abort
     int outElem = Test;
-    const int st = bc_tracking(T, x, lp, Test, done, outElem);
+    const int st = bc_tracking(T, pb, p, x, lp, Test, done, outElem);
     if (st != TRK_OK) return st;
     if (done) { elem = outElem; return TRK_OK; }
     ref_newton(T, x, xi, Test);
@@ -456,7 +478,7 @@ __global__ void __launch_bounds__(128) k_track_ref(PartBuf pb, const double* __r
     double xi[3] = {pb.xi[0][p], pb.xi[1][p], pb.xi[2][p]};
     int elem = pb.elem[p];
     bool relocated = false;
-    const int status = ref_tracking(T, x, lp, xi, elem, relocated);
+    const int status = ref_tracking(T, pb, p, x, lp, xi, elem, relocated);
     if (relocated) pb.meta[p] = pb.meta[p] | META_ISNEW;
     uint32_t key;
     if (status == TRK_OK) {

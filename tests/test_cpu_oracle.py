@@ -211,11 +211,17 @@ def test_open_boundary_removes_and_counts_nothing_lost():
     assert lost == 0 and np.array_equal(inside == 0, out)
 
 
-def test_reflective_walls_fold_the_free_flight():
+@pytest.mark.parametrize("tracking", ["tria", "ref"])
+def test_reflective_walls_fold_the_free_flight(tracking):
     """Specular walls at rest (PerfectReflection): without a field the flight in a box is the folded straight line, speeds are
-    conserved and nobody leaves; several reflections per step and corner hits included."""
-    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (3, 2, 4), 1, periodic=(False, False, False), wall_kind=hm.BC_REFLECTIVE)
-    o = Oracle(mesh, cases.electron_params(DoInterpolation=0, DoDeposition=0))
+    conserved and nobody leaves; several reflections per step and corner hits included.  Both tracking methods."""
+    ref = tracking == "ref"
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (3, 2, 4), 1, periodic=(False, False, False), wall_kind=hm.BC_REFLECTIVE,
+                       tracking=hm.REFMAPPING if ref else hm.TRIATRACKING)
+    if ref:
+        hm.add_fibgm(mesh)
+        hm.add_refmapping_tables(mesh)
+    o = Oracle(mesh, cases.electron_params(DoInterpolation=0, DoDeposition=0, TrackingMethod=mesh.tracking))
     n = 3000
     rng = np.random.default_rng(21)
     x0 = rng.uniform(0.02, 0.98, (n, 3))
@@ -225,9 +231,10 @@ def test_reflective_walls_fold_the_free_flight():
     el = hm.cartesian_locate(mesh, x0)
     inside = np.ones(n, dtype=np.int32)
     E = np.zeros((mesh.nElems, 2, 2, 2, 3))
+    xi = o.position_in_ref_elem(x0, el, force=False)[0] if ref else None
     t = 0.0
     for _ in range(3):
-        lost, _, _ = o.push_track(1.0, PS, spec, el, inside, np.zeros(n, dtype=np.int32), E)
+        lost, _, _ = o.push_track(1.0, PS, spec, el, inside, np.zeros(n, dtype=np.int32), E, PartPosRef=xi)
         t += 1.0
         assert lost == 0 and inside.all()
         y = np.mod(x0 + v0 * t, 2.0)

@@ -113,3 +113,19 @@ def test_refmapping_bilinear_and_nonrect_bc_sides(arith):
     spec = np.ones(n, dtype=np.int32)
     E = cases.smooth_field(mesh, 1e-4)
     run_ref_parity(mesh, prm, PS, spec, el, E, dt, nsteps=6)
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+def test_refmapping_reflective_walls(arith):
+    """Specular walls with RefMapping (GetBoundaryInteraction case 2 -> PerfectReflection in ParticleBCTracking): mirrored
+    velocities, several wall hits per step, one periodic direction."""
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 3, 5), 2, tracking=hm.REFMAPPING, periodic=(False, True, False),
+                       wall_kind=hm.BC_REFLECTIVE)
+    hm.add_fibgm(mesh)
+    hm.add_refmapping_tables(mesh)
+    prm = cases.electron_params(TrackingMethod=hm.REFMAPPING, DepositionType=DEPO_SF, DoDeposition=0, arithmetic=arith)
+    dt = 1e-8
+    PS, spec = cases.uniform_plasma(mesh, 12000, seed=43, vth_cells=0.8, dt=dt)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    E = cases.smooth_field(mesh, 2e-4)
+    run_ref_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=5, deposit=False)
