@@ -296,6 +296,26 @@ def test_hopr_mesh_file_in_its_own_element_order_reproduces_dg_source():
     assert np.abs(mesh.NodeVolume - nv[key(mesh.unique_coords)]).max() < 1e-15
 
 
+@pytest.mark.parametrize("tag", ["box", "deformed", "plasma_wave"])
+def test_generated_meshes_use_hoprs_flip_convention(tag):
+    """hostmesh.build_mesh derives master / slave flips geometrically ("the slave's node that coincides with the master's first
+    node"); on the reference's mesh files that rule must reproduce the flip digit HOPR stored for every slave side."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hopr_meshes.npz"))
+    EI, SI, NC, G = [g[tag + "_" + d] for d in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs")]
+    nE = len(EI)
+    _, first, inv = np.unique(G, return_index=True, return_inverse=True)
+    coords = NC[first]
+    fn = inv.reshape(nE, 8)[:, hm._CNS0][:, hm._NODEMAP_CGNS0].reshape(6 * nE, 4)
+    S = SI.astype(np.int64)
+    slaves = np.nonzero((S[:, 1] < 0) & (S[:, 2] > 0))[0]
+    nb = 6 * (S[slaves, 2] - 1) + (S[slaves, 3] // 10 - 1)
+    cen = coords[fn].mean(axis=1)
+    shift = cen[slaves] - cen[nb]                       # zero for inner sides, the periodic vector otherwise
+    shift[np.abs(shift) < 1e-9] = 0.0
+    dist = np.linalg.norm(coords[fn[slaves]] - (coords[fn[nb, 0]] + shift)[:, None, :], axis=2)
+    assert len(slaves) > 0 and np.array_equal(np.argmin(dist, axis=1) + 1, S[slaves, 3] % 10)
+
+
 def test_twisted_mesh_from_the_hopr_file_known_answer():
     """Box_deformed_mesh.h5 as written by HOPR (its master / slave choice fixes the diagonal of the twisted interface; BC 7 is the
     inner dielectric boundary of that case): deposited charge within the regression check's 1e-3."""
