@@ -172,6 +172,11 @@ int piclas_gpu_deposit(double *PartSource, double *NodeSource);
  * copies that one component, LOCAL [nElems][N+1][N+1][N+1], a quarter of the PartSource transfer. */
 int piclas_gpu_get_charge(double *ChargeDensity);
 
+/* replaces CalcKineticEnergy / CalcNumPartsOfSpec of the particle analysis (particle_analyze_tools.f90:709-842) so that
+ * PartAnalyze.csv needs no particle download: Ekin[nSpecies] in Joule (0.5 m v^2 below RelativisticLimit = (1e6/299792458)^2 c^2,
+ * (gamma-1) m c^2 above; times MacroParticleFactor), nPart[nSpecies] simulation particles.  Either may be NULL. */
+int piclas_gpu_kinetic_energy(double *Ekin, int64_t *nPart);
+
 /* after CALL HDG(time,iter): E == U_N(iElem)%E(1:3,i,j,k) packed, LOCAL [nElems][N+1][N+1][N+1][3] */
 int piclas_gpu_set_field(const double *E);
 

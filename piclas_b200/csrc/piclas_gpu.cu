@@ -1215,6 +1215,81 @@ int piclas_gpu_get_charge(double* ChargeDensity) {
   return 0;
 }
 
+// ---- particle analysis reductions ---------------------------------------------------------------------------------------------
+// CalcKineticEnergy (particle_analyze_tools.f90:709-842): per-species sums over the rank's particles.  One CTA sums a contiguous
+// chunk, threads stride through it, fixed shuffle / shared-memory tree: the result does not depend on scheduling.
+constexpr int AN_NT = 256;
+__global__ void __launch_bounds__(AN_NT) k_kinetic_energy(PartBuf pb, int64_t n, int64_t chunk, int nSpecies, double* __restrict__ partE,
+                                                          unsigned long long* __restrict__ partN) {
+  __shared__ double sE[AN_NT / 32];
+  __shared__ unsigned long long sN[AN_NT / 32];
+  const int64_t p0 = (int64_t)blockIdx.x * chunk, p1 = (p0 + chunk < n) ? p0 + chunk : n;
+  const double c2 = 1.0 / cst.c2_inv;
+  const double RelativisticLimit = (1e6 / 299792458.0) * (1e6 / 299792458.0) * c2;   // globals_init.f90:111
+  for (int sp = 0; sp < nSpecies; ++sp) {
+    double e = 0.;
+    unsigned long long cnt = 0;
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += AN_NT) {
+      if ((pb.meta[p] & META_SPEC_MASK) != sp) continue;
+      const double v0 = pb.v[0][p], v1 = pb.v[1][p], v2 = pb.v[2][p];
+      const double partV2 = (v0 * v0 + v1 * v1) + v2 * v2;
+      double Ekin_loc;
+      if (partV2 < RelativisticLimit) Ekin_loc = 0.5 * cst.MassIC[sp] * partV2;
+      else {
+        double GammaFac = partV2 * cst.c2_inv;
+        GammaFac = 1. / sqrt(1. - GammaFac);
+        Ekin_loc = (GammaFac - 1.) * cst.MassIC[sp] * c2;
+      }
+      e = e + Ekin_loc * cst.MPF[sp];
+      ++cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      e = e + __shfl_down_sync(0xffffffffu, e, o);
+      cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { sE[threadIdx.x >> 5] = e; sN[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double te = 0.;
+      unsigned long long tn = 0;
+      for (int w = 0; w < AN_NT / 32; ++w) { te = te + sE[w]; tn += sN[w]; }
+      partE[(size_t)blockIdx.x * nSpecies + sp] = te;
+      partN[(size_t)blockIdx.x * nSpecies + sp] = tn;
+    }
+    __syncthreads();
+  }
+}
+
+int piclas_gpu_kinetic_energy(double* Ekin, int64_t* nPart) {
+  if (!g.ready) return fail("piclas_gpu_kinetic_energy: not initialised");
+  if (g.exchangePending) return fail("piclas_gpu_kinetic_energy: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
+  CK(cudaSetDevice(g.device));
+  const int ns = g.prm.nSpecies;
+  for (int s = 0; s < ns; ++s) { if (Ekin) Ekin[s] = 0.; if (nPart) nPart[s] = 0; }
+  if (g.nPart == 0) return 0;
+  const int nb = g.nSMs * 8;
+  const int64_t chunk = (g.nPart + nb - 1) / nb;
+  double* dE = nullptr;
+  unsigned long long* dN = nullptr;
+  CK(cudaMalloc((void**)&dE, (size_t)nb * ns * 8));
+  CK(cudaMalloc((void**)&dN, (size_t)nb * ns * 8));
+  k_kinetic_energy<<<nb, AN_NT, 0, g.st>>>(g.buf[g.cur], g.nPart, chunk, ns, dE, dN);
+  std::vector<double> hE((size_t)nb * ns);
+  std::vector<unsigned long long> hN((size_t)nb * ns);
+  cudaError_t e1 = cudaMemcpyAsync(hE.data(), dE, hE.size() * 8, cudaMemcpyDeviceToHost, g.st);
+  cudaError_t e2 = cudaMemcpyAsync(hN.data(), dN, hN.size() * 8, cudaMemcpyDeviceToHost, g.st);
+  cudaError_t e3 = cudaStreamSynchronize(g.st);
+  cudaFree(dE); cudaFree(dN);
+  CK(e1); CK(e2); CK(e3);
+  for (int b = 0; b < nb; ++b)          // block order: fixed summation order
+    for (int s = 0; s < ns; ++s) {
+      if (Ekin) Ekin[s] = Ekin[s] + hE[(size_t)b * ns + s];
+      if (nPart) nPart[s] += (int64_t)hN[(size_t)b * ns + s];
+    }
+  return 0;
+}
+
 int piclas_gpu_nodesource_device(void** devNodeSource) {
   if (!g.ready) return fail("piclas_gpu_nodesource_device: not initialised");
   *devNodeSource = g.dS;

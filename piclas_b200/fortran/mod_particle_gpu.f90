@@ -83,6 +83,12 @@ INTERFACE
     REAL(C_DOUBLE),INTENT(OUT) :: ChargeDensity(*)               ! packed [nDOF_local] == PS_N(iElem)%PartSource(4,i,j,k)
     INTEGER(C_INT)             :: piclas_gpu_get_charge
   END FUNCTION
+  FUNCTION piclas_gpu_kinetic_energy(Ekin,nPart) BIND(C,NAME='piclas_gpu_kinetic_energy')
+    IMPORT :: C_INT, C_DOUBLE, C_INT64_T
+    REAL(C_DOUBLE),INTENT(OUT)     :: Ekin(*)                    ! [nSpecies] -> CalcKineticEnergy
+    INTEGER(C_INT64_T),INTENT(OUT) :: nPart(*)                   ! [nSpecies] -> CalcNumPartsOfSpec
+    INTEGER(C_INT)                 :: piclas_gpu_kinetic_energy
+  END FUNCTION
   FUNCTION piclas_gpu_set_field(E) BIND(C,NAME='piclas_gpu_set_field')
     IMPORT :: C_INT, C_DOUBLE
     REAL(C_DOUBLE),INTENT(IN) :: E(3,*)                          ! packed [3,nDOF_local]
@@ -156,7 +162,7 @@ END INTERFACE
 
 PUBLIC :: pgpu_mesh_t, pgpu_params_t
 PUBLIC :: piclas_gpu_init, piclas_gpu_finalize, piclas_gpu_upload_particles, piclas_gpu_deposit, piclas_gpu_set_field
-PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles, piclas_gpu_get_charge
+PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles, piclas_gpu_get_charge, piclas_gpu_kinetic_energy
 PUBLIC :: piclas_gpu_exchange_info, piclas_gpu_exchange_recv_buffer, piclas_gpu_exchange_finish
 PUBLIC :: piclas_gpu_nodesource_device, piclas_gpu_sf_halo_info, piclas_gpu_deposit_finish, piclas_gpu_phase_timing
 PUBLIC :: ParticleStepGPU, GPUAbortOnError

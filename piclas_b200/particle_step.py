@@ -131,6 +131,15 @@ class ParticleStep:
         self._check(self.lib.piclas_gpu_get_charge(_f(rho)))
         return rho
 
+    def KineticEnergy(self):
+        """CalcKineticEnergy / CalcNumPartsOfSpec (particle_analyze_tools.f90:709-842) on the device: (Ekin[nSpecies] in J,
+        nPart[nSpecies])."""
+        ns = len(self.params.ChargeIC)
+        E = np.zeros(ns)
+        N = np.zeros(ns, dtype=np.int64)
+        self._check(self.lib.piclas_gpu_kinetic_energy(_f(E), _l(N)))
+        return E, N
+
     def SetField(self, E):
         """U_N(iElem)%E(1:3,i,j,k) packed as [nElems,k,j,i,3] after CALL HDG (hdg/elem_mat.f90:709)."""
         E = np.ascontiguousarray(E, dtype=np.float64)

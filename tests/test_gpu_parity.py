@@ -290,3 +290,30 @@ def test_hopr_mesh_and_particle_output_layout():
         assert np.array_equal(np.sort(PartData[a:b], axis=0), np.sort(PD[a:b], axis=0))
     ref = g["DG_Source_charge"]
     assert np.abs(rho - ref).max() <= 1e-12 * np.abs(ref).max()
+
+
+def test_kinetic_energy_reduction():
+    """piclas_gpu_kinetic_energy against CalcKineticEnergy (particle_analyze_tools.f90:757-790) restated with numpy: classical
+    below RelativisticLimit = (1e6/299792458)^2 c^2, (gamma-1) m c^2 above, times MacroParticleFactor, per species."""
+    from piclas_b200.particle_step import ParticleStep
+    from piclas_b200.abi import Params
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (3, 3, 3), 1)
+    prm = Params(ChargeIC=(-cases.QE, cases.QE), MassIC=(cases.ME, 1.672621637e-27), MacroParticleFactor=(5e8, 2e8))
+    n = 50000
+    rng = np.random.default_rng(8)
+    x = rng.random((n, 3))
+    v = rng.normal(0, 1.0, (n, 3)) * 10.0 ** rng.uniform(3, 8, (n, 1))          # 1e3 .. 1e8 m/s: both branches
+    v = np.clip(v, -1.5e8, 1.5e8)
+    PS = np.ascontiguousarray(np.concatenate([x, v], axis=1))
+    spec = rng.integers(1, 3, n).astype(np.int32)
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(PS, spec, hm.cartesian_locate(mesh, x))
+        E, N = gpu.KineticEnergy()
+    c2 = 1.0 / prm.c2_inv
+    v2 = (v * v).sum(axis=1)
+    m = np.asarray(prm.MassIC)[spec - 1]
+    mpf = np.asarray(prm.MacroParticleFactor)[spec - 1]
+    ek = np.where(v2 < (1e6 / 299792458.0) ** 2 * c2, 0.5 * m * v2, (1.0 / np.sqrt(1.0 - v2 / c2) - 1.0) * m * c2) * mpf
+    for s in (1, 2):
+        assert N[s - 1] == (spec == s).sum()
+        assert abs(E[s - 1] - ek[spec == s].sum()) <= 1e-12 * ek[spec == s].sum()
