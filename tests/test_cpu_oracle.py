@@ -257,6 +257,25 @@ def test_oracle_reproduces_the_references_deposited_source_per_dof():
     assert abs(o.deposited_charge(src) - GOLD["NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean"]["charge"]) <= 5e-13
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/regressioncheck"), reason="reference tree not mounted")
+def test_committed_fixtures_match_the_reference_files():
+    """Where the reference tree is mounted (the build container): the committed golden fixtures are exactly what the built-in HDF5
+    reader extracts from the reference's files today."""
+    from piclas_b200.h5mini import H5File
+    d = "/root/reference/regressioncheck/NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean/"
+    st = H5File(d + "plasma_wave_State_000.00000000000000000_restart.h5")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "plasma_ball_cvwm_reference.npz"))
+    assert np.array_equal(st.read("PartData"), g["PartData"])
+    assert np.array_equal(st.read("DG_Source")[..., 3], g["DG_Source_charge"])
+    assert np.array_equal(st.read("PartInt"), g["PartInt"])
+    gm = np.load(os.path.join(ROOT, "tests", "golden", "hopr_meshes.npz"))
+    me = H5File(d + "Box_mesh.h5")
+    for ds in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType"):
+        assert np.array_equal(me.read(ds), gm["box_" + ds])
+    tw = H5File("/root/reference/tutorials/pic-poisson-plasma-wave/plasma_wave_mesh.h5")
+    assert np.array_equal(tw.read("NodeCoords"), gm["plasma_wave_NodeCoords"])
+
+
 def _hopr(tag, N, **kw):
     g = np.load(os.path.join(ROOT, "tests", "golden", "hopr_meshes.npz"))
     return hm.from_hopr_arrays(*[g[tag + "_" + d] for d in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames")],
