@@ -7,9 +7,13 @@
 //
 // Structure of the step (r1 profile: one fused kernel was instruction-cache bound — 20k SASS lines, 66 % no_inst
 // stalls, SIMD efficiency 45 %, profiles/r1_v1_push_track_stalls.txt):
-//   k_interp_push   all particles: field evaluation, push, ParticleInsideQuad3D in the own element (the common exit of
-//                   SingleParticleTriaTracking3D).  Particles that left the element are appended to a leaver list.
-//   k_track_leavers one thread per leaver: the element walk of SingleParticleTriaTracking3D on the global tables.
+//   k_interp_push   phase 1, all particles of a sweep: field evaluation, push, ParticleInsideQuad3D in the own element (the
+//                   common exit of SingleParticleTriaTracking3D); leavers are queued in shared memory.
+//                   phase 2 (restructured arithmetic), dense warps over the queue: the first element crossing on the staged
+//                   records of the element and its six face neighbours — exit side from the side planes where that is safe
+//                   (queue A), the determinant tests of ParticleThroughSideCheck3DFast otherwise (queue B).
+//   k_track_leavers one thread per particle that is not localised after that (edge / corner crossings, long flights, or all
+//                   leavers in reference-order arithmetic): the element walk on the global tables, persistent warps.
 // Loops that do not need unrolling are kept rolled so that each kernel's hot loop stays inside the instruction caches.
 #pragma once
 #include <type_traits>
