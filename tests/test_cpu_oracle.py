@@ -199,6 +199,33 @@ def test_boris_with_zero_B_equals_relativistic_leapfrog_and_leapfrog_limit():
     assert np.abs(out["boris"][:, 3:] - out["leap"][:, 3:]).max() / np.abs(out["leap"][:, 3:]).max() < 1e-5
 
 
+def test_boris_rotation_in_a_uniform_magnetic_field():
+    """Boris-Leapfrog with E = 0, B = B e_z (external field): the speed is conserved to rounding and the velocity turns by
+    exactly q B dt / (gamma m) per step about B — the reference takes t = TAN(c_1 B / gamma), i.e. the exact half angle
+    (timedisc_TimeStepPoissonByBorisLeapfrog.f90:153-185)."""
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (2, 2, 2), 1)
+    B = 2e-4
+    prm = cases.electron_params(externalField=(0.0, 0.0, 0.0, 0.0, 0.0, B), DoDeposition=0)
+    o = Oracle(mesh, prm)
+    n, dt = 200, 1e-9
+    rng = np.random.default_rng(4)
+    v0 = rng.normal(0, 3e6, (n, 3))
+    PS = np.ascontiguousarray(np.concatenate([rng.uniform(0.3, 0.7, (n, 3)), v0], axis=1))
+    spec = np.ones(n, dtype=np.int32)
+    el = hm.cartesian_locate(mesh, PS[:, :3])
+    inside, isnew = np.ones(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    E = np.zeros(mesh.Elem_xGP.shape)
+    o.push_track(dt, PS, spec, el, inside, isnew, E)
+    v1 = PS[:, 3:]
+    assert np.abs(np.linalg.norm(v1, axis=1) / np.linalg.norm(v0, axis=1) - 1.0).max() < 1e-14
+    assert np.abs(v1[:, 2] - v0[:, 2]).max() <= 1e-15 * np.abs(v0).max() * 4             # parallel component untouched
+    gamma = 1.0 / np.sqrt(1.0 - (v0 * v0).sum(1) * prm.c2_inv)
+    ang = np.arctan2(v1[:, 1], v1[:, 0]) - np.arctan2(v0[:, 1], v0[:, 0])
+    ang = (ang + np.pi) % (2 * np.pi) - np.pi
+    expect = cases.QE * B * dt / (gamma * cases.ME)                                    # electrons turn counter-clockwise about +z
+    assert np.abs(ang - expect).max() < 1e-13
+
+
 def test_open_boundary_removes_and_counts_nothing_lost():
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (3, 3, 3), 1, periodic=(False, False, False))
     o = Oracle(mesh, cases.electron_params())

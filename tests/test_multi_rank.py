@@ -26,9 +26,10 @@ def test_multi_rank_gloo_oracle(world):
     _run(world, "oracle", 29611 + world)
 
 
-def test_multi_rank_gloo_oracle_shape_function():
+@pytest.mark.parametrize("world,depo", [(2, "sf"), (3, "cc")])
+def test_multi_rank_gloo_oracle_shape_function(world, depo):
     """DOF halo of the shape-function deposition over gloo."""
-    _run(2, "oracle", 29617, depo="sf")
+    _run(world, "oracle", 29617 + world, depo=depo)
 
 
 @pytest.mark.gpu
