@@ -10,7 +10,15 @@
   regressioncheck/NIG_PIC_Deposition/Plasma_Ball_cell_volweight_mean_save_CVWM/Box_deformed_mesh.h5
                                                            corner nodes of the two-element twisted mesh
 
--> tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz (committed; the tests never read /root/reference).
+  regressioncheck/NIG_tracking_DSMC/periodic/          collisionless, field-free particles in a 3-periodic 5x5x5 box
+      periodic_restart_State_000.0000000000000000.h5       PartData / PartInt at t = 0 (1000 particles)
+      periodic_reference_State_000.0200000000000000.h5     PartData / PartInt after 200 steps of 1e-4, written by the
+                                                           reference (its h5diff check compares PartInt)
+  regressioncheck/NIG_tracking_DSMC/ANSA_box/          the same on an unstructured 1331-element box with specular walls
+      tildbox_mesh.h5, tildbox_restart_State_000...h5, tildbox_reference_State_001...h5   (2000 particles, 100 steps of 1e-2)
+
+-> tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz
+   (committed; the tests never read /root/reference).
 """
 import os
 import sys
@@ -22,6 +30,32 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 from piclas_b200.h5mini import H5File  # noqa: E402
 
 REF = "/root/reference/regressioncheck/NIG_PIC_Deposition"
+TRK = "/root/reference/regressioncheck/NIG_tracking_DSMC"
+
+
+def tracking_vectors():
+    """Particle states the reference wrote before and after pure push + tracking (DSMC time step without collisions:
+    timedisc_TimeStep_DSMC.f90:127-149 is x += v dt, then PerformTracking)."""
+    out = {}
+    for tag, d, r0, r1 in (("periodic", "periodic", "periodic_restart_State_000.0000000000000000.h5",
+                            "periodic_reference_State_000.0200000000000000.h5"),
+                           ("ansa", "ANSA_box", "tildbox_restart_State_000.0000000000000000.h5",
+                            "tildbox_reference_State_001.0000000000000000.h5")):
+        a, b = H5File(os.path.join(TRK, d, r0)), H5File(os.path.join(TRK, d, r1))
+        pd0, pi0, pd1, pi1 = a.read("PartData"), a.read("PartInt"), b.read("PartData"), b.read("PartInt")
+        # the reference state files predate the transposition of the particle arrays (analyze.ini: h5diff_flip = T)
+        if pd1.shape[0] == 7:
+            pd1 = np.ascontiguousarray(pd1.T)
+        assert pd0.shape == pd1.shape and pd0.shape[1] == 7 and pi0.shape == pi1.shape and pi0.shape[0] == 2
+        assert pi0[1, -1] == pd0.shape[0] and pi1[1, -1] == pd1.shape[0]
+        out[tag + "_PartData0"], out[tag + "_PartInt0"] = pd0, pi0
+        out[tag + "_PartData1"], out[tag + "_PartInt1"] = pd1, pi1
+    me = H5File(os.path.join(TRK, "ANSA_box", "tildbox_mesh.h5"))
+    for ds in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames"):
+        out["ansa_mesh_" + ds] = me.read(ds)
+    path = os.path.join(HERE, "tracking_dsmc_reference.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 def main():
@@ -52,6 +86,7 @@ def main():
     np.savez_compressed(out, PartData=part, DG_Source_charge=np.ascontiguousarray(src[..., 3]), ElemBarycenters=bary,
                         deformed_mesh_NodeCoords=dnodes, PartInt=st.read("PartInt"))
     print("wrote", out, os.path.getsize(out), "bytes")
+    tracking_vectors()
 
 
 if __name__ == "__main__":
