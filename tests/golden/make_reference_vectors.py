@@ -17,7 +17,14 @@
   regressioncheck/NIG_tracking_DSMC/ANSA_box/          the same on an unstructured 1331-element box with specular walls
       tildbox_mesh.h5, tildbox_restart_State_000...h5, tildbox_reference_State_001...h5   (2000 particles, 100 steps of 1e-2)
 
--> tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz
+  regressioncheck/NIG_PIC_poisson_Leapfrog/2D_innerBC_dielectric_surface_charge/
+      2D_dielectric_innerBC_mesh.h5                        101 hexahedra of several sizes, N = 1
+      2Dplasma_test_State_000.00000000000000000.h5         initial state: 791 moving electrons and ions and the DG_Source
+                                                           (current and charge density) the reference deposited from them with
+                                                           cell_volweight_mean; no surface charge yet (DG_SourceExt = 0)
+
+-> tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
+   tests/golden/cvwm_current_reference.npz
    (committed; the tests never read /root/reference).
 """
 import os
@@ -31,6 +38,23 @@ from piclas_b200.h5mini import H5File  # noqa: E402
 
 REF = "/root/reference/regressioncheck/NIG_PIC_Deposition"
 TRK = "/root/reference/regressioncheck/NIG_tracking_DSMC"
+
+
+def current_density_vectors():
+    """DG_Source with all four components (moving particles) from the initial state of a PIC-Poisson regression check.  Only
+    the initial state qualifies: later state files hold the source deposited at the start of the last step next to the
+    particles at its end."""
+    d = "/root/reference/regressioncheck/NIG_PIC_poisson_Leapfrog/2D_innerBC_dielectric_surface_charge"
+    st = H5File(os.path.join(d, "2Dplasma_test_State_000.00000000000000000.h5"))
+    me = H5File(os.path.join(d, "2D_dielectric_innerBC_mesh.h5"))
+    out = {"PartData": st.read("PartData"), "PartInt": st.read("PartInt"), "DG_Source": st.read("DG_Source")}
+    assert out["PartData"].shape == (791, 7) and out["PartInt"].shape == (101, 2) and out["DG_Source"].shape == (101, 2, 2, 2, 4)
+    assert not st.read("DG_SourceExt").any()
+    for ds in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames"):
+        out["mesh_" + ds] = me.read(ds)
+    path = os.path.join(HERE, "cvwm_current_reference.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 def tracking_vectors():
@@ -87,6 +111,7 @@ def main():
                         deformed_mesh_NodeCoords=dnodes, PartInt=st.read("PartInt"))
     print("wrote", out, os.path.getsize(out), "bytes")
     tracking_vectors()
+    current_density_vectors()
 
 
 if __name__ == "__main__":
