@@ -22,8 +22,11 @@
       2Dplasma_test_State_000.00000000000000000.h5         initial state: 791 moving electrons and ions and the DG_Source
                                                            (current and charge density) the reference deposited from them with
                                                            cell_volweight_mean; no surface charge yet (DG_SourceExt = 0)
+  regressioncheck/NIG_PIC_poisson_Leapfrog/parallel_plates/PartAnalyzeLeapfrog_ref.csv
+                                                           coupled power (kinetic-energy gain per step / dt) of one electron in
+                                                           the uniform field of a plate capacitor, all 1500 Leapfrog steps
 
--> tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
+-> tests/golden/parallel_plates_pcoupled_reference.npz, tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
    tests/golden/cvwm_current_reference.npz
    (committed; the tests never read /root/reference).
 """
@@ -54,6 +57,15 @@ def current_density_vectors():
         out["mesh_" + ds] = me.read(ds)
     path = os.path.join(HERE, "cvwm_current_reference.npz")
     np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def coupled_power_vectors():
+    ref = np.loadtxt("/root/reference/regressioncheck/NIG_PIC_poisson_Leapfrog/parallel_plates/PartAnalyzeLeapfrog_ref.csv",
+                     delimiter=",", skiprows=1)
+    assert ref.shape == (1501, 3)
+    path = os.path.join(HERE, "parallel_plates_pcoupled_reference.npz")
+    np.savez_compressed(path, time=ref[:, 0], PCoupled=ref[:, 1])
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
@@ -112,6 +124,7 @@ def main():
     print("wrote", out, os.path.getsize(out), "bytes")
     tracking_vectors()
     current_density_vectors()
+    coupled_power_vectors()
 
 
 if __name__ == "__main__":
