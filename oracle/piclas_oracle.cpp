@@ -9,9 +9,22 @@
 //     Plasma_Ball_cell_volweight_mean carries the 3333 particles and the DG_Source the reference deposited from
 //     them; this restatement reproduces all 8000 values to 3e-15 relative (tests/golden/make_reference_vectors.py,
 //     tests/test_cpu_oracle.py::test_oracle_reproduces_the_references_deposited_source_per_dof);
-//   * the integrated known answers of all NIG_PIC_Deposition checks (21 values, tests/golden/reference_known_answers.json).
-// PARITY UNPINNED for everything else: the reference's tests hold no per-particle positions, velocities or element
-// ids; interpolation, push and tracking are pinned only by analytic self-checks.  The
+//   * current AND charge density per DOF from moving particles: the initial state of regressioncheck/
+//     NIG_PIC_poisson_Leapfrog/2D_innerBC_dielectric_surface_charge (791 electrons and ions, 101 hexahedra of several
+//     sizes) reproduced to 2e-12 of the maximum, the deviation being a per-DOF factor of the host-built NodeVolume
+//     (tests/test_reference_deposition.py);
+//   * the integrated known answers of all NIG_PIC_Deposition checks (21 values, tests/golden/reference_known_answers.json);
+//   * push + tracking PER PARTICLE in field-free flight: regressioncheck/NIG_tracking_DSMC/periodic (restart state and
+//     the state the reference wrote 200 steps later: velocities bit-equal, positions to 2.4e-13, every particle in the
+//     element the reference's PartInt puts it in) and NIG_tracking_DSMC/ANSA_box (unstructured 1331-element mesh file,
+//     specular walls, 100 steps: PartInt equal, which is the reference's own h5diff criterion), TriaTracking and
+//     RefMapping (tests/test_reference_tracking.py);
+//   * the Leapfrog time staggering incl. the half step back of new particles and the field interpolation: first simulated
+//     step of NIG_PIC_poisson_Leapfrog/parallel_plates to 1.4e-11, its analytical known-answer rows to 1e-12 up to the
+//     charge constant (tests/test_reference_push.py).
+// PARITY UNPINNED for what is left: per-particle positions and velocities after interpolation + push in a NON-UNIFORM
+// field and the Boris rotation (B != 0) - the reference's tests hold no such vectors (every candidate needs the HDG solve
+// between steps) - and shape functions per DOF (integrated known answers only); these rest on analytic self-checks.  The
 // restatement follows the Fortran routine by routine, loop by loop and operator by operator; every function
 // cites the lines it restates (paths relative to the reference root).
 //
