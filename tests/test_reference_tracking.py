@@ -50,14 +50,17 @@ def _params(tracking, mass, eps):
 
 def periodic_case(tracking):
     """NIG_tracking_DSMC/periodic (hopr.ini: Corner (0,0,0)-(2,1,1), nElems 5,5,5; parameter.ini: ManualTimeStep 1e-4,
-    tend 2e-2, RefMappingEps 1e-12, Part-FIBGMdeltas (2,1,1)).  The mesh file is built by HOPR at test time in the reference
-    and is not in its tree; the element each HOPR index stands for is taken from the reference's own localisation of the
-    restart particles (every element holds some)."""
+    tend 2e-2, RefMappingEps 1e-12).  The mesh file is built by HOPR at test time in the reference and is not in its tree; the
+    element each HOPR index stands for is taken from the reference's own localisation of the restart particles (every element
+    holds some).  The check's Part-FIBGMdeltas (2,1,1) put all 125 elements into one background cell; the device kernel sorts
+    at most 32 candidates per cell (REF_MAX_BGM, csrc/ref.cuh), so the background mesh here has one cell per element - the
+    candidate list only has to contain the element the particle is in."""
     g = np.load(GOLDEN)
     mesh = hm.box_mesh([0, 0, 0], [2, 1, 1], (5, 5, 5), 1, tracking=tracking)
     if tracking == hm.REFMAPPING:
-        hm.add_fibgm(mesh, deltas=(2.0, 1.0, 1.0))
+        hm.add_fibgm(mesh, deltas=(0.4, 0.2, 0.2))
         hm.add_refmapping_tables(mesh, RefMappingEps=1e-12)
+        assert mesh.extra["FIBGM"]["nElems"].max() <= 32
     PD0, PD1 = g["periodic_PartData0"], g["periodic_PartData1"]
     n = PD0.shape[0]
     elem0 = hm.cartesian_locate(mesh, PD0[:, :3]).astype(np.int32)
@@ -82,6 +85,7 @@ def ansa_case(tracking):
     if tracking == hm.REFMAPPING:
         hm.add_fibgm(mesh, deltas=(1.0, 1.0, 1.0))
         hm.add_refmapping_tables(mesh)
+        assert mesh.extra["FIBGM"]["nElems"].max() <= 32          # REF_MAX_BGM of the device kernel
     PD0, PD1 = g["ansa_PartData0"], g["ansa_PartData1"]
     n = PD0.shape[0]
     elem0 = (_elem_of_range(g["ansa_PartInt0"], n) + 1).astype(np.int32)
