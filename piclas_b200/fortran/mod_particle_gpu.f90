@@ -158,6 +158,12 @@ INTERFACE
     REAL(C_DOUBLE),INTENT(OUT) :: ms4(4)                         ! -> LBSplitTime(LB_DEPO / LB_INTERPOLATION+LB_PUSH+LB_TRACK / LB_UNFP)
     INTEGER(C_INT)             :: piclas_gpu_phase_timing
   END FUNCTION
+  FUNCTION piclas_gpu_last_timing(ms_kernels,nLaunches) BIND(C,NAME='piclas_gpu_last_timing')
+    IMPORT :: C_INT, C_INT32_T, C_DOUBLE
+    REAL(C_DOUBLE),INTENT(OUT)     :: ms_kernels                 ! CUDA-event time of the last call's kernels
+    INTEGER(C_INT32_T),INTENT(OUT) :: nLaunches                  ! kernels launched by the last call
+    INTEGER(C_INT)                 :: piclas_gpu_last_timing
+  END FUNCTION
 END INTERFACE
 
 PUBLIC :: pgpu_mesh_t, pgpu_params_t
@@ -165,6 +171,7 @@ PUBLIC :: piclas_gpu_init, piclas_gpu_finalize, piclas_gpu_upload_particles, pic
 PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles, piclas_gpu_get_charge, piclas_gpu_kinetic_energy
 PUBLIC :: piclas_gpu_exchange_info, piclas_gpu_exchange_recv_buffer, piclas_gpu_exchange_finish
 PUBLIC :: piclas_gpu_nodesource_device, piclas_gpu_sf_halo_info, piclas_gpu_deposit_finish, piclas_gpu_phase_timing
+PUBLIC :: piclas_gpu_last_timing
 PUBLIC :: ParticleStepGPU, GPUAbortOnError
 
 CONTAINS
