@@ -21,10 +21,15 @@
 //     RefMapping (tests/test_reference_tracking.py);
 //   * the Leapfrog time staggering incl. the half step back of new particles and the field interpolation: first simulated
 //     step of NIG_PIC_poisson_Leapfrog/parallel_plates to 1.4e-11, its analytical known-answer rows to 1e-12 up to the
-//     charge constant (tests/test_reference_push.py).
+//     charge constant (tests/test_reference_push.py);
+//   * shape_function PER DOF: DG_Source(1:4) of regressioncheck/NIG_PIC_maxwell_RK4/single_particle (one electron, 27 x 64
+//     DOFs, r_sf 0.2, alpha 4, 3-D) reproduced to 1.3e-15 once the particle is put where the last Runge-Kutta stage
+//     deposited it (velocity = J/rho from the file, position = 3 fitted numbers, 1.9e-12 s of flight behind the stored end
+//     state; tests/test_reference_shapefunction.py).
 // PARITY UNPINNED for what is left: per-particle positions and velocities after interpolation + push in a NON-UNIFORM
 // field and the Boris rotation (B != 0) - the reference's tests hold no such vectors (every candidate needs the HDG solve
-// between steps) - and shape functions per DOF (integrated known answers only); these rest on analytic self-checks.  The
+// between steps) - and the charge-conserving / adaptive shape functions per DOF (integrated known answers only); these rest
+// on analytic self-checks.  The
 // restatement follows the Fortran routine by routine, loop by loop and operator by operator; every function
 // cites the lines it restates (paths relative to the reference root).
 //

@@ -25,8 +25,13 @@
   regressioncheck/NIG_PIC_poisson_Leapfrog/parallel_plates/PartAnalyzeLeapfrog_ref.csv
                                                            coupled power (kinetic-energy gain per step / dt) of one electron in
                                                            the uniform field of a plate capacitor, all 1500 Leapfrog steps
+  regressioncheck/NIG_PIC_maxwell_RK4/single_particle/
+      single-particle_mesh.h5, single-particle_reference_State_000.0000000500000000.h5
+                                                           one fast electron on a 3x3x3 mesh, N = 3: DG_Source(1:4) deposited by
+                                                           the reference with shape_function (r = 0.2, alpha = 4, 3-D) at the last
+                                                           Runge-Kutta stage of the run, and the particle's end state
 
--> tests/golden/parallel_plates_pcoupled_reference.npz, tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
+-> tests/golden/sf_single_particle_reference.npz, tests/golden/parallel_plates_pcoupled_reference.npz, tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
    tests/golden/cvwm_current_reference.npz
    (committed; the tests never read /root/reference).
 """
@@ -66,6 +71,19 @@ def coupled_power_vectors():
     assert ref.shape == (1501, 3)
     path = os.path.join(HERE, "parallel_plates_pcoupled_reference.npz")
     np.savez_compressed(path, time=ref[:, 0], PCoupled=ref[:, 1])
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def shape_function_vectors():
+    d = "/root/reference/regressioncheck/NIG_PIC_maxwell_RK4/single_particle"
+    st = H5File(os.path.join(d, "single-particle_reference_State_000.0000000500000000.h5"))
+    me = H5File(os.path.join(d, "single-particle_mesh.h5"))
+    out = {"PartData": np.ascontiguousarray(st.read("PartData").T), "DG_Source": st.read("DG_Source")}
+    assert out["PartData"].shape == (1, 7) and out["DG_Source"].shape == (27, 4, 4, 4, 4)
+    for ds in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType", "BCNames"):
+        out["mesh_" + ds] = me.read(ds)
+    path = os.path.join(HERE, "sf_single_particle_reference.npz")
+    np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
@@ -125,6 +143,7 @@ def main():
     tracking_vectors()
     current_density_vectors()
     coupled_power_vectors()
+    shape_function_vectors()
 
 
 if __name__ == "__main__":
