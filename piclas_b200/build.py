@@ -10,7 +10,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpiclas_gpu.so")
 SOURCES = ["piclas_gpu.cu", "sort.cu"]
-HEADERS = ["common.cuh", "math.cuh", "kernels.cuh", "sort.cuh", os.path.join(ROOT, "include", "piclas_gpu.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join(ROOT, "include", "piclas_gpu.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

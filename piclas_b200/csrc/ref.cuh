@@ -10,6 +10,7 @@
 // stored reference coordinates PartPosRef are bitwise equal to the CPU restatement.
 #pragma once
 #include "math.cuh"
+#include "select.cuh"
 
 struct RefTables {
   const GeoElem* geo;
@@ -24,9 +25,39 @@ struct RefTables {
 };
 
 #define REF_MAX_HITS 16
-#define REF_MAX_BGM 32
+#define REF_MAX_BGM 32   // candidates of a FIBGM cell kept as a sorted per-thread list; fuller cells are visited by repeated selection
 #define REF_ALMOSTZERO(x) (fabs(x) <= 2.22e-16)
 #define REF_ALMOSTEQUAL(x, y) (fabs((x) - (y)) <= fmax(fabs(x), fabs(y)) * 4.441e-16)
+
+// Sort keys of the two relocation searches for cells with more than REF_MAX_BGM elements (select.cuh).
+// ParticleRefTracking :192-216: squared distance to the barycentre; the old element and elements out of reach are skipped.
+struct RelocKey {
+  const RefTables& T;
+  size_t off;
+  const double* x;
+  int oldElemID;
+  __host__ __device__ double operator()(int i) const {
+    const int e = T.FIBGM_Element[off + i];
+    if (e == oldElemID) return -HUGE_D;
+    const double* b = T.ElemBary + (size_t)(e - 1) * 3;
+    const double d0 = x[0] - b[0], d1 = x[1] - b[1], d2 = x[2] - b[2];
+    const double D = (d0 * d0 + d1 * d1) + d2 * d2;
+    return (D > T.ElemRadius2[e - 1]) ? -HUGE_D : D;
+  }
+};
+// SinglePointToElement (particle_localization.f90:81-190): elements out of reach carry -1 and are skipped.
+struct LocateKey {
+  const RefTables& T;
+  size_t off;
+  const double* x;
+  __host__ __device__ double operator()(int i) const {
+    const int e = T.FIBGM_Element[off + i];
+    const double* b = T.ElemBary + (size_t)(e - 1) * 3;
+    const double d0 = x[0] - b[0], d1 = x[1] - b[1], d2 = x[2] - b[2];
+    const double D2 = (d0 * d0 + d1 * d1) + d2 * d2;
+    return (D2 <= T.ElemRadius2[e - 1]) ? D2 : -1.;
+  }
+};
 
 __device__ __forceinline__ double maxabs3(const double v[3]) { return fmax(fabs(v[0]), fmax(fabs(v[1]), fabs(v[2]))); }
 
@@ -356,10 +387,11 @@ __device__ int ref_tracking(const RefTables& T, const PartBuf& pb, int64_t p, do
   const int ni = cst.FIBGMmax[0] - cst.FIBGMmin[0] + 1, nj = cst.FIBGMmax[1] - cst.FIBGMmin[1] + 1;
   const size_t cell = (size_t)(Cell[0] - cst.FIBGMmin[0]) + (size_t)ni * ((size_t)(Cell[1] - cst.FIBGMmin[1]) + (size_t)nj * (size_t)(Cell[2] - cst.FIBGMmin[2]));
   const int nBGM = T.FIBGM_nElems[cell];
-  if (nBGM > REF_MAX_BGM) return TRK_ERR_LOOP;
+  const bool bigCell = nBGM > REF_MAX_BGM;   // the list does not fit: same visiting order by repeated selection (select.cuh)
   double Distance[REF_MAX_BGM];
   int List[REF_MAX_BGM];
-  if (nBGM > 1) {
+  if (bigCell) {
+  } else if (nBGM > 1) {
     for (int i = 0; i < nBGM; ++i) {
       const int e = T.FIBGM_Element[T.FIBGM_offsetElem[cell] + i];
       List[i] = e;
@@ -391,7 +423,17 @@ __device__ int ref_tracking(const RefTables& T, const PartBuf& pb, int64_t p, do
   const double OldXi[3] = {xi[0], xi[1], xi[2]};
   double newXi[3] = {HUGE_D, HUGE_D, HUGE_D};
   int newElemID = -1;
-  for (int i = 0; i < nBGM; ++i) {
+  if (bigCell) {
+    const RelocKey key{T, (size_t)T.FIBGM_offsetElem[cell], x, oldElemID};
+    SortedVisit sv;
+    for (int i = next_in_sorted_order(nBGM, key, -HUGE_D, sv); i >= 0; i = next_in_sorted_order(nBGM, key, -HUGE_D, sv)) {
+      ElemID = T.FIBGM_Element[T.FIBGM_offsetElem[cell] + i];
+      ref_newton(T, x, xi, ElemID);
+      if (maxabs3(xi) < 1.0) { elem = ElemID; return TRK_OK; }
+      if (maxabs3(xi) < maxabs3(newXi)) { newXi[0] = xi[0]; newXi[1] = xi[1]; newXi[2] = xi[2]; newElemID = ElemID; }
+    }
+  }
+  for (int i = 0; i < (bigCell ? 0 : nBGM); ++i) {
     if (Distance[i] == -HUGE_D) continue;
     ElemID = List[i];
     ref_newton(T, x, xi, ElemID);
@@ -425,7 +467,21 @@ __device__ int ref_tracking(const RefTables& T, const PartBuf& pb, int64_t p, do
       }
       const size_t cell2 = (size_t)(Cell[0] - cst.FIBGMmin[0]) + (size_t)ni * ((size_t)(Cell[1] - cst.FIBGMmin[1]) + (size_t)nj * (size_t)(Cell[2] - cst.FIBGMmin[2]));
       const int nB = T.FIBGM_nElems[cell2];
-      if (nB > REF_MAX_BGM) return TRK_ERR_LOOP;
+      if (nB > REF_MAX_BGM) {   // same search by repeated selection
+        const LocateKey key{T, (size_t)T.FIBGM_offsetElem[cell2], x};
+        SortedVisit sv;
+        int found = -1;
+        for (int i = next_in_sorted_order(nB, key, -1., sv); i >= 0; i = next_in_sorted_order(nB, key, -1., sv)) {
+          const int e = T.FIBGM_Element[T.FIBGM_offsetElem[cell2] + i];
+          ref_newton(T, x, xi, e);
+          if (maxabs3(xi) <= T.ElemEpsOneCell[e - 1]) { found = e; break; }
+        }
+        if (found < 1) return TRK_ERR_ELEM;   // 'Particle not inside of Element' or no candidate accepted
+        ref_newton(T, x, xi, found);
+        elem = found;
+        relocated = true;
+        return TRK_OK;
+      }
       double mx = -1.;
       for (int i = 0; i < nB; ++i) {
         const int e = T.FIBGM_Element[T.FIBGM_offsetElem[cell2] + i];

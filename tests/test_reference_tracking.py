@@ -48,19 +48,20 @@ def _params(tracking, mass, eps):
                   carryParticleIDs=1)
 
 
-def periodic_case(tracking):
+def periodic_case(tracking, fibgm_deltas=(0.4, 0.2, 0.2)):
     """NIG_tracking_DSMC/periodic (hopr.ini: Corner (0,0,0)-(2,1,1), nElems 5,5,5; parameter.ini: ManualTimeStep 1e-4,
     tend 2e-2, RefMappingEps 1e-12).  The mesh file is built by HOPR at test time in the reference and is not in its tree; the
     element each HOPR index stands for is taken from the reference's own localisation of the restart particles (every element
-    holds some).  The check's Part-FIBGMdeltas (2,1,1) put all 125 elements into one background cell; the device kernel sorts
-    at most 32 candidates per cell (REF_MAX_BGM, csrc/ref.cuh), so the background mesh here has one cell per element - the
-    candidate list only has to contain the element the particle is in."""
+    holds some).  The check's own Part-FIBGMdeltas (2,1,1) put all 125 elements into one background cell; the device kernel
+    keeps a sorted list of at most 32 candidates per cell (REF_MAX_BGM, csrc/ref.cuh) and visits fuller cells by repeated
+    selection (csrc/select.cuh), so the default here is one cell per element (stored-list path) and the last test of this
+    file runs the reference's deltas (selection path)."""
     g = np.load(GOLDEN)
     mesh = hm.box_mesh([0, 0, 0], [2, 1, 1], (5, 5, 5), 1, tracking=tracking)
     if tracking == hm.REFMAPPING:
-        hm.add_fibgm(mesh, deltas=(0.4, 0.2, 0.2))
+        hm.add_fibgm(mesh, deltas=fibgm_deltas)
         hm.add_refmapping_tables(mesh, RefMappingEps=1e-12)
-        assert mesh.extra["FIBGM"]["nElems"].max() <= 32
+        assert (mesh.extra["FIBGM"]["nElems"].max() <= 32) == (fibgm_deltas[0] < 2.0)
     PD0, PD1 = g["periodic_PartData0"], g["periodic_PartData1"]
     n = PD0.shape[0]
     elem0 = hm.cartesian_locate(mesh, PD0[:, :3]).astype(np.int32)
@@ -218,3 +219,59 @@ def test_gpu_reproduces_the_references_partint_on_the_ansa_box(tracking, arith):
     prm.arithmetic = arith
     PS, elem = run_gpu(mesh, prm, PD0, elem0, dt, nsteps)
     check_ansa(PS, elem, PD0, PD1, elem1, mesh.nElems)
+
+
+# ---- the reference's own background mesh: all 125 elements in one FIBGM cell ----------------------------------------------------
+def test_oracle_periodic_tracking_with_the_references_fibgm_deltas():
+    mesh, prm, PD0, elem0, PD1, elem1, dt, nsteps = periodic_case(hm.REFMAPPING, fibgm_deltas=(2.0, 1.0, 1.0))
+    PS, elem = run_oracle(mesh, prm, PD0, elem0, dt, nsteps)
+    check_periodic(PS, elem, PD1, elem1, mesh.nElems)
+
+
+def test_selection_order_is_the_stable_insertion_sort():
+    """csrc/select.cuh compiled for the host: the repeated selection visits 20000 random lists (ties, skipped entries, up to
+    140 entries) in exactly the order of the stable InsertionSort the stored-list path of csrc/ref.cuh uses (utils.f90:52-101)."""
+    import subprocess
+    import tempfile
+    src = r'''
+#include "select.cuh"
+#include <cstdio>
+#include <random>
+#include <vector>
+struct Arr { const double* d; double operator()(int i) const { return d[i]; } };
+int main() {
+  std::mt19937 rng(5);
+  const double skip = -1.7976931348623157e308;
+  for (int trial = 0; trial < 20000; ++trial) {
+    const int n = 1 + rng() % 140;
+    std::vector<double> D(n), S; std::vector<int> P(n);
+    for (int i = 0; i < n; ++i) { D[i] = (rng() % 10 == 0) ? skip : (double)(rng() % 12) * 0.25; P[i] = i; }
+    S = D;
+    for (int i = 1; i < n; ++i) { int j = i - 1; const double tr = S[i]; const int ti = P[i];
+      while (j >= 0) { if (S[j] <= tr) break; S[j + 1] = S[j]; P[j + 1] = P[j]; --j; } S[j + 1] = tr; P[j + 1] = ti; }
+    std::vector<int> want, got;
+    for (int i = 0; i < n; ++i) if (S[i] != skip) want.push_back(P[i]);
+    SortedVisit sv; const Arr a{D.data()};
+    for (int i = next_in_sorted_order(n, a, skip, sv); i >= 0 && (int)got.size() <= n; i = next_in_sorted_order(n, a, skip, sv)) got.push_back(i);
+    if (got != want) { std::printf("MISMATCH %d\n", trial); return 1; }
+  }
+  std::printf("OK\n");
+  return 0;
+}
+'''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.cpp"), "w").write(src)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "piclas_b200", "csrc"), "-o", os.path.join(d, "t"),
+                        os.path.join(d, "t.cpp")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "OK", out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arith", [0, 1], ids=["reference-order", "restructured"])
+def test_gpu_periodic_tracking_with_the_references_fibgm_deltas(arith):
+    """Relocation by repeated selection (more than REF_MAX_BGM candidates in the cell)."""
+    mesh, prm, PD0, elem0, PD1, elem1, dt, nsteps = periodic_case(hm.REFMAPPING, fibgm_deltas=(2.0, 1.0, 1.0))
+    prm.arithmetic = arith
+    PS, elem = run_gpu(mesh, prm, PD0, elem0, dt, nsteps)
+    check_periodic(PS, elem, PD1, elem1, mesh.nElems)
