@@ -37,9 +37,9 @@ class OracleRank:
         if self.sf:
             self.orc_full = Oracle(mesh, prm)
 
-    def upload(self, PS, spec, elem, ids):
+    def upload(self, PS, spec, elem, ids, isnew=1):
         self.PS, self.spec, self.elem, self.ids = PS.copy(), spec.copy(), elem.copy(), ids.copy()
-        self.isnew = np.ones(len(spec), dtype=np.int32)
+        self.isnew = np.full(len(spec), isnew, dtype=np.int32)
 
     def set_field(self, E):
         self.E = np.ascontiguousarray(E[int(self.off[self.rank]):int(self.off[self.rank + 1])])
@@ -110,8 +110,8 @@ class GpuRank:
         self.off = self.R.offsets
         self.rank = rank
 
-    def upload(self, PS, spec, elem, ids):
-        self.R.step.UploadParticles(PS, spec, elem, IsNewPart=np.ones(len(spec), dtype=np.int32), ids=ids)
+    def upload(self, PS, spec, elem, ids, isnew=1):
+        self.R.step.UploadParticles(PS, spec, elem, IsNewPart=np.full(len(spec), isnew, dtype=np.int32), ids=ids)
 
     def set_field(self, E):
         self.R.step.SetField(np.ascontiguousarray(E[int(self.off[self.rank]):int(self.off[self.rank + 1])]))
@@ -126,12 +126,57 @@ class GpuRank:
         return self.R.step.DownloadParticles()
 
 
+def reference_case(a, rank, world, local):
+    """The reference's own multi-rank criterion on its own data: NIG_tracking_DSMC/{periodic,ANSA_box} run with MPI = 1,2,5,10 /
+    1,2 (command_line.ini) and must reproduce the committed PartInt for every rank count.  Push + TriaTracking + migration over
+    the element partition, checked against the state file the reference wrote (tests/test_reference_tracking.py)."""
+    import test_reference_tracking as trt
+    build = trt.periodic_case if a.case == "periodic_ref" else trt.ansa_case
+    mesh, prm, PD0, elem0, PD1, elem1, dt, nsteps = build(hm.TRIATRACKING)
+    PS, spec = np.ascontiguousarray(PD0[:, :6]), PD0[:, 6].astype(np.int32)
+    ids = np.arange(len(spec), dtype=np.int64)
+    off = hm.partition(mesh, world)
+    mine = (elem0 > off[rank]) & (elem0 <= off[rank + 1])
+    eng = GpuRank(mesh, prm, rank, world, local) if a.engine == "gpu" else OracleRank(mesh, prm, rank, world)
+    eng.upload(PS[mine], spec[mine], elem0[mine], ids[mine], isnew=0)
+    eng.set_field(np.zeros((mesh.nElems, 2, 2, 2, 3)))
+    migrated = 0
+    for _ in range(nsteps):
+        before = set(eng.download()["ids"].tolist()) if a.engine == "oracle" else None
+        assert eng.push_track(dt) == 0
+        if before is not None:
+            migrated += len(set(eng.download()["ids"].tolist()) - before)
+    d = eng.download()
+    own = (d["GlobalElemID"] > off[rank]) & (d["GlobalElemID"] <= off[rank + 1])
+    assert own.all(), "rank holds particles of elements it does not own"
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object((d["ids"], d["PartState"], d["GlobalElemID"], migrated), parts, dst=0)
+    if rank == 0:
+        allid = np.concatenate([p[0] for p in parts])
+        o = np.argsort(allid)
+        assert np.array_equal(allid[o], ids), "particles lost or duplicated in migration"
+        PSe = np.concatenate([p[1] for p in parts])[o]
+        ele = np.concatenate([p[2] for p in parts])[o]
+        if a.case == "periodic_ref":
+            trt.check_periodic(PSe, ele, PD1, elem1, mesh.nElems)
+        else:
+            trt.check_ansa(PSe, ele, PD0, PD1, elem1, mesh.nElems)
+        nmig = sum(p[3] for p in parts)
+        assert a.engine != "oracle" or nmig > len(spec), "the case does not exercise the migration"
+        print("MULTI_OK engine=%s world=%d case=%s migrations=%d" % (a.engine, world, a.case, nmig))
+    if a.engine == "gpu":
+        eng.R.close()
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--engine", default="oracle")
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--particles", type=int, default=12000)
     ap.add_argument("--depo", default="cvwm", choices=["cvwm", "sf", "cc"])
+    ap.add_argument("--case", default="synthetic", choices=["synthetic", "periodic_ref", "ansa_ref"])
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,6 +185,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
         dist.init_process_group("gloo")
+    if a.case != "synthetic":
+        return reference_case(a, rank, world, local)
 
     mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 3, 6), 2)
     def params():

@@ -13,9 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "multi_worker.py")
 
 
-def _run(world, engine, port, depo="cvwm"):
+def _run(world, engine, port, depo="cvwm", case="synthetic"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, "--engine", engine, "--depo", depo]
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, "--engine", engine, "--depo", depo, "--case", case]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MULTI_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
@@ -30,6 +30,13 @@ def test_multi_rank_gloo_oracle(world):
 def test_multi_rank_gloo_oracle_shape_function(world, depo):
     """DOF halo of the shape-function deposition over gloo."""
     _run(world, "oracle", 29617 + world, depo=depo)
+
+
+@pytest.mark.parametrize("world,case", [(2, "periodic_ref"), (5, "periodic_ref"), (2, "ansa_ref")])
+def test_multi_rank_gloo_reproduces_the_references_state_files(world, case):
+    """The reference runs NIG_tracking_DSMC/periodic with MPI = 1,2,5,10 and ANSA_box with MPI = 1,2 against one committed
+    PartInt; so do we (element partition of loaddistribution.f90:362-369, migration after tracking)."""
+    _run(world, "oracle", 29640 + world + (10 if case == "ansa_ref" else 0), case=case)
 
 
 @pytest.mark.gpu
