@@ -25,7 +25,8 @@
 //   * shape_function PER DOF: DG_Source(1:4) of regressioncheck/NIG_PIC_maxwell_RK4/single_particle (one electron, 27 x 64
 //     DOFs, r_sf 0.2, alpha 4, 3-D) reproduced to 1.3e-15 once the particle is put where the last Runge-Kutta stage
 //     deposited it (velocity = J/rho from the file, position = 3 fitted numbers, 1.9e-12 s of flight behind the stored end
-//     state; tests/test_reference_shapefunction.py).
+//     state), and the 1-D shape function (alpha 8, periodic, 3-D deposition) of the 3200 resting electrons and ions of
+//     regressioncheck/WEK_PIC_maxwell/plasma_wave to 1e-13 with no fit (tests/test_reference_shapefunction.py).
 // PARITY UNPINNED for what is left: per-particle positions and velocities after interpolation + push in a NON-UNIFORM
 // field and the Boris rotation (B != 0) - the reference's tests hold no such vectors (every candidate needs the HDG solve
 // between steps) - and the charge-conserving / adaptive shape functions per DOF (integrated known answers only); these rest

@@ -30,8 +30,12 @@
                                                            one fast electron on a 3x3x3 mesh, N = 3: DG_Source(1:4) deposited by
                                                            the reference with shape_function (r = 0.2, alpha = 4, 3-D) at the last
                                                            Runge-Kutta stage of the run, and the particle's end state
+  regressioncheck/WEK_PIC_maxwell/plasma_wave/plasma_wave_restart_State_000.00000030000000000.h5
+                                                           3200 electrons and ions at rest on the 60-element mesh of the plasma-wave
+                                                           tutorial (same mesh file), N = 5, and the charge density the reference
+                                                           deposited from them with the 1-D shape_function (r = 0.15, alpha = 8)
 
--> tests/golden/sf_single_particle_reference.npz, tests/golden/parallel_plates_pcoupled_reference.npz, tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
+-> tests/golden/sf_plasma_wave_reference.npz, tests/golden/sf_single_particle_reference.npz, tests/golden/parallel_plates_pcoupled_reference.npz, tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
    tests/golden/cvwm_current_reference.npz
    (committed; the tests never read /root/reference).
 """
@@ -84,6 +88,21 @@ def shape_function_vectors():
         out["mesh_" + ds] = me.read(ds)
     path = os.path.join(HERE, "sf_single_particle_reference.npz")
     np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+def shape_function_1d_vectors():
+    d = "/root/reference/regressioncheck/WEK_PIC_maxwell/plasma_wave"
+    st = H5File(os.path.join(d, "plasma_wave_restart_State_000.00000030000000000.h5"))
+    part, src = st.read("PartData"), st.read("DG_Source")
+    assert part.shape == (3200, 7) and src.shape == (60, 6, 6, 6, 4)
+    assert not part[:, 3:6].any() and not src[..., :3].any()          # particles at rest: no current density
+    me = H5File(os.path.join(d, "plasma_wave_mesh.h5"))               # the tutorial's mesh file, already in hopr_meshes.npz
+    tw = H5File("/root/reference/tutorials/pic-poisson-plasma-wave/plasma_wave_mesh.h5")
+    for ds in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType"):
+        assert np.array_equal(me.read(ds), tw.read(ds))
+    path = os.path.join(HERE, "sf_plasma_wave_reference.npz")
+    np.savez_compressed(path, PartData=part, PartInt=st.read("PartInt"), DG_Source_charge=np.ascontiguousarray(src[..., 3]))
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
@@ -144,6 +163,7 @@ def main():
     current_density_vectors()
     coupled_power_vectors()
     shape_function_vectors()
+    shape_function_1d_vectors()
 
 
 if __name__ == "__main__":

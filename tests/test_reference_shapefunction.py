@@ -16,6 +16,12 @@ fitted position lies 1.9e-12 s of flight behind the stored end state on each axi
 step must.  Three fitted numbers against 6912 values agreeing to round-off: this pins the shape-function kernel
 w_sf (1 - r^2/r_sf^2)^alpha, its 3-D normalisation (InitShapeFunctionDimensionalty, :1245-1246), the DOF coordinates
 Elem_xGP and the element / FIBGM traversal against output of the reference.
+
+Second file (no fit needed): the restart state of regressioncheck/WEK_PIC_maxwell/plasma_wave holds 3200 electrons and ions
+AT REST on the 60-element mesh of the plasma-wave tutorial (N = 5, three periodic vectors) and the charge density the reference
+deposited from them with the 1-D shape function (PIC-shapefunction-dimension 1, direction x, radius 0.15, alpha 8,
+3-D deposition over the y-z plane).  Electrons and ions nearly cancel; all 60 x 216 values are reproduced to 1e-13 of the
+maximum.  This pins the 1-D normalisation (:1196-1198), the periodic images (GetPartPosShifted) and sfDepo3D.
 """
 import os
 
@@ -28,6 +34,26 @@ from piclas_b200.abi import Params, DEPO_SF
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "sf_single_particle_reference.npz")
+GOLDEN_1D = os.path.join(ROOT, "tests", "golden", "sf_plasma_wave_reference.npz")
+QE = 1.60217653E-19
+
+
+def case_1d():
+    """WEK_PIC_maxwell/plasma_wave parameter.ini: electrons / protons, MPF 5.625e9, shape_function 1-D in x, r 0.15, alpha 8."""
+    g, gm = np.load(GOLDEN_1D), np.load(os.path.join(ROOT, "tests", "golden", "hopr_meshes.npz"))
+    mesh = hm.from_hopr_arrays(*[gm["plasma_wave_" + d] for d in ("ElemInfo", "SideInfo", "NodeCoords", "GlobalNodeIDs", "BCType",
+                                                                  "BCNames")], 5, tracking=hm.REFMAPPING)
+    hm.add_fibgm(mesh)
+    hm.add_refmapping_tables(mesh)
+    prm = Params(TrackingMethod=hm.REFMAPPING, DepositionType=DEPO_SF, ChargeIC=(-QE, QE), MassIC=(9.1093826E-31, 1.672621637E-27),
+                 MacroParticleFactor=(5.625e9, 5.625e9))
+    hm.shape_function_setup(mesh, prm, 0.15, 8, dim_sf=1, dim_sf_dir=1)
+    PD, PI = g["PartData"], g["PartInt"]
+    elem = np.zeros(len(PD), dtype=np.int32)
+    for e in range(mesh.nElems):
+        elem[PI[0, e]:PI[1, e]] = e + 1
+    assert (elem > 0).all()
+    return mesh, prm, np.ascontiguousarray(PD[:, :6]), PD[:, 6].astype(np.int32), elem, g["DG_Source_charge"]
 
 
 def case():
@@ -92,8 +118,23 @@ def test_oracle_reproduces_the_references_shape_function_source_per_dof():
     assert np.all(lag > 1.8e-12) and np.all(lag < 2.1e-12), lag
 
 
+def test_oracle_reproduces_the_references_1d_shape_function_charge_density():
+    mesh, prm, PS, spec, elem, rho = case_1d()
+    orc = Oracle(mesh, prm)
+    xi, _, bad = orc.position_in_ref_elem(PS[:, :3], elem)
+    assert bad == 0 and np.abs(xi).max() <= 1.0          # the particles are in the elements the reference's PartInt names
+    src, _ = orc.deposit(PS, spec, elem, np.ones(len(spec), dtype=np.int32), PartPosRef=xi)
+    orc.close()
+    assert not src[..., :3].any()
+    assert np.abs(src[..., 3] - rho).max() <= 5e-13 * np.abs(rho).max()
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/regressioncheck"), reason="reference tree not mounted")
 def test_shape_function_fixture_is_what_the_reference_files_hold():
+    from piclas_b200.h5mini import H5File as _H
+    w = _H("/root/reference/regressioncheck/WEK_PIC_maxwell/plasma_wave/plasma_wave_restart_State_000.00000030000000000.h5")
+    g1 = np.load(GOLDEN_1D)
+    assert np.array_equal(w.read("PartData"), g1["PartData"]) and np.array_equal(w.read("DG_Source")[..., 3], g1["DG_Source_charge"])
     from piclas_b200.h5mini import H5File
     d = "/root/reference/regressioncheck/NIG_PIC_maxwell_RK4/single_particle/"
     st, me, g = H5File(d + "single-particle_reference_State_000.0000000500000000.h5"), H5File(d + "single-particle_mesh.h5"), np.load(GOLDEN)
@@ -120,3 +161,15 @@ def test_gpu_reproduces_the_references_shape_function_source_per_dof(arith):
         src, _ = gpu.Deposition(want_nodesource=False)
     for c in range(4):
         assert np.abs(src[..., c] - S[..., c]).max() <= 1e-12 * np.abs(S[..., c]).max(), c
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arith", [0, 1], ids=["reference-order", "restructured"])
+def test_gpu_reproduces_the_references_1d_shape_function_charge_density(arith):
+    from piclas_b200.particle_step import ParticleStep
+    mesh, prm, PS, spec, elem, rho = case_1d()
+    prm.arithmetic = arith
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(PS, spec, elem)              # PartPosRef from GetPositionInRefElem on the device, as at emission
+        src, _ = gpu.Deposition(want_nodesource=False)
+    assert np.abs(src[..., 3] - rho).max() <= 1e-12 * np.abs(rho).max()
