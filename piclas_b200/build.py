@@ -47,10 +47,29 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_EXE = os.path.join(HOST_DIR, "run_case")
+
+
+def build_host(force: bool = False) -> str:
+    """The compiled host driver above the C ABI (piclas_b200/host): plain C++17, links libpiclas_gpu.so."""
+    deps = [os.path.join(HOST_DIR, f) for f in ("run_case.cpp", "particle_step.hpp", "pgpu_case.hpp", "pgpu_fields.inc")]
+    deps += [os.path.join(ROOT, "include", "piclas_gpu.h"), LIB]
+    if not force and os.path.exists(HOST_EXE) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_EXE) for d in deps):
+        return HOST_EXE
+    cmd = [os.environ.get("CXX", "g++"), "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           "-o", HOST_EXE, os.path.join(HOST_DIR, "run_case.cpp"), "-L", HERE, "-lpiclas_gpu", "-Wl,-rpath,$ORIGIN/.."]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("host build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return HOST_EXE
+
+
 def build_oracle() -> None:
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
 
 
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))
     build_oracle()
