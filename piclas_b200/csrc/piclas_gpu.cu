@@ -258,25 +258,6 @@ __global__ void k_soa_to_aos(PartBuf pb, int64_t src0, int64_t n, double* __rest
   if (ids) ids[i] = pb.id ? pb.id[p] : -1;
 }
 
-// message layout of one migrating particle (particle_mpi.f90:472-502, TriaTracking, no LSERK/vMPF/DSMC):
-// PartState(1:6), REAL(PartSpecies), REAL(PEM%GlobalElemID) [, particle id bits when ids are carried]
-__global__ void k_pack_emigrants(PartBuf pb, int64_t src0, int64_t n, int cs, int withRef, double* __restrict__ buf) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int64_t p = src0 + i;
-  double* b = buf + i * cs;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    b[d] = pb.x[d][p];
-    b[3 + d] = pb.v[d][p];
-  }
-  int o = 6;
-  if (withRef) { b[6] = pb.xi[0][p]; b[7] = pb.xi[1][p]; b[8] = pb.xi[2][p]; o = 9; }   // PartPosRef (RefMapping)
-  b[o] = (double)((pb.meta[p] & META_SPEC_MASK) + 1);
-  b[o + 1] = (double)pb.elem[p];
-  if (cs > o + 2) b[o + 2] = __longlong_as_double(pb.id ? pb.id[p] : -1);
-}
-
 // MPIParticleRecv unpack (particle_mpi.f90:831-989): received particles are appended; IsNewPart = F
 __global__ void k_unpack_immigrants(PartBuf pb, int64_t dst0, int64_t n, int cs, int withRef, const double* __restrict__ buf) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
