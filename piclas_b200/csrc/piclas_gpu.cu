@@ -361,6 +361,8 @@ __global__ void __launch_bounds__(EM_NT) k_emig_compact(const uint32_t* __restri
     }
 }
 
+// message layout of one migrating particle (particle_mpi.f90:472-502, no LSERK/vMPF/DSMC): PartState(1:6) [, PartPosRef(1:3) with
+// RefMapping], REAL(PartSpecies), REAL(PEM%GlobalElemID) [, particle id bits when ids are carried].
 // message i <- particle emigIdx[perm[i]] (grouped by destination rank); the particle's key becomes "removed"
 __global__ void k_pack_emigrants_idx(PartBuf pb, const uint32_t* __restrict__ emigIdx, const uint32_t* __restrict__ perm, int64_t n, int cs,
                                      int withRef, double* __restrict__ buf, uint32_t* __restrict__ keys, uint32_t removedKey) {
