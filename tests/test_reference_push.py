@@ -20,7 +20,7 @@ What the file holds, and how it is used:
   analytical solution the check's readme.md describes, written by the `P_anlay` test hook quoted there.  They are the
   reference's *known answer* for this case (its tolerance: 1e-2); the Leapfrog series above coincides with that
   expression, so this repo must match them up to the charge constant, (q'/q)^2 - 1 = 1.298e-7, and the closed form with
-  its own charge to 1e-12.  (A present-day run of the reference deviates from these rows by up to 1.2e-3 once
+  its own charge to 1e-12.  (A present-day run of the reference deviates from these rows by a few 1e-3 once
   |v| > 1e6 m/s, because CalcEkinPart switches to (gamma - 1) m c^2 there, particle_analyze_pure.f90:66-76; the kinetic
   energy here is the classical one throughout, as in the analytical solution.)
 
