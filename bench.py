@@ -191,6 +191,32 @@ def config_dict(args, n_total):
             "l2": "inputs (>=26 GB of particle state at full size) exceed the 126 MB L2; no flush needed"}
 
 
+def deposited_charge(mesh, rho):
+    """CalcDepositedCharge (pic_analyze.f90:165-175): sum over all DOFs of wGP_i wGP_j wGP_k * PartSource(4) / sJ."""
+    w = mesh.wGP[:, None, None] * mesh.wGP[None, :, None] * mesh.wGP[None, None, :]
+    return float(np.sum(rho * w[None] / mesh.sJ))
+
+
+def full_size_checks(gpu, mesh, n_expected, charge_per_particle):
+    """Size-independent properties at the benchmark's full size (outside every timed region): the cell_volweight_mean
+    deposition conserves charge on the periodic box, the device reductions see every particle, nothing is lost."""
+    try:
+        n1 = mesh.N + 1
+        rho = np.empty((mesh.nElems, n1, n1, n1))
+        gpu.Deposition(want_partsource=False, want_nodesource=False)
+        gpu.ChargeDensity(out=rho)
+        n = gpu.NumParticles()
+        q_dep, q_part = deposited_charge(mesh, rho), n * charge_per_particle
+        ekin, npart = gpu.KineticEnergy()
+        return {"particles": int(n), "particles_expected": int(n_expected), "particles_in_reduction": int(npart.sum()),
+                "deposited_charge": q_dep, "particle_charge": q_part, "charge_conservation_rel_err": abs(q_dep - q_part) / abs(q_part),
+                "kinetic_energy_J": float(ekin.sum()),
+                "ok": bool(n == n_expected and int(npart.sum()) == n and abs(q_dep - q_part) <= 1e-12 * abs(q_part)
+                           and np.isfinite(ekin).all())}
+    except Exception as e:   # a failed check must not cost the measurement
+        return {"ok": False, "error": repr(e)[:300]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -293,6 +319,7 @@ def run_b200(args):
         t_rho = time.perf_counter() - t0
         e2e["charge_only"] = {"value": n_total * args.e2e_steps / t_rho, "ms_per_step": 1e3 * t_rho / args.e2e_steps,
                               "d2h_bytes_per_step": int(rho_h.nbytes)}
+    checks = full_size_checks(gpu, mesh, n_total, -QE * 1.0e3)
     gpu.close()
 
     peak, peak_src = hbm_peak()
@@ -309,7 +336,8 @@ def run_b200(args):
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, n_total), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "event_ms_per_step": ev_ms / args.steps, "particles_end": int(n_now), "lost": int(lost), "roofline": roofline}
+            "event_ms_per_step": ev_ms / args.steps, "particles_end": int(n_now), "lost": int(lost), "roofline": roofline,
+            "checks": checks}
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args, args.N)
     print(json.dumps(line))
