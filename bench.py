@@ -10,6 +10,8 @@ TimeStepPoissonByBorisLeapfrog (interpolate, push, track, re-sort by element).
   e2e       : same step through the C ABI with HOST buffers: E host->device before the push, PartSource device->host
               after the deposition, both inside the timed region
   roofline  : dominant kernel (interpolate+push+track) algorithmic bytes / its CUDA-event time vs measured HBM peak
+  checks    : size-independent properties at the full size, outside the timed regions: deposited charge vs the particles'
+              charge (CalcDepositedCharge, <= 1e-12), particle counts from the device reductions, nothing lost
   cpu_baseline / --impl reference : the CPU oracle (restated reference path; the Fortran reference cannot be built
               in this image) on the box's host cores, on a bounded sample of the same workload
 """
