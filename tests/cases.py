@@ -137,6 +137,24 @@ def uniform_plasma(mesh, n, seed, vth_cells=0.2, dt=1.0, species=1, nspecies=1):
     return PS, spec
 
 
+def sin_deviation(xmin, xmax, nx, ny, nz, amplitude, wavenumber):
+    """SetParticlePositionSinDeviation (particle_emission_tools.f90:1235-1293), loop order and expressions as written there:
+    x = xmin + x_pos + A sin(k 2 pi / xlen * x_pos) with x_pos = i x_step - x_step / 2; y, z on the cell centres."""
+    xmin, xmax = np.asarray(xmin, dtype=np.float64), np.asarray(xmax, dtype=np.float64)
+    xlen, ylen, zlen = np.abs(xmax - xmin)
+    pilen = 2.0 * np.pi / xlen
+    x_step, y_step, z_step = xlen / nx, ylen / ny, zlen / nz
+    pos = []
+    for i in range(1, nx + 1):
+        x_pos = i * x_step - x_step * 0.5
+        x = xmin[0] + x_pos + amplitude * np.sin(wavenumber * pilen * x_pos)
+        for j in range(1, ny + 1):
+            y = xmin[1] + j * y_step - y_step * 0.5
+            for k in range(1, nz + 1):
+                pos.append((x, y, xmin[2] + k * z_step - z_step * 0.5))
+    return np.array(pos)
+
+
 def electron_params(**kw):
     d = dict(ChargeIC=(-QE,), MassIC=(ME,), MacroParticleFactor=(1.0e3,), DepositionType=DEPO_CVWM,
              TimeDiscMethod=TIMEDISC_BORIS_LEAPFROG, carryParticleIDs=1)

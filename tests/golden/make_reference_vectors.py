@@ -34,8 +34,11 @@
                                                            3200 electrons and ions at rest on the 60-element mesh of the plasma-wave
                                                            tutorial (same mesh file), N = 5, and the charge density the reference
                                                            deposited from them with the 1-D shape_function (r = 0.15, alpha = 8)
+  regressioncheck/NIG_PIC_poisson_plasma_wave/poisson/plasma_wave_restart_State_000.00000000000000000.h5
+                                                           the 25 + 25 particles the reference's sin_deviation emission placed
+                                                           (initial condition of the plasma-wave configuration)
 
--> tests/golden/sf_plasma_wave_reference.npz, tests/golden/sf_single_particle_reference.npz, tests/golden/parallel_plates_pcoupled_reference.npz, tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
+-> tests/golden/emission_sin_deviation_reference.npz, tests/golden/sf_plasma_wave_reference.npz, tests/golden/sf_single_particle_reference.npz, tests/golden/parallel_plates_pcoupled_reference.npz, tests/golden/plasma_ball_cvwm_reference.npz, tests/golden/hopr_meshes.npz, tests/golden/tracking_dsmc_reference.npz,
    tests/golden/cvwm_current_reference.npz
    (committed; the tests never read /root/reference).
 """
@@ -106,6 +109,15 @@ def shape_function_1d_vectors():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def emission_vectors():
+    st = H5File("/root/reference/regressioncheck/NIG_PIC_poisson_plasma_wave/poisson/plasma_wave_restart_State_000.00000000000000000.h5")
+    part = st.read("PartData")
+    assert part.shape == (50, 7)
+    path = os.path.join(HERE, "emission_sin_deviation_reference.npz")
+    np.savez_compressed(path, PartData=part)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def tracking_vectors():
     """Particle states the reference wrote before and after pure push + tracking (DSMC time step without collisions:
     timedisc_TimeStep_DSMC.f90:127-149 is x += v dt, then PerformTracking)."""
@@ -164,6 +176,7 @@ def main():
     coupled_power_vectors()
     shape_function_vectors()
     shape_function_1d_vectors()
+    emission_vectors()
 
 
 if __name__ == "__main__":
