@@ -51,12 +51,20 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--arithmetic", type=int, default=1, help="0: reference operation order, 1: restructured (<=1e-12)")
+    ap.add_argument("--variant", default="tria_cvwm", choices=["tria_cvwm", "ref_sf"],
+                    help="tria_cvwm: TriaTracking + cell_volweight_mean (the headline workload); ref_sf: the secondary variant of "
+                         "SURVEY.md 8d, RefMapping + shape_function (r_sf = 1.5 h, alpha = 2, 3-D), one GPU only")
     return ap.parse_args()
 
 
-def workload(nelem, N):
+def workload(nelem, N, variant="tria_cvwm"):
     from piclas_b200 import hostmesh as hm
-    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (nelem, nelem, nelem), N)
+    if variant == "ref_sf":
+        mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (nelem, nelem, nelem), N, tracking=hm.REFMAPPING)
+        hm.add_fibgm(mesh)                                       # one background cell per element
+        hm.add_refmapping_tables(mesh, bc_halo_eps=2.0 / nelem)  # BC (periodic) sides within two cells: > 6 sigma of a step's flight
+    else:
+        mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (nelem, nelem, nelem), N)
     h = 1.0 / nelem
     dt = 1.0e-9
     vth = 0.2 * h / dt
@@ -186,6 +194,12 @@ def cpu_baseline(args, N, threads=None, steps=None, warmup=1):
 
 
 def config_dict(args, n_total):
+    if getattr(args, "variant", "tria_cvwm") == "ref_sf":
+        return {"workload": "synthetic 3-periodic box %d^3 hexahedra N=%d NGeo=1, %.3g electrons, RefMapping + shape_function "
+                            "(r_sf = 1.5 h, alpha = 2, 3-D), Boris-Leapfrog (secondary variant of SURVEY.md 8d)" % (args.nelem, args.N, n_total),
+                "elements": args.nelem ** 3, "N": args.N, "particles": int(n_total),
+                "tracking": "refmapping", "deposition": "shape_function", "timedisc": "Boris-Leapfrog (508)",
+                "l2": "inputs exceed the 126 MB L2; no flush needed"}
     return {"workload": "synthetic 3-periodic box %d^3 hexahedra N=%d NGeo=1, %.3g electrons, TriaTracking + "
                         "cell_volweight_mean, Boris-Leapfrog (BASELINE.json configs[4])" % (args.nelem, args.N, n_total),
             "elements": args.nelem ** 3, "N": args.N, "particles": int(n_total),
@@ -199,7 +213,7 @@ def deposited_charge(mesh, rho):
     return float(np.sum(rho * w[None] / mesh.sJ))
 
 
-def full_size_checks(gpu, mesh, n_expected, charge_per_particle):
+def full_size_checks(gpu, mesh, n_expected, charge_per_particle, charge_tol=1e-12):
     """Size-independent properties at the benchmark's full size (outside every timed region): the cell_volweight_mean
     deposition conserves charge on the periodic box, the device reductions see every particle, nothing is lost."""
     try:
@@ -213,7 +227,7 @@ def full_size_checks(gpu, mesh, n_expected, charge_per_particle):
         return {"particles": int(n), "particles_expected": int(n_expected), "particles_in_reduction": int(npart.sum()),
                 "deposited_charge": q_dep, "particle_charge": q_part, "charge_conservation_rel_err": abs(q_dep - q_part) / abs(q_part),
                 "kinetic_energy_J": float(ekin.sum()),
-                "ok": bool(n == n_expected and int(npart.sum()) == n and abs(q_dep - q_part) <= 1e-12 * abs(q_part)
+                "ok": bool(n == n_expected and int(npart.sum()) == n and abs(q_dep - q_part) <= charge_tol * abs(q_part)
                            and np.isfinite(ekin).all())}
     except Exception as e:   # a failed check must not cost the measurement
         return {"ok": False, "error": repr(e)[:300]}
@@ -239,6 +253,8 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        if args.variant != "tria_cvwm":
+            raise SystemExit("bench.py: --variant %s runs on one GPU only" % args.variant)
         from piclas_b200.multi import run_bench_multi
         return run_bench_multi(args, rank, world, local)
     if not torch.cuda.is_available():
@@ -246,10 +262,15 @@ def run_b200(args):
     from piclas_b200.abi import Params
     from piclas_b200.particle_step import ParticleStep
 
-    mesh, E, dt, vth = workload(args.nelem, args.N)
+    mesh, E, dt, vth = workload(args.nelem, args.N, args.variant)
     n_total = int(args.particles)
     prm = Params(ChargeIC=(-QE,), MassIC=(ME,), MacroParticleFactor=(1.0e3,), device=local, maxParticleNumber=n_total + 1024,
                  arithmetic=args.arithmetic)
+    if args.variant == "ref_sf":
+        from piclas_b200 import hostmesh as hm
+        from piclas_b200.abi import DEPO_SF
+        prm.TrackingMethod, prm.DepositionType = hm.REFMAPPING, DEPO_SF
+        hm.shape_function_setup(mesh, prm, 1.5 / args.nelem, 2, dim_sf=3)
     gpu = ParticleStep(mesh, prm)
     rng = np.random.default_rng(args.seed)
     chunk = 10_000_000
@@ -321,7 +342,8 @@ def run_b200(args):
         t_rho = time.perf_counter() - t0
         e2e["charge_only"] = {"value": n_total * args.e2e_steps / t_rho, "ms_per_step": 1e3 * t_rho / args.e2e_steps,
                               "d2h_bytes_per_step": int(rho_h.nbytes)}
-    checks = full_size_checks(gpu, mesh, n_total, -QE * 1.0e3)
+    # the plain shape function is not charge conserving at the DOFs (the reference accepts 5 %, NIG_PIC_Deposition analyze.ini)
+    checks = full_size_checks(gpu, mesh, n_total, -QE * 1.0e3, charge_tol=1e-12 if args.variant == "tria_cvwm" else 5e-2)
     gpu.close()
 
     peak, peak_src = hbm_peak()

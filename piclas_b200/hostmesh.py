@@ -673,12 +673,21 @@ def add_refmapping_tables(mesh: ParticleMesh, bc_halo_eps=None, RefMappingEps=1e
     rows = []
     off = 0
     bc_elem = bc_sides // 6
+    # bc_sides ascends, so the BC sides of element e are the contiguous range own_lo[e]:own_hi[e] (no scan per element);
+    # with a halo distance all neighbourhood queries go through the tree in one call and elements far from every BC side
+    # (the bulk of a large mesh) are skipped without touching the side arrays
+    own_lo = np.searchsorted(bc_elem, np.arange(nE), side="left")
+    own_hi = np.searchsorted(bc_elem, np.arange(nE), side="right")
+    all_idx = np.arange(bc_sides.size)
+    balls = None if full else tree.query_ball_point(bary, bc_halo_eps + ElemRadius + maxr)
     for e in range(nE):
-        own = bc_sides[bc_elem == e] if bc_sides.size else bc_sides
+        own = bc_sides[own_lo[e]:own_hi[e]]
         if full:
-            other_idx = np.nonzero(bc_elem != e)[0]
+            other_idx = np.concatenate([all_idx[:own_lo[e]], all_idx[own_hi[e]:]])
         else:
-            cand = np.array(sorted(tree.query_ball_point(bary[e], bc_halo_eps + ElemRadius[e] + maxr)), dtype=np.int64)
+            if not balls[e]:
+                continue                                                  # own sides would be in the ball: no BC side in reach
+            cand = np.array(sorted(balls[e]), dtype=np.int64)
             if cand.size:
                 cand = cand[bc_elem[cand] != e]
                 be = bc_elem[cand]
