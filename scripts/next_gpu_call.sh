@@ -9,3 +9,5 @@ python -m pytest tests/test_reference_deposition.py tests/test_reference_push.py
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o $OUT/fp64_peak scripts/fp64_peak.cu && $OUT/fp64_peak | tee $OUT/n_fp64_peak.json
 python -m pytest tests -m gpu -x -q > $OUT/n_all_gpu_tests.log 2>&1; tail -5 $OUT/n_all_gpu_tests.log
 python bench.py > $OUT/n_bench.json 2> $OUT/n_bench.err; tail -c 2500 $OUT/n_bench.json
+# secondary variant of SURVEY.md 8d (RefMapping + shape_function), first at a tenth of the particles
+python bench.py --variant ref_sf --particles 5e7 --steps 5 --warmup 3 --no-cpu > $OUT/n_bench_ref_sf.json 2> $OUT/n_bench_ref_sf.err; tail -c 1500 $OUT/n_bench_ref_sf.json
