@@ -127,3 +127,62 @@ def test_ctypes_prototypes_have_the_headers_arity():
         fn = getattr(so, name)
         if fn.argtypes is not None:
             assert len(fn.argtypes) == nargs, (name, len(fn.argtypes), nargs)
+
+
+def _c_prototypes():
+    """name -> (return type, [(type, stars, name)]) from the header."""
+    out = {}
+    for m in re.finditer(r"\b(int|int64_t|const char \*)\s*(piclas_gpu_\w+)\s*\((.*?)\);", _strip_c_comments(HDR), flags=re.S):
+        args = []
+        text = " ".join(m.group(3).split())
+        if text not in ("void", ""):
+            for a in text.split(","):
+                am = re.match(r"\s*(?:const\s+)?(\w+)\s*(\**)\s*(\w+)\s*$", a)
+                assert am, a
+                args.append((am.group(1), len(am.group(2)), am.group(3)))
+        out[m.group(2)] = (m.group(1).replace(" ", ""), args)
+    return out
+
+
+def test_fortran_argument_types_and_value_attributes_match_the_c_prototypes():
+    """Parsed with numpy.f2py's crackfortran (no Fortran compiler in the image): by-value C scalars need VALUE and the same
+    kind; C pointers are either a by-reference dummy of the same kind or TYPE(C_PTR),VALUE; `void **` is TYPE(C_PTR) by
+    reference; struct pointers are by-reference derived types; return types agree."""
+    import numpy.f2py.crackfortran as cf
+    cf.verbose = 0
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:           # crackfortran may leave scratch files in the working directory
+        os.chdir(d)
+        try:
+            mod = cf.crackfortran([os.path.join(ROOT, "piclas_b200", "fortran", "mod_particle_gpu.f90")])[0]
+        finally:
+            os.chdir(cwd)
+    funcs = {f["name"]: f for b in mod["body"] if b["block"] == "interface" for f in b["body"]}
+    kinds = {"int32_t": ("integer", "c_int32_t"), "int64_t": ("integer", "c_int64_t"), "double": ("real", "c_double"),
+             "int": ("integer", "c_int")}
+    protos = _c_prototypes()
+    assert sorted(protos) == sorted(funcs)
+    for name, (ret, cargs) in protos.items():
+        f = funcs[name]
+        rv = f["vars"][name]
+        if ret == "constchar*":
+            assert rv["typespec"] == "type" and rv["typename"] == "c_ptr", name
+        else:
+            assert (rv["typespec"], rv["kindselector"]["kind"]) == kinds[ret], name
+        assert len(f["args"]) == len(cargs), name
+        for fa, (ctype, stars, cname) in zip(f["args"], cargs):
+            v = f["vars"][fa]
+            where = "%s(%s)" % (name, cname)
+            assert fa == cname.lower(), where                                  # same argument names, same order
+            value = "value" in v.get("attrspec", [])
+            is_cptr = v["typespec"] == "type" and v.get("typename") == "c_ptr"
+            if stars == 0:
+                assert value and (v["typespec"], v["kindselector"]["kind"]) == kinds[ctype], where
+            elif stars == 2:
+                assert ctype == "void" and is_cptr and not value, where
+            elif ctype.startswith("pgpu_"):
+                assert v["typespec"] == "type" and v["typename"] == ctype and not value, where
+            elif is_cptr:
+                assert value, where
+            else:
+                assert not value and (v["typespec"], v["kindselector"]["kind"]) == kinds[ctype], where
