@@ -421,6 +421,18 @@ def test_product_path_has_no_cpu_fallback():
     import piclas_b200.particle_step as ps
     src = open(ps.__file__).read() + open(os.path.join(ROOT, "piclas_b200", "multi.py")).read()
     assert "oracle" not in src.lower().replace("the cpu (gloo) tests, which drive it with a cpu engine", "")
+    # no source file of the package or of the boundary loads, links or names the checker's library; the only mentions allowed are
+    # the build helper that compiles it (building the checker is not using it) and one docstring
+    exts = (".py", ".cu", ".cuh", ".h", ".hpp", ".cpp", ".f90", ".inc")
+    for base in (os.path.join(ROOT, "piclas_b200"), os.path.join(ROOT, "include")):
+        for d, _, files in os.walk(base):
+            for f in files:
+                if not f.endswith(exts):
+                    continue
+                text = open(os.path.join(d, f), errors="ignore").read().lower()
+                assert "liboracle" not in text and "oracle_lib" not in text and "piclas_oracle" not in text, f
+                if f not in ("build.py", "hostmesh.py"):
+                    assert "oracle" not in text, f
     import torch
     if not torch.cuda.is_available():
         mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (2, 2, 2), 1)
