@@ -23,7 +23,17 @@ def _has_gpu():
         return False
 
 
+# Modules whose -m gpu tests were written after the round-1 GPU minutes were spent run last, the most involved ones at the very
+# end, so that under `pytest -x` a failure there cannot hide tests that have already passed on a B200.
+_RUN_LAST = ["test_reference_deposition", "test_reference_shapefunction", "test_zz_host_cpp", "test_zz_gpu_properties",
+             "test_reference_push", "test_reference_tracking"]
+
+
 def pytest_collection_modifyitems(config, items):
+    def rank(it):
+        name = os.path.splitext(os.path.basename(str(it.fspath)))[0]
+        return _RUN_LAST.index(name) + 1 if name in _RUN_LAST else 0
+    items.sort(key=rank)                 # stable: the order inside a module and among the other modules is kept
     if _has_gpu():
         return
     skip = pytest.mark.skip(reason="no CUDA device")
