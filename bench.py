@@ -149,6 +149,24 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# FP64 work the interpolate+push+track phase executes per particle (profiles/r1_final_stalls_k_interp_push.txt: DFMA x 2 + DMUL + DADD
+# warp instructions x 29.3 active lanes / 7.8125e6 particles): the numerator of the FP64 roofline, the bound SURVEY.md F7 expects
+FP64_FLOP_PER_PARTICLE_PUSH = 1360.0
+
+
+def fp64_roofline(n_particles, t_push_s):
+    """Second roofline of the dominant phase, reported once the FP64 peak has been measured (scripts/fp64_peak.cu writes
+    profiles/fp64_peak.json); None until then."""
+    p = os.path.join(ROOT, "profiles", "fp64_peak.json")
+    try:
+        peak = float(json.load(open(p))["fp64_tflops"])
+    except Exception:
+        return None
+    achieved = FP64_FLOP_PER_PARTICLE_PUSH * n_particles / t_push_s / 1e12 if t_push_s > 0 else 0.0
+    return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "flop_per_particle": FP64_FLOP_PER_PARTICLE_PUSH, "peak_source": "measured (profiles/fp64_peak.json, scripts/fp64_peak.cu)"}
+
+
 def measured_traffic(n_particles):
     """DRAM bytes of the dominant phase per launch: dram__bytes_read+write per particle from the committed `ncu --set full`
     capture (profiles/r1_traffic.json, taken at the same particles per element) times the particles of this launch."""
@@ -356,6 +374,9 @@ def run_b200(args):
                 "step_frac": (ALG_BYTES_PER_PARTICLE_STEP * n_total * args.steps / wall / 1e9) / peak,
                 "phase_ms": {"deposit_particles": phases[0], "deposit_nodes_dofs": phases[1], "interp_push_track": phases[2],
                              "sort_permute": phases[3]}}
+    f64 = fp64_roofline(n_total, t_push)
+    if f64 is not None:
+        roofline["fp64"] = f64
     line = {"metric": "particle-steps/s (interp+push+track+depo)", "value": value, "unit": "particle-steps/s",
             "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
