@@ -40,3 +40,9 @@ def test_big_cell_and_property_bodies(oracle_device, monkeypatch):
     monkeypatch.setattr(t_prop, "NE", 10)
     monkeypatch.setattr(t_prop, "NPART", 200000)
     t_prop.test_conservation_ownership_layout_and_idempotence(0)
+
+
+def test_smoke_body(oracle_device, capsys):
+    import __graft_entry__ as entry
+    entry.smoke()
+    assert "smoke ok" in capsys.readouterr().out
