@@ -186,3 +186,34 @@ def test_fortran_argument_types_and_value_attributes_match_the_c_prototypes():
                 assert value, where
             else:
                 assert not value and (v["typespec"], v["kindselector"]["kind"]) == kinds[ctype], where
+
+
+def test_ctypes_argument_types_match_the_c_prototypes():
+    from piclas_b200 import lib
+    so = lib.load()
+    scalar = {"double": C.c_double, "int64_t": C.c_int64, "int32_t": C.c_int32, "int": C.c_int}
+    pointer = {"double": abi.c_f64p, "int32_t": abi.c_i32p, "int64_t": abi.c_i64p,
+               "pgpu_mesh_t": C.POINTER(abi.pgpu_mesh_t), "pgpu_params_t": C.POINTER(abi.pgpu_params_t)}
+    checked = 0
+    for name, (ret, cargs) in _c_prototypes().items():
+        fn = getattr(so, name)
+        if ret == "int64_t":
+            assert fn.restype is C.c_int64, name
+        elif ret == "constchar*":
+            assert fn.restype is C.c_char_p, name
+        if fn.argtypes is None:
+            assert not cargs, name + " takes arguments but has no ctypes prototype"
+            continue
+        for at, (ctype, stars, cname) in zip(fn.argtypes, cargs):
+            want = scalar[ctype] if stars == 0 else (C.POINTER(C.c_void_p) if stars == 2 else pointer[ctype])
+            assert at is want, "%s(%s): ctypes %s, header %s%s" % (name, cname, at, ctype, "*" * stars)
+            checked += 1
+    assert checked >= 40
+
+
+def test_missing_library_is_an_error_not_a_fallback(monkeypatch, tmp_path):
+    from piclas_b200 import lib
+    monkeypatch.setattr(lib, "_lib", None)
+    monkeypatch.setattr(lib, "LIB_PATH", str(tmp_path / "libpiclas_gpu.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lib.load()
