@@ -42,7 +42,7 @@ struct RelocKey {
     const double* b = T.ElemBary + (size_t)(e - 1) * 3;
     const double d0 = x[0] - b[0], d1 = x[1] - b[1], d2 = x[2] - b[2];
     const double D = (d0 * d0 + d1 * d1) + d2 * d2;
-    return (D > T.ElemRadius2[e - 1]) ? -HUGE_D : D;
+    return (D <= T.ElemRadius2[e - 1]) ? D : -HUGE_D;   // (a NaN distance is out of reach)
   }
 };
 // SinglePointToElement (particle_localization.f90:81-190): elements out of reach carry -1 and are skipped.

@@ -235,6 +235,7 @@ def test_selection_order_is_the_stable_insertion_sort():
     import tempfile
     src = r'''
 #include "select.cuh"
+#include <cmath>
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -254,6 +255,15 @@ int main() {
     SortedVisit sv; const Arr a{D.data()};
     for (int i = next_in_sorted_order(n, a, skip, sv); i >= 0 && (int)got.size() <= n; i = next_in_sorted_order(n, a, skip, sv)) got.push_back(i);
     if (got != want) { std::printf("MISMATCH %d\n", trial); return 1; }
+  }
+  // keys that do not order (NaN) must not make the visit endless: at most n entries are returned
+  {
+    const double nan = std::nan("");
+    const double D[5] = {1.0, nan, 0.5, nan, 2.0};
+    SortedVisit sv; const Arr a{D};
+    int returned = 0;
+    for (int i = next_in_sorted_order(5, a, skip, sv); i >= 0; i = next_in_sorted_order(5, a, skip, sv)) if (++returned > 5) break;
+    if (returned > 5) { std::printf("ENDLESS\n"); return 1; }
   }
   std::printf("OK\n");
   return 0;
