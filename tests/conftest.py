@@ -31,7 +31,7 @@ _RUN_LAST = ["test_reference_deposition", "test_reference_shapefunction", "test_
 
 def pytest_collection_modifyitems(config, items):
     def rank(it):
-        name = os.path.splitext(os.path.basename(str(it.fspath)))[0]
+        name = os.path.splitext(os.path.basename(str(getattr(it, "path", None) or it.fspath)))[0]
         return _RUN_LAST.index(name) + 1 if name in _RUN_LAST else 0
     items.sort(key=rank)                 # stable: the order inside a module and among the other modules is kept
     if _has_gpu():
