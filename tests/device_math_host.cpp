@@ -30,6 +30,48 @@ static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 
 static double rel(double a, double b, double scale) { return std::fabs(a - b) / scale; }
 
+#ifdef DEVMATH_SHARED
+// ---- C entry points for tests/test_device_math_on_host.py: the reference-order device functions next to the oracle -------------
+#include <cstring>
+extern "C" {
+void dm_set_newton_consts(const double* XiCL, const double* wBaryCL, double RefMappingEps, int RefMappingGuess) {
+  for (int i = 0; i < 2; ++i) { cst.XiCL[i] = XiCL[i]; cst.wBaryCL[i] = wBaryCL[i]; }
+  cst.RefMappingEps = RefMappingEps;
+  cst.RefMappingGuess = RefMappingGuess;
+}
+void dm_lagrange(int NP, double x, const double* xGP, const double* wBary, double* L) {
+  switch (NP) {
+    case 2: lagrange_polys<2>(x, xGP, wBary, L); break;
+    case 3: lagrange_polys<3>(x, xGP, wBary, L); break;
+    case 4: lagrange_polys<4>(x, xGP, wBary, L); break;
+    case 6: lagrange_polys<6>(x, xGP, wBary, L); break;
+    default: lagrange_polys<8>(x, xGP, wBary, L); break;
+  }
+}
+// GetPositionInRefElem on one element whose tables are copied into a GeoElem exactly as piclas_gpu_init does
+void dm_position_in_ref_elem(const double* XCL24, const double* dXCL72, const double* bary3, const double* xez18, const double* slen6,
+                             int64_t n, const double* x, int forceMode, double* xi, int32_t* status) {
+  GeoElem g;
+  std::memset(&g, 0, sizeof g);
+  std::memcpy(g.XCL, XCL24, 24 * 8);
+  std::memcpy(g.dXCL, dXCL72, 72 * 8);
+  std::memcpy(g.bary, bary3, 3 * 8);
+  std::memcpy(g.xez, xez18, 18 * 8);
+  std::memcpy(g.slen, slen6, 6 * 8);
+  for (int64_t i = 0; i < n; ++i) status[i] = position_in_ref_elem(&g, x + 3 * i, xi + 3 * i, forceMode != 0, true);
+}
+// ParticleInsideQuad3D on one element: corners (tensor order), side -> corner map, concave mask as in TriaElem
+void dm_inside_quad3d(const double* corner24, const int32_t* sideNode24, int concaveMask, int64_t n, const double* x, int32_t* inside,
+                      uint32_t* mask) {
+  TriaElem t;
+  std::memset(&t, 0, sizeof t);
+  for (int c = 0; c < 8; ++c) for (int d = 0; d < 3; ++d) t.corner[c][d] = corner24[3 * c + d];
+  for (int s = 0; s < 6; ++s) for (int k = 0; k < 4; ++k) t.sideNode[s][k] = (uint8_t)sideNode24[4 * s + k];
+  t.concave = (uint8_t)concaveMask;
+  for (int64_t i = 0; i < n; ++i) inside[i] = inside_quad3d_mask<false>(&t, x + 3 * i, mask[i]) ? 1 : 0;
+}
+}
+#else
 int main() {
   constexpr int NP = 4;
   const double xg[4] = {-0.8611363115940526, -0.3399810435848563, 0.3399810435848563, 0.8611363115940526};   // Gauss, N = 3
@@ -81,3 +123,4 @@ int main() {
   std::printf("lagrange %.3e field %.3e push_x %.3e push_v %.3e\n", wL, wF, wPx, wPv);
   return (wL <= 1e-14 && wF <= 1e-13 && wPx <= 1e-14 && wPv <= 1e-14) ? 0 : 1;
 }
+#endif

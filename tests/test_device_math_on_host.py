@@ -1,17 +1,102 @@
 """The device math headers of the CUDA path (piclas_b200/csrc/math.cuh, fastmath.cuh) compiled for the host
-(tests/device_math_host.cpp): restructured vs reference-order Lagrange basis, field evaluation and push on 1e5 random inputs.
-CPU only; it checks the arithmetic the kernels are built from, the -m gpu parity tests check the kernels."""
+(tests/device_math_host.cpp), CPU only:
+
+* restructured (params.arithmetic = 1) vs reference-order Lagrange basis, field evaluation and push on 1e5 random inputs;
+* the reference-order device functions against the oracle BIT FOR BIT — Lagrange basis incl. node hits, GetPositionInRefElem
+  (Newton with start guesses 1, 3, 4) on deformed elements, ParticleInsideQuad3D — i.e. the claim "arithmetic = 0 is bitwise the
+  oracle" (Arithmetic contract) checked on the code the kernels are built from.
+
+The -m gpu parity tests remain the check of the kernels themselves."""
+import ctypes as C
 import os
 import subprocess
 
+import numpy as np
+import pytest
+
+import cases
+from oracle_lib import Oracle
+from piclas_b200 import basis, hostmesh as hm
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "device_math_host.cpp")
+FLAGS = ["-std=c++17", "-O1", "-ffp-contract=off", "-I", os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include"),
+         "-I", os.path.join(ROOT, "piclas_b200", "csrc")]
+F64P, I32P = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+
+
+def _p(a, t=F64P):
+    return a.ctypes.data_as(t)
 
 
 def test_restructured_device_arithmetic_agrees_with_reference_order(tmp_path):
     exe = str(tmp_path / "device_math_host")
-    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-    subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-I", cuda_inc, "-I", os.path.join(ROOT, "piclas_b200", "csrc"),
-                    "-o", exe, os.path.join(ROOT, "tests", "device_math_host.cpp")], check=True)
+    subprocess.run(["g++"] + FLAGS + ["-o", exe, SRC], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("lagrange")
+
+
+@pytest.fixture(scope="module")
+def devmath(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("devmath") / "libdevmath.so")
+    subprocess.run(["g++"] + FLAGS + ["-fPIC", "-shared", "-DDEVMATH_SHARED", "-o", so, SRC], check=True)
+    return C.CDLL(so)
+
+
+def test_device_lagrange_basis_is_the_oracles_bit_for_bit(devmath):
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (1, 1, 1), 3)
+    orc = Oracle(mesh, cases.electron_params())
+    rng = np.random.default_rng(0)
+    for N in (1, 2, 3, 5, 7):
+        xGP, wGP = basis.legendre_gauss_nodes_weights(N)
+        wB = basis.barycentric_weights(xGP)
+        pts = np.concatenate([rng.uniform(-1.2, 1.2, 300), xGP, xGP * (1 + 2e-16), [0.0, 1.0, -1.0]])
+        for x in pts:
+            L = np.zeros(N + 1)
+            devmath.dm_lagrange(C.c_int(N + 1), C.c_double(x), _p(np.ascontiguousarray(xGP)), _p(np.ascontiguousarray(wB)), _p(L))
+            assert np.array_equal(L, orc.lagrange(x, xGP, wB)), (N, x)
+    orc.close()
+
+
+@pytest.mark.parametrize("guess", [1, 3, 4])
+def test_device_newton_and_inside_test_are_the_oracles_bit_for_bit(devmath, guess):
+    lo, hi = [0, 0, 0], [1, 1, 1]
+    mesh = hm.box_mesh(lo, hi, (3, 3, 2), 2, deform=cases.wavy(0.06, lo, hi))
+    prm = cases.electron_params(RefMappingGuess=guess)
+    orc = Oracle(mesh, prm)
+    devmath.dm_set_newton_consts(_p(np.ascontiguousarray(mesh.XiCL_NGeo)), _p(np.ascontiguousarray(mesh.wBaryCL_NGeo)),
+                                 C.c_double(prm.RefMappingEps), C.c_int(guess))
+    rng = np.random.default_rng(guess)
+    nchk = 0
+    for e in range(mesh.nElems):
+        first = mesh.ElemInfo[e, 4]                                    # ELEM_FIRSTNODEIND
+        corners = np.ascontiguousarray(mesh.NodeCoords[first:first + 8])
+        c0, c1 = corners.min(axis=0), corners.max(axis=0)
+        x = np.ascontiguousarray(c0 + (c1 - c0) * rng.uniform(-0.15, 1.15, (400, 3)))       # inside, near and outside the element
+        x[:8] = corners                                                                      # exactly on the corners
+        x[8:14] = corners[mesh.ElemSideNodeID[e, :, :] - first].mean(axis=1)                 # side centres
+        n = len(x)
+        elem = np.full(n, e + 1, dtype=np.int32)
+        # GetPositionInRefElem: ForceMode and isSuccessful as the deposition / interpolation call it
+        xi_d, st_d = np.zeros((n, 3)), np.zeros(n, dtype=np.int32)
+        devmath.dm_position_in_ref_elem(_p(np.ascontiguousarray(mesh.XCL_NGeo[e])), _p(np.ascontiguousarray(mesh.dXCL_NGeo[e])),
+                                        _p(np.ascontiguousarray(mesh.ElemBaryNGeo[e])), _p(np.ascontiguousarray(mesh.XiEtaZetaBasis[e])),
+                                        _p(np.ascontiguousarray(mesh.slenXiEtaZetaBasis[e])), C.c_int64(n), _p(x), C.c_int(1),
+                                        _p(xi_d), _p(st_d, I32P))
+        xi_o, suc_o, _ = orc.position_in_ref_elem(x, elem, force=True)
+        assert np.array_equal(xi_d, xi_o), "reference coordinates differ from the oracle (element %d)" % (e + 1)
+        assert np.array_equal(st_d & 1, suc_o)
+        # ParticleInsideQuad3D
+        side_node = np.ascontiguousarray((mesh.ElemSideNodeID[e] - first).astype(np.int32))
+        conc = int(sum(int(bool(mesh.ConcaveElemSide[e, s])) << s for s in range(6)))
+        ins_d, mask = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.uint32)
+        devmath.dm_inside_quad3d(_p(corners), _p(side_node, I32P), C.c_int(conc), C.c_int64(n), _p(x), _p(ins_d, I32P),
+                                 mask.ctypes.data_as(C.POINTER(C.c_uint32)))
+        ins_o, det = orc.inside(x, elem)
+        assert np.array_equal(ins_d, ins_o), "inside decision differs from the oracle (element %d)" % (e + 1)
+        want = sum(((det[:, s, t] <= 0).astype(np.uint32) << np.uint32(2 * s + t)) for s in range(6) for t in range(2))
+        assert np.array_equal(mask, want), "determinant signs differ from the oracle"
+        nchk += n
+    orc.close()
+    assert nchk >= 7000
