@@ -1,0 +1,113 @@
+// device_track_host.cpp — the element-crossing code of the CUDA path (tria_hop, piclas_b200/csrc/kernels.cuh, with the
+// determinant tests of math.cuh) compiled for the HOST and driven particle by particle, so that the reference-order
+// (params.arithmetic = 0) TriaTracking of the device — neighbour walk, periodic shift, specular reflection — can be run on
+// the reference's own tracking checks where no GPU exists.  Test infrastructure (tests/test_device_math_on_host.py).  The
+// loop around tria_hop below stands in for k_interp_push's inside test of the own element and k_track_leavers' walk; the
+// kernels themselves are what the -m gpu tests check.  tria_hop is instantiated with G = false (records read through plain
+// loads, as from a CTA's shared-memory copy); G = true differs only in fetching them with 256-bit PTX loads.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#undef __device__
+#undef __host__
+#undef __global__
+#undef __constant__
+#undef __shared__
+#undef __forceinline__
+#undef __noinline__
+#undef __align__
+#undef __launch_bounds__
+#define __device__
+#define __host__
+#define __global__
+#define __constant__
+#define __shared__ static
+#define __forceinline__ inline
+#define __noinline__
+#define __align__(n) __attribute__((aligned(n)))
+#define __launch_bounds__(...)
+#define asm(...)   /* inline PTX sits behind template flags that are false here, or in kernels that are never instantiated */
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static const uint3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0};
+static const dim3 blockDim(1, 1, 1), gridDim(1, 1, 1);
+static inline void __syncthreads() {}
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+static inline int __syncthreads_or(int p) { return p; }
+static inline unsigned __activemask() { return 1u; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return v; }
+template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p += v; return o; }
+template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+#include "kernels.cuh"
+
+extern "C" {
+// Tria records from the host tables, as piclas_gpu_init builds them (piclas_gpu.cu, "per-element records"), then for every
+// particle: inside test of the own element at the pushed position, walk while tria_hop asks for another crossing.
+// x: pushed positions (in/out: periodic shifts, reflections), lp: LastPartPos (in/out), v (in/out: reflections), elem (in/out,
+// 1-based; 0 = removed), status out (TRK_*).  Returns the largest number of crossings one particle needed, -1 on bad tables.
+int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* ElemInfo, const int32_t* SideInfo, const double* NodeCoords,
+                  const int32_t* ElemSideNodeID, const int32_t* ConcaveElemSide, int nBCs, const int32_t* bc_kind,
+                  const int32_t* bc_alpha, int nPV, const double* PeriodicVectors, int64_t n, double* x, double* lp, double* v,
+                  int32_t* elem, int32_t* status) {
+  std::vector<TriaElem> tria((size_t)nG);
+  for (int e = 0; e < nG; ++e) {
+    const int32_t* ei = ElemInfo + (size_t)e * elemInfoSize;
+    const int firstSide = ei[2], firstNode = ei[4];                      // ELEM_FIRSTSIDEIND, ELEM_FIRSTNODEIND
+    if (ei[3] - firstSide != 6 || ei[5] - firstNode != 8) return -1;
+    TriaElem& t = tria[e];
+    std::memset(&t, 0, sizeof t);
+    for (int c = 0; c < 8; ++c)
+      for (int d = 0; d < 3; ++d) t.corner[c][d] = NodeCoords[(size_t)(firstNode + c) * 3 + d];
+    for (int s = 0; s < 6; ++s) {
+      const int sid = firstSide + s + 1;
+      const int32_t* si = SideInfo + (size_t)(sid - 1) * sideInfoSize;
+      t.nbElem[s] = si[2];                                                 // SIDE_NBELEMID
+      t.sideID[s] = sid;
+      t.bcid[s] = (uint8_t)si[4];                                          // SIDE_BCID
+      if (ConcaveElemSide[(size_t)e * 6 + s]) t.concave |= (uint8_t)(1u << s);
+      for (int k = 0; k < 4; ++k) t.sideNode[s][k] = (uint8_t)(ElemSideNodeID[((size_t)e * 6 + s) * 4 + k] - firstNode);
+    }
+  }
+  cst.nBCs = nBCs;
+  for (int b = 0; b < nBCs; ++b) { cst.bc_kind[b] = bc_kind[b]; cst.bc_alpha[b] = bc_alpha[b]; }
+  cst.nPeriodicVectors = nPV;
+  for (int p = 0; p < nPV; ++p) for (int d = 0; d < 3; ++d) cst.PeriodicVectors[p][d] = PeriodicVectors[3 * p + d];
+  int maxHops = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    double* xi = x + 3 * i; double* li = lp + 3 * i; double* vi = v + 3 * i;
+    int ElemID = elem[i];
+    uint32_t mask = 0;
+    int st = TRK_OK;
+    if (!inside_quad3d_mask<false>(&tria[ElemID - 1], xi, mask)) {       // particle_triatracking.f90:203-218
+      HopHist h;
+      h.clear();
+      st = -1;
+      int hops = 0;
+      while (st == -1) {
+        st = tria_hop<false, false, 0>(&tria[ElemID - 1], tria.data(), (const PlaneElem*)nullptr,
+                                      [&](int, int) { return (const PlaneElem*)nullptr; },
+                                      [&](const double nrm[3]) {
+                                        const double vn = (vi[0] * nrm[0] + vi[1] * nrm[1]) + vi[2] * nrm[2];
+                                        vi[0] = vi[0] - 2. * vn * nrm[0]; vi[1] = vi[1] - 2. * vn * nrm[1]; vi[2] = vi[2] - 2. * vn * nrm[2];
+                                      },
+                                      xi, li, ElemID, mask, h);
+        if (st == -1 && ++hops > 100000) st = TRK_ERR_LOOP;
+      }
+      if (hops > maxHops) maxHops = hops;
+    }
+    status[i] = st;
+    elem[i] = (st == TRK_OK) ? ElemID : 0;
+  }
+  return maxHops;
+}
+}

@@ -6,6 +6,10 @@
   (Newton with start guesses 1, 3, 4) on deformed elements, ParticleInsideQuad3D — i.e. the claim "arithmetic = 0 is bitwise the
   oracle" (Arithmetic contract) checked on the code the kernels are built from.
 
+* the device's TriaTracking (tria_hop of kernels.cuh: determinant tests, neighbour walk, periodic shift, specular reflection;
+  tests/device_track_host.cpp) on the reference's own tracking checks: bitwise equal to the oracle at every step and in agreement
+  with the state files the reference wrote (NIG_tracking_DSMC/periodic and ANSA_box, tests/test_reference_tracking.py).
+
 The -m gpu parity tests remain the check of the kernels themselves."""
 import ctypes as C
 import os
@@ -100,3 +104,43 @@ def test_device_newton_and_inside_test_are_the_oracles_bit_for_bit(devmath, gues
         nchk += n
     orc.close()
     assert nchk >= 7000
+
+
+@pytest.fixture(scope="module")
+def devtrack(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("devtrack") / "libdevtrack.so")
+    subprocess.run(["g++"] + FLAGS + ["-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tests", "device_track_host.cpp")], check=True)
+    return C.CDLL(so)
+
+
+@pytest.mark.parametrize("name", ["periodic", "ansa"])
+def test_device_tria_tracking_is_the_oracles_and_reproduces_the_references_state_files(devtrack, name):
+    import test_reference_tracking as trt
+    mesh, prm, PD0, elem0, PD1, elem1, dt, nsteps = (trt.periodic_case if name == "periodic" else trt.ansa_case)(hm.TRIATRACKING)
+    n = len(PD0)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    x, v, elem = np.ascontiguousarray(PD0[:, :3]), np.ascontiguousarray(PD0[:, 3:6]), i32(elem0)
+    EI, SI, NC = i32(mesh.ElemInfo), i32(mesh.SideInfo), np.ascontiguousarray(mesh.NodeCoords)
+    ESN, CC, bk, ba = i32(mesh.ElemSideNodeID), i32(mesh.ConcaveElemSide), i32(mesh.bc_kind), i32(mesh.bc_alpha)
+    PV = np.ascontiguousarray(mesh.PeriodicVectors if mesh.nPeriodicVectors else np.zeros((1, 3)))
+    orc = Oracle(mesh, prm)
+    PSo, elo, spec = np.ascontiguousarray(PD0[:, :6]), elem0.copy(), PD0[:, 6].astype(np.int32)
+    inside, isnew, E = np.ones(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros((mesh.nElems, 2, 2, 2, 3))
+    status, most = np.zeros(n, dtype=np.int32), 0
+    for it in range(nsteps):
+        lp = x.copy()
+        x = np.ascontiguousarray(x + v * dt)                                    # the push of a neutral particle (Leapfrog, q = 0)
+        hops = devtrack.dt_tria_track(mesh.nElems, EI.shape[1], SI.shape[1], _p(EI, I32P), _p(SI, I32P), _p(NC), _p(ESN, I32P),
+                                      _p(CC, I32P), mesh.nBCs, _p(bk, I32P), _p(ba, I32P), mesh.nPeriodicVectors, _p(PV), C.c_int64(n),
+                                      _p(x), _p(lp), _p(v), _p(elem, I32P), _p(status, I32P))
+        assert hops >= 0 and not status.any(), (it, np.unique(status))
+        most = max(most, hops)
+        orc.push_track(dt, PSo, spec, elo, inside, isnew, E)
+        assert np.array_equal(x, PSo[:, :3]) and np.array_equal(v, PSo[:, 3:]) and np.array_equal(elem, elo), "step %d" % it
+    orc.close()
+    assert most >= 3                                                             # multi-element flights were walked
+    PS = np.concatenate([x, v], axis=1)
+    if name == "periodic":
+        trt.check_periodic(PS, elem, PD1, elem1, mesh.nElems)
+    else:
+        trt.check_ansa(PS, elem, PD0, PD1, elem1, mesh.nElems)
