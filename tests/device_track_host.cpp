@@ -48,7 +48,10 @@ template <class T> static inline T atomicAdd(T* p, T v) { T o = *p; *p += v; ret
 template <class T> static inline T atomicMax(T* p, T v) { T o = *p; if (v > o) *p = v; return o; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+static inline int max(int a, int b) { return a > b ? a : b; }   // CUDA's integer overloads
+static inline int min(int a, int b) { return a < b ? a : b; }
 #include "kernels.cuh"
+#include "ref.cuh"
 
 extern "C" {
 // Tria records from the host tables, as piclas_gpu_init builds them (piclas_gpu.cu, "per-element records"), then for every
@@ -109,5 +112,59 @@ int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* Ele
     elem[i] = (st == TRK_OK) ? ElemID : 0;
   }
   return maxHops;
+}
+// ParticleRefTracking of the device (ref_tracking of csrc/ref.cuh: Newton in the old element, BC-side intersections, periodic shift
+// and reflection, FIBGM relocation incl. the repeated-selection path, LocateParticleInElement fallback) for n particles on the host.
+// The tables are the host's (pgpu_mesh_t as handed to piclas_gpu_init); the GeoElem records and the constant table are filled as
+// piclas_gpu_init fills them.  x pushed positions, lp LastPartPos, v, xi PartPosRef, elem: all in/out.
+int dt_ref_track(const pgpu_mesh_t* m, const pgpu_params_t* p, int64_t n, double* x, double* lp, double* v, double* xi, int32_t* elem,
+                 int32_t* status, int32_t* relocated) {
+  const int nG = m->nGlobalElems;
+  std::vector<GeoElem> geo((size_t)nG);
+  for (int e = 0; e < nG; ++e) {
+    GeoElem& ge = geo[e];
+    std::memset(&ge, 0, sizeof ge);
+    std::memcpy(ge.XCL, m->XCL_NGeo + (size_t)e * 24, 24 * 8);
+    std::memcpy(ge.dXCL, m->dXCL_NGeo + (size_t)e * 72, 72 * 8);
+    std::memcpy(ge.bary, m->ElemBaryNGeo + (size_t)e * 3, 3 * 8);
+    std::memcpy(ge.xez, m->XiEtaZetaBasis + (size_t)e * 18, 18 * 8);
+    std::memcpy(ge.slen, m->slenXiEtaZetaBasis + (size_t)e * 6, 6 * 8);
+  }
+  for (int i = 0; i < 2; ++i) { cst.XiCL[i] = m->XiCL_NGeo[i]; cst.wBaryCL[i] = m->wBaryCL_NGeo[i]; }
+  cst.RefMappingEps = p->RefMappingEps;
+  cst.RefMappingGuess = p->RefMappingGuess;
+  cst.nBCs = m->nBCs;
+  for (int b = 0; b < m->nBCs; ++b) { cst.bc_kind[b] = m->bc_kind[b]; cst.bc_alpha[b] = m->bc_alpha[b]; }
+  cst.nPeriodicVectors = m->nPeriodicVectors;
+  for (int k = 0; k < m->nPeriodicVectors; ++k) for (int d = 0; d < 3; ++d) cst.PeriodicVectors[k][d] = m->PeriodicVectors[k * 3 + d];
+  for (int d = 0; d < 3; ++d) {
+    cst.FIBGMdeltas[d] = m->FIBGMdeltas[d]; cst.xyzminglob[d] = m->xyzminglob[d];
+    cst.FIBGMmin[d] = m->FIBGMmin[d]; cst.FIBGMmax[d] = m->FIBGMmax[d];
+  }
+  RefTables T;
+  T.geo = geo.data(); T.ElemToBCSides = m->ElemToBCSides; T.SideBCMetrics = m->SideBCMetrics; T.SideInfo = m->SideInfo;
+  T.sideInfoSize = m->sideInfoSize; T.SideNormVec = m->SideNormVec; T.SideDistance = m->SideDistance;
+  T.BaseVectors0 = m->BaseVectors0; T.BaseVectors1 = m->BaseVectors1; T.BaseVectors2 = m->BaseVectors2; T.BaseVectors3 = m->BaseVectors3;
+  T.SideType = m->SideType; T.ElemBary = m->ElemBaryNGeo; T.ElemRadius = m->ElemRadiusNGeo; T.ElemRadius2 = m->ElemRadius2NGeo;
+  T.ElemEpsOneCell = m->ElemEpsOneCell; T.FIBGM_nElems = m->FIBGM_nElems; T.FIBGM_offsetElem = m->FIBGM_offsetElem;
+  T.FIBGM_Element = m->FIBGM_Element;
+  // velocities as the structure of arrays bc_tracking reflects in place
+  std::vector<double> v0((size_t)n), v1((size_t)n), v2((size_t)n);
+  for (int64_t i = 0; i < n; ++i) { v0[i] = v[3 * i]; v1[i] = v[3 * i + 1]; v2[i] = v[3 * i + 2]; }
+  PartBuf pb;
+  std::memset(&pb, 0, sizeof pb);
+  pb.v[0] = v0.data(); pb.v[1] = v1.data(); pb.v[2] = v2.data();
+  int worst = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int e = elem[i];
+    bool rel = false;
+    const int st = ref_tracking(T, pb, i, x + 3 * i, lp + 3 * i, xi + 3 * i, e, rel);
+    status[i] = st;
+    relocated[i] = rel ? 1 : 0;
+    elem[i] = (st == TRK_OK) ? e : 0;
+    if (st > worst) worst = st;
+  }
+  for (int64_t i = 0; i < n; ++i) { v[3 * i] = v0[i]; v[3 * i + 1] = v1[i]; v[3 * i + 2] = v2[i]; }
+  return worst;
 }
 }

@@ -8,7 +8,11 @@
 
 * the device's TriaTracking (tria_hop of kernels.cuh: determinant tests, neighbour walk, periodic shift, specular reflection;
   tests/device_track_host.cpp) on the reference's own tracking checks: bitwise equal to the oracle at every step and in agreement
-  with the state files the reference wrote (NIG_tracking_DSMC/periodic and ANSA_box, tests/test_reference_tracking.py).
+  with the state files the reference wrote (NIG_tracking_DSMC/periodic and ANSA_box, tests/test_reference_tracking.py);
+* the device's RefMapping tracking (ref_tracking of ref.cuh: Newton in the old element, BC-side intersections on planar and
+  bilinear sides, periodic shift, reflection, FIBGM relocation - with the stored candidate list and, for the reference's own
+  background mesh with 125 elements in one cell, by repeated selection (select.cuh) - and the localisation fallback) on the same
+  checks: positions, velocities, PartPosRef and elements bitwise equal to the oracle at every step.
 
 The -m gpu parity tests remain the check of the kernels themselves."""
 import ctypes as C
@@ -144,3 +148,41 @@ def test_device_tria_tracking_is_the_oracles_and_reproduces_the_references_state
         trt.check_periodic(PS, elem, PD1, elem1, mesh.nElems)
     else:
         trt.check_ansa(PS, elem, PD0, PD1, elem1, mesh.nElems)
+
+
+@pytest.mark.parametrize("name", ["periodic", "periodic-one-fibgm-cell", "ansa"])
+def test_device_ref_tracking_is_the_oracles_and_reproduces_the_references_state_files(devtrack, name):
+    import test_reference_tracking as trt
+    from piclas_b200.abi import Marshalled
+    if name == "ansa":
+        case = trt.ansa_case(hm.REFMAPPING)
+    else:
+        case = trt.periodic_case(hm.REFMAPPING, **({"fibgm_deltas": (2.0, 1.0, 1.0)} if name.endswith("cell") else {}))
+    mesh, prm, PD0, elem0, PD1, elem1, dt, nsteps = case
+    if name.endswith("cell"):
+        assert mesh.extra["FIBGM"]["nElems"].max() == 125                        # > REF_MAX_BGM: the repeated-selection path
+    mar = Marshalled(mesh, prm)                                                   # the structs piclas_gpu_init receives
+    n = len(PD0)
+    x, v, elem = np.ascontiguousarray(PD0[:, :3]), np.ascontiguousarray(PD0[:, 3:6]), np.ascontiguousarray(elem0, dtype=np.int32)
+    orc = Oracle(mesh, prm)
+    PSo, elo, spec = np.ascontiguousarray(PD0[:, :6]), elem0.copy(), PD0[:, 6].astype(np.int32)
+    xio, _, bad = orc.position_in_ref_elem(PSo[:, :3], elo)
+    assert bad == 0
+    xi = xio.copy()
+    inside, isnew, E = np.ones(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros((mesh.nElems, 2, 2, 2, 3))
+    status, relocated = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    for it in range(nsteps):
+        lp = x.copy()
+        x = np.ascontiguousarray(x + v * dt)
+        worst = devtrack.dt_ref_track(C.byref(mar.mesh), C.byref(mar.params), C.c_int64(n), _p(x), _p(lp), _p(v), _p(xi), _p(elem, I32P),
+                                      _p(status, I32P), _p(relocated, I32P))
+        assert worst == 0, (it, np.unique(status))
+        orc.push_track(dt, PSo, spec, elo, inside, isnew, E, PartPosRef=xio)
+        assert np.array_equal(x, PSo[:, :3]) and np.array_equal(v, PSo[:, 3:]) and np.array_equal(elem, elo), "step %d" % it
+        assert np.array_equal(xi, xio), "PartPosRef differs from the oracle (step %d)" % it
+    orc.close()
+    PS = np.concatenate([x, v], axis=1)
+    if name == "ansa":
+        trt.check_ansa(PS, elem, PD0, PD1, elem1, mesh.nElems)
+    else:
+        trt.check_periodic(PS, elem, PD1, elem1, mesh.nElems)
