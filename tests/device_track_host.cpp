@@ -58,10 +58,13 @@ extern "C" {
 // particle: inside test of the own element at the pushed position, walk while tria_hop asks for another crossing.
 // x: pushed positions (in/out: periodic shifts, reflections), lp: LastPartPos (in/out), v (in/out: reflections), elem (in/out,
 // 1-based; 0 = removed), status out (TRK_*).  Returns the largest number of crossings one particle needed, -1 on bad tables.
+// fast != 0: the restructured arithmetic (params.arithmetic = 1) - inside test through the triangle planes with the exact
+// fallback, exit-side shortcut on planar convex elements - on PlaneElem records built as piclas_gpu_init builds them (that
+// builder is host code inside piclas_gpu_init and is restated here; the device functions under test are the originals).
 int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* ElemInfo, const int32_t* SideInfo, const double* NodeCoords,
                   const int32_t* ElemSideNodeID, const int32_t* ConcaveElemSide, int nBCs, const int32_t* bc_kind,
                   const int32_t* bc_alpha, int nPV, const double* PeriodicVectors, int64_t n, double* x, double* lp, double* v,
-                  int32_t* elem, int32_t* status) {
+                  int32_t* elem, int32_t* status, int fast) {
   std::vector<TriaElem> tria((size_t)nG);
   for (int e = 0; e < nG; ++e) {
     const int32_t* ei = ElemInfo + (size_t)e * elemInfoSize;
@@ -85,25 +88,75 @@ int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* Ele
   for (int b = 0; b < nBCs; ++b) { cst.bc_kind[b] = bc_kind[b]; cst.bc_alpha[b] = bc_alpha[b]; }
   cst.nPeriodicVectors = nPV;
   for (int p = 0; p < nPV; ++p) for (int d = 0; d < 3; ++d) cst.PeriodicVectors[p][d] = PeriodicVectors[3 * p + d];
+  std::vector<PlaneElem> planes(fast ? (size_t)nG : 0);
+  for (int e = 0; fast && e < nG; ++e) {
+    const TriaElem& t = tria[e];
+    PlaneElem& pl = planes[e];
+    std::memset(&pl, 0, sizeof pl);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int c = 0; c < 8; ++c)
+      for (int d = 0; d < 3; ++d) { lo[d] = std::fmin(lo[d], t.corner[c][d]); hi[d] = std::fmax(hi[d], t.corner[c][d]); }
+    const double diam = std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) + (hi[2] - lo[2]) * (hi[2] - lo[2]));
+    pl.tol = 1e-8 * diam;
+    for (int s = 0; s < 6; ++s)
+      for (int tr = 0; tr < 2; ++tr) {
+        const double* P1 = t.corner[t.sideNode[s][0]];
+        const double* Pb = t.corner[t.sideNode[s][tr + 1]];
+        const double* Pc = t.corner[t.sideNode[s][tr + 2]];
+        const double u[3] = {Pb[0] - P1[0], Pb[1] - P1[1], Pb[2] - P1[2]}, w[3] = {Pc[0] - P1[0], Pc[1] - P1[1], Pc[2] - P1[2]};
+        const double N[3] = {u[1] * w[2] - u[2] * w[1], u[2] * w[0] - u[0] * w[2], u[0] * w[1] - u[1] * w[0]};
+        const double len = std::sqrt(N[0] * N[0] + N[1] * N[1] + N[2] * N[2]);
+        if (!(len > 0.)) return -1;
+        const int k = 2 * s + tr;
+        for (int d = 0; d < 3; ++d) pl.pl[k][d] = -N[d] / len;
+        pl.pl[k][3] = pl.pl[k][0] * P1[0] + pl.pl[k][1] * P1[1] + pl.pl[k][2] * P1[2];
+      }
+    for (int s = 0; s < 6; ++s) pl.concave2 |= (uint32_t)((t.concave >> s) & 1u) << (2 * s);
+    bool planar = true;
+    for (int k = 0; k < 12; ++k)
+      for (int c = 0; c < 8; ++c)
+        if (pl.pl[k][0] * t.corner[c][0] + pl.pl[k][1] * t.corner[c][1] + pl.pl[k][2] * t.corner[c][2] - pl.pl[k][3] < -1e-12 * diam) planar = false;
+    for (int s = 0; s < 6; ++s) {
+      const double *a = pl.pl[2 * s], *b = pl.pl[2 * s + 1];
+      if (std::fabs(a[0] - b[0]) > 1e-12 || std::fabs(a[1] - b[1]) > 1e-12 || std::fabs(a[2] - b[2]) > 1e-12 || std::fabs(a[3] - b[3]) > 1e-12 * diam)
+        planar = false;
+      const double* P1 = t.corner[t.sideNode[s][0]];
+      const double* P2 = t.corner[t.sideNode[s][1]];
+      const double* P3 = t.corner[t.sideNode[s][2]];
+      const double dgn[3] = {P3[0] - P1[0], P3[1] - P1[1], P3[2] - P1[2]};
+      const double mm[3] = {a[1] * dgn[2] - a[2] * dgn[1], a[2] * dgn[0] - a[0] * dgn[2], a[0] * dgn[1] - a[1] * dgn[0]};
+      const double ml = std::sqrt(mm[0] * mm[0] + mm[1] * mm[1] + mm[2] * mm[2]);
+      if (!(ml > 0.)) { planar = false; continue; }
+      const double sgn = (mm[0] * (P2[0] - P1[0]) + mm[1] * (P2[1] - P1[1]) + mm[2] * (P2[2] - P1[2])) >= 0. ? 1. : -1.;
+      for (int d = 0; d < 3; ++d) pl.dg[s][d] = sgn * mm[d] / ml;
+      pl.dg[s][3] = pl.dg[s][0] * P1[0] + pl.dg[s][1] * P1[1] + pl.dg[s][2] * P1[2];
+    }
+    pl.planar = planar ? 1u : 0u;
+  }
   int maxHops = 0;
   for (int64_t i = 0; i < n; ++i) {
     double* xi = x + 3 * i; double* li = lp + 3 * i; double* vi = v + 3 * i;
     int ElemID = elem[i];
     uint32_t mask = 0;
     int st = TRK_OK;
-    if (!inside_quad3d_mask<false>(&tria[ElemID - 1], xi, mask)) {       // particle_triatracking.f90:203-218
+    auto reflect = [&](const double nrm[3]) {
+      const double vn = (vi[0] * nrm[0] + vi[1] * nrm[1]) + vi[2] * nrm[2];
+      vi[0] = vi[0] - 2. * vn * nrm[0]; vi[1] = vi[1] - 2. * vn * nrm[1]; vi[2] = vi[2] - 2. * vn * nrm[2];
+    };
+    const bool insideOwn = fast ? inside_fast<false>(&planes[ElemID - 1], &tria[ElemID - 1], xi, mask)
+                                : inside_quad3d_mask<false>(&tria[ElemID - 1], xi, mask);       // particle_triatracking.f90:203-218
+    if (!insideOwn) {
       HopHist h;
       h.clear();
       st = -1;
       int hops = 0;
       while (st == -1) {
-        st = tria_hop<false, false, 0>(&tria[ElemID - 1], tria.data(), (const PlaneElem*)nullptr,
-                                      [&](int, int) { return (const PlaneElem*)nullptr; },
-                                      [&](const double nrm[3]) {
-                                        const double vn = (vi[0] * nrm[0] + vi[1] * nrm[1]) + vi[2] * nrm[2];
-                                        vi[0] = vi[0] - 2. * vn * nrm[0]; vi[1] = vi[1] - 2. * vn * nrm[1]; vi[2] = vi[2] - 2. * vn * nrm[2];
-                                      },
-                                      xi, li, ElemID, mask, h);
+        if (fast)
+          st = tria_hop<true, false, 2>(&tria[ElemID - 1], tria.data(), &planes[ElemID - 1],
+                                        [&](int, int ne) { return (const PlaneElem*)&planes[ne - 1]; }, reflect, xi, li, ElemID, mask, h);
+        else
+          st = tria_hop<false, false, 0>(&tria[ElemID - 1], tria.data(), (const PlaneElem*)nullptr,
+                                         [&](int, int) { return (const PlaneElem*)nullptr; }, reflect, xi, li, ElemID, mask, h);
         if (st == -1 && ++hops > 100000) st = TRK_ERR_LOOP;
       }
       if (hops > maxHops) maxHops = hops;

@@ -117,8 +117,11 @@ def devtrack(tmp_path_factory):
     return C.CDLL(so)
 
 
+@pytest.mark.parametrize("fast", [0, 1], ids=["reference-order", "restructured"])
 @pytest.mark.parametrize("name", ["periodic", "ansa"])
-def test_device_tria_tracking_is_the_oracles_and_reproduces_the_references_state_files(devtrack, name):
+def test_device_tria_tracking_is_the_oracles_and_reproduces_the_references_state_files(devtrack, name, fast):
+    """fast = 1: the restructured arithmetic of params.arithmetic = 1 (inside test through the triangle planes with the exact
+    fallback, exit-side shortcut on planar convex elements); it takes the same decisions, so the results stay bitwise equal."""
     import test_reference_tracking as trt
     mesh, prm, PD0, elem0, PD1, elem1, dt, nsteps = (trt.periodic_case if name == "periodic" else trt.ansa_case)(hm.TRIATRACKING)
     n = len(PD0)
@@ -136,7 +139,7 @@ def test_device_tria_tracking_is_the_oracles_and_reproduces_the_references_state
         x = np.ascontiguousarray(x + v * dt)                                    # the push of a neutral particle (Leapfrog, q = 0)
         hops = devtrack.dt_tria_track(mesh.nElems, EI.shape[1], SI.shape[1], _p(EI, I32P), _p(SI, I32P), _p(NC), _p(ESN, I32P),
                                       _p(CC, I32P), mesh.nBCs, _p(bk, I32P), _p(ba, I32P), mesh.nPeriodicVectors, _p(PV), C.c_int64(n),
-                                      _p(x), _p(lp), _p(v), _p(elem, I32P), _p(status, I32P))
+                                      _p(x), _p(lp), _p(v), _p(elem, I32P), _p(status, I32P), C.c_int(fast))
         assert hops >= 0 and not status.any(), (it, np.unique(status))
         most = max(most, hops)
         orc.push_track(dt, PSo, spec, elo, inside, isnew, E)
