@@ -189,3 +189,50 @@ def test_device_ref_tracking_is_the_oracles_and_reproduces_the_references_state_
         trt.check_ansa(PS, elem, PD0, PD1, elem1, mesh.nElems)
     else:
         trt.check_periodic(PS, elem, PD1, elem1, mesh.nElems)
+
+
+@pytest.mark.parametrize("fast", [0, 1], ids=["reference-order", "restructured"])
+@pytest.mark.parametrize("tag", ["wavy-periodic", "wavy-reflective", "cartesian-open-x"])
+def test_device_tria_tracking_on_synthetic_meshes(devtrack, tag, fast):
+    """Deformed elements (non-planar sides, concave flags), specular walls and open boundaries with flights of up to several
+    elements: the device's crossing code on the host keeps particles, elements, positions and velocities bitwise equal to the oracle."""
+    from piclas_b200.abi import TIMEDISC_LEAPFROG
+    lo, hi = [0, 0, 0], [1, 1, 1]
+    mesh = {"wavy-periodic": lambda: hm.box_mesh(lo, hi, (6, 5, 4), 1, deform=cases.wavy_periodic(0.04, lo, hi)),
+            "wavy-reflective": lambda: hm.box_mesh(lo, hi, (5, 4, 4), 1, periodic=(False, False, False), wall_kind=hm.BC_REFLECTIVE,
+                                                   deform=cases.wavy(0.05, lo, hi)),
+            "cartesian-open-x": lambda: hm.box_mesh(lo, hi, (6, 6, 6), 1, periodic=(False, True, True), wall_kind=hm.BC_OPEN)}[tag]()
+    prm = cases.electron_params(TimeDiscMethod=TIMEDISC_LEAPFROG, ChargeIC=(0.0,), DoInterpolation=0, DoDeposition=0)
+    dt = 1e-8
+    PS0, spec = cases.uniform_plasma(mesh, 20000, seed=5, vth_cells=0.7, dt=dt)
+    orc = Oracle(mesh, prm)
+    elem0 = orc.locate(PS0[:, :3]).astype(np.int32)
+    keep = elem0 > 0
+    PS0, spec, elem0 = np.ascontiguousarray(PS0[keep]), spec[keep], elem0[keep]
+    n = len(spec)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    EI, SI, NC = i32(mesh.ElemInfo), i32(mesh.SideInfo), np.ascontiguousarray(mesh.NodeCoords)
+    ESN, CC, bk, ba = i32(mesh.ElemSideNodeID), i32(mesh.ConcaveElemSide), i32(mesh.bc_kind), i32(mesh.bc_alpha)
+    PV = np.ascontiguousarray(mesh.PeriodicVectors if mesh.nPeriodicVectors else np.zeros((1, 3)))
+    x, v, elem = np.ascontiguousarray(PS0[:, :3]), np.ascontiguousarray(PS0[:, 3:]), elem0.copy()
+    PSo, elo = PS0.copy(), elem0.copy()
+    inside, isnew, E = np.ones(n, dtype=np.int32), np.zeros(n, dtype=np.int32), np.zeros((mesh.nElems, 2, 2, 2, 3))
+    alive = np.ones(n, dtype=bool)
+    for it in range(6):
+        lp = x.copy()
+        x = np.ascontiguousarray(x + v * dt)
+        idx = np.nonzero(alive)[0]
+        xa, la, va = np.ascontiguousarray(x[idx]), np.ascontiguousarray(lp[idx]), np.ascontiguousarray(v[idx])
+        ea, sa = np.ascontiguousarray(elem[idx]), np.zeros(len(idx), dtype=np.int32)
+        hops = devtrack.dt_tria_track(mesh.nElems, EI.shape[1], SI.shape[1], _p(EI, I32P), _p(SI, I32P), _p(NC), _p(ESN, I32P),
+                                      _p(CC, I32P), mesh.nBCs, _p(bk, I32P), _p(ba, I32P), mesh.nPeriodicVectors, _p(PV),
+                                      C.c_int64(len(idx)), _p(xa), _p(la), _p(va), _p(ea, I32P), _p(sa, I32P), C.c_int(fast))
+        assert hops >= 0 and set(np.unique(sa)) <= {0, 2}, np.unique(sa)           # TRK_OK or TRK_REMOVED (open boundary)
+        x[idx], v[idx], elem[idx] = xa, va, ea
+        alive[idx] = sa == 0
+        orc.push_track(dt, PSo, spec, elo, inside, isnew, E)
+        live = inside.astype(bool)
+        assert np.array_equal(alive, live), "step %d: the set of removed particles differs" % it
+        assert np.array_equal(elem[alive], elo[live]) and np.array_equal(x[alive], PSo[live, :3]) and np.array_equal(v[alive], PSo[live, 3:])
+    orc.close()
+    assert tag != "cartesian-open-x" or alive.sum() < n
