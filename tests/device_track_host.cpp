@@ -220,4 +220,43 @@ int dt_ref_track(const pgpu_mesh_t* m, const pgpu_params_t* p, int64_t n, double
   for (int64_t i = 0; i < n; ++i) { v[3 * i] = v0[i]; v[3 * i + 1] = v1[i]; v[3 * i + 2] = v2[i]; }
   return worst;
 }
+// DepositionMethod_CVWM per particle on the host (deposit_particle_general of csrc/kernels.cuh: GetPositionInRefElem with ForceMode,
+// the eight trilinear weights in CGNS corner order or the inverse-distance fallback): accumulates every particle of element e into
+// acc[e][corner][1:4] in particle order and returns the reference positions.  Corners in CGNS order as the kernel hands them over.
+int dt_cvwm_accumulate(const pgpu_mesh_t* m, const pgpu_params_t* p, int64_t n, const double* PartState, const int32_t* spec,
+                       const int32_t* elem, double* acc /*[nElems][8][4]*/, double* xiOut /*[n][3]*/, int32_t* failed) {
+  for (int i = 0; i < 2; ++i) { cst.XiCL[i] = m->XiCL_NGeo[i]; cst.wBaryCL[i] = m->wBaryCL_NGeo[i]; }
+  cst.RefMappingEps = p->RefMappingEps;
+  cst.RefMappingGuess = p->RefMappingGuess;
+  for (int s = 0; s < p->nSpecies; ++s) { cst.ChargeIC[s] = p->ChargeIC[s]; cst.MPF[s] = p->MacroParticleFactor[s]; }
+  std::vector<double> f((size_t)6 * n), xif((size_t)3 * n);
+  std::vector<uint8_t> meta((size_t)n);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int a = 0; a < 6; ++a) f[(size_t)a * n + i] = PartState[6 * i + a];
+    meta[i] = (uint8_t)((spec[i] - 1) & META_SPEC_MASK);
+  }
+  PartBuf pb;
+  std::memset(&pb, 0, sizeof pb);
+  pb.f = f.data(); pb.xif = xif.data(); pb.stride = n; pb.meta = meta.data();
+  static DepAcc sAcc;
+  for (int64_t i = 0; i < n; ++i) {
+    const int e = elem[i] - 1;
+    GeoElem g;
+    std::memset(&g, 0, sizeof g);
+    std::memcpy(g.XCL, m->XCL_NGeo + (size_t)e * 24, 24 * 8);
+    std::memcpy(g.dXCL, m->dXCL_NGeo + (size_t)e * 72, 72 * 8);
+    std::memcpy(g.bary, m->ElemBaryNGeo + (size_t)e * 3, 3 * 8);
+    std::memcpy(g.xez, m->XiEtaZetaBasis + (size_t)e * 18, 18 * 8);
+    std::memcpy(g.slen, m->slenXiEtaZetaBasis + (size_t)e * 6, 6 * 8);
+    const int firstNode = m->ElemInfo[(size_t)e * m->elemInfoSize + 4];
+    double corner[8][3];
+    for (int c = 0; c < 8; ++c) for (int d = 0; d < 3; ++d) corner[c][d] = m->NodeCoords[(size_t)(firstNode + c) * 3 + d];
+    for (int a = 0; a < 32; ++a) sAcc[a][0] = acc[(size_t)e * 32 + a];
+    deposit_particle_general(pb, i, &g, corner, sAcc, 0);
+    for (int a = 0; a < 32; ++a) acc[(size_t)e * 32 + a] = sAcc[a][0];
+    for (int d = 0; d < 3; ++d) xiOut[3 * i + d] = xif[(size_t)d * n + i];
+    failed[i] = (meta[i] & META_XIFAIL) ? 1 : 0;
+  }
+  return 0;
+}
 }

@@ -236,3 +236,47 @@ def test_device_tria_tracking_on_synthetic_meshes(devtrack, tag, fast):
         assert np.array_equal(elem[alive], elo[live]) and np.array_equal(x[alive], PSo[live, :3]) and np.array_equal(v[alive], PSo[live, 3:])
     orc.close()
     assert tag != "cartesian-open-x" or alive.sum() < n
+
+
+@pytest.mark.parametrize("tag", ["wavy", "twisted-two-elements"])
+def test_device_cvwm_particle_deposit_matches_the_oracle(devtrack, tag):
+    """deposit_particle_general of kernels.cuh on the host: reference positions bitwise the oracle's, the same particles take the
+    inverse-distance fallback, and the node sums built from the per-element accumulators agree with DepositionMethod_CVWM's raw
+    NodeSource to round-off (the device sums per element first, the reference per node: different association)."""
+    from piclas_b200.abi import Marshalled
+    if tag == "wavy":
+        lo, hi = [0, 0, 0], [1, 1, 1]
+        mesh = hm.box_mesh(lo, hi, (4, 3, 3), 2, deform=cases.wavy_periodic(0.05, lo, hi))
+        prm = cases.electron_params(MacroParticleFactor=(1e9,))
+        PS, spec = cases.uniform_plasma(mesh, 6000, seed=12, vth_cells=0.3, dt=1e-8)
+        orc = Oracle(mesh, prm)
+        elem = orc.locate(PS[:, :3]).astype(np.int32)
+        keep = elem > 0
+        PS, spec, elem = np.ascontiguousarray(PS[keep]), spec[keep], elem[keep]
+    else:
+        mesh, prm, PS, spec = cases.plasma_ball_two_elements(True)
+        orc = Oracle(mesh, prm)
+        elem = np.ascontiguousarray(orc.locate(PS[:, :3]), dtype=np.int32)
+        assert (elem > 0).all()
+    n = len(spec)
+    mar = Marshalled(mesh, prm)
+    acc, xi, failed = np.zeros((mesh.nElems, 8, 4)), np.zeros((n, 3)), np.zeros(n, dtype=np.int32)
+    assert devtrack.dt_cvwm_accumulate(C.byref(mar.mesh), C.byref(mar.params), C.c_int64(n), _p(np.ascontiguousarray(PS)),
+                                       _p(np.ascontiguousarray(spec, dtype=np.int32), I32P), _p(elem, I32P), _p(acc), _p(xi),
+                                       _p(failed, I32P)) == 0
+    xi_o, suc_o, _ = orc.position_in_ref_elem(PS[:, :3], elem, force=True)
+    assert np.array_equal(xi, xi_o) and np.array_equal(failed, 1 - suc_o)
+    if tag != "wavy":
+        assert failed.sum() > 100                                       # the twisted interface: SucRefPos = F for many particles
+    NS = np.zeros((mesh.nUniqueNodes, 4))
+    node = mesh.NodeInfo[mesh.ElemNodeID - 1] - 1                       # [nElems][8] unique node of CGNS corner n
+    np.add.at(NS, node.reshape(-1), acc.reshape(-1, 4))
+    if mesh.nPeriodicVectors == 0:
+        ref = orc.deposit_raw(PS, spec, elem, np.ones(n, dtype=np.int32))
+        for c in range(4):
+            scale = np.abs(ref[:, c]).max()
+            if scale > 0:
+                assert np.abs(NS[:, c] - ref[:, c]).max() <= 1e-13 * scale, c
+    q = prm.ChargeIC[0] * prm.MacroParticleFactor[0]
+    assert abs(NS[:, 3].sum() - n * q) <= 1e-12 * abs(n * q)          # the weights of every particle sum to one
+    orc.close()
