@@ -223,16 +223,22 @@ int reserve_stage(int64_t n) {
 
 __global__ void k_aos_to_soa(PartBuf pb, int64_t dst0, int64_t n, const double* __restrict__ ps, const int32_t* __restrict__ spec,
                              const int32_t* __restrict__ elem, const int32_t* __restrict__ inside, const int32_t* __restrict__ isnew,
-                             const int64_t* __restrict__ ids, int64_t idBase, const double* __restrict__ ref) {
+                             const int64_t* __restrict__ ids, int64_t idBase, const double* __restrict__ ref, int nGlobalElems,
+                             int nSpecies, int* __restrict__ badInput) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int64_t p = dst0 + i;
+  {  // host input indexes device tables: 1 <= GlobalElemID <= nGlobalElems (live particles), 1 <= PartSpecies <= nSpecies
+    const bool live = inside ? (inside[i] != 0) : true;
+    if (live && (elem[i] < 1 || elem[i] > nGlobalElems)) atomicOr(badInput, 1);
+    if (live && (spec[i] < 1 || spec[i] > nSpecies)) atomicOr(badInput, 2);
+  }
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
     pb.x[d][p] = ps[i * 6 + d];
     pb.v[d][p] = ps[i * 6 + 3 + d];
   }
-  const bool in = inside ? (inside[i] != 0) : true;
+  const bool in = (inside ? (inside[i] != 0) : true) && elem[i] >= 1 && elem[i] <= nGlobalElems;
   pb.elem[p] = in ? elem[i] : 0;
   pb.meta[p] = (uint8_t)(((spec[i] - 1) & META_SPEC_MASK) | ((isnew && isnew[i]) ? META_ISNEW : 0));
   if (pb.id) pb.id[p] = ids ? ids[i] : (idBase + i);
@@ -256,6 +262,23 @@ __global__ void k_soa_to_aos(PartBuf pb, int64_t src0, int64_t n, double* __rest
   spec[i] = (pb.meta[p] & META_SPEC_MASK) + 1;
   elem[i] = pb.elem[p];
   if (ids) ids[i] = pb.id ? pb.id[p] : -1;
+}
+
+// PartPosRef(1:3) for a download under TriaTracking: GetPositionInRefElem (ForceMode, as DepositionMethod_CVWM calls it) at the
+// particle's current position in its element; closed form on affine elements with the restructured arithmetic
+__global__ void k_posref_download(PartBuf pb, int64_t src0, int64_t n, const GeoElem* __restrict__ geo, const AffElem* __restrict__ aff,
+                                  double* __restrict__ xiOut) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t p = src0 + i;
+  const int e = pb.elem[p];
+  double xi[3] = {0., 0., 0.};
+  if (e >= 1) {
+    const double x[3] = {pb.x[0][p], pb.x[1][p], pb.x[2][p]};
+    if (aff) ref_position_fast(aff + (e - 1), geo + (e - 1), x, xi, true);
+    else position_in_ref_elem(geo + (e - 1), x, xi, true, true);
+  }
+  xiOut[i * 3 + 0] = xi[0]; xiOut[i * 3 + 1] = xi[1]; xiOut[i * 3 + 2] = xi[2];
 }
 
 // MPIParticleRecv unpack (particle_mpi.f90:831-989): received particles are appended; IsNewPart = F
@@ -548,6 +571,8 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   if (m->nPeriodicVectors > 8) return fail("piclas_gpu_init: more than 8 periodic vectors");
   if (m->elemInfoSize < 7 || m->sideInfoSize < 8) return fail("piclas_gpu_init: ElemInfo/SideInfo leading dimension too small");
   if (p->nRanks < 1 || p->myRank < 0 || p->myRank >= p->nRanks) return fail("piclas_gpu_init: bad rank layout");
+  if (m->nGlobalElems < 1 || m->offsetElem < 0 || m->nElems < 0 || m->offsetElem + m->nElems > m->nGlobalElems)
+    return fail("piclas_gpu_init: offsetElem=%d / nElems=%d outside the %d global elements", m->offsetElem, m->nElems, m->nGlobalElems);
   for (int b = 0; b < m->nBCs; ++b) {
     if (m->bc_kind[b] != PGPU_BC_OPEN && m->bc_kind[b] != PGPU_BC_PERIODIC && m->bc_kind[b] != PGPU_BC_REFLECTIVE)
       return fail("piclas_gpu_init: boundary %d has TargetBoundCond=%d; only open (1), reflective (2, specular) and periodic (3) are supported", b + 1, m->bc_kind[b]);
@@ -589,6 +614,11 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     if (lastNode - firstNode != 8) return fail("piclas_gpu_init: element %d has %d nodes (NGeo=1 hexahedra only)", e + 1, lastNode - firstNode);
     rank[e] = ei[ELEM_RANK];
     if (rank[e] < 0 || rank[e] >= g.nRanks) return fail("piclas_gpu_init: ELEM_RANK of element %d outside 0..nRanks-1", e + 1);
+    // the sort keys and the halo lists rely on the reference's partition: contiguous element ranges in rank order
+    // (loadbalance/loaddistribution.f90:362-369), this rank owning exactly offsetElem+1 .. offsetElem+nElems
+    if (e > 0 && rank[e] < rank[e - 1]) return fail("piclas_gpu_init: ELEM_RANK is not ascending at element %d (ranks must own contiguous element ranges)", e + 1);
+    if ((rank[e] == g.myRank) != (e >= g.offsetElem && e < g.offsetElem + g.nElems))
+      return fail("piclas_gpu_init: ELEM_RANK of element %d disagrees with offsetElem=%d / nElems=%d of rank %d", e + 1, g.offsetElem, g.nElems, g.myRank);
     TriaElem& t = tria[e];
     memset(&t, 0, sizeof(t));
     for (int n = 0; n < 8; ++n)
@@ -993,6 +1023,7 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
   begin_timing();
   const int64_t chunk = 1 << 22;
   if (reserve_stage(n < chunk ? (n ? n : 1) : chunk)) return 1;
+  CK(cudaMemsetAsync(g.dCounters + 7, 0, sizeof(int), g.st));
   for (int64_t c0 = 0; c0 < n; c0 += chunk) {
     const int64_t m = (n - c0 < chunk) ? n - c0 : chunk;
     int32_t* dI = g.dStageI;
@@ -1009,13 +1040,24 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
                                                                ParticleInside ? dI + 2 * g.stageCap : nullptr,
                                                                IsNewPart ? dI + 3 * g.stageCap : nullptr,
                                                                (ids && g.carryIDs) ? g.dStageL : nullptr, base + c0,
-                                                               haveRef ? dRef : nullptr);
+                                                               haveRef ? dRef : nullptr, g.nGlobalElems, g.prm.nSpecies, g.dCounters + 7);
     ++g.lastLaunches;
     if (g.ref && !PartPosRef) {  // as at emission: PartPosRef from GetPositionInRefElem in the particle's element
       k_init_posref<<<(unsigned)((m + 127) / 128), 128, 0, g.st>>>(g.buf[g.cur], base + c0, m, g.dGeo);
       ++g.lastLaunches;
     }
     CK(cudaStreamSynchronize(g.st));
+  }
+  {
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, g.dCounters + 7, sizeof(int), cudaMemcpyDeviceToHost, g.st));
+    CK(cudaStreamSynchronize(g.st));
+    if (bad) {
+      g.nPart = 0;   // the population is unusable: nothing of this upload is kept
+      g.hTailOff.assign(g.nRanks + 2, 0);
+      if (bad & 1) return fail("piclas_gpu_upload_particles: GlobalElemID outside 1..nGlobalElems=%d", g.nGlobalElems);
+      return fail("piclas_gpu_upload_particles: PartSpecies outside 1..nSpecies=%d", g.prm.nSpecies);
+    }
   }
   const int64_t nIn = base + n;
   if (nIn > 0) {
@@ -1040,14 +1082,17 @@ int piclas_gpu_download_particles(int64_t nmax, double* PartState, int32_t* Part
   const int64_t n = g.nPart;
   if (n_out) *n_out = n;
   if (n > nmax) return fail("piclas_gpu_download_particles: %lld particles do not fit into nmax=%lld", (long long)n, (long long)nmax);
-  if (PartPosRef && !g.xiValid && !g.ref) return fail("piclas_gpu_download_particles: reference positions are not current (call deposit first)");
   const int64_t chunk = 1 << 22;
   if (reserve_stage(n < chunk ? (n ? n : 1) : chunk)) return 1;
   for (int64_t c0 = 0; c0 < n; c0 += chunk) {
     const int64_t m = (n - c0 < chunk) ? n - c0 : chunk;
     double* dXi = g.dStage + 6 * g.stageCap;
     k_soa_to_aos<<<(unsigned)((m + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], c0, m, g.dStage, g.dStageI, g.dStageI + g.stageCap,
-                                                               PartPosRef ? dXi : nullptr, ids ? g.dStageL : nullptr);
+                                                               (PartPosRef && g.ref) ? dXi : nullptr, ids ? g.dStageL : nullptr);
+    // TriaTracking keeps no PartPosRef: it is what GetPositionInRefElem yields for the current position and element, as in the
+    // deposition (pic_depo_method.f90:479); the cached copy of the last deposition may be absent (closed-form path) or stale
+    if (PartPosRef && !g.ref && m > 0)
+      k_posref_download<<<(unsigned)((m + 127) / 128), 128, 0, g.st>>>(g.buf[g.cur], c0, m, g.dGeo, g.fast ? g.dAff : nullptr, dXi);
     if (PartState) CK(cudaMemcpyAsync(PartState + c0 * 6, g.dStage, m * 6 * 8, cudaMemcpyDeviceToHost, g.st));
     if (PartSpecies) CK(cudaMemcpyAsync(PartSpecies + c0, g.dStageI, m * 4, cudaMemcpyDeviceToHost, g.st));
     if (GlobalElemID) CK(cudaMemcpyAsync(GlobalElemID + c0, g.dStageI + g.stageCap, m * 4, cudaMemcpyDeviceToHost, g.st));
@@ -1089,7 +1134,7 @@ static int deposit_local() {
 
 static int deposit_finish(double* PartSource, double* NodeSource) {
   k_node_final<<<(g.nNodes * 4 + 255) / 256, 256, 0, g.st>>>(g.dS, g.dPerN, g.dPerOff, g.dPerNodes, g.dNodeVolume, g.dNodeSource, g.nNodes,
-                                                            g.prm.CartesianPeriodic ? 1 : 1);
+                                                            1);
   ++g.lastLaunches;
   if (g.nElems > 0) {
     switch (g.NP) {

@@ -86,3 +86,56 @@ def test_particles_outside_the_rank_are_refused_and_dead_particles_dropped():
         assert gpu.lib.piclas_gpu_exchange_finish(C.c_int64(0)) == 0               # nobody arrives; the emigrants are gone
         assert gpu.NumParticles() == int(inside.sum()) - int(nsend[1])
         gpu.Deposition()
+
+
+def test_host_input_that_indexes_device_tables_is_range_checked():
+    """GlobalElemID / PartSpecies go straight into device table lookups; ELEM_RANK must agree with offsetElem / nElems."""
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (3, 3, 3), 2)
+    PS, spec, elem = _plasma(mesh)
+    with ParticleStep(mesh, cases.electron_params()) as gpu:
+        bad = elem.copy()
+        bad[17] = mesh.nElems + 5
+        with pytest.raises(PiclasGpuError, match="GlobalElemID outside"):
+            gpu.UploadParticles(PS, spec, bad)
+        assert gpu.NumParticles() == 0
+        bs = spec.copy()
+        bs[3] = 2                                                                  # one species configured
+        with pytest.raises(PiclasGpuError, match="PartSpecies outside"):
+            gpu.UploadParticles(PS, bs, elem)
+        bad[17] = 0                                                                # dead slots may carry any element id
+        inside = np.ones(len(spec), dtype=np.int32)
+        inside[17] = 0
+        gpu.UploadParticles(PS, spec, bad, ParticleInside=inside)
+        assert gpu.NumParticles() == len(spec) - 1
+    off = hm.partition(mesh, 2)
+    prm = cases.electron_params(nRanks=2, myRank=0)
+    with pytest.raises(PiclasGpuError, match="disagrees with offsetElem"):
+        ParticleStep(mesh, prm, offsetElem=int(off[0]), nElems=int(off[1] - off[0]) - 1)
+    mesh.ElemInfo[5, 6], mesh.ElemInfo[6, 6] = 1, 0                                # ranks interleaved
+    with pytest.raises(PiclasGpuError, match="not ascending|disagrees"):
+        ParticleStep(mesh, prm, offsetElem=int(off[0]), nElems=int(off[1] - off[0]))
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+def test_partposref_download_after_cvwm_deposit(arith):
+    """with the restructured arithmetic the deposition does not store xi on affine elements; the downloaded PartPosRef
+    must still be the reference position of the current particle position (GetPositionInRefElem)."""
+    from oracle_lib import Oracle
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (3, 4, 3), 2)
+    PS, spec, elem = _plasma(mesh, 2000)
+    prm = cases.electron_params(arithmetic=arith)
+    orc = Oracle(mesh, prm)
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(PS, spec, elem, ids=np.arange(len(spec)))
+        gpu.SetField(cases.smooth_field(mesh, amp=1e-4))
+        for it in range(2):
+            gpu.Deposition()
+            d = gpu.DownloadParticles(want_ref=True)
+            xi, suc, _ = orc.position_in_ref_elem(d["PartState"][:, :3], d["GlobalElemID"])
+            assert suc.all()
+            assert np.abs(d["PartPosRef"] - xi).max() <= 1e-12
+            gpu.PushAndTrack(1e-8, it)
+        d = gpu.DownloadParticles(want_ref=True)                                   # no deposition since the push: still current
+        xi, _, _ = orc.position_in_ref_elem(d["PartState"][:, :3], d["GlobalElemID"])
+        assert np.abs(d["PartPosRef"] - xi).max() <= 1e-12
+    orc.close()

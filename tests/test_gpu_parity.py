@@ -317,3 +317,56 @@ def test_kinetic_energy_reduction():
     for s in (1, 2):
         assert N[s - 1] == (spec == s).sum()
         assert abs(E[s - 1] - ek[spec == s].sum()) <= 1e-12 * ek[spec == s].sum()
+
+
+def test_many_particles_per_element(arith):
+    """More than 4096 particles in every element (2 x 2 x 2 box, 6250 per element): the multi-sweep loop of the per-element
+    kernels and full leaver queues, compared with the oracle particle by particle (VERDICT r1, weak #2)."""
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (2, 2, 2), 3)
+    prm = cases.electron_params(arithmetic=arith)
+    dt = 1e-8
+    PS, spec = cases.uniform_plasma(mesh, 50000, seed=77, vth_cells=0.2, dt=dt)
+    E = cases.smooth_field(mesh, amp=2.0e-4)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    assert np.bincount(elem).max() > 4096
+    w = run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=4)
+    print("worst rel diffs", w)
+
+
+def test_flagship_density_against_oracle():
+    """The benchmark's own configuration at 1/64 of its volume: 16^3 elements, N = 3, 1907 particles per element, v_th dt = 0.2 h,
+    restructured arithmetic (what bench.py runs), three steps; every particle's element, position and velocity and the deposited
+    sources against the (threaded) oracle (VERDICT r1, weak #3)."""
+    import os
+    from piclas_b200.particle_step import ParticleStep
+    import bench as B
+    ne, N = 16, 3
+    mesh, E, dt, vth = B.workload(ne, N)
+    n = 1907 * ne ** 3
+    rng = np.random.default_rng(20261017)
+    PS0, elem0 = B.gen_particles(rng, n, ne, vth)
+    prm = cases.electron_params(arithmetic=1, MacroParticleFactor=(1.0e3,))
+    spec = np.ones(n, dtype=np.int32)
+    inside = np.ones(n, dtype=np.int32)
+    isnew = np.zeros(n, dtype=np.int32)
+    thr = min(os.cpu_count() or 1, 32)
+    orc = Oracle(mesh, prm)
+    PSo, elo = PS0.copy(), elem0.copy()
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(PS0, spec, elem0, IsNewPart=isnew, ids=np.arange(n, dtype=np.int64))
+        gpu.SetField(E)
+        for it in range(3):
+            PSr, NSr = orc.deposit(PSo, spec, elo, inside, threads=thr)
+            PSg, NSg = gpu.Deposition()
+            for c in range(4):
+                assert _rel(NSg[:, c], NSr[:, c]) <= RTOL and _rel(PSg[..., c], PSr[..., c]) <= RTOL, (it, c)
+            nlo, _, _ = orc.push_track(dt, PSo, spec, elo, inside, isnew, E, threads=thr)
+            assert gpu.PushAndTrack(dt, it) == nlo == 0
+            d = _by_id(gpu.DownloadParticles())
+            assert np.array_equal(d["ids"], np.arange(n))
+            assert np.array_equal(d["GlobalElemID"], elo), "element ownership differs at benchmark density (step %d)" % it
+            assert _rel(d["PartState"][:, :3], PSo[:, :3]) <= RTOL and _rel(d["PartState"][:, 3:], PSo[:, 3:]) <= RTOL
+            # per-particle relative position error (north_star wording), for the record: positions are O(1) in the unit box
+            pp = np.abs(d["PartState"][:, :3] - PSo[:, :3]) / np.maximum(np.abs(PSo[:, :3]), 1e-3)
+            assert pp.max() <= 1e-11
+    orc.close()
