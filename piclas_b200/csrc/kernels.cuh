@@ -76,11 +76,13 @@ __device__ __forceinline__ void deposit_particle_general(const PartBuf& pb, int6
   const int spec = meta & META_SPEC_MASK;
   double xi[3];
   const bool suc = (position_in_ref_elem(sg, x, xi, true, true) & 1) != 0;
-  PXI[p] = xi[0];
-  PXI[1 * PS_ + p] = xi[1];
-  PXI[2 * PS_ + p] = xi[2];
-  const uint8_t nmeta = suc ? (meta & ~META_XIFAIL) : (meta | META_XIFAIL);
-  if (nmeta != meta) pb.meta[p] = nmeta;
+  if (PXI) {   // reference position cached for the interpolation of the same step (sorted layout only; the bins keep none)
+    PXI[p] = xi[0];
+    PXI[1 * PS_ + p] = xi[1];
+    PXI[2 * PS_ + p] = xi[2];
+    const uint8_t nmeta = suc ? (meta & ~META_XIFAIL) : (meta | META_XIFAIL);
+    if (nmeta != meta) pb.meta[p] = nmeta;
+  }
   const double q = cst.ChargeIC[spec];
   if (!(fabs(q) > 0.0)) return;  // isDepositParticle
   const double Charge = q * cst.MPF[spec];

@@ -13,6 +13,7 @@
 #include "sf.cuh"
 #include "ref.cuh"
 #include "sort.cuh"
+#include "bins.cuh"
 
 namespace {
 
@@ -95,6 +96,23 @@ struct Ctx {
   int64_t* dEmigOff = nullptr;   // [nRanks+1]
   int64_t commSendCap = 0, commRecvCap = 0;
   int commSize = 8;
+  // binned layout (bins.cuh): TriaTracking + cell_volweight_mean (or no deposition)
+  bool binEligible = false;      // this configuration steps on the bins
+  bool binned = false;           // the particles live in the bins (else: sorted arrays buf[cur] + dElemOff)
+  bool sortedViewValid = false;  // binned, and buf[0] + dElemOff hold a current copy in sorted order (download, analysis)
+  bool wantRebin = false;        // regions overflowed in the last step: re-plan the capacities before the next one
+  PartBuf bins;
+  int64_t binSlotsCap = 0;
+  PartBuf pool[2];
+  int64_t poolCap[2] = {0, 0};
+  int64_t* dPoolOff[2] = {nullptr, nullptr};   // [nElems + nRanks + 2] each
+  int32_t *dCapMain = nullptr, *dCapIn = nullptr, *dNMain = nullptr, *dNIn = nullptr;
+  int64_t *dBinBase = nullptr, *dBinTmp = nullptr;
+  PushElem* dPushElem = nullptr;
+  int binParity = 0;
+  int64_t nFar = 0;              // records of the far list of the open step
+  double mainSlack = 0.10, inFrac = 0.09;
+  int64_t farStats[4] = {0, 0, 0, 0};   // last step: far records, side movers, overflowed main, overflowed inbox
   // timing
   double lastMs = 0.;
   int lastLaunches = 0;
@@ -175,7 +193,7 @@ int reserve_particles(int64_t need) {
     free_partbuf(g.buf[0]);
     free_partbuf(g.buf[1]);
   }
-  {
+  if (!g.binEligible) {
     const int64_t stride = nb[0].stride;
     double* nx = nullptr;
     CK(cudaMalloc((void**)&nx, (size_t)stride * 3 * 8));
@@ -473,6 +491,41 @@ void launch_dofs() {
   k_nodes_to_dofs<NP><<<(unsigned)((total + 255) / 256), 256, 0, g.st>>>(g.dNodeSource, g.dElemNodeU, g.dPartSource, g.nElems);
 }
 
+// grows the sorted buffers (and what is sized with them) while the far list of an open step lives in them
+int reserve_far(int64_t need, int64_t keep) {
+  if (need <= g.cap) return 0;
+  int64_t ncap = need + need / 8 + 1024;
+  PartBuf nb[2];
+  if (alloc_partbuf(nb[0], ncap, g.carryIDs)) return 1;
+  if (alloc_partbuf(nb[1], ncap, g.carryIDs)) return 1;
+  uint32_t* nk = nullptr;
+  CK(cudaMalloc((void**)&nk, ncap * 4));
+  if (keep > 0 && g.cap > 0) {
+    for (int d = 0; d < 3; ++d) {
+      CK(cudaMemcpy(nb[0].x[d], g.buf[0].x[d], keep * 8, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(nb[0].v[d], g.buf[0].v[d], keep * 8, cudaMemcpyDeviceToDevice));
+      CK(cudaMemcpy(nb[1].x[d], g.buf[1].x[d], keep * 8, cudaMemcpyDeviceToDevice));
+    }
+    CK(cudaMemcpy(nb[0].elem, g.buf[0].elem, keep * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(nb[1].elem, g.buf[1].elem, keep * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(nb[0].meta, g.buf[0].meta, keep, cudaMemcpyDeviceToDevice));
+    if (g.carryIDs) CK(cudaMemcpy(nb[0].id, g.buf[0].id, keep * 8, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(nk, g.dKeys, keep * 4, cudaMemcpyDeviceToDevice));
+  }
+  if (g.cap > 0) { free_partbuf(g.buf[0]); free_partbuf(g.buf[1]); }
+  cudaFree(g.dKeys);
+  g.dKeys = nk;
+  g.buf[0] = nb[0];
+  g.buf[1] = nb[1];
+  g.cap = ncap;
+  g.cur = 0;
+  g.sortedViewValid = false;
+  CK(sort_workspace_reserve(g.sortws, (size_t)ncap));
+  return 0;
+}
+
+#include "bins_host.inc"
+
 void begin_timing() {
   g.lastLaunches = 0;
   cudaEventRecord(g.ev0, g.st);
@@ -515,6 +568,7 @@ int piclas_gpu_finalize(void) {
   }
   cudaFree(g.dXi[0]);
   sort_workspace_free(g.sortws);
+  bins_free();
   for (int i = 0; i < 10; ++i) if (g.evp[i]) cudaEventDestroy(g.evp[i]);
   if (g.ev0) cudaEventDestroy(g.ev0);
   if (g.ev1) cudaEventDestroy(g.ev1);
@@ -648,9 +702,11 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     memcpy(ge.slen, m->slenXiEtaZetaBasis + (size_t)e * 6, 6 * 8);
   }
   g.fast = p->arithmetic != 0;
+  std::vector<PlaneElem> planes;
+  std::vector<AffElem> affs;
   if (g.fast) {
-    std::vector<PlaneElem> planes(nG);
-    std::vector<AffElem> affs(nG);
+    planes.resize(nG);
+    affs.resize(nG);
     for (int e = 0; e < nG; ++e) {
       const TriaElem& t = tria[e];
       PlaneElem& pl = planes[e];
@@ -735,6 +791,20 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   if (upload(&g.dGeo, geo.data(), (size_t)nG)) return 1;
   if (upload(&g.dElemRank, rank.data(), (size_t)nG)) return 1;
   if (upload(&g.dElemXGP, m->Elem_xGP, (size_t)nG * g.ND * 3)) return 1;
+
+  // ---- particle layout: bins (bins.cuh) for TriaTracking with cell_volweight_mean or without deposition; the sorted arrays of
+  //      round 1 for RefMapping and the shape functions (PICLAS_GPU_LAYOUT=sorted forces them everywhere: A/B measurements)
+  {
+    const char* lay = getenv("PICLAS_GPU_LAYOUT");
+    const bool forceSorted = lay && strcmp(lay, "sorted") == 0;
+    g.binEligible = !isRef && !(p->DoDeposition && isSF) && !forceSorted;
+    if (const char* v = getenv("PICLAS_GPU_BIN_MAIN_SLACK")) g.mainSlack = atof(v);
+    if (const char* v = getenv("PICLAS_GPU_BIN_INBOX_FRAC")) g.inFrac = atof(v);
+    if (g.binEligible) {
+      if (bins_alloc_tables()) return 1;
+      if (build_push_elems(m, tria, planes, affs, rank)) return 1;
+    }
+  }
 
   // ---- cell_volweight_mean tables ---------------------------------------------------------------------------------
   {
@@ -1017,6 +1087,10 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
   CK(cudaSetDevice(g.device));
   if (n < 0) return fail("piclas_gpu_upload_particles: n < 0");
   if (n > 0 && (!PartState || !PartSpecies || !GlobalElemID)) return fail("piclas_gpu_upload_particles: null array");
+  if (g.binned) {   // back to the sorted arrays: the upload appends there and sorts; the next step re-plans the bins
+    if (append) { if (bins_to_sorted()) return 1; }
+    else { g.binned = false; g.sortedViewValid = false; }
+  }
   const int64_t base = append ? g.nPart : 0;
   if (base + n >= (int64_t)0x7fffffff) return fail("piclas_gpu_upload_particles: more than 2^31-1 particles on one GPU");
   if (reserve_particles(base + n)) return 1;
@@ -1079,6 +1153,10 @@ int piclas_gpu_download_particles(int64_t nmax, double* PartState, int32_t* Part
   if (!g.ready) return fail("piclas_gpu_download_particles: not initialised");
   if (g.exchangePending) return fail("piclas_gpu_download_particles: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
   CK(cudaSetDevice(g.device));
+  if (g.binned) {
+    if (reserve_far(g.nPart, 0)) return 1;
+    if (bins_sorted_view()) return 1;
+  }
   const int64_t n = g.nPart;
   if (n_out) *n_out = n;
   if (n > nmax) return fail("piclas_gpu_download_particles: %lld particles do not fit into nmax=%lld", (long long)n, (long long)nmax);
@@ -1115,8 +1193,17 @@ int piclas_gpu_set_field(const double* E) {
 
 static int deposit_local() {
   const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
+  if (g.binEligible && ensure_binned()) return 1;
   cudaEventRecord(g.evp[0], g.st);
-  if (grid > 0) {
+  if (grid > 0 && g.binned) {
+    if (g.fast)
+      k_bin_deposit_cvwm<true><<<grid, BIN_NT, 0, g.st>>>(g.bins, g.pool[g.binParity], bin_view(), g.binParity, g.offsetElem, g.dGeo, g.dTria, g.dAff,
+                                                         g.dElemAcc);
+    else
+      k_bin_deposit_cvwm<false><<<grid, BIN_NT, 0, g.st>>>(g.bins, g.pool[g.binParity], bin_view(), g.binParity, g.offsetElem, g.dGeo, g.dTria, g.dAff,
+                                                          g.dElemAcc);
+    ++g.lastLaunches;
+  } else if (grid > 0) {
     if (g.fast)
       k_deposit_cvwm<true><<<grid, STEP_NT, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nElems, g.offsetElem, g.dGeo, g.dTria, g.dAff, g.dElemAcc,
                                                        g.ref ? 1 : 0);
@@ -1128,7 +1215,7 @@ static int deposit_local() {
   k_node_sum<<<(g.nNodes * 4 + 255) / 256, 256, 0, g.st>>>(g.dAdjOff, g.dAdj, g.dElemAcc, g.dS, g.nNodes);
   ++g.lastLaunches;
   CK(cudaGetLastError());
-  g.xiValid = true;
+  g.xiValid = !g.binned;
   return 0;
 }
 
@@ -1296,6 +1383,10 @@ int piclas_gpu_kinetic_energy(double* Ekin, int64_t* nPart) {
   const int ns = g.prm.nSpecies;
   for (int s = 0; s < ns; ++s) { if (Ekin) Ekin[s] = 0.; if (nPart) nPart[s] = 0; }
   if (g.nPart == 0) return 0;
+  if (g.binned) {
+    if (reserve_far(g.nPart, 0)) return 1;
+    if (bins_sorted_view()) return 1;
+  }
   const int nb = g.nSMs * 8;
   const int64_t chunk = (g.nPart + nb - 1) / nb;
   double* dE = nullptr;
@@ -1357,12 +1448,77 @@ int piclas_gpu_deposit_finish(double* PartSource, double* NodeSource) {
   return rc;
 }
 
+// the step on the bins: push + delivery, exact walk of the far list, pool for the next step
+static int push_track_binned(double dt, int32_t* nLost) {
+  if (ensure_binned()) return 1;
+  if (reserve_far(g.nPart, 0)) return 1;   // the far list (in the idle sorted buffers) can take every particle
+  begin_timing();
+  CK(cudaMemsetAsync(g.dCounters, 0, 8 * sizeof(int), g.st));
+  cudaEventRecord(g.evp[3], g.st);
+  if (g.nElems > 0) {
+    switch (g.NP) {
+      case 2: launch_bin_push<2>(dt); break;
+      case 3: launch_bin_push<3>(dt); break;
+      case 4: launch_bin_push<4>(dt); break;
+      case 5: launch_bin_push<5>(dt); break;
+      case 6: launch_bin_push<6>(dt); break;
+      case 7: launch_bin_push<7>(dt); break;
+      case 8: launch_bin_push<8>(dt); break;
+    }
+    CK(cudaGetLastError());
+  }
+  int hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
+  CK(cudaStreamSynchronize(g.st));
+  const int64_t nFar = hc[2];
+  if (nFar > 0) launch_far_walk(nFar);
+  CK(cudaGetLastError());
+  cudaEventRecord(g.evp[4], g.st);
+  g.nFar = nFar;
+  g.farStats[0] = nFar; g.farStats[1] = hc[4]; g.farStats[2] = hc[5]; g.farStats[3] = hc[6];
+  if (hc[5] > 0 || hc[6] > 0) {
+    g.wantRebin = true;                                      // regions overflowed: capacities from the new populations next time
+    if (hc[6] > 0 && g.inFrac < 0.5) g.inFrac *= 2.0;        // inboxes too small for this flow (drifting populations)
+  }
+  g.sortedViewValid = false;
+  if (g.nRanks > 1) {
+    // several ranks: the emigrants are taken out of the far list (piclas_gpu_exchange_info), the immigrants join it, and
+    // piclas_gpu_exchange_finish sorts it into the pool
+    CK(cudaStreamSynchronize(g.st));
+    g.exchangePending = true;
+    g.nUnsorted = nFar;
+  } else {
+    if (far_finish(nFar, far_max_tag())) return 1;
+    g.nPart = g.nPart - nFar + (nFar > 0 ? g.hTailOff[0] : 0);
+  }
+  CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
+  CK(cudaStreamSynchronize(g.st));
+  if (getenv("PICLAS_GPU_DEBUG"))
+    fprintf(stderr, "[piclas_gpu] push_track (bins): %lld particles, %d delivered to face neighbours in-kernel, %lld through the far list, "
+            "%d + %d diverted by full regions\n", (long long)g.nPart, (int)g.farStats[1], (long long)nFar, (int)g.farStats[2], (int)g.farStats[3]);
+  cudaEventRecord(g.evp[5], g.st);
+  end_timing();
+  {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, g.evp[3], g.evp[4]);
+    cudaEventElapsedTime(&b, g.evp[4], g.evp[5]);
+    g.phaseMs[2] = a;
+    g.phaseMs[3] = b;
+  }
+  if (nLost) *nLost = hc[0];
+  if (hc[1] == TRK_ERR_BC) return fail("piclas_gpu_push_track: particle hit a boundary condition that is not supported");
+  if (hc[1] == TRK_ERR_ELEM) return fail("piclas_gpu_push_track: ERROR: Element not defined! Please increase the size of the halo region (HaloEpsVelo)!");
+  if (hc[1] == TRK_ERR_LOOP) return fail("piclas_gpu_push_track: tracking loop did not terminate");
+  return 0;
+}
+
 int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
   (void)iter;
   if (!g.ready) return fail("piclas_gpu_push_track: not initialised");
   CK(cudaSetDevice(g.device));
   if (g.prm.DoInterpolation && !g.haveField) return fail("piclas_gpu_push_track: no field set (piclas_gpu_set_field)");
   if (g.exchangePending) return fail("piclas_gpu_push_track: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
+  if (g.binEligible) return push_track_binned(dt, nLost);
   begin_timing();
   CK(cudaMemsetAsync(g.dCounters, 0, 8 * sizeof(int), g.st));
   cudaEventRecord(g.evp[3], g.st);
@@ -1454,7 +1610,8 @@ int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void*
     uint32_t *sk = nullptr, *perm = nullptr;
     CK(radix_sort_by_key(g.sortws, g.dEmigKey, (size_t)nEmig, rankBits, g.st, &sk, &perm, &g.lastLaunches));   // stable: by rank, then particle order
     CK(segment_offsets(sk, (size_t)nEmig, (uint32_t)g.nRanks, g.dEmigOff, g.st));
-    k_pack_emigrants_idx<<<(unsigned)((nEmig + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], g.dEmigIdx, perm, nEmig, g.commSize, g.ref ? 1 : 0,
+    // (bins: the far list lies in buf[0] with the field layout of the sorted arrays)
+    k_pack_emigrants_idx<<<(unsigned)((nEmig + 255) / 256), 256, 0, g.st>>>(g.buf[g.binned ? 0 : g.cur], g.dEmigIdx, perm, nEmig, g.commSize, g.ref ? 1 : 0,
                                                                              g.dCommSend, g.dKeys, (uint32_t)(g.nElems + g.nRanks));
     g.lastLaunches += 2;
     CK(cudaGetLastError());
@@ -1490,6 +1647,35 @@ int piclas_gpu_exchange_finish(int64_t nRecvTotal) {
     return 0;
   }
   if (nRecvTotal > 0 && nRecvTotal > g.commRecvCap) return fail("piclas_gpu_exchange_finish: receive buffer too small");
+  if (g.binned) {
+    // the immigrants join the far list behind this rank's own records, then one sort by destination builds the pool
+    const int64_t nFar = g.nFar, nAll = nFar + nRecvTotal;
+    if (nAll >= (int64_t)0x7fffffff) return fail("piclas_gpu_exchange_finish: more than 2^31-1 particles on one GPU");
+    if (reserve_far(nAll, nFar)) return 1;
+    cudaEventRecord(g.evp[8], g.st);
+    const uint32_t tag0 = far_max_tag();
+    if (nRecvTotal > 0) {
+      k_unpack_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[0], nFar, nRecvTotal, g.commSize, 0, g.dCommRecv);
+      k_keys_from_elem<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[0].elem + nFar, g.dElemRank, g.dKeys + nFar, nRecvTotal,
+                                                                               g.nElems, g.offsetElem, g.myRank, g.nRanks);
+      k_far_tag_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(far_alias().src, nFar, nRecvTotal, tag0);
+      g.lastLaunches += 3;
+      CK(cudaGetLastError());
+    }
+    g.exchangePending = false;
+    if ((uint64_t)tag0 + (uint64_t)nRecvTotal >= 0xffffffffull) return fail("piclas_gpu_exchange_finish: origin tags exceed 32 bits");
+    if (far_finish(nAll, tag0 + (uint32_t)nRecvTotal)) return 1;
+    const int64_t staying = nAll > 0 ? g.hTailOff[0] : 0;
+    if (nAll > 0 && g.hTailOff[g.nRanks] != staying) return fail("piclas_gpu_exchange_finish: received particles that belong to another rank");
+    g.nPart = g.nPart - nFar + staying;
+    cudaEventRecord(g.evp[9], g.st);
+    cudaEventSynchronize(g.evp[9]);
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, g.evp[6], g.evp[7]);
+    cudaEventElapsedTime(&b, g.evp[8], g.evp[9]);
+    g.phaseMs[3] = a + b;
+    return 0;
+  }
   const int64_t nIn0 = g.nUnsorted, nIn = nIn0 + nRecvTotal;
   if (nIn >= (int64_t)0x7fffffff) return fail("piclas_gpu_exchange_finish: more than 2^31-1 particles on one GPU");
   if (reserve_particles(nIn)) return 1;

@@ -230,6 +230,75 @@ cudaError_t radix_sort_by_key(SortWorkspace& ws, const uint32_t* keys, size_t n,
   return sort_passes<8>(ws, keys, n, 4, st, sortedKeys, perm, nLaunches);
 }
 
+// ---- stable sort by (keysHi, keysLo): LSD passes over the digits of keysLo, then over those of keysHi ------------------------------
+// Used for the far list of the binned layout: keysHi = destination, keysLo = unique origin tag, so that the order inside a
+// destination does not depend on the order in which the CTAs appended their records.
+namespace {
+template <int RADIX_BITS>
+void one_pass(SortWorkspace& ws, const uint32_t* kin, const uint32_t* pin, uint32_t* kout, uint32_t* pout, size_t n, int shift,
+              cudaStream_t st, int* nLaunches) {
+  constexpr int RADIX = 1 << RADIX_BITS;
+  const uint32_t nBlocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+  const uint32_t nGroups = (nBlocks + COL_GB - 1) / COL_GB;
+  k_hist<RADIX><<<nBlocks, SORT_NT, 0, st>>>(kin, n, shift, RADIX - 1, ws.blockHist);
+  k_col_reduce<RADIX><<<nGroups, 256, 0, st>>>(ws.blockHist, nBlocks, ws.groupSum);
+  k_col_scan<RADIX><<<1, RADIX, 0, st>>>(ws.groupSum, nGroups);
+  k_col_apply<RADIX><<<nGroups, 256, 0, st>>>(ws.blockHist, nBlocks, ws.groupSum);
+  k_scatter<RADIX><<<nBlocks, SORT_NT, 0, st>>>(kin, pin, kout, pout, n, shift, RADIX - 1, ws.blockHist);
+  *nLaunches += 5;
+}
+void plan_digits(int bits, int* width, int* passes) {
+  if (bits <= 8) { *width = 8; *passes = 1; }
+  else if (bits <= 10) { *width = 10; *passes = 1; }
+  else if (bits <= 16) { *width = 8; *passes = 2; }
+  else if (bits <= 20) { *width = 10; *passes = 2; }
+  else if (bits <= 24) { *width = 8; *passes = 3; }
+  else if (bits <= 30) { *width = 10; *passes = 3; }
+  else { *width = 8; *passes = 4; }
+}
+}  // namespace
+
+cudaError_t radix_sort_two_keys(SortWorkspace& ws, const uint32_t* keysLo, int bitsLo, const uint32_t* keysHi, int bitsHi, size_t n,
+                                cudaStream_t st, uint32_t** sortedHi, uint32_t** perm, int* nLaunches) {
+  if (n > ws.capacity) return cudaErrorInvalidValue;
+  if (n == 0) {
+    *sortedHi = ws.keysA;
+    *perm = ws.permA;
+    return cudaSuccess;
+  }
+  const uint32_t* kin = keysLo;
+  const uint32_t* pin = nullptr;
+  uint32_t* kout = ws.keysB;
+  uint32_t* pout = ws.permB;
+  auto advance = [&]() {
+    kin = kout;
+    pin = pout;
+    pout = (pout == ws.permB) ? ws.permA : ws.permB;
+    kout = (kout == ws.keysB) ? ws.keysA : ws.keysB;
+  };
+  int w, np;
+  plan_digits(bitsLo, &w, &np);
+  for (int p = 0; p < np; ++p) {
+    if (w == 8) one_pass<8>(ws, kin, pin, kout, pout, n, p * 8, st, nLaunches);
+    else one_pass<10>(ws, kin, pin, kout, pout, n, p * 10, st, nLaunches);
+    advance();
+  }
+  // destination keys in the order reached so far (kout is free: it holds the keys of the pass before the last one)
+  k_gather<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keysHi, kout, pin, n);
+  ++*nLaunches;
+  kin = kout;
+  kout = (kout == ws.keysB) ? ws.keysA : ws.keysB;
+  plan_digits(bitsHi, &w, &np);
+  for (int p = 0; p < np; ++p) {
+    if (w == 8) one_pass<8>(ws, kin, pin, kout, pout, n, p * 8, st, nLaunches);
+    else one_pass<10>(ws, kin, pin, kout, pout, n, p * 10, st, nLaunches);
+    advance();
+  }
+  *sortedHi = const_cast<uint32_t*>(kin);
+  *perm = const_cast<uint32_t*>(pin);
+  return cudaGetLastError();
+}
+
 // all particle arrays in one pass: the permutation is read once
 __global__ void k_gather_particles(const double* __restrict__ x0, const double* __restrict__ x1, const double* __restrict__ x2,
                                    const double* __restrict__ v0, const double* __restrict__ v1, const double* __restrict__ v2,

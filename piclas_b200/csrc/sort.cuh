@@ -25,6 +25,10 @@ void sort_workspace_free(SortWorkspace& ws);
 cudaError_t radix_sort_by_key(SortWorkspace& ws, const uint32_t* keys, size_t n, int bits, cudaStream_t st,
                               uint32_t** sortedKeys, uint32_t** perm, int* nLaunches);
 
+// stable sort by (keysHi, keysLo) (keysLo < 2^bitsLo, keysHi < 2^bitsHi): *sortedHi = keysHi in sorted order, *perm as above
+cudaError_t radix_sort_two_keys(SortWorkspace& ws, const uint32_t* keysLo, int bitsLo, const uint32_t* keysHi, int bitsHi, size_t n,
+                                cudaStream_t st, uint32_t** sortedHi, uint32_t** perm, int* nLaunches);
+
 // out[i] = in[perm[i]]
 cudaError_t gather_f64(const double* in, double* out, const uint32_t* perm, size_t n, cudaStream_t st);
 cudaError_t gather_i32(const int32_t* in, int32_t* out, const uint32_t* perm, size_t n, cudaStream_t st);
