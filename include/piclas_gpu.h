@@ -202,10 +202,20 @@ int piclas_gpu_exchange_recv_buffer(int64_t nRecvTotal, void **devRecvBuf);
 int piclas_gpu_exchange_finish(int64_t nRecvTotal);
 
 /* ---- cell_volweight_mean node halo (replaces pic_depo_method.f90:565-673) ------------------------------
- * deposit() leaves the rank-local NodeSource on the device; the caller sums it over ranks in rank
- * order and hands the result back before PartSource is formed.  Single-rank runs never call these. */
+ * deposit() leaves the rank-local NodeSource on the device; the caller sums it over ranks (an all-reduce
+ * is deterministic for a fixed rank count but not rank-ordered; piclas_gpu_node_halo_info below is) and
+ * hands the result back before PartSource is formed.  Single-rank runs never call these. */
 int piclas_gpu_nodesource_device(void **devNodeSource /* double[nUniqueGlobalNodes][4] */);
 int piclas_gpu_deposit_finish(double *PartSource, double *NodeSource);
+/* The same halo on the compact list of the nodes that several ranks contribute to (elements of two ranks meet there, directly
+ * or through a periodic partner; the reference exchanges exactly these, pic_depo.f90:298-571): after deposit(), devSend holds this
+ * rank's nDoubles = 4 * nSharedNodes sums; the caller all-gathers them into devRecvAll ([nRanks][nDoubles], rank order) and calls
+ * piclas_gpu_deposit_finish, which adds them up in rank order (deterministic).  Alternative to the full-array sum above. */
+int piclas_gpu_node_halo_info(int64_t *nDoubles, void **devSend, void **devRecvAll);
+
+/* Optional: run the library's kernels and copies on the caller's CUDA stream (cudaStream_t) instead of its own, so that the
+ * caller's collectives (NCCL, CUDA-aware MPI) are ordered with them without host synchronisation. */
+int piclas_gpu_set_stream(void *cudaStream);
 
 /* ---- shape-function DOF halo (replaces pic_depo_method.f90:940-996, ShapeMapping Send/RecvBuffer) ---------------
  * Multi-rank runs: deposit() also forms the contributions of local particles to elements of other ranks.

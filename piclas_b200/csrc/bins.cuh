@@ -24,6 +24,10 @@ constexpr int BIN_NT = 128;          // threads per CTA of the per-element kerne
 constexpr int BIN_PPT = 2;           // particles per thread and sweep (one 128-bit copy per array and thread)
 constexpr int BIN_CHUNK = BIN_NT * BIN_PPT;
 constexpr int BIN_NRANGE = 8;        // main, six side inboxes, pool
+#ifndef MONO_UNROLL_J
+#define MONO_UNROLL_J 2      // rows of the field tile in flight per thread in the Horner evaluation
+#endif
+constexpr int MONO_UJ = MONO_UNROLL_J;
 #ifndef KB_MINB
 #define KB_MINB 3                    // resident CTAs / SM of k_bin_push (register cap 65536 / (128 * KB_MINB))
 #endif
@@ -42,7 +46,10 @@ __device__ __forceinline__ int64_t bin_inbox_base(const BinView& b, int e, int p
   return b.base[e] + b.capMain[e] + (int64_t)(parity * 6 + box) * b.capIn[e];
 }
 
-// far list: particles that are not delivered by the push kernel itself.  Aliases the (idle) sorted buffers.
+// far list: particles that are not delivered by the push kernel itself.  Aliases the (idle) sorted buffers.  Element e owns the
+// slots [farBase[e], farBase[e+1]) (farBase = prefix sum of the element populations before the step: a region can never
+// overflow): its far records in the order of its particles from the bottom (no atomics, deterministic), the rare particles
+// diverted by a full main / inbox region from the top.  k_far_index then lists the used slots densely.
 struct FarBuf {
   double* x[3];    // pushed position (in), final position (out: periodic shifts, reflections)
   double* lp[3];   // LastPartPos
@@ -50,7 +57,6 @@ struct FarBuf {
   int32_t* elem;   // in: global element the walk starts in; out: final global element (0 = removed)
   uint8_t* meta;
   int64_t* id;     // optional
-  uint32_t* src;   // unique origin slot: tie-break that makes the order inside a destination deterministic
 };
 
 // Everything k_bin_push stages for one element besides the field tile: one contiguous record -> one bulk (TMA) copy.
@@ -170,6 +176,63 @@ __global__ void __launch_bounds__(1024) k_scan_i64(const int64_t* __restrict__ i
     __syncthreads();
   }
   if (threadIdx.x == 0) out[n] = carry;
+}
+
+// exclusive scan of up to 2^20 int64 values in three launches (tile sums, scan of the sums, tile scans); out[n] = total
+constexpr int SCAN_TILE = 1024;
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const int64_t* __restrict__ in, int n, int64_t* __restrict__ sums) {
+  __shared__ int64_t ws[8];
+  const int base = blockIdx.x * SCAN_TILE;
+  int64_t s = 0;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += 256) s += (base + i < n) ? in[base + i] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int64_t t = 0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    sums[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) k_scan_tiles(const int64_t* __restrict__ in, int n, const int64_t* __restrict__ tileOff /*scanned sums*/,
+                                                    int64_t* __restrict__ out) {
+  __shared__ int64_t ws[8];
+  const int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+  int64_t v[4], t = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; t += v[k]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t incl = t;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) ws[warp] = incl;
+  __syncthreads();
+  int64_t off = tileOff[blockIdx.x] + incl - t;
+  for (int w = 0; w < warp; ++w) off += ws[w];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (base + k < n) out[base + k] = off;
+    off += v[k];
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) out[n] = tileOff[gridDim.x];
+}
+
+// dense list of the used far slots: element by element, bottom part (far records) then top part (diverted particles)
+__global__ void k_far_index(const int64_t* __restrict__ farBase, const int32_t* __restrict__ nFarE /*[nElems][2]*/, const int64_t* __restrict__ dOff,
+                            int nElems, uint32_t* __restrict__ idx) {
+  for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
+    const int nb = nFarE[2 * e], nt = nFarE[2 * e + 1];
+    const int64_t b0 = farBase[e], b1 = farBase[e + 1], d0 = dOff[e];
+    for (int i = threadIdx.x; i < nb + nt; i += blockDim.x) idx[d0 + i] = (uint32_t)(i < nb ? b0 + i : b1 - 1 - (i - nb));
+  }
+}
+__global__ void k_far_total(const int32_t* __restrict__ nFarE, int nElems, int64_t* __restrict__ tot) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < nElems) tot[e] = (int64_t)nFarE[2 * e] + nFarE[2 * e + 1];
 }
 
 // sorted arrays -> bins: the element's segment becomes its main range; inboxes and pool empty
@@ -378,67 +441,106 @@ __global__ void __launch_bounds__(BIN_NT, DEP_MINB) k_bin_deposit_cvwm(PartBuf b
 }
 
 // ---- interpolate + push + own-element inside test + delivery ------------------------------------------------------------------------
-// field tile in shared memory in the host's order: sE[((k*NP + j)*NP + i)*3 + c].  Two particles per thread share every
-// shared-memory operand (one LDS feeds two FMAs) and give the FP64 pipe two independent dependency chains per accumulator.
+// Restructured arithmetic: the field tile of an element is converted once per field update (k_nodal_to_mono, at
+// piclas_gpu_set_field) from values at the Gauss points to the coefficients of the same polynomial in the monomial basis,
+//   E_c(xi, eta, zeta) = sum_ijk a[k][j][i][c] xi^i eta^j zeta^k ,
+// and evaluated by nested Horner recurrences: 3 ((N+1)^3 - 1) multiply-adds per particle (189 at N = 3) instead of the 252 + 54
+// of the sum-factorised Lagrange form, no basis values to hold in registers.  Same polynomial, differences O(1e-16) of the
+// field's magnitude (the reference's own form, eval_xyz.f90:207-215, is what arithmetic = 0 runs).  Two particles per thread
+// share every shared-memory operand (128-bit loads, one LDS feeds four FMAs).
 template <int NP>
-__device__ __forceinline__ void evaluate_field_fast2(const double xi[2][3], const double* __restrict__ sE, double out[2][3]) {
-  double L0[2][NP], L1[2][NP], L2[2][NP];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    lagrange_fast<NP>(xi[q][0], L0[q]);
-    lagrange_fast<NP>(xi[q][1], L1[q]);
-    lagrange_fast<NP>(xi[q][2], L2[q]);
-  }
+__device__ __forceinline__ void evaluate_field_mono2(const double xi[2][3], const double* __restrict__ sA, double out[2][3]) {
   double o[2][3] = {{0., 0., 0.}, {0., 0., 0.}};
 #pragma unroll 1
-  for (int k = 0; k < NP; ++k) {
-    double lz[2] = {L2[0][0], L2[1][0]};
-#pragma unroll
-    for (int m = 1; m < NP; ++m) { lz[0] = (k == m) ? L2[0][m] : lz[0]; lz[1] = (k == m) ? L2[1][m] : lz[1]; }
+  for (int k = NP - 1; k >= 0; --k) {
     double s[2][3] = {{0., 0., 0.}, {0., 0., 0.}};
+#pragma unroll MONO_UJ
+    for (int j = NP - 1; j >= 0; --j) {
+      const double* row = sA + ((k * NP + j) * NP) * 3;   // [i][c], NP * 3 doubles
+      double u[NP * 3];
+      if ((NP * 3) % 2 == 0) {
+        const double2* row2 = reinterpret_cast<const double2*>(row);
 #pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const double* row = sE + ((k * NP + j) * NP) * 3;
-      double t[2][3];
+        for (int m = 0; m < NP * 3 / 2; ++m) { const double2 w = row2[m]; u[2 * m] = w.x; u[2 * m + 1] = w.y; }
+      } else {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double u = row[c];
-        t[0][c] = u * L0[0][0];
-        t[1][c] = u * L0[1][0];
+        for (int m = 0; m < NP * 3; ++m) u[m] = row[m];
       }
+      double r[2][3];
 #pragma unroll
-      for (int i = 1; i < NP; ++i)
+      for (int c = 0; c < 3; ++c) { r[0][c] = u[(NP - 1) * 3 + c]; r[1][c] = u[(NP - 1) * 3 + c]; }
+#pragma unroll
+      for (int i = NP - 2; i >= 0; --i)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const double u = row[i * 3 + c];
-          t[0][c] = fma(u, L0[0][i], t[0][c]);
-          t[1][c] = fma(u, L0[1][i], t[1][c]);
+          r[0][c] = fma(r[0][c], xi[0][0], u[i * 3 + c]);
+          r[1][c] = fma(r[1][c], xi[1][0], u[i * 3 + c]);
         }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        s[0][c] = fma(t[0][c], L1[0][j], s[0][c]);
-        s[1][c] = fma(t[1][c], L1[1][j], s[1][c]);
+        s[0][c] = fma(s[0][c], xi[0][1], r[0][c]);
+        s[1][c] = fma(s[1][c], xi[1][1], r[1][c]);
       }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      o[0][c] = fma(s[0][c], lz[0], o[0][c]);
-      o[1][c] = fma(s[1][c], lz[1], o[1][c]);
+      o[0][c] = fma(o[0][c], xi[0][2], s[0][c]);
+      o[1][c] = fma(o[1][c], xi[1][2], s[1][c]);
     }
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) { out[0][c] = o[0][c]; out[1][c] = o[1][c]; }
 }
 
-// one particle through the general path (non-affine element, failed closed form, reference-order arithmetic): field at the
-// particle, push; returns the pushed state.  Out of line: keeps the registers of the hot path.
-struct PushRes { double x0, x1, x2, v0, v1, v2; };
+// values at the Gauss points -> monomial coefficients, one element per CTA: three sweeps (xi, eta, zeta) of the inverse
+// Vandermonde matrix cst.n2m over the tile
+template <int NP>
+__global__ void __launch_bounds__(128) k_nodal_to_mono(const double* __restrict__ E, double* __restrict__ A, int nElems) {
+  constexpr int ND = NP * NP * NP;
+  __shared__ double t0[ND * 3], t1[ND * 3];
+  for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < ND * 3; t += blockDim.x) t0[t] = E[(size_t)e * ND * 3 + t];
+    __syncthreads();
+    for (int t = threadIdx.x; t < ND * 3; t += blockDim.x) {   // xi direction
+      const int c = t % 3, n = t / 3, p = n % NP, kj = n / NP;
+      double a = 0.;
+#pragma unroll
+      for (int i = 0; i < NP; ++i) a = fma(cst.n2m[p][i], t0[(kj * NP + i) * 3 + c], a);
+      t1[t] = a;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ND * 3; t += blockDim.x) {   // eta direction
+      const int c = t % 3, n = t / 3, i = n % NP, p = (n / NP) % NP, k = n / (NP * NP);
+      double a = 0.;
+#pragma unroll
+      for (int j = 0; j < NP; ++j) a = fma(cst.n2m[p][j], t1[((k * NP + j) * NP + i) * 3 + c], a);
+      t0[t] = a;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < ND * 3; t += blockDim.x) {   // zeta direction
+      const int c = t % 3, n = t / 3, ji = n % (NP * NP), p = n / (NP * NP);
+      double a = 0.;
+#pragma unroll
+      for (int k = 0; k < NP; ++k) a = fma(cst.n2m[p][k], t0[(k * NP * NP + ji) * 3 + c], a);
+      A[(size_t)e * ND * 3 + t] = a;
+    }
+  }
+}
+
+// One particle through the general path — non-affine or non-planar element, closed form far outside the element, position within
+// tol of a side plane, B != 0, reference-order arithmetic: reference position (Newton), field, push, ParticleInsideQuad3D of the
+// own element.  Out of line and self-contained, so that the hot path of k_bin_push holds no state across a call.  left != 0:
+// the particle is not in its element any more (far list: exact walk).
+struct ColdRes { double x0, x1, x2, v0, v1, v2; int left; };
 template <int NP, bool FAST>
-__device__ __noinline__ PushRes push_general(double x0, double x1, double x2, double v0, double v1, double v2, int spec, int isNewIn,
-                                             const double* __restrict__ sE, const GeoElem* __restrict__ ge, const AffElem* __restrict__ af,
-                                             const double* __restrict__ Eg, const double* __restrict__ xgp, double dt) {
+__device__ __noinline__ ColdRes cold_particle(double x0, double x1, double x2, double v0, double v1, double v2, int meta,
+                                              const double* __restrict__ sE, const GeoElem* __restrict__ ge, const AffElem* __restrict__ af,
+                                              const PlaneElem* __restrict__ pl, const TriaElem* __restrict__ te, const double* __restrict__ Eg,
+                                              const double* __restrict__ xgp, double dt) {
   double x[3] = {x0, x1, x2}, v[3] = {v0, v1, v2};
-  bool isNew = isNewIn != 0;
+  const int spec = meta & META_SPEC_MASK;
+  bool isNew = (meta & META_ISNEW) != 0;
   double F[6] = {0., 0., 0., 0., 0., 0.};
   const double q = cst.ChargeIC[spec];
   if (cst.DoInterpolation && fabs(q) > 0.0) {  // isInterpolateParticle
@@ -448,12 +550,12 @@ __device__ __noinline__ PushRes push_general(double x0, double x1, double x2, do
     else suc = (position_in_ref_elem(ge, x, xi, false, true) & 1) != 0;
     double f3[3];
     if (!suc && cst.DepositionType == PGPU_DEPO_CVWM) field_inverse_distance<NP>(x, Eg, xgp, f3);
-    else if (FAST) {
+    else if (FAST) {   // sE: monomial coefficients
       const double xi2[2][3] = {{xi[0], xi[1], xi[2]}, {xi[0], xi[1], xi[2]}};
       double o2[2][3];
-      evaluate_field_fast2<NP>(xi2, sE, o2);
+      evaluate_field_mono2<NP>(xi2, sE, o2);
       f3[0] = o2[0][0]; f3[1] = o2[0][1]; f3[2] = o2[0][2];
-    } else evaluate_field<NP>(xi, sE, f3);
+    } else evaluate_field<NP>(xi, sE, f3);   // sE: values at the Gauss points
 #pragma unroll
     for (int c = 0; c < 6; ++c) F[c] = cst.externalField[c];
     F[0] = F[0] + f3[0]; F[1] = F[1] + f3[1]; F[2] = F[2] + f3[2];
@@ -461,31 +563,97 @@ __device__ __noinline__ PushRes push_general(double x0, double x1, double x2, do
   }
   if (FAST) push_particle_fast(x, v, F, spec, isNew, dt);
   else push_particle(x, v, F, spec, isNew, dt);
-  PushRes r;
+  uint32_t mask;
+  const bool in = FAST ? inside_fast<true>(pl, te, x, mask) : inside_quad3d_mask<true>(te, x, mask);
+  ColdRes r;
   r.x0 = x[0]; r.x1 = x[1]; r.x2 = x[2]; r.v0 = v[0]; r.v1 = v[1]; r.v2 = v[2];
+  r.left = in ? 0 : 1;
   return r;
 }
 
-// inside test of the own element for the general path: 0 = inside, 1 = left (far list)
-template <bool FAST>
-__device__ __noinline__ int inside_general(const PlaneElem* __restrict__ pl, const TriaElem* __restrict__ te, double x0, double x1, double x2) {
-  const double x[3] = {x0, x1, x2};
-  uint32_t mask;
-  const bool in = FAST ? inside_fast<true>(pl, te, x, mask) : inside_quad3d_mask<true>(te, x, mask);
-  return in ? 0 : 1;
+// hot-path push with B = 0 (both time discretisations), fused multiply-adds; same formulas as push_particle_fast (fastmath.cuh)
+__device__ __forceinline__ void push_inline_b0(double x[3], double v[3], const double E3[3], int spec, bool isNew, bool boris, double dt) {
+  const double q = cst.ChargeIC[spec], mass = cst.MassIC[spec];
+  const bool isPush = fabs(q) > 0.0;
+  if (boris) {
+    if (isPush && cst.DoInterpolation) {
+      if (isNew) {
+        const double h = -0.5 * dt * (q / mass);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[d] = fma(E3[d], h, v[d]);
+      }
+      const double c_1 = (q * dt) / (mass * 2.);
+      const double c2_inv = cst.c2_inv;
+      const double gamma = rsqrt(fma(-fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2])), c2_inv, 1.0));
+      double vn[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) vn[d] = fma(2. * c_1, E3[d], v[d] * gamma);
+      const double s = rsqrt(fma(fma(vn[0], vn[0], fma(vn[1], vn[1], vn[2] * vn[2])), c2_inv, 1.0));
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[d] = vn[d] * s;
+    }
+  } else {   // Leapfrog (timedisc_TimeStepPoisson.f90:124-181), operation order of push_particle
+    double Pt[3] = {0., 0., 0.};
+    if (cst.DoInterpolation && isPush) {
+      const double qmt = q / mass;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) Pt[d] = E3[d] * qmt;
+    }
+    if (isPush) {
+      if (isNew) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) v[d] = v[d] - (Pt[d] * dt) * 0.5;
+      }
+#pragma unroll
+      for (int d = 0; d < 3; ++d) v[d] = v[d] + Pt[d] * dt;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) x[d] = fma(v[d], dt, x[d]);
 }
 
 constexpr int CAT_STAY = 0, CAT_FAR = 7, CAT_NONE = 8;
 
+// ranges of element e by lanes 0..7 of one warp: loads, padded prefix by shuffles, result into shared memory
+struct RangeRegs { int64_t start; int cnt; };
+__device__ __forceinline__ RangeRegs range_load(const BinView& bv, int e, int cur, int lane) {
+  RangeRegs r;
+  r.start = 0;
+  r.cnt = 0;
+  if (lane < BIN_NRANGE) {
+    if (lane == 0) { r.start = bv.base[e]; r.cnt = bv.nMain[e]; }
+    else if (lane < 7) { r.start = bin_inbox_base(bv, e, cur, lane - 1); r.cnt = bv.nIn[((size_t)cur * bv.nElems + e) * 8 + (lane - 1)]; }
+    else { const int64_t* po = cur ? bv.poolOff[1] : bv.poolOff[0]; r.start = po[e]; r.cnt = (int)(po[e + 1] - r.start); }
+  }
+  return r;
+}
+__device__ __forceinline__ void range_store(ElemRanges& R, const RangeRegs& r, int lane) {   // whole warp calls
+  const int padded = (r.cnt + 1) & ~1;
+  int incl = padded;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane < BIN_NRANGE) {
+    R.start[lane] = r.start;
+    R.cnt[lane] = r.cnt;
+    R.pre[lane] = incl - padded;
+    if (lane == BIN_NRANGE - 1) R.pre[BIN_NRANGE] = incl;
+  }
+}
+
 template <int NP, bool FAST>
 __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, PartBuf pool, BinView bv, int cur, FarBuf far,
-                                                              const PushElem* __restrict__ pushElem, const double* __restrict__ E,
+                                                              const int64_t* __restrict__ farBase, int32_t* __restrict__ nFarE,
+                                                              const PushElem* __restrict__ pushElem, const double* __restrict__ Et /*tile source: monomial
+                                                              coefficients (FAST) or Gauss-point values*/, const double* __restrict__ E /*Gauss-point values*/,
                                                               const GeoElem* __restrict__ geo, const TriaElem* __restrict__ tria,
                                                               const PlaneElem* __restrict__ planes, const AffElem* __restrict__ aff,
                                                               const double* __restrict__ Elem_xGP, int offsetElem, double dt,
-                                                              int* __restrict__ counters /*[2] far records, [4] side movers, [5] main full, [6] inbox full*/) {
+                                                              int* __restrict__ counters /*[4] side movers, [5] main full, [6] inbox full*/) {
   constexpr int ND = NP * NP * NP;
-  // field tile: double buffered and prefetched with a bulk copy when it is small and a multiple of 16 bytes (N = 1, 3, 5);
+  // field tile: double buffered and prefetched with a bulk copy when it is small and a multiple of 16 bytes (N = 1, 3);
   // otherwise one buffer, staged with plain loads after the element's barrier
   constexpr uint32_t E_BYTES = ND * 24;
   constexpr bool TMA_E = (E_BYTES % 16 == 0) && (E_BYTES <= 4096);
@@ -493,10 +661,14 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
   __shared__ __align__(16) PushElem sPE[2];
   __shared__ __align__(16) double sEb[EBUF][ND * 3];
   __shared__ __align__(8) uint64_t mbar[2];
-  __shared__ __align__(16) double sP[2][6][BIN_CHUNK];   // x, v of the current / next pair of every thread
-  __shared__ ElemRanges R;
+  __shared__ __align__(16) double sP[2][6][BIN_CHUNK];   // x, v of the current / next pair of every thread (cp.async)
+  __shared__ uint32_t sM[2][BIN_NT][2];                  // the aligned 32-bit words that hold the pair's two meta bytes
+  __shared__ ElemRanges R2[2];
   __shared__ int sCnt[2][BIN_NT / 32][8];
   __shared__ int sRun[2][8];
+  __shared__ int64_t sNbBase[6];                         // first slot of the inbox this element fills at the neighbour behind side s
+  __shared__ int sNbCap[6];
+  __shared__ int sDiverted;                              // particles of this element sent to the far list by a full region
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int next = cur ^ 1;
   const int nElems = bv.nElems;
@@ -511,181 +683,213 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
   auto prefetch_elem = [&](int e, int b) {   // one thread: records of element e -> buffer b
     mbar_expect_tx(&mbar[b], (uint32_t)sizeof(PushElem) + (TMA_E ? E_BYTES : 0u));
     bulk_g2s(&sPE[b], pushElem + e, (uint32_t)sizeof(PushElem), &mbar[b]);
-    if (TMA_E) bulk_g2s(&sEb[TMA_E ? b : 0][0], E + (size_t)e * ND * 3, E_BYTES, &mbar[b]);
+    if (TMA_E) bulk_g2s(&sEb[TMA_E ? b : 0][0], Et + (size_t)e * ND * 3, E_BYTES, &mbar[b]);
   };
-  if (tid == 0 && (int)blockIdx.x < nElems) prefetch_elem(blockIdx.x, 0);
-  int it = 0;
-  for (int e = blockIdx.x; e < nElems; e += gridDim.x, ++it) {
-    const int b = it & 1;
-    const int gElem = offsetElem + e + 1;
-    // the barrier that ended the previous element also freed buffer b^1: prefetch the records of the next element into it
-    if (tid == 0 && e + (int)gridDim.x < nElems) prefetch_elem(e + gridDim.x, b ^ 1);
-    load_ranges(R, bv, e, cur, tid);
-    if (tid < 8) sRun[0][tid] = 0;
-    __syncthreads();
-    if (tid == 0) prefix_ranges(R);
-    mbar_wait(&mbar[b], (uint32_t)((it >> 1) & 1));
-    if (!TMA_E) {
-      for (int t = tid; t < ND * 3; t += BIN_NT) sEb[0][t] = __ldg(E + (size_t)e * ND * 3 + t);
-    }
-    __syncthreads();
-    const PushElem& pe = sPE[b];
-    const double* sE = sEb[TMA_E ? b : 0];
-    const int total = R.pre[BIN_NRANGE];
-    const bool fastElem = FAST && pe.affine != 0u;
-    const bool planarElem = FAST && pe.planar != 0u;
-    const int nChunks = (total + BIN_CHUNK - 1) / BIN_CHUNK;
-    const int64_t base_e = R.start[0];
-    const int capMain = bv.capMain[e];
-    // pair of this thread in chunk c: virtual indices c*BIN_CHUNK + 2*tid, +1.  slot < 0: no live particle
-    auto fetch = [&](int c, int stg, int& nLive, int64_t& slot, bool& fromPool, uint32_t& meta2) {
-      const int v = c * BIN_CHUNK + 2 * tid;
-      nLive = 0;
-      slot = -1;
-      fromPool = false;
-      meta2 = 0;
-      if (v < total) {
-        int r, left;
-        resolve(R, v, r, slot, left);
-        fromPool = r == 7;
+  // pair of this thread in chunk c of the element with ranges R: virtual indices c*BIN_CHUNK + 2*tid, +1.  Copies only: nothing
+  // here waits for memory.  Returns the slot of the first particle (-1: none), the number of live particles and the source.
+  auto fetch = [&](const ElemRanges& R, int c, int stg, int& nLive, int64_t& slot, bool& fromPool) {
+    const int v = c * BIN_CHUNK + 2 * tid;
+    nLive = 0;
+    slot = -1;
+    fromPool = false;
+    if (v < R.pre[BIN_NRANGE]) {
+      int r, left;
+      resolve(R, v, r, slot, left);
+      fromPool = r == 7;
+      nLive = left >= 2 ? 2 : (left > 0 ? 1 : 0);
+      if (nLive > 0) {
         const double* sf = fromPool ? pool.f : BF;
         const int64_t sst = fromPool ? pool.stride : BS;
         const uint8_t* sm = fromPool ? pool.meta : bins.meta;
-        nLive = left >= 2 ? 2 : (left > 0 ? 1 : 0);
-        if (nLive > 0) {
-          if ((slot & 1) == 0) {
+        if ((slot & 1) == 0) {
 #pragma unroll
-            for (int a = 0; a < 6; ++a) cp_async16(&sP[stg][a][2 * tid], sf + a * sst + slot);
-          } else {   // pool ranges start at any slot
+          for (int a = 0; a < 6; ++a) cp_async16(&sP[stg][a][2 * tid], sf + a * sst + slot);
+        } else {   // pool ranges start at any slot
 #pragma unroll
-            for (int a = 0; a < 6; ++a) {
-              cp_async8(&sP[stg][a][2 * tid], sf + a * sst + slot);
-              cp_async8(&sP[stg][a][2 * tid + 1], sf + a * sst + slot + 1);
-            }
+          for (int a = 0; a < 6; ++a) {
+            cp_async8(&sP[stg][a][2 * tid], sf + a * sst + slot);
+            cp_async8(&sP[stg][a][2 * tid + 1], sf + a * sst + slot + 1);
           }
-          meta2 = (uint32_t)sm[slot] | (nLive > 1 ? ((uint32_t)sm[slot + 1] << 8) : ((uint32_t)sm[slot] << 8));
         }
-      }
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&sM[stg][tid][0])), "l"(sm + (slot & ~(int64_t)3)) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&sM[stg][tid][1])), "l"(sm + ((slot + 1) & ~(int64_t)3)) : "memory");
+      } else slot = -1;
+    }
+  };
+  int nLive = 0, nLiveNext = 0;
+  int64_t slotCur = -1, slotNext = -1;
+  bool poolCur = false, poolNext = false;
+  int stg = 0;
+  if ((int)blockIdx.x < nElems) {
+    if (tid == 0) prefetch_elem(blockIdx.x, 0);
+    if (warp == 0) range_store(R2[0], range_load(bv, blockIdx.x, cur, lane), lane);
+    __syncthreads();
+    fetch(R2[0], 0, 0, nLive, slotCur, poolCur);
+  }
+  cp_async_commit();
+  int it = 0;
+  for (int e = blockIdx.x; e < nElems; e += gridDim.x, ++it) {
+    // invariant: ranges of e in R2[it & 1]; its chunk 0 in flight in stage stg (latest cp.async group); records of e in flight in
+    // buffer it & 1; every thread has passed the barrier that ended the previous element
+    const int b = it & 1;
+    const int gElem = offsetElem + e + 1;
+    const int e2 = e + gridDim.x;
+    const bool haveNext = e2 < nElems;
+    const ElemRanges& R = R2[b];
+    if (tid == 0 && haveNext) prefetch_elem(e2, b ^ 1);
+    RangeRegs rNext;
+    rNext.start = 0; rNext.cnt = 0;
+    if (warp == 0 && haveNext) rNext = range_load(bv, e2, cur, lane);   // consumed after the work of chunk 0
+    if (tid < 8) sRun[0][tid] = 0;
+    if (tid == 8) sDiverted = 0;
+    const int64_t farLo = farBase[e], farHi = farBase[e + 1];
+    mbar_wait(&mbar[b], (uint32_t)((it >> 1) & 1));
+    if (!TMA_E) {
+      for (int t = tid; t < ND * 3; t += BIN_NT) sEb[0][t] = __ldg(Et + (size_t)e * ND * 3 + t);
+      __syncthreads();
+    }
+    const PushElem& pe = sPE[b];
+    const double* sE = sEb[TMA_E ? b : 0];
+    int64_t nbBase = 0;
+    int nbCap = 0;
+    if (warp == 0 && lane >= 8 && lane < 14) {   // inboxes this element fills: consumed after the work of chunk 0
+      const int nb = pe.nbLocal[lane - 8];
+      if (nb >= 0) { nbBase = bin_inbox_base(bv, nb, next, pe.nbBox[lane - 8]); nbCap = bv.capIn[nb]; }
+    }
+    const int total = R.pre[BIN_NRANGE];
+    const bool boris = cst.TimeDiscMethod == PGPU_TIMEDISC_BORIS_LEAPFROG;
+    const bool noB = cst.externalField[3] == 0. && cst.externalField[4] == 0. && cst.externalField[5] == 0.;
+    const bool hotElem = FAST && pe.affine != 0u && pe.planar != 0u && noB;
+    const int nChunks = (total + BIN_CHUNK - 1) / BIN_CHUNK;
+    const int64_t base_e = R.start[0];
+    const int capMain = bv.capMain[e];
+    auto publish_next = [&]() {   // warp 0: ranges of the next element, inboxes of this one
+      if (haveNext) range_store(R2[b ^ 1], rNext, lane);
+      if (lane >= 8 && lane < 14) { sNbBase[lane - 8] = nbBase; sNbCap[lane - 8] = nbCap; }
     };
-    int nLive = 0, nLiveNext = 0;
-    int64_t slotCur = -1, slotNext = -1;
-    bool poolCur = false, poolNext = false;
-    uint32_t meta2 = 0, meta2Next = 0;
-    if (nChunks > 0) fetch(0, 0, nLive, slotCur, poolCur, meta2);
-    cp_async_commit();
+    if (nChunks <= 1) {   // too short to hide the loads behind chunk 0: publish now
+      if (warp == 0) publish_next();
+      __syncthreads();
+      if (nChunks == 0) {   // empty element: only the chunk 0 of the next element has to be put in flight
+        if (haveNext) fetch(R2[b ^ 1], 0, stg, nLive, slotCur, poolCur);
+        cp_async_commit();
+      }
+    }
     for (int c = 0; c < nChunks; ++c) {
-      const int stg = c & 1, cb = c & 1;
+      const int cb = c & 1;
       nLiveNext = 0;
-      if (c + 1 < nChunks) fetch(c + 1, stg ^ 1, nLiveNext, slotNext, poolNext, meta2Next);
+      slotNext = -1;
+      poolNext = false;
+      if (c + 1 < nChunks) fetch(R, c + 1, stg ^ 1, nLiveNext, slotNext, poolNext);
+      else if (haveNext) fetch(R2[b ^ 1], 0, stg ^ 1, nLiveNext, slotNext, poolNext);   // chunk 0 of the next element
       cp_async_commit();
       cp_async_wait_prev();
       // ---- per-particle work ----------------------------------------------------------------------------------------------
+      // hot path (no calls): affine + planar element, closed-form reference position, B = 0, position clear of every side plane;
+      // everything else is flagged and goes through cold_particle afterwards
       const int pq = (nLive == 1) ? 0 : 1;   // the idle half of a pair computes on a copy of the live one (finite inputs, discarded)
-      const int metaQ[2] = {(int)(meta2 & 0xffu), (int)((meta2 >> 8) & 0xffu)};
+      const double* sPs = &sP[stg][0][2 * tid];   // [a * BIN_CHUNK + q]
       double xn[2][3], vn[2][3];
+      int metaQ[2] = {0, 0};
       int cat[2] = {CAT_NONE, CAT_NONE};
+      bool cold[2] = {false, false};
       if (nLive > 0) {
-        bool simple = fastElem;
-        double f2[2][3];
-        if (fastElem) {
-          double xi[2][3];
+        metaQ[0] = (int)((sM[stg][tid][0] >> (8 * (int)(slotCur & 3))) & 0xffu);
+        metaQ[1] = pq ? (int)((sM[stg][tid][1] >> (8 * (int)((slotCur + 1) & 3))) & 0xffu) : metaQ[0];
+        if (hotElem) {
+          double f2[2][3];
+          {
+            double xi[2][3];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int qs = q ? pq : 0;
+              const double r0 = sPs[qs] - pe.x0[0], r1 = sPs[BIN_CHUNK + qs] - pe.x0[1], r2 = sPs[2 * BIN_CHUNK + qs] - pe.x0[2];
+#pragma unroll
+              for (int d = 0; d < 3; ++d) xi[q][d] = fma(pe.A[d][0], r0, fma(pe.A[d][1], r1, pe.A[d][2] * r2)) - 1.0;
+              cold[q] = !(fabs(xi[q][0]) <= 1.5 && fabs(xi[q][1]) <= 1.5 && fabs(xi[q][2]) <= 1.5);
+              if (cold[q]) { xi[q][0] = 0.; xi[q][1] = 0.; xi[q][2] = 0.; }
+            }
+            evaluate_field_mono2<NP>(xi, sE, f2);
+          }
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int qs = q ? pq : 0;
-            const double r0 = sP[stg][0][2 * tid + qs] - pe.x0[0], r1 = sP[stg][1][2 * tid + qs] - pe.x0[1], r2 = sP[stg][2][2 * tid + qs] - pe.x0[2];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) xi[q][d] = fma(pe.A[d][0], r0, fma(pe.A[d][1], r1, pe.A[d][2] * r2)) - 1.0;
-            simple = simple && fabs(xi[q][0]) <= 1.5 && fabs(xi[q][1]) <= 1.5 && fabs(xi[q][2]) <= 1.5;
+            for (int d = 0; d < 3; ++d) { xn[q][d] = sPs[d * BIN_CHUNK + qs]; vn[q][d] = sPs[(3 + d) * BIN_CHUNK + qs]; }
+            const int spec = metaQ[q] & META_SPEC_MASK;
+            double E3[3] = {0., 0., 0.};
+            if (cst.DoInterpolation && fabs(cst.ChargeIC[spec]) > 0.0) {
+#pragma unroll
+              for (int d = 0; d < 3; ++d) E3[d] = cst.externalField[d] + f2[q][d];
+            }
+            push_inline_b0(xn[q], vn[q], E3, spec, (metaQ[q] & META_ISNEW) != 0, boris, dt);
           }
-          if (simple) evaluate_field_fast2<NP>(xi, sE, f2);
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int qs = q ? pq : 0;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) { xn[q][d] = sP[stg][d][2 * tid + qs]; vn[q][d] = sP[stg][3 + d][2 * tid + qs]; }
-        }
-        if (simple) {
+          // ---- own-element inside test (first iteration of SingleParticleTriaTracking3D, particle_triatracking.f90:203-218) and
+          //      the crossing of exactly one side plane into a face neighbour -----------------------------------------------------------
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
-            const int spec = metaQ[q] & META_SPEC_MASK;
-            bool isNew = (metaQ[q] & META_ISNEW) != 0;
-            double F[6] = {0., 0., 0., 0., 0., 0.};
-            const double qc = cst.ChargeIC[spec];
-            if (cst.DoInterpolation && fabs(qc) > 0.0) {
+            if (q >= nLive) { cat[q] = CAT_NONE; cold[q] = false; continue; }
+            if (cold[q]) continue;
+            double dx[6];
+            uint32_t neg = 0;
+            bool ambiguous = false;
+            const double tol = pe.tol;
 #pragma unroll
-              for (int d = 0; d < 6; ++d) F[d] = cst.externalField[d];
-              F[0] = F[0] + f2[q][0]; F[1] = F[1] + f2[q][1]; F[2] = F[2] + f2[q][2];
+            for (int s = 0; s < 6; ++s) {
+              dx[s] = fma(pe.pl[s][0], xn[q][0], fma(pe.pl[s][1], xn[q][1], fma(pe.pl[s][2], xn[q][2], -pe.pl[s][3])));
+              ambiguous |= fabs(dx[s]) <= tol;
+              neg |= (dx[s] < 0.) ? (1u << s) : 0u;
             }
-            push_particle_fast(xn[q], vn[q], F, spec, isNew, dt);
+            if (ambiguous) { cold[q] = true; continue; }   // within tol of a side plane: the determinants decide (ParticleInsideQuad3D)
+            if (neg == 0u) { cat[q] = CAT_STAY; continue; }
+            cat[q] = CAT_FAR;
+            if (__popc(neg) != 1) continue;
+            const int s = __ffs(neg) - 1;
+            if (pe.nbLocal[s] < 0) continue;
+            // flight LastPartPos -> x crosses side s at lp + alpha (x - lp); every decision with a margin of tol, otherwise the
+            // determinant tests of the exact walk decide
+            const double lp0 = sPs[q], lp1 = sPs[BIN_CHUNK + q], lp2 = sPs[2 * BIN_CHUNK + q];
+            const double dl = fma(pe.pl[s][0], lp0, fma(pe.pl[s][1], lp1, fma(pe.pl[s][2], lp2, -pe.pl[s][3])));
+            if (!(dl > tol)) continue;
+            const double alpha = dl / (dl - dx[s]);
+            bool ok = true;
+#pragma unroll
+            for (int o = 0; o < 6; ++o) {
+              const double ol = fma(pe.pl[o][0], lp0, fma(pe.pl[o][1], lp1, fma(pe.pl[o][2], lp2, -pe.pl[o][3])));
+              const double oc = fma(alpha, dx[o] - ol, ol);
+              if (o != s && !(oc > tol)) ok = false;
+            }
+            {
+              const double gl = fma(pe.dg[s][0], lp0, fma(pe.dg[s][1], lp1, fma(pe.dg[s][2], lp2, -pe.dg[s][3])));
+              const double gx = fma(pe.dg[s][0], xn[q][0], fma(pe.dg[s][1], xn[q][1], fma(pe.dg[s][2], xn[q][2], -pe.dg[s][3])));
+              const double gc = fma(alpha, gx - gl, gl);
+              if (!(fabs(gc) > tol)) ok = false;   // crossing point on the triangle diagonal
+            }
+            // clearly inside the neighbour: ParticleInsideQuad3D there succeeds, the walk ends (:215-218)
+            const double ntol = pe.nbtol[s];
+#pragma unroll
+            for (int o = 0; o < 6; ++o) {
+              const double dn = fma(pe.nbpl[s][o][0], xn[q][0], fma(pe.nbpl[s][o][1], xn[q][1], fma(pe.nbpl[s][o][2], xn[q][2], -pe.nbpl[s][o][3])));
+              if (!(dn > ntol)) ok = false;
+            }
+            if (ok) cat[q] = 1 + s;
           }
         } else {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const PushRes r = push_general<NP, FAST>(xn[q][0], xn[q][1], xn[q][2], vn[q][0], vn[q][1], vn[q][2], metaQ[q] & META_SPEC_MASK,
-                                                     (metaQ[q] & META_ISNEW) ? 1 : 0, sE, geo + (gElem - 1), FAST ? aff + (gElem - 1) : nullptr,
-                                                     E + (size_t)e * ND * 3, Elem_xGP + (size_t)(gElem - 1) * ND * 3, dt);
-            xn[q][0] = r.x0; xn[q][1] = r.x1; xn[q][2] = r.x2; vn[q][0] = r.v0; vn[q][1] = r.v1; vn[q][2] = r.v2;
-          }
+          cold[0] = true;
+          cold[1] = nLive > 1;
         }
-        // ---- own-element inside test (first iteration of SingleParticleTriaTracking3D, particle_triatracking.f90:203-218) and,
-        //      for planar convex elements, the crossing of exactly one side plane into a face neighbour ------------------------------
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          if (q >= nLive) { cat[q] = CAT_NONE; continue; }
-          if (!planarElem) {
-            cat[q] = inside_general<FAST>(FAST ? planes + (gElem - 1) : nullptr, tria + (gElem - 1), xn[q][0], xn[q][1], xn[q][2]) ? CAT_FAR : CAT_STAY;
-            continue;
-          }
-          double dx[6];
-          uint32_t neg = 0;
-          bool ambiguous = false;
-          const double tol = pe.tol;
-#pragma unroll
-          for (int s = 0; s < 6; ++s) {
-            dx[s] = fma(pe.pl[s][0], xn[q][0], fma(pe.pl[s][1], xn[q][1], fma(pe.pl[s][2], xn[q][2], -pe.pl[s][3])));
-            ambiguous |= fabs(dx[s]) <= tol;
-            neg |= (dx[s] < 0.) ? (1u << s) : 0u;
-          }
-          if (ambiguous) {   // within tol of a side plane: the determinants decide (ParticleInsideQuad3D), leavers take the exact walk
-            const uint32_t r = inside_exact_cold<true>(tria + (gElem - 1), xn[q][0], xn[q][1], xn[q][2]);
-            cat[q] = (r >> 31) ? CAT_STAY : CAT_FAR;
-            continue;
-          }
-          if (neg == 0u) { cat[q] = CAT_STAY; continue; }
-          cat[q] = CAT_FAR;
-          if (__popc(neg) != 1) continue;
-          const int s = __ffs(neg) - 1;
-          if (pe.nbLocal[s] < 0) continue;
-          // flight LastPartPos -> x crosses side s at lp + alpha (x - lp); every decision with a margin of tol, otherwise the
-          // determinant tests of the exact walk decide
-          const double lp0 = sP[stg][0][2 * tid + q], lp1 = sP[stg][1][2 * tid + q], lp2 = sP[stg][2][2 * tid + q];
-          const double dl = fma(pe.pl[s][0], lp0, fma(pe.pl[s][1], lp1, fma(pe.pl[s][2], lp2, -pe.pl[s][3])));
-          if (!(dl > tol)) continue;
-          const double alpha = dl / (dl - dx[s]);
-          bool ok = true;
-#pragma unroll
-          for (int o = 0; o < 6; ++o) {
-            const double ol = fma(pe.pl[o][0], lp0, fma(pe.pl[o][1], lp1, fma(pe.pl[o][2], lp2, -pe.pl[o][3])));
-            const double oc = fma(alpha, dx[o] - ol, ol);
-            if (o != s && !(oc > tol)) ok = false;
-          }
-          {
-            const double gl = fma(pe.dg[s][0], lp0, fma(pe.dg[s][1], lp1, fma(pe.dg[s][2], lp2, -pe.dg[s][3])));
-            const double gx = fma(pe.dg[s][0], xn[q][0], fma(pe.dg[s][1], xn[q][1], fma(pe.dg[s][2], xn[q][2], -pe.dg[s][3])));
-            const double gc = fma(alpha, gx - gl, gl);
-            if (!(fabs(gc) > tol)) ok = false;   // crossing point on the triangle diagonal
-          }
-          // clearly inside the neighbour: ParticleInsideQuad3D there succeeds, the walk ends (:215-218)
-          const double ntol = pe.nbtol[s];
-#pragma unroll
-          for (int o = 0; o < 6; ++o) {
-            const double dn = fma(pe.nbpl[s][o][0], xn[q][0], fma(pe.nbpl[s][o][1], xn[q][1], fma(pe.nbpl[s][o][2], xn[q][2], -pe.nbpl[s][o][3])));
-            if (!(dn > ntol)) ok = false;
-          }
-          if (ok) cat[q] = 1 + s;
+          if (!cold[q]) continue;
+          const ColdRes r = cold_particle<NP, FAST>(sPs[q], sPs[BIN_CHUNK + q], sPs[2 * BIN_CHUNK + q], sPs[3 * BIN_CHUNK + q], sPs[4 * BIN_CHUNK + q],
+                                                    sPs[5 * BIN_CHUNK + q], metaQ[q], sE, geo + (gElem - 1), FAST ? aff + (gElem - 1) : nullptr,
+                                                    FAST ? planes + (gElem - 1) : nullptr, tria + (gElem - 1), E + (size_t)e * ND * 3,
+                                                    Elem_xGP + (size_t)(gElem - 1) * ND * 3, dt);
+          xn[q][0] = r.x0; xn[q][1] = r.x1; xn[q][2] = r.x2; vn[q][0] = r.v0; vn[q][1] = r.v1; vn[q][2] = r.v2;
+          cat[q] = r.left ? CAT_FAR : CAT_STAY;
         }
       }
+      if (c == 0 && nChunks > 1 && warp == 0) publish_next();   // the loads issued at the element's start have long arrived
       // particle ids (tests) have to be read before the compaction below overwrites the slots of this chunk
       int64_t id[2] = {0, 0};
       if (bins.id && nLive > 0) {
@@ -695,20 +899,22 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
       }
       // ---- stable compaction: rank of every particle within its category in the order of the element's particles (virtual
       //      index 2 * tid + q), chunk by chunk: the order inside an element never changes except by departures and arrivals ----------
+      // eight 8-bit counters (one per category, <= 64 particles per warp and sweep) packed in a 64-bit word: one inclusive warp
+      // scan yields every particle's rank within its category and the warp's totals
       int rank[2] = {0, 0};
       {
-        int myCount = 0;
-        const unsigned lt = (1u << lane) - 1u;
+        const unsigned long long w0 = cat[0] < 8 ? (1ull << (8 * cat[0])) : 0ull, w1 = cat[1] < 8 ? (1ull << (8 * cat[1])) : 0ull;
+        unsigned long long incl = w0 + w1;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const unsigned bal0 = __ballot_sync(0xffffffffu, cat[0] == k);
-          const unsigned bal1 = __ballot_sync(0xffffffffu, cat[1] == k);
-          const int below = __popc(bal0 & lt) + __popc(bal1 & lt);
-          if (cat[0] == k) rank[0] = below;
-          if (cat[1] == k) rank[1] = below + (cat[0] == k ? 1 : 0);
-          if (lane == k) myCount = __popc(bal0) + __popc(bal1);
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
         }
-        if (lane < 8) sCnt[cb][warp][lane] = myCount;
+        const unsigned long long excl = incl - w0 - w1;
+        rank[0] = (int)((excl >> (8 * (cat[0] & 7))) & 0xffull);
+        rank[1] = (int)((excl >> (8 * (cat[1] & 7))) & 0xffull) + (cat[0] == cat[1] ? 1 : 0);
+        const unsigned long long tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane < 8) sCnt[cb][warp][lane] = (int)((tot >> (8 * lane)) & 0xffull);
       }
       __syncthreads();
       int off[2] = {0, 0};
@@ -728,50 +934,37 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
         sRun[cb ^ 1][tid] = t;
       }
       // ---- delivery ----------------------------------------------------------------------------------------------------------------
-      const uint32_t srcTag = (uint32_t)((poolCur ? BS : 0) + slotCur);   // origin: slot in the bins arrays, pool slots behind them
+      // stayers -> main, side movers -> the neighbour's inbox, far records -> this element's far region from the bottom (slot =
+      // rank among the element's far particles: no atomics); a particle whose region is full -> far region from the top
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        bool toFar = cat[q] == CAT_FAR;
-        int fullKind = 0;
-        const uint8_t nmeta = (uint8_t)(metaQ[q] & META_SPEC_MASK);   // IsNewPart is consumed by the push
-        int64_t slot = -1;
+        if (cat[q] >= 8) continue;
+        int64_t dst = -1, fdst = -1;
         if (cat[q] == CAT_STAY) {
-          if (off[q] < capMain) slot = base_e + off[q];
-          else { toFar = true; fullKind = 5; }   // main full: through the far list back into this element
-        } else if (cat[q] >= 1 && cat[q] <= 6) {
-          const int s = cat[q] - 1;
-          const int nb = pe.nbLocal[s];
-          if (off[q] < bv.capIn[nb]) slot = bin_inbox_base(bv, nb, next, pe.nbBox[s]) + off[q];
-          else { toFar = true; fullKind = 6; }   // inbox full
-        }
-        if (slot >= 0) {
+          if (off[q] < capMain) dst = base_e + off[q];
+          else { fdst = farHi - 1 - atomicAdd(&sDiverted, 1); atomicAdd(&counters[5], 1); }   // main full: through the far list back in
+        } else if (cat[q] <= 6) {
+          if (off[q] < sNbCap[cat[q] - 1]) dst = sNbBase[cat[q] - 1] + off[q];
+          else { fdst = farHi - 1 - atomicAdd(&sDiverted, 1); atomicAdd(&counters[6], 1); }   // inbox full
+        } else fdst = farLo + off[q];
+        const uint8_t nmeta = (uint8_t)(metaQ[q] & META_SPEC_MASK);   // IsNewPart is consumed by the push
+        if (dst >= 0) {
 #pragma unroll
-          for (int d = 0; d < 3; ++d) { BF[d * BS + slot] = xn[q][d]; BF[(3 + d) * BS + slot] = vn[q][d]; }
-          bins.meta[slot] = nmeta;
-          if (bins.id) bins.id[slot] = id[q];
-        }
-        if (fullKind) atomicAdd(&counters[fullKind], 1);
-        const unsigned fm = __ballot_sync(0xffffffffu, toFar);
-        if (fm) {
-          int slot0 = 0;
-          const int leader = __ffs(fm) - 1;
-          if (lane == leader) slot0 = atomicAdd(&counters[2], __popc(fm));
-          slot0 = __shfl_sync(0xffffffffu, slot0, leader);
-          if (toFar) {
-            const int f = slot0 + __popc(fm & ((1u << lane) - 1u));
+          for (int d = 0; d < 3; ++d) { BF[d * BS + dst] = xn[q][d]; BF[(3 + d) * BS + dst] = vn[q][d]; }
+          bins.meta[dst] = nmeta;
+          if (bins.id) bins.id[dst] = id[q];
+        } else {
 #pragma unroll
-            for (int d = 0; d < 3; ++d) { far.x[d][f] = xn[q][d]; far.lp[d][f] = sP[stg][d][2 * tid + q]; far.v[d][f] = vn[q][d]; }
-            far.elem[f] = gElem;
-            far.meta[f] = nmeta;
-            if (far.id) far.id[f] = id[q];
-            far.src[f] = srcTag + (uint32_t)q;
-          }
+          for (int d = 0; d < 3; ++d) { far.x[d][fdst] = xn[q][d]; far.lp[d][fdst] = sPs[d * BIN_CHUNK + q]; far.v[d][fdst] = vn[q][d]; }
+          far.elem[fdst] = gElem;
+          far.meta[fdst] = nmeta;
+          if (far.id) far.id[fdst] = id[q];
         }
       }
       nLive = nLiveNext;
       slotCur = slotNext;
       poolCur = poolNext;
-      meta2 = meta2Next;
+      stg ^= 1;
     }
     __syncthreads();
     // populations after the step: this element's main, and the inboxes this element fills at its face neighbours
@@ -780,10 +973,13 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
       if (tid == 0) {
         const int n = sRun[fb][0];
         bv.nMain[e] = n < capMain ? n : capMain;
+      } else if (tid == 7) {
+        nFarE[2 * e] = sRun[fb][7];
+        nFarE[2 * e + 1] = sDiverted;
       } else if (tid >= 1 && tid <= 6) {
         const int s = tid - 1, nb = pe.nbLocal[s];
         if (nb >= 0) {
-          const int n = sRun[fb][tid], ci = bv.capIn[nb];
+          const int n = sRun[fb][tid], ci = sNbCap[s];
           const int m = n < ci ? n : ci;
           bv.nIn[((size_t)next * nElems + nb) * 8 + pe.nbBox[s]] = m;
           if (m > 0) atomicAdd(&counters[4], m);
@@ -798,12 +994,12 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
 // One thread per record, persistent warps with per-lane refill (as k_track_leavers).  key: local element, nElems + rank
 // (emigrant) or nElems + nRanks (removed).
 template <bool FAST>
-__global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, int nFar, const TriaElem* __restrict__ tria,
+__global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, const uint32_t* __restrict__ idx, int nFar, const TriaElem* __restrict__ tria,
                                                              const PlaneElem* __restrict__ planes, const int32_t* __restrict__ elemRank,
                                                              uint32_t* __restrict__ keys, int nElems, int offsetElem, int* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
   bool active = false;
-  int p = 0, ElemID = 0, guard = 0;
+  int p = 0, dense = 0, ElemID = 0, guard = 0;
   uint32_t mask = 0;
   double x[3] = {0., 0., 0.}, lp[3] = {0., 0., 0.};
   HopHist h;
@@ -819,7 +1015,8 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, int nFa
         const int mine = first + __popc(need & ((1u << lane) - 1u));
         if (!active && mine < nFar) {
           active = true;
-          p = mine;
+          dense = mine;
+          p = (int)idx[mine];
           x[0] = far.x[0][p]; x[1] = far.x[1][p]; x[2] = far.x[2][p];
           lp[0] = far.lp[0][p]; lp[1] = far.lp[1][p]; lp[2] = far.lp[2][p];
           ElemID = far.elem[p];
@@ -859,7 +1056,7 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, int nFa
         }
         far.x[0][p] = x[0]; far.x[1][p] = x[1]; far.x[2][p] = x[2];
         far.elem[p] = newElem;
-        keys[p] = key;
+        keys[dense] = key;
         active = false;
       }
     }
@@ -867,20 +1064,20 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, int nFa
 }
 
 // sorted far list -> pool: pool slot i takes record perm[i] (i < number of records that stay on this rank)
-__global__ void k_far_to_pool(FarBuf far, const uint32_t* __restrict__ perm, int64_t n, PartBuf pool) {
+__global__ void k_far_to_pool(FarBuf far, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ perm, int64_t n, PartBuf pool) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t s = perm[i];
+  const uint32_t s = idx[perm[i]];
 #pragma unroll
   for (int d = 0; d < 3; ++d) { pool.f[d * pool.stride + i] = far.x[d][s]; pool.f[(3 + d) * pool.stride + i] = far.v[d][s]; }
   pool.meta[i] = far.meta[s];
   if (pool.id) pool.id[i] = far.id[s];
 }
 
-// origin tags of received particles: behind every local slot, in arrival order
-__global__ void k_far_tag_immigrants(uint32_t* __restrict__ src, int64_t n0, int64_t n, uint32_t first) {
+// received particles lie behind every element's far region: their index entries follow the local ones in arrival order
+__global__ void k_far_index_immigrants(uint32_t* __restrict__ idx, int64_t n0, int64_t n, uint32_t firstSlot) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) src[n0 + i] = first + (uint32_t)i;
+  if (i < n) idx[n0 + i] = firstSlot + (uint32_t)i;
 }
 
 // out[i] = in[perm[i]] for 32-bit keys (second, stable pass of the far sort works on the keys in origin order)

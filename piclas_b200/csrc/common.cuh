@@ -75,6 +75,8 @@ struct ConstTables {
   int32_t sfCase[27][3];
   double r_sf, r2_sf, r2_sf_inv, w_sf, dimFactorSF;
   double FIBGMdeltas[3], xyzminglob[3];
+  // restructured arithmetic: nodal (Gauss) values -> monomial coefficients, a_p = sum_i n2m[p][i] u_i (inverse Vandermonde)
+  double n2m[PGPU_MAX_N + 1][PGPU_MAX_N + 1];
   int32_t FIBGMmin[3], FIBGMmax[3];
 };
 

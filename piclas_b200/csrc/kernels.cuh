@@ -376,26 +376,40 @@ __device__ __forceinline__ void load_plane4(const double* __restrict__ q, double
 template <bool G>
 __device__ __forceinline__ bool exit_side_planar(const PlaneElem* __restrict__ pc, const double x[3], const double lp[3], uint32_t mask,
                                                  int& side, int& tri) {
+  // The pushed position may lie beyond several side planes (flight through an edge or corner region): the flight leaves through the
+  // side whose plane it reaches first.  Every decision keeps a margin of PlaneElem::tol (start point clearly inside each crossed
+  // plane, end point clearly beyond, crossing point clearly inside all other side planes — which also separates the first from
+  // the second crossing — and clearly off the triangle diagonal); otherwise false: the determinant tests decide.
   const uint32_t ns = (mask | (mask >> 1)) & 0x555u;   // bit 2s: side s has a triangle with det <= 0
-  if (__popc(ns) != 1) return false;
+  if (ns == 0u) return false;
   if ((G ? __ldg(&pc->planar) : pc->planar) == 0u) return false;
-  const int s = (__ffs(ns) - 1) >> 1;
   const double tol = G ? __ldg(&pc->tol) : pc->tol;
-  double a, b, c, d;
-  load_plane4<G>(pc->pl[2 * s], a, b, c, d);
-  const double dl = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
-  const double dx = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));
-  if (!(dl > tol && dx < -tol)) return false;
-  const double alpha = dl / (dl - dx);   // crossing point = lp + alpha (x - lp)
+  double ol[6], ox[6];
+#pragma unroll
+  for (int o = 0; o < 6; ++o) {
+    double a, b, c, d;
+    load_plane4<G>(pc->pl[2 * o], a, b, c, d);
+    ol[o] = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
+    ox[o] = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));
+  }
+  int s = -1;
+  double alpha = 2.0;
   bool ok = true;
 #pragma unroll
   for (int o = 0; o < 6; ++o) {
-    load_plane4<G>(pc->pl[2 * o], a, b, c, d);
-    const double ol = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
-    const double ox = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));
-    const double oc = fma(alpha, ox - ol, ol);
+    if ((ns >> (2 * o)) & 1u) {
+      if (!(ol[o] > tol && ox[o] < -tol)) ok = false;
+      const double a = ol[o] / (ol[o] - ox[o]);   // crossing point = lp + a (x - lp)
+      if (a < alpha) { alpha = a; s = o; }
+    }
+  }
+  if (!ok || s < 0) return false;
+#pragma unroll
+  for (int o = 0; o < 6; ++o) {
+    const double oc = fma(alpha, ox[o] - ol[o], ol[o]);
     if (o != s && !(oc > tol)) ok = false;
   }
+  double a, b, c, d;
   load_plane4<G>(pc->dg[s], a, b, c, d);
   const double gl = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
   const double gx = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));

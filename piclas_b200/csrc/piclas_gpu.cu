@@ -67,6 +67,7 @@ struct Ctx {
   int64_t sfFacCap = 0;
   // field
   double* dE = nullptr;
+  double* dEmono = nullptr;   // the same polynomials in the monomial basis (restructured arithmetic on the bins, bins.cuh)
   bool haveField = false;
   // particles
   PartBuf buf[2];
@@ -96,6 +97,12 @@ struct Ctx {
   int64_t* dEmigOff = nullptr;   // [nRanks+1]
   int64_t commSendCap = 0, commRecvCap = 0;
   int commSize = 8;
+  // compact node halo of cell_volweight_mean (nRanks > 1): the unique nodes whose sums need contributions of several ranks
+  int32_t* dHaloNodes = nullptr;
+  int nHaloNodes = 0;
+  double *dHaloSend = nullptr, *dHaloRecv = nullptr;   // [nHaloNodes][4], [nRanks][nHaloNodes][4]
+  bool haloPacked = false;
+  bool ownStream = true;
   // binned layout (bins.cuh): TriaTracking + cell_volweight_mean (or no deposition)
   bool binEligible = false;      // this configuration steps on the bins
   bool binned = false;           // the particles live in the bins (else: sorted arrays buf[cur] + dElemOff)
@@ -108,6 +115,10 @@ struct Ctx {
   int64_t* dPoolOff[2] = {nullptr, nullptr};   // [nElems + nRanks + 2] each
   int32_t *dCapMain = nullptr, *dCapIn = nullptr, *dNMain = nullptr, *dNIn = nullptr;
   int64_t *dBinBase = nullptr, *dBinTmp = nullptr;
+  int64_t *dFarBase = nullptr, *dFarDOff = nullptr, *dScanSums = nullptr, *dScanOff = nullptr;   // far regions, dense offsets, scan scratch
+  int32_t* dNFarE = nullptr;     // [nElems][2] far records / diverted particles of every element in the last step
+  uint32_t* dFarIdx = nullptr;   // [cap] used far slots, densely listed
+  int64_t farIdxCap = 0;
   PushElem* dPushElem = nullptr;
   int binParity = 0;
   int64_t nFar = 0;              // records of the far list of the open step
@@ -406,10 +417,12 @@ __global__ void __launch_bounds__(EM_NT) k_emig_compact(const uint32_t* __restri
 // RefMapping], REAL(PartSpecies), REAL(PEM%GlobalElemID) [, particle id bits when ids are carried].
 // message i <- particle emigIdx[perm[i]] (grouped by destination rank); the particle's key becomes "removed"
 __global__ void k_pack_emigrants_idx(PartBuf pb, const uint32_t* __restrict__ emigIdx, const uint32_t* __restrict__ perm, int64_t n, int cs,
-                                     int withRef, double* __restrict__ buf, uint32_t* __restrict__ keys, uint32_t removedKey) {
+                                     int withRef, double* __restrict__ buf, uint32_t* __restrict__ keys, uint32_t removedKey,
+                                     const uint32_t* __restrict__ slotOf /*bins: key index -> slot of the far list; else null*/) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int64_t p = emigIdx[perm[i]];
+  const int64_t kp = emigIdx[perm[i]];
+  const int64_t p = slotOf ? (int64_t)slotOf[kp] : kp;
   double* b = buf + i * cs;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -421,7 +434,7 @@ __global__ void k_pack_emigrants_idx(PartBuf pb, const uint32_t* __restrict__ em
   b[o] = (double)((pb.meta[p] & META_SPEC_MASK) + 1);
   b[o + 1] = (double)pb.elem[p];
   if (cs > o + 2) b[o + 2] = __longlong_as_double(pb.id ? pb.id[p] : -1);
-  keys[p] = removedKey;
+  keys[kp] = removedKey;
 }
 
 // PEM%GlobalElemID of the sorted particles follows from their segment: cheaper to write than to gather (a gathered mover costs a
@@ -512,6 +525,14 @@ int reserve_far(int64_t need, int64_t keep) {
     if (g.carryIDs) CK(cudaMemcpy(nb[0].id, g.buf[0].id, keep * 8, cudaMemcpyDeviceToDevice));
     CK(cudaMemcpy(nk, g.dKeys, keep * 4, cudaMemcpyDeviceToDevice));
   }
+  {
+    uint32_t* ni = nullptr;
+    CK(cudaMalloc((void**)&ni, ncap * 4));
+    if (keep > 0 && g.dFarIdx) CK(cudaMemcpy(ni, g.dFarIdx, (keep < g.farIdxCap ? keep : g.farIdxCap) * 4, cudaMemcpyDeviceToDevice));
+    cudaFree(g.dFarIdx);
+    g.dFarIdx = ni;
+    g.farIdxCap = ncap;
+  }
   if (g.cap > 0) { free_partbuf(g.buf[0]); free_partbuf(g.buf[1]); }
   cudaFree(g.dKeys);
   g.dKeys = nk;
@@ -551,9 +572,10 @@ int piclas_gpu_finalize(void) {
   cudaFree(g.dTria); cudaFree(g.dGeo); cudaFree(g.dPlanes); cudaFree(g.dAff); cudaFree(g.dElemRank); cudaFree(g.dElemXGP);
   cudaFree(g.dAdjOff); cudaFree(g.dAdj); cudaFree(g.dElemNodeU); cudaFree(g.dPerN); cudaFree(g.dPerOff); cudaFree(g.dPerNodes);
   cudaFree(g.dNodeVolume); cudaFree(g.dElemAcc); cudaFree(g.dS); cudaFree(g.dNodeSource); cudaFree(g.dPartSource); cudaFree(g.dCharge);
-  cudaFree(g.dE); cudaFree(g.dElemOff); cudaFree(g.dKeys); cudaFree(g.dCounters);
+  cudaFree(g.dE); cudaFree(g.dEmono); cudaFree(g.dElemOff); cudaFree(g.dKeys); cudaFree(g.dCounters);
   cudaFree(g.dStage); cudaFree(g.dStageI); cudaFree(g.dStageL);
   cudaFree(g.dCommSend); cudaFree(g.dCommRecv);
+  cudaFree(g.dHaloNodes); cudaFree(g.dHaloSend); cudaFree(g.dHaloRecv);
   cudaFree(g.dTileCnt); cudaFree(g.dEmigIdx); cudaFree(g.dEmigKey); cudaFree(g.dEmigOff);
   cudaFree(g.dFibN); cudaFree(g.dFibOff); cudaFree(g.dFibElem); cudaFree(g.dElemToBGM); cudaFree(g.dCandOff); cudaFree(g.dCandSrc);
   cudaFree(g.dCandCase); cudaFree(g.dElemBary); cudaFree(g.dElemRadius); cudaFree(g.dElemsJ); cudaFree(g.dSFElemr2);
@@ -572,7 +594,7 @@ int piclas_gpu_finalize(void) {
   for (int i = 0; i < 10; ++i) if (g.evp[i]) cudaEventDestroy(g.evp[i]);
   if (g.ev0) cudaEventDestroy(g.ev0);
   if (g.ev1) cudaEventDestroy(g.ev1);
-  if (g.st) cudaStreamDestroy(g.st);
+  if (g.st && g.ownStream) cudaStreamDestroy(g.st);
   g = Ctx();
   return 0;
 }
@@ -833,6 +855,28 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     CK(cudaMalloc((void**)&g.dPartSource, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 4 * 8));
   }
 
+  if (g.nRanks > 1 && p->DoDeposition && p->DepositionType == PGPU_DEPO_CVWM) {
+    // nodes whose NodeSource needs the sums of several ranks: touched by elements of two ranks, directly or through a periodic
+    // partner (pic_depo.f90:298-571 builds the same lists per neighbour rank)
+    std::vector<int32_t> halo;
+    if (g.nRanks <= 64) {
+      std::vector<uint64_t> touch((size_t)g.nNodes, 0);
+      for (int e = 0; e < nG; ++e)
+        for (int c = 0; c < 8; ++c) touch[m->NodeInfo[m->ElemNodeID[(size_t)e * 8 + c] - 1] - 1] |= 1ull << rank[e];
+      for (int n = 0; n < g.nNodes; ++n) {
+        uint64_t need = touch[n];
+        for (int j = 0; j < m->Periodic_nNodes[n]; ++j) need |= touch[m->Periodic_Nodes[m->Periodic_offsetNode[n] + j] - 1];
+        if (touch[n] != 0 && (need & (need - 1)) != 0) halo.push_back(n);
+      }
+    } else {
+      for (int n = 0; n < g.nNodes; ++n) halo.push_back(n);
+    }
+    g.nHaloNodes = (int)halo.size();
+    if (upload(&g.dHaloNodes, halo.data(), halo.size())) return 1;
+    CK(cudaMalloc((void**)&g.dHaloSend, (size_t)(g.nHaloNodes ? g.nHaloNodes : 1) * 4 * 8));
+    CK(cudaMalloc((void**)&g.dHaloRecv, (size_t)(g.nHaloNodes ? g.nHaloNodes : 1) * 4 * 8 * g.nRanks));
+  }
+
   // ---- tables shared by RefMapping and the shape functions -----------------------------------------------------------
   g.sfActive = p->DoDeposition && isSF;
   g.ref = isRef;
@@ -1033,6 +1077,10 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   }
   CK(cudaMalloc((void**)&g.dE, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
   CK(cudaMemset(g.dE, 0, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
+  if (g.binEligible && g.fast) {
+    CK(cudaMalloc((void**)&g.dEmono, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
+    CK(cudaMemset(g.dEmono, 0, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 3 * 8));
+  }
   CK(cudaMalloc((void**)&g.dElemOff, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
   CK(cudaMemset(g.dElemOff, 0, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
   CK(cudaMalloc((void**)&g.dCounters, 8 * sizeof(int)));
@@ -1069,6 +1117,31 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   h.r_sf = p->r_sf; h.r2_sf = p->r_sf * p->r_sf; h.r2_sf_inv = (p->r_sf > 0.) ? 1. / (p->r_sf * p->r_sf) : 0.;
   h.w_sf = p->w_sf; h.dimFactorSF = p->dimFactorSF;
   for (int d = 0; d < 3; ++d) { h.FIBGMdeltas[d] = m->FIBGMdeltas[d]; h.xyzminglob[d] = m->xyzminglob[d]; h.FIBGMmin[d] = m->FIBGMmin[d]; h.FIBGMmax[d] = m->FIBGMmax[d]; }
+  {
+    // inverse Vandermonde matrix of the Gauss points: column i = monomial coefficients of the i-th Lagrange polynomial
+    // (Gauss-Jordan with partial pivoting in long double; (N+1) <= 8)
+    const int n = m->N + 1;
+    long double V[8][16];
+    for (int r = 0; r < n; ++r) {
+      long double pw = 1.0L;
+      for (int c = 0; c < n; ++c) { V[r][c] = pw; pw *= (long double)m->xGP[r]; }
+      for (int c = 0; c < n; ++c) V[r][n + c] = (r == c) ? 1.0L : 0.0L;
+    }
+    for (int c = 0; c < n; ++c) {
+      int piv = c;
+      for (int r = c + 1; r < n; ++r) if (fabsl(V[r][c]) > fabsl(V[piv][c])) piv = r;
+      for (int k = 0; k < 2 * n; ++k) std::swap(V[c][k], V[piv][k]);
+      const long double d = V[c][c];
+      for (int k = 0; k < 2 * n; ++k) V[c][k] /= d;
+      for (int r = 0; r < n; ++r) {
+        if (r == c) continue;
+        const long double f = V[r][c];
+        for (int k = 0; k < 2 * n; ++k) V[r][k] -= f * V[c][k];
+      }
+    }
+    for (int pw = 0; pw < n; ++pw)
+      for (int i = 0; i < n; ++i) h.n2m[pw][i] = (double)V[pw][n + i];
+  }
   h.nGlobalElems = nG; h.nElems = g.nElems; h.offsetElem = g.offsetElem; h.N = g.N; h.nRanks = g.nRanks; h.myRank = g.myRank;
   CK(cudaMemcpyToSymbol(cst, &h, sizeof(h)));
   CK(cudaDeviceSynchronize());
@@ -1186,6 +1259,19 @@ int piclas_gpu_set_field(const double* E) {
   if (!E) return fail("piclas_gpu_set_field: null field");
   CK(cudaSetDevice(g.device));
   CK(cudaMemcpyAsync(g.dE, E, (size_t)g.nElems * g.ND * 3 * 8, cudaMemcpyHostToDevice, g.st));
+  if (g.dEmono && g.nElems > 0) {
+    const int grid = g.nElems < g.nSMs * 16 ? g.nElems : g.nSMs * 16;
+    switch (g.NP) {
+      case 2: k_nodal_to_mono<2><<<grid, 128, 0, g.st>>>(g.dE, g.dEmono, g.nElems); break;
+      case 3: k_nodal_to_mono<3><<<grid, 128, 0, g.st>>>(g.dE, g.dEmono, g.nElems); break;
+      case 4: k_nodal_to_mono<4><<<grid, 128, 0, g.st>>>(g.dE, g.dEmono, g.nElems); break;
+      case 5: k_nodal_to_mono<5><<<grid, 128, 0, g.st>>>(g.dE, g.dEmono, g.nElems); break;
+      case 6: k_nodal_to_mono<6><<<grid, 128, 0, g.st>>>(g.dE, g.dEmono, g.nElems); break;
+      case 7: k_nodal_to_mono<7><<<grid, 128, 0, g.st>>>(g.dE, g.dEmono, g.nElems); break;
+      case 8: k_nodal_to_mono<8><<<grid, 128, 0, g.st>>>(g.dE, g.dEmono, g.nElems); break;
+    }
+    CK(cudaGetLastError());
+  }
   CK(cudaStreamSynchronize(g.st));
   g.haveField = true;
   return 0;
@@ -1310,6 +1396,20 @@ int piclas_gpu_deposit(double* PartSource, double* NodeSource) {
   return deposit_finish(PartSource, NodeSource);
 }
 
+// ---- compact node halo (pic_depo_method.f90:565-673): only the nodes that several ranks contribute to travel ------------------------------
+__global__ void k_halo_pack(const double* __restrict__ S, const int32_t* __restrict__ nodes, int n, double* __restrict__ out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n * 4) out[t] = S[(size_t)nodes[t >> 2] * 4 + (t & 3)];
+}
+// S[node] = contributions of rank 0 + rank 1 + ... in rank order (deterministic, as the receive loop of the reference, :659-673)
+__global__ void k_halo_sum(const double* __restrict__ all, int nRanks, const int32_t* __restrict__ nodes, int n, double* __restrict__ S) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 4) return;
+  double s = all[t];
+  for (int r = 1; r < nRanks; ++r) s = s + all[(size_t)r * n * 4 + t];
+  S[(size_t)nodes[t >> 2] * 4 + (t & 3)] = s;
+}
+
 __global__ void k_extract_component(const double* __restrict__ src4, double* __restrict__ dst, int64_t n, int comp) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src4[i * 4 + comp];
@@ -1415,6 +1515,32 @@ int piclas_gpu_nodesource_device(void** devNodeSource) {
   return 0;
 }
 
+int piclas_gpu_node_halo_info(int64_t* nDoubles, void** devSend, void** devRecvAll) {
+  if (!g.ready) return fail("piclas_gpu_node_halo_info: not initialised");
+  if (g.nRanks < 2 || !g.dHaloNodes) return fail("piclas_gpu_node_halo_info: needs several ranks and cell_volweight_mean");
+  CK(cudaSetDevice(g.device));
+  if (g.nHaloNodes > 0) {
+    k_halo_pack<<<(g.nHaloNodes * 4 + 255) / 256, 256, 0, g.st>>>(g.dS, g.dHaloNodes, g.nHaloNodes, g.dHaloSend);
+    ++g.lastLaunches;
+    CK(cudaGetLastError());
+  }
+  g.haloPacked = true;
+  *nDoubles = (int64_t)g.nHaloNodes * 4;
+  *devSend = g.dHaloSend;
+  *devRecvAll = g.dHaloRecv;
+  return 0;
+}
+
+int piclas_gpu_set_stream(void* cudaStream) {
+  if (!g.ready) return fail("piclas_gpu_set_stream: not initialised");
+  CK(cudaSetDevice(g.device));
+  CK(cudaStreamSynchronize(g.st));
+  if (g.ownStream && g.st) cudaStreamDestroy(g.st);
+  g.st = (cudaStream_t)cudaStream;
+  g.ownStream = false;
+  return 0;
+}
+
 int piclas_gpu_sf_halo_info(int64_t* nSendElemsPerRank, int64_t* nRecvElemsPerRank, int32_t* doublesPerElem, void** devSend,
                             void** devRecv) {
   if (!g.ready || !g.sfActive) return fail("piclas_gpu_sf_halo_info: shape-function deposition is not active");
@@ -1443,6 +1569,13 @@ int piclas_gpu_deposit_finish(double* PartSource, double* NodeSource) {
   const double ms = g.lastMs;
   begin_timing();
   g.lastLaunches = keep;
+  if (g.haloPacked) {   // the caller gathered every rank's compact contributions into dHaloRecv (piclas_gpu_node_halo_info)
+    if (g.nHaloNodes > 0) {
+      k_halo_sum<<<(g.nHaloNodes * 4 + 255) / 256, 256, 0, g.st>>>(g.dHaloRecv, g.nRanks, g.dHaloNodes, g.nHaloNodes, g.dS);
+      ++g.lastLaunches;
+    }
+    g.haloPacked = false;
+  }
   const int rc = deposit_finish(PartSource, NodeSource);
   g.lastMs += ms;
   return rc;
@@ -1452,10 +1585,20 @@ int piclas_gpu_deposit_finish(double* PartSource, double* NodeSource) {
 static int push_track_binned(double dt, int32_t* nLost) {
   if (ensure_binned()) return 1;
   if (reserve_far(g.nPart, 0)) return 1;   // the far list (in the idle sorted buffers) can take every particle
+  if (g.farIdxCap < g.cap) {               // (the sorted buffers may have been sized by an upload)
+    cudaFree(g.dFarIdx);
+    CK(cudaMalloc((void**)&g.dFarIdx, (size_t)(g.cap ? g.cap : 1) * 4));
+    g.farIdxCap = g.cap;
+  }
   begin_timing();
   CK(cudaMemsetAsync(g.dCounters, 0, 8 * sizeof(int), g.st));
   cudaEventRecord(g.evp[3], g.st);
-  if (g.nElems > 0) {
+  const int ne = g.nElems;
+  if (ne > 0) {
+    // far regions: element e may use as many slots of the far list as it holds particles
+    k_bin_count<<<(ne + 255) / 256, 256, 0, g.st>>>(bin_view(), g.binParity, g.dBinTmp);
+    ++g.lastLaunches;
+    if (scan_i64(g.dBinTmp, ne, g.dFarBase)) return 1;
     switch (g.NP) {
       case 2: launch_bin_push<2>(dt); break;
       case 3: launch_bin_push<3>(dt); break;
@@ -1465,13 +1608,21 @@ static int push_track_binned(double dt, int32_t* nLost) {
       case 7: launch_bin_push<7>(dt); break;
       case 8: launch_bin_push<8>(dt); break;
     }
+    k_far_total<<<(ne + 255) / 256, 256, 0, g.st>>>(g.dNFarE, ne, g.dBinTmp);
+    ++g.lastLaunches;
+    if (scan_i64(g.dBinTmp, ne, g.dFarDOff)) return 1;
     CK(cudaGetLastError());
   }
   int hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t nFar = 0;
   CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
+  if (ne > 0) CK(cudaMemcpyAsync(&nFar, g.dFarDOff + ne, 8, cudaMemcpyDeviceToHost, g.st));
   CK(cudaStreamSynchronize(g.st));
-  const int64_t nFar = hc[2];
-  if (nFar > 0) launch_far_walk(nFar);
+  if (nFar > 0) {
+    k_far_index<<<ne < g.nSMs * 16 ? ne : g.nSMs * 16, 128, 0, g.st>>>(g.dFarBase, g.dNFarE, g.dFarDOff, ne, g.dFarIdx);
+    ++g.lastLaunches;
+    launch_far_walk(nFar);
+  }
   CK(cudaGetLastError());
   cudaEventRecord(g.evp[4], g.st);
   g.nFar = nFar;
@@ -1488,7 +1639,7 @@ static int push_track_binned(double dt, int32_t* nLost) {
     g.exchangePending = true;
     g.nUnsorted = nFar;
   } else {
-    if (far_finish(nFar, far_max_tag())) return 1;
+    if (far_finish(nFar)) return 1;
     g.nPart = g.nPart - nFar + (nFar > 0 ? g.hTailOff[0] : 0);
   }
   CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
@@ -1612,7 +1763,8 @@ int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void*
     CK(segment_offsets(sk, (size_t)nEmig, (uint32_t)g.nRanks, g.dEmigOff, g.st));
     // (bins: the far list lies in buf[0] with the field layout of the sorted arrays)
     k_pack_emigrants_idx<<<(unsigned)((nEmig + 255) / 256), 256, 0, g.st>>>(g.buf[g.binned ? 0 : g.cur], g.dEmigIdx, perm, nEmig, g.commSize, g.ref ? 1 : 0,
-                                                                             g.dCommSend, g.dKeys, (uint32_t)(g.nElems + g.nRanks));
+                                                                             g.dCommSend, g.dKeys, (uint32_t)(g.nElems + g.nRanks),
+                                                                             g.binned ? g.dFarIdx : nullptr);
     g.lastLaunches += 2;
     CK(cudaGetLastError());
     std::vector<int64_t> off(g.nRanks + 1, 0);
@@ -1648,23 +1800,21 @@ int piclas_gpu_exchange_finish(int64_t nRecvTotal) {
   }
   if (nRecvTotal > 0 && nRecvTotal > g.commRecvCap) return fail("piclas_gpu_exchange_finish: receive buffer too small");
   if (g.binned) {
-    // the immigrants join the far list behind this rank's own records, then one sort by destination builds the pool
-    const int64_t nFar = g.nFar, nAll = nFar + nRecvTotal;
-    if (nAll >= (int64_t)0x7fffffff) return fail("piclas_gpu_exchange_finish: more than 2^31-1 particles on one GPU");
-    if (reserve_far(nAll, nFar)) return 1;
+    // the immigrants join the far list behind every element's region, then one sort by destination builds the pool
+    const int64_t nFar = g.nFar, nAll = nFar + nRecvTotal, slot0 = g.nPart;
+    if (slot0 + nRecvTotal >= (int64_t)0x7fffffff) return fail("piclas_gpu_exchange_finish: more than 2^31-1 particles on one GPU");
+    if (reserve_far(slot0 + nRecvTotal, slot0 > nFar ? slot0 : nFar)) return 1;
     cudaEventRecord(g.evp[8], g.st);
-    const uint32_t tag0 = far_max_tag();
     if (nRecvTotal > 0) {
-      k_unpack_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[0], nFar, nRecvTotal, g.commSize, 0, g.dCommRecv);
-      k_keys_from_elem<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[0].elem + nFar, g.dElemRank, g.dKeys + nFar, nRecvTotal,
+      k_unpack_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[0], slot0, nRecvTotal, g.commSize, 0, g.dCommRecv);
+      k_keys_from_elem<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.buf[0].elem + slot0, g.dElemRank, g.dKeys + nFar, nRecvTotal,
                                                                                g.nElems, g.offsetElem, g.myRank, g.nRanks);
-      k_far_tag_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(far_alias().src, nFar, nRecvTotal, tag0);
+      k_far_index_immigrants<<<(unsigned)((nRecvTotal + 255) / 256), 256, 0, g.st>>>(g.dFarIdx, nFar, nRecvTotal, (uint32_t)slot0);
       g.lastLaunches += 3;
       CK(cudaGetLastError());
     }
     g.exchangePending = false;
-    if ((uint64_t)tag0 + (uint64_t)nRecvTotal >= 0xffffffffull) return fail("piclas_gpu_exchange_finish: origin tags exceed 32 bits");
-    if (far_finish(nAll, tag0 + (uint32_t)nRecvTotal)) return 1;
+    if (far_finish(nAll)) return 1;
     const int64_t staying = nAll > 0 ? g.hTailOff[0] : 0;
     if (nAll > 0 && g.hTailOff[g.nRanks] != staying) return fail("piclas_gpu_exchange_finish: received particles that belong to another rank");
     g.nPart = g.nPart - nFar + staying;

@@ -220,7 +220,9 @@ cudaError_t radix_sort_by_key(SortWorkspace& ws, const uint32_t* keys, size_t n,
     *perm = ws.permA;
     return cudaSuccess;
   }
-  // digit widths: as few passes as the key width allows with 8- or 10-bit digits (64^3 elements: 19 key bits -> 2 x 10)
+  // digit widths: as few passes as the key width allows with 8- or 10-bit digits (64^3 elements: 19 key bits -> 2 x 10); short
+  // lists (the far list of the binned layout) use 8-bit digits, see plan_digits
+  if (n < ((size_t)1 << 26) && bits > 10) return sort_passes<8>(ws, keys, n, (bits + 7) / 8, st, sortedKeys, perm, nLaunches);
   if (bits <= 8) return sort_passes<8>(ws, keys, n, 1, st, sortedKeys, perm, nLaunches);
   if (bits <= 10) return sort_passes<10>(ws, keys, n, 1, st, sortedKeys, perm, nLaunches);
   if (bits <= 16) return sort_passes<8>(ws, keys, n, 2, st, sortedKeys, perm, nLaunches);
@@ -247,7 +249,10 @@ void one_pass(SortWorkspace& ws, const uint32_t* kin, const uint32_t* pin, uint3
   k_scatter<RADIX><<<nBlocks, SORT_NT, 0, st>>>(kin, pin, kout, pout, n, shift, RADIX - 1, ws.blockHist);
   *nLaunches += 5;
 }
-void plan_digits(int bits, int* width, int* passes) {
+// far lists are a few per cent of the particles: with so few tiles the column kernels of a 10-bit pass (1024-entry rows) run on a
+// handful of CTAs and cost 3.5 x an 8-bit pass (measured at 4.4e6 keys: 270 vs 77 us), so short lists use 8-bit digits throughout
+void plan_digits(int bits, int* width, int* passes, size_t n) {
+  if (n < ((size_t)1 << 26)) { *width = 8; *passes = (bits + 7) / 8; return; }
   if (bits <= 8) { *width = 8; *passes = 1; }
   else if (bits <= 10) { *width = 10; *passes = 1; }
   else if (bits <= 16) { *width = 8; *passes = 2; }
@@ -277,7 +282,7 @@ cudaError_t radix_sort_two_keys(SortWorkspace& ws, const uint32_t* keysLo, int b
     kout = (kout == ws.keysB) ? ws.keysA : ws.keysB;
   };
   int w, np;
-  plan_digits(bitsLo, &w, &np);
+  plan_digits(bitsLo, &w, &np, n);
   for (int p = 0; p < np; ++p) {
     if (w == 8) one_pass<8>(ws, kin, pin, kout, pout, n, p * 8, st, nLaunches);
     else one_pass<10>(ws, kin, pin, kout, pout, n, p * 10, st, nLaunches);
@@ -288,7 +293,7 @@ cudaError_t radix_sort_two_keys(SortWorkspace& ws, const uint32_t* keysLo, int b
   ++*nLaunches;
   kin = kout;
   kout = (kout == ws.keysB) ? ws.keysA : ws.keysB;
-  plan_digits(bitsHi, &w, &np);
+  plan_digits(bitsHi, &w, &np, n);
   for (int p = 0; p < np; ++p) {
     if (w == 8) one_pass<8>(ws, kin, pin, kout, pout, n, p * 8, st, nLaunches);
     else one_pass<10>(ws, kin, pin, kout, pout, n, p * 10, st, nLaunches);

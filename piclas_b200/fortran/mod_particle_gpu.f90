@@ -140,6 +140,17 @@ INTERFACE
     TYPE(C_PTR),INTENT(OUT) :: devNodeSource                     ! [4,nUniqueGlobalNodes] doubles on the device
     INTEGER(C_INT)          :: piclas_gpu_nodesource_device
   END FUNCTION
+  FUNCTION piclas_gpu_node_halo_info(nDoubles,devSend,devRecvAll) BIND(C,NAME='piclas_gpu_node_halo_info')
+    IMPORT :: C_INT, C_INT64_T, C_PTR
+    INTEGER(C_INT64_T),INTENT(OUT) :: nDoubles                   ! 4 * number of nodes shared between ranks
+    TYPE(C_PTR),INTENT(OUT)        :: devSend,devRecvAll         ! device buffers [nDoubles], [nProcessors*nDoubles] for MPI_ALLGATHER
+    INTEGER(C_INT)                 :: piclas_gpu_node_halo_info
+  END FUNCTION
+  FUNCTION piclas_gpu_set_stream(cudaStream) BIND(C,NAME='piclas_gpu_set_stream')
+    IMPORT :: C_INT, C_PTR
+    TYPE(C_PTR),VALUE :: cudaStream                              ! cudaStream_t of the host's communication library
+    INTEGER(C_INT)    :: piclas_gpu_set_stream
+  END FUNCTION
   FUNCTION piclas_gpu_sf_halo_info(nSendElemsPerRank,nRecvElemsPerRank,doublesPerElem,devSend,devRecv) &
       BIND(C,NAME='piclas_gpu_sf_halo_info')
     IMPORT :: C_INT, C_INT32_T, C_INT64_T, C_PTR
@@ -171,7 +182,7 @@ PUBLIC :: piclas_gpu_init, piclas_gpu_finalize, piclas_gpu_upload_particles, pic
 PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles, piclas_gpu_get_charge, piclas_gpu_kinetic_energy
 PUBLIC :: piclas_gpu_exchange_info, piclas_gpu_exchange_recv_buffer, piclas_gpu_exchange_finish
 PUBLIC :: piclas_gpu_nodesource_device, piclas_gpu_sf_halo_info, piclas_gpu_deposit_finish, piclas_gpu_phase_timing
-PUBLIC :: piclas_gpu_last_timing
+PUBLIC :: piclas_gpu_last_timing, piclas_gpu_node_halo_info, piclas_gpu_set_stream
 PUBLIC :: ParticleStepGPU, GPUAbortOnError
 
 CONTAINS

@@ -84,6 +84,9 @@ class ParticleStepRank:
         self.lib = self.step.lib
         self.mesh = mesh
         self.migrated = 0
+        # the library works on torch's current stream: its kernels and the NCCL collectives issued below are then ordered on the
+        # device, no host synchronisation between them
+        self._check(self.lib.piclas_gpu_set_stream(C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
     def close(self):
         self.step.close()
@@ -105,7 +108,6 @@ class ParticleStepRank:
         sbuf = device_tensor(sp.value, sum(send_counts) * cs.value, self.device)
         rbuf = device_tensor(rp.value, nrecv * cs.value, self.device)
         exchange_particles(sbuf, send_counts, rbuf, recv_counts, cs.value, self.group)
-        torch.cuda.synchronize(self.device)
         self._check(self.lib.piclas_gpu_exchange_finish(C.c_int64(nrecv)))
         self.migrated = sum(send_counts)
         return sum(send_counts), nrecv
@@ -128,16 +130,18 @@ class ParticleStepRank:
             sbuf = device_tensor(sp.value, sum(ns) * dpe.value, self.device)
             rbuf = device_tensor(rp.value, sum(nr) * dpe.value, self.device)
             exchange_sf_halo(sbuf, ns, rbuf, nr, dpe.value, self.group)
-            torch.cuda.synchronize(self.device)
             PS = out_partsource if out_partsource is not None else (np.empty(self.step._ps_shape) if want_partsource else None)
             self._check(self.lib.piclas_gpu_deposit_finish(_f(PS), _f(None)))
             return PS, None
         self._check(self.lib.piclas_gpu_deposit(_f(None), _f(None)))       # rank-local node sums
-        p = C.c_void_p(0)
-        self._check(self.lib.piclas_gpu_nodesource_device(C.byref(p)))
-        t = device_tensor(p.value, self.mesh.nUniqueNodes * 4, self.device)
-        halo_sum(t, self.group)
-        torch.cuda.synchronize(self.device)
+        # node halo on the compact list of shared nodes: all-gather, then the library adds the ranks' parts in rank order
+        nd = C.c_int64(0)
+        sp, rp = C.c_void_p(0), C.c_void_p(0)
+        self._check(self.lib.piclas_gpu_node_halo_info(C.byref(nd), C.byref(sp), C.byref(rp)))
+        if nd.value > 0:
+            sbuf = device_tensor(sp.value, nd.value, self.device)
+            rbuf = device_tensor(rp.value, nd.value * self.world, self.device)
+            dist.all_gather_into_tensor(rbuf, sbuf, group=self.group)
         PS = out_partsource if out_partsource is not None else (np.empty(self.step._ps_shape) if want_partsource else None)
         NS = np.empty((self.mesh.nUniqueNodes, 4)) if want_nodesource else None
         self._check(self.lib.piclas_gpu_deposit_finish(_f(PS), _f(NS)))

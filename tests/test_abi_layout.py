@@ -193,7 +193,7 @@ def test_ctypes_argument_types_match_the_c_prototypes():
     so = lib.load()
     scalar = {"double": C.c_double, "int64_t": C.c_int64, "int32_t": C.c_int32, "int": C.c_int}
     pointer = {"double": abi.c_f64p, "int32_t": abi.c_i32p, "int64_t": abi.c_i64p,
-               "pgpu_mesh_t": C.POINTER(abi.pgpu_mesh_t), "pgpu_params_t": C.POINTER(abi.pgpu_params_t)}
+               "pgpu_mesh_t": C.POINTER(abi.pgpu_mesh_t), "pgpu_params_t": C.POINTER(abi.pgpu_params_t), "void": C.c_void_p}
     checked = 0
     for name, (ret, cargs) in _c_prototypes().items():
         fn = getattr(so, name)
