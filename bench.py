@@ -150,9 +150,14 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-# FP64 work the interpolate+push+track phase executes per particle (profiles/r1_final_stalls_k_interp_push.txt: DFMA x 2 + DMUL + DADD
-# warp instructions x 29.3 active lanes / 7.8125e6 particles): the numerator of the FP64 roofline, the bound SURVEY.md F7 expects
-FP64_FLOP_PER_PARTICLE_PUSH = 1360.0
+# FP64 work the interpolate+push+track phase executes per particle, from the committed ncu capture of this round's kernels
+# (profiles/r2_traffic.json: (2 DFMA + DMUL + DADD) thread instructions of k_bin_push + k_far_walk / particles): the numerator of the
+# FP64 roofline, the bound SURVEY.md F7 expects
+def fp64_flop_per_particle():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["fp64_flop_per_particle_interp_push_track"])
+    except Exception:
+        return 900.0
 
 
 def fp64_roofline(n_particles, t_push_s):
@@ -163,15 +168,16 @@ def fp64_roofline(n_particles, t_push_s):
         peak = float(json.load(open(p))["fp64_tflops"])
     except Exception:
         return None
-    achieved = FP64_FLOP_PER_PARTICLE_PUSH * n_particles / t_push_s / 1e12 if t_push_s > 0 else 0.0
+    fpp = fp64_flop_per_particle()
+    achieved = fpp * n_particles / t_push_s / 1e12 if t_push_s > 0 else 0.0
     return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "flop_per_particle": FP64_FLOP_PER_PARTICLE_PUSH, "peak_source": "measured (profiles/fp64_peak.json, scripts/fp64_peak.cu)"}
+            "flop_per_particle": fpp, "peak_source": "measured (profiles/fp64_peak.json, scripts/fp64_peak.cu)"}
 
 
 def measured_traffic(n_particles):
     """DRAM bytes of the dominant phase per launch: dram__bytes_read+write per particle from the committed `ncu --set full`
-    capture (profiles/r1_traffic.json, taken at the same particles per element) times the particles of this launch."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    capture (profiles/r2_traffic.json, taken at 6.25e7 particles and the same particles per element) times the particles of this launch."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
@@ -212,6 +218,12 @@ def cpu_baseline(args, N, threads=None, steps=None, warmup=1):
                       % (ne, N, n, ppe, steps, t, threads)}
 
 
+def kernel_names(variant):
+    if variant == "ref_sf":
+        return "k_interp_push + k_track_ref (interpolate+push+RefMapping tracking phase)"
+    return "k_bin_push + k_far_walk (interpolate + push + track + delivery on the binned layout)"
+
+
 def config_dict(args, n_total):
     if getattr(args, "variant", "tria_cvwm") == "ref_sf":
         return {"workload": "synthetic 3-periodic box %d^3 hexahedra N=%d NGeo=1, %.3g electrons, RefMapping + shape_function "
@@ -250,6 +262,102 @@ def full_size_checks(gpu, mesh, n_expected, charge_per_particle, charge_tol=1e-1
                            and np.isfinite(ekin).all())}
     except Exception as e:   # a failed check must not cost the measurement
         return {"ok": False, "error": repr(e)[:300]}
+
+
+# ---- checks of the multi-rank device path inside the benchmark run (the oracle is the checker here, outside every timed region) ----
+def small_parity_check(rank, world, local, arithmetic, steps=3):
+    """The N-rank device path (migration pack / exchange / unpack, node halo sum) against the single-rank CPU oracle on a small
+    box that is partitioned exactly like the benchmark's (z-slabs, periodic wrap between the last and the first rank): every
+    particle's element (exact), position and velocity, and the deposited sources of ALL elements — the rank-boundary slabs
+    included — gathered on rank 0.  The oracle is used here as the checker only (outside every timed region)."""
+    import torch
+    import torch.distributed as dist
+    import cases
+    from piclas_b200 import hostmesh as hm
+    from piclas_b200.multi import ParticleStepRank
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (6, 6, 3 * world), 3)
+    prm = cases.electron_params(arithmetic=arithmetic, carryParticleIDs=1)
+    dt = 1e-8
+    n = 150 * mesh.nElems
+    PS, spec = cases.uniform_plasma(mesh, n, seed=4242, vth_cells=0.3, dt=dt)       # identical on every rank
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    E = cases.smooth_field(mesh, amp=2e-4)
+    R = ParticleStepRank(mesh, prm, rank, world, local)
+    off = R.offsets
+    mine = (elem > off[rank]) & (elem <= off[rank + 1])
+    ids = np.arange(n, dtype=np.int64)
+    R.step.UploadParticles(PS[mine], spec[mine], elem[mine], IsNewPart=np.ones(int(mine.sum()), dtype=np.int32), ids=ids[mine])
+    R.step.SetField(np.ascontiguousarray(E[int(off[rank]):int(off[rank + 1])]))
+    res = {"ok": True, "ranks": world, "elements": int(mesh.nElems), "particles": int(n), "steps": steps, "migrated": 0,
+           "max_rel_state": 0.0, "max_rel_source": 0.0}
+    if rank == 0:
+        from oracle_lib import Oracle
+        orc = Oracle(mesh, cases.electron_params(arithmetic=arithmetic, carryParticleIDs=1))
+        PSo, elo = PS.copy(), elem.copy()
+        inside = np.ones(n, dtype=np.int32)
+        isnew = np.ones(n, dtype=np.int32)
+    try:
+        for it in range(steps):
+            PSrc, NS = R.Deposition()
+            R.PushAndTrack(dt, it)
+            res["migrated"] += R.migrated
+            d = R.step.DownloadParticles()
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object((d["ids"], d["PartState"], d["GlobalElemID"], PSrc), parts, dst=0)
+            if rank == 0:
+                PSr, _ = orc.deposit(PSo, spec, elo, inside)
+                orc.push_track(dt, PSo, spec, elo, inside, isnew, E)
+                allid = np.concatenate([p[0] for p in parts])
+                o = np.argsort(allid)
+                same_set = len(allid) == n and np.array_equal(allid[o], ids)
+                own_ok = same_set and np.array_equal(np.concatenate([p[2] for p in parts])[o], elo)
+                if same_set:
+                    res["max_rel_state"] = max(res["max_rel_state"],
+                                               float(np.abs(np.concatenate([p[1] for p in parts])[o] - PSo).max() / np.abs(PSo).max()))
+                src = np.concatenate([p[3] for p in parts])
+                for c in range(4):
+                    res["max_rel_source"] = max(res["max_rel_source"], float(np.abs(src[..., c] - PSr[..., c]).max() / np.abs(PSr[..., c]).max()))
+                res["ok"] = bool(res["ok"] and same_set and own_ok and res["max_rel_state"] <= 1e-12 and res["max_rel_source"] <= 1e-12)
+                res["ownership_exact"] = bool(own_ok)
+    except Exception as e:   # a failed check must not cost the measurement
+        res = {"ok": False, "error": repr(e)[:300]}
+    R.close()
+    if rank == 0:
+        orc.close()
+    tot = torch.tensor([res.get("migrated", 0)], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    res["migrated"] = int(tot.item())
+    return res
+
+
+def full_size_checks_multi(R, mesh, n_expected, charge_per_particle, rank, world):
+    """Size-independent properties of the N-rank run at the benchmark's full size, outside the timed regions: particle count
+    conserved over the ranks, deposited charge after the node halo sum (CalcDepositedCharge, pic_analyze.f90:165-175, summed over the
+    ranks' elements) against the particles' charge, every particle in the device reductions."""
+    try:
+        import torch
+        import torch.distributed as dist
+        n1 = mesh.N + 1
+        off = R.offsets
+        nloc = int(off[rank + 1] - off[rank])
+        R.Deposition(want_partsource=False, want_nodesource=False)
+        rho = np.empty((nloc, n1, n1, n1))
+        R.step.ChargeDensity(out=rho)
+        w = mesh.wGP[:, None, None] * mesh.wGP[None, :, None] * mesh.wGP[None, None, :]
+        q_loc = float(np.sum(rho * w[None] / mesh.sJ[int(off[rank]):int(off[rank + 1])]))
+        ekin, npart = R.step.KineticEnergy()
+        t = torch.tensor([q_loc, float(R.step.NumParticles()), float(npart.sum()), float(ekin.sum())], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        q_dep, n_now, n_red, ek = [float(v) for v in t.tolist()]
+        q_part = n_expected * charge_per_particle
+        return {"particles": int(n_now), "particles_expected": int(n_expected), "particles_in_reduction": int(n_red),
+                "deposited_charge": q_dep, "particle_charge": q_part, "charge_conservation_rel_err": abs(q_dep - q_part) / abs(q_part),
+                "kinetic_energy_J": ek,
+                "ok": bool(int(n_now) == int(n_expected) and int(n_red) == int(n_now) and abs(q_dep - q_part) <= 1e-12 * abs(q_part)
+                           and np.isfinite(ek))}
+    except Exception as e:
+        return {"ok": False, "error": repr(e)[:300]}
+
 
 
 def run_reference(args):
@@ -374,12 +482,14 @@ def run_b200(args):
     t_push = phases[2] * 1e-3
     achieved = ALG_BYTES_PER_PARTICLE_STEP * n_total / t_push / 1e9 if t_push > 0 else 0.0
     traffic, traffic_src = measured_traffic(n_total)
-    roofline = {"bound": "hbm", "kernel": "k_interp_push + k_track_leavers (interpolate+push+track phase)", "achieved": achieved, "peak": peak,
+    roofline = {"bound": "hbm", "kernel": (kernel_names(args.variant)), "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_launch": ALG_BYTES_PER_PARTICLE_STEP * n_total, "ms_per_launch": phases[2],
                 "step_frac": (ALG_BYTES_PER_PARTICLE_STEP * n_total * args.steps / wall / 1e9) / peak,
                 "phase_ms": {"deposit_particles": phases[0], "deposit_nodes_dofs": phases[1], "interp_push_track": phases[2],
-                             "sort_permute": phases[3]}}
+                             "sort_permute": phases[3]},
+                "phase_note": "sort_permute = what replaces UpdateNextFreePosition: far-list sort + pool on the bins (tria_cvwm), the "
+                              "radix sort + gather of all particles on the sorted arrays (ref_sf)"}
     f64 = fp64_roofline(n_total, t_push)
     if f64 is not None:
         roofline["fp64"] = f64

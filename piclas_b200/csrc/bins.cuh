@@ -25,11 +25,26 @@ constexpr int BIN_PPT = 2;           // particles per thread and sweep (one 128-
 constexpr int BIN_CHUNK = BIN_NT * BIN_PPT;
 constexpr int BIN_NRANGE = 8;        // main, six side inboxes, pool
 #ifndef MONO_UNROLL_J
-#define MONO_UNROLL_J 2      // rows of the field tile in flight per thread in the Horner evaluation
+#define MONO_UNROLL_J 4      // rows of the field tile in flight per thread in the Horner evaluation
 #endif
 constexpr int MONO_UJ = MONO_UNROLL_J;
+// k_bin_push: threads per CTA and resident CTAs per SM (register cap 65536 / (KB_NT * KB_MINB) = 168).  One warp per CTA: the
+// stable compaction of every sweep is a warp scan, no block barrier, no shared-memory exchange of counts; the per-element
+// prologue (ranges, records, inbox bases) is executed by one warp instead of four; 64-particle sweeps waste less of the last one
+#ifndef KB_NT
+#define KB_NT 32
+#endif
+#ifndef KB_UNROLL_Q
+#define KB_UNROLL_Q 1     // 1: push + inside test of the thread's two particles interleaved
+#endif
 #ifndef KB_MINB
-#define KB_MINB 3                    // resident CTAs / SM of k_bin_push (register cap 65536 / (128 * KB_MINB))
+#define KB_MINB (384 / KB_NT)
+#endif
+constexpr int KB_CHUNK = KB_NT * BIN_PPT;
+#if KB_NT == 32
+#define KB_SYNC() __syncwarp()
+#else
+#define KB_SYNC() __syncthreads()
 #endif
 
 struct BinView {
@@ -318,8 +333,13 @@ __global__ void __launch_bounds__(BIN_NT, DEP_MINB) k_bin_deposit_cvwm(PartBuf b
   __shared__ GeoElem sg;
   __shared__ AffElem sa;
   __shared__ double corner[8][3];
-  __shared__ DepAcc sAcc;
-  __shared__ double sP[2][6][BIN_NT];
+  // the per-thread accumulators of the general path / of the final reduction and the staging slots of the fast path are never
+  // live at the same time: one buffer
+  typedef double StageBuf[2][6][2 * BIN_NT];
+  __shared__ __align__(16) unsigned char sBuf[sizeof(DepAcc) > sizeof(StageBuf) ? sizeof(DepAcc) : sizeof(StageBuf)];
+  DepAcc& sAcc = *reinterpret_cast<DepAcc*>(sBuf);
+  StageBuf& sP = *reinterpret_cast<StageBuf*>(sBuf);
+  __shared__ uint32_t sM[2][BIN_NT][2];
   const int tid = threadIdx.x;
   for (int e = blockIdx.x; e < bv.nElems; e += gridDim.x) {
     __syncthreads();
@@ -349,57 +369,64 @@ __global__ void __launch_bounds__(BIN_NT, DEP_MINB) k_bin_deposit_cvwm(PartBuf b
       live = left > 0;
     };
     if (fastElem) {
-      int v = tid, stage = 0;
-      uint8_t meta = 0, metaNext = 0;
-      bool live = false, liveNext = false;
-      if (v < total) {
-        int r;
-        int64_t slot;
-        src_of(v, r, slot, live);
-        if (live) {
-          const double* sf = (r == 7) ? pool.f : bins.f;
-          const int64_t sst = (r == 7) ? pool.stride : bins.stride;
-#pragma unroll
-          for (int a = 0; a < 6; ++a) cp_async8(&sP[0][a][tid], sf + a * sst + slot);
-          meta = ((r == 7) ? pool.meta : bins.meta)[slot];
-        }
-      }
-      cp_async_commit();
-      for (; v < total; v += BIN_NT, stage ^= 1, meta = metaNext, live = liveNext) {
-        const int vn = v + BIN_NT;
-        liveNext = false;
-        if (vn < total) {
-          int r;
+      // two particles per thread and sweep: one 128-bit copy per array and thread, meta bytes through their aligned words
+      int stage = 0, nLive = 0, nLiveNext = 0, sh = 0, shNext = 0;
+      auto fetch2 = [&](int v, int stg, int& nl, int& shifts) {
+        nl = 0;
+        shifts = 0;
+        if (v < total) {
+          int r, left;
           int64_t slot;
-          src_of(vn, r, slot, liveNext);
-          if (liveNext) {
+          resolve(R, v, r, slot, left);
+          nl = left >= 2 ? 2 : (left > 0 ? 1 : 0);
+          if (nl > 0) {
             const double* sf = (r == 7) ? pool.f : bins.f;
             const int64_t sst = (r == 7) ? pool.stride : bins.stride;
+            const uint8_t* sm = (r == 7) ? pool.meta : bins.meta;
+            if ((slot & 1) == 0) {
 #pragma unroll
-            for (int a = 0; a < 6; ++a) cp_async8(&sP[stage ^ 1][a][tid], sf + a * sst + slot);
-            metaNext = ((r == 7) ? pool.meta : bins.meta)[slot];
+              for (int a = 0; a < 6; ++a) cp_async16(&sP[stg][a][2 * tid], sf + a * sst + slot);
+            } else {
+#pragma unroll
+              for (int a = 0; a < 6; ++a) {
+                cp_async8(&sP[stg][a][2 * tid], sf + a * sst + slot);
+                cp_async8(&sP[stg][a][2 * tid + 1], sf + a * sst + slot + 1);
+              }
+            }
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&sM[stg][tid][0])), "l"(sm + (slot & ~(int64_t)3)) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&sM[stg][tid][1])), "l"(sm + ((slot + 1) & ~(int64_t)3)) : "memory");
+            shifts = (int)(8 * (slot & 3)) | ((int)(8 * ((slot + 1) & 3)) << 8);
           }
         }
+      };
+      fetch2(2 * tid, 0, nLive, sh);
+      cp_async_commit();
+      for (int v = 2 * tid; v < total; v += 2 * BIN_NT, stage ^= 1, nLive = nLiveNext, sh = shNext) {
+        fetch2(v + 2 * BIN_NT, stage ^ 1, nLiveNext, shNext);
         cp_async_commit();
         cp_async_wait_prev();
-        if (!live) continue;
-        const double x[3] = {sP[stage][0][tid], sP[stage][1][tid], sP[stage][2][tid]};
-        double xi[3];
-        if (!affine_xi(&sa, x, xi)) { ++nGeneral; continue; }
-        const int spec = meta & META_SPEC_MASK;
-        const double q = cst.ChargeIC[spec];
-        if (!(fabs(q) > 0.0)) continue;  // isDepositParticle
-        const double Charge = q * cst.MPF[spec];
-        const double T[4] = {sP[stage][3][tid] * Charge, sP[stage][4][tid] * Charge, sP[stage][5][tid] * Charge, Charge};
-        const double a1 = 0.5 * (xi[0] + 1.0), a2 = 0.5 * (xi[1] + 1.0), a3 = 0.5 * (xi[2] + 1.0);
-        const double b1 = 1 - a1, b2 = 1 - a2, b3 = 1 - a3;
-        const double w[8] = {(b1 * b2) * b3, (a1 * b2) * b3, (a1 * a2) * b3, (b1 * a2) * b3,
-                             (b1 * b2) * a3, (a1 * b2) * a3, (a1 * a2) * a3, (b1 * a2) * a3};
 #pragma unroll
-        for (int n = 0; n < 8; ++n)
+        for (int q = 0; q < 2; ++q) {
+          if (q >= nLive) continue;
+          const double x[3] = {sP[stage][0][2 * tid + q], sP[stage][1][2 * tid + q], sP[stage][2][2 * tid + q]};
+          double xi[3];
+          if (!affine_xi(&sa, x, xi)) { ++nGeneral; continue; }
+          const int spec = (int)((sM[stage][tid][q] >> ((sh >> (8 * q)) & 0xff)) & META_SPEC_MASK);
+          const double qc = cst.ChargeIC[spec];
+          if (!(fabs(qc) > 0.0)) continue;  // isDepositParticle
+          const double Charge = qc * cst.MPF[spec];
+          const double T[4] = {sP[stage][3][2 * tid + q] * Charge, sP[stage][4][2 * tid + q] * Charge, sP[stage][5][2 * tid + q] * Charge, Charge};
+          const double a1 = 0.5 * (xi[0] + 1.0), a2 = 0.5 * (xi[1] + 1.0), a3 = 0.5 * (xi[2] + 1.0);
+          const double b1 = 1 - a1, b2 = 1 - a2, b3 = 1 - a3;
+          const double w[8] = {(b1 * b2) * b3, (a1 * b2) * b3, (a1 * a2) * b3, (b1 * a2) * b3,
+                               (b1 * b2) * a3, (a1 * b2) * a3, (a1 * a2) * a3, (b1 * a2) * a3};
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[n * 4 + c] = fma(T[c], w[n], acc[n * 4 + c]);
+          for (int n = 0; n < 8; ++n)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[n * 4 + c] = fma(T[c], w[n], acc[n * 4 + c]);
+        }
       }
+      __syncthreads();   // every thread is done with its staging slots before the buffer takes the accumulators
 #pragma unroll
       for (int a = 0; a < 32; ++a) sAcc[a][tid] = acc[a];
     }
@@ -643,8 +670,12 @@ __device__ __forceinline__ void range_store(ElemRanges& R, const RangeRegs& r, i
   }
 }
 
-template <int NP, bool FAST>
-__global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, PartBuf pool, BinView bv, int cur, FarBuf far,
+// HOTONLY: every local element is affine with planar sides, B = 0, restructured arithmetic.  The kernel then contains no call at
+// all (a call anywhere in the loop makes the compiler keep the loop's state in local memory: 340 bytes of spills per thread); the
+// rare particle that needs the general path (closed-form reference position far outside the element, pushed position within tol
+// of a side plane) is handed UNPUSHED to the far list, where k_far_unpushed runs the general path for it before the walk.
+template <int NP, bool FAST, bool HOTONLY>
+__global__ void __launch_bounds__(KB_NT, KB_MINB) k_bin_push(PartBuf bins, PartBuf pool, BinView bv, int cur, FarBuf far,
                                                               const int64_t* __restrict__ farBase, int32_t* __restrict__ nFarE,
                                                               const PushElem* __restrict__ pushElem, const double* __restrict__ Et /*tile source: monomial
                                                               coefficients (FAST) or Gauss-point values*/, const double* __restrict__ E /*Gauss-point values*/,
@@ -661,10 +692,11 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
   __shared__ __align__(16) PushElem sPE[2];
   __shared__ __align__(16) double sEb[EBUF][ND * 3];
   __shared__ __align__(8) uint64_t mbar[2];
-  __shared__ __align__(16) double sP[2][6][BIN_CHUNK];   // x, v of the current / next pair of every thread (cp.async)
-  __shared__ uint32_t sM[2][BIN_NT][2];                  // the aligned 32-bit words that hold the pair's two meta bytes
+  __shared__ __align__(16) double sP[2][6][KB_CHUNK];   // x, v of the current / next pair of every thread (cp.async)
+  __shared__ uint32_t sM[2][KB_NT][2];                  // the aligned 32-bit words that hold the pair's two meta bytes
+  __shared__ __align__(16) double sN[6][KB_CHUNK];       // pushed x, v of the sweep's particles
   __shared__ ElemRanges R2[2];
-  __shared__ int sCnt[2][BIN_NT / 32][8];
+  __shared__ int sCnt[2][KB_NT / 32][8];
   __shared__ int sRun[2][8];
   __shared__ int64_t sNbBase[6];                         // first slot of the inbox this element fills at the neighbour behind side s
   __shared__ int sNbCap[6];
@@ -679,16 +711,16 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
     mbar_init(&mbar[1], 1);
     mbar_fence_init();
   }
-  __syncthreads();
+  KB_SYNC();
   auto prefetch_elem = [&](int e, int b) {   // one thread: records of element e -> buffer b
     mbar_expect_tx(&mbar[b], (uint32_t)sizeof(PushElem) + (TMA_E ? E_BYTES : 0u));
     bulk_g2s(&sPE[b], pushElem + e, (uint32_t)sizeof(PushElem), &mbar[b]);
     if (TMA_E) bulk_g2s(&sEb[TMA_E ? b : 0][0], Et + (size_t)e * ND * 3, E_BYTES, &mbar[b]);
   };
-  // pair of this thread in chunk c of the element with ranges R: virtual indices c*BIN_CHUNK + 2*tid, +1.  Copies only: nothing
+  // pair of this thread in chunk c of the element with ranges R: virtual indices c*KB_CHUNK + 2*tid, +1.  Copies only: nothing
   // here waits for memory.  Returns the slot of the first particle (-1: none), the number of live particles and the source.
   auto fetch = [&](const ElemRanges& R, int c, int stg, int& nLive, int64_t& slot, bool& fromPool) {
-    const int v = c * BIN_CHUNK + 2 * tid;
+    const int v = c * KB_CHUNK + 2 * tid;
     nLive = 0;
     slot = -1;
     fromPool = false;
@@ -723,7 +755,7 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
   if ((int)blockIdx.x < nElems) {
     if (tid == 0) prefetch_elem(blockIdx.x, 0);
     if (warp == 0) range_store(R2[0], range_load(bv, blockIdx.x, cur, lane), lane);
-    __syncthreads();
+    KB_SYNC();
     fetch(R2[0], 0, 0, nLive, slotCur, poolCur);
   }
   cp_async_commit();
@@ -745,8 +777,8 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
     const int64_t farLo = farBase[e], farHi = farBase[e + 1];
     mbar_wait(&mbar[b], (uint32_t)((it >> 1) & 1));
     if (!TMA_E) {
-      for (int t = tid; t < ND * 3; t += BIN_NT) sEb[0][t] = __ldg(Et + (size_t)e * ND * 3 + t);
-      __syncthreads();
+      for (int t = tid; t < ND * 3; t += KB_NT) sEb[0][t] = __ldg(Et + (size_t)e * ND * 3 + t);
+      KB_SYNC();
     }
     const PushElem& pe = sPE[b];
     const double* sE = sEb[TMA_E ? b : 0];
@@ -759,8 +791,8 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
     const int total = R.pre[BIN_NRANGE];
     const bool boris = cst.TimeDiscMethod == PGPU_TIMEDISC_BORIS_LEAPFROG;
     const bool noB = cst.externalField[3] == 0. && cst.externalField[4] == 0. && cst.externalField[5] == 0.;
-    const bool hotElem = FAST && pe.affine != 0u && pe.planar != 0u && noB;
-    const int nChunks = (total + BIN_CHUNK - 1) / BIN_CHUNK;
+    const bool hotElem = HOTONLY || (FAST && pe.affine != 0u && pe.planar != 0u && noB);
+    const int nChunks = (total + KB_CHUNK - 1) / KB_CHUNK;
     const int64_t base_e = R.start[0];
     const int capMain = bv.capMain[e];
     auto publish_next = [&]() {   // warp 0: ranges of the next element, inboxes of this one
@@ -769,7 +801,7 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
     };
     if (nChunks <= 1) {   // too short to hide the loads behind chunk 0: publish now
       if (warp == 0) publish_next();
-      __syncthreads();
+      KB_SYNC();
       if (nChunks == 0) {   // empty element: only the chunk 0 of the next element has to be put in flight
         if (haveNext) fetch(R2[b ^ 1], 0, stg, nLive, slotCur, poolCur);
         cp_async_commit();
@@ -786,124 +818,131 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
       cp_async_wait_prev();
       // ---- per-particle work ----------------------------------------------------------------------------------------------
       // hot path (no calls): affine + planar element, closed-form reference position, B = 0, position clear of every side plane;
-      // everything else is flagged and goes through cold_particle afterwards
+      // everything else goes through cold_particle.  The field of the thread's two particles is evaluated together (shared
+      // operands); push, inside test and delivery then run particle by particle in rolled loops, the pushed state parked in
+      // shared memory: half the code and far fewer live registers than two interleaved copies.
       const int pq = (nLive == 1) ? 0 : 1;   // the idle half of a pair computes on a copy of the live one (finite inputs, discarded)
-      const double* sPs = &sP[stg][0][2 * tid];   // [a * BIN_CHUNK + q]
-      double xn[2][3], vn[2][3];
-      int metaQ[2] = {0, 0};
-      int cat[2] = {CAT_NONE, CAT_NONE};
-      bool cold[2] = {false, false};
+      const double* sPs = &sP[stg][0][2 * tid];   // [a * KB_CHUNK + q]: x, v as loaded (x = LastPartPos)
+      double* sNs = &sN[0][2 * tid];              // [a * KB_CHUNK + q]: pushed x, v
+      int cats = CAT_NONE | (CAT_NONE << 4);
+      int unpushed = 0;
       if (nLive > 0) {
-        metaQ[0] = (int)((sM[stg][tid][0] >> (8 * (int)(slotCur & 3))) & 0xffu);
-        metaQ[1] = pq ? (int)((sM[stg][tid][1] >> (8 * (int)((slotCur + 1) & 3))) & 0xffu) : metaQ[0];
+        double f2[2][3];
+        bool farOut[2] = {false, false};   // closed-form reference position far outside the element
         if (hotElem) {
-          double f2[2][3];
-          {
-            double xi[2][3];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const int qs = q ? pq : 0;
-              const double r0 = sPs[qs] - pe.x0[0], r1 = sPs[BIN_CHUNK + qs] - pe.x0[1], r2 = sPs[2 * BIN_CHUNK + qs] - pe.x0[2];
-#pragma unroll
-              for (int d = 0; d < 3; ++d) xi[q][d] = fma(pe.A[d][0], r0, fma(pe.A[d][1], r1, pe.A[d][2] * r2)) - 1.0;
-              cold[q] = !(fabs(xi[q][0]) <= 1.5 && fabs(xi[q][1]) <= 1.5 && fabs(xi[q][2]) <= 1.5);
-              if (cold[q]) { xi[q][0] = 0.; xi[q][1] = 0.; xi[q][2] = 0.; }
-            }
-            evaluate_field_mono2<NP>(xi, sE, f2);
-          }
+          double xi[2][3];
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int qs = q ? pq : 0;
+            const double r0 = sPs[qs] - pe.x0[0], r1 = sPs[KB_CHUNK + qs] - pe.x0[1], r2 = sPs[2 * KB_CHUNK + qs] - pe.x0[2];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) { xn[q][d] = sPs[d * BIN_CHUNK + qs]; vn[q][d] = sPs[(3 + d) * BIN_CHUNK + qs]; }
-            const int spec = metaQ[q] & META_SPEC_MASK;
+            for (int d = 0; d < 3; ++d) xi[q][d] = fma(pe.A[d][0], r0, fma(pe.A[d][1], r1, pe.A[d][2] * r2)) - 1.0;
+            farOut[q] = !(fabs(xi[q][0]) <= 1.5 && fabs(xi[q][1]) <= 1.5 && fabs(xi[q][2]) <= 1.5);
+            if (farOut[q]) { xi[q][0] = 0.; xi[q][1] = 0.; xi[q][2] = 0.; }
+          }
+          evaluate_field_mono2<NP>(xi, sE, f2);
+        }
+#if KB_UNROLL_Q
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+        for (int q = 0; q < 2; ++q) {
+          if (q >= nLive) continue;
+          const int metaQ = (int)((sM[stg][tid][q] >> (8 * (int)((slotCur + q) & 3))) & 0xffu);
+          double xq[3] = {sPs[q], sPs[KB_CHUNK + q], sPs[2 * KB_CHUNK + q]};
+          double vq[3] = {sPs[3 * KB_CHUNK + q], sPs[4 * KB_CHUNK + q], sPs[5 * KB_CHUNK + q]};
+          int cat = CAT_FAR;
+          bool cold = !hotElem || (q ? farOut[1] : farOut[0]);
+          if (!cold) {
+            const int spec = metaQ & META_SPEC_MASK;
             double E3[3] = {0., 0., 0.};
             if (cst.DoInterpolation && fabs(cst.ChargeIC[spec]) > 0.0) {
 #pragma unroll
-              for (int d = 0; d < 3; ++d) E3[d] = cst.externalField[d] + f2[q][d];
+              for (int d = 0; d < 3; ++d) E3[d] = cst.externalField[d] + (q ? f2[1][d] : f2[0][d]);
             }
-            push_inline_b0(xn[q], vn[q], E3, spec, (metaQ[q] & META_ISNEW) != 0, boris, dt);
-          }
-          // ---- own-element inside test (first iteration of SingleParticleTriaTracking3D, particle_triatracking.f90:203-218) and
-          //      the crossing of exactly one side plane into a face neighbour -----------------------------------------------------------
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            if (q >= nLive) { cat[q] = CAT_NONE; cold[q] = false; continue; }
-            if (cold[q]) continue;
+            const double lp0 = xq[0], lp1 = xq[1], lp2 = xq[2];
+            push_inline_b0(xq, vq, E3, spec, (metaQ & META_ISNEW) != 0, boris, dt);
+            // ---- own-element inside test (first iteration of SingleParticleTriaTracking3D, particle_triatracking.f90:203-218)
+            //      and the crossing of exactly one side plane into a face neighbour ------------------------------------------------
             double dx[6];
             uint32_t neg = 0;
             bool ambiguous = false;
             const double tol = pe.tol;
 #pragma unroll
             for (int s = 0; s < 6; ++s) {
-              dx[s] = fma(pe.pl[s][0], xn[q][0], fma(pe.pl[s][1], xn[q][1], fma(pe.pl[s][2], xn[q][2], -pe.pl[s][3])));
+              dx[s] = fma(pe.pl[s][0], xq[0], fma(pe.pl[s][1], xq[1], fma(pe.pl[s][2], xq[2], -pe.pl[s][3])));
               ambiguous |= fabs(dx[s]) <= tol;
               neg |= (dx[s] < 0.) ? (1u << s) : 0u;
             }
-            if (ambiguous) { cold[q] = true; continue; }   // within tol of a side plane: the determinants decide (ParticleInsideQuad3D)
-            if (neg == 0u) { cat[q] = CAT_STAY; continue; }
-            cat[q] = CAT_FAR;
-            if (__popc(neg) != 1) continue;
-            const int s = __ffs(neg) - 1;
-            if (pe.nbLocal[s] < 0) continue;
-            // flight LastPartPos -> x crosses side s at lp + alpha (x - lp); every decision with a margin of tol, otherwise the
-            // determinant tests of the exact walk decide
-            const double lp0 = sPs[q], lp1 = sPs[BIN_CHUNK + q], lp2 = sPs[2 * BIN_CHUNK + q];
-            const double dl = fma(pe.pl[s][0], lp0, fma(pe.pl[s][1], lp1, fma(pe.pl[s][2], lp2, -pe.pl[s][3])));
-            if (!(dl > tol)) continue;
-            const double alpha = dl / (dl - dx[s]);
-            bool ok = true;
+            if (ambiguous) cold = true;   // within tol of a side plane: the determinants decide (ParticleInsideQuad3D)
+            else if (neg == 0u) cat = CAT_STAY;
+            else if (__popc(neg) == 1 && pe.nbLocal[__ffs(neg) - 1] >= 0) {
+              const int s = __ffs(neg) - 1;
+              // flight LastPartPos -> x crosses side s at lp + alpha (x - lp); every decision with a margin of tol, otherwise
+              // the determinant tests of the exact walk decide
+              const double dl = fma(pe.pl[s][0], lp0, fma(pe.pl[s][1], lp1, fma(pe.pl[s][2], lp2, -pe.pl[s][3])));
+              const double dxs = fma(pe.pl[s][0], xq[0], fma(pe.pl[s][1], xq[1], fma(pe.pl[s][2], xq[2], -pe.pl[s][3])));   // == dx[s], no dynamic index
+              const double alpha = dl / (dl - dxs);
+              bool ok = dl > tol;
 #pragma unroll
-            for (int o = 0; o < 6; ++o) {
-              const double ol = fma(pe.pl[o][0], lp0, fma(pe.pl[o][1], lp1, fma(pe.pl[o][2], lp2, -pe.pl[o][3])));
-              const double oc = fma(alpha, dx[o] - ol, ol);
-              if (o != s && !(oc > tol)) ok = false;
-            }
-            {
-              const double gl = fma(pe.dg[s][0], lp0, fma(pe.dg[s][1], lp1, fma(pe.dg[s][2], lp2, -pe.dg[s][3])));
-              const double gx = fma(pe.dg[s][0], xn[q][0], fma(pe.dg[s][1], xn[q][1], fma(pe.dg[s][2], xn[q][2], -pe.dg[s][3])));
-              const double gc = fma(alpha, gx - gl, gl);
-              if (!(fabs(gc) > tol)) ok = false;   // crossing point on the triangle diagonal
-            }
-            // clearly inside the neighbour: ParticleInsideQuad3D there succeeds, the walk ends (:215-218)
-            const double ntol = pe.nbtol[s];
+              for (int o = 0; o < 6; ++o) {
+                const double ol = fma(pe.pl[o][0], lp0, fma(pe.pl[o][1], lp1, fma(pe.pl[o][2], lp2, -pe.pl[o][3])));
+                const double oc = fma(alpha, dx[o] - ol, ol);
+                if (o != s && !(oc > tol)) ok = false;
+              }
+              {
+                const double gl = fma(pe.dg[s][0], lp0, fma(pe.dg[s][1], lp1, fma(pe.dg[s][2], lp2, -pe.dg[s][3])));
+                const double gx = fma(pe.dg[s][0], xq[0], fma(pe.dg[s][1], xq[1], fma(pe.dg[s][2], xq[2], -pe.dg[s][3])));
+                const double gc = fma(alpha, gx - gl, gl);
+                if (!(fabs(gc) > tol)) ok = false;   // crossing point on the triangle diagonal
+              }
+              // clearly inside the neighbour: ParticleInsideQuad3D there succeeds, the walk ends (:215-218)
+              const double ntol = pe.nbtol[s];
 #pragma unroll
-            for (int o = 0; o < 6; ++o) {
-              const double dn = fma(pe.nbpl[s][o][0], xn[q][0], fma(pe.nbpl[s][o][1], xn[q][1], fma(pe.nbpl[s][o][2], xn[q][2], -pe.nbpl[s][o][3])));
-              if (!(dn > ntol)) ok = false;
+              for (int o = 0; o < 6; ++o) {
+                const double dn = fma(pe.nbpl[s][o][0], xq[0], fma(pe.nbpl[s][o][1], xq[1], fma(pe.nbpl[s][o][2], xq[2], -pe.nbpl[s][o][3])));
+                if (!(dn > ntol)) ok = false;
+              }
+              if (ok) cat = 1 + s;
             }
-            if (ok) cat[q] = 1 + s;
           }
-        } else {
-          cold[0] = true;
-          cold[1] = nLive > 1;
-        }
+          if (cold) {
+            if (HOTONLY) {   // unpushed to the far list: state as loaded
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (!cold[q]) continue;
-          const ColdRes r = cold_particle<NP, FAST>(sPs[q], sPs[BIN_CHUNK + q], sPs[2 * BIN_CHUNK + q], sPs[3 * BIN_CHUNK + q], sPs[4 * BIN_CHUNK + q],
-                                                    sPs[5 * BIN_CHUNK + q], metaQ[q], sE, geo + (gElem - 1), FAST ? aff + (gElem - 1) : nullptr,
-                                                    FAST ? planes + (gElem - 1) : nullptr, tria + (gElem - 1), E + (size_t)e * ND * 3,
-                                                    Elem_xGP + (size_t)(gElem - 1) * ND * 3, dt);
-          xn[q][0] = r.x0; xn[q][1] = r.x1; xn[q][2] = r.x2; vn[q][0] = r.v0; vn[q][1] = r.v1; vn[q][2] = r.v2;
-          cat[q] = r.left ? CAT_FAR : CAT_STAY;
+              for (int d = 0; d < 3; ++d) { xq[d] = sPs[d * KB_CHUNK + q]; vq[d] = sPs[(3 + d) * KB_CHUNK + q]; }
+              cat = CAT_FAR;
+              unpushed |= 1 << q;
+            } else {
+              const ColdRes r = cold_particle<NP, FAST>(sPs[q], sPs[KB_CHUNK + q], sPs[2 * KB_CHUNK + q], sPs[3 * KB_CHUNK + q], sPs[4 * KB_CHUNK + q],
+                                                        sPs[5 * KB_CHUNK + q], metaQ, sE, geo + (gElem - 1), FAST ? aff + (gElem - 1) : nullptr,
+                                                        FAST ? planes + (gElem - 1) : nullptr, tria + (gElem - 1), E + (size_t)e * ND * 3,
+                                                        Elem_xGP + (size_t)(gElem - 1) * ND * 3, dt);
+              xq[0] = r.x0; xq[1] = r.x1; xq[2] = r.x2; vq[0] = r.v0; vq[1] = r.v1; vq[2] = r.v2;
+              cat = r.left ? CAT_FAR : CAT_STAY;
+            }
+          }
+#pragma unroll
+          for (int d = 0; d < 3; ++d) { sNs[d * KB_CHUNK + q] = xq[d]; sNs[(3 + d) * KB_CHUNK + q] = vq[d]; }
+          cats = q ? ((cats & 0xf) | (cat << 4)) : ((cats & 0xf0) | cat);
         }
       }
       if (c == 0 && nChunks > 1 && warp == 0) publish_next();   // the loads issued at the element's start have long arrived
-      // particle ids (tests) have to be read before the compaction below overwrites the slots of this chunk
-      int64_t id[2] = {0, 0};
+      // particle ids (tests) have to be read before the delivery below overwrites slots of this sweep
+      int64_t id0 = 0, id1 = 0;
       if (bins.id && nLive > 0) {
         const int64_t* sid = poolCur ? pool.id : bins.id;
-        id[0] = sid[slotCur];
-        if (nLive > 1) id[1] = sid[slotCur + 1];
+        id0 = sid[slotCur];
+        if (nLive > 1) id1 = sid[slotCur + 1];
       }
       // ---- stable compaction: rank of every particle within its category in the order of the element's particles (virtual
       //      index 2 * tid + q), chunk by chunk: the order inside an element never changes except by departures and arrivals ----------
       // eight 8-bit counters (one per category, <= 64 particles per warp and sweep) packed in a 64-bit word: one inclusive warp
       // scan yields every particle's rank within its category and the warp's totals
-      int rank[2] = {0, 0};
+      const int cat0 = cats & 0xf, cat1 = cats >> 4;
+      int rank0, rank1;
       {
-        const unsigned long long w0 = cat[0] < 8 ? (1ull << (8 * cat[0])) : 0ull, w1 = cat[1] < 8 ? (1ull << (8 * cat[1])) : 0ull;
+        const unsigned long long w0 = cat0 < 8 ? (1ull << (8 * cat0)) : 0ull, w1 = cat1 < 8 ? (1ull << (8 * cat1)) : 0ull;
         unsigned long long incl = w0 + w1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -911,54 +950,52 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
           if (lane >= o) incl += t;
         }
         const unsigned long long excl = incl - w0 - w1;
-        rank[0] = (int)((excl >> (8 * (cat[0] & 7))) & 0xffull);
-        rank[1] = (int)((excl >> (8 * (cat[1] & 7))) & 0xffull) + (cat[0] == cat[1] ? 1 : 0);
+        rank0 = (int)((excl >> (8 * (cat0 & 7))) & 0xffull);
+        rank1 = (int)((excl >> (8 * (cat1 & 7))) & 0xffull) + (cat0 == cat1 ? 1 : 0);
         const unsigned long long tot = __shfl_sync(0xffffffffu, incl, 31);
         if (lane < 8) sCnt[cb][warp][lane] = (int)((tot >> (8 * lane)) & 0xffull);
       }
-      __syncthreads();
-      int off[2] = {0, 0};
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (cat[q] >= 8) continue;
-        int o = sRun[cb][cat[q]] + rank[q];
-#pragma unroll
-        for (int w = 0; w < BIN_NT / 32; ++w)
-          if (w < warp) o += sCnt[cb][w][cat[q]];
-        off[q] = o;
-      }
+      KB_SYNC();
       if (tid < 8) {
         int t = sRun[cb][tid];
 #pragma unroll
-        for (int w = 0; w < BIN_NT / 32; ++w) t += sCnt[cb][w][tid];
+        for (int w = 0; w < KB_NT / 32; ++w) t += sCnt[cb][w][tid];
         sRun[cb ^ 1][tid] = t;
       }
       // ---- delivery ----------------------------------------------------------------------------------------------------------------
       // stayers -> main, side movers -> the neighbour's inbox, far records -> this element's far region from the bottom (slot =
       // rank among the element's far particles: no atomics); a particle whose region is full -> far region from the top
+#pragma unroll 1
+      for (int q = 0; q < nLive; ++q) {
+        const int cat = q ? cat1 : cat0;
+        int off = sRun[cb][cat] + (q ? rank1 : rank0);
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        if (cat[q] >= 8) continue;
+        for (int w = 0; w < KB_NT / 32; ++w)
+          if (w < warp) off += sCnt[cb][w][cat];
         int64_t dst = -1, fdst = -1;
-        if (cat[q] == CAT_STAY) {
-          if (off[q] < capMain) dst = base_e + off[q];
+        if (cat == CAT_STAY) {
+          if (off < capMain) dst = base_e + off;
           else { fdst = farHi - 1 - atomicAdd(&sDiverted, 1); atomicAdd(&counters[5], 1); }   // main full: through the far list back in
-        } else if (cat[q] <= 6) {
-          if (off[q] < sNbCap[cat[q] - 1]) dst = sNbBase[cat[q] - 1] + off[q];
+        } else if (cat <= 6) {
+          if (off < sNbCap[cat - 1]) dst = sNbBase[cat - 1] + off;
           else { fdst = farHi - 1 - atomicAdd(&sDiverted, 1); atomicAdd(&counters[6], 1); }   // inbox full
-        } else fdst = farLo + off[q];
-        const uint8_t nmeta = (uint8_t)(metaQ[q] & META_SPEC_MASK);   // IsNewPart is consumed by the push
+        } else fdst = farLo + off;
+        const int metaQ = (int)((sM[stg][tid][q] >> (8 * (int)((slotCur + q) & 3))) & 0xffu);
+        // IsNewPart is consumed by the push; an unpushed far record keeps it
+        const uint8_t nmeta = (HOTONLY && ((unpushed >> q) & 1)) ? (uint8_t)((metaQ & (META_SPEC_MASK | META_ISNEW)) | META_UNPUSHED)
+                                                                 : (uint8_t)(metaQ & META_SPEC_MASK);
+        if (HOTONLY && ((unpushed >> q) & 1)) atomicAdd(&counters[7], 1);
         if (dst >= 0) {
 #pragma unroll
-          for (int d = 0; d < 3; ++d) { BF[d * BS + dst] = xn[q][d]; BF[(3 + d) * BS + dst] = vn[q][d]; }
+          for (int a = 0; a < 6; ++a) BF[a * BS + dst] = sNs[a * KB_CHUNK + q];
           bins.meta[dst] = nmeta;
-          if (bins.id) bins.id[dst] = id[q];
+          if (bins.id) bins.id[dst] = q ? id1 : id0;
         } else {
 #pragma unroll
-          for (int d = 0; d < 3; ++d) { far.x[d][fdst] = xn[q][d]; far.lp[d][fdst] = sPs[d * BIN_CHUNK + q]; far.v[d][fdst] = vn[q][d]; }
+          for (int d = 0; d < 3; ++d) { far.x[d][fdst] = sNs[d * KB_CHUNK + q]; far.lp[d][fdst] = sPs[d * KB_CHUNK + q]; far.v[d][fdst] = sNs[(3 + d) * KB_CHUNK + q]; }
           far.elem[fdst] = gElem;
           far.meta[fdst] = nmeta;
-          if (far.id) far.id[fdst] = id[q];
+          if (far.id) far.id[fdst] = q ? id1 : id0;
         }
       }
       nLive = nLiveNext;
@@ -966,7 +1003,7 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
       poolCur = poolNext;
       stg ^= 1;
     }
-    __syncthreads();
+    KB_SYNC();
     // populations after the step: this element's main, and the inboxes this element fills at its face neighbours
     {
       const int fb = nChunks & 1;
@@ -986,8 +1023,29 @@ __global__ void __launch_bounds__(BIN_NT, KB_MINB) k_bin_push(PartBuf bins, Part
         }
       }
     }
-    __syncthreads();
+    KB_SYNC();
   }
+}
+
+// general path for the far records that k_bin_push<.., HOTONLY> handed over unpushed: field at the particle, push (x = pushed
+// position, lp = LastPartPos stays); the walk that follows does the inside test of the own element
+template <int NP>
+__global__ void k_far_unpushed(FarBuf far, const uint32_t* __restrict__ idx, int nFar, const double* __restrict__ Emono, const double* __restrict__ E,
+                               const GeoElem* __restrict__ geo, const AffElem* __restrict__ aff, const PlaneElem* __restrict__ planes,
+                               const TriaElem* __restrict__ tria, const double* __restrict__ Elem_xGP, int offsetElem, double dt) {
+  constexpr int ND = NP * NP * NP;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nFar) return;
+  const int64_t p = idx[i];
+  const int meta = far.meta[p];
+  if (!(meta & META_UNPUSHED)) return;
+  const int g = far.elem[p], e = g - 1 - offsetElem;
+  const ColdRes r = cold_particle<NP, true>(far.x[0][p], far.x[1][p], far.x[2][p], far.v[0][p], far.v[1][p], far.v[2][p], meta & ~META_UNPUSHED,
+                                            Emono + (size_t)e * ND * 3, geo + (g - 1), aff + (g - 1), planes + (g - 1), tria + (g - 1),
+                                            E + (size_t)e * ND * 3, Elem_xGP + (size_t)(g - 1) * ND * 3, dt);
+  far.x[0][p] = r.x0; far.x[1][p] = r.x1; far.x[2][p] = r.x2;
+  far.v[0][p] = r.v0; far.v[1][p] = r.v1; far.v[2][p] = r.v2;
+  far.meta[p] = (uint8_t)(meta & META_SPEC_MASK);
 }
 
 // ---- SingleParticleTriaTracking3D for the far list (particle_triatracking.f90:137-484), from the start -----------------------------

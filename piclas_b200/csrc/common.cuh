@@ -96,5 +96,6 @@ struct PartBuf {
 #define META_SPEC_MASK 0x3F
 #define META_XIFAIL 0x40
 #define META_ISNEW 0x80
+#define META_UNPUSHED 0x40   /* far records of the binned layout only (same bit as META_XIFAIL, which the bins do not use) */
 
 #define KEY_DEAD 0xFFFFFFFFu

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <chrono>
 
 #include "kernels.cuh"
 #include "sf.cuh"
@@ -107,6 +108,7 @@ struct Ctx {
   bool binEligible = false;      // this configuration steps on the bins
   bool binned = false;           // the particles live in the bins (else: sorted arrays buf[cur] + dElemOff)
   bool sortedViewValid = false;  // binned, and buf[0] + dElemOff hold a current copy in sorted order (download, analysis)
+  bool allHot = false;           // every local element affine + planar, B = 0, restructured arithmetic: call-free push kernel
   bool wantRebin = false;        // regions overflowed in the last step: re-plan the capacities before the next one
   PartBuf bins;
   int64_t binSlotsCap = 0;
@@ -1582,7 +1584,12 @@ int piclas_gpu_deposit_finish(double* PartSource, double* NodeSource) {
 }
 
 // the step on the bins: push + delivery, exact walk of the far list, pool for the next step
+static double host_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int push_track_binned(double dt, int32_t* nLost) {
+  const double t0 = host_ms();
   if (ensure_binned()) return 1;
   if (reserve_far(g.nPart, 0)) return 1;   // the far list (in the idle sorted buffers) can take every particle
   if (g.farIdxCap < g.cap) {               // (the sorted buffers may have been sized by an upload)
@@ -1618,18 +1625,36 @@ static int push_track_binned(double dt, int32_t* nLost) {
   CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
   if (ne > 0) CK(cudaMemcpyAsync(&nFar, g.dFarDOff + ne, 8, cudaMemcpyDeviceToHost, g.st));
   CK(cudaStreamSynchronize(g.st));
+  const double t1 = host_ms();
   if (nFar > 0) {
     k_far_index<<<ne < g.nSMs * 16 ? ne : g.nSMs * 16, 128, 0, g.st>>>(g.dFarBase, g.dNFarE, g.dFarDOff, ne, g.dFarIdx);
     ++g.lastLaunches;
+    if (hc[7] > 0) {   // particles the call-free push kernel handed over unpushed
+      switch (g.NP) {
+        case 2: launch_far_unpushed<2>(nFar, dt); break;
+        case 3: launch_far_unpushed<3>(nFar, dt); break;
+        case 4: launch_far_unpushed<4>(nFar, dt); break;
+        case 5: launch_far_unpushed<5>(nFar, dt); break;
+        case 6: launch_far_unpushed<6>(nFar, dt); break;
+        case 7: launch_far_unpushed<7>(nFar, dt); break;
+        case 8: launch_far_unpushed<8>(nFar, dt); break;
+      }
+    }
     launch_far_walk(nFar);
   }
   CK(cudaGetLastError());
   cudaEventRecord(g.evp[4], g.st);
   g.nFar = nFar;
   g.farStats[0] = nFar; g.farStats[1] = hc[4]; g.farStats[2] = hc[5]; g.farStats[3] = hc[6];
-  if (hc[5] > 0 || hc[6] > 0) {
-    g.wantRebin = true;                                      // regions overflowed: capacities from the new populations next time
-    if (hc[6] > 0 && g.inFrac < 0.5) g.inFrac *= 2.0;        // inboxes too small for this flow (drifting populations)
+  {
+    // Particles that met a full region took the far list (correct, only slower).  Re-planning the capacities costs about three
+    // steps, so it waits until the detour is no longer negligible: more than 0.1 % of the particles in one step
+    const int64_t diverted = (int64_t)hc[5] + hc[6];
+    const int64_t limit = g.nPart / 1000 > 1000 ? g.nPart / 1000 : 1000;
+    if (diverted > limit) {
+      g.wantRebin = true;                                      // capacities from the new populations before the next step
+      if (hc[6] > hc[5] && g.inFrac < 0.5) g.inFrac *= 2.0;    // inboxes too small for this flow (drifting populations)
+    }
   }
   g.sortedViewValid = false;
   if (g.nRanks > 1) {
@@ -1642,11 +1667,13 @@ static int push_track_binned(double dt, int32_t* nLost) {
     if (far_finish(nFar)) return 1;
     g.nPart = g.nPart - nFar + (nFar > 0 ? g.hTailOff[0] : 0);
   }
+  const double t2 = host_ms();
   CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
   CK(cudaStreamSynchronize(g.st));
   if (getenv("PICLAS_GPU_DEBUG"))
     fprintf(stderr, "[piclas_gpu] push_track (bins): %lld particles, %d delivered to face neighbours in-kernel, %lld through the far list, "
-            "%d + %d diverted by full regions\n", (long long)g.nPart, (int)g.farStats[1], (long long)nFar, (int)g.farStats[2], (int)g.farStats[3]);
+            "%d + %d diverted by full regions; host ms: push kernel %.2f, walk + far list %.2f, tail %.2f\n", (long long)g.nPart, (int)g.farStats[1],
+            (long long)nFar, (int)g.farStats[2], (int)g.farStats[3], t1 - t0, t2 - t1, host_ms() - t2);
   cudaEventRecord(g.evp[5], g.st);
   end_timing();
   {

@@ -328,6 +328,22 @@ def build_mesh(coords, elem_nodes, N, bcs, bc_of_face, periodic_vectors=(),
     Elem_xGP = np.einsum("qc,ecx->eqx", W, XCL.reshape(nE, 8, 3), optimize=True).reshape(nE, N + 1, N + 1, N + 1, 3)
     Jac = np.einsum("qc,ecx->eqx", W, dXCL.reshape(nE, 8, 9), optimize=True).reshape(nE, N + 1, N + 1, N + 1, 3, 3)
     detJ = _det3(Jac)
+    # metrics.f90:255-372: the reference evaluates DetJac at the Gauss points of degree NGeoRef = 3 NGeo and brings it to the solution
+    # basis with a MODAL Vandermonde matrix (GetVandermonde(..., modal=.TRUE.), interpolation.f90:395-403): for N >= NGeoRef that is the
+    # value at the Gauss point (above); for N < NGeoRef it is the L2 projection onto degree N, which differs on non-parallelepiped
+    # elements.  sJ enters NodeVolume (pic_depo_tools.f90:282-338) and CalcDepositedCharge.
+    NGeoRef = 3
+    if N < NGeoRef:
+        xr, _ = basis.legendre_gauss_nodes_weights(NGeoRef)
+        LGr = np.array([basis.lagrange_polys(x, XiCL, wBaryCL) for x in xr])            # (4, 2)
+        Wr = (LGr[:, None, None, :, None, None] * LGr[None, :, None, None, :, None]
+              * LGr[None, None, :, None, None, :]).reshape((NGeoRef + 1) ** 3, 8)
+        Jr = np.einsum("qc,ecx->eqx", Wr, dXCL.reshape(nE, 8, 9), optimize=True).reshape(nE, NGeoRef + 1, NGeoRef + 1, NGeoRef + 1, 3, 3)
+        detr = _det3(Jr)                                                                  # [e, k, j, i]
+        Vin = np.polynomial.legendre.legvander(xr, NGeoRef)                               # (4, 4) Legendre modes at the input nodes
+        Vout = np.polynomial.legendre.legvander(xGP, N)                                   # (N+1, N+1)
+        P = Vout @ np.linalg.inv(Vin)[:N + 1, :]                                          # Vdm_Leg_Out(0:N,0:N) sVdm_Leg_In(0:N,0:NGeoRef)
+        detJ = np.einsum("ck,bj,ai,ekji->ecba", P, P, P, detr, optimize=True)
     if np.any(detJ <= 0):
         raise ValueError("mesh has elements with non-positive Jacobian")
     sJ = 1.0 / detJ

@@ -148,106 +148,12 @@ class ParticleStepRank:
         return PS, NS
 
 
-# ---- checks of the multi-rank device path inside the benchmark run ------------------------------------------------------------
-def small_parity_check(rank, world, local, arithmetic, steps=3):
-    """The N-rank device path (migration pack / exchange / unpack, node halo sum) against the single-rank CPU oracle on a small
-    box that is partitioned exactly like the benchmark's (z-slabs, periodic wrap between the last and the first rank): every
-    particle's element (exact), position and velocity, and the deposited sources of ALL elements — the rank-boundary slabs
-    included — gathered on rank 0.  The oracle is used here as the checker only (outside every timed region)."""
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    if os.path.join(root, "tests") not in sys.path:
-        sys.path.insert(0, os.path.join(root, "tests"))
-    import cases
-    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (6, 6, 3 * world), 3)
-    prm = cases.electron_params(arithmetic=arithmetic, carryParticleIDs=1)
-    dt = 1e-8
-    n = 150 * mesh.nElems
-    PS, spec = cases.uniform_plasma(mesh, n, seed=4242, vth_cells=0.3, dt=dt)       # identical on every rank
-    elem = hm.cartesian_locate(mesh, PS[:, :3])
-    E = cases.smooth_field(mesh, amp=2e-4)
-    R = ParticleStepRank(mesh, prm, rank, world, local)
-    off = R.offsets
-    mine = (elem > off[rank]) & (elem <= off[rank + 1])
-    ids = np.arange(n, dtype=np.int64)
-    R.step.UploadParticles(PS[mine], spec[mine], elem[mine], IsNewPart=np.ones(int(mine.sum()), dtype=np.int32), ids=ids[mine])
-    R.step.SetField(np.ascontiguousarray(E[int(off[rank]):int(off[rank + 1])]))
-    res = {"ok": True, "ranks": world, "elements": int(mesh.nElems), "particles": int(n), "steps": steps, "migrated": 0,
-           "max_rel_state": 0.0, "max_rel_source": 0.0}
-    if rank == 0:
-        from oracle_lib import Oracle
-        orc = Oracle(mesh, cases.electron_params(arithmetic=arithmetic, carryParticleIDs=1))
-        PSo, elo = PS.copy(), elem.copy()
-        inside = np.ones(n, dtype=np.int32)
-        isnew = np.ones(n, dtype=np.int32)
-    try:
-        for it in range(steps):
-            PSrc, NS = R.Deposition()
-            R.PushAndTrack(dt, it)
-            res["migrated"] += R.migrated
-            d = R.step.DownloadParticles()
-            parts = [None] * world if rank == 0 else None
-            dist.gather_object((d["ids"], d["PartState"], d["GlobalElemID"], PSrc), parts, dst=0)
-            if rank == 0:
-                PSr, _ = orc.deposit(PSo, spec, elo, inside)
-                orc.push_track(dt, PSo, spec, elo, inside, isnew, E)
-                allid = np.concatenate([p[0] for p in parts])
-                o = np.argsort(allid)
-                same_set = len(allid) == n and np.array_equal(allid[o], ids)
-                own_ok = same_set and np.array_equal(np.concatenate([p[2] for p in parts])[o], elo)
-                if same_set:
-                    res["max_rel_state"] = max(res["max_rel_state"],
-                                               float(np.abs(np.concatenate([p[1] for p in parts])[o] - PSo).max() / np.abs(PSo).max()))
-                src = np.concatenate([p[3] for p in parts])
-                for c in range(4):
-                    res["max_rel_source"] = max(res["max_rel_source"], float(np.abs(src[..., c] - PSr[..., c]).max() / np.abs(PSr[..., c]).max()))
-                res["ok"] = bool(res["ok"] and same_set and own_ok and res["max_rel_state"] <= 1e-12 and res["max_rel_source"] <= 1e-12)
-                res["ownership_exact"] = bool(own_ok)
-    except Exception as e:   # a failed check must not cost the measurement
-        res = {"ok": False, "error": repr(e)[:300]}
-    R.close()
-    if rank == 0:
-        orc.close()
-    tot = torch.tensor([res.get("migrated", 0)], dtype=torch.int64, device="cuda")
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    res["migrated"] = int(tot.item())
-    return res
-
-
-def full_size_checks_multi(R, mesh, n_expected, charge_per_particle, rank, world):
-    """Size-independent properties of the N-rank run at the benchmark's full size, outside the timed regions: particle count
-    conserved over the ranks, deposited charge after the node halo sum (CalcDepositedCharge, pic_analyze.f90:165-175, summed over the
-    ranks' elements) against the particles' charge, every particle in the device reductions."""
-    try:
-        import bench as B
-        n1 = mesh.N + 1
-        off = R.offsets
-        nloc = int(off[rank + 1] - off[rank])
-        R.Deposition(want_partsource=False, want_nodesource=False)
-        rho = np.empty((nloc, n1, n1, n1))
-        R.step.ChargeDensity(out=rho)
-        w = mesh.wGP[:, None, None] * mesh.wGP[None, :, None] * mesh.wGP[None, None, :]
-        q_loc = float(np.sum(rho * w[None] / mesh.sJ[int(off[rank]):int(off[rank + 1])]))
-        ekin, npart = R.step.KineticEnergy()
-        t = torch.tensor([q_loc, float(R.step.NumParticles()), float(npart.sum()), float(ekin.sum())], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        q_dep, n_now, n_red, ek = [float(v) for v in t.tolist()]
-        q_part = n_expected * charge_per_particle
-        return {"particles": int(n_now), "particles_expected": int(n_expected), "particles_in_reduction": int(n_red),
-                "deposited_charge": q_dep, "particle_charge": q_part, "charge_conservation_rel_err": abs(q_dep - q_part) / abs(q_part),
-                "kinetic_energy_J": ek,
-                "ok": bool(int(n_now) == int(n_expected) and int(n_red) == int(n_now) and abs(q_dep - q_part) <= 1e-12 * abs(q_part)
-                           and np.isfinite(ek))}
-    except Exception as e:
-        return {"ok": False, "error": repr(e)[:300]}
-
-
 # ---- bench.py --gpus N (N > 1) -------------------------------------------------------------------------------------------
 def run_bench_multi(args, rank, world, local):
     import bench as B
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    parity = small_parity_check(rank, world, local, args.arithmetic) if not getattr(args, "no_checks", False) else None
+    parity = B.small_parity_check(rank, world, local, args.arithmetic) if not getattr(args, "no_checks", False) else None
     mesh, E, dt, vth = B.workload(args.nelem, args.N)
     n_total = int(args.particles)
     prm = Params(ChargeIC=(-B.QE,), MassIC=(B.ME,), MacroParticleFactor=(1.0e3,), device=local, arithmetic=args.arithmetic)
@@ -333,9 +239,9 @@ def run_bench_multi(args, rank, world, local):
         e2e = {"value": n_total * args.e2e_steps / float(te.item()), "unit": "particle-steps/s",
                "h2d_bytes_per_step": int(E.nbytes), "d2h_bytes_per_step": int(mesh.nElems * n1 ** 3 * 4 * 8),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps}
-    checks = full_size_checks_multi(R, mesh, n_total, -B.QE * 1.0e3, rank, world)
+    checks = B.full_size_checks_multi(R, mesh, n_total, -B.QE * 1.0e3, rank, world)
     if parity is not None:
-        checks["oracle_parity_small"] = parity
+        checks["parity_small_case"] = parity
         checks["ok"] = bool(checks.get("ok") and parity.get("ok"))
     R.close()
     if rank == 0:
@@ -350,7 +256,7 @@ def run_bench_multi(args, rank, world, local):
                 "dtype": "f64", "data": "synthetic", "config": B.config_dict(args, n_total), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(cnt[2].item()), "particles_end": int(cnt[0].item()),
                 "migrated_per_step": int(cnt[1].item()) // max(args.steps, 1),
-                "roofline": {"bound": "hbm", "kernel": "k_interp_push + k_track_leavers (per GPU, slowest rank)",
+                "roofline": {"bound": "hbm", "kernel": "k_bin_push + k_far_walk (per GPU, slowest rank)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": B.measured_traffic(per_gpu)[0],
                              "traffic_source": B.measured_traffic(per_gpu)[1],
                              "peak_source": peak_src,

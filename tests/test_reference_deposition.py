@@ -28,7 +28,7 @@ from piclas_b200.abi import Params, TIMEDISC_LEAPFROG, DEPO_CVWM
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden", "cvwm_current_reference.npz")
 QE = 1.60217653E-19
-RTOL = 5e-12
+RTOL = 2e-12   # measured 1.5e-12 (current) / 1.0e-12 (charge) with the reference's modal DetJac projection (hostmesh), 2e-12 before
 BCS = ("BC_WALL", "BC_WALL_INLET", "BC_WALL_PUMP", "BC_SUBSTRAT", "BC_ELECTRODE", "BC_SYMMETRY")
 
 

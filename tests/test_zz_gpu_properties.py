@@ -59,7 +59,15 @@ def test_conservation_ownership_layout_and_idempotence(arith):
             dist = np.abs(x[off] / h - np.round(x[off] / h)).min(axis=1) * h
             assert dist.max() <= 1e-12, "a particle is not in the element that contains its position"
         assert np.sort(d["PartState"][:, 3:], axis=0).tobytes() == np.sort(PS[:, 3:], axis=0).tobytes()   # velocities only permuted
-        # a step of zero length changes nothing, bit for bit (stable sort, same keys)
+        # a step of zero length changes no particle and no ownership, bit for bit.  The storage order inside an element is kept as
+        # well, except for the few particles within 1e-8 element diameters of an element face: the call-free push kernel hands
+        # those to the exact tracking path, from which they return behind the others of their element
         assert gpu.PushAndTrack(0.0, 99) == 0
         d2 = gpu.DownloadParticles()
-        assert np.array_equal(d2["PartState"], d["PartState"]) and np.array_equal(d2["GlobalElemID"], d["GlobalElemID"])
+        assert np.array_equal(d2["GlobalElemID"], d["GlobalElemID"])
+        same = (d2["PartState"] == d["PartState"]).all(axis=1)
+        assert same.mean() > 0.999
+        def canon(dd):
+            a = np.concatenate([dd["GlobalElemID"][:, None].astype(np.float64), dd["PartState"]], axis=1)
+            return a[np.lexsort(a.T[::-1])]
+        assert np.array_equal(canon(d2), canon(d))
