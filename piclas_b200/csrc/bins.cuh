@@ -154,6 +154,35 @@ __device__ __forceinline__ void resolve(const ElemRanges& R, int v, int& r, int6
   left = R.cnt[r] - o;
 }
 
+// ranges of element e by lanes 0..7 of one warp: loads, padded prefix by shuffles, result into shared memory
+struct RangeRegs { int64_t start; int cnt; };
+__device__ __forceinline__ RangeRegs range_load(const BinView& bv, int e, int cur, int lane) {
+  RangeRegs r;
+  r.start = 0;
+  r.cnt = 0;
+  if (lane < BIN_NRANGE) {
+    if (lane == 0) { r.start = bv.base[e]; r.cnt = bv.nMain[e]; }
+    else if (lane < 7) { r.start = bin_inbox_base(bv, e, cur, lane - 1); r.cnt = bv.nIn[((size_t)cur * bv.nElems + e) * 8 + (lane - 1)]; }
+    else { const int64_t* po = cur ? bv.poolOff[1] : bv.poolOff[0]; r.start = po[e]; r.cnt = (int)(po[e + 1] - r.start); }
+  }
+  return r;
+}
+__device__ __forceinline__ void range_store(ElemRanges& R, const RangeRegs& r, int lane) {   // whole warp calls
+  const int padded = (r.cnt + 1) & ~1;
+  int incl = padded;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane < BIN_NRANGE) {
+    R.start[lane] = r.start;
+    R.cnt[lane] = r.cnt;
+    R.pre[lane] = incl - padded;
+    if (lane == BIN_NRANGE - 1) R.pre[BIN_NRANGE] = incl;
+  }
+}
+
 // ---- layout construction -------------------------------------------------------------------------------------------------------
 // capacities from the element populations (segment offsets of the sorted arrays): main = n + slack, side inbox = fraction of n
 __global__ void k_bin_plan(const int64_t* __restrict__ elemOff, int nElems, double mainSlack, double inFrac, int32_t* __restrict__ capMain,
@@ -315,8 +344,10 @@ __global__ void __launch_bounds__(BIN_NT) k_bin_gather(PartBuf bins, PartBuf poo
 // eight ranges in order.  No reference position is stored: the interpolation of the same step recomputes it (closed form on
 // affine elements, the reference's second Newton call otherwise, pic_interpolation_tools.f90:241).
 // general path of the deposition for one slot of the bins / pool arrays (no cached reference position)
+constexpr int DB_NT = 32;   // one warp per CTA: no block barriers, the 32 sums of an element leave the warp by a shuffle reduce-scatter
+typedef double DepAccW[32][DB_NT];
 __device__ __noinline__ void deposit_slot_cold(const double* __restrict__ f, int64_t stride, uint8_t meta, int64_t p, const GeoElem* sg,
-                                               const double (*corner)[3], DepAcc* sAcc, int tid) {
+                                               const double (*corner)[3], DepAccW* sAcc, int tid) {
   PartBuf pb;
   pb.f = const_cast<double*>(f);
   pb.xif = nullptr;
@@ -325,51 +356,38 @@ __device__ __noinline__ void deposit_slot_cold(const double* __restrict__ f, int
   deposit_particle_general(pb, p, sg, corner, *sAcc, tid);
 }
 
+// ---- cell_volweight_mean particle loop on the bins (DepositionMethod_CVWM, pic_depo_method.f90:471-544) -----------------------------
+// Same arithmetic as k_deposit_cvwm (kernels.cuh); the particles of the element are the eight ranges in order, two particles per
+// thread and sweep on 128-bit copies.  The 32 element sums (8 nodes x 4 components) are reduced over the warp in a fixed
+// pattern (deterministic).  No reference position is stored: the interpolation of the same step recomputes it (closed form on
+// affine elements, the reference's second Newton call otherwise, pic_interpolation_tools.f90:241).
 template <bool FAST>
-__global__ void __launch_bounds__(BIN_NT, DEP_MINB) k_bin_deposit_cvwm(PartBuf bins, PartBuf pool, BinView bv, int cur, int offsetElem,
-                                                                       const GeoElem* __restrict__ geo, const TriaElem* __restrict__ tria,
-                                                                       const AffElem* __restrict__ aff, double* __restrict__ elemAcc) {
+__global__ void __launch_bounds__(DB_NT, 16) k_bin_deposit_cvwm(PartBuf bins, PartBuf pool, BinView bv, int cur, int offsetElem,
+                                                                const GeoElem* __restrict__ geo, const TriaElem* __restrict__ tria,
+                                                                const AffElem* __restrict__ aff, double* __restrict__ elemAcc) {
   __shared__ ElemRanges R;
   __shared__ GeoElem sg;
   __shared__ AffElem sa;
   __shared__ double corner[8][3];
-  // the per-thread accumulators of the general path / of the final reduction and the staging slots of the fast path are never
-  // live at the same time: one buffer
-  typedef double StageBuf[2][6][2 * BIN_NT];
-  __shared__ __align__(16) unsigned char sBuf[sizeof(DepAcc) > sizeof(StageBuf) ? sizeof(DepAcc) : sizeof(StageBuf)];
-  DepAcc& sAcc = *reinterpret_cast<DepAcc*>(sBuf);
+  // the accumulators of the general path and the staging slots of the fast path are never live at the same time: one buffer
+  typedef double StageBuf[2][6][2 * DB_NT];
+  __shared__ __align__(16) unsigned char sBuf[sizeof(DepAccW) > sizeof(StageBuf) ? sizeof(DepAccW) : sizeof(StageBuf)];
+  DepAccW& sAcc = *reinterpret_cast<DepAccW*>(sBuf);
   StageBuf& sP = *reinterpret_cast<StageBuf*>(sBuf);
-  __shared__ uint32_t sM[2][BIN_NT][2];
-  const int tid = threadIdx.x;
+  __shared__ uint32_t sM[2][DB_NT][2];
+  const int tid = threadIdx.x, lane = tid;
   for (int e = blockIdx.x; e < bv.nElems; e += gridDim.x) {
-    __syncthreads();
-    load_ranges(R, bv, e, cur, tid);
+    __syncwarp();
+    range_store(R, range_load(bv, e, cur, lane), lane);
     if (FAST) stage_words(&sa, aff + (offsetElem + e), sizeof(AffElem));
-    __syncthreads();
-    if (tid == 0) prefix_ranges(R);
-    __syncthreads();
+    __syncwarp();
     const int total = R.pre[BIN_NRANGE];
     const bool fastElem = FAST && sa.affine != 0.0;
-    if (!fastElem && total > 0) {
-      stage_words(&sg, geo + (offsetElem + e), sizeof(GeoElem));
-      if (tid < 24) corner[tid / 3][tid % 3] = tria[offsetElem + e].corner[tid / 3][tid % 3];
-      __syncthreads();
-    }
     double acc[32];
 #pragma unroll
     for (int a = 0; a < 32; ++a) acc[a] = 0.;
-    if (!fastElem) {
-#pragma unroll
-      for (int a = 0; a < 32; ++a) sAcc[a][tid] = 0.;
-    }
     int nGeneral = 0;
-    auto src_of = [&](int v, int& r, int64_t& slot, bool& live) {
-      int left;
-      resolve(R, v, r, slot, left);
-      live = left > 0;
-    };
     if (fastElem) {
-      // two particles per thread and sweep: one 128-bit copy per array and thread, meta bytes through their aligned words
       int stage = 0, nLive = 0, nLiveNext = 0, sh = 0, shNext = 0;
       auto fetch2 = [&](int v, int stg, int& nl, int& shifts) {
         nl = 0;
@@ -401,8 +419,8 @@ __global__ void __launch_bounds__(BIN_NT, DEP_MINB) k_bin_deposit_cvwm(PartBuf b
       };
       fetch2(2 * tid, 0, nLive, sh);
       cp_async_commit();
-      for (int v = 2 * tid; v < total; v += 2 * BIN_NT, stage ^= 1, nLive = nLiveNext, sh = shNext) {
-        fetch2(v + 2 * BIN_NT, stage ^ 1, nLiveNext, shNext);
+      for (int v = 2 * tid; v < total; v += 2 * DB_NT, stage ^= 1, nLive = nLiveNext, sh = shNext) {
+        fetch2(v + 2 * DB_NT, stage ^ 1, nLiveNext, shNext);
         cp_async_commit();
         cp_async_wait_prev();
 #pragma unroll
@@ -426,25 +444,25 @@ __global__ void __launch_bounds__(BIN_NT, DEP_MINB) k_bin_deposit_cvwm(PartBuf b
             for (int c = 0; c < 4; ++c) acc[n * 4 + c] = fma(T[c], w[n], acc[n * 4 + c]);
         }
       }
-      __syncthreads();   // every thread is done with its staging slots before the buffer takes the accumulators
+    }
+    if (!fastElem || __any_sync(0xffffffffu, nGeneral != 0)) {
+      // general path (Newton; inverse-distance fallback): accumulators in shared memory so that the iteration keeps the registers
+      __syncwarp();   // every lane is done with its staging slots before the buffer takes the accumulators
 #pragma unroll
       for (int a = 0; a < 32; ++a) sAcc[a][tid] = acc[a];
-    }
-    if (!fastElem || __syncthreads_or(nGeneral)) {
-      if (fastElem) {   // (never observed) particles far outside their affine element: general path in a second sweep
+      if (total > 0) {
         stage_words(&sg, geo + (offsetElem + e), sizeof(GeoElem));
         if (tid < 24) corner[tid / 3][tid % 3] = tria[offsetElem + e].corner[tid / 3][tid % 3];
-        __syncthreads();
       }
-      for (int v = tid; v < total; v += BIN_NT) {
-        int r;
+      __syncwarp();
+      for (int v = tid; v < total; v += DB_NT) {
+        int r, left;
         int64_t slot;
-        bool live;
-        src_of(v, r, slot, live);
-        if (!live) continue;
+        resolve(R, v, r, slot, left);
+        if (left <= 0) continue;
         const double* sf = (r == 7) ? pool.f : bins.f;
         const int64_t sst = (r == 7) ? pool.stride : bins.stride;
-        if (fastElem) {
+        if (fastElem) {   // (never observed) particles far outside their affine element only
           const double x[3] = {sf[slot], sf[sst + slot], sf[2 * sst + slot]};
           double xi[3];
           if (affine_xi(&sa, x, xi)) continue;
@@ -452,18 +470,23 @@ __global__ void __launch_bounds__(BIN_NT, DEP_MINB) k_bin_deposit_cvwm(PartBuf b
         asm volatile("" ::: "memory");
         deposit_slot_cold(sf, sst, ((r == 7) ? pool.meta : bins.meta)[slot], slot, &sg, corner, &sAcc, tid);
       }
-    }
-    __syncthreads();
-    {
-      const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll 1
-      for (int a = warp * 8; a < warp * 8 + 8; ++a) {
-        double v = ((sAcc[a][lane] + sAcc[a][lane + 32]) + sAcc[a][lane + 64]) + sAcc[a][lane + 96];
+      __syncwarp();
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = v + __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) elemAcc[(size_t)e * 32 + a] = v;
+      for (int a = 0; a < 32; ++a) acc[a] = sAcc[a][tid];
+    }
+    // reduce-scatter over the warp: after the step with offset o every lane keeps the half of its values whose index has bit o
+    // equal to the lane's; lane L ends with the element's sum number L.  Fixed pattern: the result does not depend on scheduling.
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const double send = up ? acc[i] : acc[i + o];
+        const double keep = up ? acc[i + o] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
       }
     }
+    elemAcc[(size_t)e * 32 + lane] = acc[0];
   }
 }
 
@@ -477,10 +500,11 @@ __global__ void __launch_bounds__(BIN_NT, DEP_MINB) k_bin_deposit_cvwm(PartBuf b
 // share every shared-memory operand (128-bit loads, one LDS feeds four FMAs).
 template <int NP>
 __device__ __forceinline__ void evaluate_field_mono2(const double xi[2][3], const double* __restrict__ sA, double out[2][3]) {
+  static_assert(NP >= 2, "N >= 1");
   double o[2][3] = {{0., 0., 0.}, {0., 0., 0.}};
 #pragma unroll 1
   for (int k = NP - 1; k >= 0; --k) {
-    double s[2][3] = {{0., 0., 0.}, {0., 0., 0.}};
+    double s[2][3];
 #pragma unroll MONO_UJ
     for (int j = NP - 1; j >= 0; --j) {
       const double* row = sA + ((k * NP + j) * NP) * 3;   // [i][c], NP * 3 doubles
@@ -493,11 +517,15 @@ __device__ __forceinline__ void evaluate_field_mono2(const double xi[2][3], cons
 #pragma unroll
         for (int m = 0; m < NP * 3; ++m) u[m] = row[m];
       }
+      // Horner in xi; the first step takes both coefficients straight from the tile (no copy of the leading one)
       double r[2][3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { r[0][c] = u[(NP - 1) * 3 + c]; r[1][c] = u[(NP - 1) * 3 + c]; }
+      for (int c = 0; c < 3; ++c) {
+        r[0][c] = fma(u[(NP - 1) * 3 + c], xi[0][0], u[(NP - 2) * 3 + c]);
+        r[1][c] = fma(u[(NP - 1) * 3 + c], xi[1][0], u[(NP - 2) * 3 + c]);
+      }
 #pragma unroll
-      for (int i = NP - 2; i >= 0; --i)
+      for (int i = NP - 3; i >= 0; --i)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           r[0][c] = fma(r[0][c], xi[0][0], u[i * 3 + c]);
@@ -505,8 +533,8 @@ __device__ __forceinline__ void evaluate_field_mono2(const double xi[2][3], cons
         }
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        s[0][c] = fma(s[0][c], xi[0][1], r[0][c]);
-        s[1][c] = fma(s[1][c], xi[1][1], r[1][c]);
+        if (j == NP - 1) { s[0][c] = r[0][c]; s[1][c] = r[1][c]; }
+        else { s[0][c] = fma(s[0][c], xi[0][1], r[0][c]); s[1][c] = fma(s[1][c], xi[1][1], r[1][c]); }
       }
     }
 #pragma unroll
@@ -640,35 +668,6 @@ __device__ __forceinline__ void push_inline_b0(double x[3], double v[3], const d
 }
 
 constexpr int CAT_STAY = 0, CAT_FAR = 7, CAT_NONE = 8;
-
-// ranges of element e by lanes 0..7 of one warp: loads, padded prefix by shuffles, result into shared memory
-struct RangeRegs { int64_t start; int cnt; };
-__device__ __forceinline__ RangeRegs range_load(const BinView& bv, int e, int cur, int lane) {
-  RangeRegs r;
-  r.start = 0;
-  r.cnt = 0;
-  if (lane < BIN_NRANGE) {
-    if (lane == 0) { r.start = bv.base[e]; r.cnt = bv.nMain[e]; }
-    else if (lane < 7) { r.start = bin_inbox_base(bv, e, cur, lane - 1); r.cnt = bv.nIn[((size_t)cur * bv.nElems + e) * 8 + (lane - 1)]; }
-    else { const int64_t* po = cur ? bv.poolOff[1] : bv.poolOff[0]; r.start = po[e]; r.cnt = (int)(po[e + 1] - r.start); }
-  }
-  return r;
-}
-__device__ __forceinline__ void range_store(ElemRanges& R, const RangeRegs& r, int lane) {   // whole warp calls
-  const int padded = (r.cnt + 1) & ~1;
-  int incl = padded;
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane < BIN_NRANGE) {
-    R.start[lane] = r.start;
-    R.cnt[lane] = r.cnt;
-    R.pre[lane] = incl - padded;
-    if (lane == BIN_NRANGE - 1) R.pre[BIN_NRANGE] = incl;
-  }
-}
 
 // HOTONLY: every local element is affine with planar sides, B = 0, restructured arithmetic.  The kernel then contains no call at
 // all (a call anywhere in the loop makes the compiler keep the loop's state in local memory: 340 bytes of spills per thread); the

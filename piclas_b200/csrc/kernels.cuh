@@ -66,8 +66,9 @@ __device__ __forceinline__ void cp_async_wait_prev() { asm volatile("cp.async.wa
 typedef double DepAcc[32][STEP_NT];
 
 // one particle through the general path.  x, xi: position and (output) reference position
+template <int NT>
 __device__ __forceinline__ void deposit_particle_general(const PartBuf& pb, int64_t p, const GeoElem* sg, const double (*corner)[3],
-                                                         DepAcc& sAcc, int tid) {
+                                                         double (&sAcc)[32][NT], int tid) {
   double* __restrict__ const PF = pb.f;
   double* __restrict__ const PXI = pb.xif;
   const int64_t PS_ = pb.stride;

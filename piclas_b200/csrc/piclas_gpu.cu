@@ -10,6 +10,8 @@
 #include <vector>
 #include <chrono>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "kernels.cuh"
 #include "sf.cuh"
 #include "ref.cuh"
@@ -133,6 +135,13 @@ struct Ctx {
 
 Ctx g;
 std::string g_err;
+
+// NVTX ranges named after the reference's load-balance sections (LB_* of piclas.h:298-321, loadbalance_timers.f90:70-266), so that
+// an nsys / ncu timeline of the host shows the same sections the Fortran timers report (header-only NVTX3: no library to link)
+struct LbRange {
+  explicit LbRange(const char* name) { nvtxRangePushA(name); }
+  ~LbRange() { nvtxRangePop(); }
+};
 
 int fail(const char* fmt, ...) {
   char buf[1024];
@@ -1282,13 +1291,14 @@ int piclas_gpu_set_field(const double* E) {
 static int deposit_local() {
   const int grid = g.nElems < g.nSMs * 8 ? g.nElems : g.nSMs * 8;
   if (g.binEligible && ensure_binned()) return 1;
+  const int gridB = g.nElems < g.nSMs * 16 ? g.nElems : g.nSMs * 16;   // k_bin_deposit_cvwm: one warp per CTA, 16 CTAs per SM
   cudaEventRecord(g.evp[0], g.st);
   if (grid > 0 && g.binned) {
     if (g.fast)
-      k_bin_deposit_cvwm<true><<<grid, BIN_NT, 0, g.st>>>(g.bins, g.pool[g.binParity], bin_view(), g.binParity, g.offsetElem, g.dGeo, g.dTria, g.dAff,
+      k_bin_deposit_cvwm<true><<<gridB, DB_NT, 0, g.st>>>(g.bins, g.pool[g.binParity], bin_view(), g.binParity, g.offsetElem, g.dGeo, g.dTria, g.dAff,
                                                          g.dElemAcc);
     else
-      k_bin_deposit_cvwm<false><<<grid, BIN_NT, 0, g.st>>>(g.bins, g.pool[g.binParity], bin_view(), g.binParity, g.offsetElem, g.dGeo, g.dTria, g.dAff,
+      k_bin_deposit_cvwm<false><<<gridB, DB_NT, 0, g.st>>>(g.bins, g.pool[g.binParity], bin_view(), g.binParity, g.offsetElem, g.dGeo, g.dTria, g.dAff,
                                                           g.dElemAcc);
     ++g.lastLaunches;
   } else if (grid > 0) {
@@ -1380,6 +1390,7 @@ static int deposit_sf(double* PartSource) {
 }
 
 int piclas_gpu_deposit(double* PartSource, double* NodeSource) {
+  LbRange lb("LB_DEPO_SF: Deposition");
   if (!g.ready) return fail("piclas_gpu_deposit: not initialised");
   if (!g.prm.DoDeposition) return fail("piclas_gpu_deposit: PIC-DoDeposition=F");
   if (g.exchangePending) return fail("piclas_gpu_deposit: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
@@ -1554,6 +1565,7 @@ int piclas_gpu_sf_halo_info(int64_t* nSendElemsPerRank, int64_t* nRecvElemsPerRa
 }
 
 int piclas_gpu_deposit_finish(double* PartSource, double* NodeSource) {
+  LbRange lb("LB_DEPO_SF: halo sum + node -> DOF");
   if (!g.ready) return fail("piclas_gpu_deposit_finish: not initialised");
   CK(cudaSetDevice(g.device));
   if (g.sfActive) {
@@ -1650,7 +1662,8 @@ static int push_track_binned(double dt, int32_t* nLost) {
     // Particles that met a full region took the far list (correct, only slower).  Re-planning the capacities costs about three
     // steps, so it waits until the detour is no longer negligible: more than 0.1 % of the particles in one step
     const int64_t diverted = (int64_t)hc[5] + hc[6];
-    const int64_t limit = g.nPart / 1000 > 1000 ? g.nPart / 1000 : 1000;
+    int64_t limit = g.nPart / 1000 > 1000 ? g.nPart / 1000 : 1000;
+    if (const char* v = getenv("PICLAS_GPU_REBIN_MIN")) limit = atoll(v);   // tests: re-plan on the first diverted particle
     if (diverted > limit) {
       g.wantRebin = true;                                      // capacities from the new populations before the next step
       if (hc[6] > hc[5] && g.inFrac < 0.5) g.inFrac *= 2.0;    // inboxes too small for this flow (drifting populations)
@@ -1691,6 +1704,7 @@ static int push_track_binned(double dt, int32_t* nLost) {
 }
 
 int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
+  LbRange lb("LB_INTERPOLATION + LB_PUSH + LB_TRACK + LB_UNFP: push_track");
   (void)iter;
   if (!g.ready) return fail("piclas_gpu_push_track: not initialised");
   CK(cudaSetDevice(g.device));
@@ -1744,6 +1758,7 @@ int piclas_gpu_push_track(double dt, int64_t iter, int32_t* nLost) {
 }
 
 int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void** devSendBuf) {
+  LbRange lb("LB_PARTCOMM: emigrant extraction + pack");
   if (!g.ready) return fail("piclas_gpu_exchange_info: not initialised");
   CK(cudaSetDevice(g.device));
   if (partCommSize) *partCommSize = g.commSize;
@@ -1819,6 +1834,7 @@ int piclas_gpu_exchange_recv_buffer(int64_t nRecvTotal, void** devRecvBuf) {
 }
 
 int piclas_gpu_exchange_finish(int64_t nRecvTotal) {
+  LbRange lb("LB_PARTCOMM + LB_UNFP: unpack + far list sort");
   if (!g.ready) return fail("piclas_gpu_exchange_finish: not initialised");
   CK(cudaSetDevice(g.device));
   if (!g.exchangePending) {

@@ -370,3 +370,24 @@ def test_flagship_density_against_oracle():
             pp = np.abs(d["PartState"][:, :3] - PSo[:, :3]) / np.maximum(np.abs(PSo[:, :3]), 1e-3)
             assert pp.max() <= 1e-11
     orc.close()
+
+
+@pytest.mark.parametrize("rebin_min", ["1", "1000000"], ids=["replan", "detour-only"])
+def test_full_regions_are_diverted_and_replanned(monkeypatch, rebin_min):
+    """Binned layout with no slack at all (main regions exactly as large as the initial populations, 32-slot inboxes) under a strong
+    drift: stayers and movers meet full regions every step, take the far list instead ("detour-only"), and the capacities are re-planned
+    from the new populations ("replan").  Ownership, positions, velocities and sources must not notice."""
+    monkeypatch.setenv("PICLAS_GPU_BIN_MAIN_SLACK", "-0.03")
+    monkeypatch.setenv("PICLAS_GPU_BIN_INBOX_FRAC", "0.0")
+    monkeypatch.setenv("PICLAS_GPU_REBIN_MIN", rebin_min)
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (4, 4, 3), 2)
+    prm = cases.electron_params(arithmetic=1)
+    dt = 1e-8
+    PS, spec = cases.uniform_plasma(mesh, 60000, seed=31, vth_cells=0.25, dt=dt)
+    PS[:, 3] += 0.45 * 0.25 / dt          # drift of 0.45 cells per step along x
+    # a density bump: the populations of the elements change from step to step
+    PS[::3, 0] = 0.5 + 0.2 * (PS[::3, 0] - 0.5)
+    E = cases.smooth_field(mesh, amp=2.0e-4)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    w = run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=6)
+    print("worst rel diffs", w)
