@@ -199,6 +199,11 @@ int piclas_gpu_download_particles(int64_t nmax, double *PartState, int32_t *Part
  * migrates; deposit / download / the next push_track fail while the step is open. */
 int piclas_gpu_exchange_info(int32_t *partCommSize, int64_t *nSendPerRank /*[nRanks]*/, void **devSendBuf);
 int piclas_gpu_exchange_recv_buffer(int64_t nRecvTotal, void **devRecvBuf);
+/* Optional, for transports that work on device memory throughout: after exchange_info, devSendCounts is int64[nRanks] ON THE
+ * DEVICE (the counts of nSendPerRank), so that the count exchange (IRecvNbOfParticles / SendNbOfParticles) needs no host->device
+ * copy; sendCap / recvCapDoubles are the current capacities of the send / receive buffers in doubles (a caller may wrap the
+ * buffers once and slice). */
+int piclas_gpu_exchange_device_info(void **devSendCounts, int64_t *sendCapDoubles, int64_t *recvCapDoubles);
 int piclas_gpu_exchange_finish(int64_t nRecvTotal);
 
 /* ---- cell_volweight_mean node halo (replaces pic_depo_method.f90:565-673) ------------------------------

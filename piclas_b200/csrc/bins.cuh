@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(KB_NT, KB_MINB) k_bin_push(PartBuf bins, PartB
             for (int s = 0; s < 6; ++s) {
               dx[s] = fma(pe.pl[s][0], xq[0], fma(pe.pl[s][1], xq[1], fma(pe.pl[s][2], xq[2], -pe.pl[s][3])));
               ambiguous |= fabs(dx[s]) <= tol;
-              neg |= (dx[s] < 0.) ? (1u << s) : 0u;
+              neg |= ((uint32_t)__double2hiint(dx[s]) >> 31) << s;   // sign bit (a zero of either sign is ambiguous anyway)
             }
             if (ambiguous) cold = true;   // within tol of a side plane: the determinants decide (ParticleInsideQuad3D)
             else if (neg == 0u) cat = CAT_STAY;
@@ -1053,7 +1053,8 @@ __global__ void k_far_unpushed(FarBuf far, const uint32_t* __restrict__ idx, int
 template <bool FAST>
 __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, const uint32_t* __restrict__ idx, int nFar, const TriaElem* __restrict__ tria,
                                                              const PlaneElem* __restrict__ planes, const int32_t* __restrict__ elemRank,
-                                                             uint32_t* __restrict__ keys, int nElems, int offsetElem, int* __restrict__ counters) {
+                                                             uint32_t* __restrict__ keys, int nElems, int offsetElem, int* __restrict__ counters,
+                                                             int* __restrict__ emigCnt /*[nRanks] emigrants per destination rank, or null*/) {
   const int lane = threadIdx.x & 31;
   bool active = false;
   int p = 0, dense = 0, ElemID = 0, guard = 0;
@@ -1105,6 +1106,7 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, const u
         if (status == TRK_OK) {
           const int rk = (cst.nRanks == 1) ? cst.myRank : elemRank[newElem - 1];
           key = (rk == cst.myRank) ? (uint32_t)(newElem - 1 - offsetElem) : (uint32_t)(nElems + rk);
+          if (rk != cst.myRank && emigCnt) atomicAdd(&emigCnt[rk], 1);
         } else {
           key = (uint32_t)(nElems + cst.nRanks);
           newElem = 0;

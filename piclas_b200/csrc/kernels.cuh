@@ -848,7 +848,7 @@ __global__ void __launch_bounds__(STEP_NT, KA_MINB) k_interp_push(PartBuf pb, do
 // that were not localised in a face neighbour (edge / corner crossings, multi-element flights).
 constexpr int LV_NT = 128;
 #ifndef LV_MINB
-#define LV_MINB 4
+#define LV_MINB 5
 #endif
 
 template <bool FAST>

@@ -106,6 +106,10 @@ struct Ctx {
   double *dHaloSend = nullptr, *dHaloRecv = nullptr;   // [nHaloNodes][4], [nRanks][nHaloNodes][4]
   bool haloPacked = false;
   bool ownStream = true;
+  int64_t* hPin = nullptr;          // pinned host words for the small device->host readbacks of a step (counters, offsets)
+  int64_t* dSendCounts = nullptr;   // [nRanks] emigrant counts of the open step on the device (for a device-side count exchange)
+  int* dEmigCnt = nullptr;          // [nRanks] counted by k_far_walk
+  std::vector<int64_t> hEmigCnt;    // host copy (valid while the exchange of a binned step is pending)
   // binned layout (bins.cuh): TriaTracking + cell_volweight_mean (or no deposition)
   bool binEligible = false;      // this configuration steps on the bins
   bool binned = false;           // the particles live in the bins (else: sorted arrays buf[cur] + dElemOff)
@@ -606,6 +610,8 @@ int piclas_gpu_finalize(void) {
   if (g.ev0) cudaEventDestroy(g.ev0);
   if (g.ev1) cudaEventDestroy(g.ev1);
   if (g.st && g.ownStream) cudaStreamDestroy(g.st);
+  if (g.hPin) cudaFreeHost(g.hPin);
+  cudaFree(g.dSendCounts); cudaFree(g.dEmigCnt);
   g = Ctx();
   return 0;
 }
@@ -671,6 +677,10 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   CK(cudaGetDeviceProperties(&prop, g.device));
   g.nSMs = prop.multiProcessorCount;
   CK(cudaStreamCreate(&g.st));
+  CK(cudaMallocHost((void**)&g.hPin, 256 * sizeof(int64_t)));
+  CK(cudaMalloc((void**)&g.dSendCounts, (size_t)(p->nRanks > 0 ? p->nRanks : 1) * sizeof(int64_t)));
+  CK(cudaMemset(g.dSendCounts, 0, (size_t)(p->nRanks > 0 ? p->nRanks : 1) * sizeof(int64_t)));
+  CK(cudaMalloc((void**)&g.dEmigCnt, (size_t)(p->nRanks > 0 ? p->nRanks : 1) * sizeof(int)));
   CK(cudaEventCreate(&g.ev0));
   CK(cudaEventCreate(&g.ev1));
   for (int i = 0; i < 10; ++i) CK(cudaEventCreate(&g.evp[i]));
@@ -988,6 +998,17 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     std::vector<int32_t> candOff, candSrc;
     std::vector<uint8_t> candCase;
     std::vector<int> stamp(nG, -1);
+    // corner boxes of the elements: a target's Gauss points lie inside its box, a source's particles inside its box up to the
+    // localisation tolerance of RefMapping (ElemEpsOneCell, a few per cent of the element) -> source boxes are inflated by 5 %
+    std::vector<std::array<double, 6>> ebox(nG);
+    for (int e2 = 0; e2 < nG; ++e2) {
+      for (int d = 0; d < 3; ++d) { ebox[e2][d] = 1e300; ebox[e2][3 + d] = -1e300; }
+      for (int n = 0; n < 8; ++n)
+        for (int d = 0; d < 3; ++d) {
+          ebox[e2][d] = std::min(ebox[e2][d], tria[e2].corner[n][d]);
+          ebox[e2][3 + d] = std::max(ebox[e2][3 + d], tria[e2].corner[n][d]);
+        }
+    }
     double RsMaxAll = 0.;
     for (int s2 = 0; s2 < nG; ++s2) RsMaxAll = std::max(RsMaxAll, m->ElemRadiusNGeo[s2]);
     int tagCounter = 0;
@@ -1018,7 +1039,15 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
             if (gs < srcLo || gs >= srcHi) continue;
             const double* bs = m->ElemBaryNGeo + (size_t)gs * 3;
             const double dv[3] = {q[0] - bs[0], q[1] - bs[1], q[2] - bs[2]};
-            if (sfnorm(dv) <= 1.0000001 * (rmax + Re + m->ElemRadiusNGeo[gs])) found.push_back(gs);
+            if (!(sfnorm(dv) <= 1.0000001 * (rmax + Re + m->ElemRadiusNGeo[gs]))) continue;
+            // sharper: distance between the target's box (shifted as the particle images are) and the inflated source box
+            double gap[3];
+            for (int d = 0; d < 3; ++d) {
+              const double ext = 0.05 * (ebox[gs][3 + d] - ebox[gs][d]) + 1e-12;
+              const double tlo = ebox[ge][d] - shift[c][d], thi = ebox[ge][3 + d] - shift[c][d];
+              gap[d] = std::max(std::max(tlo - (ebox[gs][3 + d] + ext), (ebox[gs][d] - ext) - thi), 0.0);
+            }
+            if (sfnorm(gap) <= 1.0000001 * rmax) found.push_back(gs);
           }
         }
         std::sort(found.begin(), found.end());
@@ -1611,6 +1640,7 @@ static int push_track_binned(double dt, int32_t* nLost) {
   }
   begin_timing();
   CK(cudaMemsetAsync(g.dCounters, 0, 8 * sizeof(int), g.st));
+  if (g.nRanks > 1) CK(cudaMemsetAsync(g.dEmigCnt, 0, (size_t)g.nRanks * sizeof(int), g.st));
   cudaEventRecord(g.evp[3], g.st);
   const int ne = g.nElems;
   if (ne > 0) {
@@ -1634,9 +1664,15 @@ static int push_track_binned(double dt, int32_t* nLost) {
   }
   int hc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int64_t nFar = 0;
-  CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
-  if (ne > 0) CK(cudaMemcpyAsync(&nFar, g.dFarDOff + ne, 8, cudaMemcpyDeviceToHost, g.st));
-  CK(cudaStreamSynchronize(g.st));
+  {
+    int* pc = reinterpret_cast<int*>(g.hPin);   // pinned: a true asynchronous copy, no staging in the driver
+    g.hPin[8] = 0;
+    CK(cudaMemcpyAsync(pc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
+    if (ne > 0) CK(cudaMemcpyAsync(&g.hPin[8], g.dFarDOff + ne, 8, cudaMemcpyDeviceToHost, g.st));
+    CK(cudaStreamSynchronize(g.st));
+    memcpy(hc, pc, sizeof(hc));
+    nFar = g.hPin[8];
+  }
   const double t1 = host_ms();
   if (nFar > 0) {
     k_far_index<<<ne < g.nSMs * 16 ? ne : g.nSMs * 16, 128, 0, g.st>>>(g.dFarBase, g.dNFarE, g.dFarDOff, ne, g.dFarIdx);
@@ -1672,8 +1708,19 @@ static int push_track_binned(double dt, int32_t* nLost) {
   g.sortedViewValid = false;
   if (g.nRanks > 1) {
     // several ranks: the emigrants are taken out of the far list (piclas_gpu_exchange_info), the immigrants join it, and
-    // piclas_gpu_exchange_finish sorts it into the pool
-    CK(cudaStreamSynchronize(g.st));
+    // piclas_gpu_exchange_finish sorts it into the pool.  The walk counted the emigrants per destination rank.
+    g.hEmigCnt.assign(g.nRanks, 0);
+    if (g.nRanks <= 128) {
+      int* pc = reinterpret_cast<int*>(g.hPin + 32);
+      CK(cudaMemcpyAsync(pc, g.dEmigCnt, (size_t)g.nRanks * sizeof(int), cudaMemcpyDeviceToHost, g.st));
+      CK(cudaStreamSynchronize(g.st));
+      for (int r = 0; r < g.nRanks; ++r) g.hEmigCnt[r] = pc[r];
+    } else {
+      std::vector<int> tmp(g.nRanks);
+      CK(cudaMemcpyAsync(tmp.data(), g.dEmigCnt, (size_t)g.nRanks * sizeof(int), cudaMemcpyDeviceToHost, g.st));
+      CK(cudaStreamSynchronize(g.st));
+      for (int r = 0; r < g.nRanks; ++r) g.hEmigCnt[r] = tmp[r];
+    }
     g.exchangePending = true;
     g.nUnsorted = nFar;
   } else {
@@ -1681,8 +1728,12 @@ static int push_track_binned(double dt, int32_t* nLost) {
     g.nPart = g.nPart - nFar + (nFar > 0 ? g.hTailOff[0] : 0);
   }
   const double t2 = host_ms();
-  CK(cudaMemcpyAsync(hc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
-  CK(cudaStreamSynchronize(g.st));
+  {
+    int* pc = reinterpret_cast<int*>(g.hPin);
+    CK(cudaMemcpyAsync(pc, g.dCounters, sizeof(hc), cudaMemcpyDeviceToHost, g.st));
+    CK(cudaStreamSynchronize(g.st));
+    memcpy(hc, pc, sizeof(hc));
+  }
   if (getenv("PICLAS_GPU_DEBUG"))
     fprintf(stderr, "[piclas_gpu] push_track (bins): %lld particles, %d delivered to face neighbours in-kernel, %lld through the far list, "
             "%d + %d diverted by full regions; host ms: push kernel %.2f, walk + far list %.2f, tail %.2f\n", (long long)g.nPart, (int)g.farStats[1],
@@ -1777,12 +1828,17 @@ int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void*
     CK(cudaMalloc((void**)&g.dTileCnt, (size_t)g.tileCntCap * 4));
   }
   int64_t nEmig = 0;
+  const bool known = g.binned && (int)g.hEmigCnt.size() == g.nRanks;   // bins: k_far_walk counted the emigrants of every rank
   if (n > 0) {
     k_emig_count<<<(unsigned)nTiles, EM_NT, 0, g.st>>>(g.dKeys, n, lo, hi, g.dTileCnt);
     k_emig_scan<<<1, 1024, 0, g.st>>>(g.dTileCnt, (uint32_t)nTiles, g.dEmigOff);
     g.lastLaunches += 2;
-    CK(cudaMemcpyAsync(&nEmig, g.dEmigOff, sizeof(int64_t), cudaMemcpyDeviceToHost, g.st));
-    CK(cudaStreamSynchronize(g.st));
+    if (known) {
+      for (int r = 0; r < g.nRanks; ++r) nEmig += g.hEmigCnt[r];
+    } else {
+      CK(cudaMemcpyAsync(&nEmig, g.dEmigOff, sizeof(int64_t), cudaMemcpyDeviceToHost, g.st));
+      CK(cudaStreamSynchronize(g.st));
+    }
   }
   if (nEmig > g.emigCap) {
     cudaFree(g.dEmigIdx); cudaFree(g.dEmigKey);
@@ -1809,15 +1865,31 @@ int piclas_gpu_exchange_info(int32_t* partCommSize, int64_t* nSendPerRank, void*
                                                                              g.binned ? g.dFarIdx : nullptr);
     g.lastLaunches += 2;
     CK(cudaGetLastError());
-    std::vector<int64_t> off(g.nRanks + 1, 0);
-    CK(cudaMemcpyAsync(off.data(), g.dEmigOff, (size_t)(g.nRanks + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, g.st));
-    CK(cudaStreamSynchronize(g.st));
-    for (int r = 0; r < g.nRanks; ++r) nSendPerRank[r] = off[r + 1] - off[r];
+    if (known) {
+      for (int r = 0; r < g.nRanks; ++r) nSendPerRank[r] = g.hEmigCnt[r];
+    } else {
+      std::vector<int64_t> off(g.nRanks + 1, 0);
+      CK(cudaMemcpyAsync(off.data(), g.dEmigOff, (size_t)(g.nRanks + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, g.st));
+      CK(cudaStreamSynchronize(g.st));
+      for (int r = 0; r < g.nRanks; ++r) nSendPerRank[r] = off[r + 1] - off[r];
+    }
     if (nSendPerRank[g.myRank] != 0) return fail("piclas_gpu_exchange_info: internal error, emigrants addressed to the own rank");
   }
+  // the counts on the device as well (piclas_gpu_exchange_device_info): a count exchange without a host->device copy
+  for (int r = 0; r < g.nRanks && r < 200; ++r) g.hPin[48 + r] = nSendPerRank[r];
+  if (g.nRanks <= 200) CK(cudaMemcpyAsync(g.dSendCounts, g.hPin + 48, (size_t)g.nRanks * sizeof(int64_t), cudaMemcpyHostToDevice, g.st));
+  g.hEmigCnt.clear();
   g.nEmig = nEmig;
   cudaEventRecord(g.evp[7], g.st);
   if (devSendBuf) *devSendBuf = g.dCommSend;
+  return 0;
+}
+
+int piclas_gpu_exchange_device_info(void** devSendCounts, int64_t* sendCapDoubles, int64_t* recvCapDoubles) {
+  if (!g.ready) return fail("piclas_gpu_exchange_device_info: not initialised");
+  if (devSendCounts) *devSendCounts = g.dSendCounts;
+  if (sendCapDoubles) *sendCapDoubles = g.commSendCap * g.commSize;
+  if (recvCapDoubles) *recvCapDoubles = g.commRecvCap * g.commSize;
   return 0;
 }
 

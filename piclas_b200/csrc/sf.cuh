@@ -193,6 +193,8 @@ __global__ void k_sf_gather(PartBuf pb, const int64_t* __restrict__ elemOff, int
                             const double* __restrict__ f3, double* __restrict__ PartSource) {
   __shared__ double sx[SF_CHUNK][3];
   __shared__ double sf4[SF_CHUNK][4];
+  __shared__ double sBox[2][3];            // bounding box of the target's Gauss points
+  __shared__ uint32_t sPass[SF_CHUNK / 32];  // staged particles within reach of that box (the others cannot touch any DOF)
   const int NP = cst.N + 1, ND = NP * NP * NP;
   const int t = threadIdx.x;
   for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
@@ -202,6 +204,15 @@ __global__ void k_sf_gather(PartBuf pb, const int64_t* __restrict__ elemOff, int
       const double* xg = T.Elem_xGP + ((size_t)(g - 1) * ND + t) * 3;
       xd[0] = xg[0]; xd[1] = xg[1]; xd[2] = xg[2];
     }
+    __syncthreads();
+    if (t < 3) {
+      const double* xg = T.Elem_xGP + (size_t)(g - 1) * ND * 3 + t;
+      double lo = xg[0], hi = xg[0];
+      for (int n = 1; n < ND; ++n) { lo = fmin(lo, xg[3 * n]); hi = fmax(hi, xg[3 * n]); }
+      sBox[0][t] = lo;
+      sBox[1][t] = hi;
+    }
+    __syncthreads();
     double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
     for (int ci = T.candOff[e]; ci < T.candOff[e + 1]; ++ci) {
       const int s = T.candSrc[ci];
@@ -215,24 +226,40 @@ __global__ void k_sf_gather(PartBuf pb, const int64_t* __restrict__ elemOff, int
       for (int64_t c0 = p0; c0 < p1; c0 += SF_CHUNK) {
         const int m = (int)min((int64_t)SF_CHUNK, p1 - c0);
         __syncthreads();
-        for (int i = t; i < m; i += blockDim.x) {
-          const double x[3] = {pb.x[0][c0 + i], pb.x[1][c0 + i], pb.x[2][c0 + i]};
-          double xs[3];
-          sf_shifted(iCase, x, xs);
-          sx[i][0] = xs[0]; sx[i][1] = xs[1]; sx[i][2] = xs[2];
-          sf4[i][0] = f0[c0 + i]; sf4[i][1] = f1[c0 + i]; sf4[i][2] = f2[c0 + i]; sf4[i][3] = f3[c0 + i];
+        for (int i0 = 0; i0 < SF_CHUNK; i0 += blockDim.x) {   // every warp walks whole 32-particle groups: one mask word each
+          const int i = i0 + t;
+          bool pass = false;
+          if (i < m) {
+            const double x[3] = {pb.x[0][c0 + i], pb.x[1][c0 + i], pb.x[2][c0 + i]};
+            double xs[3];
+            sf_shifted(iCase, x, xs);
+            sx[i][0] = xs[0]; sx[i][1] = xs[1]; sx[i][2] = xs[2];
+            sf4[i][0] = f0[c0 + i]; sf4[i][1] = f1[c0 + i]; sf4[i][2] = f2[c0 + i]; sf4[i][3] = f3[c0 + i];
+            // distance from the particle to the box of the DOFs (in the directions the shape function spans)
+            double gap[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) gap[d] = fmax(fmax(sBox[0][d] - xs[d], xs[d] - sBox[1][d]), 0.);
+            pass = sf_radius2(gap) <= r2_sf * (1. + 1e-12);
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, pass);
+          if ((t & 31) == 0 && i0 + t < SF_CHUNK) sPass[(i0 + t) >> 5] = bal;
         }
         __syncthreads();
         if (t < ND) {
-          for (int i = 0; i < m; ++i) {
-            const double dd[3] = {sx[i][0] - xd[0], sx[i][1] - xd[1], sx[i][2] - xd[2]};
-            const double radius2 = sf_radius2(dd);
-            if (radius2 <= r2_sf) {
-              const double S1 = sf_kernel(1. - r2_sf_inv * radius2);
-              a0 = a0 + S1 * sf4[i][0];
-              a1 = a1 + S1 * sf4[i][1];
-              a2 = a2 + S1 * sf4[i][2];
-              a3 = a3 + S1 * sf4[i][3];
+          for (int w = 0; w < SF_CHUNK / 32; ++w) {
+            uint32_t bits = sPass[w];
+            while (bits) {   // ascending particle order: the sums keep the order of the unfiltered loop
+              const int i = w * 32 + __ffs(bits) - 1;
+              bits &= bits - 1;
+              const double dd[3] = {sx[i][0] - xd[0], sx[i][1] - xd[1], sx[i][2] - xd[2]};
+              const double radius2 = sf_radius2(dd);
+              if (radius2 <= r2_sf) {
+                const double S1 = sf_kernel(1. - r2_sf_inv * radius2);
+                a0 = a0 + S1 * sf4[i][0];
+                a1 = a1 + S1 * sf4[i][1];
+                a2 = a2 + S1 * sf4[i][2];
+                a3 = a3 + S1 * sf4[i][3];
+              }
             }
           }
         }

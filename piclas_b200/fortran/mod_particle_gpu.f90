@@ -129,6 +129,12 @@ INTERFACE
     TYPE(C_PTR),INTENT(OUT)  :: devRecvBuf
     INTEGER(C_INT)           :: piclas_gpu_exchange_recv_buffer
   END FUNCTION
+  FUNCTION piclas_gpu_exchange_device_info(devSendCounts,sendCapDoubles,recvCapDoubles) BIND(C,NAME='piclas_gpu_exchange_device_info')
+    IMPORT :: C_INT, C_INT64_T, C_PTR
+    TYPE(C_PTR),INTENT(OUT)        :: devSendCounts              ! INTEGER(8) nSendPerRank(1:nProcessors) on the device
+    INTEGER(C_INT64_T),INTENT(OUT) :: sendCapDoubles,recvCapDoubles
+    INTEGER(C_INT)                 :: piclas_gpu_exchange_device_info
+  END FUNCTION
   FUNCTION piclas_gpu_exchange_finish(nRecvTotal) BIND(C,NAME='piclas_gpu_exchange_finish')
     IMPORT :: C_INT, C_INT64_T
     INTEGER(C_INT64_T),VALUE :: nRecvTotal
@@ -182,7 +188,7 @@ PUBLIC :: piclas_gpu_init, piclas_gpu_finalize, piclas_gpu_upload_particles, pic
 PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_particles, piclas_gpu_get_charge, piclas_gpu_kinetic_energy
 PUBLIC :: piclas_gpu_exchange_info, piclas_gpu_exchange_recv_buffer, piclas_gpu_exchange_finish
 PUBLIC :: piclas_gpu_nodesource_device, piclas_gpu_sf_halo_info, piclas_gpu_deposit_finish, piclas_gpu_phase_timing
-PUBLIC :: piclas_gpu_last_timing, piclas_gpu_node_halo_info, piclas_gpu_set_stream
+PUBLIC :: piclas_gpu_last_timing, piclas_gpu_node_halo_info, piclas_gpu_set_stream, piclas_gpu_exchange_device_info
 PUBLIC :: ParticleStepGPU, GPUAbortOnError
 
 CONTAINS

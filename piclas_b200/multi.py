@@ -35,7 +35,7 @@ class _DevPtr:
 
 def device_tensor(ptr, nelem, device, typestr="<f8"):
     if nelem == 0 or not ptr:
-        return torch.empty(0, dtype=torch.float64, device=device)
+        return torch.empty(0, dtype=torch.int64 if typestr == "<i8" else torch.float64, device=device)
     return torch.as_tensor(_DevPtr(ptr, nelem, typestr), device=device)
 
 
@@ -87,6 +87,19 @@ class ParticleStepRank:
         # the library works on torch's current stream: its kernels and the NCCL collectives issued below are then ordered on the
         # device, no host synchronisation between them
         self._check(self.lib.piclas_gpu_set_stream(C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        self._wrapped = {}                                                   # (device pointer, capacity) -> tensor over the whole buffer
+        self._rcnt = torch.zeros(world, dtype=torch.int64, device=self.device)
+
+    def _buffer(self, ptr, cap, typestr="<f8"):
+        """Tensor over a whole device buffer of the library, wrapped once (wrapping costs tens of microseconds) and sliced per step."""
+        key = (int(ptr or 0), int(cap), typestr)
+        t = self._wrapped.get(key)
+        if t is None:
+            if len(self._wrapped) > 64:
+                self._wrapped.clear()
+            t = device_tensor(ptr, cap, self.device, typestr)
+            self._wrapped[key] = t
+        return t
 
     def close(self):
         self.step.close()
@@ -101,12 +114,19 @@ class ParticleStepRank:
         sp = C.c_void_p(0)
         self._check(self.lib.piclas_gpu_exchange_info(C.byref(cs), nsend, C.byref(sp)))
         send_counts = [int(nsend[r]) for r in range(world)]
-        recv_counts = exchange_counts(send_counts, self.device, self.group)
+        # counts to / from every rank (IRecvNbOfParticles / SendNbOfParticles): the library left them on the device as well
+        cp = C.c_void_p(0)
+        scap, rcap = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.piclas_gpu_exchange_device_info(C.byref(cp), C.byref(scap), C.byref(rcap)))
+        dist.all_to_all_single(self._rcnt, self._buffer(cp.value, world, "<i8"), group=self.group)
+        recv_counts = [int(v) for v in self._rcnt.tolist()]
         nrecv = sum(recv_counts)
         rp = C.c_void_p(0)
         self._check(self.lib.piclas_gpu_exchange_recv_buffer(C.c_int64(nrecv), C.byref(rp)))
-        sbuf = device_tensor(sp.value, sum(send_counts) * cs.value, self.device)
-        rbuf = device_tensor(rp.value, nrecv * cs.value, self.device)
+        self._check(self.lib.piclas_gpu_exchange_device_info(C.byref(cp), C.byref(scap), C.byref(rcap)))
+        nsd, nrd = sum(send_counts) * cs.value, nrecv * cs.value
+        sbuf = self._buffer(sp.value, scap.value)[:nsd] if nsd else torch.empty(0, dtype=torch.float64, device=self.device)
+        rbuf = self._buffer(rp.value, rcap.value)[:nrd] if nrd else torch.empty(0, dtype=torch.float64, device=self.device)
         exchange_particles(sbuf, send_counts, rbuf, recv_counts, cs.value, self.group)
         self._check(self.lib.piclas_gpu_exchange_finish(C.c_int64(nrecv)))
         self.migrated = sum(send_counts)
@@ -139,9 +159,7 @@ class ParticleStepRank:
         sp, rp = C.c_void_p(0), C.c_void_p(0)
         self._check(self.lib.piclas_gpu_node_halo_info(C.byref(nd), C.byref(sp), C.byref(rp)))
         if nd.value > 0:
-            sbuf = device_tensor(sp.value, nd.value, self.device)
-            rbuf = device_tensor(rp.value, nd.value * self.world, self.device)
-            dist.all_gather_into_tensor(rbuf, sbuf, group=self.group)
+            dist.all_gather_into_tensor(self._buffer(rp.value, nd.value * self.world), self._buffer(sp.value, nd.value), group=self.group)
         PS = out_partsource if out_partsource is not None else (np.empty(self.step._ps_shape) if want_partsource else None)
         NS = np.empty((self.mesh.nUniqueNodes, 4)) if want_nodesource else None
         self._check(self.lib.piclas_gpu_deposit_finish(_f(PS), _f(NS)))
