@@ -10,7 +10,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpiclas_gpu.so")
 SOURCES = ["piclas_gpu.cu", "sort.cu"]
-HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + [os.path.join(ROOT, "include", "piclas_gpu.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".inc"))) + [os.path.join(ROOT, "include", "piclas_gpu.h")]
+STAMP = LIB + ".srchash"   # hash of sources + flags the library was built from (travels with the .so, git-ignored)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,12 +28,24 @@ def _nvcc():
     return "nvcc"
 
 
+def source_hash() -> str:
+    """sha256 over the compiler flags and every source / header of the library: the build is keyed on content, not on
+    modification times (a snapshot copied to another machine keeps the former, not the latter)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [x if os.path.isabs(x) else os.path.join(CSRC, x) for x in HEADERS]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
@@ -44,6 +57,8 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

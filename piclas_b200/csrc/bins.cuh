@@ -86,7 +86,8 @@ struct __align__(16) PushElem {
   int32_t nbBox[6];       // inbox of that neighbour = its local side facing this element
   uint32_t planar;        // convex element with planar sides: exit side from the side planes
   uint32_t affine;
-  uint32_t pad[2];
+  uint32_t nbValid;       // bit s: nbpl[s] / nbtol[s] hold the planes of an inner, planar neighbour (any rank)
+  uint32_t pad[1];
 };
 static_assert(sizeof(PushElem) % 16 == 0, "PushElem is copied with cp.async.bulk (16-byte granules)");
 
@@ -667,6 +668,7 @@ __device__ __forceinline__ void push_inline_b0(double x[3], double v[3], const d
   for (int d = 0; d < 3; ++d) x[d] = fma(v[d], dt, x[d]);
 }
 
+constexpr int UNPUSHED_LIST = 4096;   // far slots of unpushed records kept behind the eight counters; more: scan of the whole far list
 constexpr int CAT_STAY = 0, CAT_FAR = 7, CAT_NONE = 8;
 
 // HOTONLY: every local element is affine with planar sides, B = 0, restructured arithmetic.  The kernel then contains no call at
@@ -983,7 +985,10 @@ __global__ void __launch_bounds__(KB_NT, KB_MINB) k_bin_push(PartBuf bins, PartB
         // IsNewPart is consumed by the push; an unpushed far record keeps it
         const uint8_t nmeta = (HOTONLY && ((unpushed >> q) & 1)) ? (uint8_t)((metaQ & (META_SPEC_MASK | META_ISNEW)) | META_UNPUSHED)
                                                                  : (uint8_t)(metaQ & META_SPEC_MASK);
-        if (HOTONLY && ((unpushed >> q) & 1)) atomicAdd(&counters[7], 1);
+        if (HOTONLY && ((unpushed >> q) & 1)) {   // the few unpushed records are listed behind the counters (k_far_unpushed)
+          const int pos = atomicAdd(&counters[7], 1);
+          if (pos < UNPUSHED_LIST) counters[8 + pos] = (int)fdst;
+        }
         if (dst >= 0) {
 #pragma unroll
           for (int a = 0; a < 6; ++a) BF[a * BS + dst] = sNs[a * KB_CHUNK + q];
@@ -1029,13 +1034,13 @@ __global__ void __launch_bounds__(KB_NT, KB_MINB) k_bin_push(PartBuf bins, PartB
 // general path for the far records that k_bin_push<.., HOTONLY> handed over unpushed: field at the particle, push (x = pushed
 // position, lp = LastPartPos stays); the walk that follows does the inside test of the own element
 template <int NP>
-__global__ void k_far_unpushed(FarBuf far, const uint32_t* __restrict__ idx, int nFar, const double* __restrict__ Emono, const double* __restrict__ E,
+__global__ void k_far_unpushed(FarBuf far, const uint32_t* __restrict__ idx, const int* __restrict__ list, int nFar, const double* __restrict__ Emono, const double* __restrict__ E,
                                const GeoElem* __restrict__ geo, const AffElem* __restrict__ aff, const PlaneElem* __restrict__ planes,
                                const TriaElem* __restrict__ tria, const double* __restrict__ Elem_xGP, int offsetElem, double dt) {
   constexpr int ND = NP * NP * NP;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nFar) return;
-  const int64_t p = idx[i];
+  const int64_t p = idx ? (int64_t)idx[i] : (int64_t)list[i];   // list: the slots k_bin_push noted; idx: every far slot
   const int meta = far.meta[p];
   if (!(meta & META_UNPUSHED)) return;
   const int g = far.elem[p], e = g - 1 - offsetElem;
@@ -1047,6 +1052,178 @@ __global__ void k_far_unpushed(FarBuf far, const uint32_t* __restrict__ idx, int
   far.meta[p] = (uint8_t)(meta & META_SPEC_MASK);
 }
 
+// ---- far records that come to rest within two side crossings --------------------------------------------------------------------
+// Most far records left their element through an edge region: beyond two side planes, at rest in the neighbour's neighbour.
+// One warp per element stages the element's PushElem (own planes and the planes of the six neighbours, one coalesced copy for
+// all its records) and takes up to two crossings with the side planes exactly as exit_side_planar does (every decision with a
+// margin of tol, the flight taken from LastPartPos as SingleParticleTriaTracking3D does, particle_triatracking.f90:171-173);
+// only the planes of the last element are gathered from the element table.  A record is settled when it is clearly inside
+// the element reached (ParticleInsideQuad3D there succeeds, :215-218); everything else - boundary sides, non-planar
+// elements, a third crossing, any decision within tol - is appended to the pending list, which k_far_walk takes from the start
+// with the determinant tests.  Also writes the dense index of the element's far slots (k_far_index).
+// second ring of an element: global ids (0: none / boundary side / non-planar) of the neighbours and of their neighbours
+struct __align__(16) HintNb {
+  int32_t nb[6];
+  int32_t nbnb[6][6];
+  int32_t pad[2];
+};
+static_assert(sizeof(HintNb) % 16 == 0, "HintNb is staged with 16-byte loads");
+
+// -1: undecided, 0: clearly inside, 1: leaves through `side`; the crossing point is lp + (num / den) (x - lp), den > 0 (the
+// diagonal test hint_diag is still due).  Division-free: with a_o = ol_o / (ol_o - ox_o) and positive denominators, a_1 < a_2 is
+// ol_1 den_2 < ol_2 den_1, and a distance at the crossing point, ol + a_s (ox - ol) > tol, is ol den_s + ol_s (ox - ol) > tol den_s.
+// den_s >= 1e4 tol (the flight crosses the plane by more than 1e-4 element diameters) keeps the margin tol den_s four orders of
+// magnitude above the rounding error of the products; shorter crossings are left to the exact walk.
+template <class PL>
+__device__ __forceinline__ int hint_exit(PL pl, double tol, const double x[3], const double lp[3], int& side, double& num, double& den) {
+  double ol[6], ox[6];
+  uint32_t neg = 0;
+  bool amb = false;
+#pragma unroll
+  for (int o = 0; o < 6; ++o) {
+    double a, b, c, d;
+    pl(o, a, b, c, d);
+    ox[o] = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));
+    ol[o] = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
+    amb |= fabs(ox[o]) <= tol;
+    neg |= ((uint32_t)__double2hiint(ox[o]) >> 31) << o;
+  }
+  if (amb) return -1;
+  if (neg == 0u) return 0;
+  int s = -1;
+  num = 1.0;
+  den = 0.0;   // a = num / den = +inf
+  bool ok = true;
+#pragma unroll
+  for (int o = 0; o < 6; ++o) {
+    const bool cr = (neg >> o) & 1u;
+    const double dn = ol[o] - ox[o];
+    if (cr && !(ol[o] > tol)) ok = false;
+    if (cr && ol[o] * den < num * dn) { num = ol[o]; den = dn; s = o; }
+  }
+  if (!ok || s < 0 || !(den >= 1e4 * tol)) return -1;
+  const double lim = tol * den;
+#pragma unroll
+  for (int o = 0; o < 6; ++o) {
+    const double oc = fma(ol[o], den, num * (ox[o] - ol[o]));
+    if (o != s && !(oc > lim)) ok = false;
+  }
+  side = s;
+  return ok ? 1 : -1;
+}
+// crossing point clearly off the triangle diagonal of the side (plane a, b, c, d as PlaneElem::dg)
+__device__ __forceinline__ bool hint_diag(double a, double b, double c, double d, double num, double den, double tol, const double x[3],
+                                          const double lp[3]) {
+  const double gl = fma(a, lp[0], fma(b, lp[1], fma(c, lp[2], -d)));
+  const double gx = fma(a, x[0], fma(b, x[1], fma(c, x[2], -d)));
+  return fabs(fma(gl, den, num * (gx - gl))) > tol * den;
+}
+
+#ifndef FH_MINB
+#define FH_MINB 5
+#endif
+constexpr int FH_WARPS = 4, FH_PEND = 512;
+__global__ void __launch_bounds__(FH_WARPS * 32, FH_MINB) k_far_hint(FarBuf far, const int64_t* __restrict__ farBase, const int32_t* __restrict__ nFarE,
+                                                            const int64_t* __restrict__ dOff, int nElems, int offsetElem,
+                                                            const PushElem* __restrict__ pushElems, const HintNb* __restrict__ hintNb,
+                                                            const PlaneElem* __restrict__ planes, const int32_t* __restrict__ elemRank,
+                                                            uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ pend,
+                                                            int* __restrict__ counters, int* __restrict__ emigCnt) {
+  __shared__ PushElem sPe[FH_WARPS];
+  __shared__ HintNb sHn[FH_WARPS];
+  __shared__ uint32_t sPend[FH_WARPS][FH_PEND];
+  int nPend = 0;   // warp-uniform
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const PushElem& pe = sPe[w];
+  const HintNb& hn = sHn[w];
+  for (int e = blockIdx.x * FH_WARPS + w; e < nElems; e += gridDim.x * FH_WARPS) {
+    const int nb = nFarE[2 * e], n = nb + nFarE[2 * e + 1];
+    if (n == 0) continue;
+    const int64_t b0 = farBase[e], b1 = farBase[e + 1], d0 = dOff[e];
+    __syncwarp();
+    {
+      const int4* src = reinterpret_cast<const int4*>(pushElems + e);
+      int4* dst = reinterpret_cast<int4*>(&sPe[w]);
+      for (int i = lane; i < (int)(sizeof(PushElem) / 16); i += 32) dst[i] = __ldg(src + i);
+      if (lane < (int)(sizeof(HintNb) / 16)) reinterpret_cast<int4*>(&sHn[w])[lane] = __ldg(reinterpret_cast<const int4*>(hintNb + e) + lane);
+    }
+    __syncwarp();
+    const int ge = offsetElem + e + 1;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < n;
+      int64_t slot = 0;
+      int fin = 0;   // element the record comes to rest in, 0: undecided
+      if (valid) {
+        slot = i < nb ? b0 + i : b1 - 1 - (i - nb);
+        idx[d0 + i] = (uint32_t)slot;
+        if (pe.planar) {
+          const double x[3] = {far.x[0][slot], far.x[1][slot], far.x[2][slot]};
+          const double lp[3] = {far.lp[0][slot], far.lp[1][slot], far.lp[2][slot]};
+          int s0 = 0, s1 = 0;
+          double n0 = 0., q0 = 0., n1 = 0., q1 = 0.;   // crossing parameters num / den of the two crossings
+          const int r0 = hint_exit([&](int o, double& a, double& b, double& c, double& d) { a = pe.pl[o][0]; b = pe.pl[o][1]; c = pe.pl[o][2]; d = pe.pl[o][3]; },
+                                   pe.tol, x, lp, s0, n0, q0);
+          if (r0 == 0) fin = ge;
+          else if (r0 == 1 && hn.nb[s0] > 0 && hint_diag(pe.dg[s0][0], pe.dg[s0][1], pe.dg[s0][2], pe.dg[s0][3], n0, q0, pe.tol, x, lp)) {
+            const int nb1 = hn.nb[s0];
+            const double(*npl)[4] = pe.nbpl[s0];
+            const double tol1 = pe.nbtol[s0];
+            const int r1 = hint_exit([&](int o, double& a, double& b, double& c, double& d) { a = npl[o][0]; b = npl[o][1]; c = npl[o][2]; d = npl[o][3]; },
+                                     tol1, x, lp, s1, n1, q1);
+            if (r1 == 0) fin = nb1;
+            else if (r1 == 1 && hn.nbnb[s0][s1] > 0) {
+              // the diagonal plane of the neighbour's side and the planes of the element behind it: independent loads, one round trip
+              const int nb2 = hn.nbnb[s0][s1];
+              const PlaneElem* p2 = planes + (nb2 - 1);
+              double ga, gb, gc, gd;
+              load_plane4<true>((planes + (nb1 - 1))->dg[s1], ga, gb, gc, gd);
+              const double tol2 = __ldg(&p2->tol);
+              bool in = true;
+#pragma unroll
+              for (int o = 0; o < 6; ++o) {
+                double a, b, c, d;
+                load_plane4<true>(p2->pl[2 * o], a, b, c, d);
+                if (!(fma(a, x[0], fma(b, x[1], fma(c, x[2], -d))) > tol2)) in = false;
+              }
+              if (in && hint_diag(ga, gb, gc, gd, n1, q1, tol1, x, lp)) fin = nb2;
+            }
+          }
+        }
+        if (fin > 0) {
+          const int rk = (cst.nRanks == 1) ? cst.myRank : elemRank[fin - 1];
+          keys[d0 + i] = (rk == cst.myRank) ? (uint32_t)(fin - 1 - offsetElem) : (uint32_t)(nElems + rk);
+          if (rk != cst.myRank && emigCnt) atomicAdd(&emigCnt[rk], 1);
+          if (fin != ge) far.elem[slot] = fin;
+        }
+      }
+      // undecided records: collected per warp, appended to the pending list a few hundred at a time (one atomic on the list's
+      // counter per flush; one per 32 records made the kernel wait on that one address for most of its run time)
+      const unsigned open = __ballot_sync(0xffffffffu, valid && fin == 0);
+      if (open) {
+        if (valid && fin == 0) sPend[w][nPend + __popc(open & ((1u << lane) - 1u))] = (uint32_t)(d0 + i);
+        nPend += __popc(open);
+        if (nPend > FH_PEND - 32) {
+          __syncwarp();
+          int first = 0;
+          if (lane == 0) first = atomicAdd(&counters[2], nPend);
+          first = __shfl_sync(0xffffffffu, first, 0);
+          for (int j = lane; j < nPend; j += 32) pend[first + j] = sPend[w][j];
+          nPend = 0;
+          __syncwarp();
+        }
+      }
+    }
+  }
+  if (nPend > 0) {
+    __syncwarp();
+    int first = 0;
+    if (lane == 0) first = atomicAdd(&counters[2], nPend);
+    first = __shfl_sync(0xffffffffu, first, 0);
+    for (int j = lane; j < nPend; j += 32) pend[first + j] = sPend[w][j];
+  }
+}
+
 // ---- SingleParticleTriaTracking3D for the far list (particle_triatracking.f90:137-484), from the start -----------------------------
 // One thread per record, persistent warps with per-lane refill (as k_track_leavers).  key: local element, nElems + rank
 // (emigrant) or nElems + nRanks (removed).
@@ -1054,8 +1231,13 @@ template <bool FAST>
 __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, const uint32_t* __restrict__ idx, int nFar, const TriaElem* __restrict__ tria,
                                                              const PlaneElem* __restrict__ planes, const int32_t* __restrict__ elemRank,
                                                              uint32_t* __restrict__ keys, int nElems, int offsetElem, int* __restrict__ counters,
-                                                             int* __restrict__ emigCnt /*[nRanks] emigrants per destination rank, or null*/) {
+                                                             int* __restrict__ emigCnt /*[nRanks] emigrants per destination rank, or null*/,
+                                                             const uint32_t* __restrict__ pend /*dense indices left by k_far_hint (count in counters[2]), or null: all*/) {
   const int lane = threadIdx.x & 31;
+  if (pend) nFar = counters[2];
+  constexpr int FW_CHUNK = 256;
+  int chunkNext = 0, chunkEnd = 0;   // warp-uniform
+  bool drained = false;
   bool active = false;
   int p = 0, dense = 0, ElemID = 0, guard = 0;
   uint32_t mask = 0;
@@ -1065,16 +1247,26 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, const u
   while (true) {
     int status = -1;
     {
-      const unsigned need = __ballot_sync(0xffffffffu, !active);
-      if (need) {
-        int first = 0;
-        if (lane == __ffs(need) - 1) first = atomicAdd(&counters[3], __popc(need));
-        first = __shfl_sync(0xffffffffu, first, __ffs(need) - 1);
-        const int mine = first + __popc(need & ((1u << lane) - 1u));
-        if (!active && mine < nFar) {
+      // idle lanes take the next records of the warp's chunk of the list; a new chunk (one atomic on the list's counter per
+      // FW_CHUNK records, not one per refill) when it runs out
+      unsigned need = __ballot_sync(0xffffffffu, !active);
+      while (need) {
+        if (chunkNext >= chunkEnd) {
+          if (drained) break;
+          int first = 0;
+          if (lane == 0) first = atomicAdd(&counters[3], FW_CHUNK);
+          first = __shfl_sync(0xffffffffu, first, 0);
+          if (first >= nFar) { drained = true; break; }
+          chunkNext = first;
+          chunkEnd = first + FW_CHUNK < nFar ? first + FW_CHUNK : nFar;
+        }
+        const int avail = chunkEnd - chunkNext, want = __popc(need);
+        const int rank = __popc(need & ((1u << lane) - 1u));
+        if (!active && rank < avail) {
+          const int mine = chunkNext + rank;
           active = true;
-          dense = mine;
-          p = (int)idx[mine];
+          dense = pend ? (int)pend[mine] : mine;
+          p = (int)idx[dense];
           x[0] = far.x[0][p]; x[1] = far.x[1][p]; x[2] = far.x[2][p];
           lp[0] = far.lp[0][p]; lp[1] = far.lp[1][p]; lp[2] = far.lp[2][p];
           ElemID = far.elem[p];
@@ -1085,6 +1277,9 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, const u
                                : inside_quad3d_mask<true>(tria + (ElemID - 1), x, mask);
           if (in) status = TRK_OK;
         }
+        chunkNext += want < avail ? want : avail;
+        if (want <= avail) break;
+        need = __ballot_sync(0xffffffffu, !active);
       }
       if (__ballot_sync(0xffffffffu, active) == 0) break;
     }

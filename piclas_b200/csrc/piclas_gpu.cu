@@ -128,6 +128,9 @@ struct Ctx {
   uint32_t* dFarIdx = nullptr;   // [cap] used far slots, densely listed
   int64_t farIdxCap = 0;
   PushElem* dPushElem = nullptr;
+  HintNb* dHintNb = nullptr;
+  uint32_t* dFarPend = nullptr;   // dense indices of the far records k_far_hint left to the exact walk
+  int64_t farPendCap = 0;
   int binParity = 0;
   int64_t nFar = 0;              // records of the far list of the open step
   double mainSlack = 0.10, inFrac = 0.09;
@@ -1123,7 +1126,7 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   }
   CK(cudaMalloc((void**)&g.dElemOff, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
   CK(cudaMemset(g.dElemOff, 0, (size_t)(g.nElems + g.nRanks + 2) * sizeof(int64_t)));
-  CK(cudaMalloc((void**)&g.dCounters, 8 * sizeof(int)));
+  CK(cudaMalloc((void**)&g.dCounters, (8 + UNPUSHED_LIST) * sizeof(int)));   // counters, then the far slots of unpushed records
   g.keyBits = 1;
   while ((1u << g.keyBits) < (uint32_t)(g.nElems + g.nRanks + 1)) ++g.keyBits;
 
@@ -1675,20 +1678,24 @@ static int push_track_binned(double dt, int32_t* nLost) {
   }
   const double t1 = host_ms();
   if (nFar > 0) {
-    k_far_index<<<ne < g.nSMs * 16 ? ne : g.nSMs * 16, 128, 0, g.st>>>(g.dFarBase, g.dNFarE, g.dFarDOff, ne, g.dFarIdx);
-    ++g.lastLaunches;
+    const bool listed = hc[7] <= UNPUSHED_LIST;   // few: k_bin_push noted their far slots; many: scan of the indexed far list
     if (hc[7] > 0) {   // particles the call-free push kernel handed over unpushed
+      if (!listed) {
+        k_far_index<<<ne < g.nSMs * 16 ? ne : g.nSMs * 16, 128, 0, g.st>>>(g.dFarBase, g.dNFarE, g.dFarDOff, ne, g.dFarIdx);
+        ++g.lastLaunches;
+      }
+      const int64_t nu = listed ? hc[7] : nFar;
       switch (g.NP) {
-        case 2: launch_far_unpushed<2>(nFar, dt); break;
-        case 3: launch_far_unpushed<3>(nFar, dt); break;
-        case 4: launch_far_unpushed<4>(nFar, dt); break;
-        case 5: launch_far_unpushed<5>(nFar, dt); break;
-        case 6: launch_far_unpushed<6>(nFar, dt); break;
-        case 7: launch_far_unpushed<7>(nFar, dt); break;
-        case 8: launch_far_unpushed<8>(nFar, dt); break;
+        case 2: launch_far_unpushed<2>(nu, dt, listed); break;
+        case 3: launch_far_unpushed<3>(nu, dt, listed); break;
+        case 4: launch_far_unpushed<4>(nu, dt, listed); break;
+        case 5: launch_far_unpushed<5>(nu, dt, listed); break;
+        case 6: launch_far_unpushed<6>(nu, dt, listed); break;
+        case 7: launch_far_unpushed<7>(nu, dt, listed); break;
+        case 8: launch_far_unpushed<8>(nu, dt, listed); break;
       }
     }
-    launch_far_walk(nFar);
+    if (launch_far_walk(nFar, hc[7] > 0 && !listed)) return 1;
   }
   CK(cudaGetLastError());
   cudaEventRecord(g.evp[4], g.st);
@@ -1736,8 +1743,8 @@ static int push_track_binned(double dt, int32_t* nLost) {
   }
   if (getenv("PICLAS_GPU_DEBUG"))
     fprintf(stderr, "[piclas_gpu] push_track (bins): %lld particles, %d delivered to face neighbours in-kernel, %lld through the far list, "
-            "%d + %d diverted by full regions; host ms: push kernel %.2f, walk + far list %.2f, tail %.2f\n", (long long)g.nPart, (int)g.farStats[1],
-            (long long)nFar, (int)g.farStats[2], (int)g.farStats[3], t1 - t0, t2 - t1, host_ms() - t2);
+            "%d + %d diverted by full regions, %d walked with the determinant tests; host ms: push kernel %.2f, walk + far list %.2f, tail %.2f\n",
+            (long long)g.nPart, (int)g.farStats[1], (long long)nFar, (int)g.farStats[2], (int)g.farStats[3], hc[2], t1 - t0, t2 - t1, host_ms() - t2);
   cudaEventRecord(g.evp[5], g.st);
   end_timing();
   {
