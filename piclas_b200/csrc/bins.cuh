@@ -87,7 +87,7 @@ struct __align__(16) PushElem {
   uint32_t planar;        // convex element with planar sides: exit side from the side planes
   uint32_t affine;
   uint32_t nbValid;       // bit s: nbpl[s] / nbtol[s] hold the planes of an inner, planar neighbour (any rank)
-  uint32_t pad[1];
+  uint32_t shiftCode;     // 5 bits per side with nbLocal >= 0: periodic vector the crossing adds (0: inner side), see build_push_elems
 };
 static_assert(sizeof(PushElem) % 16 == 0, "PushElem is copied with cp.async.bulk (16-byte granules)");
 
@@ -898,14 +898,27 @@ __global__ void __launch_bounds__(KB_NT, KB_MINB) k_bin_push(PartBuf bins, PartB
                 const double gc = fma(alpha, gx - gl, gl);
                 if (!(fabs(gc) > tol)) ok = false;   // crossing point on the triangle diagonal
               }
+              // periodic side: the particle goes on behind the partner side (PeriodicBoundary, particle_boundary_condition.f90:224-284:
+              // LastPartPos = crossing point + vector, PartState = LastPartPos + rest of the flight; here the vector is added
+              // to the pushed position, the same point to rounding)
+              double xs[3] = {xq[0], xq[1], xq[2]};
+              const uint32_t sc = (pe.shiftCode >> (5 * s)) & 31u;
+              if (sc) {
+                const int pv = (int)(sc & 15u) - 1;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) xs[d] = (sc & 16u) ? xq[d] - cst.PeriodicVectors[pv][d] : xq[d] + cst.PeriodicVectors[pv][d];
+              }
               // clearly inside the neighbour: ParticleInsideQuad3D there succeeds, the walk ends (:215-218)
               const double ntol = pe.nbtol[s];
 #pragma unroll
               for (int o = 0; o < 6; ++o) {
-                const double dn = fma(pe.nbpl[s][o][0], xq[0], fma(pe.nbpl[s][o][1], xq[1], fma(pe.nbpl[s][o][2], xq[2], -pe.nbpl[s][o][3])));
+                const double dn = fma(pe.nbpl[s][o][0], xs[0], fma(pe.nbpl[s][o][1], xs[1], fma(pe.nbpl[s][o][2], xs[2], -pe.nbpl[s][o][3])));
                 if (!(dn > ntol)) ok = false;
               }
-              if (ok) cat = 1 + s;
+              if (ok) {
+                cat = 1 + s;
+                xq[0] = xs[0]; xq[1] = xs[1]; xq[2] = xs[2];
+              }
             }
           }
           if (cold) {
@@ -1065,7 +1078,9 @@ __global__ void k_far_unpushed(FarBuf far, const uint32_t* __restrict__ idx, con
 struct __align__(16) HintNb {
   int32_t nb[6];
   int32_t nbnb[6][6];
-  int32_t pad[2];
+  uint32_t sh1;       // 5 bits per side: periodic vector added when crossing into nb[s] (as PushElem::shiftCode)
+  uint32_t sh2[6];    // the same for the crossing nb[s] -> nbnb[s][o]
+  int32_t pad[3];
 };
 static_assert(sizeof(HintNb) % 16 == 0, "HintNb is staged with 16-byte loads");
 
@@ -1126,6 +1141,7 @@ constexpr int FH_WARPS = 4, FH_PEND = 512;
 __global__ void __launch_bounds__(FH_WARPS * 32, FH_MINB) k_far_hint(FarBuf far, const int64_t* __restrict__ farBase, const int32_t* __restrict__ nFarE,
                                                             const int64_t* __restrict__ dOff, int nElems, int offsetElem,
                                                             const PushElem* __restrict__ pushElems, const HintNb* __restrict__ hintNb,
+                                                            const TriaElem* __restrict__ tria,
                                                             const PlaneElem* __restrict__ planes, const int32_t* __restrict__ elemRank,
                                                             uint32_t* __restrict__ keys, uint32_t* __restrict__ idx, uint32_t* __restrict__ pend,
                                                             int* __restrict__ counters, int* __restrict__ emigCnt) {
@@ -1158,15 +1174,29 @@ __global__ void __launch_bounds__(FH_WARPS * 32, FH_MINB) k_far_hint(FarBuf far,
         slot = i < nb ? b0 + i : b1 - 1 - (i - nb);
         idx[d0 + i] = (uint32_t)slot;
         if (pe.planar) {
-          const double x[3] = {far.x[0][slot], far.x[1][slot], far.x[2][slot]};
-          const double lp[3] = {far.lp[0][slot], far.lp[1][slot], far.lp[2][slot]};
-          int s0 = 0, s1 = 0;
-          double n0 = 0., q0 = 0., n1 = 0., q1 = 0.;   // crossing parameters num / den of the two crossings
+          double x[3] = {far.x[0][slot], far.x[1][slot], far.x[2][slot]};
+          double lp[3] = {far.lp[0][slot], far.lp[1][slot], far.lp[2][slot]};
+          bool moved = false;
+          // periodic side: the flight goes on behind the partner side, both of its end points displaced by the periodic vector
+          auto periodic = [&](uint32_t sc) {
+            if (!sc) return;
+            const int pv = (int)(sc & 15u) - 1;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              const double v = (sc & 16u) ? -cst.PeriodicVectors[pv][d] : cst.PeriodicVectors[pv][d];
+              x[d] += v;
+              lp[d] += v;
+            }
+            moved = true;
+          };
+          int s0 = 0, s1 = 0, s2 = 0;
+          double n0 = 0., q0 = 0., n1 = 0., q1 = 0., n2 = 0., q2 = 0.;   // crossing parameters num / den of the crossings
           const int r0 = hint_exit([&](int o, double& a, double& b, double& c, double& d) { a = pe.pl[o][0]; b = pe.pl[o][1]; c = pe.pl[o][2]; d = pe.pl[o][3]; },
                                    pe.tol, x, lp, s0, n0, q0);
           if (r0 == 0) fin = ge;
           else if (r0 == 1 && hn.nb[s0] > 0 && hint_diag(pe.dg[s0][0], pe.dg[s0][1], pe.dg[s0][2], pe.dg[s0][3], n0, q0, pe.tol, x, lp)) {
             const int nb1 = hn.nb[s0];
+            periodic((hn.sh1 >> (5 * s0)) & 31u);
             const double(*npl)[4] = pe.nbpl[s0];
             const double tol1 = pe.nbtol[s0];
             const int r1 = hint_exit([&](int o, double& a, double& b, double& c, double& d) { a = npl[o][0]; b = npl[o][1]; c = npl[o][2]; d = npl[o][3]; },
@@ -1178,17 +1208,33 @@ __global__ void __launch_bounds__(FH_WARPS * 32, FH_MINB) k_far_hint(FarBuf far,
               const PlaneElem* p2 = planes + (nb2 - 1);
               double ga, gb, gc, gd;
               load_plane4<true>((planes + (nb1 - 1))->dg[s1], ga, gb, gc, gd);
+              const bool offDiag = hint_diag(ga, gb, gc, gd, n1, q1, tol1, x, lp);   // before the displacement of the second crossing
+              periodic((hn.sh2[s0] >> (5 * s1)) & 31u);
               const double tol2 = __ldg(&p2->tol);
-              bool in = true;
+              const int r2 = hint_exit([&](int o, double& a, double& b, double& c, double& d) { load_plane4<true>(p2->pl[2 * o], a, b, c, d); },
+                                       tol2, x, lp, s2, n2, q2);
+              if (r2 == 0 && offDiag) fin = nb2;
+              else if (r2 == 1 && offDiag) {
+                // third crossing (flight through a corner region): inner sides only
+                const TriaElem* t2 = tria + (nb2 - 1);
+                const int nb3 = t2->nbElem[s2];
+                if (t2->bcid[s2] == 0 && nb3 >= 1) {
+                  const PlaneElem* p3 = planes + (nb3 - 1);
+                  load_plane4<true>(p2->dg[s2], ga, gb, gc, gd);
+                  const double tol3 = __ldg(&p3->tol);
+                  bool in = __ldg(&p3->planar) != 0u;
 #pragma unroll
-              for (int o = 0; o < 6; ++o) {
-                double a, b, c, d;
-                load_plane4<true>(p2->pl[2 * o], a, b, c, d);
-                if (!(fma(a, x[0], fma(b, x[1], fma(c, x[2], -d))) > tol2)) in = false;
+                  for (int o = 0; o < 6; ++o) {
+                    double a, b, c, d;
+                    load_plane4<true>(p3->pl[2 * o], a, b, c, d);
+                    if (!(fma(a, x[0], fma(b, x[1], fma(c, x[2], -d))) > tol3)) in = false;
+                  }
+                  if (in && hint_diag(ga, gb, gc, gd, n2, q2, tol2, x, lp)) fin = nb3;
+                }
               }
-              if (in && hint_diag(ga, gb, gc, gd, n1, q1, tol1, x, lp)) fin = nb2;
             }
           }
+          if (fin > 0 && moved) { far.x[0][slot] = x[0]; far.x[1][slot] = x[1]; far.x[2][slot] = x[2]; }
         }
         if (fin > 0) {
           const int rk = (cst.nRanks == 1) ? cst.myRank : elemRank[fin - 1];
@@ -1235,7 +1281,10 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, const u
                                                              const uint32_t* __restrict__ pend /*dense indices left by k_far_hint (count in counters[2]), or null: all*/) {
   const int lane = threadIdx.x & 31;
   if (pend) nFar = counters[2];
-  constexpr int FW_CHUNK = 256;
+  // records per grab: the list spread over all warps of the grid (a short pending list in 256-record chunks would be walked by a
+  // handful of warps, eight rounds each), between 32 and 256
+  int FW_CHUNK = (nFar / (int)(gridDim.x * (blockDim.x >> 5)) + 31) & ~31;
+  FW_CHUNK = FW_CHUNK < 32 ? 32 : (FW_CHUNK > 256 ? 256 : FW_CHUNK);
   int chunkNext = 0, chunkEnd = 0;   // warp-uniform
   bool drained = false;
   bool active = false;
@@ -1248,7 +1297,7 @@ __global__ void __launch_bounds__(LV_NT, LV_MINB) k_far_walk(FarBuf far, const u
     int status = -1;
     {
       // idle lanes take the next records of the warp's chunk of the list; a new chunk (one atomic on the list's counter per
-      // FW_CHUNK records, not one per refill) when it runs out
+      // chunk, not one per refill) when it runs out
       unsigned need = __ballot_sync(0xffffffffu, !active);
       while (need) {
         if (chunkNext >= chunkEnd) {
