@@ -162,6 +162,19 @@ int piclas_gpu_upload_particles(int64_t n, const double *PartState, const int32_
                                 const int32_t *IsNewPart, const double *PartPosRef, const int64_t *ids,
                                 int32_t append);
 
+/* replaces the initial emission of one Part-Species$-Init$ whose SpaceIC is a lattice with a displacement in x and whose
+ * velocityDistribution is constant (InitialParticleInserting -> SetParticlePosition -> SetParticlePositionSinDeviation /
+ * SetParticlePositionCosDistribution, particle_emission_tools.f90:1235-1371; SinglePointToElement(doHALO=F),
+ * particle_position_and_velocity.f90:434, particle_localization.f90:81-190; SetParticleVelocity 'constant').
+ * SpaceIC: PGPU_EMIT_SIN_DEVIATION / PGPU_EMIT_COS_DISTRIBUTION; maxParticleNumber[3] = maxParticleNumberX/Y/Z;
+ * velocity[3] = VeloIC * VeloVecIC.  Every rank calls it with the same arguments and keeps the positions that lie in its own
+ * elements; IsNewPart is set; particle ids = position in the reference's loop nest (0-based).  Needs the FIBGM tables of the
+ * mesh.  nEmitted: particles this rank accepted. */
+#define PGPU_EMIT_SIN_DEVIATION 1
+#define PGPU_EMIT_COS_DISTRIBUTION 2
+int piclas_gpu_emit_lattice(int32_t SpaceIC, int32_t iSpec, const int32_t *maxParticleNumber, double Amplitude,
+                            double WaveNumber, const double *velocity, int32_t append, int64_t *nEmitted);
+
 /* replaces CALL Deposition() (pic_depo.f90:944-1018).
  * PartSource: LOCAL [nElems][N+1][N+1][N+1][4] == PS_N(iElem)%PartSource(1:4,i,j,k) packed by element;
  * NodeSource: [nUniqueGlobalNodes][4] (cell_volweight_mean only) or NULL.  Either may be NULL. */

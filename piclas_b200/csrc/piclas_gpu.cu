@@ -17,6 +17,7 @@
 #include "ref.cuh"
 #include "sort.cuh"
 #include "bins.cuh"
+#include "emit.cuh"
 
 namespace {
 
@@ -128,6 +129,8 @@ struct Ctx {
   uint32_t* dFarIdx = nullptr;   // [cap] used far slots, densely listed
   int64_t farIdxCap = 0;
   PushElem* dPushElem = nullptr;
+  RefTables locT{};                   // FIBGM + barycentres + radii for SinglePointToElement (emission); zero when the mesh has no FIBGM
+  double globLo[3] = {0., 0., 0.}, globHi[3] = {0., 0., 0.};   // GEO%xminglob .. zmaxglob
   HintNb* dHintNb = nullptr;
   uint32_t* dFarPend = nullptr;   // dense indices of the far records k_far_hint left to the exact walk
   int64_t farPendCap = 0;
@@ -904,14 +907,21 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   // ---- tables shared by RefMapping and the shape functions -----------------------------------------------------------
   g.sfActive = p->DoDeposition && isSF;
   g.ref = isRef;
-  if (g.sfActive || g.ref) {
+  g.locT = RefTables{};
+  for (int d = 0; d < 3; ++d) { g.globLo[d] = m->xyzminglob[d]; g.globHi[d] = m->xyzmaxglob[d]; }
+  if (g.sfActive || g.ref || (m->FIBGM_nElems && m->FIBGM_offsetElem && m->FIBGM_Element && m->ElemBaryNGeo && m->ElemRadius2NGeo)) {
     const int ni0 = m->FIBGMmax[0] - m->FIBGMmin[0] + 1, nj0 = m->FIBGMmax[1] - m->FIBGMmin[1] + 1, nk0 = m->FIBGMmax[2] - m->FIBGMmin[2] + 1;
     const size_t nCells0 = (size_t)ni0 * nj0 * nk0;
     if (upload(&g.dFibN, m->FIBGM_nElems, nCells0)) return 1;
     if (upload(&g.dFibOff, m->FIBGM_offsetElem, nCells0)) return 1;
     if (upload(&g.dFibElem, m->FIBGM_Element, (size_t)m->nFIBGMElemsTotal)) return 1;
     if (upload(&g.dElemBary, m->ElemBaryNGeo, (size_t)nG * 3)) return 1;
-    if (upload(&g.dElemRadius, m->ElemRadiusNGeo, (size_t)nG)) return 1;
+    if (m->ElemRadiusNGeo && upload(&g.dElemRadius, m->ElemRadiusNGeo, (size_t)nG)) return 1;
+    if (m->ElemRadius2NGeo) {   // SinglePointToElement of the emission (any tracking method)
+      if (upload(&g.dElemRadius2, m->ElemRadius2NGeo, (size_t)nG)) return 1;
+      g.locT.geo = g.dGeo; g.locT.ElemBary = g.dElemBary; g.locT.ElemRadius2 = g.dElemRadius2;
+      g.locT.FIBGM_nElems = g.dFibN; g.locT.FIBGM_offsetElem = g.dFibOff; g.locT.FIBGM_Element = g.dFibElem;
+    }
   }
   if (g.ref) {
     if (upload(&g.dElemToBCSides, m->ElemToBCSides, (size_t)nG * 2)) return 1;
@@ -924,8 +934,9 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     if (upload(&g.dBV2, m->BaseVectors2, (size_t)m->nSides * 3)) return 1;
     if (m->BaseVectors3 && upload(&g.dBV3, m->BaseVectors3, (size_t)m->nSides * 3)) return 1;
     if (upload(&g.dSideType, m->SideType, (size_t)m->nSides)) return 1;
-    if (upload(&g.dElemRadius2, m->ElemRadius2NGeo, (size_t)nG)) return 1;
+    if (!g.dElemRadius2 && upload(&g.dElemRadius2, m->ElemRadius2NGeo, (size_t)nG)) return 1;
     if (upload(&g.dElemEpsOneCell, m->ElemEpsOneCell, (size_t)nG)) return 1;
+    g.locT.ElemEpsOneCell = g.dElemEpsOneCell;
     g.refT.geo = g.dGeo; g.refT.ElemToBCSides = g.dElemToBCSides; g.refT.SideBCMetrics = g.dSideBCMetrics; g.refT.SideInfo = g.dSideInfo;
     g.refT.sideInfoSize = m->sideInfoSize; g.refT.SideNormVec = g.dSideNormVec; g.refT.SideDistance = g.dSideDistance;
     g.refT.BaseVectors0 = g.dBV0; g.refT.BaseVectors1 = g.dBV1; g.refT.BaseVectors2 = g.dBV2; g.refT.BaseVectors3 = g.dBV3;
@@ -1195,20 +1206,19 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   return 0;
 }
 
-int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_t* PartSpecies, const int32_t* GlobalElemID,
-                                const int32_t* ParticleInside, const int32_t* IsNewPart, const double* PartPosRef,
-                                const int64_t* ids, int32_t append) {
-  if (!g.ready) return fail("piclas_gpu_upload_particles: not initialised");
-  if (g.exchangePending) return fail("piclas_gpu_upload_particles: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
-  CK(cudaSetDevice(g.device));
-  if (n < 0) return fail("piclas_gpu_upload_particles: n < 0");
-  if (n > 0 && (!PartState || !PartSpecies || !GlobalElemID)) return fail("piclas_gpu_upload_particles: null array");
+// common part of an upload from the host and an emission on the device: `fill(c0, m)` stages records c0 .. c0+m-1 (PartState as
+// [m][6], species, element, ParticleInside, IsNewPart, ids) in g.dStage / g.dStageI / g.dStageL; they are transposed into the particle
+// arrays and the whole population is sorted by element.
+extern "C++" {
+namespace {
+template <class Fill>
+int upload_impl(const char* who, int64_t n, int32_t append, bool haveInside, bool haveIsNew, bool haveIds, bool haveRef, Fill fill) {
   if (g.binned) {   // back to the sorted arrays: the upload appends there and sorts; the next step re-plans the bins
     if (append) { if (bins_to_sorted()) return 1; }
     else { g.binned = false; g.sortedViewValid = false; }
   }
   const int64_t base = append ? g.nPart : 0;
-  if (base + n >= (int64_t)0x7fffffff) return fail("piclas_gpu_upload_particles: more than 2^31-1 particles on one GPU");
+  if (base + n >= (int64_t)0x7fffffff) return fail("%s: more than 2^31-1 particles on one GPU", who);
   if (reserve_particles(base + n)) return 1;
   begin_timing();
   const int64_t chunk = 1 << 22;
@@ -1217,22 +1227,15 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
   for (int64_t c0 = 0; c0 < n; c0 += chunk) {
     const int64_t m = (n - c0 < chunk) ? n - c0 : chunk;
     int32_t* dI = g.dStageI;
-    CK(cudaMemcpyAsync(g.dStage, PartState + c0 * 6, m * 6 * 8, cudaMemcpyHostToDevice, g.st));
-    CK(cudaMemcpyAsync(dI, PartSpecies + c0, m * 4, cudaMemcpyHostToDevice, g.st));
-    CK(cudaMemcpyAsync(dI + g.stageCap, GlobalElemID + c0, m * 4, cudaMemcpyHostToDevice, g.st));
-    if (ParticleInside) CK(cudaMemcpyAsync(dI + 2 * g.stageCap, ParticleInside + c0, m * 4, cudaMemcpyHostToDevice, g.st));
-    if (IsNewPart) CK(cudaMemcpyAsync(dI + 3 * g.stageCap, IsNewPart + c0, m * 4, cudaMemcpyHostToDevice, g.st));
-    if (ids && g.carryIDs) CK(cudaMemcpyAsync(g.dStageL, ids + c0, m * 8, cudaMemcpyHostToDevice, g.st));
+    if (fill(c0, m)) return 1;
     double* dRef = g.dStage + 6 * g.stageCap;
-    const bool haveRef = g.ref && PartPosRef;
-    if (haveRef) CK(cudaMemcpyAsync(dRef, PartPosRef + c0 * 3, m * 3 * 8, cudaMemcpyHostToDevice, g.st));
     k_aos_to_soa<<<(unsigned)((m + 255) / 256), 256, 0, g.st>>>(g.buf[g.cur], base + c0, m, g.dStage, dI, dI + g.stageCap,
-                                                               ParticleInside ? dI + 2 * g.stageCap : nullptr,
-                                                               IsNewPart ? dI + 3 * g.stageCap : nullptr,
-                                                               (ids && g.carryIDs) ? g.dStageL : nullptr, base + c0,
+                                                               haveInside ? dI + 2 * g.stageCap : nullptr,
+                                                               haveIsNew ? dI + 3 * g.stageCap : nullptr,
+                                                               (haveIds && g.carryIDs) ? g.dStageL : nullptr, base + c0,
                                                                haveRef ? dRef : nullptr, g.nGlobalElems, g.prm.nSpecies, g.dCounters + 7);
     ++g.lastLaunches;
-    if (g.ref && !PartPosRef) {  // as at emission: PartPosRef from GetPositionInRefElem in the particle's element
+    if (g.ref && !haveRef) {  // as at emission: PartPosRef from GetPositionInRefElem in the particle's element
       k_init_posref<<<(unsigned)((m + 127) / 128), 128, 0, g.st>>>(g.buf[g.cur], base + c0, m, g.dGeo);
       ++g.lastLaunches;
     }
@@ -1245,8 +1248,8 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
     if (bad) {
       g.nPart = 0;   // the population is unusable: nothing of this upload is kept
       g.hTailOff.assign(g.nRanks + 2, 0);
-      if (bad & 1) return fail("piclas_gpu_upload_particles: GlobalElemID outside 1..nGlobalElems=%d", g.nGlobalElems);
-      return fail("piclas_gpu_upload_particles: PartSpecies outside 1..nSpecies=%d", g.prm.nSpecies);
+      if (bad & 1) return fail("%s: GlobalElemID outside 1..nGlobalElems=%d", who, g.nGlobalElems);
+      return fail("%s: PartSpecies outside 1..nSpecies=%d", who, g.prm.nSpecies);
     }
   }
   const int64_t nIn = base + n;
@@ -1257,9 +1260,79 @@ int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_
   }
   if (sort_and_permute(nIn)) return 1;
   end_timing();
-  if (g.nTotalSorted != g.nPart) return fail("piclas_gpu_upload_particles: %lld particles lie in elements of other ranks",
-                                             (long long)(g.nTotalSorted - g.nPart));
+  if (g.nTotalSorted != g.nPart) return fail("%s: %lld particles lie in elements of other ranks", who, (long long)(g.nTotalSorted - g.nPart));
   return 0;
+}
+}  // namespace
+}  // extern "C++"
+
+int piclas_gpu_upload_particles(int64_t n, const double* PartState, const int32_t* PartSpecies, const int32_t* GlobalElemID,
+                                const int32_t* ParticleInside, const int32_t* IsNewPart, const double* PartPosRef,
+                                const int64_t* ids, int32_t append) {
+  if (!g.ready) return fail("piclas_gpu_upload_particles: not initialised");
+  if (g.exchangePending) return fail("piclas_gpu_upload_particles: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
+  CK(cudaSetDevice(g.device));
+  if (n < 0) return fail("piclas_gpu_upload_particles: n < 0");
+  if (n > 0 && (!PartState || !PartSpecies || !GlobalElemID)) return fail("piclas_gpu_upload_particles: null array");
+  const bool haveRef = g.ref && PartPosRef;
+  return upload_impl("piclas_gpu_upload_particles", n, append, ParticleInside != nullptr, IsNewPart != nullptr, ids != nullptr, haveRef,
+                     [&](int64_t c0, int64_t m) {
+    int32_t* dI = g.dStageI;
+    CK(cudaMemcpyAsync(g.dStage, PartState + c0 * 6, m * 6 * 8, cudaMemcpyHostToDevice, g.st));
+    CK(cudaMemcpyAsync(dI, PartSpecies + c0, m * 4, cudaMemcpyHostToDevice, g.st));
+    CK(cudaMemcpyAsync(dI + g.stageCap, GlobalElemID + c0, m * 4, cudaMemcpyHostToDevice, g.st));
+    if (ParticleInside) CK(cudaMemcpyAsync(dI + 2 * g.stageCap, ParticleInside + c0, m * 4, cudaMemcpyHostToDevice, g.st));
+    if (IsNewPart) CK(cudaMemcpyAsync(dI + 3 * g.stageCap, IsNewPart + c0, m * 4, cudaMemcpyHostToDevice, g.st));
+    if (ids && g.carryIDs) CK(cudaMemcpyAsync(g.dStageL, ids + c0, m * 8, cudaMemcpyHostToDevice, g.st));
+    if (haveRef) CK(cudaMemcpyAsync(g.dStage + 6 * g.stageCap, PartPosRef + c0 * 3, m * 3 * 8, cudaMemcpyHostToDevice, g.st));
+    return 0;
+  });
+}
+
+// replaces the initial emission of one Part-Species[$]-Init[$] with SpaceIC = sin_deviation / cos_distribution and
+// velocityDistribution = constant (SetParticlePosition + SetParticleVelocity, particle_emission.f90 -> particle_position_and_velocity.f90:
+// 257-470, particle_emission_tools.f90:1235-1371): lattice positions, SinglePointToElement(doHALO = F) for each, particles outside the
+// rank's elements dropped, IsNewPart set.
+int piclas_gpu_emit_lattice(int32_t SpaceIC, int32_t iSpec, const int32_t* maxParticleNumber, double Amplitude, double WaveNumber,
+                            const double* velocity, int32_t append, int64_t* nEmitted) {
+  if (!g.ready) return fail("piclas_gpu_emit_lattice: not initialised");
+  if (g.exchangePending) return fail("piclas_gpu_emit_lattice: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
+  CK(cudaSetDevice(g.device));
+  if (SpaceIC != EMIT_SIN_DEVIATION && SpaceIC != EMIT_COS_DISTRIBUTION)
+    return fail("piclas_gpu_emit_lattice: SpaceIC=%d; 1 (sin_deviation) and 2 (cos_distribution) are supported", SpaceIC);
+  if (!maxParticleNumber || !velocity) return fail("piclas_gpu_emit_lattice: null array");
+  if (iSpec < 1 || iSpec > g.prm.nSpecies) return fail("piclas_gpu_emit_lattice: species %d outside 1..nSpecies=%d", iSpec, g.prm.nSpecies);
+  if (maxParticleNumber[0] < 1 || maxParticleNumber[1] < 1 || maxParticleNumber[2] < 1) return fail("piclas_gpu_emit_lattice: maxParticleNumberX/Y/Z < 1");
+  if (SpaceIC == EMIT_COS_DISTRIBUTION && WaveNumber == 0.) return fail("piclas_gpu_emit_lattice: cos_distribution needs WaveNumber /= 0");
+  if (!g.locT.FIBGM_nElems) return fail("piclas_gpu_emit_lattice: the mesh came without the FIBGM tables (GEO%%FIBGM*, FIBGM_Element)");
+  EmitSpec s;
+  s.kind = SpaceIC;
+  s.nx = maxParticleNumber[0]; s.ny = maxParticleNumber[1]; s.nz = maxParticleNumber[2];
+  s.amplitude = Amplitude; s.wavenumber = WaveNumber;
+  for (int d = 0; d < 3; ++d) { s.velo[d] = velocity[d]; s.lo[d] = g.globLo[d]; s.len[d] = fabs(g.globHi[d] - g.globLo[d]); }
+  s.species = iSpec;
+  s.firstLocal = g.offsetElem + 1; s.lastLocal = g.offsetElem + g.nElems;
+  const int64_t n = (int64_t)s.nx * s.ny * s.nz;
+  unsigned long long* dAcc = nullptr;
+  CK(cudaMalloc((void**)&dAcc, 8));
+  CK(cudaMemsetAsync(dAcc, 0, 8, g.st));
+  const int rc = upload_impl("piclas_gpu_emit_lattice", n, append, true, true, true, false, [&](int64_t c0, int64_t m) {
+    int32_t* dI = g.dStageI;
+    if (g.ref)
+      k_emit_lattice<true><<<(unsigned)((m + 127) / 128), 128, 0, g.st>>>(g.locT, g.dTria, s, c0, m, g.dStage, dI, dI + g.stageCap, dI + 2 * g.stageCap,
+                                                                         dI + 3 * g.stageCap, g.dStageL, dAcc);
+    else
+      k_emit_lattice<false><<<(unsigned)((m + 127) / 128), 128, 0, g.st>>>(g.locT, g.dTria, s, c0, m, g.dStage, dI, dI + g.stageCap, dI + 2 * g.stageCap,
+                                                                          dI + 3 * g.stageCap, g.dStageL, dAcc);
+    ++g.lastLaunches;
+    CK(cudaGetLastError());
+    return 0;
+  });
+  unsigned long long acc = 0;
+  if (!rc) cudaMemcpy(&acc, dAcc, 8, cudaMemcpyDeviceToHost);
+  cudaFree(dAcc);
+  if (nEmitted) *nEmitted = (int64_t)acc;
+  return rc;
 }
 
 int64_t piclas_gpu_num_particles(void) { return g.ready ? g.nPart : -1; }
@@ -1702,10 +1775,11 @@ static int push_track_binned(double dt, int32_t* nLost) {
   g.nFar = nFar;
   g.farStats[0] = nFar; g.farStats[1] = hc[4]; g.farStats[2] = hc[5]; g.farStats[3] = hc[6];
   {
-    // Particles that met a full region took the far list (correct, only slower).  Re-planning the capacities costs about three
-    // steps, so it waits until the detour is no longer negligible: more than 0.1 % of the particles in one step
+    // Particles that met a full region took the far list (correct, only slower: about 0.1 ms per million at 5e8 particles, on
+    // top of a step of 37 ms).  Re-planning the capacities costs about 3.5 steps (130 ms there), which a detour of 1 % of the
+    // particles pays back within 30 steps; below that it waits.
     const int64_t diverted = (int64_t)hc[5] + hc[6];
-    int64_t limit = g.nPart / 1000 > 1000 ? g.nPart / 1000 : 1000;
+    int64_t limit = g.nPart / 100 > 1000 ? g.nPart / 100 : 1000;
     if (const char* v = getenv("PICLAS_GPU_REBIN_MIN")) limit = atoll(v);   // tests: re-plan on the first diverted particle
     if (diverted > limit) {
       g.wantRebin = true;                                      // capacities from the new populations before the next step

@@ -89,6 +89,18 @@ INTERFACE
     INTEGER(C_INT64_T),INTENT(OUT) :: nPart(*)                   ! [nSpecies] -> CalcNumPartsOfSpec
     INTEGER(C_INT)                 :: piclas_gpu_kinetic_energy
   END FUNCTION
+  FUNCTION piclas_gpu_emit_lattice(SpaceIC,iSpec,maxParticleNumber,Amplitude,WaveNumber,velocity,append,nEmitted) &
+      BIND(C,NAME='piclas_gpu_emit_lattice')
+    IMPORT :: C_INT, C_INT32_T, C_INT64_T, C_DOUBLE
+    INTEGER(C_INT32_T),VALUE       :: SpaceIC                    ! 1 sin_deviation, 2 cos_distribution
+    INTEGER(C_INT32_T),VALUE       :: iSpec
+    INTEGER(C_INT32_T),INTENT(IN)  :: maxParticleNumber(3)       ! Species(iSpec)%Init(iInit)%maxParticleNumberX/Y/Z
+    REAL(C_DOUBLE),VALUE           :: Amplitude, WaveNumber
+    REAL(C_DOUBLE),INTENT(IN)      :: velocity(3)                ! VeloIC*VeloVecIC
+    INTEGER(C_INT32_T),VALUE       :: append
+    INTEGER(C_INT64_T),INTENT(OUT) :: nEmitted
+    INTEGER(C_INT)                 :: piclas_gpu_emit_lattice
+  END FUNCTION
   FUNCTION piclas_gpu_set_field(E) BIND(C,NAME='piclas_gpu_set_field')
     IMPORT :: C_INT, C_DOUBLE
     REAL(C_DOUBLE),INTENT(IN) :: E(3,*)                          ! packed [3,nDOF_local]
@@ -189,6 +201,7 @@ PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_p
 PUBLIC :: piclas_gpu_exchange_info, piclas_gpu_exchange_recv_buffer, piclas_gpu_exchange_finish
 PUBLIC :: piclas_gpu_nodesource_device, piclas_gpu_sf_halo_info, piclas_gpu_deposit_finish, piclas_gpu_phase_timing
 PUBLIC :: piclas_gpu_last_timing, piclas_gpu_node_halo_info, piclas_gpu_set_stream, piclas_gpu_exchange_device_info
+PUBLIC :: piclas_gpu_emit_lattice
 PUBLIC :: ParticleStepGPU, GPUAbortOnError
 
 CONTAINS

@@ -75,6 +75,14 @@ class ParticleStep {
   void KineticEnergy(double* Ekin, int64_t* nPart) {
     if (piclas_gpu_kinetic_energy(Ekin, nPart)) throw Abort("piclas_gpu_kinetic_energy");
   }
+  // initial emission with SpaceIC = sin_deviation (1) / cos_distribution (2), velocityDistribution = constant
+  // (particle_emission_tools.f90:1235-1371 + SinglePointToElement); returns the particles this rank accepted
+  int64_t EmitLattice(int32_t SpaceIC, int32_t iSpec, const int32_t maxParticleNumber[3], double Amplitude, double WaveNumber,
+                      const double velocity[3], bool append = false) {
+    int64_t n = 0;
+    if (piclas_gpu_emit_lattice(SpaceIC, iSpec, maxParticleNumber, Amplitude, WaveNumber, velocity, append ? 1 : 0, &n)) throw Abort("piclas_gpu_emit_lattice");
+    return n;
+  }
   int nSpecies() const { return nSpecies_; }
 
   // One pass of TimeStepPoissonByBorisLeapfrog (or TimeStepPoisson with TimeDiscMethod 509): the HDG solve stays with the host and is

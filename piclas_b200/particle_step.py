@@ -140,6 +140,23 @@ class ParticleStep:
         self._check(self.lib.piclas_gpu_kinetic_energy(_f(E), _l(N)))
         return E, N
 
+    def EmitLattice(self, SpaceIC, iSpec, maxParticleNumber, Amplitude=0.0, WaveNumber=0.0, velocity=(0.0, 0.0, 0.0), append=False) -> int:
+        """Initial emission on the device: SpaceIC 'sin_deviation' / 'cos_distribution' (particle_emission_tools.f90:1235-1371) with
+        velocityDistribution = constant, localisation by SinglePointToElement (particle_localization.f90:81-190).  Returns the number
+        of particles this rank accepted."""
+        kinds = {"sin_deviation": 1, "cos_distribution": 2}
+        if SpaceIC not in kinds:
+            raise PiclasGpuError(f"EmitLattice: SpaceIC={SpaceIC!r}; supported: {sorted(kinds)}")
+        n3 = np.ascontiguousarray(maxParticleNumber, dtype=np.int32)
+        v3 = np.ascontiguousarray(velocity, dtype=np.float64)
+        if n3.shape != (3,) or v3.shape != (3,):
+            raise PiclasGpuError("EmitLattice: maxParticleNumber and velocity take three entries")
+        ne = C.c_int64(0)
+        self._check(self.lib.piclas_gpu_emit_lattice(C.c_int32(kinds[SpaceIC]), C.c_int32(int(iSpec)), n3.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                     C.c_double(Amplitude), C.c_double(WaveNumber), _f(v3), C.c_int32(int(bool(append))),
+                                                     C.byref(ne)))
+        return int(ne.value)
+
     def SetField(self, E):
         """U_N(iElem)%E(1:3,i,j,k) packed as [nElems,k,j,i,3] after CALL HDG (hdg/elem_mat.f90:709)."""
         E = np.ascontiguousarray(E, dtype=np.float64)

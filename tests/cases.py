@@ -155,6 +155,62 @@ def sin_deviation(xmin, xmax, nx, ny, nz, amplitude, wavenumber):
     return np.array(pos)
 
 
+def cos_distribution(xmin, xmax, nx, ny, nz, amplitude, wavenumber):
+    """SetParticlePositionCosDistribution (particle_emission_tools.f90:1299-1371): x from the inverse of F(x) = x + a/w sin(w x)
+    by Newton's method (residual <= 1e-12), y and z on the cell centres; loop order as written there."""
+    xmin, xmax = np.asarray(xmin, dtype=np.float64), np.asarray(xmax, dtype=np.float64)
+    xlen, ylen, zlen = np.abs(xmax - xmin)
+    x_step, y_step, z_step = xlen / nx, ylen / ny, zlen / nz
+    a, w = amplitude, wavenumber
+    pos = []
+    for i in range(1, nx + 1):
+        x_uniform = i * x_step - x_step * 0.5
+        x_pos = x_uniform
+        while abs(x_pos + a / w * np.sin(w * x_pos) - x_uniform) > 1e-12:
+            x_pos = x_pos - (x_pos + a / w * np.sin(w * x_pos) - x_uniform) / (1 + a * np.cos(w * x_pos))
+        x = xmin[0] + x_pos
+        for j in range(1, ny + 1):
+            y = xmin[1] + j * y_step - y_step * 0.5
+            for k in range(1, nz + 1):
+                pos.append((x, y, xmin[2] + k * z_step - z_step * 0.5))
+    return np.array(pos)
+
+
+def single_point_to_element(mesh, orc, X, first=None, last=None, refmapping=False):
+    """SinglePointToElement(doHALO=F) (particle_localization.f90:81-190) for many points: FIBGM cell by CEILING, the cell's
+    elements within ElemRadius2NGeo of the point, nearest barycentre first (stable order), the first one that holds the point
+    (ParticleInsideQuad3D, or MAXVAL|xi| <= ElemEpsOneCell under RefMapping) among the elements first..last; -1 otherwise.
+    The element tests are the oracle's."""
+    fb = mesh.extra["FIBGM"]
+    first = 1 if first is None else first
+    last = mesh.nElems if last is None else last
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    out = np.full(len(X), -1, dtype=np.int32)
+    ni, nj, nk = fb["max"]
+    nE, off, El = fb["nElems"].reshape(-1), fb["offsetElem"].reshape(-1), fb["Element"]
+    for p, x in enumerate(X):
+        c = np.ceil((x - mesh.xyz_min) / fb["deltas"]).astype(np.int64)
+        c = np.maximum(np.minimum(np.array([ni, nj, nk]), c), 1)
+        cell = (c[0] - 1) + ni * ((c[1] - 1) + nj * (c[2] - 1))
+        cand = El[off[cell]:off[cell] + nE[cell]]
+        d2 = ((x[None, :] - mesh.ElemBaryNGeo[cand - 1]) ** 2).sum(axis=1)
+        keep = d2 <= mesh.ElemRadius2NGeo[cand - 1]
+        order = np.argsort(np.where(keep, d2, -1.0), kind="stable")
+        for i in order:
+            e = int(cand[i])
+            if not keep[i] or e < first or e > last:
+                continue
+            if refmapping:
+                xi, suc, _ = orc.position_in_ref_elem(x[None, :], np.array([e], dtype=np.int32), force=False)
+                ok = bool(suc[0]) and np.abs(xi[0]).max() <= mesh.extra["ElemEpsOneCell"][e - 1]
+            else:
+                ok = bool(orc.inside(x[None, :], np.array([e], dtype=np.int32))[0][0])
+            if ok:
+                out[p] = e
+                break
+    return out
+
+
 def electron_params(**kw):
     d = dict(ChargeIC=(-QE,), MassIC=(ME,), MacroParticleFactor=(1.0e3,), DepositionType=DEPO_CVWM,
              TimeDiscMethod=TIMEDISC_BORIS_LEAPFROG, carryParticleIDs=1)
