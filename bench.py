@@ -151,7 +151,7 @@ def hbm_peak():
 
 
 # FP64 work the interpolate+push+track phase executes per particle, from the committed ncu capture of this round's kernels
-# (profiles/r2_traffic.json: (2 DFMA + DMUL + DADD) thread instructions of k_bin_push + k_far_walk / particles): the numerator of the
+# (profiles/r2_traffic.json: (2 DFMA + DMUL + DADD) thread instructions of k_bin_push + k_far_hint + k_far_walk / particles): the numerator of the
 # FP64 roofline, the bound SURVEY.md F7 expects
 def fp64_flop_per_particle():
     try:
@@ -221,7 +221,7 @@ def cpu_baseline(args, N, threads=None, steps=None, warmup=1):
 def kernel_names(variant):
     if variant == "ref_sf":
         return "k_interp_push + k_track_ref (interpolate+push+RefMapping tracking phase)"
-    return "k_bin_push + k_far_walk (interpolate + push + track + delivery on the binned layout)"
+    return "k_bin_push + k_far_hint + k_far_walk (interpolate + push + track + delivery on the binned layout)"
 
 
 def config_dict(args, n_total):

@@ -274,7 +274,7 @@ def run_bench_multi(args, rank, world, local):
                 "dtype": "f64", "data": "synthetic", "config": B.config_dict(args, n_total), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(cnt[2].item()), "particles_end": int(cnt[0].item()),
                 "migrated_per_step": int(cnt[1].item()) // max(args.steps, 1),
-                "roofline": {"bound": "hbm", "kernel": "k_bin_push + k_far_walk (per GPU, slowest rank)",
+                "roofline": {"bound": "hbm", "kernel": "k_bin_push + k_far_hint + k_far_walk (per GPU, slowest rank)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": B.measured_traffic(per_gpu)[0],
                              "traffic_source": B.measured_traffic(per_gpu)[1],
                              "peak_source": peak_src,

@@ -37,12 +37,12 @@ for r in rows[2:]:
             f += w * float(r[ix[k]].replace(",", "")) * cyc
     d["fp64_flop"] = f
     kern[name] = d
-dom = [k for k in kern if k.startswith("k_bin_push") or k.startswith("k_far_walk")]
+dom = [k for k in kern if k.startswith("k_bin_push") or k.startswith("k_far_walk") or k.startswith("k_far_hint")]
 res = {"particles": npart, "kernels": {k: {kk: vv for kk, vv in v.items()} for k, v in kern.items()},
        "dram_bytes_per_particle_interp_push_track": sum(kern[k]["dram_read_bytes"] + kern[k]["dram_write_bytes"] for k in dom) / npart,
        "fp64_flop_per_particle_interp_push_track": sum(kern[k]["fp64_flop"] for k in dom) / npart,
        "dram_bytes_per_particle_step": sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in kern.values()) / npart,
-       "source": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum of k_bin_push and k_far_walk at 32^3 elements, "
+       "source": "ncu --set full --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum of k_bin_push, k_far_hint and k_far_walk at 32^3 elements, "
                  "%.4g particles (1907 per element, as the flagship workload); profiles/r2_ncu_full_32cube_summary.txt" % npart}
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps({k: res[k] for k in res if k != "kernels"}, indent=1))
