@@ -137,6 +137,8 @@ struct Ctx {
   int binParity = 0;
   int64_t nFar = 0;              // records of the far list of the open step
   double mainSlack = 0.10, inFrac = 0.09;
+  bool inFracCapped = false;     // a larger inbox share did not fit into the memory: no re-plan for full inboxes any more
+  double detourMs = 0.;          // time the diverted particles have cost since the bins were planned (estimate)
   int64_t farStats[4] = {0, 0, 0, 0};   // last step: far records, side movers, overflowed main, overflowed inbox
   // timing
   double lastMs = 0.;
@@ -1775,14 +1777,18 @@ static int push_track_binned(double dt, int32_t* nLost) {
   g.nFar = nFar;
   g.farStats[0] = nFar; g.farStats[1] = hc[4]; g.farStats[2] = hc[5]; g.farStats[3] = hc[6];
   {
-    // Particles that met a full region took the far list (correct, only slower: about 0.1 ms per million at 5e8 particles, on
-    // top of a step of 37 ms).  Re-planning the capacities costs about 3.5 steps (130 ms there), which a detour of 1 % of the
-    // particles pays back within 30 steps; below that it waits.
+    // Particles that met a full region took the far list (correct, only slower: 0.1 ns per record, measured as 3.4 ms for 3.6e7 far
+    // records).  Re-planning the capacities costs about 3.5 steps (130 ms at 5e8 particles), so it waits until the detours since
+    // the last plan have cost as much (rent or buy: at most twice the cost of the best choice in hindsight).
     const int64_t diverted = (int64_t)hc[5] + hc[6];
-    int64_t limit = g.nPart / 100 > 1000 ? g.nPart / 100 : 1000;
-    if (const char* v = getenv("PICLAS_GPU_REBIN_MIN")) limit = atoll(v);   // tests: re-plan on the first diverted particle
-    if (diverted > limit) {
+    const double pushMs = host_ms() - t0;   // the push kernel has been waited for (nFar read back): about 3/4 of a step
+    g.detourMs += 1.0e-7 * (double)diverted;
+    bool replan = g.detourMs > 4.5 * pushMs;
+    if (const char* v = getenv("PICLAS_GPU_REBIN_MIN")) replan = diverted > atoll(v);   // tests: re-plan on the first diverted particle
+    if (hc[6] > hc[5] && g.inFracCapped && !getenv("PICLAS_GPU_REBIN_MIN")) replan = false;   // larger inboxes do not fit
+    if (replan) {
       g.wantRebin = true;                                      // capacities from the new populations before the next step
+      g.detourMs = 0.;
       if (hc[6] > hc[5] && g.inFrac < 0.5) g.inFrac *= 2.0;    // inboxes too small for this flow (drifting populations)
     }
   }

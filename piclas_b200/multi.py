@@ -172,7 +172,7 @@ def run_bench_multi(args, rank, world, local):
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     parity = B.small_parity_check(rank, world, local, args.arithmetic) if not getattr(args, "no_checks", False) else None
-    mesh, E, dt, vth = B.workload(args.nelem, args.N)
+    mesh, E, dt, vth = B.workload(args.nelem, args.N, kick=args.kick)
     n_total = int(args.particles)
     prm = Params(ChargeIC=(-B.QE,), MassIC=(B.ME,), MacroParticleFactor=(1.0e3,), device=local, arithmetic=args.arithmetic)
     off = hm.partition(mesh, world)
