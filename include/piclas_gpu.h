@@ -146,6 +146,11 @@ typedef struct pgpu_params {
   int64_t maxParticleNumber;    /* PDM%maxParticleNumber (capacity of the device SoA)                    */
   int32_t carryParticleIDs;     /* 1: carry a 64-bit id per particle through sort/migration (tests)      */
   int32_t arithmetic;           /* 0: reference operation order everywhere; 1: restructured (<=1e-12)    */
+  /* options of the reference whose non-default values change the sources / the push and are NOT implemented: piclas_gpu_init
+   * fails for any value but 0 ("abort, never ignore") */
+  int32_t PartLorentzType;      /* Part-LorentzType: 0 = non-relativistic (default)  particle_rhs.f90:90-123 */
+  int32_t NoDirichletDeposition;/* .NOT. PIC-DoDirichletDeposition (NullifyNodeSourceDirichletSides) pic_depo_method.f90:692-697 */
+  int32_t DoDielectricSurfaceCharge; /* NodeSourceExt / NodeSourceExtTmp                pic_depo.f90:281-284 */
 } pgpu_params_t;
 
 /* after InitParticleMesh + InitializeDeposition (piclaslib.f90:177) */

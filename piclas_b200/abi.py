@@ -68,6 +68,7 @@ class pgpu_params_t(C.Structure):
         ("sfDepo3D", C.c_int32), ("w_sf", C.c_double), ("dimFactorSF", C.c_double),
         ("device", C.c_int32), ("myRank", C.c_int32), ("nRanks", C.c_int32),
         ("maxParticleNumber", C.c_int64), ("carryParticleIDs", C.c_int32), ("arithmetic", C.c_int32),
+        ("PartLorentzType", C.c_int32), ("NoDirichletDeposition", C.c_int32), ("DoDielectricSurfaceCharge", C.c_int32),
     ]
 
 
@@ -105,6 +106,9 @@ class Params:
     maxParticleNumber: int = 0
     carryParticleIDs: int = 0
     arithmetic: int = 0
+    PartLorentzType: int = 0            # only 0 (non-relativistic) is implemented; anything else fails at init
+    NoDirichletDeposition: int = 0      # .NOT. PIC-DoDirichletDeposition
+    DoDielectricSurfaceCharge: int = 0
 
 
 def _p(arr, typ):
@@ -199,7 +203,8 @@ class Marshalled:
         for k in ("TrackingMethod", "RefMappingGuess", "RefMappingEps", "CartesianPeriodic", "TimeDiscMethod",
                   "DoInterpolation", "DoDeposition", "DepositionType", "c2_inv", "r_sf", "alpha_sf", "dim_sf",
                   "dim_sf_dir", "sfDepo3D", "w_sf", "dimFactorSF", "device", "myRank", "nRanks",
-                  "maxParticleNumber", "carryParticleIDs", "arithmetic"):
+                  "maxParticleNumber", "carryParticleIDs", "arithmetic", "PartLorentzType", "NoDirichletDeposition",
+                  "DoDielectricSurfaceCharge"):
             setattr(p, k, getattr(params, k))
         for d in range(6):
             p.externalField[d] = float(params.externalField[d])

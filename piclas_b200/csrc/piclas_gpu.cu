@@ -665,6 +665,9 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   if (p->TimeDiscMethod != PGPU_TIMEDISC_BORIS_LEAPFROG && p->TimeDiscMethod != PGPU_TIMEDISC_LEAPFROG)
     return fail("piclas_gpu_init: TimeDiscMethod=%d not supported (508 Boris-Leapfrog, 509 Leapfrog)", p->TimeDiscMethod);
   if (p->CartesianPeriodic) return fail("piclas_gpu_init: CartesianPeriodic=T not supported");
+  if (p->PartLorentzType != 0) return fail("piclas_gpu_init: Part-LorentzType=%d; only non-relativistic (0) is implemented for the new-particle half step", p->PartLorentzType);
+  if (p->NoDirichletDeposition) return fail("piclas_gpu_init: PIC-DoDirichletDeposition=F (NullifyNodeSourceDirichletSides) is not implemented");
+  if (p->DoDielectricSurfaceCharge) return fail("piclas_gpu_init: DoDielectricSurfaceCharge=T (NodeSourceExt) is not implemented");
   if (p->RefMappingGuess == 2) return fail("piclas_gpu_init: RefMappingGuess=2 not supported (use 1, 3 or 4)");
   if (p->RefMappingGuess < 1 || p->RefMappingGuess > 4) return fail("piclas_gpu_init: RefMappingGuess=%d invalid", p->RefMappingGuess);
   if (p->nSpecies < 1 || p->nSpecies > 32) return fail("piclas_gpu_init: nSpecies=%d outside 1..32", p->nSpecies);
@@ -858,7 +861,12 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
   }
 
   // ---- cell_volweight_mean tables ---------------------------------------------------------------------------------
-  {
+  // The reference builds ElemNodeID for TriaTracking only (particle_mesh.f90:411-450) and NodeVolume / Periodic_* for
+  // cell_volweight_mean only: the pointers are read in that mode alone (a host may pass NULL otherwise).
+  CK(cudaMalloc((void**)&g.dPartSource, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 4 * 8));
+  if (p->DoDeposition && p->DepositionType == PGPU_DEPO_CVWM) {
+    if (!m->ElemNodeID || !m->NodeInfo || !m->Periodic_nNodes || !m->Periodic_offsetNode || !m->NodeVolume || (m->nPeriodicNodesTotal > 0 && !m->Periodic_Nodes))
+      return fail("piclas_gpu_init: cell_volweight_mean needs ElemNodeID, NodeInfo, Periodic_nNodes / offsetNode / Nodes and NodeVolume");
     std::vector<int32_t> elemNodeU((size_t)g.nElems * 8), cnt(g.nNodes + 1, 0);
     for (int e = 0; e < g.nElems; ++e)
       for (int c = 0; c < 8; ++c) {
@@ -881,7 +889,6 @@ int piclas_gpu_init(const pgpu_mesh_t* m, const pgpu_params_t* p) {
     CK(cudaMalloc((void**)&g.dElemAcc, (size_t)(g.nElems ? g.nElems : 1) * 32 * 8));
     CK(cudaMalloc((void**)&g.dS, (size_t)g.nNodes * 4 * 8));
     CK(cudaMalloc((void**)&g.dNodeSource, (size_t)g.nNodes * 4 * 8));
-    CK(cudaMalloc((void**)&g.dPartSource, (size_t)(g.nElems ? g.nElems : 1) * g.ND * 4 * 8));
   }
 
   if (g.nRanks > 1 && p->DoDeposition && p->DepositionType == PGPU_DEPO_CVWM) {

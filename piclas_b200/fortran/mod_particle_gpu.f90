@@ -46,6 +46,7 @@ TYPE, BIND(C) :: pgpu_params_t
   INTEGER(C_INT32_T) :: device, myRank, nRanks
   INTEGER(C_INT64_T) :: maxParticleNumber
   INTEGER(C_INT32_T) :: carryParticleIDs, arithmetic
+  INTEGER(C_INT32_T) :: PartLorentzType, NoDirichletDeposition, DoDielectricSurfaceCharge   ! must be 0: not implemented
 END TYPE
 
 INTERFACE

@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
+import sys
 import time
 
 import numpy as np
@@ -87,8 +88,30 @@ class ParticleStepRank:
         # the library works on torch's current stream: its kernels and the NCCL collectives issued below are then ordered on the
         # device, no host synchronisation between them
         self._check(self.lib.piclas_gpu_set_stream(C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        # PICLAS_MULTI_TIMING=1: CUDA-event marks between the calls of a step (bench diagnostics; events only, no synchronisation)
+        self._marks = [] if os.environ.get("PICLAS_MULTI_TIMING") else None
         self._wrapped = {}                                                   # (device pointer, capacity) -> tensor over the whole buffer
         self._rcnt = torch.zeros(world, dtype=torch.int64, device=self.device)
+
+    def _mark(self, name):
+        if self._marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev, time.perf_counter()))
+
+    def timing_report(self):
+        """Average milliseconds between consecutive marks, on the device (events) and on the host (perf_counter)."""
+        if not self._marks:
+            return {}
+        torch.cuda.synchronize()
+        acc, cnt = {}, {}
+        for (n0, e0, h0), (n1, e1, h1) in zip(self._marks[:-1], self._marks[1:]):
+            k = n0 + " -> " + n1
+            a = acc.setdefault(k, [0.0, 0.0])
+            a[0] += e0.elapsed_time(e1)
+            a[1] += 1e3 * (h1 - h0)
+            cnt[k] = cnt.get(k, 0) + 1
+        return {k: (round(v[0] / cnt[k], 3), round(v[1] / cnt[k], 3)) for k, v in acc.items()}
 
     def _buffer(self, ptr, cap, typestr="<f8"):
         """Tensor over a whole device buffer of the library, wrapped once (wrapping costs tens of microseconds) and sliced per step."""
@@ -112,7 +135,9 @@ class ParticleStepRank:
         cs = C.c_int32(0)
         nsend = (C.c_int64 * world)()
         sp = C.c_void_p(0)
+        self._mark("exchange_info")
         self._check(self.lib.piclas_gpu_exchange_info(C.byref(cs), nsend, C.byref(sp)))
+        self._mark("counts")
         send_counts = [int(nsend[r]) for r in range(world)]
         # counts to / from every rank (IRecvNbOfParticles / SendNbOfParticles): the library left them on the device as well
         cp = C.c_void_p(0)
@@ -120,6 +145,7 @@ class ParticleStepRank:
         self._check(self.lib.piclas_gpu_exchange_device_info(C.byref(cp), C.byref(scap), C.byref(rcap)))
         dist.all_to_all_single(self._rcnt, self._buffer(cp.value, world, "<i8"), group=self.group)
         recv_counts = [int(v) for v in self._rcnt.tolist()]
+        self._mark("messages")
         nrecv = sum(recv_counts)
         rp = C.c_void_p(0)
         self._check(self.lib.piclas_gpu_exchange_recv_buffer(C.c_int64(nrecv), C.byref(rp)))
@@ -128,11 +154,14 @@ class ParticleStepRank:
         sbuf = self._buffer(sp.value, scap.value)[:nsd] if nsd else torch.empty(0, dtype=torch.float64, device=self.device)
         rbuf = self._buffer(rp.value, rcap.value)[:nrd] if nrd else torch.empty(0, dtype=torch.float64, device=self.device)
         exchange_particles(sbuf, send_counts, rbuf, recv_counts, cs.value, self.group)
+        self._mark("exchange_finish")
         self._check(self.lib.piclas_gpu_exchange_finish(C.c_int64(nrecv)))
+        self._mark("step_end")
         self.migrated = sum(send_counts)
         return sum(send_counts), nrecv
 
     def PushAndTrack(self, dt, it=0):
+        self._mark("push_track")
         lost = self.step.PushAndTrack(dt, it)
         self.exchange()
         return lost
@@ -153,7 +182,9 @@ class ParticleStepRank:
             PS = out_partsource if out_partsource is not None else (np.empty(self.step._ps_shape) if want_partsource else None)
             self._check(self.lib.piclas_gpu_deposit_finish(_f(PS), _f(None)))
             return PS, None
+        self._mark("deposit")
         self._check(self.lib.piclas_gpu_deposit(_f(None), _f(None)))       # rank-local node sums
+        self._mark("node_halo")
         # node halo on the compact list of shared nodes: all-gather, then the library adds the ranks' parts in rank order
         nd = C.c_int64(0)
         sp, rp = C.c_void_p(0), C.c_void_p(0)
@@ -162,6 +193,7 @@ class ParticleStepRank:
             dist.all_gather_into_tensor(self._buffer(rp.value, nd.value * self.world), self._buffer(sp.value, nd.value), group=self.group)
         PS = out_partsource if out_partsource is not None else (np.empty(self.step._ps_shape) if want_partsource else None)
         NS = np.empty((self.mesh.nUniqueNodes, 4)) if want_nodesource else None
+        self._mark("deposit_finish")
         self._check(self.lib.piclas_gpu_deposit_finish(_f(PS), _f(NS)))
         return PS, NS
 
@@ -218,6 +250,8 @@ def run_bench_multi(args, rank, world, local):
         sampler.start()
     dist.barrier()
     torch.cuda.synchronize()
+    if R._marks is not None:
+        R._marks.clear()
     t0 = time.perf_counter()
     launches, phases, migrated = 0, np.zeros(4), 0
     for _ in range(args.steps):
@@ -228,6 +262,11 @@ def run_bench_multi(args, rank, world, local):
     torch.cuda.synchronize()
     dist.barrier()
     wall = time.perf_counter() - t0
+    if R._marks is not None:
+        rep = R.timing_report()
+        R._marks = None
+        if rank == 0 or rank == world - 1:
+            print("[multi timing rank %d] (device ms, host ms) " % rank + json.dumps(rep), file=sys.stderr)
     clocks = sampler.stop() if sampler else None
     tmax = torch.tensor([wall], dtype=torch.float64, device="cuda")
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

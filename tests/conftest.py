@@ -23,8 +23,8 @@ def _has_gpu():
         return False
 
 
-# Modules whose -m gpu tests were written after the round-1 GPU minutes were spent run last, the most involved ones at the very
-# end, so that under `pytest -x` a failure there cannot hide tests that have already passed on a B200.
+# The longest-running modules of the -m gpu suite (reference fixtures, compiled host, full-size properties) run last, so that under
+# `pytest -x` a failure there cannot hide the quick parity tests.
 _RUN_LAST = ["test_reference_deposition", "test_reference_shapefunction", "test_zz_host_cpp", "test_zz_gpu_properties",
              "test_reference_push", "test_reference_tracking"]
 

@@ -139,3 +139,14 @@ def test_partposref_download_after_cvwm_deposit(arith):
         xi, _, _ = orc.position_in_ref_elem(d["PartState"][:, :3], d["GlobalElemID"])
         assert np.abs(d["PartPosRef"] - xi).max() <= 1e-12
     orc.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("field,match", [("PartLorentzType", "LorentzType"), ("NoDirichletDeposition", "DoDirichletDeposition"),
+                                         ("DoDielectricSurfaceCharge", "DielectricSurfaceCharge")])
+def test_unimplemented_reference_options_are_rejected_at_init(field, match):
+    """Options of the reference that change the sources / the push and are not implemented abort at init instead of being ignored."""
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (2, 2, 2), 2)
+    prm = cases.electron_params(**{field: 1})
+    with pytest.raises(PiclasGpuError, match=match):
+        ParticleStep(mesh, prm)
