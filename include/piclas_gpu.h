@@ -190,6 +190,15 @@ int piclas_gpu_deposit(double *PartSource, double *NodeSource);
  * copies that one component, LOCAL [nElems][N+1][N+1][N+1], a quarter of the PartSource transfer. */
 int piclas_gpu_get_charge(double *ChargeDensity);
 
+/* PartSource of the last deposition to the host without stopping the step: the device -> host copy runs on its own stream, behind
+ * the deposition and beside the calls that follow (the host -> device copy of piclas_gpu_set_field uses the other direction of the
+ * link).  The HDG source term needs PS_N%PartSource(4,:) only (piclas_gpu_get_charge above, equations/poisson/equation.f90:1043);
+ * the current density PartSource(1:3,:) is read by output and analysis (timedisc.f90:399-410), i.e. after the step.  PartSource:
+ * LOCAL [nElems][N+1][N+1][N+1][4], page-locked host memory for a truly asynchronous copy.  The next piclas_gpu_deposit waits on
+ * the device for the copy; the host reads the array after piclas_gpu_partsource_wait. */
+int piclas_gpu_get_partsource_async(double *PartSource);
+int piclas_gpu_partsource_wait(void);
+
 /* replaces CalcKineticEnergy / CalcNumPartsOfSpec of the particle analysis (particle_analyze_tools.f90:709-842) so that
  * PartAnalyze.csv needs no particle download: Ekin[nSpecies] in Joule (0.5 m v^2 below RelativisticLimit = (1e6/299792458)^2 c^2,
  * (gamma-1) m c^2 above; times MacroParticleFactor), nPart[nSpecies] simulation particles.  Either may be NULL. */

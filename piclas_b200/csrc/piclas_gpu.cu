@@ -131,6 +131,9 @@ struct Ctx {
   PushElem* dPushElem = nullptr;
   RefTables locT{};                   // FIBGM + barycentres + radii for SinglePointToElement (emission); zero when the mesh has no FIBGM
   double globLo[3] = {0., 0., 0.}, globHi[3] = {0., 0., 0.};   // GEO%xminglob .. zmaxglob
+  cudaStream_t stCopy = nullptr;      // piclas_gpu_get_partsource_async: device -> host copy beside the step's own stream
+  cudaEvent_t evDepoDone = nullptr, evCopyDone = nullptr;
+  bool psCopyPending = false;
   HintNb* dHintNb = nullptr;
   uint32_t* dFarPend = nullptr;   // dense indices of the far records k_far_hint left to the exact walk
   int64_t farPendCap = 0;
@@ -617,6 +620,7 @@ int piclas_gpu_finalize(void) {
   for (int i = 0; i < 10; ++i) if (g.evp[i]) cudaEventDestroy(g.evp[i]);
   if (g.ev0) cudaEventDestroy(g.ev0);
   if (g.ev1) cudaEventDestroy(g.ev1);
+  if (g.stCopy) { cudaStreamSynchronize(g.stCopy); cudaStreamDestroy(g.stCopy); cudaEventDestroy(g.evDepoDone); cudaEventDestroy(g.evCopyDone); }
   if (g.st && g.ownStream) cudaStreamDestroy(g.st);
   if (g.hPin) cudaFreeHost(g.hPin);
   cudaFree(g.dSendCounts); cudaFree(g.dEmigCnt);
@@ -1509,6 +1513,7 @@ int piclas_gpu_deposit(double* PartSource, double* NodeSource) {
   if (!g.prm.DoDeposition) return fail("piclas_gpu_deposit: PIC-DoDeposition=F");
   if (g.exchangePending) return fail("piclas_gpu_deposit: the particle exchange of the last step is still open (piclas_gpu_exchange_finish)");
   CK(cudaSetDevice(g.device));
+  if (g.psCopyPending) CK(cudaStreamWaitEvent(g.st, g.evCopyDone, 0));   // the last PartSource is still on its way to the host
   begin_timing();
   if (g.sfActive) {
     if (NodeSource) return fail("piclas_gpu_deposit: NodeSource exists for cell_volweight_mean only");
@@ -1554,6 +1559,38 @@ int piclas_gpu_get_charge(double* ChargeDensity) {
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(ChargeDensity, g.dCharge, (size_t)n * 8, cudaMemcpyDeviceToHost, g.st));
   CK(cudaStreamSynchronize(g.st));
+  return 0;
+}
+
+// PartSource of the last deposition to the host WITHOUT stopping the step: the copy runs on its own stream behind the deposition
+// and beside what follows (piclas_gpu_set_field's host -> device copy uses the other direction of the link, the push kernels the
+// SMs).  The Poisson solve needs the charge component only (piclas_gpu_get_charge); the current density is output / analysis data.
+int piclas_gpu_get_partsource_async(double* PartSource) {
+  if (!g.ready) return fail("piclas_gpu_get_partsource_async: not initialised");
+  if (!g.prm.DoDeposition) return fail("piclas_gpu_get_partsource_async: PIC-DoDeposition=F");
+  if (!PartSource) return fail("piclas_gpu_get_partsource_async: null array");
+  CK(cudaSetDevice(g.device));
+  if (!g.stCopy) {
+    CK(cudaStreamCreateWithFlags(&g.stCopy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.evDepoDone, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.evCopyDone, cudaEventDisableTiming));
+  }
+  const size_t bytes = (size_t)g.nElems * g.ND * 4 * 8;
+  CK(cudaEventRecord(g.evDepoDone, g.st));
+  CK(cudaStreamWaitEvent(g.stCopy, g.evDepoDone, 0));
+  if (bytes) CK(cudaMemcpyAsync(PartSource, g.dPartSource, bytes, cudaMemcpyDeviceToHost, g.stCopy));
+  CK(cudaEventRecord(g.evCopyDone, g.stCopy));
+  g.psCopyPending = true;
+  return 0;
+}
+
+// blocks until the array of the last piclas_gpu_get_partsource_async is complete on the host
+int piclas_gpu_partsource_wait(void) {
+  if (!g.ready) return fail("piclas_gpu_partsource_wait: not initialised");
+  if (!g.psCopyPending) return 0;
+  CK(cudaSetDevice(g.device));
+  CK(cudaEventSynchronize(g.evCopyDone));
+  g.psCopyPending = false;
   return 0;
 }
 

@@ -84,6 +84,15 @@ INTERFACE
     REAL(C_DOUBLE),INTENT(OUT) :: ChargeDensity(*)               ! packed [nDOF_local] == PS_N(iElem)%PartSource(4,i,j,k)
     INTEGER(C_INT)             :: piclas_gpu_get_charge
   END FUNCTION
+  FUNCTION piclas_gpu_get_partsource_async(PartSource) BIND(C,NAME='piclas_gpu_get_partsource_async')
+    IMPORT :: C_INT, C_DOUBLE
+    REAL(C_DOUBLE),INTENT(OUT) :: PartSource(4,*)                ! packed [4,nDOF_local]; valid after piclas_gpu_partsource_wait
+    INTEGER(C_INT)             :: piclas_gpu_get_partsource_async
+  END FUNCTION
+  FUNCTION piclas_gpu_partsource_wait() BIND(C,NAME='piclas_gpu_partsource_wait')
+    IMPORT :: C_INT
+    INTEGER(C_INT)             :: piclas_gpu_partsource_wait
+  END FUNCTION
   FUNCTION piclas_gpu_kinetic_energy(Ekin,nPart) BIND(C,NAME='piclas_gpu_kinetic_energy')
     IMPORT :: C_INT, C_DOUBLE, C_INT64_T
     REAL(C_DOUBLE),INTENT(OUT)     :: Ekin(*)                    ! [nSpecies] -> CalcKineticEnergy
@@ -202,7 +211,7 @@ PUBLIC :: piclas_gpu_push_track, piclas_gpu_num_particles, piclas_gpu_download_p
 PUBLIC :: piclas_gpu_exchange_info, piclas_gpu_exchange_recv_buffer, piclas_gpu_exchange_finish
 PUBLIC :: piclas_gpu_nodesource_device, piclas_gpu_sf_halo_info, piclas_gpu_deposit_finish, piclas_gpu_phase_timing
 PUBLIC :: piclas_gpu_last_timing, piclas_gpu_node_halo_info, piclas_gpu_set_stream, piclas_gpu_exchange_device_info
-PUBLIC :: piclas_gpu_emit_lattice
+PUBLIC :: piclas_gpu_emit_lattice, piclas_gpu_get_partsource_async, piclas_gpu_partsource_wait
 PUBLIC :: ParticleStepGPU, GPUAbortOnError
 
 CONTAINS

@@ -71,6 +71,13 @@ class ParticleStep {
       throw Abort("piclas_gpu_download_particles");
     return nOut;
   }
+  // PartSource to the host beside the rest of the step (the HDG source needs the charge only); complete after PartSourceWait()
+  void PartSourceAsync(double* PartSourcePinned) {
+    if (piclas_gpu_get_partsource_async(PartSourcePinned)) throw Abort("piclas_gpu_get_partsource_async");
+  }
+  void PartSourceWait() {
+    if (piclas_gpu_partsource_wait()) throw Abort("piclas_gpu_partsource_wait");
+  }
   // CalcKineticEnergy / CalcNumPartsOfSpec (particle_analyze_tools.f90:709-842)
   void KineticEnergy(double* Ekin, int64_t* nPart) {
     if (piclas_gpu_kinetic_energy(Ekin, nPart)) throw Abort("piclas_gpu_kinetic_energy");

@@ -17,6 +17,7 @@ EXPORTS = [
     "piclas_gpu_exchange_finish", "piclas_gpu_nodesource_device", "piclas_gpu_deposit_finish",
     "piclas_gpu_last_timing", "piclas_gpu_phase_timing", "piclas_gpu_sf_halo_info", "piclas_gpu_get_charge", "piclas_gpu_kinetic_energy",
     "piclas_gpu_node_halo_info", "piclas_gpu_set_stream", "piclas_gpu_exchange_device_info", "piclas_gpu_emit_lattice",
+    "piclas_gpu_get_partsource_async", "piclas_gpu_partsource_wait",
 ]
 
 _lib = None
@@ -50,6 +51,8 @@ def load() -> C.CDLL:
     lib.piclas_gpu_kinetic_energy.argtypes = [c_f64p, c_i64p]
     lib.piclas_gpu_node_halo_info.argtypes = [c_i64p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.piclas_gpu_set_stream.argtypes = [C.c_void_p]
+    lib.piclas_gpu_get_partsource_async.argtypes = [c_f64p]
+    lib.piclas_gpu_partsource_wait.argtypes = []
     lib.piclas_gpu_emit_lattice.argtypes = [C.c_int32, C.c_int32, c_i32p, C.c_double, C.c_double, c_f64p, C.c_int32, c_i64p]
     lib.piclas_gpu_exchange_device_info.argtypes = [C.POINTER(C.c_void_p), c_i64p, c_i64p]
     lib.piclas_gpu_sf_halo_info.argtypes = [c_i64p, c_i64p, c_i32p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]

@@ -131,6 +131,16 @@ class ParticleStep:
         self._check(self.lib.piclas_gpu_get_charge(_f(rho)))
         return rho
 
+    def PartSourceAsync(self, out):
+        """Starts the device -> host copy of PS_N%PartSource of the last Deposition into `out` (page-locked memory) beside the calls
+        that follow; `out` is complete after PartSourceWait()."""
+        if out.shape != self._ps_shape or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise PiclasGpuError(f"PartSourceAsync: expected a C-contiguous float64 array of shape {self._ps_shape}")
+        self._check(self.lib.piclas_gpu_get_partsource_async(_f(out)))
+
+    def PartSourceWait(self):
+        self._check(self.lib.piclas_gpu_partsource_wait())
+
     def KineticEnergy(self):
         """CalcKineticEnergy / CalcNumPartsOfSpec (particle_analyze_tools.f90:709-842) on the device: (Ekin[nSpecies] in J,
         nPart[nSpecies])."""

@@ -391,3 +391,34 @@ def test_full_regions_are_diverted_and_replanned(monkeypatch, rebin_min):
     elem = hm.cartesian_locate(mesh, PS[:, :3])
     w = run_parity(mesh, prm, PS, spec, elem, E, dt, nsteps=6)
     print("worst rel diffs", w)
+
+
+def test_partsource_async_copy_equals_the_blocking_one():
+    """piclas_gpu_get_partsource_async: the copy on its own stream delivers the PartSource of the deposition it was started after,
+    also when push, tracking and the next deposition are queued behind it before the host waits."""
+    import torch
+    from piclas_b200.particle_step import ParticleStep
+    mesh = hm.box_mesh([0, 0, 0], [1, 1, 1], (6, 6, 6), 3)
+    prm = cases.electron_params(arithmetic=1)
+    dt = 1e-8
+    PS, spec = cases.uniform_plasma(mesh, 60000, seed=77, vth_cells=0.3, dt=dt)
+    elem = hm.cartesian_locate(mesh, PS[:, :3])
+    E = cases.smooth_field(mesh, amp=1e-4)
+    with ParticleStep(mesh, prm) as gpu:
+        gpu.UploadParticles(PS, spec, elem)
+        gpu.SetField(E)
+        src0, _ = gpu.Deposition()
+        pinned = torch.empty(src0.shape, dtype=torch.float64).pin_memory()
+        out = pinned.numpy()
+        out[...] = -1.0
+        gpu.PartSourceAsync(out)
+        gpu.PushAndTrack(dt)
+        src1, _ = gpu.Deposition()          # waits on the device for the copy before it overwrites the array
+        gpu.PartSourceWait()
+        assert np.array_equal(out, src0)
+        assert not np.array_equal(src1, src0)
+        gpu.PartSourceAsync(out)
+        gpu.PartSourceWait()
+        assert np.array_equal(out, src1)
+        rho = gpu.ChargeDensity()
+        assert np.array_equal(rho, src1[..., 3])
