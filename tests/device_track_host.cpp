@@ -50,22 +50,16 @@ static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p;
 static inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 static inline int max(int a, int b) { return a > b ? a : b; }   // CUDA's integer overloads
 static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int __double2hiint(double d) { long long v; std::memcpy(&v, &d, 8); return (int)(v >> 32); }
 #include "kernels.cuh"
 #include "ref.cuh"
+#include "hint.cuh"
 
-extern "C" {
-// Tria records from the host tables, as piclas_gpu_init builds them (piclas_gpu.cu, "per-element records"), then for every
-// particle: inside test of the own element at the pushed position, walk while tria_hop asks for another crossing.
-// x: pushed positions (in/out: periodic shifts, reflections), lp: LastPartPos (in/out), v (in/out: reflections), elem (in/out,
-// 1-based; 0 = removed), status out (TRK_*).  Returns the largest number of crossings one particle needed, -1 on bad tables.
-// fast != 0: the restructured arithmetic (params.arithmetic = 1) - inside test through the triangle planes with the exact
-// fallback, exit-side shortcut on planar convex elements - on PlaneElem records built as piclas_gpu_init builds them (that
-// builder is host code inside piclas_gpu_init and is restated here; the device functions under test are the originals).
-int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* ElemInfo, const int32_t* SideInfo, const double* NodeCoords,
-                  const int32_t* ElemSideNodeID, const int32_t* ConcaveElemSide, int nBCs, const int32_t* bc_kind,
-                  const int32_t* bc_alpha, int nPV, const double* PeriodicVectors, int64_t n, double* x, double* lp, double* v,
-                  int32_t* elem, int32_t* status, int fast) {
-  std::vector<TriaElem> tria((size_t)nG);
+static int dt_build_tables(int nG, int elemInfoSize, int sideInfoSize, const int32_t* ElemInfo, const int32_t* SideInfo, const double* NodeCoords,
+                           const int32_t* ElemSideNodeID, const int32_t* ConcaveElemSide, int nBCs, const int32_t* bc_kind,
+                           const int32_t* bc_alpha, int nPV, const double* PeriodicVectors, int fast, std::vector<TriaElem>& tria,
+                           std::vector<PlaneElem>& planes) {
+  tria.assign((size_t)nG, TriaElem());
   for (int e = 0; e < nG; ++e) {
     const int32_t* ei = ElemInfo + (size_t)e * elemInfoSize;
     const int firstSide = ei[2], firstNode = ei[4];                      // ELEM_FIRSTSIDEIND, ELEM_FIRSTNODEIND
@@ -88,7 +82,7 @@ int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* Ele
   for (int b = 0; b < nBCs; ++b) { cst.bc_kind[b] = bc_kind[b]; cst.bc_alpha[b] = bc_alpha[b]; }
   cst.nPeriodicVectors = nPV;
   for (int p = 0; p < nPV; ++p) for (int d = 0; d < 3; ++d) cst.PeriodicVectors[p][d] = PeriodicVectors[3 * p + d];
-  std::vector<PlaneElem> planes(fast ? (size_t)nG : 0);
+  planes.assign(fast ? (size_t)nG : 0, PlaneElem());
   for (int e = 0; fast && e < nG; ++e) {
     const TriaElem& t = tria[e];
     PlaneElem& pl = planes[e];
@@ -133,6 +127,24 @@ int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* Ele
     }
     pl.planar = planar ? 1u : 0u;
   }
+  return 0;
+}
+extern "C" {
+// Tria records from the host tables, as piclas_gpu_init builds them (piclas_gpu.cu, "per-element records"), then for every
+// particle: inside test of the own element at the pushed position, walk while tria_hop asks for another crossing.
+// x: pushed positions (in/out: periodic shifts, reflections), lp: LastPartPos (in/out), v (in/out: reflections), elem (in/out,
+// 1-based; 0 = removed), status out (TRK_*).  Returns the largest number of crossings one particle needed, -1 on bad tables.
+// fast != 0: the restructured arithmetic (params.arithmetic = 1) - inside test through the triangle planes with the exact
+// fallback, exit-side shortcut on planar convex elements - on PlaneElem records built as piclas_gpu_init builds them (that
+// builder is host code inside piclas_gpu_init and is restated here; the device functions under test are the originals).
+int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* ElemInfo, const int32_t* SideInfo, const double* NodeCoords,
+                  const int32_t* ElemSideNodeID, const int32_t* ConcaveElemSide, int nBCs, const int32_t* bc_kind,
+                  const int32_t* bc_alpha, int nPV, const double* PeriodicVectors, int64_t n, double* x, double* lp, double* v,
+                  int32_t* elem, int32_t* status, int fast) {
+  std::vector<TriaElem> tria;
+  std::vector<PlaneElem> planes;
+  if (dt_build_tables(nG, elemInfoSize, sideInfoSize, ElemInfo, SideInfo, NodeCoords, ElemSideNodeID, ConcaveElemSide, nBCs, bc_kind, bc_alpha, nPV,
+                      PeriodicVectors, fast, tria, planes)) return -1;
   int maxHops = 0;
   for (int64_t i = 0; i < n; ++i) {
     double* xi = x + 3 * i; double* li = lp + 3 * i; double* vi = v + 3 * i;
@@ -165,6 +177,70 @@ int dt_tria_track(int nG, int elemInfoSize, int sideInfoSize, const int32_t* Ele
     elem[i] = (st == TRK_OK) ? ElemID : 0;
   }
   return maxHops;
+}
+// k_far_hint's per-record decision (far_hint_record of csrc/hint.cuh) on the host.  PushElem / HintNb are filled as build_push_elems
+// (csrc/bins_host.inc) fills the fields the hint reads; that builder is host code inside the library and is restated here, the device
+// function under test is the original.  For every flight lp -> x starting in elem: fin[i] = element the hint settles the particle
+// in (0: left to the exact walk), x (and lp) displaced by the periodic vectors crossed.  Returns the number of settled records.
+int64_t dt_tria_hint(int nG, int elemInfoSize, int sideInfoSize, const int32_t* ElemInfo, const int32_t* SideInfo, const double* NodeCoords,
+                     const int32_t* ElemSideNodeID, const int32_t* ConcaveElemSide, int nBCs, const int32_t* bc_kind,
+                     const int32_t* bc_alpha, int nPV, const double* PeriodicVectors, int64_t n, double* x, double* lp,
+                     const int32_t* elem, int32_t* fin) {
+  std::vector<TriaElem> tria;
+  std::vector<PlaneElem> planes;
+  if (dt_build_tables(nG, elemInfoSize, sideInfoSize, ElemInfo, SideInfo, NodeCoords, ElemSideNodeID, ConcaveElemSide, nBCs, bc_kind, bc_alpha, nPV,
+                      PeriodicVectors, 1, tria, planes)) return -1;
+  auto shift_code = [&](const TriaElem& t, int s, uint32_t& code) {
+    code = 0;
+    if (t.nbElem[s] < 1) return false;
+    if (t.bcid[s] == 0) return true;
+    if (bc_kind[t.bcid[s] - 1] != PGPU_BC_PERIODIC) return false;
+    const int pvid = bc_alpha[t.bcid[s] - 1];
+    const int pv = pvid < 0 ? -pvid : pvid;
+    if (pv < 1 || pv > nPV) return false;
+    code = (uint32_t)pv | (pvid < 0 ? 16u : 0u);
+    return true;
+  };
+  std::vector<PushElem> pe((size_t)nG);
+  std::vector<HintNb> hn((size_t)nG);
+  std::memset(pe.data(), 0, pe.size() * sizeof(PushElem));
+  std::memset(hn.data(), 0, hn.size() * sizeof(HintNb));
+  for (int e = 0; e < nG; ++e) {
+    const PlaneElem& pl = planes[e];
+    const TriaElem& t = tria[e];
+    PushElem& P = pe[e];
+    P.planar = pl.planar;
+    P.tol = pl.tol;
+    for (int s = 0; s < 6; ++s)
+      for (int c = 0; c < 4; ++c) { P.pl[s][c] = pl.pl[2 * s][c]; P.dg[s][c] = pl.dg[s][c]; }
+    if (!pl.planar) continue;
+    for (int s = 0; s < 6; ++s) {
+      uint32_t c1 = 0;
+      if (!shift_code(t, s, c1) || !planes[t.nbElem[s] - 1].planar) continue;
+      const int nb = t.nbElem[s];
+      P.nbValid |= 1u << s;
+      P.nbtol[s] = planes[nb - 1].tol;
+      for (int o = 0; o < 6; ++o)
+        for (int c = 0; c < 4; ++c) P.nbpl[s][o][c] = planes[nb - 1].pl[2 * o][c];
+      hn[e].nb[s] = nb;
+      hn[e].sh1 |= c1 << (5 * s);
+      const TriaElem& t1 = tria[nb - 1];
+      for (int o = 0; o < 6; ++o) {
+        uint32_t c2 = 0;
+        if (!shift_code(t1, o, c2) || !planes[t1.nbElem[o] - 1].planar) continue;
+        hn[e].nbnb[s][o] = t1.nbElem[o];
+        hn[e].sh2[s] |= c2 << (5 * o);
+      }
+    }
+  }
+  int64_t settled = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int ge = elem[i];
+    bool moved = false;
+    fin[i] = pe[ge - 1].planar ? far_hint_record<false>(pe[ge - 1], hn[ge - 1], tria.data(), planes.data(), ge, x + 3 * i, lp + 3 * i, moved) : 0;
+    if (fin[i] > 0) ++settled;
+  }
+  return settled;
 }
 // ParticleRefTracking of the device (ref_tracking of csrc/ref.cuh: Newton in the old element, BC-side intersections, periodic shift
 // and reflection, FIBGM relocation incl. the repeated-selection path, LocateParticleInElement fallback) for n particles on the host.

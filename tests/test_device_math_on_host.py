@@ -280,3 +280,70 @@ def test_device_cvwm_particle_deposit_matches_the_oracle(devtrack, tag):
     q = prm.ChargeIC[0] * prm.MacroParticleFactor[0]
     assert abs(NS[:, 3].sum() - n * q) <= 1e-12 * abs(n * q)          # the weights of every particle sum to one
     orc.close()
+
+
+def _hint_vs_exact(devtrack, mesh, x, lp, elem):
+    """far_hint_record (csrc/hint.cuh) and the device's exact walk (reference order), both on the host, for the flights lp -> x."""
+    n = len(x)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    EI, SI, NC = i32(mesh.ElemInfo), i32(mesh.SideInfo), np.ascontiguousarray(mesh.NodeCoords)
+    ESN, CC, bk, ba = i32(mesh.ElemSideNodeID), i32(mesh.ConcaveElemSide), i32(mesh.bc_kind), i32(mesh.bc_alpha)
+    PV = np.ascontiguousarray(mesh.PeriodicVectors if mesh.nPeriodicVectors else np.zeros((1, 3)))
+    args = (mesh.nElems, EI.shape[1], SI.shape[1], _p(EI, I32P), _p(SI, I32P), _p(NC), _p(ESN, I32P), _p(CC, I32P), mesh.nBCs,
+            _p(bk, I32P), _p(ba, I32P), mesh.nPeriodicVectors, _p(PV), C.c_int64(n))
+    xe, lpe, ve, ele, st = x.copy(), lp.copy(), np.zeros_like(x), i32(elem).copy(), np.zeros(n, dtype=np.int32)
+    hops = devtrack.dt_tria_track(*args, _p(xe), _p(lpe), _p(ve), _p(ele, I32P), _p(st, I32P), C.c_int(0))
+    assert hops >= 0
+    xh, lph, fin = x.copy(), lp.copy(), np.zeros(n, dtype=np.int32)
+    devtrack.dt_tria_hint.restype = C.c_int64
+    settled = devtrack.dt_tria_hint(*args, _p(xh), _p(lph), _p(i32(elem), I32P), _p(fin, I32P))
+    assert settled == int((fin > 0).sum())
+    s = fin > 0
+    assert not (st[s] != 0).any(), "the hint settled a particle the exact walk removes or loses"
+    assert np.array_equal(fin[s], ele[s]), "the hint's element differs from the exact walk's"
+    L = np.abs(mesh.NodeCoords).max()
+    if s.any():
+        assert np.abs(xh[s] - xe[s]).max() <= 1e-12 * L                  # periodic displacement: x + vector vs crossing point + rest
+    return fin, ele, st
+
+
+@pytest.mark.parametrize("tag", ["periodic-box", "open-x", "thin-periodic", "wavy"])
+def test_far_hint_decisions_are_the_exact_walks(devtrack, tag):
+    """k_far_hint's per-record decision, compiled for the host, on flights of up to several elements: whenever it settles a
+    record, the element (and the periodically displaced position) is what SingleParticleTriaTracking3D finds; what it cannot
+    decide with its margins it leaves alone.  Includes flights that graze edges and corners and end points on element faces."""
+    rng = np.random.default_rng(20261018)
+    lo, hi = np.zeros(3), np.ones(3)
+    if tag == "periodic-box":
+        mesh = hm.box_mesh(lo, hi, (6, 5, 4), 1)
+    elif tag == "open-x":
+        mesh = hm.box_mesh(lo, hi, (6, 5, 4), 1, periodic=(False, True, True))
+    elif tag == "thin-periodic":
+        mesh = hm.box_mesh(lo, hi, (8, 1, 2), 1)                           # an element is its own neighbour in y
+    else:
+        mesh = hm.box_mesh(lo, hi, (5, 4, 4), 1, deform=cases.wavy(0.05, lo, hi))   # non-planar inner sides: nothing to decide
+    ne = np.array(mesh.extra["nelems"])
+    h = 1.0 / ne
+    n = 60000
+    lp = rng.random((n, 3))
+    step = rng.normal(0.0, 0.6, (n, 3)) * h                                # up to three crossings are common
+    # adversarial thirds: start points near element corners (flights through edge / corner regions), end points exactly on faces
+    k = n // 3
+    corner = np.round(lp[:k] / h) * h
+    lp[:k] = np.clip(corner + rng.normal(0.0, 0.02, (k, 3)) * h, 1e-9, 1 - 1e-9)
+    x = lp + step
+    x[k:2 * k, 0] = np.round(x[k:2 * k, 0] / h[0]) * h[0]
+    if tag == "wavy":
+        orc = Oracle(mesh, cases.electron_params())
+        elem = orc.locate(lp)
+        orc.close()
+    else:
+        elem = hm.cartesian_locate(mesh, lp)
+    fin, ele, st = _hint_vs_exact(devtrack, mesh, np.ascontiguousarray(x), np.ascontiguousarray(lp), elem)
+    share = (fin > 0).mean()
+    if tag == "wavy":
+        assert share < 0.2                                                 # planar elements exist only where the deformation vanishes
+    else:
+        assert share > {"periodic-box": 0.5, "open-x": 0.35, "thin-periodic": 0.3}[tag], share   # up to three crossings are decided by the planes
+        left = (fin == 0) & (st == 0)
+        assert left.any()                                                  # ... and the margins did leave records to the exact walk
