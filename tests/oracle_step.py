@@ -59,6 +59,8 @@ class OracleStep:
         if out is not None:
             out[...] = self.src[..., 3]; return out
         return self.src[..., 3].copy()
+    def PartSourceAsync(self, out): out[...] = self.src
+    def PartSourceWait(self): pass
     def PushAndTrack(self, dt, iter=0):
         assert self.E is not None or not self.params.DoInterpolation
         n = len(self.spec); ins = np.ones(n, np.int32)
