@@ -1485,8 +1485,12 @@ static int deposit_sf(double* PartSource) {
     int nt = ((g.ND + 31) / 32) * 32;
     if (nt < 64) nt = 64;
     const int grid = g.nSfTargets < g.nSMs * 16 ? g.nSfTargets : g.nSMs * 16;
-    k_sf_gather<<<grid, nt, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nSfTargets, g.offsetElem, g.sfT, g.dSfFac[0], g.dSfFac[1], g.dSfFac[2],
-                                       g.dSfFac[3], g.dPartSource);
+    if (g.prm.arithmetic != 0 && g.prm.dim_sf == 3)
+      k_sf_gather<true><<<grid, nt, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nSfTargets, g.offsetElem, g.sfT, g.dSfFac[0], g.dSfFac[1], g.dSfFac[2],
+                                               g.dSfFac[3], g.dPartSource);
+    else
+      k_sf_gather<false><<<grid, nt, 0, g.st>>>(g.buf[g.cur], g.dElemOff, g.nSfTargets, g.offsetElem, g.sfT, g.dSfFac[0], g.dSfFac[1], g.dSfFac[2],
+                                                g.dSfFac[3], g.dPartSource);
     ++g.lastLaunches;
   }
   CK(cudaGetLastError());

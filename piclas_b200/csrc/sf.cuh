@@ -188,6 +188,7 @@ __global__ void k_sf_add_halo(double* __restrict__ PartSource, const double* __r
 // PartSource of one target element per CTA; thread t < ND owns DOF t (k fastest)
 // targets 0..nElems-1 are the local elements; further targets are elements of other ranks reached by local particles
 // (the reference's SendBuffer for ShapeMapping, pic_depo_shapefunction_tools.f90:948-964)
+template <bool FUSED>
 __global__ void k_sf_gather(PartBuf pb, const int64_t* __restrict__ elemOff, int nElems, int offsetElem, SFTables T,
                             const double* __restrict__ f0, const double* __restrict__ f1, const double* __restrict__ f2,
                             const double* __restrict__ f3, double* __restrict__ PartSource) {
@@ -197,6 +198,7 @@ __global__ void k_sf_gather(PartBuf pb, const int64_t* __restrict__ elemOff, int
   __shared__ uint32_t sPass[SF_CHUNK / 32];  // staged particles within reach of that box (the others cannot touch any DOF)
   const int NP = cst.N + 1, ND = NP * NP * NP;
   const int t = threadIdx.x;
+  const int alpha = cst.alpha_sf;
   for (int e = blockIdx.x; e < nElems; e += gridDim.x) {
     const int g = T.target[e];
     double xd[3] = {0., 0., 0.};
@@ -245,7 +247,30 @@ __global__ void k_sf_gather(PartBuf pb, const int64_t* __restrict__ elemOff, int
           if ((t & 31) == 0 && i0 + t < SF_CHUNK) sPass[(i0 + t) >> 5] = bal;
         }
         __syncthreads();
-        if (t < ND) {
+        if (FUSED) {
+          // restructured arithmetic, 3-D shape function: fused multiply-adds, exponent unrolled, no per-pair switches
+          // (same polynomial, same particle order; differences O(1e-16) of the element's source)
+          if (t < ND) {
+            for (int w = 0; w < SF_CHUNK / 32; ++w) {
+              uint32_t bits = sPass[w];
+              while (bits) {
+                const int i = w * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const double d0 = sx[i][0] - xd[0], d1 = sx[i][1] - xd[1], d2 = sx[i][2] - xd[2];
+                const double radius2 = fma(d2, d2, fma(d1, d1, d0 * d0));
+                if (radius2 <= r2_sf) {
+                  const double S = fma(-r2_sf_inv, radius2, 1.);
+                  double S1 = S * S;
+                  for (int ex = 3; ex <= alpha; ++ex) S1 = S * S1;
+                  a0 = fma(S1, sf4[i][0], a0);
+                  a1 = fma(S1, sf4[i][1], a1);
+                  a2 = fma(S1, sf4[i][2], a2);
+                  a3 = fma(S1, sf4[i][3], a3);
+                }
+              }
+            }
+          }
+        } else if (t < ND) {
           for (int w = 0; w < SF_CHUNK / 32; ++w) {
             uint32_t bits = sPass[w];
             while (bits) {   // ascending particle order: the sums keep the order of the unfiltered loop
