@@ -34,3 +34,40 @@ def test_emission_fixture_is_what_the_reference_file_holds():
     st = H5File("/root/reference/regressioncheck/NIG_PIC_poisson_plasma_wave/poisson/plasma_wave_restart_State_000.00000000000000000.h5")
     g = np.load(os.path.join(ROOT, "tests", "golden", "emission_sin_deviation_reference.npz"))["PartData"]
     assert np.array_equal(st.read("PartData"), g)
+
+
+def test_cos_distribution_inverts_its_cumulative_distribution():
+    """SetParticlePositionCosDistribution (particle_emission_tools.f90:1299-1371): x solves x + a/w sin(w x) = x_uniform to the
+    1e-12 the reference's Newton loop stops at; y, z are the cell centres of the lattice."""
+    lo, hi = np.array([0.5, -1.0, 2.0]), np.array([6.5, 1.0, 2.5])
+    a, w, n3 = 0.3, 1.5, (37, 3, 2)
+    X = cases.cos_distribution(lo, hi, *n3, a, w)
+    assert X.shape == (37 * 3 * 2, 3)
+    xs = X[::6, 0] - lo[0]
+    xu = (np.arange(1, 38) - 0.5) * (6.0 / 37)
+    assert np.abs(xs + a / w * np.sin(w * xs) - xu).max() <= 1e-12
+    assert np.all(np.diff(xs) > 0)
+    assert np.array_equal(np.unique(X[:, 1]), (lo[1] + np.arange(1, 4) * (2.0 / 3)) - (2.0 / 3) * 0.5)   # left to right, as written there
+    assert np.array_equal(np.unique(X[:, 2]), (lo[2] + np.arange(1, 3) * 0.25) - 0.25 * 0.5)
+
+
+def test_single_point_to_element_restatement_finds_the_containing_element():
+    """The harness restatement of SinglePointToElement (cases.single_point_to_element; FIBGM cell, radius filter, nearest
+    barycentre first) against the brute-force search of the oracle on a deformed mesh: same element for points off the faces,
+    -1 outside the mesh and for elements of other ranks (doHALO = F)."""
+    from oracle_lib import Oracle
+    from piclas_b200 import hostmesh as hm
+    lo, hi = [0, 0, 0], [1, 1, 1]
+    mesh = hm.box_mesh(lo, hi, (5, 4, 3), 2, deform=cases.wavy(0.05, lo, hi))
+    hm.add_fibgm(mesh)
+    orc = Oracle(mesh, cases.electron_params())
+    rng = np.random.default_rng(5)
+    X = rng.random((1500, 3))
+    el = cases.single_point_to_element(mesh, orc, X)
+    brute = orc.locate(X)
+    assert (el > 0).all() and np.array_equal(el, brute)
+    out = cases.single_point_to_element(mesh, orc, X + np.array([2.0, 0.0, 0.0]))
+    assert (out == -1).all()
+    part = cases.single_point_to_element(mesh, orc, X, first=21, last=40)
+    assert np.array_equal(part, np.where((brute >= 21) & (brute <= 40), brute, -1))
+    orc.close()
