@@ -146,3 +146,27 @@ def test_device_emission_reproduces_the_references_restart_file():
     # order and the determinant test (zero is not negative) give it to 18
     orc = Oracle(mesh, prm)
     assert np.array_equal(d["GlobalElemID"], cases.single_point_to_element(mesh, orc, d["PartState"][:, :3]))
+
+
+def test_every_rank_keeps_the_lattice_points_of_its_own_elements():
+    """doHALO = F: each rank calls the emission with the same arguments and accepts the positions inside its own element range
+    (one GPU plays the three ranks in turn, as tests/test_gpu_loopback.py does); the union is the single-rank emission."""
+    from test_gpu_loopback import LoopRank
+    mesh = _mesh(hm.TRIATRACKING, nel=(6, 3, 2))
+    n3, amp, wn = (25, 6, 4), 0.01, 2.0
+    exp = cases.sin_deviation(mesh.xyz_min, mesh.xyz_max, *n3, amp, wn)
+    orc = Oracle(mesh, cases.electron_params())
+    el_o = cases.single_point_to_element(mesh, orc, exp)
+    world, seen = 3, []
+    for r in range(world):
+        R = LoopRank(mesh, cases.electron_params(), r, world)
+        n = R.step.EmitLattice("sin_deviation", 1, n3, Amplitude=amp, WaveNumber=wn)
+        d = R.step.DownloadParticles()
+        R.close()
+        lo, hi = int(R.off[r]) + 1, int(R.off[r + 1])
+        mine = np.nonzero((el_o >= lo) & (el_o <= hi))[0]
+        o = np.argsort(d["ids"])
+        assert n == len(mine) and np.array_equal(d["ids"][o], mine)
+        assert np.array_equal(d["GlobalElemID"][o], el_o[mine])
+        seen.append(d["ids"])
+    assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(len(exp)))
