@@ -23,7 +23,8 @@ struct EmitSpec {
 // SinglePointToElement (particle_localization.f90:81-190) for TriaTracking (ParticleInsideQuad3D) and RefMapping
 // (MAXVAL(ABS(xi)) <= ElemEpsOneCell; doEmission_opt is absent at the call of the emission).  doHALO = F: elements of other ranks
 // are passed over.  Returns the global element id or -1.
-template <bool REF>
+// G: element tables in global memory (device) / plain host arrays (tests/device_track_host.cpp).
+template <bool REF, bool G = true>
 __device__ int single_point_to_element(const RefTables& T, const TriaElem* __restrict__ tria, const double x[3], int firstLocal, int lastLocal) {
   int Cell[3];
 #pragma unroll
@@ -50,23 +51,17 @@ __device__ int single_point_to_element(const RefTables& T, const TriaElem* __res
       in = (rc & 1) != 0 && maxabs3(xi) <= T.ElemEpsOneCell[e - 1];
     } else {
       uint32_t mask;
-      in = inside_quad3d_mask<true>(tria + (e - 1), x, mask);
+      in = inside_quad3d_mask<G>(tria + (e - 1), x, mask);
     }
     if (in) return e;
   }
   return -1;
 }
 
-template <bool REF>
-__global__ void k_emit_lattice(RefTables T, const TriaElem* __restrict__ tria, EmitSpec s, int64_t t0, int64_t m, double* __restrict__ ps,
-                               int32_t* __restrict__ spec, int32_t* __restrict__ elem, int32_t* __restrict__ inside, int32_t* __restrict__ isnew,
-                               int64_t* __restrict__ ids, unsigned long long* __restrict__ nAccepted) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  const int64_t t = t0 + i;   // position in the reference's loop nest: i outermost, k innermost
+// position number t of the reference's loop nest (i outermost, k innermost), expressions in the order they are written there
+__device__ __forceinline__ void emit_lattice_position(const EmitSpec& s, int64_t t, double x[3]) {
   const int kz = (int)(t % s.nz) + 1, jy = (int)((t / s.nz) % s.ny) + 1, ix = (int)(t / ((int64_t)s.nz * s.ny)) + 1;
   const double x_step = s.len[0] / (double)s.nx, y_step = s.len[1] / (double)s.ny, z_step = s.len[2] / (double)s.nz;
-  double x[3];
   if (s.kind == EMIT_SIN_DEVIATION) {
     const double pilen = 2.0 * 3.141592653589793238 / s.len[0];
     const double x_pos = ((double)ix * x_step - x_step * 0.5);
@@ -83,6 +78,17 @@ __global__ void k_emit_lattice(RefTables T, const TriaElem* __restrict__ tria, E
   }
   x[1] = (s.lo[1] + (double)jy * y_step) - y_step * 0.5;
   x[2] = (s.lo[2] + (double)kz * z_step) - z_step * 0.5;
+}
+
+template <bool REF>
+__global__ void k_emit_lattice(RefTables T, const TriaElem* __restrict__ tria, EmitSpec s, int64_t t0, int64_t m, double* __restrict__ ps,
+                               int32_t* __restrict__ spec, int32_t* __restrict__ elem, int32_t* __restrict__ inside, int32_t* __restrict__ isnew,
+                               int64_t* __restrict__ ids, unsigned long long* __restrict__ nAccepted) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int64_t t = t0 + i;
+  double x[3];
+  emit_lattice_position(s, t, x);
   const int e = single_point_to_element<REF>(T, tria, x, s.firstLocal, s.lastLocal);
 #pragma unroll
   for (int d = 0; d < 3; ++d) {

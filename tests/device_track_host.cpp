@@ -54,6 +54,7 @@ static inline int __double2hiint(double d) { long long v; std::memcpy(&v, &d, 8)
 #include "kernels.cuh"
 #include "ref.cuh"
 #include "hint.cuh"
+#include "emit.cuh"
 
 static int dt_build_tables(int nG, int elemInfoSize, int sideInfoSize, const int32_t* ElemInfo, const int32_t* SideInfo, const double* NodeCoords,
                            const int32_t* ElemSideNodeID, const int32_t* ConcaveElemSide, int nBCs, const int32_t* bc_kind,
@@ -241,6 +242,50 @@ int64_t dt_tria_hint(int nG, int elemInfoSize, int sideInfoSize, const int32_t* 
     if (fin[i] > 0) ++settled;
   }
   return settled;
+}
+// The emission of csrc/emit.cuh on the host: emit_lattice_position for every lattice point and single_point_to_element (TriaTracking:
+// ParticleInsideQuad3D; RefMapping: Newton + ElemEpsOneCell) among the elements first..last.  X [n][3], elem [n] (-1: not accepted).
+int dt_emit_lattice(const pgpu_mesh_t* m, const pgpu_params_t* p, int kind, int nx, int ny, int nz, double amplitude, double wavenumber,
+                    int first, int last, double* X, int32_t* elem) {
+  const int nG = m->nGlobalElems;
+  std::vector<TriaElem> tria;
+  std::vector<PlaneElem> planes;
+  if (dt_build_tables(nG, m->elemInfoSize, m->sideInfoSize, m->ElemInfo, m->SideInfo, m->NodeCoords, m->ElemSideNodeID, m->ConcaveElemSide, m->nBCs,
+                      m->bc_kind, m->bc_alpha, m->nPeriodicVectors, m->PeriodicVectors, 0, tria, planes)) return -1;
+  std::vector<GeoElem> geo((size_t)nG);
+  for (int e = 0; e < nG; ++e) {
+    GeoElem& ge = geo[e];
+    std::memset(&ge, 0, sizeof ge);
+    std::memcpy(ge.XCL, m->XCL_NGeo + (size_t)e * 24, 24 * 8);
+    std::memcpy(ge.dXCL, m->dXCL_NGeo + (size_t)e * 72, 72 * 8);
+    std::memcpy(ge.bary, m->ElemBaryNGeo + (size_t)e * 3, 3 * 8);
+    std::memcpy(ge.xez, m->XiEtaZetaBasis + (size_t)e * 18, 18 * 8);
+    std::memcpy(ge.slen, m->slenXiEtaZetaBasis + (size_t)e * 6, 6 * 8);
+  }
+  for (int i = 0; i < 2; ++i) { cst.XiCL[i] = m->XiCL_NGeo[i]; cst.wBaryCL[i] = m->wBaryCL_NGeo[i]; }
+  cst.RefMappingEps = p->RefMappingEps;
+  cst.RefMappingGuess = p->RefMappingGuess;
+  for (int d = 0; d < 3; ++d) {
+    cst.FIBGMdeltas[d] = m->FIBGMdeltas[d]; cst.xyzminglob[d] = m->xyzminglob[d];
+    cst.FIBGMmin[d] = m->FIBGMmin[d]; cst.FIBGMmax[d] = m->FIBGMmax[d];
+  }
+  RefTables T;
+  std::memset(&T, 0, sizeof T);
+  T.geo = geo.data(); T.ElemBary = m->ElemBaryNGeo; T.ElemRadius2 = m->ElemRadius2NGeo; T.ElemEpsOneCell = m->ElemEpsOneCell;
+  T.FIBGM_nElems = m->FIBGM_nElems; T.FIBGM_offsetElem = m->FIBGM_offsetElem; T.FIBGM_Element = m->FIBGM_Element;
+  EmitSpec s;
+  std::memset(&s, 0, sizeof s);
+  s.kind = kind; s.nx = nx; s.ny = ny; s.nz = nz; s.amplitude = amplitude; s.wavenumber = wavenumber;
+  for (int d = 0; d < 3; ++d) { s.lo[d] = m->xyzminglob[d]; s.len[d] = std::fabs(m->xyzmaxglob[d] - m->xyzminglob[d]); }
+  s.species = 1; s.firstLocal = first; s.lastLocal = last;
+  const bool ref = p->TrackingMethod == 1;   // REFMAPPING (piclas.h:357)
+  const int64_t n = (int64_t)nx * ny * nz;
+  for (int64_t t = 0; t < n; ++t) {
+    emit_lattice_position(s, t, X + 3 * t);
+    elem[t] = ref ? single_point_to_element<true, false>(T, tria.data(), X + 3 * t, first, last)
+                  : single_point_to_element<false, false>(T, tria.data(), X + 3 * t, first, last);
+  }
+  return 0;
 }
 // ParticleRefTracking of the device (ref_tracking of csrc/ref.cuh: Newton in the old element, BC-side intersections, periodic shift
 // and reflection, FIBGM relocation incl. the repeated-selection path, LocateParticleInElement fallback) for n particles on the host.

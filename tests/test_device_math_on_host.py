@@ -347,3 +347,37 @@ def test_far_hint_decisions_are_the_exact_walks(devtrack, tag):
         assert share > {"periodic-box": 0.5, "open-x": 0.35, "thin-periodic": 0.3}[tag], share   # up to three crossings are decided by the planes
         left = (fin == 0) & (st == 0)
         assert left.any()                                                  # ... and the margins did leave records to the exact walk
+
+
+@pytest.mark.parametrize("tracking", ["triatracking", "refmapping"])
+@pytest.mark.parametrize("kind", ["sin_deviation", "cos_distribution"])
+def test_device_emission_on_the_host(devtrack, tracking, kind):
+    """csrc/emit.cuh compiled for the host: the lattice positions are bitwise the harness restatements' (the sin_deviation one is
+    pinned on the reference's restart file, tests/test_reference_emission.py) and single_point_to_element finds the element
+    SinglePointToElement does (FIBGM cell, radius filter, nearest barycentre first; lattice points on faces included), for the
+    whole mesh and for the element range of one rank."""
+    from piclas_b200.abi import Marshalled, DEPO_SF
+    lo, hi = [0.0, 0.0, 0.0], [6.2831, 0.9, 0.4]
+    ref = tracking == "refmapping"
+    mesh = hm.box_mesh(lo, hi, (6, 3, 2), 2, tracking=hm.REFMAPPING if ref else hm.TRIATRACKING,
+                       deform=cases.wavy(0.04, lo, hi) if ref else None)
+    hm.add_fibgm(mesh)
+    if ref:
+        hm.add_refmapping_tables(mesh)
+        prm = cases.electron_params(TrackingMethod=hm.REFMAPPING, DepositionType=DEPO_SF, DoDeposition=0)
+    else:
+        prm = cases.electron_params()
+    n3, amp, wn = ((25, 6, 4), 0.01, 2.0) if kind == "sin_deviation" else ((40, 3, 3), 0.05, 0.5)
+    want = (cases.sin_deviation if kind == "sin_deviation" else cases.cos_distribution)(mesh.xyz_min, mesh.xyz_max, *n3, amp, wn)
+    mar = Marshalled(mesh, prm)
+    orc = Oracle(mesh, prm)
+    n = len(want)
+    for first, last in ((1, mesh.nElems), (13, 24)):
+        X, el = np.zeros((n, 3)), np.zeros(n, dtype=np.int32)
+        rc = devtrack.dt_emit_lattice(C.byref(mar.mesh), C.byref(mar.params), 1 if kind == "sin_deviation" else 2, *n3, C.c_double(amp),
+                                      C.c_double(wn), first, last, _p(X), _p(el, I32P))
+        assert rc == 0
+        assert np.array_equal(X, want)
+        assert np.array_equal(el, cases.single_point_to_element(mesh, orc, want, first=first, last=last, refmapping=ref))
+        assert (el > 0).sum() >= n // 4
+    orc.close()
